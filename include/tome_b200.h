@@ -1,0 +1,160 @@
+/*
+ * tome_b200.h -- C ABI of the B200 (sm_100a) token-merging hot path.
+ *
+ * Drop-in boundary for the per-block ToMe step of sjpollard/video-how-do-your-tokens-merge:
+ *   tome/merge.py:17-102   bipartite_soft_matching   -> tome_match + tome_select
+ *   tome/merge.py:75-85    merge() closure           -> tome_merge
+ *   tome/merge.py:87-100   unmerge() closure         -> tome_unmerge
+ *   tome/merge.py:215-271  bipartite_soft_matching_drop   -> tome_merge(mode = TOME_MODE_DROP)
+ *   tome/merge.py:274-352  bipartite_soft_matching_hybrid -> tome_merge(hybrid_threshold)
+ *   tome/merge.py:355-369  merge_wavg                -> tome_merge(mode = TOME_MODE_WAVG)
+ *   tome/merge.py:372-384  merge_source              -> tome_merge_source
+ *   tome/merge.py:54-57    random_* modes (torch.rand scores) -> tome_rowmax
+ *
+ * Plain C: raw device pointers, sizes and strides; no torch / C++ types.  The caller owns
+ * every buffer (inputs, outputs, workspace) and keeps it alive until the stream work is
+ * done.  Every call only enqueues work on `stream` (a cudaStream_t passed as void*): no
+ * host synchronisation, no allocation, CUDA-graph capturable.  Returns TOME_OK (0) or a
+ * negative tome_status; tome_last_error() gives a thread-local message.  There is no CPU
+ * fallback: on a device that is not sm_100 every compute entry point fails.
+ */
+#ifndef TOME_B200_H
+#define TOME_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TOME_ABI_VERSION 2
+
+#if defined(__GNUC__)
+#define TOME_API __attribute__((visibility("default")))
+#else
+#define TOME_API
+#endif
+
+typedef enum tome_status {
+  TOME_OK = 0,
+  TOME_ERR_ARG = -1,          /* bad shape / null pointer / inconsistent plan            */
+  TOME_ERR_DTYPE = -2,        /* unsupported element type                                */
+  TOME_ERR_ALIGN = -3,        /* pointer or stride alignment the kernels cannot take     */
+  TOME_ERR_WORKSPACE = -4,    /* workspace too small (see tome_*_workspace_bytes)        */
+  TOME_ERR_CUDA = -5,         /* CUDA runtime / driver error (message has the string)    */
+  TOME_ERR_ARCH = -6,         /* device is not compute capability 10.x                   */
+  TOME_ERR_UNSUPPORTED = -7   /* valid request this build cannot serve                   */
+} tome_status;
+
+typedef enum tome_dtype { TOME_F32 = 0, TOME_BF16 = 1 } tome_dtype;
+
+/* tome_match algorithm.  Both produce the SAME canonical node_max/node_idx bits. */
+typedef enum tome_match_algo {
+  TOME_MATCH_AUTO = 0,
+  TOME_MATCH_EXACT_SIMT = 1,  /* fp64 CUDA-core tiles; any shape                          */
+  TOME_MATCH_TCGEN05 = 2      /* 3xTF32 tcgen05/TMEM pass + exact fp64 candidate refine   */
+} tome_match_algo;
+
+/* tome_merge reduction (merge.py:75 `mode`, plus the fused / drop forms). */
+typedef enum tome_merge_mode {
+  TOME_MODE_WAVG = 0,  /* merge_wavg: sum(x*size)/sum(size), also writes size / log(size) */
+  TOME_MODE_SUM = 1,   /* scatter_reduce 'sum'                                            */
+  TOME_MODE_MEAN = 2,  /* scatter_reduce 'mean', include_self=True                        */
+  TOME_MODE_AMAX = 3,  /* scatter_reduce 'max' / 'amax' (NaN propagating)                 */
+  TOME_MODE_DROP = 4   /* bipartite_soft_matching_drop: src tokens discarded              */
+} tome_merge_mode;
+
+/*
+ * A matching plan: what the reference's merge()/unmerge() closures capture
+ * (merge.py:75: unm_idx, src_idx, dst_idx, r) plus two derived maps the kernels use.
+ * na = ceil(n/2) "A" (even) tokens, nb = floor(n/2) "B" (odd) tokens.  All int32, device.
+ */
+typedef struct tome_plan {
+  int32_t bm;             /* matching batch (clips, or clips*frames)                      */
+  int32_t n;              /* tokens per batch element before the merge                    */
+  int32_t r;              /* EFFECTIVE r = min(r, (n - protected)/2) > 0  (merge.py:44)   */
+  int32_t class_token;    /* merge.py:59-60, 71-73                                        */
+  int32_t distill_token;  /* merge.py:61-62, 82-83                                        */
+  const float* node_max;  /* (bm, na)   best score of each A token          (merge.py:64) */
+  const int32_t* node_idx;/* (bm, na)   B index attaining it, lowest on ties              */
+  int32_t* src_idx;       /* (bm, r)    A tokens merged away, best first    (merge.py:68) */
+  int32_t* unm_idx;       /* (bm, na-r) A tokens kept (rank order; ascending if cls)      */
+  int32_t* dst_idx;       /* (bm, r)    B token each src merges into        (merge.py:69) */
+  int32_t* a_map;         /* (bm, na)   >=0: position in unm_idx; <0: -(dst+1)            */
+  int32_t* b_off;         /* (bm, nb+1) CSR offsets into b_src                            */
+  int32_t* b_src;         /* (bm, r)    A tokens grouped by dst, ascending k inside       */
+} tome_plan;
+
+/* Tensor addressing: element (b, t, c) of a (bm, tokens, c) tensor lives at
+ *   base + (b / inner) * stride_bo + (b % inner) * stride_bi + t * stride_n + c
+ * (strides in ELEMENTS, channel stride 1).  inner = 1 is a plain batched tensor; inner = T
+ * expresses TimeSformer/Motionformer's 'b (p t) m -> (b t) p m' view
+ * (tome/patch/timesformer.py:89-90, motionformer.py:150-151) without a copy. */
+typedef struct tome_view {
+  int64_t stride_bo;
+  int64_t stride_bi;
+  int64_t stride_n;
+  int32_t inner;
+} tome_view;
+
+TOME_API int tome_abi_version(void);
+TOME_API const char* tome_last_error(void);
+
+/* TOME_OK when `device` is compute capability 10.x and the kernels can launch. */
+TOME_API int tome_device_check(int device);
+
+/* --- kernel 1: match (merge.py:49-64) ------------------------------------------------
+ * metric: (bm, n, cm) of `dtype`, addressed by `view`.  Writes node_max (bm, na) fp32 and
+ * node_idx (bm, na) int32.  Canonical arithmetic (DESIGN.md "score definition"):
+ *   norm = fp32(sqrt(sum fp64(x)^2)); mhat = fp32(x / norm);
+ *   score = fp32(sum fp64(mhat_a) * fp64(mhat_b)); class token -> row 0 = -inf;
+ *   distill token -> column 0 = -inf; argmax = lowest column on ties.
+ * The (bm, na, nb) score matrix is never written to memory. */
+TOME_API size_t tome_match_workspace_bytes(int32_t bm, int32_t n, int32_t cm, int32_t algo);
+TOME_API int tome_match(const void* metric, int32_t dtype, int32_t bm, int32_t n, int32_t cm,
+               const tome_view* view, int32_t class_token, int32_t distill_token, int32_t algo,
+               float* node_max, int32_t* node_idx, void* workspace, size_t workspace_bytes,
+               void* stream);
+
+/* Row max/argmax of a MATERIALISED (bm, na, nb) fp32 score tensor, same masking and tie
+ * rule.  Serves the random_merge / random_drop modes, whose scores are torch.rand
+ * (merge.py:54-57, 235-238). */
+TOME_API int tome_rowmax(const float* scores, int32_t bm, int32_t na, int32_t nb, int32_t class_token,
+                int32_t distill_token, float* node_max, int32_t* node_idx, void* stream);
+
+/* --- kernel 2: select (merge.py:65-73) -----------------------------------------------
+ * Stable descending rank of node_max (ties: lower A index first; NaN above +inf), then
+ * src = first r, unm = rest (ascending when class_token), dst = node_idx[src]; also fills
+ * a_map / b_off / b_src.  plan->r must already be the effective r (> 0). */
+TOME_API size_t tome_select_workspace_bytes(int32_t bm, int32_t n);
+TOME_API int tome_select(const tome_plan* plan, void* workspace, size_t workspace_bytes, void* stream);
+
+/* --- kernel 3: merge (merge.py:75-85, 260-269, 316-334, 355-369) ----------------------
+ * x: (bm, n, c) -> out: (bm, n - r, c), same dtype.  Output token order is the
+ * reference's: kept A tokens in unm_idx order, then ALL B tokens in original order
+ * (distill: [unm0, dst0, unm1.., dst1..]).  Per B token the reduction order is the
+ * reference CPU order (itself, then its sources by ascending k), fp32, no FMA
+ * contraction, so fp32 results are bit-identical to the CPU reference.
+ *   size_in : (bm, n) fp32 token sizes or NULL (= ones)          [WAVG only]
+ *   size_out, logsize_out : (bm, n - r) fp32 or NULL             [WAVG, DROP: ones / zeros]
+ *   hybrid_threshold : NaN = off; else merge.py:326 -- a B token hit by any edge with
+ *                      node_max < threshold is zeroed before its sources are added. */
+TOME_API int tome_merge(const tome_plan* plan, const void* x, int32_t dtype, int32_t c,
+               const tome_view* x_view, const float* size_in, int32_t mode,
+               float hybrid_threshold, void* out, const tome_view* out_view, float* size_out,
+               float* logsize_out, void* stream);
+
+/* merge_source (merge.py:372-384): source (bm, n, n0) fp32 0/1 adjacency, 'max' reduce.
+ * source == NULL means the implicit identity (n0 == n), generated on the fly. */
+TOME_API int tome_merge_source(const tome_plan* plan, const float* source, int32_t n0,
+                      float hybrid_threshold, float* out, void* stream);
+
+/* unmerge (merge.py:87-100): x (bm, n - r, c) -> out (bm, n, c); contiguous tensors. */
+TOME_API int tome_unmerge(const tome_plan* plan, const void* x, int32_t dtype, int32_t c, void* out,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOME_B200_H */

@@ -1,0 +1,311 @@
+// Kernel 3: merge.  Replaces the reference's merge()/drop()/unmerge() closures and
+// merge_wavg / merge_source (tome/merge.py:75-100, 260-269, 316-334, 355-384).
+//
+// The reference does, per call: two strided slices, two gathers with stride-0 int64 index
+// tensors, an out-of-place scatter_reduce (clone + atomics) and a cat -- and merge_wavg
+// does all of that twice plus two elementwise passes.  Here every OUTPUT token row is
+// produced by one warp in one pass: it gathers its own row and (for a B token) the rows
+// of the A tokens merged into it through the dst-grouped CSR built by select.cu, reduces
+// in fp32 in the reference CPU order (self, then ascending k; products and sums rounded
+// separately, no FMA contraction), and writes the merged row, its new size and log(size)
+// once.  HBM traffic = read x once + write x' once (kernel 3).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace tome {
+
+struct MergeArgs {
+  int bm, n, r, distill, c, mode, hybrid;
+  float thr;
+  const float* node_max;
+  const int *unm_idx, *b_off, *b_src;
+  const void* x;
+  View xv;
+  const float* size_in;
+  void* out;
+  View ov;
+  float* size_out;
+  float* logsize_out;
+};
+
+// output slot -> (kind, index): merge.py:82-85 ordering
+__device__ __forceinline__ void slot_to_token(int o, int nu, int distill, bool& is_unm, int& idx) {
+  if (!distill) { is_unm = o < nu; idx = is_unm ? o : o - nu; return; }
+  if (o == 0) { is_unm = true; idx = 0; }
+  else if (o == 1) { is_unm = false; idx = 0; }
+  else if (o <= nu) { is_unm = true; idx = o - 1; }
+  else { is_unm = false; idx = o - nu; }
+}
+__device__ __forceinline__ int token_to_slot(bool is_unm, int idx, int nu, int distill) {
+  if (!distill) return is_unm ? idx : nu + idx;
+  if (is_unm) return idx == 0 ? 0 : idx + 1;
+  return idx == 0 ? 1 : nu + idx;
+}
+
+template <typename T, int E> struct Vec;
+template <> struct Vec<float, 4> {
+  static __device__ __forceinline__ void load(const float* p, float (&f)[4]) {
+    const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(p));
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&f)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+template <> struct Vec<float, 1> {
+  static __device__ __forceinline__ void load(const float* p, float (&f)[1]) { f[0] = __ldg(p); }
+  static __device__ __forceinline__ void store(float* p, const float (&f)[1]) { *p = f[0]; }
+};
+template <> struct Vec<__nv_bfloat16, 8> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 v = ld_stream_u4(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <> struct Vec<__nv_bfloat16, 1> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[1]) { f[0] = __bfloat162float(*p); }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[1]) { *p = __float2bfloat16_rn(f[0]); }
+};
+
+__device__ __forceinline__ float nanmax(float a, float b) { return (a != a || a > b) ? a : ((b != b) ? b : (a > b ? a : b)); }
+
+// One warp per output row; NV vectors of E elements per lane per chunk.
+template <typename T, int E, int NV>
+__global__ void __launch_bounds__(256) merge_rows_kernel(MergeArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b = blockIdx.y;
+  const int n = a.n, na = na_of(n), nb = nb_of(n), r = a.r, nu = na - r, nout = n - r;
+  if (o >= nout) return;
+  bool is_unm; int idx;
+  slot_to_token(o, nu, a.distill, is_unm, idx);
+
+  const T* xb = reinterpret_cast<const T*>(a.x) + a.xv.batch_offset(b);
+  T* ob = reinterpret_cast<T*>(a.out) + a.ov.batch_offset(b) + (long long)o * a.ov.sn;
+  const float* szb = a.size_in ? a.size_in + (long long)b * n : nullptr;
+
+  int self_tok, beg = 0, end = 0;
+  if (is_unm) {
+    self_tok = 2 * __ldg(a.unm_idx + (long long)b * nu + idx);
+  } else {
+    self_tok = 2 * idx + 1;
+    if (a.mode != TOME_MODE_DROP) {
+      const int* off = a.b_off + (long long)b * (nb + 1) + idx;
+      beg = __ldg(off); end = __ldg(off + 1);
+    }
+  }
+  const int* bsrc = a.b_src + (long long)b * r;
+  bool keep_self = true;
+  if (a.hybrid) {   // merge.py:326: 'prod' with (node_max_sorted[:r] >= thr) over edges hitting this B token
+    for (int q = beg; q < end; ++q)
+      keep_self &= (__ldg(a.node_max + (long long)b * na + __ldg(bsrc + q)) >= a.thr);
+  }
+  const float s_self = szb ? __ldg(szb + self_tok) : 1.0f;
+  const bool wavg = a.mode == TOME_MODE_WAVG;
+
+  // new size (exact: sizes are small integers in fp32)
+  float S = s_self;
+  if (!is_unm) {
+    if (!keep_self) S = __fmul_rn(S, 0.0f);
+    if (wavg) for (int q = beg; q < end; ++q) S = __fadd_rn(S, szb ? __ldg(szb + 2 * __ldg(bsrc + q)) : 1.0f);
+  }
+  const float cnt = (float)(1 + end - beg);
+
+  const int chunk = 32 * E * NV;
+  for (int cb = 0; cb < a.c; cb += chunk) {
+    float acc[NV][E];
+    const T* row = xb + (long long)self_tok * a.xv.sn + cb;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c0 = (v * 32 + lane) * E;
+      if (cb + c0 < a.c) Vec<T, E>::load(row + c0, acc[v]);
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        float t = acc[v][e];
+        if (wavg) t = __fmul_rn(t, s_self);
+        if (!keep_self) t = __fmul_rn(t, 0.0f);
+        acc[v][e] = t;
+      }
+    for (int q = beg; q < end; ++q) {
+      const int tok = 2 * __ldg(bsrc + q);
+      const float s = (wavg && szb) ? __ldg(szb + tok) : 1.0f;
+      const T* srow = xb + (long long)tok * a.xv.sn + cb;
+      float tmp[NV][E];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c0 = (v * 32 + lane) * E;
+        if (cb + c0 < a.c) Vec<T, E>::load(srow + c0, tmp[v]);
+      }
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if (a.mode == TOME_MODE_AMAX) acc[v][e] = nanmax(acc[v][e], tmp[v][e]);
+          else if (wavg) acc[v][e] = __fadd_rn(acc[v][e], __fmul_rn(tmp[v][e], s));
+          else acc[v][e] = __fadd_rn(acc[v][e], tmp[v][e]);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c0 = (v * 32 + lane) * E;
+      if (cb + c0 < a.c) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if (wavg) acc[v][e] = __fdiv_rn(acc[v][e], S);
+          else if (a.mode == TOME_MODE_MEAN && !is_unm) acc[v][e] = __fdiv_rn(acc[v][e], cnt);
+        }
+        Vec<T, E>::store(ob + cb + c0, acc[v]);
+      }
+    }
+  }
+  if (lane == 0) {
+    const long long so = (long long)b * nout + o;
+    const float So = (a.mode == TOME_MODE_DROP) ? 1.0f : S;
+    if (a.size_out) a.size_out[so] = So;
+    if (a.logsize_out) a.logsize_out[so] = logf(So);
+  }
+}
+
+// merge_source with the implicit identity (merge.py:379-381): row of slot o is the OR of
+// one-hot rows, generated without reading anything but the plan.
+__global__ void __launch_bounds__(256) source_identity_kernel(MergeArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b = blockIdx.y;
+  const int n = a.n, na = na_of(n), nb = nb_of(n), r = a.r, nu = na - r, nout = n - r;
+  if (o >= nout) return;
+  bool is_unm; int idx;
+  slot_to_token(o, nu, a.distill, is_unm, idx);
+  float* orow = reinterpret_cast<float*>(a.out) + ((long long)b * nout + o) * n;
+  int self_tok, beg = 0, end = 0;
+  if (is_unm) self_tok = 2 * __ldg(a.unm_idx + (long long)b * nu + idx);
+  else {
+    self_tok = 2 * idx + 1;
+    const int* off = a.b_off + (long long)b * (nb + 1) + idx;
+    beg = __ldg(off); end = __ldg(off + 1);
+  }
+  const int* bsrc = a.b_src + (long long)b * r;
+  bool keep_self = true;
+  if (a.hybrid)
+    for (int q = beg; q < end; ++q)
+      keep_self &= (__ldg(a.node_max + (long long)b * na + __ldg(bsrc + q)) >= a.thr);
+  for (int c = lane; c < n; c += 32) {
+    float v = (c == self_tok && keep_self) ? 1.0f : 0.0f;
+    for (int q = beg; q < end; ++q) v = (c == 2 * __ldg(bsrc + q)) ? 1.0f : v;
+    orow[c] = v;
+  }
+}
+
+template <typename T, int E>
+__global__ void __launch_bounds__(256) unmerge_rows_kernel(const int* __restrict__ a_map, int n, int r, int distill,
+                                                           int c, const T* __restrict__ x, T* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b = blockIdx.y;
+  if (t >= n) return;
+  const int na = na_of(n), nu = na - r, nout = n - r;
+  int slot;
+  if (t & 1) slot = token_to_slot(false, t >> 1, nu, distill);
+  else {
+    const int m = __ldg(a_map + (long long)b * na + (t >> 1));
+    slot = m >= 0 ? token_to_slot(true, m, nu, distill) : token_to_slot(false, -m - 1, nu, distill);
+  }
+  const T* src = x + ((long long)b * nout + slot) * c;
+  T* dst = out + ((long long)b * n + t) * c;
+  for (int c0 = lane * E; c0 < c; c0 += 32 * E) {
+    float f[E];
+    Vec<T, E>::load(src + c0, f);
+    Vec<T, E>::store(dst + c0, f);
+  }
+}
+
+// ---- host -----------------------------------------------------------------------------------
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+static bool view_vec_ok(const View& v, int e) { return v.sbo % e == 0 && v.sbi % e == 0 && v.sn % e == 0; }
+
+template <typename T, int E>
+static int launch_merge_t(const MergeArgs& a, cudaStream_t st) {
+  const int nout = a.n - a.r;
+  dim3 grid((nout + 7) / 8, a.bm);
+  const int per_nv = 32 * E;
+  const int nv = (a.c + per_nv - 1) / per_nv;
+  if (nv <= 1) merge_rows_kernel<T, E, 1><<<grid, 256, 0, st>>>(a);
+  else if (nv <= 2) merge_rows_kernel<T, E, 2><<<grid, 256, 0, st>>>(a);
+  else if (nv <= 3) merge_rows_kernel<T, E, 3><<<grid, 256, 0, st>>>(a);
+  else if (nv <= 4) merge_rows_kernel<T, E, 4><<<grid, 256, 0, st>>>(a);
+  else if (nv <= 6) merge_rows_kernel<T, E, 6><<<grid, 256, 0, st>>>(a);
+  else merge_rows_kernel<T, E, 8><<<grid, 256, 0, st>>>(a);
+  TOME_LAUNCH_CHECK("merge_rows_kernel");
+  return TOME_OK;
+}
+
+int launch_merge(const tome_plan* plan, const void* x, int dtype, int c, const View& xv, const float* size_in,
+                 int mode, float thr, void* out, const View& ov, float* size_out, float* logsize_out,
+                 cudaStream_t st) {
+  MergeArgs a;
+  a.bm = plan->bm; a.n = plan->n; a.r = plan->r; a.distill = plan->distill_token; a.c = c; a.mode = mode;
+  a.hybrid = (thr == thr) ? 1 : 0; a.thr = thr; a.node_max = plan->node_max;
+  a.unm_idx = plan->unm_idx; a.b_off = plan->b_off; a.b_src = plan->b_src;
+  a.x = x; a.xv = xv; a.size_in = size_in; a.out = out; a.ov = ov; a.size_out = size_out; a.logsize_out = logsize_out;
+  if (dtype == TOME_F32) {
+    const bool vec = c % 4 == 0 && aligned16(x) && aligned16(out) && view_vec_ok(xv, 4) && view_vec_ok(ov, 4);
+    return vec ? launch_merge_t<float, 4>(a, st) : launch_merge_t<float, 1>(a, st);
+  } else if (dtype == TOME_BF16) {
+    const bool vec = c % 8 == 0 && aligned16(x) && aligned16(out) && view_vec_ok(xv, 8) && view_vec_ok(ov, 8);
+    return vec ? launch_merge_t<__nv_bfloat16, 8>(a, st) : launch_merge_t<__nv_bfloat16, 1>(a, st);
+  }
+  return set_error(TOME_ERR_DTYPE, "tome_merge: unsupported dtype %d", dtype);
+}
+
+int launch_merge_source(const tome_plan* plan, const float* source, int n0, float thr, float* out, cudaStream_t st) {
+  const int nout = plan->n - plan->r;
+  if (source) {
+    View xv{(long long)plan->n * n0, 0, n0, 1}, ov{(long long)nout * n0, 0, n0, 1};
+    return launch_merge(plan, source, TOME_F32, n0, xv, nullptr, TOME_MODE_AMAX, thr, out, ov, nullptr, nullptr, st);
+  }
+  MergeArgs a{};
+  a.bm = plan->bm; a.n = plan->n; a.r = plan->r; a.distill = plan->distill_token; a.c = plan->n;
+  a.mode = TOME_MODE_AMAX; a.hybrid = (thr == thr) ? 1 : 0; a.thr = thr; a.node_max = plan->node_max;
+  a.unm_idx = plan->unm_idx; a.b_off = plan->b_off; a.b_src = plan->b_src; a.out = out;
+  dim3 grid((nout + 7) / 8, plan->bm);
+  source_identity_kernel<<<grid, 256, 0, st>>>(a);
+  TOME_LAUNCH_CHECK("source_identity_kernel");
+  return TOME_OK;
+}
+
+int launch_unmerge(const tome_plan* plan, const void* x, int dtype, int c, void* out, cudaStream_t st) {
+  dim3 grid((plan->n + 7) / 8, plan->bm);
+  if (dtype == TOME_F32) {
+    if (c % 4 == 0 && aligned16(x) && aligned16(out))
+      unmerge_rows_kernel<float, 4><<<grid, 256, 0, st>>>(plan->a_map, plan->n, plan->r, plan->distill_token, c, (const float*)x, (float*)out);
+    else
+      unmerge_rows_kernel<float, 1><<<grid, 256, 0, st>>>(plan->a_map, plan->n, plan->r, plan->distill_token, c, (const float*)x, (float*)out);
+  } else if (dtype == TOME_BF16) {
+    if (c % 8 == 0 && aligned16(x) && aligned16(out))
+      unmerge_rows_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>(plan->a_map, plan->n, plan->r, plan->distill_token, c, (const __nv_bfloat16*)x, (__nv_bfloat16*)out);
+    else
+      unmerge_rows_kernel<__nv_bfloat16, 1><<<grid, 256, 0, st>>>(plan->a_map, plan->n, plan->r, plan->distill_token, c, (const __nv_bfloat16*)x, (__nv_bfloat16*)out);
+  } else return set_error(TOME_ERR_DTYPE, "tome_unmerge: unsupported dtype %d", dtype);
+  TOME_LAUNCH_CHECK("unmerge_rows_kernel");
+  return TOME_OK;
+}
+
+}  // namespace tome

@@ -1,0 +1,180 @@
+// extern "C" entry points declared in include/tome_b200.h: argument validation, error
+// strings, dispatch.  No torch types, no allocation, no host synchronisation.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace tome {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int g_dev_ok[64];   // 0 unknown, 1 ok, -1 bad
+static int g_sms[64];
+
+int ensure_device_ok() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return set_error(TOME_ERR_CUDA, "cudaGetDevice failed: %s", cudaGetErrorString(e));
+  if (dev < 0 || dev >= 64) return set_error(TOME_ERR_ARG, "device index %d out of range", dev);
+  if (g_dev_ok[dev] == 0) {
+    int major = 0, sms = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return set_error(TOME_ERR_CUDA, "cudaDeviceGetAttribute failed: %s", cudaGetErrorString(e));
+    g_sms[dev] = sms;
+    g_dev_ok[dev] = (major == 10) ? 1 : -1;
+  }
+  if (g_dev_ok[dev] < 0)
+    return set_error(TOME_ERR_ARCH, "device %d is not compute capability 10.x (this library is sm_100a only, no fallback)", dev);
+  return TOME_OK;
+}
+
+int sm_count() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < 64 && g_sms[dev] > 0) ? g_sms[dev] : 148;
+}
+
+// implemented in the kernel translation units
+size_t match_exact_workspace(int bm, int n, int cm);
+int launch_match_exact(const void*, int, int, int, int, const View&, int, int, float*, int*, void*, size_t, cudaStream_t);
+int launch_rowmax(const float*, int, int, int, int, int, float*, int*, cudaStream_t);
+size_t match_tc_workspace(int bm, int n, int cm);
+bool match_tc_supported(int dtype, int bm, int n, int cm, const View& v, const void* metric);
+int launch_match_tc(const void*, int, int, int, int, const View&, int, int, float*, int*, void*, size_t, cudaStream_t);
+size_t select_workspace(int bm, int n);
+int launch_select(const tome_plan*, void*, size_t, cudaStream_t);
+int launch_merge(const tome_plan*, const void*, int, int, const View&, const float*, int, float, void*, const View&,
+                 float*, float*, cudaStream_t);
+int launch_merge_source(const tome_plan*, const float*, int, float, float*, cudaStream_t);
+int launch_unmerge(const tome_plan*, const void*, int, int, void*, cudaStream_t);
+
+static int check_plan(const tome_plan* p, const char* who) {
+  if (!p) return set_error(TOME_ERR_ARG, "%s: plan is NULL", who);
+  if (p->bm <= 0 || p->n < 2) return set_error(TOME_ERR_ARG, "%s: bad plan shape bm=%d n=%d", who, p->bm, p->n);
+  const int prot = (p->class_token ? 1 : 0) + (p->distill_token ? 1 : 0);
+  if (p->r <= 0 || p->r > (p->n - prot) / 2)
+    return set_error(TOME_ERR_ARG, "%s: plan->r=%d is not an effective r for n=%d (max %d)", who, p->r, p->n, (p->n - prot) / 2);
+  if (!p->node_max || !p->node_idx || !p->src_idx || !p->unm_idx || !p->dst_idx || !p->a_map || !p->b_off || !p->b_src)
+    return set_error(TOME_ERR_ARG, "%s: plan has NULL buffers", who);
+  return TOME_OK;
+}
+
+}  // namespace tome
+
+using namespace tome;
+
+extern "C" {
+
+int tome_abi_version(void) { return TOME_ABI_VERSION; }
+const char* tome_last_error(void) { return g_err; }
+
+int tome_device_check(int device) {
+  int cur = 0;
+  TOME_CUDA(cudaGetDevice(&cur));
+  if (device != cur) TOME_CUDA(cudaSetDevice(device));
+  int rc = ensure_device_ok();
+  if (device != cur) cudaSetDevice(cur);
+  return rc;
+}
+
+size_t tome_match_workspace_bytes(int32_t bm, int32_t n, int32_t cm, int32_t algo) {
+  if (bm <= 0 || n <= 0 || cm <= 0) return 0;
+  size_t e = match_exact_workspace(bm, n, cm), t = match_tc_workspace(bm, n, cm);
+  if (algo == TOME_MATCH_EXACT_SIMT) return e;
+  if (algo == TOME_MATCH_TCGEN05) return t;
+  return e > t ? e : t;
+}
+
+int tome_match(const void* metric, int32_t dtype, int32_t bm, int32_t n, int32_t cm, const tome_view* view,
+               int32_t class_token, int32_t distill_token, int32_t algo, float* node_max, int32_t* node_idx,
+               void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(metric && node_max && node_idx && workspace, "tome_match: NULL pointer argument");
+  TOME_CHECK_ARG(bm > 0 && n >= 2 && cm > 0, "tome_match: bad shape bm=%d n=%d cm=%d", bm, n, cm);
+  if (dtype != TOME_F32 && dtype != TOME_BF16) return set_error(TOME_ERR_DTYPE, "tome_match: unsupported dtype %d", dtype);
+  TOME_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "tome_match: workspace must be 256-byte aligned");
+  const View v = make_view(view, n, cm);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (algo == TOME_MATCH_AUTO)
+    algo = match_tc_supported(dtype, bm, n, cm, v, metric) ? TOME_MATCH_TCGEN05 : TOME_MATCH_EXACT_SIMT;
+  if (algo == TOME_MATCH_TCGEN05) {
+    if (!match_tc_supported(dtype, bm, n, cm, v, metric))
+      return set_error(TOME_ERR_UNSUPPORTED, "tome_match: tcgen05 path needs contiguous fp32/bf16 metric, cm %% 32 == 0, cm <= 1024 (got cm=%d)", cm);
+    return launch_match_tc(metric, dtype, bm, n, cm, v, class_token, distill_token, node_max, node_idx, workspace,
+                           workspace_bytes, st);
+  }
+  if (algo != TOME_MATCH_EXACT_SIMT) return set_error(TOME_ERR_ARG, "tome_match: unknown algo %d", algo);
+  return launch_match_exact(metric, dtype, bm, n, cm, v, class_token, distill_token, node_max, node_idx, workspace,
+                            workspace_bytes, st);
+}
+
+int tome_rowmax(const float* scores, int32_t bm, int32_t na, int32_t nb, int32_t class_token, int32_t distill_token,
+                float* node_max, int32_t* node_idx, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(scores && node_max && node_idx, "tome_rowmax: NULL pointer argument");
+  TOME_CHECK_ARG(bm > 0 && na > 0 && nb > 0, "tome_rowmax: bad shape bm=%d na=%d nb=%d", bm, na, nb);
+  return launch_rowmax(scores, bm, na, nb, class_token, distill_token, node_max, node_idx, (cudaStream_t)stream);
+}
+
+size_t tome_select_workspace_bytes(int32_t bm, int32_t n) { return (bm > 0 && n > 0) ? select_workspace(bm, n) : 0; }
+
+int tome_select(const tome_plan* plan, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  rc = check_plan(plan, "tome_select");
+  if (rc) return rc;
+  TOME_CHECK_ARG(workspace, "tome_select: workspace is NULL");
+  return launch_select(plan, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int tome_merge(const tome_plan* plan, const void* x, int32_t dtype, int32_t c, const tome_view* x_view,
+               const float* size_in, int32_t mode, float hybrid_threshold, void* out, const tome_view* out_view,
+               float* size_out, float* logsize_out, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  rc = check_plan(plan, "tome_merge");
+  if (rc) return rc;
+  TOME_CHECK_ARG(x && out && c > 0, "tome_merge: NULL tensor or c=%d", c);
+  TOME_CHECK_ARG(mode >= TOME_MODE_WAVG && mode <= TOME_MODE_DROP, "tome_merge: unknown mode %d", mode);
+  TOME_CHECK_ARG(mode == TOME_MODE_WAVG || size_in == nullptr, "tome_merge: size_in is only meaningful for TOME_MODE_WAVG");
+  TOME_CHECK_ARG(x != out, "tome_merge: in-place merge is not supported");
+  const View xv = make_view(x_view, plan->n, c), ov = make_view(out_view, plan->n - plan->r, c);
+  return launch_merge(plan, x, dtype, c, xv, size_in, mode, hybrid_threshold, out, ov, size_out, logsize_out,
+                      (cudaStream_t)stream);
+}
+
+int tome_merge_source(const tome_plan* plan, const float* source, int32_t n0, float hybrid_threshold, float* out,
+                      void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  rc = check_plan(plan, "tome_merge_source");
+  if (rc) return rc;
+  TOME_CHECK_ARG(out, "tome_merge_source: out is NULL");
+  TOME_CHECK_ARG(source || n0 == plan->n, "tome_merge_source: implicit identity needs n0 == n (n0=%d n=%d)", n0, plan->n);
+  TOME_CHECK_ARG(n0 > 0, "tome_merge_source: n0=%d", n0);
+  return launch_merge_source(plan, source, n0, hybrid_threshold, out, (cudaStream_t)stream);
+}
+
+int tome_unmerge(const tome_plan* plan, const void* x, int32_t dtype, int32_t c, void* out, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  rc = check_plan(plan, "tome_unmerge");
+  if (rc) return rc;
+  TOME_CHECK_ARG(x && out && c > 0, "tome_unmerge: NULL tensor or c=%d", c);
+  return launch_unmerge(plan, x, dtype, c, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,293 @@
+"""ctypes binding of libtome_b200.so (the C ABI in include/tome_b200.h).
+
+PyTorch is only the plumbing here: it owns device memory and the stream; every kernel on the
+token-merging path is ours.  There is NO CPU fallback and no alternative backend: if the
+library is missing, the device is not sm_100, or a tensor is not on a CUDA device, these
+functions raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+from typing import Optional, Tuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
+ABI_VERSION = 2
+
+TOME_F32, TOME_BF16 = 0, 1
+MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
+MODE_WAVG, MODE_SUM, MODE_MEAN, MODE_AMAX, MODE_DROP = 0, 1, 2, 3, 4
+_MODES = {"wavg": MODE_WAVG, "sum": MODE_SUM, "mean": MODE_MEAN, "max": MODE_AMAX, "amax": MODE_AMAX,
+          "drop": MODE_DROP}
+
+EXPORTS = (
+    "tome_abi_version", "tome_last_error", "tome_device_check", "tome_match_workspace_bytes", "tome_match",
+    "tome_rowmax", "tome_select_workspace_bytes", "tome_select", "tome_merge", "tome_merge_source", "tome_unmerge",
+)
+
+
+class TomePlanC(ctypes.Structure):
+    _fields_ = [
+        ("bm", ctypes.c_int32), ("n", ctypes.c_int32), ("r", ctypes.c_int32),
+        ("class_token", ctypes.c_int32), ("distill_token", ctypes.c_int32),
+        ("node_max", ctypes.c_void_p), ("node_idx", ctypes.c_void_p),
+        ("src_idx", ctypes.c_void_p), ("unm_idx", ctypes.c_void_p), ("dst_idx", ctypes.c_void_p),
+        ("a_map", ctypes.c_void_p), ("b_off", ctypes.c_void_p), ("b_src", ctypes.c_void_p),
+    ]
+
+
+class TomeViewC(ctypes.Structure):
+    _fields_ = [("stride_bo", ctypes.c_int64), ("stride_bi", ctypes.c_int64), ("stride_n", ctypes.c_int64),
+                ("inner", ctypes.c_int32)]
+
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None) -> ctypes.CDLL:
+    """Load (once) and type the shared library.  Raises if it is absent: build it with
+    ``python video-how-do-your-tokens-merge_b200/build.py`` or ``__graft_entry__.build()``."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or os.environ.get("TOME_B200_LIB", LIB_PATH)
+    if not os.path.exists(p):
+        raise RuntimeError(
+            f"tome_b200: CUDA extension not found at {p}; there is no CPU fallback. "
+            "Build it with `python video-how-do-your-tokens-merge_b200/build.py`.")
+    lib = ctypes.CDLL(p)
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise RuntimeError(f"tome_b200: {p} does not export {name}")
+    c_i32, c_f32, c_vp, c_sz = ctypes.c_int32, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+    lib.tome_abi_version.restype = c_i32
+    lib.tome_last_error.restype = ctypes.c_char_p
+    lib.tome_device_check.argtypes = [c_i32]
+    lib.tome_match_workspace_bytes.restype = c_sz
+    lib.tome_match_workspace_bytes.argtypes = [c_i32, c_i32, c_i32, c_i32]
+    lib.tome_match.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(TomeViewC), c_i32, c_i32, c_i32,
+                               c_vp, c_vp, c_vp, c_sz, c_vp]
+    lib.tome_rowmax.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]
+    lib.tome_select_workspace_bytes.restype = c_sz
+    lib.tome_select_workspace_bytes.argtypes = [c_i32, c_i32]
+    lib.tome_select.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_sz, c_vp]
+    lib.tome_merge.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_i32, ctypes.POINTER(TomeViewC), c_vp, c_i32,
+                               c_f32, c_vp, ctypes.POINTER(TomeViewC), c_vp, c_vp, c_vp]
+    lib.tome_merge_source.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_f32, c_vp, c_vp]
+    lib.tome_unmerge.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_i32, c_vp, c_vp]
+    for name in ("tome_device_check", "tome_match", "tome_rowmax", "tome_select", "tome_merge", "tome_merge_source",
+                 "tome_unmerge"):
+        getattr(lib, name).restype = c_i32
+    if lib.tome_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"tome_b200: ABI version {lib.tome_abi_version()} != expected {ABI_VERSION}; rebuild")
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _check(rc: int, lib) -> None:
+    if rc != 0:
+        raise RuntimeError(f"tome_b200 error {rc}: {lib.tome_last_error().decode()}")
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"tome_b200: {what} must live on a CUDA (sm_100) device; got {t.device}. "
+                           "The token-merging path has no CPU fallback.")
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return TOME_F32
+    if t.dtype == torch.bfloat16:
+        return TOME_BF16
+    raise RuntimeError(f"tome_b200: unsupported dtype {t.dtype} (fp32 and bf16 only)")
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _view_of(t: torch.Tensor) -> TomeViewC:
+    """(bm, tokens, c) tensor with unit channel stride -> tome_view."""
+    return TomeViewC(t.stride(0), 0, t.stride(1), 1)
+
+
+def _align(n: int, a: int = 64) -> int:
+    return (n + a - 1) // a * a
+
+
+class DevicePlan:
+    """Device buffers of one matching plan (mirrors ``tome_plan``)."""
+
+    __slots__ = ("bm", "n", "r", "class_token", "distill_token", "node_max", "node_idx", "src_idx", "unm_idx",
+                 "dst_idx", "a_map", "b_off", "b_src", "_ints", "_c", "device")
+
+    def __init__(self, bm, n, r, class_token, distill_token, node_max, node_idx):
+        na, nb = (n + 1) // 2, n // 2
+        self.bm, self.n, self.r = bm, n, r
+        self.class_token, self.distill_token = bool(class_token), bool(distill_token)
+        self.node_max, self.node_idx = node_max, node_idx
+        self.device = node_max.device
+        sizes = [bm * r, bm * (na - r), bm * r, bm * na, bm * (nb + 1), bm * r]
+        offs, tot = [], 0
+        for s in sizes:
+            offs.append(tot)
+            tot += _align(s)
+        self._ints = torch.empty(tot, dtype=torch.int32, device=self.device)
+        v = [self._ints[o:o + s] for o, s in zip(offs, sizes)]
+        self.src_idx = v[0].view(bm, r)
+        self.unm_idx = v[1].view(bm, na - r)
+        self.dst_idx = v[2].view(bm, r)
+        self.a_map = v[3].view(bm, na)
+        self.b_off = v[4].view(bm, nb + 1)
+        self.b_src = v[5].view(bm, r)
+        self._c = TomePlanC(bm, n, r, int(self.class_token), int(self.distill_token),
+                            node_max.data_ptr(), node_idx.data_ptr(), self.src_idx.data_ptr(),
+                            self.unm_idx.data_ptr(), self.dst_idx.data_ptr(), self.a_map.data_ptr(),
+                            self.b_off.data_ptr(), self.b_src.data_ptr())
+
+    @property
+    def na(self):
+        return (self.n + 1) // 2
+
+    @property
+    def nb(self):
+        return self.n // 2
+
+    def c_ptr(self):
+        return ctypes.byref(self._c)
+
+
+def device_check(device: Optional[int] = None) -> None:
+    lib = load_library()
+    if not torch.cuda.is_available():
+        raise RuntimeError("tome_b200: no CUDA device visible; the token-merging path has no CPU fallback")
+    dev = torch.cuda.current_device() if device is None else device
+    _check(lib.tome_device_check(dev), lib)
+
+
+def match(metric: torch.Tensor, class_token=False, distill_token=False, algo: int = MATCH_AUTO
+          ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Kernel 1.  metric (bm, n, cm) fp32/bf16 -> node_max (bm, na) f32, node_idx (bm, na) i32."""
+    lib = load_library()
+    _require_cuda(metric, "metric")
+    if metric.dim() != 3:
+        raise RuntimeError(f"tome_b200: metric must be (batch, tokens, channels); got {tuple(metric.shape)}")
+    if metric.dtype not in (torch.float32, torch.bfloat16):
+        metric = metric.float()
+    if metric.stride(2) != 1:
+        metric = metric.contiguous()
+    bm, n, cm = metric.shape
+    na = (n + 1) // 2
+    with torch.cuda.device(metric.device):
+        node_max = torch.empty(bm, na, dtype=torch.float32, device=metric.device)
+        node_idx = torch.empty(bm, na, dtype=torch.int32, device=metric.device)
+        ws_bytes = lib.tome_match_workspace_bytes(bm, n, cm, algo)
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=metric.device)
+        view = _view_of(metric)
+        _check(lib.tome_match(metric.data_ptr(), _dtype_code(metric), bm, n, cm, ctypes.byref(view),
+                              int(bool(class_token)), int(bool(distill_token)), algo, node_max.data_ptr(),
+                              node_idx.data_ptr(), ws.data_ptr(), ws_bytes, _stream(metric)), lib)
+    return node_max, node_idx
+
+
+def rowmax(scores: torch.Tensor, class_token=False, distill_token=False) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = load_library()
+    _require_cuda(scores, "scores")
+    scores = scores.float().contiguous()
+    bm, na, nb = scores.shape
+    with torch.cuda.device(scores.device):
+        node_max = torch.empty(bm, na, dtype=torch.float32, device=scores.device)
+        node_idx = torch.empty(bm, na, dtype=torch.int32, device=scores.device)
+        _check(lib.tome_rowmax(scores.data_ptr(), bm, na, nb, int(bool(class_token)), int(bool(distill_token)),
+                               node_max.data_ptr(), node_idx.data_ptr(), _stream(scores)), lib)
+    return node_max, node_idx
+
+
+def select(node_max: torch.Tensor, node_idx: torch.Tensor, n: int, r: int, class_token=False,
+           distill_token=False) -> DevicePlan:
+    """Kernel 2.  ``r`` must be the effective r (> 0)."""
+    lib = load_library()
+    _require_cuda(node_max, "node_max")
+    bm = node_max.shape[0]
+    with torch.cuda.device(node_max.device):
+        plan = DevicePlan(bm, n, r, class_token, distill_token, node_max.contiguous(), node_idx.contiguous())
+        ws_bytes = lib.tome_select_workspace_bytes(bm, n)
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=node_max.device)
+        _check(lib.tome_select(plan.c_ptr(), ws.data_ptr(), ws_bytes, _stream(node_max)), lib)
+    return plan
+
+
+def merge(plan: DevicePlan, x: torch.Tensor, mode: str, size: Optional[torch.Tensor] = None,
+          hybrid_threshold: Optional[float] = None, want_size: bool = False):
+    """Kernel 3.  x (bm, n, c) -> (bm, n - r, c).  mode in wavg/sum/mean/max/amax/drop.
+    Returns out, or (out, size_out, logsize_out) when ``want_size``."""
+    lib = load_library()
+    _require_cuda(x, "x")
+    if x.dim() != 3 or x.shape[0] != plan.bm or x.shape[1] != plan.n:
+        raise RuntimeError(f"tome_b200: merge expects x of shape ({plan.bm}, {plan.n}, c); got {tuple(x.shape)}")
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError(f"tome_b200: unsupported dtype {x.dtype} (fp32 and bf16 only)")
+    if x.stride(2) != 1:
+        x = x.contiguous()
+    m = _MODES[mode]
+    bm, n, c = x.shape
+    nout = n - plan.r
+    thr = float("nan") if hybrid_threshold is None else float(hybrid_threshold)
+    with torch.cuda.device(x.device):
+        out = torch.empty(bm, nout, c, dtype=x.dtype, device=x.device)
+        size_out = logsize_out = None
+        so = lo = None
+        if want_size:
+            size_out = torch.empty(bm, nout, dtype=torch.float32, device=x.device)
+            logsize_out = torch.empty(bm, nout, dtype=torch.float32, device=x.device)
+            so, lo = size_out.data_ptr(), logsize_out.data_ptr()
+        sp = None
+        if size is not None:
+            if m != MODE_WAVG:
+                raise RuntimeError("tome_b200: size is only used by the wavg mode")
+            size = size.reshape(bm, n).to(dtype=torch.float32).contiguous()
+            sp = size.data_ptr()
+        xv, ov = _view_of(x), _view_of(out)
+        _check(lib.tome_merge(plan.c_ptr(), x.data_ptr(), _dtype_code(x), c, ctypes.byref(xv), sp, m, thr,
+                              out.data_ptr(), ctypes.byref(ov), so, lo, _stream(x)), lib)
+    if want_size:
+        return out, size_out, logsize_out
+    return out
+
+
+def merge_source(plan: DevicePlan, source: Optional[torch.Tensor], hybrid_threshold: Optional[float] = None
+                 ) -> torch.Tensor:
+    lib = load_library()
+    thr = float("nan") if hybrid_threshold is None else float(hybrid_threshold)
+    dev = plan.device
+    with torch.cuda.device(dev):
+        if source is None:
+            n0, sp = plan.n, None
+        else:
+            _require_cuda(source, "source")
+            source = source.to(torch.float32).contiguous()
+            n0, sp = source.shape[2], source.data_ptr()
+        out = torch.empty(plan.bm, plan.n - plan.r, n0, dtype=torch.float32, device=dev)
+        _check(lib.tome_merge_source(plan.c_ptr(), sp, n0, thr, out.data_ptr(),
+                                     torch.cuda.current_stream(dev).cuda_stream), lib)
+    return out
+
+
+def unmerge(plan: DevicePlan, x: torch.Tensor) -> torch.Tensor:
+    lib = load_library()
+    _require_cuda(x, "x")
+    x = x.contiguous()
+    bm, nout, c = x.shape
+    if bm != plan.bm or nout != plan.n - plan.r:
+        raise RuntimeError(f"tome_b200: unmerge expects ({plan.bm}, {plan.n - plan.r}, c); got {tuple(x.shape)}")
+    with torch.cuda.device(x.device):
+        out = torch.empty(bm, plan.n, c, dtype=x.dtype, device=x.device)
+        _check(lib.tome_unmerge(plan.c_ptr(), x.data_ptr(), _dtype_code(x), c, out.data_ptr(), _stream(x)), lib)
+    return out

@@ -1,0 +1,212 @@
+"""B200-native drop-in for the reference's ``tome/merge.py``.
+
+Same public names, argument meaning and return conventions as
+/root/reference/tome/merge.py; the work runs in the sm_100a kernels behind the C ABI
+(include/tome_b200.h) instead of ~40 ATen launches per block:
+
+  bipartite_soft_matching        (merge.py:17-102)   -> tome_match + tome_select
+  bipartite_soft_matching_drop   (merge.py:215-271)  -> same matching, tome_merge(DROP)
+  bipartite_soft_matching_hybrid (merge.py:274-352)  -> same matching, tome_merge(threshold)
+  merge_wavg                     (merge.py:355-369)  -> ONE fused tome_merge(WAVG) pass
+  merge_source                   (merge.py:372-384)  -> tome_merge_source
+  kth_/random_bipartite_soft_matching (merge.py:105-212) -- upstream-ToMe leftovers with no
+      caller in the reference; kept importable, built from device torch ops.
+
+Differences that are deliberate and documented in DESIGN.md: ties are broken by the stable
+rule (lowest index) where the reference's argsort is unstable; scores use the canonical
+fp64-accumulated definition; token sizes are always fp32.  No CPU fallback: tensors must
+be on an sm_100 CUDA device.
+"""
+import math
+from typing import Callable, Optional, Tuple
+
+import torch
+
+from . import _native
+
+
+def do_nothing(x, mode=None):
+    return x
+
+
+def _effective_r(metric: torch.Tensor, r: int, class_token: bool, distill_token: bool) -> int:
+    protected = int(bool(class_token)) + int(bool(distill_token))
+    t = metric.shape[1]
+    return min(r, (t - protected) // 2)          # merge.py:43-44
+
+
+def _make_plan(metric, r, class_token, distill_token, random_scores: bool) -> "_native.DevicePlan":
+    _native._require_cuda(metric, "metric")
+    with torch.no_grad():
+        if random_scores:                          # merge.py:54-57: same torch.rand call, same generator
+            length = metric.size(1)
+            len_a, len_b = (length + 1) // 2, length // 2
+            scores = torch.rand(size=(metric.size(0), len_a, len_b), device=metric.device)
+            node_max, node_idx = _native.rowmax(scores, class_token, distill_token)
+        else:
+            node_max, node_idx = _native.match(metric, class_token, distill_token)
+        return _native.select(node_max, node_idx, metric.shape[1], r, class_token, distill_token)
+
+
+class _PlanCallable:
+    """Base of the merge/unmerge/drop callables: exposes what the reference closures
+    capture (``unm_idx``, ``src_idx``, ``dst_idx`` as int64 (bm, k, 1); ``r``)."""
+
+    def __init__(self, plan: "_native.DevicePlan", threshold: Optional[float] = None):
+        self.plan = plan
+        self.threshold = threshold
+
+    r = property(lambda self: self.plan.r)
+    src_idx = property(lambda self: self.plan.src_idx.long()[..., None])
+    unm_idx = property(lambda self: self.plan.unm_idx.long()[..., None])
+    dst_idx = property(lambda self: self.plan.dst_idx.long()[..., None])
+    node_max = property(lambda self: self.plan.node_max)
+
+
+class Merge(_PlanCallable):
+    def __call__(self, x: torch.Tensor, mode="mean") -> torch.Tensor:      # merge.py:75-85 / 316-334
+        return _native.merge(self.plan, x, mode, hybrid_threshold=self.threshold)
+
+    def wavg(self, x, size=None):
+        """Fused merge_wavg: (x', size' (bm, n', 1) fp32, log size' (bm, n', 1) fp32)."""
+        out, s, ls = _native.merge(self.plan, x, "wavg", size=size, hybrid_threshold=self.threshold, want_size=True)
+        return out, s[..., None], ls[..., None]
+
+    def source(self, source=None):
+        return _native.merge_source(self.plan, source, self.threshold)
+
+
+class Unmerge(_PlanCallable):
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:                    # merge.py:87-100
+        return _native.unmerge(self.plan, x)
+
+
+class Drop(_PlanCallable):
+    und_idx = property(lambda self: self.plan.unm_idx.long()[..., None])
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:                    # merge.py:260-269
+        return _native.merge(self.plan, x, "drop")
+
+
+def bipartite_soft_matching(
+    metric: torch.Tensor, r: int, class_token: bool = False, distill_token: bool = False, mode: str = 'merge'
+) -> Tuple[Callable, Callable]:
+    """Balanced (50/50) bipartite soft matching; see the reference docstring (merge.py:24-35).
+
+    metric: [batch, tokens, channels]; r: tokens to remove (clamped to 50% of unprotected)."""
+    r = _effective_r(metric, r, class_token, distill_token)
+    if r <= 0:
+        return do_nothing, do_nothing
+    if mode not in ('merge', 'random_merge'):
+        raise ValueError(f"bipartite_soft_matching: mode must be 'merge' or 'random_merge', got {mode!r}")
+    plan = _make_plan(metric, r, class_token, distill_token, mode == 'random_merge')
+    return Merge(plan), Unmerge(plan)
+
+
+def bipartite_soft_matching_drop(
+    metric: torch.Tensor, r: int, class_token: bool = False, distill_token: bool = False, mode: str = 'drop'
+):
+    r = _effective_r(metric, r, class_token, distill_token)
+    if r <= 0:
+        return do_nothing, do_nothing      # sic: the reference returns a tuple here (merge.py:232-233)
+    if mode not in ('drop', 'random_drop'):
+        raise ValueError(f"bipartite_soft_matching_drop: mode must be 'drop' or 'random_drop', got {mode!r}")
+    plan = _make_plan(metric, r, class_token, distill_token, mode == 'random_drop')
+    return Drop(plan)
+
+
+def bipartite_soft_matching_hybrid(
+    metric: torch.Tensor, r: int, class_token: bool = False, distill_token: bool = False, mode: str = 'merge',
+    threshold: float = 0.0
+) -> Tuple[Callable, Callable]:
+    r = _effective_r(metric, r, class_token, distill_token)
+    if r <= 0:
+        return do_nothing, do_nothing
+    if mode not in ('merge', 'hybrid', 'random_merge'):
+        raise ValueError(f"bipartite_soft_matching_hybrid: bad mode {mode!r}")
+    plan = _make_plan(metric, r, class_token, distill_token, mode == 'random_merge')
+    return Merge(plan, threshold=float(threshold)), Unmerge(plan)
+
+
+def merge_wavg(merge: Callable, x: torch.Tensor, size: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Size-weighted average merge; returns (merged x, new sizes) like merge.py:355-369."""
+    if isinstance(merge, Merge):
+        out, size_out, _ = merge.wavg(x, size)
+        return out, size_out
+    if size is None:
+        size = torch.ones_like(x[..., 0, None])
+    x = merge(x * size, mode="sum")
+    size = merge(size, mode="sum")
+    x = x / size
+    return x, size
+
+
+def merge_source(merge: Callable, x: torch.Tensor, source: torch.Tensor = None) -> torch.Tensor:
+    """Source adjacency tracking (merge.py:372-384)."""
+    if isinstance(merge, Merge):
+        return merge.source(source)
+    if source is None:
+        n, t, _ = x.shape
+        source = torch.eye(t, device=x.device)[None, ...].expand(n, t, t)
+    return merge(source, mode="max")
+
+
+# ---- upstream-ToMe variants with no caller in the reference (merge.py:105-212) -------------
+def kth_bipartite_soft_matching(metric: torch.Tensor, k: int) -> Tuple[Callable, Callable]:
+    if k <= 1:
+        return do_nothing, do_nothing
+
+    def split(x):
+        t_rnd = (x.shape[1] // k) * k
+        x = x[:, :t_rnd, :].view(x.shape[0], -1, k, x.shape[2])
+        return x[:, :, :k - 1, :].contiguous().view(x.shape[0], -1, x.shape[-1]), x[:, :, k - 1, :]
+
+    with torch.no_grad():
+        metric = metric / metric.norm(dim=-1, keepdim=True)
+        a, b = split(metric)
+        r = a.shape[1]
+        dst_idx = (a @ b.transpose(-1, -2)).argmax(dim=-1)[..., None]
+
+    def merge(x, mode="mean"):
+        src, dst = split(x)
+        n, _, c = src.shape
+        return dst.scatter_reduce(-2, dst_idx.expand(n, r, c), src, reduce=mode)
+
+    def unmerge(x):
+        n, _, c = x.shape
+        src = x.gather(dim=-2, index=dst_idx.expand(n, r, c)).to(x.dtype).view(n, -1, k - 1, c)
+        return torch.cat([src, x.view(n, -1, 1, c)], dim=-2).contiguous().view(n, -1, c)
+
+    return merge, unmerge
+
+
+def random_bipartite_soft_matching(metric: torch.Tensor, r: int) -> Tuple[Callable, Callable]:
+    if r <= 0:
+        return do_nothing, do_nothing
+    with torch.no_grad():
+        B, N, _ = metric.shape
+        rand_idx = torch.rand(B, N, 1, device=metric.device).argsort(dim=1)
+        a_idx, b_idx = rand_idx[:, :r, :], rand_idx[:, r:, :]
+
+        def split(x):
+            C = x.shape[-1]
+            return x.gather(dim=1, index=a_idx.expand(B, r, C)), x.gather(dim=1, index=b_idx.expand(B, N - r, C))
+
+        metric = metric / metric.norm(dim=-1, keepdim=True)
+        a, b = split(metric)
+        dst_idx = (a @ b.transpose(-1, -2)).argmax(dim=-1)[..., None]
+
+    def merge(x, mode="mean"):
+        src, dst = split(x)
+        C = src.shape[-1]
+        return dst.scatter_reduce(-2, dst_idx.expand(B, r, C), src, reduce=mode)
+
+    def unmerge(x):
+        C = x.shape[-1]
+        src = x.gather(dim=-2, index=dst_idx.expand(B, r, C))
+        out = torch.zeros(B, N, C, device=x.device, dtype=x.dtype)
+        out.scatter_(dim=-2, index=a_idx.expand(B, r, C), src=src)
+        out.scatter_(dim=-2, index=b_idx.expand(B, N - r, C), src=x)
+        return out
+
+    return merge, unmerge
