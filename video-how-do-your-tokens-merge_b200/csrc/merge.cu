@@ -292,17 +292,20 @@ int launch_merge_source(const tome_plan* plan, const float* source, int n0, floa
 }
 
 int launch_unmerge(const tome_plan* plan, const void* x, int dtype, int c, void* out, cudaStream_t st) {
+  // NB: the reference's unmerge (merge.py:87-100) splits x as [unm | dst] even when a
+  // distill token made merge() interleave them (merge.py:82-83); kept as is, so the slot
+  // mapping here never uses the distill layout.
   dim3 grid((plan->n + 7) / 8, plan->bm);
   if (dtype == TOME_F32) {
     if (c % 4 == 0 && aligned16(x) && aligned16(out))
-      unmerge_rows_kernel<float, 4><<<grid, 256, 0, st>>>(plan->a_map, plan->n, plan->r, plan->distill_token, c, (const float*)x, (float*)out);
+      unmerge_rows_kernel<float, 4><<<grid, 256, 0, st>>>(plan->a_map, plan->n, plan->r, 0, c, (const float*)x, (float*)out);
     else
-      unmerge_rows_kernel<float, 1><<<grid, 256, 0, st>>>(plan->a_map, plan->n, plan->r, plan->distill_token, c, (const float*)x, (float*)out);
+      unmerge_rows_kernel<float, 1><<<grid, 256, 0, st>>>(plan->a_map, plan->n, plan->r, 0, c, (const float*)x, (float*)out);
   } else if (dtype == TOME_BF16) {
     if (c % 8 == 0 && aligned16(x) && aligned16(out))
-      unmerge_rows_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>(plan->a_map, plan->n, plan->r, plan->distill_token, c, (const __nv_bfloat16*)x, (__nv_bfloat16*)out);
+      unmerge_rows_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>(plan->a_map, plan->n, plan->r, 0, c, (const __nv_bfloat16*)x, (__nv_bfloat16*)out);
     else
-      unmerge_rows_kernel<__nv_bfloat16, 1><<<grid, 256, 0, st>>>(plan->a_map, plan->n, plan->r, plan->distill_token, c, (const __nv_bfloat16*)x, (__nv_bfloat16*)out);
+      unmerge_rows_kernel<__nv_bfloat16, 1><<<grid, 256, 0, st>>>(plan->a_map, plan->n, plan->r, 0, c, (const __nv_bfloat16*)x, (__nv_bfloat16*)out);
   } else return set_error(TOME_ERR_DTYPE, "tome_unmerge: unsupported dtype %d", dtype);
   TOME_LAUNCH_CHECK("unmerge_rows_kernel");
   return TOME_OK;
