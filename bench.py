@@ -1,0 +1,446 @@
+#!/usr/bin/env python3
+"""Benchmark of the B200-native token-merging path on the workload BASELINE.json names.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (configs[1]): VideoMAE ViT-B 16x224, ToMe merge mode, constant r schedule
+(model.r = (r, 0), r = 100), 8 synthetic clips per GPU, random-init weights, bf16 model,
+fp32 matching.  A step = one forward of one batch through the patched model.  Prints ONE JSON
+line (see the task contract): clips/s with inputs resident in HBM (`value`), the same
+through host buffers (`e2e`), the roofline of the dominant hot-path kernel (merge_wavg,
+HBM-bound), and the CPU baseline (oracle/torch_port.py, the reference's ATen call mix,
+timed on this box's host cores).
+
+Multi-GPU: pure data parallelism, one process per GPU (torchrun), weights replicated from
+the same seed, no collective on the data path; logits are all-gathered once per step over
+NCCL (slowfast/utils/distributed.py:25-44, tools/test_net.py:159).  Timing = CUDA events,
+barrier + synchronize on both sides, max over ranks.
+"""
+import argparse
+import contextlib
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "video-how-do-your-tokens-merge_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+NUM_CLASSES = 400
+FRAMES, CROP = 16, 224
+L2_BYTES = 126 * 2 ** 20
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="clips per GPU per step (experiments.sh:126)")
+    ap.add_argument("--r", type=int, default=100)
+    ap.add_argument("--schedule", type=float, default=0.0, help="r inflection: 0 const, -1 decreasing, +1 increasing")
+    ap.add_argument("--mode", default="merge")
+    ap.add_argument("--prop-attn", type=int, default=0, help="VideoMAE default False (videomae.py:173)")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--match-algo", type=int, default=0, help="0 auto, 1 exact SIMT, 2 tcgen05")
+    ap.add_argument("--cpu-clips", type=int, default=1, help="clips per CPU-baseline step")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-micro", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+# plumbing
+# ------------------------------------------------------------------------------------------
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for row in self.rows:
+            f = [s.strip() for s in row.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_videomae(device, dtype, args):
+    import hostmodels
+    import tome
+    torch.manual_seed(0)
+    model = hostmodels.VideoMAE(arch="vit_base_patch16_224", num_classes=NUM_CLASSES, num_frames=FRAMES,
+                                tubelet_size=2, use_mean_pooling=True, init_scale=0.001).eval()
+    model = model.to(device=device, dtype=dtype)
+    tome.patch.videomae(model, trace_source=False, prop_attn=bool(args.prop_attn), mode=args.mode,
+                        head_aggregation="mean", threshold=0.8)
+    model.r = (args.r, args.schedule)
+    return model
+
+
+def token_schedule(args, depth=12, n0=1568):
+    from tome.utils import parse_r
+    n, out = n0, []
+    for r in parse_r(depth, (args.r, args.schedule)):
+        r_eff = max(min(r, n // 2), 0)
+        out.append((n, r_eff))
+        n -= r_eff
+    return out
+
+
+@contextlib.contextmanager
+def cpu_port_backend():
+    """Route tome.patch.videomae's merge calls to oracle/torch_port.py (CPU baseline legs only)."""
+    from oracle import torch_port as P
+    mod = sys.modules["tome.patch.videomae"]
+    names = ("bipartite_soft_matching", "bipartite_soft_matching_drop", "bipartite_soft_matching_hybrid",
+             "merge_wavg", "merge_source")
+    saved = {n: getattr(mod, n) for n in names}
+    try:
+        for n in names:
+            setattr(mod, n, getattr(P, n))
+        yield
+    finally:
+        for n, f in saved.items():
+            setattr(mod, n, f)
+
+
+def time_cpu_reference(args, steps, warmup):
+    """The reference's CPU path (kind 'port'): fp32 VideoMAE-B on the host cores, merge path =
+    oracle/torch_port.py, `cpu_clips` clips per step."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    a2 = argparse.Namespace(**vars(args))
+    model = build_videomae(torch.device("cpu"), torch.float32, a2)
+    x = torch.rand(args.cpu_clips, 3, FRAMES, CROP, CROP)
+    times = []
+    with cpu_port_backend(), torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            model([x])
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    mean = sum(times) / len(times)
+    return {"value": args.cpu_clips / mean, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} steps x {args.cpu_clips} clip(s) after {warmup} warm-up, fp32, "
+                      f"oracle/torch_port.py merge path, {mean * 1e3:.0f} ms/step"}, mean
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm
+# ------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return 0
+    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
+    cb, mean = time_cpu_reference(args, steps, warmup)
+    line = {
+        "impl": "reference", "metric": "clips_per_sec", "value": cb["value"], "unit": "clips/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": mean * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, cpu=True),
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, cpu=False):
+    return {
+        "workload": "VideoMAE ViT-B 16x224 (tubelet 2x16x16, 1568 tokens, 12 layers, 400 classes), ToMe "
+                    f"mode={args.mode} r=({args.r},{args.schedule:g}) prop_attn={bool(args.prop_attn)}, "
+                    "synthetic torch.rand clips, random-init weights (seed 0)",
+        "clips_per_gpu_per_step": args.cpu_clips if cpu else args.batch,
+        "token_schedule": [n for n, _ in token_schedule(args)],
+        "parallelism": f"dp{args.gpus}",
+        "cuda_graph": (not args.no_graph) and not cpu,
+        "l2": "each step reads a different resident input batch (4 x 38.5 MB rotate) and 172 MB of bf16 weights: "
+              "working set > 126 MB L2",
+    }
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def micro_kernels(args, device, dtype):
+    """CUDA-event timing of the hot-path kernels at the workload's layer-0 shape, rotating
+    over buffers larger than L2.  Returns (roofline dict for merge_wavg, per-kernel dict)."""
+    from tome import _native
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    bm, n, c, cm, r = args.batch, 1568, 768, 64, min(args.r, 784)
+    e = 2 if dtype == torch.bfloat16 else 4
+    nrot = max(2, int(math.ceil(1.5 * L2_BYTES / (bm * n * c * e))))
+    g = torch.Generator(device=device).manual_seed(1)
+    xs = [torch.randn(bm, n, c, device=device, dtype=dtype, generator=g) for _ in range(nrot)]
+    ms = [torch.randn(bm, n, cm, device=device, dtype=dtype, generator=g) for _ in range(nrot)]
+    size = torch.randint(1, 4, (bm, n, 1), device=device, generator=g).float()
+    res = {}
+
+    def timeit(fn, iters=40):
+        for i in range(5):
+            fn(i)
+        torch.cuda.synchronize()
+        st = [torch.cuda.Event(enable_timing=True) for _ in range(iters)]
+        en = [torch.cuda.Event(enable_timing=True) for _ in range(iters)]
+        for i in range(iters):
+            st[i].record()
+            fn(i)
+            en[i].record()
+        torch.cuda.synchronize()
+        ts = sorted(s.elapsed_time(e_) for s, e_ in zip(st, en))
+        return sum(ts) / len(ts) * 1e3, ts[len(ts) // 2] * 1e3   # mean, median in us
+
+    nm, ni = _native.match(ms[0], algo=args.match_algo)
+    plan = _native.select(nm, ni, n, r)
+    mean_us, med_us = timeit(lambda i: _native.merge(plan, xs[i % nrot], "wavg", size=size, want_size=True))
+    na = (n + 1) // 2
+    alg_bytes = bm * (n * c * e + n * 4 + (n - r) * c * e + (n - r) * 8 + na * 12)
+    achieved = alg_bytes / (mean_us * 1e-6) / 1e9
+    roofline = {"kernel": "merge_rows_kernel (merge_wavg + size + log size, layer-0 shape "
+                          f"Bm={bm} N={n} C={c} r={r} {args.dtype})",
+                "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "algorithmic_bytes": alg_bytes, "us_mean": mean_us, "us_median": med_us,
+                "peak_source": peak_src, "timing": f"cuda events per launch, {nrot} rotating inputs > L2"}
+    m_mean, m_med = timeit(lambda i: _native.match(ms[i % nrot], algo=args.match_algo))
+    flops = 2.0 * bm * na * (n // 2) * cm
+    res["match"] = {"us_mean": m_mean, "us_median": m_med, "algorithmic_gflop": flops / 1e9,
+                    "tflops": flops / (m_mean * 1e-6) / 1e12, "algo": args.match_algo}
+    s_mean, s_med = timeit(lambda i: _native.select(nm, ni, n, r))
+    res["select"] = {"us_mean": s_mean, "us_median": s_med}
+    return roofline, res
+
+
+def run_ours(args):
+    rank, local, world = dist_env()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the token-merging path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    from tome import _native
+    _native.device_check(local)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    if args.match_algo:
+        orig_match = _native.match
+        _native.match = lambda metric, c=False, d=False, algo=0: orig_match(metric, c, d, algo=args.match_algo)
+    model = build_videomae(device, dtype, args)
+    B = args.batch
+    nrot = 4
+    g = torch.Generator(device=device).manual_seed(1234 + rank)
+    resident = [torch.rand(B, 3, FRAMES, CROP, CROP, device=device, generator=g).to(dtype) for _ in range(nrot)]
+    static_in = torch.empty_like(resident[0])
+    logits_all = torch.empty(world * B, NUM_CLASSES, device=device, dtype=torch.float32) if world > 1 else None
+
+    def forward():
+        return model([static_in]).float()
+
+    # warm-up (eager: lazy init, cuBLAS handles, kernel attribute setup), then graph capture
+    launches_before = _native.launch_count()
+    with torch.no_grad():
+        static_in.copy_(resident[0])
+        out = forward()
+        launches_per_step = _native.launch_count() - launches_before
+        for i in range(max(args.warmup, 3)):
+            static_in.copy_(resident[i % nrot])
+            out = forward()
+        torch.cuda.synchronize()
+        graph = None
+        if not args.no_graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                forward()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = forward()
+        else:
+            static_out = None
+
+        def step(i):
+            static_in.copy_(resident[i % nrot], non_blocking=True)
+            if graph is not None:
+                graph.replay()
+                o = static_out
+            else:
+                o = forward()
+            if world > 1:
+                torch.distributed.all_gather_into_tensor(logits_all, o)
+            return o
+
+        for i in range(args.warmup):
+            step(i)
+        torch.cuda.synchronize()
+
+        def barrier():
+            if world > 1:
+                torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+        # ---- value: inputs resident in HBM -------------------------------------------------
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clocks:
+            barrier()
+            start.record()
+            for i in range(args.steps):
+                out = step(i)
+            end.record()
+            barrier()
+        ms = start.elapsed_time(end)
+        top1 = out.argmax(-1)
+
+        # ---- e2e: pinned host clips -> H2D -> forward -> logits D2H, copies overlapped -----
+        host_in = [torch.rand(B, 3, FRAMES, CROP, CROP).pin_memory() for _ in range(2)]
+        host_out = torch.empty(B, NUM_CLASSES, dtype=torch.float32).pin_memory()
+        stage = [torch.empty(B, 3, FRAMES, CROP, CROP, device=device) for _ in range(2)]
+        copy_stream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        copied = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+
+        def e2e_loop(k):
+            for i in range(k + 1):
+                if i < k:                     # prefetch step i's clips on the copy stream
+                    with torch.cuda.stream(copy_stream):
+                        if i >= 2:
+                            copy_stream.wait_event(consumed[i % 2])
+                        stage[i % 2].copy_(host_in[i % 2], non_blocking=True)
+                        copied[i % 2].record(copy_stream)
+                if i >= 1:                    # run step i-1
+                    j = i - 1
+                    main.wait_event(copied[j % 2])
+                    static_in.copy_(stage[j % 2])          # fp32 -> model dtype on device
+                    consumed[j % 2].record(main)
+                    if graph is not None:
+                        graph.replay()
+                        o = static_out
+                    else:
+                        o = forward()
+                    if world > 1:
+                        torch.distributed.all_gather_into_tensor(logits_all, o)
+                    host_out.copy_(o, non_blocking=True)
+
+        e2e_loop(2)
+        barrier()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        e2e_loop(args.steps)
+        e2.record()
+        barrier()
+        ms_e2e = s2.elapsed_time(e2)
+
+    times = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
+    ms, ms_e2e = float(times[0]), float(times[1])
+
+    roofline, kernels, cpu_baseline = None, None, None
+    if rank == 0 and not args.skip_micro:
+        roofline, kernels = micro_kernels(args, device, dtype)
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        cpu_baseline, _ = time_cpu_reference(args, steps=2, warmup=1)
+    if world > 1:
+        torch.distributed.barrier()
+
+    if rank == 0:
+        total_clips = world * B * args.steps
+        h2d = B * 3 * FRAMES * CROP * CROP * 4
+        line = {
+            "metric": "clips_per_sec", "value": total_clips / (ms * 1e-3), "unit": "clips/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": workload_config(args),
+            "clocks": clocks.summary(),
+            "e2e": {"value": total_clips / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": B * NUM_CLASSES * 4, "ms_per_step": ms_e2e / args.steps,
+                    "note": "pinned fp32 clips -> H2D on a copy stream (double-buffered) -> bf16 cast + forward -> logits D2H"},
+            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_per_step": launches_per_step,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+            "match_algo": "auto" if not args.match_algo else args.match_algo,
+            "top1_sample": top1[:4].tolist(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -100,6 +100,8 @@ typedef struct tome_view {
 
 TOME_API int tome_abi_version(void);
 TOME_API const char* tome_last_error(void);
+/* Number of kernels this library has enqueued since load (bench.py's gpu_launches). */
+TOME_API unsigned long long tome_launch_count(void);
 
 /* TOME_OK when `device` is compute capability 10.x and the kernels can launch. */
 TOME_API int tome_device_check(int device);

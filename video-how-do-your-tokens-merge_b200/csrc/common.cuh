@@ -21,8 +21,10 @@ int set_error(int code, const char* fmt, ...);
     if (_e != cudaSuccess)                                                                \
       return tome::set_error(TOME_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
+void count_launch();
 #define TOME_LAUNCH_CHECK(name)                                                           \
   do {                                                                                    \
+    tome::count_launch();                                                                 \
     cudaError_t _e = cudaGetLastError();                                                  \
     if (_e != cudaSuccess)                                                                \
       return tome::set_error(TOME_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \

@@ -18,6 +18,9 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
 static int g_dev_ok[64];   // 0 unknown, 1 ok, -1 bad
 static int g_sms[64];
 
@@ -79,6 +82,7 @@ extern "C" {
 
 int tome_abi_version(void) { return TOME_ABI_VERSION; }
 const char* tome_last_error(void) { return g_err; }
+unsigned long long tome_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int tome_device_check(int device) {
   int cur = 0;

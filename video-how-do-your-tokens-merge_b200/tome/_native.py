@@ -26,7 +26,7 @@ _MODES = {"wavg": MODE_WAVG, "sum": MODE_SUM, "mean": MODE_MEAN, "max": MODE_AMA
           "drop": MODE_DROP}
 
 EXPORTS = (
-    "tome_abi_version", "tome_last_error", "tome_device_check", "tome_match_workspace_bytes", "tome_match",
+    "tome_abi_version", "tome_last_error", "tome_launch_count", "tome_device_check", "tome_match_workspace_bytes", "tome_match",
     "tome_rowmax", "tome_select_workspace_bytes", "tome_select", "tome_merge", "tome_merge_source", "tome_unmerge",
 )
 
@@ -67,6 +67,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     c_i32, c_f32, c_vp, c_sz = ctypes.c_int32, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
     lib.tome_abi_version.restype = c_i32
     lib.tome_last_error.restype = ctypes.c_char_p
+    lib.tome_launch_count.restype = ctypes.c_ulonglong
     lib.tome_device_check.argtypes = [c_i32]
     lib.tome_match_workspace_bytes.restype = c_sz
     lib.tome_match_workspace_bytes.argtypes = [c_i32, c_i32, c_i32, c_i32]
@@ -162,6 +163,11 @@ class DevicePlan:
 
     def c_ptr(self):
         return ctypes.byref(self._c)
+
+
+def launch_count() -> int:
+    """Kernels enqueued by libtome_b200 since it was loaded."""
+    return int(load_library().tome_launch_count())
 
 
 def device_check(device: Optional[int] = None) -> None:

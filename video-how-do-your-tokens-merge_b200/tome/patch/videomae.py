@@ -1,0 +1,231 @@
+"""``tome.patch.videomae`` -- drop-in for the reference's tome/patch/videomae.py.
+
+Same entry points and semantics (apply_patch, apply_duplicate_patch, model.r, the shared
+``_tome_info`` dict with the reference's keys), but
+  * modules are matched structurally (class name + attributes) instead of by
+    ``isinstance(slowfast...Block)``, so both the reference's slowfast VideoMAE and
+    ``hostmodels.videomae`` can be patched;
+  * the per-block reduction calls the sm_100a kernels: one match, one select, ONE fused
+    merge_wavg pass that also emits the new token sizes and log(size)
+    (reference: videomae.py:80-151 -> ~40 ATen launches);
+  * proportional attention reads the kernel-emitted ``_tome_info['log_size']`` instead of
+    recomputing ``size.log()`` (videomae.py:62-63) and goes through fused SDPA.
+"""
+import copy
+
+import torch
+import torch.nn.functional as F
+
+from tome.merge import (Merge, bipartite_soft_matching, bipartite_soft_matching_drop,
+                        bipartite_soft_matching_hybrid, merge_source, merge_wavg)
+from tome.utils import parse_r
+
+
+class ToMeBlockMixin:
+    """videomae.py:13-30."""
+
+    def forward(self, x):
+        info = self._tome_info
+        attn_size = info["size"] if info["prop_attn"] else None
+        attn_bias = info.get("log_size") if info["prop_attn"] else None
+        attn, metric = self.attn(self.norm1(x), attn_size, info["head_aggregation"], attn_bias)
+        if self.gamma_1 is None:
+            x = x + self.drop_path(attn)
+            x = self.reduction_function(metric, x, info)
+            x = x + self.drop_path(self.mlp(self.norm2(x)))
+        else:
+            x = x + self.drop_path(self.gamma_1 * attn)
+            x = self.reduction_function(metric, x, info)
+            x = x + self.drop_path(self.gamma_2 * self.mlp(self.norm2(x)))
+        return x
+
+
+class ToMeDuplicateBlockMixin:
+    """videomae.py:33-44: attention-only replica used by the layer-duplication ablation."""
+
+    def forward(self, x):
+        info = self._tome_info
+        attn_size = info["size"] if info["prop_attn"] else None
+        attn_bias = info.get("log_size") if info["prop_attn"] else None
+        _, metric = self.attn(self.norm1(x), attn_size, info["head_aggregation"], attn_bias)
+        return self.reduction_function(metric, x, info)
+
+
+class ToMeAttentionMixin:
+    """videomae.py:47-77: attention that also returns the matching metric."""
+
+    def forward(self, x, size: torch.Tensor = None, head_aggregation: str = 'mean', log_size: torch.Tensor = None):
+        B, N, C = x.shape
+        qkv_bias = None
+        if self.q_bias is not None:
+            qkv_bias = torch.cat((self.q_bias, torch.zeros_like(self.v_bias, requires_grad=False), self.v_bias))
+        qkv = F.linear(input=x, weight=self.qkv.weight, bias=qkv_bias)
+        qkv = qkv.reshape(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv[0], qkv[1], qkv[2]
+
+        bias = None
+        if size is not None:                     # proportional attention (videomae.py:62-63)
+            if log_size is None:
+                log_size = size.log()
+            bias = log_size[:, None, None, :, 0].to(q.dtype).expand(B, 1, N, N)
+        drop = self.attn_drop.p if self.training else 0.0
+        x = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, dropout_p=drop, scale=self.scale)
+        x = x.transpose(1, 2).reshape(B, N, -1)
+        x = self.proj_drop(self.proj(x))
+
+        if head_aggregation == 'mean':
+            metric = k.mean(1)
+        elif head_aggregation == 'concat':
+            metric = k.transpose(1, 2).reshape(B, N, -1)       # == cat(k.split(1, dim=1), -1).squeeze(1)
+        else:
+            raise ValueError(f"head_aggregation must be 'mean' or 'concat', got {head_aggregation!r}")
+        return x, metric
+
+
+def videomae_merge(metric, x, _tome_info):
+    """videomae.py:80-100."""
+    r = _tome_info["r"].pop(0)
+    if r > 0:
+        merge, _ = bipartite_soft_matching(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
+                                           _tome_info["mode"])
+        if _tome_info["trace_source"]:
+            _tome_info["source"] = merge_source(merge, x, _tome_info["source"])
+        pre_merge = x.size(1)
+        if isinstance(merge, Merge):
+            x, _tome_info["size"], _tome_info["log_size"] = merge.wavg(x, _tome_info["size"])
+        else:
+            x, _tome_info["size"] = merge_wavg(merge, x, _tome_info["size"])
+            _tome_info["log_size"] = None
+        if _tome_info['verbose']:
+            print(f'Merged {pre_merge} to {x.size(1)} tokens')
+    return x
+
+
+def videomae_drop(metric, x, _tome_info):
+    """videomae.py:103-126."""
+    r = _tome_info["r"].pop(0)
+    if r > 0:
+        drop = bipartite_soft_matching_drop(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
+                                            _tome_info["mode"])
+        if isinstance(drop, tuple):              # r clamped to 0 (reference returns a tuple there)
+            return x
+        if _tome_info["trace_source"]:
+            if _tome_info["source"] is None:
+                n, t, _ = x.shape
+                _tome_info["source"] = torch.eye(t, device=x.device)[None, ...].expand(n, t, t)
+            _tome_info["source"] = drop(_tome_info["source"].contiguous())
+        pre_drop = x.size(1)
+        x = drop(x)
+        _tome_info["size"] = torch.ones((x.size(0), x.size(1), 1), device=x.device)
+        _tome_info["log_size"] = torch.zeros((x.size(0), x.size(1), 1), device=x.device)
+        if _tome_info['verbose']:
+            print(f'Dropped {pre_drop} to {x.size(1)} tokens')
+    return x
+
+
+def videomae_hybrid(metric, x, _tome_info):
+    """videomae.py:129-151."""
+    r = _tome_info["r"].pop(0)
+    if r > 0:
+        merge, _ = bipartite_soft_matching_hybrid(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
+                                                  _tome_info["mode"], _tome_info["threshold"])
+        if _tome_info["trace_source"]:
+            _tome_info["source"] = merge_source(merge, x, _tome_info["source"])
+        pre_merge = x.size(1)
+        if isinstance(merge, Merge):
+            x, _tome_info["size"], _tome_info["log_size"] = merge.wavg(x, _tome_info["size"])
+        else:
+            x, _tome_info["size"] = merge_wavg(merge, x, _tome_info["size"])
+            _tome_info["log_size"] = None
+        if _tome_info['verbose']:
+            print(f'Merged {pre_merge} to {x.size(1)} tokens')
+    return x
+
+
+# ---- structural matching of the modules to patch ----------------------------------------------
+def _is_block(m):
+    return all(hasattr(m, a) for a in ("norm1", "attn", "norm2", "mlp", "gamma_1")) and _is_attention(m.attn)
+
+
+def _is_attention(m):
+    return all(hasattr(m, a) for a in ("qkv", "q_bias", "v_bias", "proj", "num_heads", "scale"))
+
+
+_CLASS_CACHE = {}
+
+
+def _swap(module, mixin, tag):
+    base = module.__class__
+    if getattr(base, "_tome_mixin", None) is mixin:
+        return
+    if getattr(base, "_tome_mixin", None) is not None:       # re-patching: go back to the original class
+        base = base._tome_base
+    key = (base, mixin)
+    if key not in _CLASS_CACHE:
+        _CLASS_CACHE[key] = type(tag + base.__name__, (mixin, base), {"_tome_mixin": mixin, "_tome_base": base})
+    module.__class__ = _CLASS_CACHE[key]
+
+
+def apply_duplicate_patch(model, layer_to_duplicate, quantity):
+    """videomae.py:154-157."""
+    for i in range(layer_to_duplicate, layer_to_duplicate + quantity - 1):
+        model.model.blocks.insert(index=i, module=copy.deepcopy(model.model.blocks[i]))
+        _swap(model.model.blocks[i], ToMeDuplicateBlockMixin, "ToMeDuplicate")
+
+
+def make_tome_class(transformer_class):
+    """videomae.py:160-169: per-forward reset of the shared state."""
+    class ToMeVisionTransformer(transformer_class):
+        def forward(self, *args, **kwdargs) -> torch.Tensor:
+            self._tome_info["r"] = parse_r(len(self.model.blocks), self.r)
+            self._tome_info["size"] = None
+            self._tome_info["log_size"] = None
+            self._tome_info["source"] = None
+            return super().forward(*args, **kwdargs)
+
+    return ToMeVisionTransformer
+
+
+def apply_patch(model_wrapper, trace_source: bool = False, prop_attn: bool = False, mode: str = 'merge',
+                head_aggregation: str = 'mean', threshold: float = 0.0, verbose: bool = False):
+    """videomae.py:172-214.  After this, set ``model_wrapper.r`` (int | (r, inflect) | list)."""
+    model = model_wrapper.model
+    if not getattr(model_wrapper.__class__, "_tome_wrapper", False):
+        cls = make_tome_class(model_wrapper.__class__)
+        cls._tome_wrapper = True
+        model_wrapper.__class__ = cls
+    model_wrapper.r = 0
+    model_wrapper._tome_info = {
+        "r": model_wrapper.r,
+        "size": None,
+        "log_size": None,
+        "source": None,
+        "trace_source": trace_source,
+        "prop_attn": prop_attn,
+        "verbose": verbose,
+        "class_token": False,
+        "distill_token": False,
+        "mode": mode,
+        "head_aggregation": head_aggregation,
+        "threshold": threshold,
+    }
+    if hasattr(model, "dist_token") and model.dist_token is not None:
+        model_wrapper._tome_info["distill_token"] = True     # (the reference has a typo here: videomae.py:195-196)
+
+    if mode in ['merge', 'random_merge']:
+        reduction_function = videomae_merge
+    elif mode in ['drop', 'random_drop']:
+        reduction_function = videomae_drop
+    elif mode in ['hybrid']:
+        reduction_function = videomae_hybrid
+    else:
+        raise ValueError(f"unknown ToMe mode {mode!r}")
+
+    for module in model.modules():
+        if _is_block(module):
+            if getattr(module.__class__, "_tome_mixin", None) is not ToMeDuplicateBlockMixin:
+                _swap(module, ToMeBlockMixin, "ToMe")
+            module._tome_info = model_wrapper._tome_info
+            module.reduction_function = reduction_function
+        elif _is_attention(module):
+            _swap(module, ToMeAttentionMixin, "ToMe")
