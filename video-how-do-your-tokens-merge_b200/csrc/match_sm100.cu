@@ -1,11 +1,417 @@
-// Kernel 1, tensor-core form (tcgen05 / TMEM / TMA).  Placeholder until the sm_100a
-// pipeline lands: reports "unsupported" so TOME_MATCH_AUTO routes to the exact kernel.
+// Kernel 1, tensor-core form: fused key-normalise + A.B^T cosine similarity + masked row
+// max/argmax on tcgen05 / TMEM fed by TMA.  Replaces tome/merge.py:51-64 of the reference
+// (norm, div, strided bmm that materialises a (bm, N/2, N/2) score tensor, two masked
+// fills, max).  The score matrix never leaves TMEM.
+//
+// Three launches:
+//   1. split_rows_kernel   one warp per token: fp64 sum of squares -> fp32 norm ->
+//                          mhat = fp32(x / norm), written as hi (tf32-exact top bits) and
+//                          lo = mhat - hi (exact) in the A-rows-then-B-rows layout TMA reads.
+//   2. match_tc_kernel     per (128 A rows) x (BN <= 256 B rows) x batch tile: TMA
+//                          (SWIZZLE_128B, K-major) -> 3xTF32 tcgen05.mma
+//                          (hi.hi + hi.lo + lo.hi, fp32 accumulate in TMEM) ->
+//                          epilogue straight out of TMEM: per row the approximate max and
+//                          every column within a proven error window of it (<= KCAND, else
+//                          "overflow").
+//   3. refine_rows_kernel  per A row: exact canonical score (fp64 FMA over mhat, same order
+//                          as match_exact.cu) of the few candidates -> node_max / node_idx.
+// The tensor-core pass only prunes; every reported bit comes from step 3, so this path and
+// the exact kernel agree bit for bit (tests/test_kernels_gpu.py).
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace tome {
-size_t match_tc_workspace(int, int, int) { return 0; }
-bool match_tc_supported(int, int, int, int, const View&, const void*) { return false; }
-int launch_match_tc(const void*, int, int, int, int, const View&, int, int, float*, int*, void*, size_t, cudaStream_t) {
-  return set_error(TOME_ERR_UNSUPPORTED, "tome_match: tcgen05 path not built");
+
+constexpr int TC_BM = 128;        // A rows per tile == UMMA M == TMEM lanes
+constexpr int TC_BK = 32;         // fp32 per k-block == one 128-byte swizzle row
+constexpr int TC_UK = 8;          // UMMA K for kind::tf32
+constexpr int KCAND = 4;          // candidates kept per (row, column tile)
+constexpr int TC_THREADS = 192;   // warp0 TMA, warp1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr int CNT_OVERFLOW = 255;
+
+struct TcParams {
+  int bm, n, na, nb, cm, cls, distill;
+  int BN, n_ct, stages, num_kb, tmem_cols;
+  int rows_total;          // bm * n : row offset of the "lo" half of the split buffer
+  float window;            // 2 * error bound of the tensor-core pass
+  float* tile_max;         // (bm, na, n_ct)
+  int* tile_cnt;           // (bm, na, n_ct)
+  int* tile_cand;          // (bm, na, n_ct, KCAND)
+};
+
+// ---------------------------------------------------------------------------------------------
+// 1. normalise + hi/lo split
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) split_rows_kernel(const T* __restrict__ metric, View v, int bm, int n, int cm,
+                                                         float* __restrict__ split) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= bm * n) return;
+  const int b = warp / n, t = warp - b * n, na = na_of(n);
+  const T* src = metric + v.batch_offset(b) + (long long)t * v.sn;
+  double ss = 0.0;
+  for (int k = lane; k < cm; k += 32) {
+    const double x = (double)ld_as_float(src + k);
+    ss = fma(x, x, ss);
+  }
+  ss = warp_sum(ss);
+  const float norm = (float)sqrt(ss);
+  const int row = (t & 1) ? na + (t >> 1) : (t >> 1);
+  float* hi = split + ((long long)b * n + row) * cm;
+  float* lo = hi + (long long)bm * n * cm;
+  for (int k = lane; k < cm; k += 32) {
+    const float m = __fdiv_rn(ld_as_float(src + k), norm);
+    const float h = __uint_as_float(__float_as_uint(m) & 0xFFFFE000u);
+    hi[k] = h;
+    lo[k] = m - h;     // exact: fewer than 24 significant bits remain
+  }
 }
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers (sm_100a)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a lost arrival must abort the kernel (trap), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
+//   [0,14) start address >> 4, [16,30) LBO >> 4 (unused for swizzled K-major),
+//   [32,46) SBO >> 4 = 1024 B between 8-row groups, [46,48) version = 1, [61,64) layout = 2.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. TMA -> tcgen05 -> TMEM epilogue
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jt = blockIdx.x, it = blockIdx.y, b = blockIdx.z;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024-byte alignment
+  const uint32_t a_bytes = TC_BM * 128u, b_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t stage_bytes = 2u * (a_bytes + b_bytes);
+  const uint32_t bars = base + (uint32_t)p.stages * stage_bytes;    // full[stages] | empty[stages] | tmem_full | tmem_ptr
+  const uint32_t bar_full = bars, bar_empty = bars + 8u * p.stages, bar_tmem = bars + 16u * p.stages;
+  const uint32_t tmem_slot = bar_tmem + 8u;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
+    mbar_init(bar_tmem, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int row_a = b * p.n + it * TC_BM;               // rows of the split buffer (hi half)
+  const int row_b = b * p.n + p.na + jt * p.BN;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int s = kb % p.stages;
+        mbar_wait(bar_empty + 8u * s, ((kb / p.stages) & 1) ^ 1);
+        const uint32_t st = base + (uint32_t)s * stage_bytes, full = bar_full + 8u * s;
+        mbar_expect_tx(full, stage_bytes);
+        tma_load_2d(st, &map_a, kb * TC_BK, row_a, full);                                   // A hi
+        tma_load_2d(st + a_bytes, &map_a, kb * TC_BK, row_a + p.rows_total, full);          // A lo
+        tma_load_2d(st + 2u * a_bytes, &map_b, kb * TC_BK, row_b, full);                    // B hi
+        tma_load_2d(st + 2u * a_bytes + b_bytes, &map_b, kb * TC_BK, row_b + p.rows_total, full);  // B lo
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B tf32, both K-major, N = BN, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int s = kb % p.stages;
+        mbar_wait(bar_full + 8u * s, (kb / p.stages) & 1);
+        tc_fence_after();
+        const uint32_t st = base + (uint32_t)s * stage_bytes;
+        const uint64_t a_hi = make_sw128_desc(st), a_lo = make_sw128_desc(st + a_bytes);
+        const uint64_t b_hi = make_sw128_desc(st + 2u * a_bytes), b_lo = make_sw128_desc(st + 2u * a_bytes + b_bytes);
+#pragma unroll
+        for (int k = 0; k < TC_BK / TC_UK; ++k) {
+          const uint64_t adv = (uint64_t)((k * TC_UK * 4) >> 4);     // +32 bytes inside the swizzle row
+          umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+          umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+          umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
+        }
+        umma_commit(bar_empty + 8u * s);      // frees the stage when these MMAs retire
+      }
+      umma_commit(bar_tmem);                  // accumulator complete
+    }
+  } else {
+    // ---- epilogue: thread <-> TMEM lane <-> A row ------------------------------------------
+    const int q = warp & 3;                    // TMEM lane quarter this warp may touch
+    const int row = q * 32 + lane, i = it * TC_BM + row;
+    const int j0 = jt * p.BN;
+    mbar_wait(bar_tmem, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float m = -INFINITY;
+    bool has_nan = false;
+    for (int c = 0; c < p.BN; c += 16) {
+      float v[16];
+      tmem_ld16(taddr + (uint32_t)c, v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int j = j0 + c + e;
+        const bool valid = j < p.nb && !(p.distill && j == 0);
+        has_nan |= valid && (v[e] != v[e]);
+        m = fmaxf(m, valid ? v[e] : -INFINITY);
+      }
+    }
+    const float thr = m - p.window;
+    int cnt = 0, cand[KCAND];
+#pragma unroll
+    for (int e = 0; e < KCAND; ++e) cand[e] = 0;
+    for (int c = 0; c < p.BN; c += 16) {
+      float v[16];
+      tmem_ld16(taddr + (uint32_t)c, v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int j = j0 + c + e;
+        const bool valid = j < p.nb && !(p.distill && j == 0);
+        if (valid && v[e] >= thr) {
+#pragma unroll
+          for (int s = 0; s < KCAND; ++s) if (cnt == s) cand[s] = j;
+          ++cnt;
+        }
+      }
+    }
+    if (i < p.na) {
+      const long long o = ((long long)b * p.na + i) * p.n_ct + jt;
+      p.tile_max[o] = m;
+      p.tile_cnt[o] = (has_nan || cnt > KCAND) ? CNT_OVERFLOW : cnt;
+#pragma unroll
+      for (int s = 0; s < KCAND; ++s) p.tile_cand[o * KCAND + s] = cand[s];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. exact refine: canonical fp64 score of the surviving candidates
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float exact_score(const float* __restrict__ ah, const float* __restrict__ al,
+                                             const float* __restrict__ bh, const float* __restrict__ bl, int cm) {
+  double acc = 0.0;
+  for (int k = 0; k < cm; ++k) acc = fma((double)(ah[k] + al[k]), (double)(bh[k] + bl[k]), acc);
+  return (float)acc;
+}
+
+__global__ void __launch_bounds__(128) refine_rows_kernel(const float* __restrict__ split, TcParams p,
+                                                          float* __restrict__ node_max, int* __restrict__ node_idx) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.bm * p.na) return;
+  const int b = t / p.na, i = t - b * p.na;
+  if (p.cls && i == 0) { node_max[t] = -INFINITY; node_idx[t] = 0; return; }
+  const long long lo_off = (long long)p.rows_total * p.cm;
+  const float* ah = split + ((long long)b * p.n + i) * p.cm;
+  const float* bbase = split + ((long long)b * p.n + p.na) * p.cm;
+  const long long o = (long long)t * p.n_ct;
+  float big = -INFINITY;
+  for (int c = 0; c < p.n_ct; ++c) big = fmaxf(big, p.tile_max[o + c]);
+  const float thr = big - p.window;
+  unsigned long long best = 0ull;
+  for (int c = 0; c < p.n_ct; ++c) {
+    const int cnt = p.tile_cnt[o + c];
+    if (cnt == CNT_OVERFLOW) {            // too many near-ties (or NaN): score the whole column tile exactly
+      const int je = min(p.nb, (c + 1) * p.BN);
+      for (int j = c * p.BN; j < je; ++j) {
+        const float s = (p.distill && j == 0) ? -INFINITY
+                                              : exact_score(ah, ah + lo_off, bbase + (long long)j * p.cm, bbase + (long long)j * p.cm + lo_off, p.cm);
+        const unsigned long long k = pack_best(s, j);
+        best = k > best ? k : best;
+      }
+    } else if (p.tile_max[o + c] >= thr) {
+      for (int s = 0; s < cnt; ++s) {
+        const int j = p.tile_cand[(o + c) * KCAND + s];
+        const float sc = exact_score(ah, ah + lo_off, bbase + (long long)j * p.cm, bbase + (long long)j * p.cm + lo_off, p.cm);
+        const unsigned long long k = pack_best(sc, j);
+        best = k > best ? k : best;
+      }
+    }
+  }
+  node_max[t] = key_to_float((uint32_t)(best >> 32));
+  node_idx[t] = (int)(0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull));
+}
+
+// ---------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------
+static void tc_geometry(int n, int cm, TcParams& p) {
+  p.n = n; p.na = na_of(n); p.nb = nb_of(n); p.cm = cm;
+  p.n_ct = (p.nb + 255) / 256;
+  int bn = (p.nb + p.n_ct - 1) / p.n_ct;
+  bn = (bn + 15) & ~15;
+  p.BN = bn < 16 ? 16 : bn;
+  p.num_kb = (cm + TC_BK - 1) / TC_BK;
+  const int stage_bytes = 2 * (TC_BM + p.BN) * 128;
+  int st = (200 * 1024) / stage_bytes;
+  st = st > 4 ? 4 : st;
+  p.stages = st > p.num_kb ? p.num_kb : st;
+  p.tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+  // error bound of hi.hi + hi.lo + lo.hi with fp32 accumulation on unit vectors:
+  // 3 * 2^-20 (dropped lo.lo + truncated lo) + (3 cm / 8) accumulations * 2^-22, with margin
+  const float eps = 4e-6f + 2e-7f * (float)cm;
+  p.window = 2.0f * eps;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t match_tc_workspace(int bm, int n, int cm) {
+  TcParams p;
+  tc_geometry(n, cm, p);
+  const size_t rows = (size_t)bm * p.na * p.n_ct;
+  return align256((size_t)2 * bm * n * cm * sizeof(float)) + align256(rows * 4) + align256(rows * 4) + align256(rows * 4 * KCAND);
+}
+
+bool match_tc_supported(int dtype, int bm, int n, int cm, const View& v, const void* metric) {
+  (void)metric; (void)v;
+  if (dtype != TOME_F32 && dtype != TOME_BF16) return false;
+  if (cm % 4 != 0 || cm < 4 || cm > 4096) return false;          // TMA: 16-byte row pitch
+  if (n < 2 || (long long)bm * n * 2 > 0x7fffffffLL) return false;
+  return true;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, float* base, int rows, int cm, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(TOME_ERR_CUDA, "tome_match: cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cm, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cm * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(TOME_ERR_CUDA, "tome_match: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return TOME_OK;
+}
+
+int launch_match_tc(const void* metric, int dtype, int bm, int n, int cm, const View& v, int cls, int distill,
+                    float* node_max, int* node_idx, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (ws_bytes < match_tc_workspace(bm, n, cm))
+    return set_error(TOME_ERR_WORKSPACE, "tome_match: workspace %zu < %zu bytes", ws_bytes, match_tc_workspace(bm, n, cm));
+  TcParams p;
+  tc_geometry(n, cm, p);
+  p.bm = bm; p.cls = cls; p.distill = distill; p.rows_total = bm * n;
+  char* w = (char*)ws;
+  float* split = (float*)w;                      w += align256((size_t)2 * bm * n * cm * sizeof(float));
+  const size_t rows = (size_t)bm * p.na * p.n_ct;
+  p.tile_max = (float*)w;                        w += align256(rows * 4);
+  p.tile_cnt = (int*)w;                          w += align256(rows * 4);
+  p.tile_cand = (int*)w;
+
+  const int blocks = (int)(((long long)bm * n * 32 + 255) / 256);
+  if (dtype == TOME_F32) split_rows_kernel<float><<<blocks, 256, 0, st>>>((const float*)metric, v, bm, n, cm, split);
+  else split_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)metric, v, bm, n, cm, split);
+  TOME_LAUNCH_CHECK("split_rows_kernel");
+
+  alignas(64) CUtensorMap map_a, map_b;
+  int rc = make_map(&map_a, split, 2 * bm * n, cm, TC_BM);
+  if (rc) return rc;
+  rc = make_map(&map_b, split, 2 * bm * n, cm, p.BN);
+  if (rc) return rc;
+  const size_t smem = (size_t)p.stages * 2 * (TC_BM + p.BN) * 128 + 16 * p.stages + 16 + 1024;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    TOME_CUDA(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    smem_set = 227 * 1024;
+  }
+  dim3 grid(p.n_ct, (p.na + TC_BM - 1) / TC_BM, bm);
+  match_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+  TOME_LAUNCH_CHECK("match_tc_kernel");
+  const int total = bm * p.na;
+  refine_rows_kernel<<<(total + 127) / 128, 128, 0, st>>>(split, p, node_max, node_idx);
+  TOME_LAUNCH_CHECK("refine_rows_kernel");
+  return TOME_OK;
+}
+
 }  // namespace tome

@@ -178,8 +178,8 @@ def device_check(device: Optional[int] = None) -> None:
     _check(lib.tome_device_check(dev), lib)
 
 
-def match(metric: torch.Tensor, class_token=False, distill_token=False, algo: int = MATCH_AUTO
-          ) -> Tuple[torch.Tensor, torch.Tensor]:
+def match(metric: torch.Tensor, class_token=False, distill_token=False, algo: int = MATCH_AUTO,
+          _return_workspace: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """Kernel 1.  metric (bm, n, cm) fp32/bf16 -> node_max (bm, na) f32, node_idx (bm, na) i32."""
     lib = load_library()
     _require_cuda(metric, "metric")
@@ -200,6 +200,8 @@ def match(metric: torch.Tensor, class_token=False, distill_token=False, algo: in
         _check(lib.tome_match(metric.data_ptr(), _dtype_code(metric), bm, n, cm, ctypes.byref(view),
                               int(bool(class_token)), int(bool(distill_token)), algo, node_max.data_ptr(),
                               node_idx.data_ptr(), ws.data_ptr(), ws_bytes, _stream(metric)), lib)
+    if _return_workspace:          # tests only: lets them inspect the tensor-core pass's pruning
+        return node_max, node_idx, ws
     return node_max, node_idx
 
 
