@@ -30,17 +30,22 @@ def _oracle_plan(case, metric):
     return O.bipartite_soft_matching(metric, case["r"], bool(case.get("cls")), bool(case.get("distill")))
 
 
-ALGOS = [1, 2]
+ALGOS = ["exact", "tc", "tc_streamed", "tc_nct5"]
 
 
 @pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("case", ALL_ACTIVE, ids=lambda c: c["name"])
-def test_match_bit_exact_vs_oracle(native, case, algo):
+def test_match_bit_exact_vs_oracle(native, case, algo, monkeypatch):
+    """Every variant of kernel 1 gives the oracle's bits: fp64 SIMT tiles; tcgen05 with the
+    exact refine fused in the epilogue (operands resident in smem); tcgen05 with streamed
+    k-blocks + separate refine kernel; and a different column tiling."""
     metric, _, _ = util.case_arrays(case)
     cls, dis = bool(case.get("cls")), bool(case.get("distill"))
-    if algo == 2 and case["cm"] % 32 != 0:
-        pytest.skip("tcgen05 path needs cm % 32 == 0 (AUTO routes these to the exact kernel)")
-    nm, ni = native.match(_dev(metric), cls, dis, algo=algo)
+    if algo == "tc_streamed":
+        monkeypatch.setenv("TOME_TC_NO_FUSED_REFINE", "1")
+    if algo == "tc_nct5":
+        monkeypatch.setenv("TOME_TC_NCT", "5")
+    nm, ni = native.match(_dev(metric), cls, dis, algo=1 if algo == "exact" else 2)
     onm, oni = O.match(metric, cls, dis)
     np.testing.assert_array_equal(ni.cpu().numpy(), oni)
     np.testing.assert_array_equal(nm.cpu().numpy().view(np.uint32), onm.view(np.uint32))
@@ -261,7 +266,7 @@ def _tc_layout(bm, n, cm):
 
 
 @pytest.mark.parametrize("name", ["config1_m1p", "config1_m1", "tokens_tsf", "vivit_layer0"])
-def test_tensor_core_pass_really_prunes(native, name):
+def test_tensor_core_pass_really_prunes(native, name, monkeypatch):
     """The exact refine would hide a broken MMA pass (everything would overflow into the
     fallback).  Check the tcgen05 pass itself: its per-tile maxima equal the true maxima to
     within the error window, almost every tile keeps exactly one candidate, none overflow."""
@@ -269,6 +274,7 @@ def test_tensor_core_pass_really_prunes(native, name):
     metric, _, _ = util.case_arrays(case)
     cls = bool(case.get("cls"))
     bm, n, cm = metric.shape
+    monkeypatch.setenv("TOME_TC_NO_FUSED_REFINE", "1")      # the streamed path leaves its pruning record in the workspace
     nm, ni, ws = native.match(_dev(metric), cls, False, algo=2, _return_workspace=True)
     na, nb, n_ct, bn, rows, off_max, off_cnt = _tc_layout(bm, n, cm)
     tile_max = ws[off_max:off_max + rows * 4].view(torch.float32).view(bm, na, n_ct).cpu().numpy()

@@ -18,6 +18,7 @@
 // The tensor-core pass only prunes; every reported bit comes from step 3, so this path and
 // the exact kernel agree bit for bit (tests/test_kernels_gpu.py).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -35,9 +36,14 @@ struct TcParams {
   int BN, n_ct, stages, num_kb, tmem_cols;
   int rows_total;          // bm * n : row offset of the "lo" half of the split buffer
   float window;            // 2 * error bound of the tensor-core pass
-  float* tile_max;         // (bm, na, n_ct)
+  float* tile_max;         // (bm, na, n_ct)            [streamed-K path only]
   int* tile_cnt;           // (bm, na, n_ct)
   int* tile_cand;          // (bm, na, n_ct, KCAND)
+  int resident;            // all k-blocks stay in shared memory -> exact refine fused in the epilogue
+  unsigned long long* keys;  // (bm, na) packed (score key, ~column), atomicMax across column tiles
+  int* strip_count;        // (bm, row tiles) arrivals; last column tile of a strip decodes the keys
+  float* node_max;         // (bm, na)
+  int* node_idx;           // (bm, na)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -45,10 +51,16 @@ struct TcParams {
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) split_rows_kernel(const T* __restrict__ metric, View v, int bm, int n, int cm,
-                                                         float* __restrict__ split) {
+                                                         float* __restrict__ split,
+                                                         unsigned long long* __restrict__ keys,
+                                                         int* __restrict__ strip_count, int n_strips) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= bm * n) return;
   const int b = warp / n, t = warp - b * n, na = na_of(n);
+  if (lane == 0) {
+    if (!(t & 1)) keys[(long long)b * na + (t >> 1)] = 0ull;
+    if (warp < n_strips) strip_count[warp] = 0;
+  }
   const T* src = metric + v.batch_offset(b) + (long long)t * v.sn;
   double ss = 0.0;
   for (int k = lane; k < cm; k += 32) {
@@ -124,6 +136,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// byte offset of the 16-byte chunk holding k..k+3 (k % 4 == 0, k < 32) of row r in a SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t sw128_off(int r, int k) { return (uint32_t)r * 128u + ((((uint32_t)k >> 2) ^ ((uint32_t)r & 7u)) << 4); }
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
 //   [0,14) start address >> 4, [16,30) LBO >> 4 (unused for swizzled K-major),
 //   [32,46) SBO >> 4 = 1024 B between 8-row groups, [46,48) version = 1, [61,64) layout = 2.
@@ -139,6 +173,27 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // ---------------------------------------------------------------------------------------------
 // 2. TMA -> tcgen05 -> TMEM epilogue
 // ---------------------------------------------------------------------------------------------
+// Exact canonical score of (tile row r, tile column c) from the SWIZZLE_128B stage buffers
+// (all k-blocks resident): same fp64 FMA order as match_exact.cu / refine_rows_kernel.
+__device__ __forceinline__ float exact_from_smem(uint32_t base, uint32_t stage_bytes, uint32_t a_bytes, uint32_t b_bytes,
+                                                 int num_kb, int r, int c) {
+  double acc = 0.0;
+  for (int kb = 0; kb < num_kb; ++kb) {
+    const uint32_t st = base + (uint32_t)kb * stage_bytes;
+#pragma unroll
+    for (int k = 0; k < TC_BK; k += 4) {
+      const uint32_t oa = sw128_off(r, k), ob = sw128_off(c, k);
+      const float4 ah = lds128(st + oa), al = lds128(st + a_bytes + oa);
+      const float4 bh = lds128(st + 2u * a_bytes + ob), bl = lds128(st + 2u * a_bytes + b_bytes + ob);
+      acc = fma((double)(ah.x + al.x), (double)(bh.x + bl.x), acc);
+      acc = fma((double)(ah.y + al.y), (double)(bh.y + bl.y), acc);
+      acc = fma((double)(ah.z + al.z), (double)(bh.z + bl.z), acc);
+      acc = fma((double)(ah.w + al.w), (double)(bh.w + bl.w), acc);
+    }
+  }
+  return (float)acc;
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -153,6 +208,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const uint32_t tmem_slot = bar_tmem + 8u;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+  volatile int* is_last_ptr = reinterpret_cast<volatile int*>(gen_base + (tmem_slot + 4u - base));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
@@ -211,58 +267,123 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int q = warp & 3;                    // TMEM lane quarter this warp may touch
     const int row = q * 32 + lane, i = it * TC_BM + row;
     const int j0 = jt * p.BN;
+    const int ncol = min(p.BN, p.nb - j0);     // valid columns of this tile (>= 1)
+    const bool mask0 = p.distill && jt == 0;   // column 0 is the distillation token
     mbar_wait(bar_tmem, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    // pass 1: approximate row max over the valid columns
     float m = -INFINITY;
     bool has_nan = false;
-    for (int c = 0; c < p.BN; c += 16) {
+    int c = 0;
+    for (; c + 32 <= ncol; c += 32) {
+      float v[32];
+      tmem_ld32(taddr + (uint32_t)c, v);
+      if (mask0 && c == 0) v[0] = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) { has_nan |= (v[e] != v[e]); m = fmaxf(m, v[e]); }
+    }
+    for (; c < ncol; c += 16) {
       float v[16];
       tmem_ld16(taddr + (uint32_t)c, v);
+      if (mask0 && c == 0) v[0] = -INFINITY;
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        const int j = j0 + c + e;
-        const bool valid = j < p.nb && !(p.distill && j == 0);
-        has_nan |= valid && (v[e] != v[e]);
-        m = fmaxf(m, valid ? v[e] : -INFINITY);
+        const float x = (c + e < ncol) ? v[e] : -INFINITY;
+        has_nan |= (x != x); m = fmaxf(m, x);
       }
     }
+    // pass 2: every column within the error window of the max is a candidate
     const float thr = m - p.window;
     int cnt = 0, cand[KCAND];
 #pragma unroll
     for (int e = 0; e < KCAND; ++e) cand[e] = 0;
-    for (int c = 0; c < p.BN; c += 16) {
-      float v[16];
-      tmem_ld16(taddr + (uint32_t)c, v);
+    c = 0;
+    for (; c + 32 <= ncol; c += 32) {
+      float v[32];
+      tmem_ld32(taddr + (uint32_t)c, v);
+      if (mask0 && c == 0) v[0] = -INFINITY;
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int j = j0 + c + e;
-        const bool valid = j < p.nb && !(p.distill && j == 0);
-        if (valid && v[e] >= thr) {
+      for (int e = 0; e < 32; ++e)
+        if (v[e] >= thr) {
 #pragma unroll
-          for (int s = 0; s < KCAND; ++s) if (cnt == s) cand[s] = j;
+          for (int s = 0; s < KCAND; ++s) if (cnt == s) cand[s] = c + e;
           ++cnt;
         }
-      }
     }
-    if (i < p.na) {
-      const long long o = ((long long)b * p.na + i) * p.n_ct + jt;
-      p.tile_max[o] = m;
-      p.tile_cnt[o] = (has_nan || cnt > KCAND) ? CNT_OVERFLOW : cnt;
+    for (; c < ncol; c += 16) {
+      float v[16];
+      tmem_ld16(taddr + (uint32_t)c, v);
+      if (mask0 && c == 0) v[0] = -INFINITY;
 #pragma unroll
-      for (int s = 0; s < KCAND; ++s) p.tile_cand[o * KCAND + s] = cand[s];
+      for (int e = 0; e < 16; ++e)
+        if (c + e < ncol && v[e] >= thr) {
+#pragma unroll
+          for (int s = 0; s < KCAND; ++s) if (cnt == s) cand[s] = c + e;
+          ++cnt;
+        }
+    }
+    const bool overflow = has_nan || cnt > KCAND;
+    if (!p.resident) {
+      if (i < p.na) {
+        const long long o = ((long long)b * p.na + i) * p.n_ct + jt;
+        p.tile_max[o] = m;
+        p.tile_cnt[o] = overflow ? CNT_OVERFLOW : cnt;
+#pragma unroll
+        for (int s = 0; s < KCAND; ++s) p.tile_cand[o * KCAND + s] = j0 + cand[s];
+      }
+    } else if (i < p.na) {
+      // exact refine straight from the operand tiles still sitting in shared memory
+      for (int s = 0; s < p.num_kb; ++s) mbar_wait(bar_full + 8u * s, 0);     // acquire the TMA writes
+      unsigned long long best = 0ull;
+      if (p.cls && i == 0) {
+        best = pack_best(-INFINITY, 0);
+      } else if (overflow) {
+        for (int cc = 0; cc < ncol; ++cc) {
+          const float sc = (mask0 && cc == 0) ? -INFINITY : exact_from_smem(base, stage_bytes, a_bytes, b_bytes, p.num_kb, row, cc);
+          const unsigned long long k = pack_best(sc, j0 + cc);
+          best = k > best ? k : best;
+        }
+      } else {
+        for (int s = 0; s < cnt; ++s) {
+          const float sc = exact_from_smem(base, stage_bytes, a_bytes, b_bytes, p.num_kb, row, cand[s]);
+          const unsigned long long k = pack_best(sc, j0 + cand[s]);
+          best = k > best ? k : best;
+        }
+      }
+      atomicMax(p.keys + (long long)b * p.na + i, best);
     }
   }
   tc_fence_before();
+  if (p.resident) __threadfence();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
+  if (p.resident) {
+    // last column tile of this (batch, row strip) turns the packed keys into node_max / node_idx
+    if (threadIdx.x == 0) {
+      const int strip = b * gridDim.y + it;
+      const int old = atomicAdd(p.strip_count + strip, 1);
+      *is_last_ptr = (old == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (*is_last_ptr) {
+      __threadfence();
+      const int i = it * TC_BM + (int)threadIdx.x;
+      if (threadIdx.x < TC_BM && i < p.na) {
+        const long long o = (long long)b * p.na + i;
+        const unsigned long long k = __ldcg(p.keys + o);
+        p.node_max[o] = key_to_float((uint32_t)(k >> 32));
+        p.node_idx[o] = (int)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
-// 3. exact refine: canonical fp64 score of the surviving candidates
+// 3. exact refine (streamed-K path): canonical fp64 score of the surviving candidates
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float exact_score(const float* __restrict__ ah, const float* __restrict__ al,
                                              const float* __restrict__ bh, const float* __restrict__ bl, int cm) {
@@ -311,17 +432,28 @@ __global__ void __launch_bounds__(128) refine_rows_kernel(const float* __restric
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
-static void tc_geometry(int n, int cm, TcParams& p) {
-  p.n = n; p.na = na_of(n); p.nb = nb_of(n); p.cm = cm;
-  p.n_ct = (p.nb + 255) / 256;
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+static void tc_geometry(int bm, int n, int cm, TcParams& p) {
+  p.bm = bm; p.n = n; p.na = na_of(n); p.nb = nb_of(n); p.cm = cm;
+  p.num_kb = (cm + TC_BK - 1) / TC_BK;
+  int n_ct = (p.nb + 255) / 256;
+  const int forced = env_int("TOME_TC_NCT", 0);          // tuning knob (bench sweeps)
+  if (forced > 0) n_ct = forced > (p.nb + 15) / 16 ? (p.nb + 15) / 16 : forced;
+  if (n_ct < (p.nb + 255) / 256) n_ct = (p.nb + 255) / 256;
+  p.n_ct = n_ct;
   int bn = (p.nb + p.n_ct - 1) / p.n_ct;
   bn = (bn + 15) & ~15;
   p.BN = bn < 16 ? 16 : bn;
-  p.num_kb = (cm + TC_BK - 1) / TC_BK;
+  p.n_ct = (p.nb + p.BN - 1) / p.BN;
   const int stage_bytes = 2 * (TC_BM + p.BN) * 128;
-  int st = (200 * 1024) / stage_bytes;
+  int st = (216 * 1024) / stage_bytes;
   st = st > 4 ? 4 : st;
   p.stages = st > p.num_kb ? p.num_kb : st;
+  p.resident = (p.num_kb <= p.stages) && !env_int("TOME_TC_NO_FUSED_REFINE", 0);
   p.tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
   // error bound of hi.hi + hi.lo + lo.hi with fp32 accumulation on unit vectors:
   // 3 * 2^-20 (dropped lo.lo + truncated lo) + (3 cm / 8) accumulations * 2^-22, with margin
@@ -333,9 +465,11 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 size_t match_tc_workspace(int bm, int n, int cm) {
   TcParams p;
-  tc_geometry(n, cm, p);
+  tc_geometry(bm, n, cm, p);
   const size_t rows = (size_t)bm * p.na * p.n_ct;
-  return align256((size_t)2 * bm * n * cm * sizeof(float)) + align256(rows * 4) + align256(rows * 4) + align256(rows * 4 * KCAND);
+  const size_t strips = (size_t)bm * ((p.na + TC_BM - 1) / TC_BM);
+  return align256((size_t)2 * bm * n * cm * sizeof(float)) + align256(rows * 4) + align256(rows * 4) +
+         align256(rows * 4 * KCAND) + align256((size_t)bm * p.na * 8) + align256(strips * 4);
 }
 
 bool match_tc_supported(int dtype, int bm, int n, int cm, const View& v, const void* metric) {
@@ -380,18 +514,24 @@ int launch_match_tc(const void* metric, int dtype, int bm, int n, int cm, const 
   if (ws_bytes < match_tc_workspace(bm, n, cm))
     return set_error(TOME_ERR_WORKSPACE, "tome_match: workspace %zu < %zu bytes", ws_bytes, match_tc_workspace(bm, n, cm));
   TcParams p;
-  tc_geometry(n, cm, p);
-  p.bm = bm; p.cls = cls; p.distill = distill; p.rows_total = bm * n;
+  tc_geometry(bm, n, cm, p);
+  p.cls = cls; p.distill = distill; p.rows_total = bm * n;
+  p.node_max = node_max; p.node_idx = node_idx;
+  const int n_rt = (p.na + TC_BM - 1) / TC_BM;
   char* w = (char*)ws;
   float* split = (float*)w;                      w += align256((size_t)2 * bm * n * cm * sizeof(float));
   const size_t rows = (size_t)bm * p.na * p.n_ct;
   p.tile_max = (float*)w;                        w += align256(rows * 4);
   p.tile_cnt = (int*)w;                          w += align256(rows * 4);
-  p.tile_cand = (int*)w;
+  p.tile_cand = (int*)w;                         w += align256(rows * 4 * KCAND);
+  p.keys = (unsigned long long*)w;               w += align256((size_t)bm * p.na * 8);
+  p.strip_count = (int*)w;
 
   const int blocks = (int)(((long long)bm * n * 32 + 255) / 256);
-  if (dtype == TOME_F32) split_rows_kernel<float><<<blocks, 256, 0, st>>>((const float*)metric, v, bm, n, cm, split);
-  else split_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)metric, v, bm, n, cm, split);
+  if (dtype == TOME_F32)
+    split_rows_kernel<float><<<blocks, 256, 0, st>>>((const float*)metric, v, bm, n, cm, split, p.keys, p.strip_count, bm * n_rt);
+  else
+    split_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)metric, v, bm, n, cm, split, p.keys, p.strip_count, bm * n_rt);
   TOME_LAUNCH_CHECK("split_rows_kernel");
 
   alignas(64) CUtensorMap map_a, map_b;
@@ -400,17 +540,19 @@ int launch_match_tc(const void* metric, int dtype, int bm, int n, int cm, const 
   rc = make_map(&map_b, split, 2 * bm * n, cm, p.BN);
   if (rc) return rc;
   const size_t smem = (size_t)p.stages * 2 * (TC_BM + p.BN) * 128 + 16 * p.stages + 16 + 1024;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    TOME_CUDA(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    smem_set = 227 * 1024;
+  static bool smem_set = false;
+  if (!smem_set) {
+    TOME_CUDA(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    smem_set = true;
   }
-  dim3 grid(p.n_ct, (p.na + TC_BM - 1) / TC_BM, bm);
+  dim3 grid(p.n_ct, n_rt, bm);
   match_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
   TOME_LAUNCH_CHECK("match_tc_kernel");
-  const int total = bm * p.na;
-  refine_rows_kernel<<<(total + 127) / 128, 128, 0, st>>>(split, p, node_max, node_idx);
-  TOME_LAUNCH_CHECK("refine_rows_kernel");
+  if (!p.resident) {
+    const int total = bm * p.na;
+    refine_rows_kernel<<<(total + 127) / 128, 128, 0, st>>>(split, p, node_max, node_idx);
+    TOME_LAUNCH_CHECK("refine_rows_kernel");
+  }
   return TOME_OK;
 }
 

@@ -95,7 +95,14 @@ class PatchEmbed(nn.Module):                            # builder:138-160
     def forward(self, x):
         B, C, T, H, W = x.shape
         assert (H, W) == self.img_size, f"Input image size ({H}*{W}) doesn't match model {self.img_size}."
-        return self.proj(x).flatten(2).transpose(1, 2)
+        if self.training or not x.is_cuda:
+            return self.proj(x).flatten(2).transpose(1, 2)
+        # kernel == stride, so the tubelet conv is one GEMM over non-overlapping patches: cuDNN's
+        # implicit-GEMM Conv3d ran as an fp32 SIMT kernel (22% of the forward, profiles/r01_launches_v1).
+        tt, (ph, pw) = self.tubelet_size, self.patch_size
+        x = x.reshape(B, C, T // tt, tt, H // ph, ph, W // pw, pw).permute(0, 2, 4, 6, 1, 3, 5, 7)
+        x = x.reshape(B, (T // tt) * (H // ph) * (W // pw), C * tt * ph * pw)
+        return F.linear(x, self.proj.weight.reshape(self.proj.out_channels, -1), self.proj.bias)
 
 
 def get_sinusoid_encoding_table(n_position, d_hid):    # builder:164-174
