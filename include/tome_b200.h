@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 2
+#define TOME_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define TOME_API __attribute__((visibility("default")))
@@ -84,6 +84,8 @@ typedef struct tome_plan {
   int32_t* a_map;         /* (bm, na)   >=0: position in unm_idx; <0: -(dst+1)            */
   int32_t* b_off;         /* (bm, nb+1) CSR offsets into b_src                            */
   int32_t* b_src;         /* (bm, r)    A tokens grouped by dst, ascending k inside       */
+  int32_t* b_head;        /* (bm, nb, 4) per B token {count, source 0, source 1, CSR begin}: one
+                                        16-byte lookup names up to two merged A tokens      */
 } tome_plan;
 
 /* Tensor addressing: element (b, t, c) of a (bm, tokens, c) tensor lives at
@@ -128,7 +130,7 @@ TOME_API int tome_rowmax(const float* scores, int32_t bm, int32_t na, int32_t nb
 /* --- kernel 2: select (merge.py:65-73) -----------------------------------------------
  * Stable descending rank of node_max (ties: lower A index first; NaN above +inf), then
  * src = first r, unm = rest (ascending when class_token), dst = node_idx[src]; also fills
- * a_map / b_off / b_src.  plan->r must already be the effective r (> 0). */
+ * a_map / b_off / b_src / b_head.  plan->r must already be the effective r (> 0). */
 TOME_API size_t tome_select_workspace_bytes(int32_t bm, int32_t n);
 TOME_API int tome_select(const tome_plan* plan, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -38,8 +38,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_ctypes_structs_match_header_layout():
     from tome import _native
-    # tome_plan: 5 int32 (+4 pad) then 8 pointers; tome_view: 3 int64 + int32 (+pad)
-    assert ctypes.sizeof(_native.TomePlanC) == 24 + 8 * 8
+    # tome_plan: 5 int32 (+4 pad) then 9 pointers; tome_view: 3 int64 + int32 (+pad)
+    assert ctypes.sizeof(_native.TomePlanC) == 24 + 9 * 8
     assert _native.TomePlanC.node_max.offset == 24
     assert ctypes.sizeof(_native.TomeViewC) == 32
 

@@ -71,6 +71,9 @@ def test_select_bit_exact_vs_oracle(native, case):
         for j in range(plan.nb):
             want = [plan.src_idx[b, k] for k in range(plan.r) if plan.dst_idx[b, k] == j]
             assert list(b_src[b, b_off[b, j]:b_off[b, j + 1]]) == want
+            head = dp.b_head[b, j].tolist()
+            assert head[0] == len(want) and head[3] == b_off[b, j]
+            assert head[1] == (want[0] if want else 0) and head[2] == (want[1] if len(want) > 1 else 0)
 
 
 @pytest.mark.parametrize("case", ALL_ACTIVE, ids=lambda c: c["name"])

@@ -10,6 +10,7 @@
 // separately, no FMA contraction), and writes the merged row, its new size and log(size)
 // once.  HBM traffic = read x once + write x' once (kernel 3).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -19,7 +20,7 @@ struct MergeArgs {
   int bm, n, r, distill, c, mode, hybrid;
   float thr;
   const float* node_max;
-  const int *unm_idx, *b_off, *b_src;
+  const int *unm_idx, *b_off, *b_src, *b_head;
   const void* x;
   View xv;
   const float* size_in;
@@ -184,6 +185,217 @@ __global__ void __launch_bounds__(256) merge_rows_kernel(MergeArgs a) {
   }
 }
 
+// ---- fast path: 16-byte vectors -------------------------------------------------------------
+// Most output rows are plain copies (kept tokens of size 1, B tokens nobody merged into):
+// they stay packed in registers and go straight back out.  Only rows that need arithmetic
+// ((x*s)/s with s != 1, or a reduction over merged sources) are unpacked to fp32.
+template <typename T> struct Pack;
+template <> struct Pack<float> {
+  static constexpr int E = 4;
+  static __device__ __forceinline__ void unpack(const uint4& v, float (&f)[4]) {
+    f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+  }
+  static __device__ __forceinline__ uint4 pack(const float (&f)[4]) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+  }
+};
+template <> struct Pack<__nv_bfloat16> {
+  static constexpr int E = 8;
+  static __device__ __forceinline__ void unpack(const uint4& v, float (&f)[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+  }
+  static __device__ __forceinline__ uint4 pack(const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+// One-shot gather, one output row per warp.
+//
+// What this kernel is bound by is not bandwidth but the length of its dependent chains: a
+// plain device memcpy of the same bytes takes 6.1 us, and so does this kernel when no row
+// has merged sources -- but the first versions took 11-13 us because the ~7% of warps that
+// reduce merged sources chased plan lookup -> row -> lookup -> row chains (up to 7 dependent
+// global round trips) and every other CTA slot waited behind them
+// (profiles/r01_merge_notes.md).  Hence:
+//   * hop 1 is ONE 16-byte lookup (plan.b_head = {count, source 0, source 1, CSR begin});
+//   * hop 2 requests the token's own row (registers) and up to two source rows (cp.async into
+//     a per-warp shared-memory slot pair, so they cost no registers) all at once;
+//   * further sources (rare) go through the same slot pair two at a time: one hop per pair.
+// Rows nobody merged into -- the vast majority -- are copies out of packed registers.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+template <typename T, int NV, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) merge_gather_kernel(MergeArgs a) {
+  constexpr int E = Pack<T>::E;
+  constexpr bool kCopyIfNoSrc = sizeof(T) == 2;   // bf16: round(fp32(x*s)/s) == x -> kept tokens are plain copies
+  constexpr int SLOT = NV * 32;                   // 16-byte groups per staged row
+  extern __shared__ uint4 stage[];                // WARPS x 2 x SLOT
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // grid = (batch, row blocks), row blocks walked from the END of the output: CTAs are dispatched in
+  // blockIdx order, so the B-token rows (the only ones that may carry a reduction) start first and
+  // the tail of the kernel is made of plain copies
+  const int o = ((int)gridDim.y - 1 - (int)blockIdx.y) * WARPS + warp;
+  const int b = blockIdx.x;
+  const int n = a.n, na = na_of(n), nb = nb_of(n), r = a.r, nu = na - r, nout = n - r;
+  if (o >= nout) return;
+  const T* xb = reinterpret_cast<const T*>(a.x) + a.xv.batch_offset(b);
+  const int nvec = a.c / E;
+  const bool wavg = a.mode == TOME_MODE_WAVG;
+
+  // hop 1: which input row is this, and what merges into it
+  bool is_unm; int idx;
+  slot_to_token(o, nu, a.distill, is_unm, idx);
+  int tok;
+  int4 head = make_int4(0, 0, 0, 0);
+  if (is_unm) tok = 2 * __ldg(a.unm_idx + (long long)b * nu + idx);
+  else {
+    tok = 2 * idx + 1;
+    if (a.mode != TOME_MODE_DROP) head = __ldg(reinterpret_cast<const int4*>(a.b_head) + (long long)b * nb + idx);
+  }
+  const int nsrc = head.x;
+  uint4* mine = stage + (size_t)warp * 2 * SLOT;
+  // hop 2: own row into registers, first two source rows into shared memory
+  uint4 raw[NV];
+  {
+    const uint4* row = reinterpret_cast<const uint4*>(xb + (long long)tok * a.xv.sn);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { const int i = v * 32 + lane; if (i < nvec) raw[v] = ld_stream_u4(row + i); }
+    if (nsrc > 0) {
+      const uint4* s0 = reinterpret_cast<const uint4*>(xb + (long long)(2 * head.y) * a.xv.sn);
+      const uint4* s1 = reinterpret_cast<const uint4*>(xb + (long long)(2 * head.z) * a.xv.sn);
+      for (int i = lane; i < nvec; i += 32) {
+        cp_async16(mine + i, s0 + i);
+        if (nsrc > 1) cp_async16(mine + SLOT + i, s1 + i);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  }
+  const float* szb = a.size_in ? a.size_in + (long long)b * n : nullptr;
+  float S = (wavg && szb) ? __ldg(szb + tok) : 1.0f;
+  uint4* orow = reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.out) + a.ov.batch_offset(b) + (long long)o * a.ov.sn);
+
+  if (nsrc == 0) {
+    if (kCopyIfNoSrc || S == 1.0f) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) { const int i = v * 32 + lane; if (i < nvec) orow[i] = raw[v]; }
+    } else {
+      // kept token of size s != 1: the reference really computes (x*s)/s  (merge.py:365-368)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int i = v * 32 + lane;
+        if (i < nvec) {
+          float f[E];
+          Pack<T>::unpack(raw[v], f);
+#pragma unroll
+          for (int e = 0; e < E; ++e) f[e] = __fdiv_rn(__fmul_rn(f[e], S), S);
+          orow[i] = Pack<T>::pack(f);
+        }
+      }
+    }
+  } else {
+    const int* bsrc = a.b_src + (long long)b * r + head.w;
+    // lane k looks up source k (token, size, hybrid keep flag); k = 0, 1 come from the head word
+    int k_ai = lane == 0 ? head.y : head.z;
+    if (lane >= 2 && lane < nsrc) k_ai = __ldg(bsrc + lane);
+    float k_s = 1.0f;
+    bool k_keep = true;
+    if (lane < nsrc) {
+      if (wavg && szb) k_s = __ldg(szb + 2 * k_ai);
+      if (a.hybrid) k_keep = (__ldg(a.node_max + (long long)b * na + k_ai) >= a.thr);     // merge.py:326
+    }
+    bool keep_self = __all_sync(0xffffffffu, k_keep);
+    if (a.hybrid)
+      for (int k = 32; k < nsrc; ++k) keep_self &= (__ldg(a.node_max + (long long)b * na + __ldg(bsrc + k)) >= a.thr);
+    const float s_self = keep_self ? S : __fmul_rn(S, 0.0f);
+    float Ssum = s_self;
+    for (int k = 0; k < nsrc; ++k) {
+      const float s = k < 32 ? __shfl_sync(0xffffffffu, k_s, k & 31) : ((wavg && szb) ? __ldg(szb + 2 * __ldg(bsrc + k)) : 1.0f);
+      if (wavg) Ssum = __fadd_rn(Ssum, s);
+    }
+    const float cnt = (float)(1 + nsrc);
+    // own row -> fp32 accumulators, kept packed-width: NV x E floats would be 24+ registers, so the
+    // accumulation runs per 16-byte group and parks partial sums back in `raw` (as fp32 bit patterns
+    // for fp32 rows; bf16 rows re-round only at the very end, see below)
+    // pass over source pairs: slots hold sources [k0, k0 + 2)
+    float accv[NV][E];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      Pack<T>::unpack(raw[v], accv[v]);
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        if (wavg) accv[v][e] = __fmul_rn(accv[v][e], S);
+        if (!keep_self) accv[v][e] = __fmul_rn(accv[v][e], 0.0f);
+      }
+    }
+    for (int k0 = 0; k0 < nsrc; k0 += 2) {
+      if (k0 > 0) {                              // rare: refill the slot pair with the next two sources
+        __syncwarp();
+        const int a0 = k0 < 32 ? __shfl_sync(0xffffffffu, k_ai, k0 & 31) : __ldg(bsrc + k0);
+        const int a1 = (k0 + 1 < nsrc) ? ((k0 + 1) < 32 ? __shfl_sync(0xffffffffu, k_ai, (k0 + 1) & 31) : __ldg(bsrc + k0 + 1)) : a0;
+        const uint4* s0 = reinterpret_cast<const uint4*>(xb + (long long)(2 * a0) * a.xv.sn);
+        const uint4* s1 = reinterpret_cast<const uint4*>(xb + (long long)(2 * a1) * a.xv.sn);
+        for (int i = lane; i < nvec; i += 32) {
+          cp_async16(mine + i, s0 + i);
+          if (k0 + 1 < nsrc) cp_async16(mine + SLOT + i, s1 + i);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int k = k0 + kk;
+        if (k < nsrc) {
+          const float s = k < 32 ? __shfl_sync(0xffffffffu, k_s, k & 31) : ((wavg && szb) ? __ldg(szb + 2 * __ldg(bsrc + k)) : 1.0f);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            const int i = v * 32 + lane;
+            if (i < nvec) {
+              float f[E];
+              Pack<T>::unpack(mine[kk * SLOT + i], f);
+#pragma unroll
+              for (int e = 0; e < E; ++e) {
+                if (a.mode == TOME_MODE_AMAX) accv[v][e] = nanmax(accv[v][e], f[e]);
+                else if (wavg) accv[v][e] = __fadd_rn(accv[v][e], __fmul_rn(f[e], s));
+                else accv[v][e] = __fadd_rn(accv[v][e], f[e]);
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int i = v * 32 + lane;
+      if (i < nvec) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if (wavg) accv[v][e] = __fdiv_rn(accv[v][e], Ssum);
+          else if (a.mode == TOME_MODE_MEAN) accv[v][e] = __fdiv_rn(accv[v][e], cnt);
+        }
+        orow[i] = Pack<T>::pack(accv[v]);
+      }
+    }
+    S = Ssum;
+  }
+  if (lane == 0) {
+    const long long so = (long long)b * nout + o;
+    const float So = wavg ? S : 1.0f;
+    if (a.size_out) a.size_out[so] = So;
+    if (a.logsize_out) a.logsize_out[so] = logf(So);
+  }
+}
+
 // merge_source with the implicit identity (merge.py:379-381): row of slot o is the OR of
 // one-hot rows, generated without reading anything but the plan.
 __global__ void __launch_bounds__(256) source_identity_kernel(MergeArgs a) {
@@ -241,20 +453,42 @@ __global__ void __launch_bounds__(256) unmerge_rows_kernel(const int* __restrict
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 static bool view_vec_ok(const View& v, int e) { return v.sbo % e == 0 && v.sbi % e == 0 && v.sn % e == 0; }
 
-template <typename T, int E>
-static int launch_merge_t(const MergeArgs& a, cudaStream_t st) {
+template <typename T>
+static int launch_merge_scalar(const MergeArgs& a, cudaStream_t st) {
   const int nout = a.n - a.r;
   dim3 grid((nout + 7) / 8, a.bm);
-  const int per_nv = 32 * E;
-  const int nv = (a.c + per_nv - 1) / per_nv;
-  if (nv <= 1) merge_rows_kernel<T, E, 1><<<grid, 256, 0, st>>>(a);
-  else if (nv <= 2) merge_rows_kernel<T, E, 2><<<grid, 256, 0, st>>>(a);
-  else if (nv <= 3) merge_rows_kernel<T, E, 3><<<grid, 256, 0, st>>>(a);
-  else if (nv <= 4) merge_rows_kernel<T, E, 4><<<grid, 256, 0, st>>>(a);
-  else if (nv <= 6) merge_rows_kernel<T, E, 6><<<grid, 256, 0, st>>>(a);
-  else merge_rows_kernel<T, E, 8><<<grid, 256, 0, st>>>(a);
+  merge_rows_kernel<T, 1, 8><<<grid, 256, 0, st>>>(a);
   TOME_LAUNCH_CHECK("merge_rows_kernel");
   return TOME_OK;
+}
+
+template <typename T, int NV, int WARPS, int MINB>
+static int launch_gather_inst(const MergeArgs& a, cudaStream_t st) {
+  const int nout = a.n - a.r;
+  dim3 grid(a.bm, (nout + WARPS - 1) / WARPS);
+  if (grid.y > 65535) return set_error(TOME_ERR_UNSUPPORTED, "tome_merge: too many output rows per batch element (%d)", nout);
+  const size_t smem = (size_t)WARPS * 2 * NV * 32 * sizeof(uint4);
+  static bool attr = false;
+  if (!attr && smem > 48 * 1024) {
+    TOME_CUDA(cudaFuncSetAttribute(merge_gather_kernel<T, NV, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  merge_gather_kernel<T, NV, WARPS, MINB><<<grid, WARPS * 32, smem, st>>>(a);
+  TOME_LAUNCH_CHECK("merge_gather_kernel");
+  return TOME_OK;
+}
+
+template <typename T, int WARPS, int MINB>
+static int launch_merge_gather(const MergeArgs& a, cudaStream_t st) {
+  constexpr int E = Pack<T>::E;
+  const int nv = (a.c / E + 31) / 32;
+  if (nv <= 1) return launch_gather_inst<T, 1, WARPS, MINB>(a, st);
+  if (nv <= 2) return launch_gather_inst<T, 2, WARPS, MINB>(a, st);
+  if (nv <= 3) return launch_gather_inst<T, 3, WARPS, MINB>(a, st);
+  if (nv <= 4) return launch_gather_inst<T, 4, WARPS, MINB>(a, st);
+  if (nv <= 6) return launch_gather_inst<T, 6, WARPS, MINB>(a, st);
+  if (nv <= 8) return launch_gather_inst<T, 8, WARPS, MINB>(a, st);
+  return launch_merge_scalar<T>(a, st);     // very wide rows: chunked generic kernel
 }
 
 int launch_merge(const tome_plan* plan, const void* x, int dtype, int c, const View& xv, const float* size_in,
@@ -263,14 +497,22 @@ int launch_merge(const tome_plan* plan, const void* x, int dtype, int c, const V
   MergeArgs a;
   a.bm = plan->bm; a.n = plan->n; a.r = plan->r; a.distill = plan->distill_token; a.c = c; a.mode = mode;
   a.hybrid = (thr == thr) ? 1 : 0; a.thr = thr; a.node_max = plan->node_max;
-  a.unm_idx = plan->unm_idx; a.b_off = plan->b_off; a.b_src = plan->b_src;
+  a.unm_idx = plan->unm_idx; a.b_off = plan->b_off; a.b_src = plan->b_src; a.b_head = plan->b_head;
   a.x = x; a.xv = xv; a.size_in = size_in; a.out = out; a.ov = ov; a.size_out = size_out; a.logsize_out = logsize_out;
+  const int variant = getenv("TOME_MERGE_VARIANT") ? atoi(getenv("TOME_MERGE_VARIANT")) : 0;   // tuning knob
   if (dtype == TOME_F32) {
     const bool vec = c % 4 == 0 && aligned16(x) && aligned16(out) && view_vec_ok(xv, 4) && view_vec_ok(ov, 4);
-    return vec ? launch_merge_t<float, 4>(a, st) : launch_merge_t<float, 1>(a, st);
+    if (!vec) return launch_merge_scalar<float>(a, st);
+    if (variant == 1) return launch_merge_gather<float, 8, 3>(a, st);
+    if (variant == 2) return launch_merge_gather<float, 8, 2>(a, st);
+    return launch_merge_gather<float, 4, 6>(a, st);
   } else if (dtype == TOME_BF16) {
     const bool vec = c % 8 == 0 && aligned16(x) && aligned16(out) && view_vec_ok(xv, 8) && view_vec_ok(ov, 8);
-    return vec ? launch_merge_t<__nv_bfloat16, 8>(a, st) : launch_merge_t<__nv_bfloat16, 1>(a, st);
+    if (!vec) return launch_merge_scalar<__nv_bfloat16>(a, st);
+    if (variant == 1) return launch_merge_gather<__nv_bfloat16, 4, 8>(a, st);
+    if (variant == 2) return launch_merge_gather<__nv_bfloat16, 8, 3>(a, st);
+    if (variant == 3) return launch_merge_gather<__nv_bfloat16, 8, 5>(a, st);
+    return launch_merge_gather<__nv_bfloat16, 8, 4>(a, st);
   }
   return set_error(TOME_ERR_DTYPE, "tome_merge: unsupported dtype %d", dtype);
 }
@@ -284,7 +526,7 @@ int launch_merge_source(const tome_plan* plan, const float* source, int n0, floa
   MergeArgs a{};
   a.bm = plan->bm; a.n = plan->n; a.r = plan->r; a.distill = plan->distill_token; a.c = plan->n;
   a.mode = TOME_MODE_AMAX; a.hybrid = (thr == thr) ? 1 : 0; a.thr = thr; a.node_max = plan->node_max;
-  a.unm_idx = plan->unm_idx; a.b_off = plan->b_off; a.b_src = plan->b_src; a.out = out;
+  a.unm_idx = plan->unm_idx; a.b_off = plan->b_off; a.b_src = plan->b_src; a.b_head = plan->b_head; a.out = out;
   dim3 grid((nout + 7) / 8, plan->bm);
   source_identity_kernel<<<grid, 256, 0, st>>>(a);
   TOME_LAUNCH_CHECK("source_identity_kernel");

@@ -14,7 +14,7 @@ struct PlanDev {
   int bm, n, r, cls, distill;
   const float* node_max;
   const int* node_idx;
-  int *src_idx, *unm_idx, *dst_idx, *a_map, *b_off, *b_src;
+  int *src_idx, *unm_idx, *dst_idx, *a_map, *b_off, *b_src, *b_head;
 };
 
 constexpr int RANK_ROWS = 32;     // A tokens ranked per CTA (one per lane)
@@ -136,6 +136,13 @@ __global__ void __launch_bounds__(1024) finish_kernel(PlanDev p, const int* __re
   int* boff = p.b_off + (long long)b * (nb + 1);
   for (int j = tid; j <= nb; j += 1024) boff[j] = off[j];
   for (int k = tid; k < r; k += 1024) p.b_src[br + k] = p.src_idx[br + lst[k]];
+  // per-B-token head {count, source 0, source 1, CSR begin}: one 16-byte lookup lets the merge
+  // kernel request the merged rows together with the token's own row
+  int4* bhead = reinterpret_cast<int4*>(p.b_head) + (long long)b * nb;
+  for (int j = tid; j < nb; j += 1024) {
+    const int s0 = off[j], c = off[j + 1] - s0;
+    bhead[j] = make_int4(c, c > 0 ? p.src_idx[br + lst[s0]] : 0, c > 1 ? p.src_idx[br + lst[s0 + 1]] : 0, s0);
+  }
 }
 
 size_t select_workspace(int bm, int n) { return (size_t)bm * na_of(n) * sizeof(int); }
@@ -146,7 +153,7 @@ int launch_select(const tome_plan* plan, void* ws, size_t ws_bytes, cudaStream_t
     return set_error(TOME_ERR_WORKSPACE, "tome_select: workspace %zu < %zu bytes", ws_bytes,
                      select_workspace(bm, n));
   PlanDev p{bm, n, r, plan->class_token, plan->distill_token, plan->node_max, plan->node_idx,
-            plan->src_idx, plan->unm_idx, plan->dst_idx, plan->a_map, plan->b_off, plan->b_src};
+            plan->src_idx, plan->unm_idx, plan->dst_idx, plan->a_map, plan->b_off, plan->b_src, plan->b_head};
   const size_t sm_rank = (size_t)na * sizeof(uint32_t);
   const size_t sm_fin = ((size_t)2 * nb + 1 + r) * sizeof(int);
   if (sm_rank > 200 * 1024 || sm_fin > 200 * 1024)

@@ -69,7 +69,7 @@ static int check_plan(const tome_plan* p, const char* who) {
   if (p->r <= 0 || p->r > (p->n - prot) / 2)
     return set_error(TOME_ERR_ARG, "%s: plan->r=%d is not an effective r for n=%d (max %d)", who, p->r, p->n, (p->n - prot) / 2);
   const bool unm_ok = p->unm_idx || (p->n + 1) / 2 == p->r;   // nothing is kept when r == na
-  if (!p->node_max || !p->node_idx || !p->src_idx || !unm_ok || !p->dst_idx || !p->a_map || !p->b_off || !p->b_src)
+  if (!p->node_max || !p->node_idx || !p->src_idx || !unm_ok || !p->dst_idx || !p->a_map || !p->b_off || !p->b_src || !p->b_head)
     return set_error(TOME_ERR_ARG, "%s: plan has NULL buffers", who);
   return TOME_OK;
 }

@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 4
 
 TOME_F32, TOME_BF16 = 0, 1
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -38,6 +38,7 @@ class TomePlanC(ctypes.Structure):
         ("node_max", ctypes.c_void_p), ("node_idx", ctypes.c_void_p),
         ("src_idx", ctypes.c_void_p), ("unm_idx", ctypes.c_void_p), ("dst_idx", ctypes.c_void_p),
         ("a_map", ctypes.c_void_p), ("b_off", ctypes.c_void_p), ("b_src", ctypes.c_void_p),
+        ("b_head", ctypes.c_void_p),
     ]
 
 
@@ -127,7 +128,7 @@ class DevicePlan:
     """Device buffers of one matching plan (mirrors ``tome_plan``)."""
 
     __slots__ = ("bm", "n", "r", "class_token", "distill_token", "node_max", "node_idx", "src_idx", "unm_idx",
-                 "dst_idx", "a_map", "b_off", "b_src", "_ints", "_c", "device")
+                 "dst_idx", "a_map", "b_off", "b_src", "b_head", "_ints", "_c", "device")
 
     def __init__(self, bm, n, r, class_token, distill_token, node_max, node_idx):
         na, nb = (n + 1) // 2, n // 2
@@ -135,7 +136,7 @@ class DevicePlan:
         self.class_token, self.distill_token = bool(class_token), bool(distill_token)
         self.node_max, self.node_idx = node_max, node_idx
         self.device = node_max.device
-        sizes = [bm * r, bm * (na - r), bm * r, bm * na, bm * (nb + 1), bm * r]
+        sizes = [bm * r, bm * (na - r), bm * r, bm * na, bm * (nb + 1), bm * r, bm * nb * 4]
         offs, tot = [], 0
         for s in sizes:
             offs.append(tot)
@@ -148,10 +149,11 @@ class DevicePlan:
         self.a_map = v[3].view(bm, na)
         self.b_off = v[4].view(bm, nb + 1)
         self.b_src = v[5].view(bm, r)
+        self.b_head = v[6].view(bm, nb, 4)
         self._c = TomePlanC(bm, n, r, int(self.class_token), int(self.distill_token),
                             node_max.data_ptr(), node_idx.data_ptr(), self.src_idx.data_ptr(),
                             self.unm_idx.data_ptr(), self.dst_idx.data_ptr(), self.a_map.data_ptr(),
-                            self.b_off.data_ptr(), self.b_src.data_ptr())
+                            self.b_off.data_ptr(), self.b_src.data_ptr(), self.b_head.data_ptr())
 
     @property
     def na(self):
