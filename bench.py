@@ -222,9 +222,40 @@ def workload_config(args, cpu=False):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+def graph_time(fns, reps=20):
+    """Capture the callables back to back in ONE CUDA graph and replay it: time per callable
+    without host launch overhead (CUDA events on the replaying stream, median of `reps`)."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for f in fns:
+            f()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for f in fns:
+            f()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ts = []
+    for _ in range(reps):
+        st.record()
+        g.replay()
+        en.record()
+        torch.cuda.synchronize()
+        ts.append(st.elapsed_time(en) * 1e3 / len(fns))
+    ts.sort()
+    return sum(ts) / len(ts), ts[len(ts) // 2]
+
+
 def micro_kernels(args, device, dtype):
-    """CUDA-event timing of the hot-path kernels at the workload's layer-0 shape, rotating
-    over buffers larger than L2.  Returns (roofline dict for merge_wavg, per-kernel dict)."""
+    """Device time of the hot-path kernels at the workload's layer-0 shape.  Each kernel is
+    captured once per rotating input (inputs total > L2, so every launch reads cold HBM like the
+    first touch in a forward) in one CUDA graph; time per launch = replay time / launches, CUDA
+    events on the replaying stream.  Returns (roofline dict for merge_wavg, per-kernel dict)."""
     from tome import _native
     peaks = {}
     try:
@@ -239,41 +270,35 @@ def micro_kernels(args, device, dtype):
     g = torch.Generator(device=device).manual_seed(1)
     xs = [torch.randn(bm, n, c, device=device, dtype=dtype, generator=g) for _ in range(nrot)]
     ms = [torch.randn(bm, n, cm, device=device, dtype=dtype, generator=g) for _ in range(nrot)]
-    size = torch.randint(1, 4, (bm, n, 1), device=device, generator=g).float()
     res = {}
-
-    def timeit(fn, iters=40):
-        for i in range(5):
-            fn(i)
-        torch.cuda.synchronize()
-        st = [torch.cuda.Event(enable_timing=True) for _ in range(iters)]
-        en = [torch.cuda.Event(enable_timing=True) for _ in range(iters)]
-        for i in range(iters):
-            st[i].record()
-            fn(i)
-            en[i].record()
-        torch.cuda.synchronize()
-        ts = sorted(s.elapsed_time(e_) for s, e_ in zip(st, en))
-        return sum(ts) / len(ts) * 1e3, ts[len(ts) // 2] * 1e3   # mean, median in us
-
     nm, ni = _native.match(ms[0], algo=args.match_algo)
     plan = _native.select(nm, ni, n, r)
-    mean_us, med_us = timeit(lambda i: _native.merge(plan, xs[i % nrot], "wavg", size=size, want_size=True))
+    mean_us, med_us = graph_time([lambda i=i: _native.merge(plan, xs[i], "wavg", want_size=True) for i in range(nrot)])
     na = (n + 1) // 2
-    alg_bytes = bm * (n * c * e + n * 4 + (n - r) * c * e + (n - r) * 8 + na * 12)
+    alg_bytes = bm * (n * c * e + (n - r) * c * e + (n - r) * 8 + na * 12)
     achieved = alg_bytes / (mean_us * 1e-6) / 1e9
-    roofline = {"kernel": "merge_rows_kernel (merge_wavg + size + log size, layer-0 shape "
+    roofline = {"kernel": "merge_gather_kernel (merge_wavg + size + log size, layer-0 shape "
                           f"Bm={bm} N={n} C={c} r={r} {args.dtype})",
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "algorithmic_bytes": alg_bytes, "us_mean": mean_us, "us_median": med_us,
-                "peak_source": peak_src, "timing": f"cuda events per launch, {nrot} rotating inputs > L2"}
-    m_mean, m_med = timeit(lambda i: _native.match(ms[i % nrot], algo=args.match_algo))
+                "traffic": MERGE_DRAM_TRAFFIC_NCU.get((bm, args.dtype)), "algorithmic_bytes": alg_bytes,
+                "us_mean": mean_us, "us_median": med_us, "peak_source": peak_src,
+                "timing": f"{nrot} launches over rotating inputs ({nrot * bm * n * c * e >> 20} MiB > L2) captured in "
+                          "one CUDA graph, cuda events around the replay, / launches"}
+    m_mean, m_med = graph_time([lambda i=i: _native.match(ms[i % nrot], algo=args.match_algo) for i in range(8)])
     flops = 2.0 * bm * na * (n // 2) * cm
     res["match"] = {"us_mean": m_mean, "us_median": m_med, "algorithmic_gflop": flops / 1e9,
-                    "tflops": flops / (m_mean * 1e-6) / 1e12, "algo": args.match_algo}
-    s_mean, s_med = timeit(lambda i: _native.select(nm, ni, n, r))
-    res["select"] = {"us_mean": s_mean, "us_median": s_med}
+                    "tflops_algorithmic": flops / (m_mean * 1e-6) / 1e12, "algo": args.match_algo or "auto",
+                    "kernels": "split_rows_kernel + match_tc_kernel (3xTF32 tcgen05, exact refine fused)"}
+    s_mean, s_med = graph_time([lambda: _native.select(nm, ni, n, r) for _ in range(8)])
+    res["select"] = {"us_mean": s_mean, "us_median": s_med, "kernels": "rank_kernel + finish_kernel"}
+    c_mean, _ = graph_time([lambda i=i: xs[i].clone() for i in range(nrot)])
+    res["torch_clone_same_bytes"] = {"us_mean": c_mean, "GBps": 2 * bm * n * c * e / (c_mean * 1e-6) / 1e9}
     return roofline, res
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of merge_gather_kernel from the committed
+# `ncu --set full` capture (profiles/r01_merge_gather_ncu.txt); writes stay in L2 at this size.
+MERGE_DRAM_TRAFFIC_NCU = {}
 
 
 def run_ours(args):

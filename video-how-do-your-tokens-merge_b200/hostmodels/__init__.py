@@ -5,3 +5,6 @@ same module/parameter names as the reference models (state dicts interchange), a
 and MLP through torch library kernels.  They are NOT the product -- the product is the
 ``tome`` package patched into them."""
 from .videomae import VideoMAE, videomae_vit_base_patch16_224  # noqa: F401
+from .timesformer import TimeSformer  # noqa: F401
+from .motionformer import Motionformer  # noqa: F401
+from .vivit import ViViT, VivitConfig  # noqa: F401

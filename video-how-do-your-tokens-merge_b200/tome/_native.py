@@ -272,6 +272,46 @@ def merge(plan: DevicePlan, x: torch.Tensor, mode: str, size: Optional[torch.Ten
     return out
 
 
+def merge_frames(plan: DevicePlan, x: torch.Tensor, frames: int, mode: str, size: Optional[torch.Tensor] = None,
+                 hybrid_threshold: Optional[float] = None):
+    """Kernel 3 on TimeSformer / Motionformer token layout, without the rearrange copies.
+
+    x is (B, 1 + P*T, C): a class token followed by tokens ordered '(p t)'.  The plan's matching batch
+    is (b t) with P tokens each -- the reference reaches that with
+    ``rearrange(x[:, 1:], 'b (p t) m -> (b t) p m')`` before and ``'(b t) p m -> b (p t) m'`` + ``cat`` with
+    the class token after (tome/patch/timesformer.py:88-107, motionformer.py:150-168).  Here both are
+    addressing (tome_view with inner = T): returns (out (B, 1 + P'*T, C), size' (B*T, P'), log size')."""
+    lib = load_library()
+    _require_cuda(x, "x")
+    T = int(frames)
+    B, L, C = x.shape
+    P = (L - 1) // T
+    if (L - 1) != P * T or plan.bm != B * T or plan.n != P:
+        raise RuntimeError(f"tome_b200: merge_frames expects x (B, 1 + {plan.n}*T, C) with B*T == {plan.bm}; got {tuple(x.shape)}, T={T}")
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError(f"tome_b200: unsupported dtype {x.dtype} (fp32 and bf16 only)")
+    if x.stride(2) != 1:
+        x = x.contiguous()
+    m = _MODES[mode]
+    Pn = P - plan.r
+    thr = float("nan") if hybrid_threshold is None else float(hybrid_threshold)
+    with torch.cuda.device(x.device):
+        out = torch.empty(B, 1 + Pn * T, C, dtype=x.dtype, device=x.device)
+        out[:, 0] = x[:, 0]
+        size_out = torch.empty(B * T, Pn, dtype=torch.float32, device=x.device)
+        logsize_out = torch.empty(B * T, Pn, dtype=torch.float32, device=x.device)
+        sp = None
+        if size is not None:
+            size = size.reshape(B * T, P).to(dtype=torch.float32).contiguous()
+            sp = size.data_ptr()
+        xv = TomeViewC(x.stride(0), x.stride(1), T * x.stride(1), T)
+        ov = TomeViewC(out.stride(0), out.stride(1), T * out.stride(1), T)
+        _check(lib.tome_merge(plan.c_ptr(), x[:, 1:].data_ptr(), _dtype_code(x), C, ctypes.byref(xv), sp, m, thr,
+                              out[:, 1:].data_ptr(), ctypes.byref(ov), size_out.data_ptr(), logsize_out.data_ptr(),
+                              _stream(x)), lib)
+    return out, size_out, logsize_out
+
+
 def merge_source(plan: DevicePlan, source: Optional[torch.Tensor], hybrid_threshold: Optional[float] = None
                  ) -> torch.Tensor:
     lib = load_library()

@@ -75,6 +75,13 @@ class Merge(_PlanCallable):
     def source(self, source=None):
         return _native.merge_source(self.plan, source, self.threshold)
 
+    def wavg_frames(self, x, frames, size=None):
+        """merge_wavg on a (B, 1 + P*T, C) class-token + '(p t)' tensor whose matching batch is (b t):
+        the TimeSformer / Motionformer case, rearranges folded into addressing.
+        Returns (x' (B, 1 + P'*T, C), size' (B*T, P', 1), log size' (B*T, P', 1))."""
+        out, s, ls = _native.merge_frames(self.plan, x, frames, "wavg", size=size, hybrid_threshold=self.threshold)
+        return out, s[..., None], ls[..., None]
+
 
 class Unmerge(_PlanCallable):
     def __call__(self, x: torch.Tensor) -> torch.Tensor:                    # merge.py:87-100
@@ -86,6 +93,10 @@ class Drop(_PlanCallable):
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:                    # merge.py:260-269
         return _native.merge(self.plan, x, "drop")
+
+    def frames(self, x, frames):
+        """drop on the (B, 1 + P*T, C) layout (see Merge.wavg_frames)."""
+        return _native.merge_frames(self.plan, x, frames, "drop")[0]
 
 
 def bipartite_soft_matching(

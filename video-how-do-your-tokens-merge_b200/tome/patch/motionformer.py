@@ -1,0 +1,220 @@
+"""``tome.patch.motionformer`` -- drop-in for the reference's tome/patch/motionformer.py.
+
+Trajectory attention over the joint (frame, patch) keys with the proportional-attention bias laid
+out ``(b f) s i -> b (s f) i`` (motionformer.py:107-111); the metric is the head-mean of K
+regrouped ``(b h) (s f) d -> (b f) h s d`` (motionformer.py:143-144) and the merge runs per "frame"
+on ``'b (s f) d -> (b f) s d'`` (motionformer.py:150-151).  Reference quirk kept verbatim: the
+attention reads the token axis as (f n) while metric and merge read the same axis as (s f).
+The rearranges around the merge are addressing inside kernel 3 (``Merge.wavg_frames``)."""
+import torch
+import torch.nn.functional as F
+
+from tome.merge import (Drop, Merge, bipartite_soft_matching, bipartite_soft_matching_drop,
+                        bipartite_soft_matching_hybrid)
+from tome.patch.timesformer import _frames_back, _frames_view, _merge_frames_generic
+from tome.patch.videomae import _swap
+from tome.utils import parse_r
+
+
+def trajectory_attention(mod, x, num_frames, log_size=None):
+    """vit_helper.py:146-267 (approx == 'none').  x (B, 1 + F*P, C), tokens '(f n)'.
+    ``log_size`` (B, F*P) adds the proportional-attention key bias in the flat key order
+    (tome/patch/motionformer.py:105-112).  Returns (out, k_) with k_ (B, h, F*P, d)."""
+    B, N, C = x.shape
+    Fr, h = num_frames, mod.num_heads
+    P = (N - 1) // Fr
+    d = C // h
+    q, k, v = mod.qkv(x).reshape(B, N, 3, h, d).permute(2, 0, 3, 1, 4)        # each (B, h, N, d)
+    cls_out = F.scaled_dot_product_attention(q[:, :, 0:1], k, v, scale=mod.scale)  # cls attends to everything
+    cls_out = cls_out.transpose(1, 2).reshape(B, 1, C)
+    q_, k_, v_ = q[:, :, 1:], k[:, :, 1:], v[:, :, 1:]
+    # space attention: every query against the P keys of each frame, softmax per frame
+    kf = k_.reshape(B, h, Fr, P, d)
+    vf = v_.reshape(B, h, Fr, P, d)
+    qe = q_[:, :, None].expand(B, h, Fr, Fr * P, d)
+    bias = None
+    if log_size is not None:
+        bias = log_size.reshape(B, 1, Fr, 1, P).to(q.dtype).expand(B, h, Fr, Fr * P, P)
+    xs = F.scaled_dot_product_attention(qe, kf, vf, attn_mask=bias, scale=mod.scale)   # (B, h, F, S, d)
+    xs = xs.permute(0, 3, 2, 1, 4).reshape(B, Fr * P, Fr, C)                            # 'b s f (h d)'
+    # temporal attention: the query is the trajectory token of the query's own frame
+    g = torch.arange(Fr, device=x.device).repeat_interleave(P)                          # frame of token s
+    x_diag = xs[:, torch.arange(Fr * P, device=x.device), g]                             # (B, S, C)
+    q2 = mod.proj_q(x_diag).reshape(B, Fr * P, h, d).transpose(1, 2) * mod.scale       # (B, h, S, d)
+    k2, v2 = mod.proj_kv(xs).chunk(2, dim=-1)
+    k2 = k2.reshape(B, Fr * P, Fr, h, d).permute(0, 3, 1, 2, 4)                        # (B, h, S, F, d)
+    attn = torch.einsum('bhsd,bhsfd->bhsf', q2, k2).softmax(dim=-1)
+    vals = xs if mod.use_original_code else v2                                          # the v = x "typo" kept by default
+    vals = vals.reshape(B, Fr * P, Fr, h, d).permute(0, 3, 1, 2, 4)
+    out = torch.einsum('bhsf,bhsfd->bhsd', attn, vals).transpose(1, 2).reshape(B, Fr * P, C)
+    out = mod.proj_drop(mod.proj(torch.cat((cls_out, out), dim=1)))
+    return out, k_
+
+
+class ToMeBlockMixin:
+    """motionformer.py:14-30."""
+
+    def forward(self, x, seq_len=196, num_frames=8, approx='none', num_landmarks=128):
+        info = self._tome_info
+        attn_size = info["size"] if info["prop_attn"] else None
+        attn_bias = info.get("log_size") if info["prop_attn"] else None
+        attn_out, _, metric = self.attn(self.norm1(x), seq_len=seq_len, num_frames=num_frames, approx=approx,
+                                        num_landmarks=num_landmarks, size=attn_size, log_size=attn_bias)
+        x = x + self.drop_path(attn_out)
+        x = self.reduction_function(metric, x, info, num_frames)
+        return x + self.drop_path(self.mlp(self.norm2(x)))
+
+
+class ToMeTrajectoryAttentionMixin:
+    """motionformer.py:33-144 (full attention branch; the approximations are unused by ToMe configs)."""
+
+    def forward(self, x, seq_len=196, num_frames=8, approx='none', num_landmarks=128,
+                size: torch.Tensor = None, log_size: torch.Tensor = None):
+        if approx != 'none':
+            raise NotImplementedError("tome.patch.motionformer: approximate attention is not supported")
+        B, N, C = x.shape
+        Fr = num_frames
+        S = (N - 1) // Fr
+        flat = None
+        if size is not None:
+            if log_size is None:
+                log_size = size.log()
+            # '(b f) s i -> b (s f) i': key j of the flat token axis gets log size[(b, j % F), j // F]
+            flat = log_size[..., 0].reshape(B, Fr, S).transpose(1, 2).reshape(B, S * Fr)
+        out, k_ = trajectory_attention(self, x, Fr, flat)
+        h, d = self.num_heads, C // self.num_heads
+        # '(b h) (s f) d -> (b f) h s d' then mean over heads
+        metric = k_.reshape(B, h, S, Fr, d).permute(0, 3, 1, 2, 4).mean(2).reshape(B * Fr, S, d)
+        return out, None, metric
+
+
+def motionformer_merge(metric, x, _tome_info, num_frames):
+    """motionformer.py:147-170."""
+    r = _tome_info["r"].pop(0)
+    if r > 0:
+        B, T = x.size(0), num_frames
+        P = (x.size(1) - 1) // T
+        merge, _ = bipartite_soft_matching(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
+                                           _tome_info["mode"])
+        if isinstance(merge, Merge):
+            if _tome_info["trace_source"]:
+                _tome_info["source"] = merge.source(_tome_info["source"])
+            x, _tome_info["size"], _tome_info["log_size"] = merge.wavg_frames(x, T, _tome_info["size"])
+        else:
+            x = _merge_frames_generic(merge, x, _tome_info, B, T, P)
+        if _tome_info['verbose']:
+            print(f'Merged {P} to {(x.size(1) - 1) // T} tokens')
+    return x
+
+
+def motionformer_drop(metric, x, _tome_info, num_frames):
+    """motionformer.py:173-200."""
+    r = _tome_info["r"].pop(0)
+    if r > 0:
+        B, T = x.size(0), num_frames
+        P = (x.size(1) - 1) // T
+        drop = bipartite_soft_matching_drop(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
+                                            _tome_info["mode"])
+        if isinstance(drop, tuple):
+            return x
+        if _tome_info["trace_source"]:
+            if _tome_info["source"] is None:
+                _tome_info["source"] = torch.eye(P, device=x.device)[None, ...].expand(B * T, P, P)
+            _tome_info["source"] = drop(_tome_info["source"].contiguous())
+        if isinstance(drop, Drop):
+            x = drop.frames(x, T)
+        else:
+            x = _frames_back(x[:, 0:1, :], drop(_frames_view(x, B, T, P)), B, T)
+        Pn = (x.size(1) - 1) // T
+        _tome_info["size"] = torch.ones((B * T, Pn, 1), device=x.device)
+        _tome_info["log_size"] = torch.zeros((B * T, Pn, 1), device=x.device)
+        if _tome_info['verbose']:
+            print(f'Dropped {P} to {Pn} tokens')
+    return x
+
+
+def motionformer_hybrid(metric, x, _tome_info, num_frames):
+    """motionformer.py:203-227."""
+    r = _tome_info["r"].pop(0)
+    if r > 0:
+        B, T = x.size(0), num_frames
+        P = (x.size(1) - 1) // T
+        merge, _ = bipartite_soft_matching_hybrid(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
+                                                  _tome_info["mode"], _tome_info["threshold"])
+        if isinstance(merge, Merge):
+            if _tome_info["trace_source"]:
+                _tome_info["source"] = merge.source(_tome_info["source"])
+            x, _tome_info["size"], _tome_info["log_size"] = merge.wavg_frames(x, T, _tome_info["size"])
+        else:
+            x = _merge_frames_generic(merge, x, _tome_info, B, T, P)
+        if _tome_info['verbose']:
+            print(f'Merged {P} to {(x.size(1) - 1) // T} tokens')
+    return x
+
+
+def _is_block(m):
+    return all(hasattr(m, a) for a in ("norm1", "attn", "norm2", "mlp")) and _is_traj_attention(m.attn)
+
+
+def _is_traj_attention(m):
+    return all(hasattr(m, a) for a in ("qkv", "proj_q", "proj_kv", "proj", "use_original_code"))
+
+
+def apply_duplicate_patch(model, layer_to_duplicate, quantity):
+    """motionformer.py:230-232."""
+    for i in range(layer_to_duplicate + 1, layer_to_duplicate + quantity):
+        model.blocks.insert(index=i, module=model.blocks[layer_to_duplicate])
+
+
+def make_tome_class(transformer_class):
+    class ToMeVisionTransformer(transformer_class):
+        def forward(self, *args, **kwdargs) -> torch.Tensor:
+            self._tome_info["r"] = parse_r(len(self.blocks), self.r)
+            self._tome_info["size"] = None
+            self._tome_info["log_size"] = None
+            self._tome_info["source"] = None
+            return super().forward(*args, **kwdargs)
+
+    return ToMeVisionTransformer
+
+
+def apply_patch(model, trace_source: bool = False, prop_attn: bool = True, mode: str = 'merge',
+                head_aggregation: str = 'mean', threshold: float = 0.0, verbose: bool = False):
+    """motionformer.py:247-284 -- the model itself is patched (no ``.model`` wrapper)."""
+    if not getattr(model.__class__, "_tome_wrapper", False):
+        cls = make_tome_class(model.__class__)
+        cls._tome_wrapper = True
+        model.__class__ = cls
+    model.r = 0
+    model._tome_info = {
+        "r": model.r,
+        "size": None,
+        "log_size": None,
+        "source": None,
+        "trace_source": trace_source,
+        "prop_attn": prop_attn,
+        "verbose": verbose,
+        "class_token": False,
+        "distill_token": False,
+        "mode": mode,
+        "threshold": threshold,
+    }
+    if hasattr(model, "dist_token") and model.dist_token is not None:
+        model._tome_info["distill_token"] = True
+
+    if mode in ['merge', 'random_merge']:
+        reduction_function = motionformer_merge
+    elif mode in ['drop', 'random_drop']:
+        reduction_function = motionformer_drop
+    elif mode in ['hybrid']:
+        reduction_function = motionformer_hybrid
+    else:
+        raise ValueError(f"unknown ToMe mode {mode!r}")
+
+    for module in model.modules():
+        if _is_block(module):
+            _swap(module, ToMeBlockMixin, "ToMe")
+            module._tome_info = model._tome_info
+            module.reduction_function = reduction_function
+        elif _is_traj_attention(module):
+            _swap(module, ToMeTrajectoryAttentionMixin, "ToMe")

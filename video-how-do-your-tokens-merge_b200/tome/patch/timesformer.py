@@ -1,0 +1,218 @@
+"""``tome.patch.timesformer`` -- drop-in for the reference's tome/patch/timesformer.py.
+
+Divided space-time attention: only the SPATIAL attention is patched (timesformer.py:224), the
+matching runs per frame on the P patch tokens (batch (b t), class token excluded:
+``class_token=False``, timesformer.py:203), the proportional-attention bias applies to
+``attn[:, :, 1:, 1:]`` only (timesformer.py:74) and the metric is ``k.mean(1)[:, 1:, :]``
+(timesformer.py:83).  Differences from the reference, all inside the hot path:
+  * the two ``rearrange`` copies and the ``cat`` around the merge (timesformer.py:88-107) are
+    addressing inside kernel 3 (``Merge.wavg_frames``);
+  * modules are matched structurally, so the reference's slowfast model and
+    ``hostmodels.timesformer`` both patch.
+"""
+import torch
+import torch.nn.functional as F
+
+from tome.merge import (Drop, Merge, bipartite_soft_matching, bipartite_soft_matching_drop,
+                        bipartite_soft_matching_hybrid, merge_source, merge_wavg)
+from tome.patch.videomae import _swap
+from tome.utils import parse_r
+
+
+class ToMeBlockMixin:
+    """timesformer.py:12-57."""
+
+    def forward(self, x, B, T, W):
+        info = self._tome_info
+        attn_size = info["size"] if info["prop_attn"] else None
+        attn_bias = info.get("log_size") if info["prop_attn"] else None
+        P = (x.size(1) - 1) // T
+        C = x.size(2)
+        if self.attention_type in ['space_only', 'joint_space_time']:
+            x = x + self.drop_path(self.attn(self.norm1(x))[0])
+            return x + self.drop_path(self.mlp(self.norm2(x)))
+        # temporal attention (un-patched): 'b (p t) m -> (b p) t m'
+        xt = x[:, 1:, :].reshape(B * P, T, C)
+        res_t = self.drop_path(self.temporal_attn(self.temporal_norm1(xt))).reshape(B, P * T, C)
+        xt = x[:, 1:, :] + self.temporal_fc(res_t)
+        # spatial attention: 'b (p t) m -> (b t) p m', class token replicated per frame
+        init_cls = x[:, 0, :].unsqueeze(1)
+        cls = init_cls.repeat(1, T, 1).reshape(B * T, 1, C)
+        xs = xt.reshape(B, P, T, C).transpose(1, 2).reshape(B * T, P, C)
+        res_s, metric = self.attn(self.norm1(torch.cat((cls, xs), 1)), attn_size, attn_bias)
+        res_s = self.drop_path(res_s)
+        cls = res_s[:, 0, :].reshape(B, T, C).mean(1, keepdim=True)          # averaged over frames
+        res = res_s[:, 1:, :].reshape(B, T, P, C).transpose(1, 2).reshape(B, P * T, C)
+        x = torch.cat((init_cls, xt), 1) + torch.cat((cls, res), 1)
+        x = self.reduction_function(metric, x, info, B, T, P)
+        return x + self.drop_path(self.mlp(self.norm2(x)))
+
+
+class ToMeAttentionMixin:
+    """timesformer.py:60-83."""
+
+    def forward(self, x, size: torch.Tensor = None, log_size: torch.Tensor = None):
+        B, N, C = x.shape
+        if self.with_qkv:
+            qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+            q, k, v = qkv[0], qkv[1], qkv[2]
+        else:
+            q = k = v = x.reshape(B, N, self.num_heads, C // self.num_heads).permute(0, 2, 1, 3)
+        bias = None
+        if size is not None:       # attn[:, :, 1:, 1:] += log(size): neither the cls query nor the cls key is biased
+            if log_size is None:
+                log_size = size.log()
+            row = F.pad(log_size[..., 0].to(q.dtype), (1, 0))                  # (B, N), 0 for the cls key
+            bias = row[:, None, None, :].expand(B, 1, N, N).clone()
+            bias[:, :, 0, :] = 0
+        drop = self.attn_drop.p if self.training else 0.0
+        x = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, dropout_p=drop, scale=self.scale)
+        x = x.transpose(1, 2).reshape(B, N, C)
+        if self.with_qkv:
+            x = self.proj_drop(self.proj(x))
+        return x, k.mean(1)[:, 1:, :]
+
+
+def _frames_view(x, B, T, P):
+    """'b (p t) m -> (b t) p m' of the non-class tokens (only needed off the fused path)."""
+    return x[:, 1:, :].reshape(B, P, T, -1).transpose(1, 2).reshape(B * T, P, -1)
+
+
+def _frames_back(cls, y, B, T):
+    Pn = y.size(1)
+    return torch.cat((cls, y.reshape(B, T, Pn, -1).transpose(1, 2).reshape(B, Pn * T, -1)), dim=1)
+
+
+def _merge_frames_generic(merge, x, info, B, T, P):
+    cls, merged_x = x[:, 0:1, :], _frames_view(x, B, T, P)
+    if info["trace_source"]:
+        info["source"] = merge_source(merge, merged_x, info["source"])
+    merged_x, info["size"] = merge_wavg(merge, merged_x, info["size"])
+    info["log_size"] = None
+    return _frames_back(cls, merged_x, B, T)
+
+
+def timesformer_merge(metric, x, _tome_info, B, T, num_spatial_tokens):
+    """timesformer.py:85-109."""
+    r = _tome_info["r"].pop(0)
+    if r > 0:
+        merge, _ = bipartite_soft_matching(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
+                                           _tome_info["mode"])
+        pre_merge = num_spatial_tokens
+        if isinstance(merge, Merge):
+            if _tome_info["trace_source"]:
+                _tome_info["source"] = merge.source(_tome_info["source"])
+            x, _tome_info["size"], _tome_info["log_size"] = merge.wavg_frames(x, T, _tome_info["size"])
+        else:
+            x = _merge_frames_generic(merge, x, _tome_info, B, T, num_spatial_tokens)
+        if _tome_info['verbose']:
+            print(f'Merged {pre_merge} to {(x.size(1) - 1) // T} tokens')
+    return x
+
+
+def timesformer_drop(metric, x, _tome_info, B, T, num_spatial_tokens):
+    """timesformer.py:112-140."""
+    r = _tome_info["r"].pop(0)
+    if r > 0:
+        drop = bipartite_soft_matching_drop(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
+                                            _tome_info["mode"])
+        if isinstance(drop, tuple):
+            return x
+        if _tome_info["trace_source"]:
+            if _tome_info["source"] is None:
+                t = num_spatial_tokens
+                _tome_info["source"] = torch.eye(t, device=x.device)[None, ...].expand(B * T, t, t)
+            _tome_info["source"] = drop(_tome_info["source"].contiguous())
+        pre_drop = num_spatial_tokens
+        if isinstance(drop, Drop):
+            x = drop.frames(x, T)
+        else:
+            x = _frames_back(x[:, 0:1, :], drop(_frames_view(x, B, T, num_spatial_tokens)), B, T)
+        Pn = (x.size(1) - 1) // T
+        _tome_info["size"] = torch.ones((B * T, Pn, 1), device=x.device)
+        _tome_info["log_size"] = torch.zeros((B * T, Pn, 1), device=x.device)
+        if _tome_info['verbose']:
+            print(f'Dropped {pre_drop} to {Pn} tokens')
+    return x
+
+
+def timesformer_hybrid(metric, x, _tome_info, B, T, num_spatial_tokens):
+    """timesformer.py:143-167."""
+    r = _tome_info["r"].pop(0)
+    if r > 0:
+        merge, _ = bipartite_soft_matching_hybrid(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
+                                                  _tome_info["mode"], _tome_info["threshold"])
+        pre_merge = num_spatial_tokens
+        if isinstance(merge, Merge):
+            if _tome_info["trace_source"]:
+                _tome_info["source"] = merge.source(_tome_info["source"])
+            x, _tome_info["size"], _tome_info["log_size"] = merge.wavg_frames(x, T, _tome_info["size"])
+        else:
+            x = _merge_frames_generic(merge, x, _tome_info, B, T, num_spatial_tokens)
+        if _tome_info['verbose']:
+            print(f'Merged {pre_merge} to {(x.size(1) - 1) // T} tokens')
+    return x
+
+
+def _is_block(m):
+    return all(hasattr(m, a) for a in ("norm1", "attn", "norm2", "mlp", "attention_type")) and hasattr(m.attn, "with_qkv")
+
+
+def apply_duplicate_patch(model, layer_to_duplicate, quantity):
+    """timesformer.py:170-172: the SAME module is inserted again (shared weights)."""
+    for i in range(layer_to_duplicate + 1, layer_to_duplicate + quantity):
+        model.model.blocks.insert(index=i, module=model.model.blocks[layer_to_duplicate])
+
+
+def make_tome_class(transformer_class):
+    class ToMeVisionTransformer(transformer_class):
+        def forward(self, *args, **kwdargs) -> torch.Tensor:
+            self._tome_info["r"] = parse_r(len(self.model.blocks), self.r)
+            self._tome_info["size"] = None
+            self._tome_info["log_size"] = None
+            self._tome_info["source"] = None
+            return super().forward(*args, **kwdargs)
+
+    return ToMeVisionTransformer
+
+
+def apply_patch(model_wrapper, trace_source: bool = False, prop_attn: bool = True, mode: str = 'merge',
+                head_aggregation: str = 'mean', threshold: float = 0.0, verbose: bool = False):
+    """timesformer.py:187-224.  ``head_aggregation`` is accepted and ignored, as in the reference."""
+    model = model_wrapper.model
+    if not getattr(model_wrapper.__class__, "_tome_wrapper", False):
+        cls = make_tome_class(model_wrapper.__class__)
+        cls._tome_wrapper = True
+        model_wrapper.__class__ = cls
+    model_wrapper.r = 0
+    model_wrapper._tome_info = {
+        "r": model_wrapper.r,
+        "size": None,
+        "log_size": None,
+        "source": None,
+        "trace_source": trace_source,
+        "prop_attn": prop_attn,
+        "verbose": verbose,
+        "class_token": False,
+        "distill_token": False,
+        "mode": mode,
+        "threshold": threshold,
+    }
+    if hasattr(model, "dist_token") and model.dist_token is not None:
+        model_wrapper._tome_info["distill_token"] = True
+
+    if mode in ['merge', 'random_merge']:
+        reduction_function = timesformer_merge
+    elif mode in ['drop', 'random_drop']:
+        reduction_function = timesformer_drop
+    elif mode in ['hybrid']:
+        reduction_function = timesformer_hybrid
+    else:
+        raise ValueError(f"unknown ToMe mode {mode!r}")
+
+    for module in model.modules():
+        if _is_block(module):
+            _swap(module, ToMeBlockMixin, "ToMe")
+            module._tome_info = model_wrapper._tome_info
+            module.reduction_function = reduction_function
+            _swap(module.attn, ToMeAttentionMixin, "ToMe")      # spatial attention only (timesformer.py:224)

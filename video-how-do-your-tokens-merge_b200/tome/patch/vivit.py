@@ -1,0 +1,231 @@
+"""``tome.patch.vivit`` -- drop-in for the reference's tome/patch/vivit.py.
+
+The reference class-swaps HuggingFace's VivitLayer / VivitAttention / VivitSelfAttention and
+relies on the pre-4.4x tuple-returning layer API (vivit.py:17-130); that code cannot run against
+the installed transformers 5.5.  This patch matches the three module kinds structurally
+(``layernorm_before``/``attention``/``intermediate``/``output``; ``attention``+``output``;
+``query``/``key``/``value``) so it applies to ``hostmodels.vivit`` and to HF's own modules of either
+API generation (a layer whose original ``forward`` takes ``head_mask`` gets tuple returns).
+Class token kept out of the merge (``class_token = embeddings.cls_token is not None``,
+vivit.py:242): score row 0 = -inf, kept tokens re-sorted ascending."""
+import copy
+import inspect
+
+import torch
+import torch.nn.functional as F
+
+from tome.merge import (Merge, bipartite_soft_matching, bipartite_soft_matching_drop,
+                        bipartite_soft_matching_hybrid, merge_source, merge_wavg)
+from tome.patch.videomae import _swap
+from tome.utils import parse_r
+
+
+class ToMeVivitLayerMixin:
+    """vivit.py:17-47."""
+
+    def forward(self, hidden_states, head_mask=None, output_attentions=False, **kwargs):
+        info = self._tome_info
+        attn_size = info["size"] if info["prop_attn"] else None
+        attn_bias = info.get("log_size") if info["prop_attn"] else None
+        attention_output, metric = self.attention(self.layernorm_before(hidden_states), attn_size,
+                                                  info["head_aggregation"], attn_bias)
+        hidden_states = attention_output + hidden_states                       # first residual
+        hidden_states = self.reduction_function(metric, hidden_states, info)
+        layer_output = self.output(self.intermediate(self.layernorm_after(hidden_states)), hidden_states)
+        return (layer_output,) if self._tome_tuple_api else layer_output
+
+
+class ToMeDuplicateVivitLayerMixin:
+    """vivit.py:50-66."""
+
+    def forward(self, hidden_states, head_mask=None, output_attentions=False, **kwargs):
+        info = self._tome_info
+        attn_size = info["size"] if info["prop_attn"] else None
+        attn_bias = info.get("log_size") if info["prop_attn"] else None
+        _, metric = self.attention(self.layernorm_before(hidden_states), attn_size, info["head_aggregation"], attn_bias)
+        hidden_states = self.reduction_function(metric, hidden_states, info)
+        return [hidden_states] if self._tome_tuple_api else hidden_states
+
+
+class ToMeVivitAttentionMixin:
+    """vivit.py:69-83."""
+
+    def forward(self, hidden_states, size=None, head_aggregation='mean', log_size=None, **kwargs):
+        ctx, metric = self.attention(hidden_states, size, head_aggregation, log_size)
+        return self.output(ctx, hidden_states), metric
+
+
+class ToMeVivitSelfAttentionMixin:
+    """vivit.py:86-130."""
+
+    def forward(self, hidden_states, size=None, head_aggregation='mean', log_size=None, **kwargs):
+        B, N, _ = hidden_states.shape
+        h, d = self.num_attention_heads, self.attention_head_size
+        q = self.query(hidden_states).view(B, N, h, d).transpose(1, 2)
+        k = self.key(hidden_states).view(B, N, h, d).transpose(1, 2)
+        v = self.value(hidden_states).view(B, N, h, d).transpose(1, 2)
+        bias = None
+        if size is not None:                             # proportional attention (vivit.py:103-104)
+            if log_size is None:
+                log_size = size.log()
+            bias = log_size[:, None, None, :, 0].to(q.dtype).expand(B, 1, N, N)
+        ctx = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, scale=d ** -0.5)
+        ctx = ctx.transpose(1, 2).reshape(B, N, h * d)
+        if head_aggregation == 'mean':
+            metric = k.mean(1)
+        elif head_aggregation == 'concat':
+            metric = k.transpose(1, 2).reshape(B, N, h * d)
+        else:
+            raise ValueError(f"head_aggregation must be 'mean' or 'concat', got {head_aggregation!r}")
+        return ctx, metric
+
+
+def vivit_merge(metric, x, _tome_info):
+    """vivit.py:133-153."""
+    r = _tome_info["r"].pop(0)
+    if r > 0:
+        merge, _ = bipartite_soft_matching(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
+                                           _tome_info["mode"])
+        if _tome_info["trace_source"]:
+            _tome_info["source"] = merge_source(merge, x, _tome_info["source"])
+        pre_merge = x.size(1)
+        if isinstance(merge, Merge):
+            x, _tome_info["size"], _tome_info["log_size"] = merge.wavg(x, _tome_info["size"])
+        else:
+            x, _tome_info["size"] = merge_wavg(merge, x, _tome_info["size"])
+            _tome_info["log_size"] = None
+        if _tome_info['verbose']:
+            print(f'Merged {pre_merge} to {x.size(1)} tokens')
+    return x
+
+
+def vivit_drop(metric, x, _tome_info):
+    """vivit.py:156-179."""
+    r = _tome_info["r"].pop(0)
+    if r > 0:
+        drop = bipartite_soft_matching_drop(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
+                                            _tome_info["mode"])
+        if isinstance(drop, tuple):
+            return x
+        if _tome_info["trace_source"]:
+            if _tome_info["source"] is None:
+                n, t, _ = x.shape
+                _tome_info["source"] = torch.eye(t, device=x.device)[None, ...].expand(n, t, t)
+            _tome_info["source"] = drop(_tome_info["source"].contiguous())
+        pre_drop = x.size(1)
+        x = drop(x)
+        _tome_info["size"] = torch.ones((x.size(0), x.size(1), 1), device=x.device)
+        _tome_info["log_size"] = torch.zeros((x.size(0), x.size(1), 1), device=x.device)
+        if _tome_info['verbose']:
+            print(f'Dropped {pre_drop} to {x.size(1)} tokens')
+    return x
+
+
+def vivit_hybrid(metric, x, _tome_info):
+    """vivit.py:182-204."""
+    r = _tome_info["r"].pop(0)
+    if r > 0:
+        merge, _ = bipartite_soft_matching_hybrid(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
+                                                  _tome_info["mode"], _tome_info["threshold"])
+        if _tome_info["trace_source"]:
+            _tome_info["source"] = merge_source(merge, x, _tome_info["source"])
+        pre_merge = x.size(1)
+        if isinstance(merge, Merge):
+            x, _tome_info["size"], _tome_info["log_size"] = merge.wavg(x, _tome_info["size"])
+        else:
+            x, _tome_info["size"] = merge_wavg(merge, x, _tome_info["size"])
+            _tome_info["log_size"] = None
+        if _tome_info['verbose']:
+            print(f'Merged {pre_merge} to {x.size(1)} tokens')
+    return x
+
+
+def _is_layer(m):
+    return all(hasattr(m, a) for a in ("attention", "intermediate", "output", "layernorm_before", "layernorm_after"))
+
+
+def _is_attention(m):
+    return hasattr(m, "attention") and hasattr(m, "output") and _is_self_attention(getattr(m, "attention", None))
+
+
+def _is_self_attention(m):
+    return m is not None and all(hasattr(m, a) for a in ("query", "key", "value", "num_attention_heads", "attention_head_size"))
+
+
+def _uses_tuple_api(layer):
+    base = getattr(layer.__class__, "_tome_base", layer.__class__)
+    try:
+        return "head_mask" in inspect.signature(base.forward).parameters
+    except (TypeError, ValueError):
+        return False
+
+
+def apply_duplicate_patch(model, layer_to_duplicate, quantity):
+    """vivit.py:207-211."""
+    for i in range(layer_to_duplicate, layer_to_duplicate + quantity - 1):
+        model.vivit.encoder.layer.insert(index=i, module=copy.deepcopy(model.vivit.encoder.layer[i]))
+        lyr = model.vivit.encoder.layer[i]
+        lyr._tome_tuple_api = _uses_tuple_api(lyr)
+        _swap(lyr, ToMeDuplicateVivitLayerMixin, "ToMeDuplicate")
+    if hasattr(model.vivit, "config"):
+        model.vivit.config.num_hidden_layers = model.vivit.config.num_hidden_layers + quantity
+
+
+def make_tome_class(transformer_class):
+    class ToMeVisionTransformer(transformer_class):
+        def forward(self, *args, **kwdargs) -> torch.Tensor:
+            self._tome_info["r"] = parse_r(len(self.vivit.encoder.layer), self.r)
+            self._tome_info["size"] = None
+            self._tome_info["log_size"] = None
+            self._tome_info["source"] = None
+            return super().forward(*args, **kwdargs)
+
+    return ToMeVisionTransformer
+
+
+def apply_patch(model_wrapper, trace_source: bool = False, prop_attn: bool = True, mode: str = 'merge',
+                head_aggregation: str = 'mean', threshold: float = 0.0, verbose: bool = False):
+    """vivit.py:226-270."""
+    model = model_wrapper.vivit
+    if not getattr(model_wrapper.__class__, "_tome_wrapper", False):
+        cls = make_tome_class(model_wrapper.__class__)
+        cls._tome_wrapper = True
+        model_wrapper.__class__ = cls
+    model_wrapper.r = 0
+    model_wrapper._tome_info = {
+        "r": model_wrapper.r,
+        "size": None,
+        "log_size": None,
+        "source": None,
+        "trace_source": trace_source,
+        "prop_attn": prop_attn,
+        "verbose": verbose,
+        "class_token": model.embeddings.cls_token is not None,
+        "distill_token": False,
+        "mode": mode,
+        "head_aggregation": head_aggregation,
+        "threshold": threshold,
+    }
+    if hasattr(model, "dist_token") and model.dist_token is not None:
+        model_wrapper._tome_info["distill_token"] = True
+
+    if mode in ['merge', 'random_merge']:
+        reduction_function = vivit_merge
+    elif mode in ['drop', 'random_drop']:
+        reduction_function = vivit_drop
+    elif mode in ['hybrid']:
+        reduction_function = vivit_hybrid
+    else:
+        raise ValueError(f"unknown ToMe mode {mode!r}")
+
+    for module in model.modules():
+        if _is_layer(module):
+            module._tome_tuple_api = _uses_tuple_api(module)
+            if getattr(module.__class__, "_tome_mixin", None) is not ToMeDuplicateVivitLayerMixin:
+                _swap(module, ToMeVivitLayerMixin, "ToMe")
+            module._tome_info = model_wrapper._tome_info
+            module.reduction_function = reduction_function
+        elif _is_attention(module):
+            _swap(module, ToMeVivitAttentionMixin, "ToMe")
+        elif _is_self_attention(module):
+            _swap(module, ToMeVivitSelfAttentionMixin, "ToMe")
