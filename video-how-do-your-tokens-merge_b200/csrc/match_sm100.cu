@@ -44,6 +44,7 @@ struct TcParams {
   int* strip_count;        // (bm, row tiles) arrivals; last column tile of a strip decodes the keys
   float* node_max;         // (bm, na)
   int* node_idx;           // (bm, na)
+  long long* trace;        // optional (TOME_TC_TRACE): per-CTA phase timestamps, 16 per CTA
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -150,6 +151,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_TRACE(slot) do { if (p.trace) p.trace[(((long long)b * gridDim.y + it) * gridDim.x + jt) * 16 + (slot)] = gtime(); } while (0)
+__device__ __forceinline__ float fmax_nan(float a, float b) {     // NaN-propagating max
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -200,6 +212,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jt = blockIdx.x, it = blockIdx.y, b = blockIdx.z;
 
+  if (threadIdx.x == 0) TC_TRACE(0);
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024-byte alignment
   const uint32_t a_bytes = TC_BM * 128u, b_bytes = (uint32_t)p.BN * 128u;
   const uint32_t stage_bytes = 2u * (a_bytes + b_bytes);
@@ -223,6 +236,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) TC_TRACE(1);
 
   const int row_a = b * p.n + it * TC_BM;               // rows of the split buffer (hi half)
   const int row_b = b * p.n + p.na + jt * p.BN;
@@ -248,6 +262,8 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int s = kb % p.stages;
         mbar_wait(bar_full + 8u * s, (kb / p.stages) & 1);
         tc_fence_after();
+        if (kb == 0) TC_TRACE(2);
+        if (kb == p.num_kb - 1) TC_TRACE(3);
         const uint32_t st = base + (uint32_t)s * stage_bytes;
         const uint64_t a_hi = make_sw128_desc(st), a_lo = make_sw128_desc(st + a_bytes);
         const uint64_t b_hi = make_sw128_desc(st + 2u * a_bytes), b_lo = make_sw128_desc(st + 2u * a_bytes + b_bytes);
@@ -261,6 +277,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         umma_commit(bar_empty + 8u * s);      // frees the stage when these MMAs retire
       }
       umma_commit(bar_tmem);                  // accumulator complete
+      TC_TRACE(4);
     }
   } else {
     // ---- epilogue: thread <-> TMEM lane <-> A row ------------------------------------------
@@ -271,58 +288,90 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const bool mask0 = p.distill && jt == 0;   // column 0 is the distillation token
     mbar_wait(bar_tmem, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) TC_TRACE(5);
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    // pass 1: approximate row max over the valid columns
+    // pass 1: approximate row max over the valid columns, remembering the max of every 32-column
+    // chunk.  max.NaN propagates NaN, so a NaN anywhere (zero-norm row) surfaces in m.
+    constexpr int MAXCH = 8;                   // BN <= 256
+    float chmax[MAXCH];
+#pragma unroll
+    for (int q = 0; q < MAXCH; ++q) chmax[q] = -INFINITY;
     float m = -INFINITY;
-    bool has_nan = false;
-    int c = 0;
-    for (; c + 32 <= ncol; c += 32) {
-      float v[32];
-      tmem_ld32(taddr + (uint32_t)c, v);
-      if (mask0 && c == 0) v[0] = -INFINITY;
 #pragma unroll
-      for (int e = 0; e < 32; ++e) { has_nan |= (v[e] != v[e]); m = fmaxf(m, v[e]); }
-    }
-    for (; c < ncol; c += 16) {
-      float v[16];
-      tmem_ld16(taddr + (uint32_t)c, v);
-      if (mask0 && c == 0) v[0] = -INFINITY;
+    for (int q = 0; q < MAXCH; ++q) {
+      const int c = q * 32;
+      if (c < ncol) {                          // warp-uniform
+        float cm = -INFINITY;
+        if (c + 32 <= ncol) {
+          float v[32];
+          tmem_ld32(taddr + (uint32_t)c, v);
+          if (mask0 && c == 0) v[0] = -INFINITY;
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const float x = (c + e < ncol) ? v[e] : -INFINITY;
-        has_nan |= (x != x); m = fmaxf(m, x);
+          for (int e = 0; e < 32; ++e) cm = fmax_nan(cm, v[e]);
+        } else {
+          for (int cc = c; cc < ncol; cc += 16) {
+            float v[16];
+            tmem_ld16(taddr + (uint32_t)cc, v);
+            if (mask0 && cc == 0) v[0] = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) cm = fmax_nan(cm, (cc + e < ncol) ? v[e] : -INFINITY);
+          }
+        }
+        chmax[q] = cm;
+        m = fmax_nan(m, cm);
       }
     }
-    // pass 2: every column within the error window of the max is a candidate
+    const bool has_nan = (m != m);
+    if (threadIdx.x == 64) TC_TRACE(6);
+    // pass 2: every column within the error window of the max is a candidate.  Branch-free: one bit
+    // per column (a divergent scan with a dynamically indexed candidate list cost 5.6 us per CTA,
+    // see profiles/r01_match_notes.md), candidates are pulled out of the masks afterwards.
     const float thr = m - p.window;
-    int cnt = 0, cand[KCAND];
+    uint32_t bits[MAXCH];
+#pragma unroll
+    for (int q = 0; q < MAXCH; ++q) {
+      const int c = q * 32;
+      uint32_t bm_ = 0u;
+      if (c < ncol && !has_nan) {              // warp-uniform
+        if (c + 32 <= ncol) {
+          float v[32];
+          tmem_ld32(taddr + (uint32_t)c, v);
+          if (mask0 && c == 0) v[0] = -INFINITY;
+          uint32_t part[4] = {0u, 0u, 0u, 0u};     // four independent OR chains (this phase is issue-latency bound)
+#pragma unroll
+          for (int e = 0; e < 32; ++e) part[e & 3] |= (v[e] >= thr ? 1u : 0u) << e;
+          bm_ = (part[0] | part[1]) | (part[2] | part[3]);
+        } else {
+          for (int cc = c; cc < ncol; cc += 16) {
+            float v[16];
+            tmem_ld16(taddr + (uint32_t)cc, v);
+            if (mask0 && cc == 0) v[0] = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) bm_ |= ((cc + e < ncol && v[e] >= thr) ? 1u : 0u) << (cc - c + e);
+          }
+        }
+      }
+      bits[q] = bm_;
+    }
+    if (threadIdx.x == 64) TC_TRACE(11);
+    int cnt = 0, filled = 0, cand[KCAND];
 #pragma unroll
     for (int e = 0; e < KCAND; ++e) cand[e] = 0;
-    c = 0;
-    for (; c + 32 <= ncol; c += 32) {
-      float v[32];
-      tmem_ld32(taddr + (uint32_t)c, v);
-      if (mask0 && c == 0) v[0] = -INFINITY;
 #pragma unroll
-      for (int e = 0; e < 32; ++e)
-        if (v[e] >= thr) {
-#pragma unroll
-          for (int s = 0; s < KCAND; ++s) if (cnt == s) cand[s] = c + e;
-          ++cnt;
-        }
+    for (int q = 0; q < MAXCH; ++q) {
+      uint32_t w = bits[q];
+      cnt += __popc(w);
+      while (w != 0u && filled < KCAND) {        // rare per (lane, chunk): a real branch beats a predicated chain
+        const int col = q * 32 + __ffs(w) - 1;
+        w &= w - 1u;
+        if (filled == 0) cand[0] = col;
+        else if (filled == 1) cand[1] = col;
+        else if (filled == 2) cand[2] = col;
+        else cand[3] = col;
+        ++filled;
+      }
     }
-    for (; c < ncol; c += 16) {
-      float v[16];
-      tmem_ld16(taddr + (uint32_t)c, v);
-      if (mask0 && c == 0) v[0] = -INFINITY;
-#pragma unroll
-      for (int e = 0; e < 16; ++e)
-        if (c + e < ncol && v[e] >= thr) {
-#pragma unroll
-          for (int s = 0; s < KCAND; ++s) if (cnt == s) cand[s] = c + e;
-          ++cnt;
-        }
-    }
+    if (threadIdx.x == 64) TC_TRACE(7);
     const bool overflow = has_nan || cnt > KCAND;
     if (!p.resident) {
       if (i < p.na) {
@@ -354,9 +403,11 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       atomicMax(p.keys + (long long)b * p.na + i, best);
     }
   }
+  if (threadIdx.x == 64) TC_TRACE(8);
   tc_fence_before();
   if (p.resident) __threadfence();
   __syncthreads();
+  if (threadIdx.x == 0) TC_TRACE(9);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -380,6 +431,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
     }
   }
+  if (threadIdx.x == 0) TC_TRACE(10);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -517,6 +569,7 @@ int launch_match_tc(const void* metric, int dtype, int bm, int n, int cm, const 
   tc_geometry(bm, n, cm, p);
   p.cls = cls; p.distill = distill; p.rows_total = bm * n;
   p.node_max = node_max; p.node_idx = node_idx;
+  p.trace = getenv("TOME_TC_TRACE") ? (long long*)strtoull(getenv("TOME_TC_TRACE"), nullptr, 0) : nullptr;
   const int n_rt = (p.na + TC_BM - 1) / TC_BM;
   char* w = (char*)ws;
   float* split = (float*)w;                      w += align256((size_t)2 * bm * n * cm * sizeof(float));
