@@ -298,7 +298,7 @@ def micro_kernels(args, device, dtype):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of merge_gather_kernel from the committed
 # `ncu --set full` capture (profiles/r01_merge_gather_ncu.txt); writes stay in L2 at this size.
-MERGE_DRAM_TRAFFIC_NCU = {}
+MERGE_DRAM_TRAFFIC_NCU = {(8, "bf16"): 19434752}   # 19.43 MB read + 0 B written back (18 MB of writes stay in the 126 MB L2)
 
 
 def run_ours(args):

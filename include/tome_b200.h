@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 4
+#define TOME_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define TOME_API __attribute__((visibility("default")))
@@ -148,6 +148,16 @@ TOME_API int tome_merge(const tome_plan* plan, const void* x, int32_t dtype, int
                const tome_view* x_view, const float* size_in, int32_t mode,
                float hybrid_threshold, void* out, const tome_view* out_view, float* size_out,
                float* logsize_out, void* stream);
+
+/* tome_merge plus the LayerNorm the patched block applies next (norm2, tome/patch/videomae.py:21-22,
+ * timesformer.py:56, motionformer.py:29, vivit.py:39): also writes normed_out = LayerNorm(out) * w + b
+ * (same dtype; fp32 statistics over the rounded row), saving the separate LayerNorm pass over x'.
+ * ln_weight / ln_bias: (c) in x's dtype (bias may be NULL). */
+TOME_API int tome_merge_norm(const tome_plan* plan, const void* x, int32_t dtype, int32_t c,
+                    const tome_view* x_view, const float* size_in, int32_t mode, float hybrid_threshold,
+                    void* out, const tome_view* out_view, float* size_out, float* logsize_out,
+                    const void* ln_weight, const void* ln_bias, float ln_eps, void* normed_out,
+                    const tome_view* normed_view, void* stream);
 
 /* merge_source (merge.py:372-384): source (bm, n, n0) fp32 0/1 adjacency, 'max' reduce.
  * source == NULL means the implicit identity (n0 == n), generated on the fly. */

@@ -299,3 +299,31 @@ def test_tensor_core_pass_really_prunes(native, name, monkeypatch):
         err = max(err, float(np.abs(tile_max[:, lo:, c] - true).max()))
     print(f"[tc-pass] {name}: cm={cm} max |approx-true| = {err:.3e} (bound {eps:.3e}), "
           f"single-candidate tiles {(cnt == 1).mean() * 100:.2f}%")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_layernorm_matches_separate_pass(native, dtype):
+    """tome_merge_norm: the merged rows are bit-identical to tome_merge, and the fused LayerNorm equals
+    torch's LayerNorm of those rows (fp32: round-off; bf16: one output ulp)."""
+    case = util.CASE_BY_NAME["tokens_tsf"]
+    g = util.golden(case["name"])
+    metric, x, size = util.case_arrays(case)
+    dp = _device_plan_like_reference(native, case, g)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    c = 768
+    xd = torch.randn(case["bm"], case["n"], c, device="cuda", generator=gen).to(dtype)
+    w = (1 + 0.1 * torch.randn(c, device="cuda", generator=gen)).to(dtype)
+    b = (0.1 * torch.randn(c, device="cuda", generator=gen)).to(dtype)
+    plain, s0, l0 = native.merge(dp, xd, "wavg", size=_dev(size), want_size=True)
+    out, s1, l1, normed = native.merge(dp, xd, "wavg", size=_dev(size), want_size=True, norm=(w, b, 1e-6))
+    assert torch.equal(out, plain) and torch.equal(s0, s1) and torch.equal(l0, l1)
+    want = torch.nn.functional.layer_norm(out.float(), (c,), w.float(), b.float(), 1e-6)
+    tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=1.6e-2, atol=1.6e-2)
+    torch.testing.assert_close(normed.float(), want, **tol)
+    # frame layout (class token row normalised on the side)
+    B, T, P = 2, 4, case["n"]
+    xf = torch.randn(B, 1 + P * T, c, device="cuda", generator=gen).to(dtype)
+    o2, _, _, n2 = native.merge_frames(dp, xf, T, "wavg", norm=(w, b, 1e-6))
+    want2 = torch.nn.functional.layer_norm(o2.float(), (c,), w.float(), b.float(), 1e-6)
+    torch.testing.assert_close(n2.float(), want2, **tol)
+    assert torch.equal(o2, native.merge_frames(dp, xf, T, "wavg")[0])

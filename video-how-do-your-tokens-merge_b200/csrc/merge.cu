@@ -28,6 +28,12 @@ struct MergeArgs {
   View ov;
   float* size_out;
   float* logsize_out;
+  // optional fused LayerNorm of the merged rows (the block's norm2, tome/patch/videomae.py:21-22):
+  const void* ln_w;      // gamma (c) in x's dtype, or NULL
+  const void* ln_b;      // beta  (c) or NULL
+  float ln_eps;
+  void* normed;          // (bm, n - r, c) LayerNorm(out), addressed like `out` through nv
+  View nv;
 };
 
 // output slot -> (kind, index): merge.py:82-85 ordering
@@ -234,7 +240,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 
-template <typename T, int NV, int WARPS, int MINB>
+template <typename T, int NV, int WARPS, int MINB, bool LN>
 __global__ void __launch_bounds__(WARPS * 32, MINB) merge_gather_kernel(MergeArgs a) {
   constexpr int E = Pack<T>::E;
   constexpr bool kCopyIfNoSrc = sizeof(T) == 2;   // bf16: round(fp32(x*s)/s) == x -> kept tokens are plain copies
@@ -285,21 +291,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) merge_gather_kernel(MergeArg
   uint4* orow = reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.out) + a.ov.batch_offset(b) + (long long)o * a.ov.sn);
 
   if (nsrc == 0) {
-    if (kCopyIfNoSrc || S == 1.0f) {
-#pragma unroll
-      for (int v = 0; v < NV; ++v) { const int i = v * 32 + lane; if (i < nvec) orow[i] = raw[v]; }
-    } else {
+    if (!(kCopyIfNoSrc || S == 1.0f)) {
       // kept token of size s != 1: the reference really computes (x*s)/s  (merge.py:365-368)
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
-        const int i = v * 32 + lane;
-        if (i < nvec) {
-          float f[E];
-          Pack<T>::unpack(raw[v], f);
+        float f[E];
+        Pack<T>::unpack(raw[v], f);
 #pragma unroll
-          for (int e = 0; e < E; ++e) f[e] = __fdiv_rn(__fmul_rn(f[e], S), S);
-          orow[i] = Pack<T>::pack(f);
-        }
+        for (int e = 0; e < E; ++e) f[e] = __fdiv_rn(__fmul_rn(f[e], S), S);
+        raw[v] = Pack<T>::pack(f);
       }
     }
   } else {
@@ -376,17 +376,66 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) merge_gather_kernel(MergeArg
     }
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      const int i = v * 32 + lane;
-      if (i < nvec) {
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-          if (wavg) accv[v][e] = __fdiv_rn(accv[v][e], Ssum);
-          else if (a.mode == TOME_MODE_MEAN) accv[v][e] = __fdiv_rn(accv[v][e], cnt);
-        }
-        orow[i] = Pack<T>::pack(accv[v]);
+      for (int e = 0; e < E; ++e) {
+        if (wavg) accv[v][e] = __fdiv_rn(accv[v][e], Ssum);
+        else if (a.mode == TOME_MODE_MEAN) accv[v][e] = __fdiv_rn(accv[v][e], cnt);
       }
+      raw[v] = Pack<T>::pack(accv[v]);
     }
     S = Ssum;
+  }
+  // the finished row sits in `raw` (packed, already rounded to the output dtype)
+#pragma unroll
+  for (int v = 0; v < NV; ++v) { const int i = v * 32 + lane; if (i < nvec) orow[i] = raw[v]; }
+  if (LN) {
+    // fused LayerNorm over the row this warp holds: fp32 statistics of the ROUNDED row (what a separate
+    // LayerNorm kernel would read back), two-pass variance, one more row written instead of a whole
+    // read-modify-write pass over x'
+    float sum = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int i = v * 32 + lane;
+      if (i < nvec) {
+        float f[E];
+        Pack<T>::unpack(raw[v], f);
+#pragma unroll
+        for (int e = 0; e < E; ++e) sum += f[e];
+      }
+    }
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, of);
+    const float mean = sum / (float)a.c;
+    float sq = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int i = v * 32 + lane;
+      if (i < nvec) {
+        float f[E];
+        Pack<T>::unpack(raw[v], f);
+#pragma unroll
+        for (int e = 0; e < E; ++e) { const float d = f[e] - mean; sq = fmaf(d, d, sq); }
+      }
+    }
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, of);
+    const float rstd = rsqrtf(sq / (float)a.c + a.ln_eps);
+    uint4* nrow = reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.normed) + a.nv.batch_offset(b) + (long long)o * a.nv.sn);
+    const uint4* gw = reinterpret_cast<const uint4*>(a.ln_w);
+    const uint4* gb = reinterpret_cast<const uint4*>(a.ln_b);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int i = v * 32 + lane;
+      if (i < nvec) {
+        float f[E], w[E], bb[E];
+        Pack<T>::unpack(raw[v], f);
+        Pack<T>::unpack(__ldg(gw + i), w);
+        if (gb) Pack<T>::unpack(__ldg(gb + i), bb);
+#pragma unroll
+        for (int e = 0; e < E; ++e) f[e] = (f[e] - mean) * rstd * w[e] + (gb ? bb[e] : 0.f);
+        nrow[i] = Pack<T>::pack(f);
+      }
+    }
   }
   if (lane == 0) {
     const long long so = (long long)b * nout + o;
@@ -470,10 +519,12 @@ static int launch_gather_inst(const MergeArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)WARPS * 2 * NV * 32 * sizeof(uint4);
   static bool attr = false;
   if (!attr && smem > 48 * 1024) {
-    TOME_CUDA(cudaFuncSetAttribute(merge_gather_kernel<T, NV, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TOME_CUDA(cudaFuncSetAttribute(merge_gather_kernel<T, NV, WARPS, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TOME_CUDA(cudaFuncSetAttribute(merge_gather_kernel<T, NV, WARPS, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  merge_gather_kernel<T, NV, WARPS, MINB><<<grid, WARPS * 32, smem, st>>>(a);
+  if (a.normed) merge_gather_kernel<T, NV, WARPS, MINB, true><<<grid, WARPS * 32, smem, st>>>(a);
+  else merge_gather_kernel<T, NV, WARPS, MINB, false><<<grid, WARPS * 32, smem, st>>>(a);
   TOME_LAUNCH_CHECK("merge_gather_kernel");
   return TOME_OK;
 }
@@ -493,8 +544,9 @@ static int launch_merge_gather(const MergeArgs& a, cudaStream_t st) {
 
 int launch_merge(const tome_plan* plan, const void* x, int dtype, int c, const View& xv, const float* size_in,
                  int mode, float thr, void* out, const View& ov, float* size_out, float* logsize_out,
-                 cudaStream_t st) {
+                 cudaStream_t st, const void* ln_w, const void* ln_b, float ln_eps, void* normed, const View* nv) {
   MergeArgs a;
+  a.ln_w = ln_w; a.ln_b = ln_b; a.ln_eps = ln_eps; a.normed = normed; a.nv = nv ? *nv : ov;
   a.bm = plan->bm; a.n = plan->n; a.r = plan->r; a.distill = plan->distill_token; a.c = c; a.mode = mode;
   a.hybrid = (thr == thr) ? 1 : 0; a.thr = thr; a.node_max = plan->node_max;
   a.unm_idx = plan->unm_idx; a.b_off = plan->b_off; a.b_src = plan->b_src; a.b_head = plan->b_head;
@@ -502,12 +554,18 @@ int launch_merge(const tome_plan* plan, const void* x, int dtype, int c, const V
   const int variant = getenv("TOME_MERGE_VARIANT") ? atoi(getenv("TOME_MERGE_VARIANT")) : 0;   // tuning knob
   if (dtype == TOME_F32) {
     const bool vec = c % 4 == 0 && aligned16(x) && aligned16(out) && view_vec_ok(xv, 4) && view_vec_ok(ov, 4);
+    if (!vec && normed) return set_error(TOME_ERR_ALIGN, "tome_merge_norm: fused LayerNorm needs 16-byte aligned rows (c %% 4 == 0)");
+    if (normed && (c > 4 * 32 * 8 || !aligned16(ln_w) || (ln_b && !aligned16(ln_b)) || !aligned16(normed) || !view_vec_ok(a.nv, 4)))
+      return set_error(TOME_ERR_UNSUPPORTED, "tome_merge_norm: c=%d too wide or LayerNorm buffers misaligned", c);
     if (!vec) return launch_merge_scalar<float>(a, st);
     if (variant == 1) return launch_merge_gather<float, 8, 3>(a, st);
     if (variant == 2) return launch_merge_gather<float, 8, 2>(a, st);
     return launch_merge_gather<float, 4, 6>(a, st);
   } else if (dtype == TOME_BF16) {
     const bool vec = c % 8 == 0 && aligned16(x) && aligned16(out) && view_vec_ok(xv, 8) && view_vec_ok(ov, 8);
+    if (!vec && normed) return set_error(TOME_ERR_ALIGN, "tome_merge_norm: fused LayerNorm needs 16-byte aligned rows (c %% 8 == 0)");
+    if (normed && (c > 8 * 32 * 8 || !aligned16(ln_w) || (ln_b && !aligned16(ln_b)) || !aligned16(normed) || !view_vec_ok(a.nv, 8)))
+      return set_error(TOME_ERR_UNSUPPORTED, "tome_merge_norm: c=%d too wide or LayerNorm buffers misaligned", c);
     if (!vec) return launch_merge_scalar<__nv_bfloat16>(a, st);
     if (variant == 1) return launch_merge_gather<__nv_bfloat16, 4, 8>(a, st);
     if (variant == 2) return launch_merge_gather<__nv_bfloat16, 8, 3>(a, st);
@@ -521,7 +579,7 @@ int launch_merge_source(const tome_plan* plan, const float* source, int n0, floa
   const int nout = plan->n - plan->r;
   if (source) {
     View xv{(long long)plan->n * n0, 0, n0, 1}, ov{(long long)nout * n0, 0, n0, 1};
-    return launch_merge(plan, source, TOME_F32, n0, xv, nullptr, TOME_MODE_AMAX, thr, out, ov, nullptr, nullptr, st);
+    return launch_merge(plan, source, TOME_F32, n0, xv, nullptr, TOME_MODE_AMAX, thr, out, ov, nullptr, nullptr, st, nullptr, nullptr, 0.f, nullptr, nullptr);
   }
   MergeArgs a{};
   a.bm = plan->bm; a.n = plan->n; a.r = plan->r; a.distill = plan->distill_token; a.c = plan->n;

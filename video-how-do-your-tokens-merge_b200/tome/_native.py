@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 TOME_F32, TOME_BF16 = 0, 1
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -27,7 +27,8 @@ _MODES = {"wavg": MODE_WAVG, "sum": MODE_SUM, "mean": MODE_MEAN, "max": MODE_AMA
 
 EXPORTS = (
     "tome_abi_version", "tome_last_error", "tome_launch_count", "tome_device_check", "tome_match_workspace_bytes", "tome_match",
-    "tome_rowmax", "tome_select_workspace_bytes", "tome_select", "tome_merge", "tome_merge_source", "tome_unmerge",
+    "tome_rowmax", "tome_select_workspace_bytes", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_source",
+    "tome_unmerge",
 )
 
 
@@ -80,9 +81,12 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.tome_select.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_sz, c_vp]
     lib.tome_merge.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_i32, ctypes.POINTER(TomeViewC), c_vp, c_i32,
                                c_f32, c_vp, ctypes.POINTER(TomeViewC), c_vp, c_vp, c_vp]
+    lib.tome_merge_norm.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_i32, ctypes.POINTER(TomeViewC), c_vp, c_i32,
+                                    c_f32, c_vp, ctypes.POINTER(TomeViewC), c_vp, c_vp, c_vp, c_vp, c_f32, c_vp,
+                                    ctypes.POINTER(TomeViewC), c_vp]
     lib.tome_merge_source.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_f32, c_vp, c_vp]
     lib.tome_unmerge.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_i32, c_vp, c_vp]
-    for name in ("tome_device_check", "tome_match", "tome_rowmax", "tome_select", "tome_merge", "tome_merge_source",
+    for name in ("tome_device_check", "tome_match", "tome_rowmax", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_source",
                  "tome_unmerge"):
         getattr(lib, name).restype = c_i32
     if lib.tome_abi_version() != ABI_VERSION:
@@ -234,10 +238,21 @@ def select(node_max: torch.Tensor, node_idx: torch.Tensor, n: int, r: int, class
     return plan
 
 
+def _norm_args(norm, x):
+    """(weight, bias, eps) of a LayerNorm the kernel can fuse, as raw pointers in x's dtype."""
+    w, b, eps = norm
+    if w.dtype != x.dtype or w.device != x.device or not w.is_contiguous() or w.numel() != x.shape[-1]:
+        raise RuntimeError("tome_b200: fused LayerNorm needs a contiguous weight of x's dtype/device and length c")
+    if b is not None and (b.dtype != x.dtype or not b.is_contiguous() or b.numel() != w.numel()):
+        raise RuntimeError("tome_b200: fused LayerNorm bias must match the weight")
+    return w.data_ptr(), (None if b is None else b.data_ptr()), float(eps)
+
+
 def merge(plan: DevicePlan, x: torch.Tensor, mode: str, size: Optional[torch.Tensor] = None,
-          hybrid_threshold: Optional[float] = None, want_size: bool = False):
+          hybrid_threshold: Optional[float] = None, want_size: bool = False, norm=None):
     """Kernel 3.  x (bm, n, c) -> (bm, n - r, c).  mode in wavg/sum/mean/max/amax/drop.
-    Returns out, or (out, size_out, logsize_out) when ``want_size``."""
+    Returns out, or (out, size_out, logsize_out) when ``want_size``; with ``norm=(weight, bias, eps)``
+    the LayerNorm of the merged rows is produced in the same pass and appended to the result."""
     lib = load_library()
     _require_cuda(x, "x")
     if x.dim() != 3 or x.shape[0] != plan.bm or x.shape[1] != plan.n:
@@ -265,15 +280,25 @@ def merge(plan: DevicePlan, x: torch.Tensor, mode: str, size: Optional[torch.Ten
             size = size.reshape(bm, n).to(dtype=torch.float32).contiguous()
             sp = size.data_ptr()
         xv, ov = _view_of(x), _view_of(out)
-        _check(lib.tome_merge(plan.c_ptr(), x.data_ptr(), _dtype_code(x), c, ctypes.byref(xv), sp, m, thr,
-                              out.data_ptr(), ctypes.byref(ov), so, lo, _stream(x)), lib)
-    if want_size:
-        return out, size_out, logsize_out
-    return out
+        normed = None
+        if norm is None:
+            _check(lib.tome_merge(plan.c_ptr(), x.data_ptr(), _dtype_code(x), c, ctypes.byref(xv), sp, m, thr,
+                                  out.data_ptr(), ctypes.byref(ov), so, lo, _stream(x)), lib)
+        else:
+            wp, bp, eps = _norm_args(norm, x)
+            normed = torch.empty_like(out)
+            nv = _view_of(normed)
+            _check(lib.tome_merge_norm(plan.c_ptr(), x.data_ptr(), _dtype_code(x), c, ctypes.byref(xv), sp, m, thr,
+                                       out.data_ptr(), ctypes.byref(ov), so, lo, wp, bp, eps, normed.data_ptr(),
+                                       ctypes.byref(nv), _stream(x)), lib)
+    res = (out, size_out, logsize_out) if want_size else (out,)
+    if norm is not None:
+        res = res + (normed,)
+    return res if len(res) > 1 else res[0]
 
 
 def merge_frames(plan: DevicePlan, x: torch.Tensor, frames: int, mode: str, size: Optional[torch.Tensor] = None,
-                 hybrid_threshold: Optional[float] = None):
+                 hybrid_threshold: Optional[float] = None, norm=None):
     """Kernel 3 on TimeSformer / Motionformer token layout, without the rearrange copies.
 
     x is (B, 1 + P*T, C): a class token followed by tokens ordered '(p t)'.  The plan's matching batch
@@ -306,10 +331,19 @@ def merge_frames(plan: DevicePlan, x: torch.Tensor, frames: int, mode: str, size
             sp = size.data_ptr()
         xv = TomeViewC(x.stride(0), x.stride(1), T * x.stride(1), T)
         ov = TomeViewC(out.stride(0), out.stride(1), T * out.stride(1), T)
-        _check(lib.tome_merge(plan.c_ptr(), x[:, 1:].data_ptr(), _dtype_code(x), C, ctypes.byref(xv), sp, m, thr,
-                              out[:, 1:].data_ptr(), ctypes.byref(ov), size_out.data_ptr(), logsize_out.data_ptr(),
-                              _stream(x)), lib)
-    return out, size_out, logsize_out
+        if norm is None:
+            _check(lib.tome_merge(plan.c_ptr(), x[:, 1:].data_ptr(), _dtype_code(x), C, ctypes.byref(xv), sp, m, thr,
+                                  out[:, 1:].data_ptr(), ctypes.byref(ov), size_out.data_ptr(), logsize_out.data_ptr(),
+                                  _stream(x)), lib)
+            return out, size_out, logsize_out
+        wp, bp, eps = _norm_args(norm, x)
+        normed = torch.empty_like(out)
+        normed[:, 0] = torch.nn.functional.layer_norm(out[:, 0], (C,), norm[0], norm[1], eps)     # class token row
+        nv = TomeViewC(normed.stride(0), normed.stride(1), T * normed.stride(1), T)
+        _check(lib.tome_merge_norm(plan.c_ptr(), x[:, 1:].data_ptr(), _dtype_code(x), C, ctypes.byref(xv), sp, m, thr,
+                                   out[:, 1:].data_ptr(), ctypes.byref(ov), size_out.data_ptr(), logsize_out.data_ptr(),
+                                   wp, bp, eps, normed[:, 1:].data_ptr(), ctypes.byref(nv), _stream(x)), lib)
+    return out, size_out, logsize_out, normed
 
 
 def merge_source(plan: DevicePlan, source: Optional[torch.Tensor], hybrid_threshold: Optional[float] = None

@@ -67,20 +67,23 @@ class Merge(_PlanCallable):
     def __call__(self, x: torch.Tensor, mode="mean") -> torch.Tensor:      # merge.py:75-85 / 316-334
         return _native.merge(self.plan, x, mode, hybrid_threshold=self.threshold)
 
-    def wavg(self, x, size=None):
-        """Fused merge_wavg: (x', size' (bm, n', 1) fp32, log size' (bm, n', 1) fp32)."""
-        out, s, ls = _native.merge(self.plan, x, "wavg", size=size, hybrid_threshold=self.threshold, want_size=True)
-        return out, s[..., None], ls[..., None]
+    def wavg(self, x, size=None, norm=None):
+        """Fused merge_wavg: (x', size' (bm, n', 1) fp32, log size' (bm, n', 1) fp32); with
+        ``norm=(weight, bias, eps)`` also LayerNorm(x') from the same pass as a 4th result."""
+        res = _native.merge(self.plan, x, "wavg", size=size, hybrid_threshold=self.threshold, want_size=True, norm=norm)
+        out, s, ls = res[:3]
+        return (out, s[..., None], ls[..., None]) + tuple(res[3:])
 
     def source(self, source=None):
         return _native.merge_source(self.plan, source, self.threshold)
 
-    def wavg_frames(self, x, frames, size=None):
+    def wavg_frames(self, x, frames, size=None, norm=None):
         """merge_wavg on a (B, 1 + P*T, C) class-token + '(p t)' tensor whose matching batch is (b t):
         the TimeSformer / Motionformer case, rearranges folded into addressing.
         Returns (x' (B, 1 + P'*T, C), size' (B*T, P', 1), log size' (B*T, P', 1))."""
-        out, s, ls = _native.merge_frames(self.plan, x, frames, "wavg", size=size, hybrid_threshold=self.threshold)
-        return out, s[..., None], ls[..., None]
+        res = _native.merge_frames(self.plan, x, frames, "wavg", size=size, hybrid_threshold=self.threshold, norm=norm)
+        out, s, ls = res[:3]
+        return (out, s[..., None], ls[..., None]) + tuple(res[3:])
 
 
 class Unmerge(_PlanCallable):

@@ -12,7 +12,7 @@ import torch.nn.functional as F
 from tome.merge import (Drop, Merge, bipartite_soft_matching, bipartite_soft_matching_drop,
                         bipartite_soft_matching_hybrid)
 from tome.patch.timesformer import _frames_back, _frames_view, _merge_frames_generic
-from tome.patch.videomae import _swap
+from tome.patch.videomae import _normed_or, _swap, fusable_norm
 from tome.utils import parse_r
 
 
@@ -61,8 +61,8 @@ class ToMeBlockMixin:
         attn_out, _, metric = self.attn(self.norm1(x), seq_len=seq_len, num_frames=num_frames, approx=approx,
                                         num_landmarks=num_landmarks, size=attn_size, log_size=attn_bias)
         x = x + self.drop_path(attn_out)
-        x = self.reduction_function(metric, x, info, num_frames)
-        return x + self.drop_path(self.mlp(self.norm2(x)))
+        x = self.reduction_function(metric, x, info, num_frames, norm=self.norm2)
+        return x + self.drop_path(self.mlp(_normed_or(self.norm2, x, info)))
 
 
 class ToMeTrajectoryAttentionMixin:
@@ -88,8 +88,9 @@ class ToMeTrajectoryAttentionMixin:
         return out, None, metric
 
 
-def motionformer_merge(metric, x, _tome_info, num_frames):
+def motionformer_merge(metric, x, _tome_info, num_frames, norm=None):
     """motionformer.py:147-170."""
+    _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
     if r > 0:
         B, T = x.size(0), num_frames
@@ -99,7 +100,10 @@ def motionformer_merge(metric, x, _tome_info, num_frames):
         if isinstance(merge, Merge):
             if _tome_info["trace_source"]:
                 _tome_info["source"] = merge.source(_tome_info["source"])
-            x, _tome_info["size"], _tome_info["log_size"] = merge.wavg_frames(x, T, _tome_info["size"])
+            fn = fusable_norm(norm, x) if norm is not None else None
+            res = merge.wavg_frames(x, T, _tome_info["size"], norm=fn)
+            x, _tome_info["size"], _tome_info["log_size"] = res[0], res[1], res[2]
+            _tome_info["normed"] = res[3] if fn is not None else None
         else:
             x = _merge_frames_generic(merge, x, _tome_info, B, T, P)
         if _tome_info['verbose']:
@@ -107,8 +111,9 @@ def motionformer_merge(metric, x, _tome_info, num_frames):
     return x
 
 
-def motionformer_drop(metric, x, _tome_info, num_frames):
+def motionformer_drop(metric, x, _tome_info, num_frames, norm=None):
     """motionformer.py:173-200."""
+    _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
     if r > 0:
         B, T = x.size(0), num_frames
@@ -133,8 +138,9 @@ def motionformer_drop(metric, x, _tome_info, num_frames):
     return x
 
 
-def motionformer_hybrid(metric, x, _tome_info, num_frames):
+def motionformer_hybrid(metric, x, _tome_info, num_frames, norm=None):
     """motionformer.py:203-227."""
+    _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
     if r > 0:
         B, T = x.size(0), num_frames
@@ -144,7 +150,10 @@ def motionformer_hybrid(metric, x, _tome_info, num_frames):
         if isinstance(merge, Merge):
             if _tome_info["trace_source"]:
                 _tome_info["source"] = merge.source(_tome_info["source"])
-            x, _tome_info["size"], _tome_info["log_size"] = merge.wavg_frames(x, T, _tome_info["size"])
+            fn = fusable_norm(norm, x) if norm is not None else None
+            res = merge.wavg_frames(x, T, _tome_info["size"], norm=fn)
+            x, _tome_info["size"], _tome_info["log_size"] = res[0], res[1], res[2]
+            _tome_info["normed"] = res[3] if fn is not None else None
         else:
             x = _merge_frames_generic(merge, x, _tome_info, B, T, P)
         if _tome_info['verbose']:
@@ -172,6 +181,7 @@ def make_tome_class(transformer_class):
             self._tome_info["r"] = parse_r(len(self.blocks), self.r)
             self._tome_info["size"] = None
             self._tome_info["log_size"] = None
+            self._tome_info["normed"] = None
             self._tome_info["source"] = None
             return super().forward(*args, **kwdargs)
 
@@ -190,6 +200,7 @@ def apply_patch(model, trace_source: bool = False, prop_attn: bool = True, mode:
         "r": model.r,
         "size": None,
         "log_size": None,
+        "normed": None,
         "source": None,
         "trace_source": trace_source,
         "prop_attn": prop_attn,

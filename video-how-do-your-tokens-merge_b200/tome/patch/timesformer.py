@@ -15,7 +15,7 @@ import torch.nn.functional as F
 
 from tome.merge import (Drop, Merge, bipartite_soft_matching, bipartite_soft_matching_drop,
                         bipartite_soft_matching_hybrid, merge_source, merge_wavg)
-from tome.patch.videomae import _swap
+from tome.patch.videomae import _normed_or, _swap, fusable_norm
 from tome.utils import parse_r
 
 
@@ -44,8 +44,8 @@ class ToMeBlockMixin:
         cls = res_s[:, 0, :].reshape(B, T, C).mean(1, keepdim=True)          # averaged over frames
         res = res_s[:, 1:, :].reshape(B, T, P, C).transpose(1, 2).reshape(B, P * T, C)
         x = torch.cat((init_cls, xt), 1) + torch.cat((cls, res), 1)
-        x = self.reduction_function(metric, x, info, B, T, P)
-        return x + self.drop_path(self.mlp(self.norm2(x)))
+        x = self.reduction_function(metric, x, info, B, T, P, norm=self.norm2)
+        return x + self.drop_path(self.mlp(_normed_or(self.norm2, x, info)))
 
 
 class ToMeAttentionMixin:
@@ -92,8 +92,9 @@ def _merge_frames_generic(merge, x, info, B, T, P):
     return _frames_back(cls, merged_x, B, T)
 
 
-def timesformer_merge(metric, x, _tome_info, B, T, num_spatial_tokens):
+def timesformer_merge(metric, x, _tome_info, B, T, num_spatial_tokens, norm=None):
     """timesformer.py:85-109."""
+    _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
     if r > 0:
         merge, _ = bipartite_soft_matching(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
@@ -102,7 +103,10 @@ def timesformer_merge(metric, x, _tome_info, B, T, num_spatial_tokens):
         if isinstance(merge, Merge):
             if _tome_info["trace_source"]:
                 _tome_info["source"] = merge.source(_tome_info["source"])
-            x, _tome_info["size"], _tome_info["log_size"] = merge.wavg_frames(x, T, _tome_info["size"])
+            fn = fusable_norm(norm, x) if norm is not None else None
+            res = merge.wavg_frames(x, T, _tome_info["size"], norm=fn)
+            x, _tome_info["size"], _tome_info["log_size"] = res[0], res[1], res[2]
+            _tome_info["normed"] = res[3] if fn is not None else None
         else:
             x = _merge_frames_generic(merge, x, _tome_info, B, T, num_spatial_tokens)
         if _tome_info['verbose']:
@@ -110,8 +114,9 @@ def timesformer_merge(metric, x, _tome_info, B, T, num_spatial_tokens):
     return x
 
 
-def timesformer_drop(metric, x, _tome_info, B, T, num_spatial_tokens):
+def timesformer_drop(metric, x, _tome_info, B, T, num_spatial_tokens, norm=None):
     """timesformer.py:112-140."""
+    _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
     if r > 0:
         drop = bipartite_soft_matching_drop(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
@@ -136,8 +141,9 @@ def timesformer_drop(metric, x, _tome_info, B, T, num_spatial_tokens):
     return x
 
 
-def timesformer_hybrid(metric, x, _tome_info, B, T, num_spatial_tokens):
+def timesformer_hybrid(metric, x, _tome_info, B, T, num_spatial_tokens, norm=None):
     """timesformer.py:143-167."""
+    _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
     if r > 0:
         merge, _ = bipartite_soft_matching_hybrid(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
@@ -146,7 +152,10 @@ def timesformer_hybrid(metric, x, _tome_info, B, T, num_spatial_tokens):
         if isinstance(merge, Merge):
             if _tome_info["trace_source"]:
                 _tome_info["source"] = merge.source(_tome_info["source"])
-            x, _tome_info["size"], _tome_info["log_size"] = merge.wavg_frames(x, T, _tome_info["size"])
+            fn = fusable_norm(norm, x) if norm is not None else None
+            res = merge.wavg_frames(x, T, _tome_info["size"], norm=fn)
+            x, _tome_info["size"], _tome_info["log_size"] = res[0], res[1], res[2]
+            _tome_info["normed"] = res[3] if fn is not None else None
         else:
             x = _merge_frames_generic(merge, x, _tome_info, B, T, num_spatial_tokens)
         if _tome_info['verbose']:
@@ -170,6 +179,7 @@ def make_tome_class(transformer_class):
             self._tome_info["r"] = parse_r(len(self.model.blocks), self.r)
             self._tome_info["size"] = None
             self._tome_info["log_size"] = None
+            self._tome_info["normed"] = None
             self._tome_info["source"] = None
             return super().forward(*args, **kwdargs)
 
@@ -189,6 +199,7 @@ def apply_patch(model_wrapper, trace_source: bool = False, prop_attn: bool = Tru
         "r": model_wrapper.r,
         "size": None,
         "log_size": None,
+        "normed": None,
         "source": None,
         "trace_source": trace_source,
         "prop_attn": prop_attn,

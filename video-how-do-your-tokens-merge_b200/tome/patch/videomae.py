@@ -21,6 +21,25 @@ from tome.merge import (Merge, bipartite_soft_matching, bipartite_soft_matching_
 from tome.utils import parse_r
 
 
+def fusable_norm(norm, x):
+    """(weight, bias, eps) when ``norm`` is a LayerNorm kernel 3 can apply in its own pass (inference,
+    affine, over the channel axis, same dtype/device as x); None otherwise."""
+    if (isinstance(norm, torch.nn.LayerNorm) and not norm.training and not torch.is_grad_enabled()
+            and norm.elementwise_affine and tuple(norm.normalized_shape) == (x.shape[-1],) and x.is_cuda
+            and norm.weight.dtype == x.dtype and norm.weight.device == x.device
+            and x.dtype in (torch.float32, torch.bfloat16)
+            and x.shape[-1] % (8 if x.dtype == torch.bfloat16 else 4) == 0
+            and x.shape[-1] <= (2048 if x.dtype == torch.bfloat16 else 1024)):
+        return norm.weight, norm.bias, norm.eps
+    return None
+
+
+def _normed_or(norm, x, info):
+    """LayerNorm(x): taken from the merge kernel's fused output when it produced one for this x."""
+    y = info.pop("normed", None)
+    return y if y is not None and y.shape == x.shape else norm(x)
+
+
 class ToMeBlockMixin:
     """videomae.py:13-30."""
 
@@ -31,12 +50,12 @@ class ToMeBlockMixin:
         attn, metric = self.attn(self.norm1(x), attn_size, info["head_aggregation"], attn_bias)
         if self.gamma_1 is None:
             x = x + self.drop_path(attn)
-            x = self.reduction_function(metric, x, info)
-            x = x + self.drop_path(self.mlp(self.norm2(x)))
+            x = self.reduction_function(metric, x, info, norm=self.norm2)
+            x = x + self.drop_path(self.mlp(_normed_or(self.norm2, x, info)))
         else:
             x = x + self.drop_path(self.gamma_1 * attn)
-            x = self.reduction_function(metric, x, info)
-            x = x + self.drop_path(self.gamma_2 * self.mlp(self.norm2(x)))
+            x = self.reduction_function(metric, x, info, norm=self.norm2)
+            x = x + self.drop_path(self.gamma_2 * self.mlp(_normed_or(self.norm2, x, info)))
         return x
 
 
@@ -58,7 +77,16 @@ class ToMeAttentionMixin:
         B, N, C = x.shape
         qkv_bias = None
         if self.q_bias is not None:
-            qkv_bias = torch.cat((self.q_bias, torch.zeros_like(self.v_bias, requires_grad=False), self.v_bias))
+            if self.training or torch.is_grad_enabled():
+                qkv_bias = torch.cat((self.q_bias, torch.zeros_like(self.v_bias, requires_grad=False), self.v_bias))
+            else:
+                # inference: build (q_bias, 0, v_bias) once instead of a fill + cat per block per forward
+                key = (self.q_bias.data_ptr(), self.v_bias.data_ptr(), self.q_bias._version, self.v_bias._version,
+                       self.q_bias.dtype, self.q_bias.device)
+                if getattr(self, "_tome_qkv_bias_key", None) != key:
+                    self._tome_qkv_bias = torch.cat((self.q_bias, torch.zeros_like(self.v_bias), self.v_bias)).detach()
+                    self._tome_qkv_bias_key = key
+                qkv_bias = self._tome_qkv_bias
         qkv = F.linear(input=x, weight=self.qkv.weight, bias=qkv_bias)
         qkv = qkv.reshape(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4)
         q, k, v = qkv[0], qkv[1], qkv[2]
@@ -82,8 +110,19 @@ class ToMeAttentionMixin:
         return x, metric
 
 
-def videomae_merge(metric, x, _tome_info):
+def _wavg(merge, x, info, norm):
+    """merge_wavg through the fused kernel: x', sizes, log sizes and (when the following LayerNorm is
+    fusable) LayerNorm(x') stashed in info["normed"] for the block to pick up."""
+    fn = fusable_norm(norm, x) if norm is not None else None
+    res = merge.wavg(x, info["size"], norm=fn)
+    info["size"], info["log_size"] = res[1], res[2]
+    info["normed"] = res[3] if fn is not None else None
+    return res[0]
+
+
+def videomae_merge(metric, x, _tome_info, norm=None):
     """videomae.py:80-100."""
+    _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
     if r > 0:
         merge, _ = bipartite_soft_matching(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
@@ -92,7 +131,7 @@ def videomae_merge(metric, x, _tome_info):
             _tome_info["source"] = merge_source(merge, x, _tome_info["source"])
         pre_merge = x.size(1)
         if isinstance(merge, Merge):
-            x, _tome_info["size"], _tome_info["log_size"] = merge.wavg(x, _tome_info["size"])
+            x = _wavg(merge, x, _tome_info, norm)
         else:
             x, _tome_info["size"] = merge_wavg(merge, x, _tome_info["size"])
             _tome_info["log_size"] = None
@@ -101,8 +140,9 @@ def videomae_merge(metric, x, _tome_info):
     return x
 
 
-def videomae_drop(metric, x, _tome_info):
+def videomae_drop(metric, x, _tome_info, norm=None):
     """videomae.py:103-126."""
+    _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
     if r > 0:
         drop = bipartite_soft_matching_drop(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
@@ -123,8 +163,9 @@ def videomae_drop(metric, x, _tome_info):
     return x
 
 
-def videomae_hybrid(metric, x, _tome_info):
+def videomae_hybrid(metric, x, _tome_info, norm=None):
     """videomae.py:129-151."""
+    _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
     if r > 0:
         merge, _ = bipartite_soft_matching_hybrid(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
@@ -133,7 +174,7 @@ def videomae_hybrid(metric, x, _tome_info):
             _tome_info["source"] = merge_source(merge, x, _tome_info["source"])
         pre_merge = x.size(1)
         if isinstance(merge, Merge):
-            x, _tome_info["size"], _tome_info["log_size"] = merge.wavg(x, _tome_info["size"])
+            x = _wavg(merge, x, _tome_info, norm)
         else:
             x, _tome_info["size"] = merge_wavg(merge, x, _tome_info["size"])
             _tome_info["log_size"] = None
@@ -180,6 +221,7 @@ def make_tome_class(transformer_class):
             self._tome_info["r"] = parse_r(len(self.model.blocks), self.r)
             self._tome_info["size"] = None
             self._tome_info["log_size"] = None
+            self._tome_info["normed"] = None
             self._tome_info["source"] = None
             return super().forward(*args, **kwdargs)
 
@@ -199,6 +241,7 @@ def apply_patch(model_wrapper, trace_source: bool = False, prop_attn: bool = Fal
         "r": model_wrapper.r,
         "size": None,
         "log_size": None,
+        "normed": None,
         "source": None,
         "trace_source": trace_source,
         "prop_attn": prop_attn,

@@ -16,7 +16,7 @@ import torch.nn.functional as F
 
 from tome.merge import (Merge, bipartite_soft_matching, bipartite_soft_matching_drop,
                         bipartite_soft_matching_hybrid, merge_source, merge_wavg)
-from tome.patch.videomae import _swap
+from tome.patch.videomae import _normed_or, _swap, _wavg
 from tome.utils import parse_r
 
 
@@ -30,8 +30,8 @@ class ToMeVivitLayerMixin:
         attention_output, metric = self.attention(self.layernorm_before(hidden_states), attn_size,
                                                   info["head_aggregation"], attn_bias)
         hidden_states = attention_output + hidden_states                       # first residual
-        hidden_states = self.reduction_function(metric, hidden_states, info)
-        layer_output = self.output(self.intermediate(self.layernorm_after(hidden_states)), hidden_states)
+        hidden_states = self.reduction_function(metric, hidden_states, info, norm=self.layernorm_after)
+        layer_output = self.output(self.intermediate(_normed_or(self.layernorm_after, hidden_states, info)), hidden_states)
         return (layer_output,) if self._tome_tuple_api else layer_output
 
 
@@ -80,8 +80,9 @@ class ToMeVivitSelfAttentionMixin:
         return ctx, metric
 
 
-def vivit_merge(metric, x, _tome_info):
+def vivit_merge(metric, x, _tome_info, norm=None):
     """vivit.py:133-153."""
+    _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
     if r > 0:
         merge, _ = bipartite_soft_matching(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
@@ -90,7 +91,7 @@ def vivit_merge(metric, x, _tome_info):
             _tome_info["source"] = merge_source(merge, x, _tome_info["source"])
         pre_merge = x.size(1)
         if isinstance(merge, Merge):
-            x, _tome_info["size"], _tome_info["log_size"] = merge.wavg(x, _tome_info["size"])
+            x = _wavg(merge, x, _tome_info, norm)
         else:
             x, _tome_info["size"] = merge_wavg(merge, x, _tome_info["size"])
             _tome_info["log_size"] = None
@@ -99,8 +100,9 @@ def vivit_merge(metric, x, _tome_info):
     return x
 
 
-def vivit_drop(metric, x, _tome_info):
+def vivit_drop(metric, x, _tome_info, norm=None):
     """vivit.py:156-179."""
+    _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
     if r > 0:
         drop = bipartite_soft_matching_drop(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
@@ -121,8 +123,9 @@ def vivit_drop(metric, x, _tome_info):
     return x
 
 
-def vivit_hybrid(metric, x, _tome_info):
+def vivit_hybrid(metric, x, _tome_info, norm=None):
     """vivit.py:182-204."""
+    _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
     if r > 0:
         merge, _ = bipartite_soft_matching_hybrid(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
@@ -131,7 +134,7 @@ def vivit_hybrid(metric, x, _tome_info):
             _tome_info["source"] = merge_source(merge, x, _tome_info["source"])
         pre_merge = x.size(1)
         if isinstance(merge, Merge):
-            x, _tome_info["size"], _tome_info["log_size"] = merge.wavg(x, _tome_info["size"])
+            x = _wavg(merge, x, _tome_info, norm)
         else:
             x, _tome_info["size"] = merge_wavg(merge, x, _tome_info["size"])
             _tome_info["log_size"] = None
@@ -177,6 +180,7 @@ def make_tome_class(transformer_class):
             self._tome_info["r"] = parse_r(len(self.vivit.encoder.layer), self.r)
             self._tome_info["size"] = None
             self._tome_info["log_size"] = None
+            self._tome_info["normed"] = None
             self._tome_info["source"] = None
             return super().forward(*args, **kwdargs)
 
@@ -196,6 +200,7 @@ def apply_patch(model_wrapper, trace_source: bool = False, prop_attn: bool = Tru
         "r": model_wrapper.r,
         "size": None,
         "log_size": None,
+        "normed": None,
         "source": None,
         "trace_source": trace_source,
         "prop_attn": prop_attn,
