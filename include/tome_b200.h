@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 5
+#define TOME_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define TOME_API __attribute__((visibility("default")))
@@ -120,6 +120,16 @@ TOME_API int tome_match(const void* metric, int32_t dtype, int32_t bm, int32_t n
                const tome_view* view, int32_t class_token, int32_t distill_token, int32_t algo,
                float* node_max, int32_t* node_idx, void* workspace, size_t workspace_bytes,
                void* stream);
+
+/* tome_match on metric = mean over heads of K, without materialising the mean
+ * (tome/patch/videomae.py:72-73, timesformer.py:83, motionformer.py:143-144, vivit.py:123-124):
+ * keys element (b, h, t, k) lives at  base + view(b, t) + h * stride_h + k.  The mean is rounded to
+ * `dtype` before normalisation, as the reference's k.mean(1) tensor is.  Workspace as tome_match
+ * with TOME_MATCH_TCGEN05. */
+TOME_API int tome_match_heads(const void* keys, int32_t dtype, int32_t bm, int32_t heads, int32_t n, int32_t cm,
+                     const tome_view* view, int64_t stride_h, int32_t class_token, int32_t distill_token,
+                     float* node_max, int32_t* node_idx, void* workspace, size_t workspace_bytes,
+                     void* stream);
 
 /* Row max/argmax of a MATERIALISED (bm, na, nb) fp32 score tensor, same masking and tie
  * rule.  Serves the random_merge / random_drop modes, whose scores are torch.rand

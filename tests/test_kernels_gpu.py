@@ -327,3 +327,34 @@ def test_fused_layernorm_matches_separate_pass(native, dtype):
     want2 = torch.nn.functional.layer_norm(o2.float(), (c,), w.float(), b.float(), 1e-6)
     torch.testing.assert_close(n2.float(), want2, **tol)
     assert torch.equal(o2, native.merge_frames(dp, xf, T, "wavg")[0])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_match_heads_equals_match_of_mean(native, dtype):
+    """tome_match_heads (head-mean taken in kernel 1's prologue) against tome_match on k.mean(1)."""
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    B, H, N, d = 3, 12, 197, 64
+    qkv = torch.randn(B, N, 3, H, d, device="cuda", generator=gen).to(dtype)
+    k = qkv.permute(2, 0, 3, 1, 4)[1]                                  # (B, H, N, d) strided view, as in the patches
+    nm, ni = native.match_heads(native.HeadMeanMetric(k), True, False)
+    if dtype == torch.float32:
+        # the kernel adds heads 0..H-1 sequentially in fp32: same values as an explicit sequential sum
+        seq = torch.zeros(B, N, d, device="cuda")
+        for h in range(H):
+            seq = seq + k[:, h]
+        ref = seq * (1.0 / H)                                           # ATen's mean multiplies by 1/H
+    else:
+        ref = k.float().mean(1).to(dtype)
+    onm, oni = O.match(ref.float().cpu().numpy(), True, False)
+    agree = (ni.cpu().numpy() == oni).mean()
+    assert agree > 0.999, agree                                         # bf16: the mean's rounding may differ in rare ties
+    if dtype == torch.float32:
+        np.testing.assert_array_equal(ni.cpu().numpy(), oni)
+        np.testing.assert_array_equal(nm.cpu().numpy(), onm)
+    # Motionformer regrouping: (B, H, S*F, d) with tokens '(s f)' -> batch (b f)
+    F_, S = 4, 49
+    k2 = torch.randn(2, H, S * F_, d, device="cuda", generator=gen).to(dtype)
+    m2 = native.HeadMeanMetric(k2, frames=F_)
+    nm2, ni2 = native.match_heads(m2)
+    nm3, ni3 = native.match(m2.materialize().contiguous())
+    assert (ni2 == ni3).float().mean() > 0.999

@@ -76,6 +76,11 @@ def main():
     for algo, name in ((2, "match_tc"), (1, "match_exact")):
         med, best = graph_time([lambda i=i: _native.match(ms[i % nrot], bool(a.cls), algo=algo) for i in range(8)])
         out[name] = dict(us=med, us_best=best, tflops_alg=flops / med / 1e6)
+    ks = [torch.randn(bm, n, 3, 12, cm, device=dev, dtype=dt, generator=g).permute(2, 0, 3, 1, 4)[1] for _ in range(4)]
+    med, best = graph_time([lambda i=i: _native.match_heads(_native.HeadMeanMetric(ks[i % 4]), bool(a.cls)) for i in range(8)])
+    out["match_heads12"] = dict(us=med, us_best=best)
+    med, best = graph_time([lambda i=i: _native.match(ks[i % 4].mean(1), bool(a.cls)) for i in range(8)])
+    out["torch_mean_then_match"] = dict(us=med, us_best=best)
     med, best = graph_time([lambda: _native.select(nm, ni, n, r, bool(a.cls)) for _ in range(8)])
     out["select"] = dict(us=med, us_best=best)
     med, best = graph_time([lambda: _native.merge_source(plan, None) for _ in range(4)])

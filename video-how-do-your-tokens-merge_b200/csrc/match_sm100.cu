@@ -50,9 +50,12 @@ struct TcParams {
 // ---------------------------------------------------------------------------------------------
 // 1. normalise + hi/lo split
 // ---------------------------------------------------------------------------------------------
+// `heads` > 1: the metric is the head-mean of K (tome/patch/videomae.py:72-73 `k.mean(1)`), taken here
+// instead of in a separate reduction kernel: element (b, t, k) = mean_h keys[b, h, t, k], rounded to
+// the input dtype first (what the reference's k.mean(1) tensor holds), then normalised.
 template <typename T>
-__global__ void __launch_bounds__(256) split_rows_kernel(const T* __restrict__ metric, View v, int bm, int n, int cm,
-                                                         float* __restrict__ split,
+__global__ void __launch_bounds__(256) split_rows_kernel(const T* __restrict__ metric, View v, int heads, long long stride_h,
+                                                         int bm, int n, int cm, float* __restrict__ split,
                                                          unsigned long long* __restrict__ keys,
                                                          int* __restrict__ strip_count, int n_strips) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -63,21 +66,61 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const T* __restrict__ m
     if (warp < n_strips) strip_count[warp] = 0;
   }
   const T* src = metric + v.batch_offset(b) + (long long)t * v.sn;
+  const int row = (t & 1) ? na + (t >> 1) : (t >> 1);
+  float* hi = split + ((long long)b * n + row) * cm;
+  float* lo = hi + (long long)bm * n * cm;
+  auto value = [&](int k) -> float {
+    if (heads == 1) return ld_as_float(src + k);
+    float s = 0.f;                 // heads added in order; 1/H multiply like ATen's MeanOps
+    int h = 0;
+    for (; h + 4 <= heads; h += 4) {          // four loads in flight, adds kept sequential
+      const float a0 = ld_as_float(src + (long long)(h + 0) * stride_h + k);
+      const float a1 = ld_as_float(src + (long long)(h + 1) * stride_h + k);
+      const float a2 = ld_as_float(src + (long long)(h + 2) * stride_h + k);
+      const float a3 = ld_as_float(src + (long long)(h + 3) * stride_h + k);
+      s = ((s + a0) + a1) + a2;
+      s = s + a3;
+    }
+    for (; h < heads; ++h) s += ld_as_float(src + (long long)h * stride_h + k);
+    s = s * (1.0f / (float)heads);
+    if (sizeof(T) == 2) s = __bfloat162float(__float2bfloat16_rn(s));
+    return s;
+  };
+  if (cm <= 128) {                 // whole row in registers: one pass over global memory
+    float x[4];
+    double ss = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = lane + 32 * q;
+      x[q] = k < cm ? value(k) : 0.f;
+      ss = fma((double)x[q], (double)x[q], ss);
+    }
+    ss = warp_sum(ss);
+    const float norm = (float)sqrt(ss);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = lane + 32 * q;
+      if (k < cm) {
+        const float m = __fdiv_rn(x[q], norm);
+        const float h = __uint_as_float(__float_as_uint(m) & 0xFFFFE000u);
+        hi[k] = h;
+        lo[k] = m - h;             // exact: fewer than 24 significant bits remain
+      }
+    }
+    return;
+  }
   double ss = 0.0;
   for (int k = lane; k < cm; k += 32) {
-    const double x = (double)ld_as_float(src + k);
+    const double x = (double)value(k);
     ss = fma(x, x, ss);
   }
   ss = warp_sum(ss);
   const float norm = (float)sqrt(ss);
-  const int row = (t & 1) ? na + (t >> 1) : (t >> 1);
-  float* hi = split + ((long long)b * n + row) * cm;
-  float* lo = hi + (long long)bm * n * cm;
   for (int k = lane; k < cm; k += 32) {
-    const float m = __fdiv_rn(ld_as_float(src + k), norm);
+    const float m = __fdiv_rn(value(k), norm);
     const float h = __uint_as_float(__float_as_uint(m) & 0xFFFFE000u);
     hi[k] = h;
-    lo[k] = m - h;     // exact: fewer than 24 significant bits remain
+    lo[k] = m - h;
   }
 }
 
@@ -562,7 +605,8 @@ static int make_map(CUtensorMap* map, float* base, int rows, int cm, int box_row
 }
 
 int launch_match_tc(const void* metric, int dtype, int bm, int n, int cm, const View& v, int cls, int distill,
-                    float* node_max, int* node_idx, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    float* node_max, int* node_idx, void* ws, size_t ws_bytes, cudaStream_t st, int heads,
+                    long long stride_h) {
   if (ws_bytes < match_tc_workspace(bm, n, cm))
     return set_error(TOME_ERR_WORKSPACE, "tome_match: workspace %zu < %zu bytes", ws_bytes, match_tc_workspace(bm, n, cm));
   TcParams p;
@@ -582,9 +626,9 @@ int launch_match_tc(const void* metric, int dtype, int bm, int n, int cm, const 
 
   const int blocks = (int)(((long long)bm * n * 32 + 255) / 256);
   if (dtype == TOME_F32)
-    split_rows_kernel<float><<<blocks, 256, 0, st>>>((const float*)metric, v, bm, n, cm, split, p.keys, p.strip_count, bm * n_rt);
+    split_rows_kernel<float><<<blocks, 256, 0, st>>>((const float*)metric, v, heads, stride_h, bm, n, cm, split, p.keys, p.strip_count, bm * n_rt);
   else
-    split_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)metric, v, bm, n, cm, split, p.keys, p.strip_count, bm * n_rt);
+    split_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)metric, v, heads, stride_h, bm, n, cm, split, p.keys, p.strip_count, bm * n_rt);
   TOME_LAUNCH_CHECK("split_rows_kernel");
 
   alignas(64) CUtensorMap map_a, map_b;

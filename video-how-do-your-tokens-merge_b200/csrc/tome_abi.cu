@@ -54,7 +54,7 @@ int launch_match_exact(const void*, int, int, int, int, const View&, int, int, f
 int launch_rowmax(const float*, int, int, int, int, int, float*, int*, cudaStream_t);
 size_t match_tc_workspace(int bm, int n, int cm);
 bool match_tc_supported(int dtype, int bm, int n, int cm, const View& v, const void* metric);
-int launch_match_tc(const void*, int, int, int, int, const View&, int, int, float*, int*, void*, size_t, cudaStream_t);
+int launch_match_tc(const void*, int, int, int, int, const View&, int, int, float*, int*, void*, size_t, cudaStream_t, int, long long);
 size_t select_workspace(int bm, int n);
 int launch_select(const tome_plan*, void*, size_t, cudaStream_t);
 int launch_merge(const tome_plan*, const void*, int, int, const View&, const float*, int, float, void*, const View&,
@@ -118,11 +118,27 @@ int tome_match(const void* metric, int32_t dtype, int32_t bm, int32_t n, int32_t
     if (!match_tc_supported(dtype, bm, n, cm, v, metric))
       return set_error(TOME_ERR_UNSUPPORTED, "tome_match: tcgen05 path needs contiguous fp32/bf16 metric, cm %% 32 == 0, cm <= 1024 (got cm=%d)", cm);
     return launch_match_tc(metric, dtype, bm, n, cm, v, class_token, distill_token, node_max, node_idx, workspace,
-                           workspace_bytes, st);
+                           workspace_bytes, st, 1, 0);
   }
   if (algo != TOME_MATCH_EXACT_SIMT) return set_error(TOME_ERR_ARG, "tome_match: unknown algo %d", algo);
   return launch_match_exact(metric, dtype, bm, n, cm, v, class_token, distill_token, node_max, node_idx, workspace,
                             workspace_bytes, st);
+}
+
+int tome_match_heads(const void* keys, int32_t dtype, int32_t bm, int32_t heads, int32_t n, int32_t cm,
+                     const tome_view* view, int64_t stride_h, int32_t class_token, int32_t distill_token,
+                     float* node_max, int32_t* node_idx, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(keys && node_max && node_idx && workspace && view, "tome_match_heads: NULL pointer argument");
+  TOME_CHECK_ARG(bm > 0 && n >= 2 && cm > 0 && heads >= 1, "tome_match_heads: bad shape bm=%d heads=%d n=%d cm=%d", bm, heads, n, cm);
+  if (dtype != TOME_F32 && dtype != TOME_BF16) return set_error(TOME_ERR_DTYPE, "tome_match_heads: unsupported dtype %d", dtype);
+  TOME_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "tome_match_heads: workspace must be 256-byte aligned");
+  const View v = make_view(view, n, cm);
+  if (!match_tc_supported(dtype, bm, n, cm, v, keys))
+    return set_error(TOME_ERR_UNSUPPORTED, "tome_match_heads: needs cm %% 4 == 0 (got cm=%d); average the heads and call tome_match", cm);
+  return launch_match_tc(keys, dtype, bm, n, cm, v, class_token, distill_token, node_max, node_idx, workspace,
+                         workspace_bytes, (cudaStream_t)stream, heads, stride_h);
 }
 
 int tome_rowmax(const float* scores, int32_t bm, int32_t na, int32_t nb, int32_t class_token, int32_t distill_token,

@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 TOME_F32, TOME_BF16 = 0, 1
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -26,7 +26,7 @@ _MODES = {"wavg": MODE_WAVG, "sum": MODE_SUM, "mean": MODE_MEAN, "max": MODE_AMA
           "drop": MODE_DROP}
 
 EXPORTS = (
-    "tome_abi_version", "tome_last_error", "tome_launch_count", "tome_device_check", "tome_match_workspace_bytes", "tome_match",
+    "tome_abi_version", "tome_last_error", "tome_launch_count", "tome_device_check", "tome_match_workspace_bytes", "tome_match", "tome_match_heads",
     "tome_rowmax", "tome_select_workspace_bytes", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_source",
     "tome_unmerge",
 )
@@ -75,6 +75,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.tome_match_workspace_bytes.argtypes = [c_i32, c_i32, c_i32, c_i32]
     lib.tome_match.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(TomeViewC), c_i32, c_i32, c_i32,
                                c_vp, c_vp, c_vp, c_sz, c_vp]
+    lib.tome_match_heads.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(TomeViewC), ctypes.c_int64,
+                                     c_i32, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]
     lib.tome_rowmax.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]
     lib.tome_select_workspace_bytes.restype = c_sz
     lib.tome_select_workspace_bytes.argtypes = [c_i32, c_i32]
@@ -86,7 +88,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
                                     ctypes.POINTER(TomeViewC), c_vp]
     lib.tome_merge_source.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_f32, c_vp, c_vp]
     lib.tome_unmerge.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_i32, c_vp, c_vp]
-    for name in ("tome_device_check", "tome_match", "tome_rowmax", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_source",
+    for name in ("tome_device_check", "tome_match", "tome_match_heads", "tome_rowmax", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_source",
                  "tome_unmerge"):
         getattr(lib, name).restype = c_i32
     if lib.tome_abi_version() != ABI_VERSION:
@@ -208,6 +210,63 @@ def match(metric: torch.Tensor, class_token=False, distill_token=False, algo: in
                               node_idx.data_ptr(), ws.data_ptr(), ws_bytes, _stream(metric)), lib)
     if _return_workspace:          # tests only: lets them inspect the tensor-core pass's pruning
         return node_max, node_idx, ws
+    return node_max, node_idx
+
+
+class HeadMeanMetric:
+    """A matching metric that is the mean over heads of an attention key tensor, kept lazy so kernel 1's
+    prologue takes the mean itself (no separate reduction kernel, no metric tensor in HBM).
+
+    ``keys`` is any (Bm, H, N, d) view with unit channel stride; ``frames`` > 1 says the Bm axis is
+    (b f) over a (B, H, S*F, d) tensor whose token axis is '(s f)' -- Motionformer's regrouping
+    (tome/patch/motionformer.py:143-144)."""
+
+    def __init__(self, keys: torch.Tensor, frames: int = 1):
+        self.keys, self.frames = keys, int(frames)
+        if self.frames == 1:
+            bm, h, n, d = keys.shape
+        else:
+            b, h, sf, d = keys.shape
+            bm, n = b * self.frames, sf // self.frames
+        self.shape = (bm, n, d)
+        self.heads = h
+        self.dtype, self.device = keys.dtype, keys.device
+        self.is_cuda = keys.is_cuda
+
+    def size(self, i):
+        return self.shape[i]
+
+    def materialize(self) -> torch.Tensor:
+        k = self.keys
+        if self.frames == 1:
+            return k.mean(1)
+        b, h, sf, d = k.shape
+        f = self.frames
+        return k.reshape(b, h, sf // f, f, d).permute(0, 3, 1, 2, 4).mean(2).reshape(b * f, sf // f, d)
+
+
+def match_heads(metric: "HeadMeanMetric", class_token=False, distill_token=False):
+    """Kernel 1 on a lazy head-mean metric."""
+    lib = load_library()
+    k = metric.keys
+    _require_cuda(k, "keys")
+    bm, n, cm = metric.shape
+    if k.dtype not in (torch.float32, torch.bfloat16) or k.stride(3) != 1 or cm % 4 != 0:
+        return match(metric.materialize(), class_token, distill_token)
+    f = metric.frames
+    if f == 1:
+        view = TomeViewC(k.stride(0), 0, k.stride(2), 1)
+    else:                                   # batch (b f): b steps by stride(0), f by one token; tokens step by f
+        view = TomeViewC(k.stride(0), k.stride(2), f * k.stride(2), f)
+    na = (n + 1) // 2
+    with torch.cuda.device(k.device):
+        node_max = torch.empty(bm, na, dtype=torch.float32, device=k.device)
+        node_idx = torch.empty(bm, na, dtype=torch.int32, device=k.device)
+        ws_bytes = lib.tome_match_workspace_bytes(bm, n, cm, MATCH_TCGEN05)
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=k.device)
+        _check(lib.tome_match_heads(k.data_ptr(), _dtype_code(k), bm, metric.heads, n, cm, ctypes.byref(view),
+                                    k.stride(1), int(bool(class_token)), int(bool(distill_token)),
+                                    node_max.data_ptr(), node_idx.data_ptr(), ws.data_ptr(), ws_bytes, _stream(k)), lib)
     return node_max, node_idx
 
 

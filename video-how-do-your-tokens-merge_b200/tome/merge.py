@@ -36,13 +36,15 @@ def _effective_r(metric: torch.Tensor, r: int, class_token: bool, distill_token:
 
 
 def _make_plan(metric, r, class_token, distill_token, random_scores: bool) -> "_native.DevicePlan":
-    _native._require_cuda(metric, "metric")
+    _native._require_cuda(metric if not isinstance(metric, _native.HeadMeanMetric) else metric.keys, "metric")
     with torch.no_grad():
         if random_scores:                          # merge.py:54-57: same torch.rand call, same generator
             length = metric.size(1)
             len_a, len_b = (length + 1) // 2, length // 2
             scores = torch.rand(size=(metric.size(0), len_a, len_b), device=metric.device)
             node_max, node_idx = _native.rowmax(scores, class_token, distill_token)
+        elif isinstance(metric, _native.HeadMeanMetric):
+            node_max, node_idx = _native.match_heads(metric, class_token, distill_token)
         else:
             node_max, node_idx = _native.match(metric, class_token, distill_token)
         return _native.select(node_max, node_idx, metric.shape[1], r, class_token, distill_token)

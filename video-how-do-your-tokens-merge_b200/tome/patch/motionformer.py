@@ -12,7 +12,7 @@ import torch.nn.functional as F
 from tome.merge import (Drop, Merge, bipartite_soft_matching, bipartite_soft_matching_drop,
                         bipartite_soft_matching_hybrid)
 from tome.patch.timesformer import _frames_back, _frames_view, _merge_frames_generic
-from tome.patch.videomae import _normed_or, _swap, fusable_norm
+from tome.patch.videomae import _normed_or, _swap, fusable_norm, lazy_head_mean
 from tome.utils import parse_r
 
 
@@ -82,10 +82,8 @@ class ToMeTrajectoryAttentionMixin:
             # '(b f) s i -> b (s f) i': key j of the flat token axis gets log size[(b, j % F), j // F]
             flat = log_size[..., 0].reshape(B, Fr, S).transpose(1, 2).reshape(B, S * Fr)
         out, k_ = trajectory_attention(self, x, Fr, flat)
-        h, d = self.num_heads, C // self.num_heads
-        # '(b h) (s f) d -> (b f) h s d' then mean over heads
-        metric = k_.reshape(B, h, S, Fr, d).permute(0, 3, 1, 2, 4).mean(2).reshape(B * Fr, S, d)
-        return out, None, metric
+        # '(b h) (s f) d -> (b f) h s d' then mean over heads (motionformer.py:143-144)
+        return out, None, lazy_head_mean(k_, frames=Fr)
 
 
 def motionformer_merge(metric, x, _tome_info, num_frames, norm=None):

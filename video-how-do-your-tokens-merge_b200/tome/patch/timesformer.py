@@ -15,7 +15,7 @@ import torch.nn.functional as F
 
 from tome.merge import (Drop, Merge, bipartite_soft_matching, bipartite_soft_matching_drop,
                         bipartite_soft_matching_hybrid, merge_source, merge_wavg)
-from tome.patch.videomae import _normed_or, _swap, fusable_norm
+from tome.patch.videomae import _normed_or, _swap, fusable_norm, lazy_head_mean
 from tome.utils import parse_r
 
 
@@ -70,7 +70,7 @@ class ToMeAttentionMixin:
         x = x.transpose(1, 2).reshape(B, N, C)
         if self.with_qkv:
             x = self.proj_drop(self.proj(x))
-        return x, k.mean(1)[:, 1:, :]
+        return x, lazy_head_mean(k[:, :, 1:, :])                       # k.mean(1)[:, 1:, :]
 
 
 def _frames_view(x, B, T, P):

@@ -21,6 +21,15 @@ from tome.merge import (Merge, bipartite_soft_matching, bipartite_soft_matching_
 from tome.utils import parse_r
 
 
+def lazy_head_mean(k, frames=1):
+    """``k.mean(1)`` (videomae.py:72-73) -- on the CUDA inference path left to kernel 1's prologue
+    (``tome_match_heads``), which reads K once and never writes the metric out."""
+    from tome import _native
+    if k.is_cuda and not torch.is_grad_enabled() and k.dtype in (torch.float32, torch.bfloat16) and k.stride(-1) == 1:
+        return _native.HeadMeanMetric(k, frames)
+    return _native.HeadMeanMetric(k, frames).materialize()
+
+
 def fusable_norm(norm, x):
     """(weight, bias, eps) when ``norm`` is a LayerNorm kernel 3 can apply in its own pass (inference,
     affine, over the channel axis, same dtype/device as x); None otherwise."""
@@ -102,7 +111,7 @@ class ToMeAttentionMixin:
         x = self.proj_drop(self.proj(x))
 
         if head_aggregation == 'mean':
-            metric = k.mean(1)
+            metric = lazy_head_mean(k)
         elif head_aggregation == 'concat':
             metric = k.transpose(1, 2).reshape(B, N, -1)       # == cat(k.split(1, dim=1), -1).squeeze(1)
         else:

@@ -16,7 +16,7 @@ import torch.nn.functional as F
 
 from tome.merge import (Merge, bipartite_soft_matching, bipartite_soft_matching_drop,
                         bipartite_soft_matching_hybrid, merge_source, merge_wavg)
-from tome.patch.videomae import _normed_or, _swap, _wavg
+from tome.patch.videomae import _normed_or, _swap, _wavg, lazy_head_mean
 from tome.utils import parse_r
 
 
@@ -72,7 +72,7 @@ class ToMeVivitSelfAttentionMixin:
         ctx = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, scale=d ** -0.5)
         ctx = ctx.transpose(1, 2).reshape(B, N, h * d)
         if head_aggregation == 'mean':
-            metric = k.mean(1)
+            metric = lazy_head_mean(k)
         elif head_aggregation == 'concat':
             metric = k.transpose(1, 2).reshape(B, N, h * d)
         else:
