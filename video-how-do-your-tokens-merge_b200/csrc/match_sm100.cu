@@ -480,19 +480,25 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 // ---------------------------------------------------------------------------------------------
 // 3. exact refine (streamed-K path): canonical fp64 score of the surviving candidates
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float exact_score(const float* __restrict__ ah, const float* __restrict__ al,
-                                             const float* __restrict__ bh, const float* __restrict__ bl, int cm) {
+// One WARP per A row: lanes stride k, so every candidate costs four coalesced row reads (hi/lo of A and
+// B) and a warp reduction.  (The first version used one thread per row: at Cm = 768 its uncoalesced,
+// serial 768-step loops took 400 us.)  fp64 partial sums per lane, then a butterfly: the order of the
+// fp64 additions is not part of the score definition (it can move the fp32-rounded result only when
+// the fp64 sum lies within ~1e-16 of a rounding boundary).
+__device__ __forceinline__ float exact_score_warp(const float* __restrict__ ah, const float* __restrict__ al,
+                                                  const float* __restrict__ bh, const float* __restrict__ bl, int cm, int lane) {
   double acc = 0.0;
-  for (int k = 0; k < cm; ++k) acc = fma((double)(ah[k] + al[k]), (double)(bh[k] + bl[k]), acc);
+  for (int k = lane; k < cm; k += 32) acc = fma((double)(ah[k] + al[k]), (double)(bh[k] + bl[k]), acc);
+  acc = warp_sum(acc);
   return (float)acc;
 }
 
-__global__ void __launch_bounds__(128) refine_rows_kernel(const float* __restrict__ split, TcParams p,
+__global__ void __launch_bounds__(256) refine_rows_kernel(const float* __restrict__ split, TcParams p,
                                                           float* __restrict__ node_max, int* __restrict__ node_idx) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t >= p.bm * p.na) return;
   const int b = t / p.na, i = t - b * p.na;
-  if (p.cls && i == 0) { node_max[t] = -INFINITY; node_idx[t] = 0; return; }
+  if (p.cls && i == 0) { if (lane == 0) { node_max[t] = -INFINITY; node_idx[t] = 0; } return; }
   const long long lo_off = (long long)p.rows_total * p.cm;
   const float* ah = split + ((long long)b * p.n + i) * p.cm;
   const float* bbase = split + ((long long)b * p.n + p.na) * p.cm;
@@ -507,21 +513,23 @@ __global__ void __launch_bounds__(128) refine_rows_kernel(const float* __restric
       const int je = min(p.nb, (c + 1) * p.BN);
       for (int j = c * p.BN; j < je; ++j) {
         const float s = (p.distill && j == 0) ? -INFINITY
-                                              : exact_score(ah, ah + lo_off, bbase + (long long)j * p.cm, bbase + (long long)j * p.cm + lo_off, p.cm);
+                                              : exact_score_warp(ah, ah + lo_off, bbase + (long long)j * p.cm, bbase + (long long)j * p.cm + lo_off, p.cm, lane);
         const unsigned long long k = pack_best(s, j);
         best = k > best ? k : best;
       }
     } else if (p.tile_max[o + c] >= thr) {
       for (int s = 0; s < cnt; ++s) {
         const int j = p.tile_cand[(o + c) * KCAND + s];
-        const float sc = exact_score(ah, ah + lo_off, bbase + (long long)j * p.cm, bbase + (long long)j * p.cm + lo_off, p.cm);
+        const float sc = exact_score_warp(ah, ah + lo_off, bbase + (long long)j * p.cm, bbase + (long long)j * p.cm + lo_off, p.cm, lane);
         const unsigned long long k = pack_best(sc, j);
         best = k > best ? k : best;
       }
     }
   }
-  node_max[t] = key_to_float((uint32_t)(best >> 32));
-  node_idx[t] = (int)(0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull));
+  if (lane == 0) {
+    node_max[t] = key_to_float((uint32_t)(best >> 32));
+    node_idx[t] = (int)(0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -646,8 +654,8 @@ int launch_match_tc(const void* metric, int dtype, int bm, int n, int cm, const 
   match_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
   TOME_LAUNCH_CHECK("match_tc_kernel");
   if (!p.resident) {
-    const int total = bm * p.na;
-    refine_rows_kernel<<<(total + 127) / 128, 128, 0, st>>>(split, p, node_max, node_idx);
+    const long long total = (long long)bm * p.na * 32;
+    refine_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(split, p, node_max, node_idx);
     TOME_LAUNCH_CHECK("refine_rows_kernel");
   }
   return TOME_OK;
