@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 6
+#define TOME_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define TOME_API __attribute__((visibility("default")))
@@ -173,6 +173,13 @@ TOME_API int tome_merge_norm(const tome_plan* plan, const void* x, int32_t dtype
  * source == NULL means the implicit identity (n0 == n), generated on the fly. */
 TOME_API int tome_merge_source(const tome_plan* plan, const float* source, int32_t n0,
                       float hybrid_threshold, float* out, void* stream);
+
+/* Caller-side fusion: sum_out = a + b, normed_out = LayerNorm(sum_out) * w + bias for
+ * contiguous (rows, c) tensors -- the residual add that closes a patched block plus the LayerNorm that
+ * opens the next (tome/patch/videomae.py:17-22), one pass instead of two kernels. */
+TOME_API int tome_add_layernorm(const void* a, const void* b, int32_t dtype, int64_t rows, int32_t c,
+                       const void* ln_weight, const void* ln_bias, float ln_eps, void* sum_out,
+                       void* normed_out, void* stream);
 
 /* unmerge (merge.py:87-100): x (bm, n - r, c) -> out (bm, n, c); contiguous tensors. */
 TOME_API int tome_unmerge(const tome_plan* plan, const void* x, int32_t dtype, int32_t c, void* out,

@@ -358,3 +358,26 @@ def test_match_heads_equals_match_of_mean(native, dtype):
     nm2, ni2 = native.match_heads(m2)
     nm3, ni3 = native.match(m2.materialize().contiguous())
     assert (ni2 == ni3).float().mean() > 0.999
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(8, 1568, 768), (3, 197, 384), (2, 50, 1024)])
+def test_add_layernorm_matches_two_passes(native, dtype, shape):
+    """tome_add_layernorm: the sum is bit-identical to torch's a + b, the LayerNorm equals torch's
+    LayerNorm of that sum (fp32: round-off; bf16: one output ulp)."""
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    c = shape[-1]
+    a = torch.randn(*shape, device="cuda", generator=gen).to(dtype)
+    b = torch.randn(*shape, device="cuda", generator=gen).to(dtype)
+    w = (1 + 0.1 * torch.randn(c, device="cuda", generator=gen)).to(dtype)
+    bias = (0.1 * torch.randn(c, device="cuda", generator=gen)).to(dtype)
+    s, y = native.add_layernorm(a, b, (w, bias, 1e-6))
+    assert torch.equal(s, a + b)
+    want = torch.nn.functional.layer_norm((a + b).float(), (c,), w.float(), bias.float(), 1e-6)
+    tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=1.6e-2, atol=1.6e-2)
+    torch.testing.assert_close(y.float(), want, **tol)
+    s2, y2 = native.add_layernorm(a, b, (w, None, 1e-6))
+    want2 = torch.nn.functional.layer_norm((a + b).float(), (c,), w.float(), None, 1e-6)
+    torch.testing.assert_close(y2.float(), want2, **tol)
+    with pytest.raises(RuntimeError):
+        native.add_layernorm(a, b[:, :-1], (w, bias, 1e-6))

@@ -575,6 +575,99 @@ int launch_merge(const tome_plan* plan, const void* x, int dtype, int c, const V
   return set_error(TOME_ERR_DTYPE, "tome_merge: unsupported dtype %d", dtype);
 }
 
+// ---- caller-side fusion: residual add + LayerNorm in one pass -------------------------------------
+// The patched blocks end with  x = x + mlp(norm2(x))  and the next block starts with norm1(x)
+// (tome/patch/videomae.py:17-22).  torch runs that as an add kernel plus a LayerNorm kernel (5.5 + 14.4 us
+// at the bench shape); here one warp per row adds, writes the sum, and normalises it while it is
+// still in registers.
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) add_layernorm_kernel(const T* __restrict__ a, const T* __restrict__ b2, long long rows,
+                                                           int c, const T* __restrict__ w, const T* __restrict__ bias, float eps,
+                                                           T* __restrict__ sum_out, T* __restrict__ normed) {
+  constexpr int E = Pack<T>::E;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = c / E;
+  const uint4* ar = reinterpret_cast<const uint4*>(a + row * c);
+  const uint4* br = reinterpret_cast<const uint4*>(b2 + row * c);
+  uint4 va[NV], vb[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) { const int i = v * 32 + lane; if (i < nvec) { va[v] = ld_stream_u4(ar + i); vb[v] = ld_stream_u4(br + i); } }
+  float sum = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int i = v * 32 + lane;
+    if (i < nvec) {
+      float fa[E], fb[E];
+      Pack<T>::unpack(va[v], fa);
+      Pack<T>::unpack(vb[v], fb);
+#pragma unroll
+      for (int e = 0; e < E; ++e) fa[e] = fa[e] + fb[e];
+      va[v] = Pack<T>::pack(fa);                    // rounded to T: what x + y holds in the reference
+      Pack<T>::unpack(va[v], fa);
+#pragma unroll
+      for (int e = 0; e < E; ++e) sum += fa[e];
+      reinterpret_cast<uint4*>(sum_out + row * c)[i] = va[v];
+    }
+  }
+#pragma unroll
+  for (int of = 16; of > 0; of >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, of);
+  const float mean = sum / (float)c;
+  float sq = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int i = v * 32 + lane;
+    if (i < nvec) {
+      float f[E];
+      Pack<T>::unpack(va[v], f);
+#pragma unroll
+      for (int e = 0; e < E; ++e) { const float d = f[e] - mean; sq = fmaf(d, d, sq); }
+    }
+  }
+#pragma unroll
+  for (int of = 16; of > 0; of >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, of);
+  const float rstd = rsqrtf(sq / (float)c + eps);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int i = v * 32 + lane;
+    if (i < nvec) {
+      float f[E], wf[E], bf[E];
+      Pack<T>::unpack(va[v], f);
+      Pack<T>::unpack(__ldg(reinterpret_cast<const uint4*>(w) + i), wf);
+      if (bias) Pack<T>::unpack(__ldg(reinterpret_cast<const uint4*>(bias) + i), bf);
+#pragma unroll
+      for (int e = 0; e < E; ++e) f[e] = (f[e] - mean) * rstd * wf[e] + (bias ? bf[e] : 0.f);
+      reinterpret_cast<uint4*>(normed + row * c)[i] = Pack<T>::pack(f);
+    }
+  }
+}
+
+template <typename T>
+static int launch_add_ln_t(const void* a, const void* b, long long rows, int c, const void* w, const void* bias, float eps,
+                           void* sum_out, void* normed, cudaStream_t st) {
+  constexpr int E = Pack<T>::E;
+  const int nv = (c / E + 31) / 32;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+#define TOME_ADDLN(NV_) add_layernorm_kernel<T, NV_><<<grid, 256, 0, st>>>((const T*)a, (const T*)b, rows, c, (const T*)w, (const T*)bias, eps, (T*)sum_out, (T*)normed)
+  if (nv <= 1) TOME_ADDLN(1); else if (nv <= 2) TOME_ADDLN(2); else if (nv <= 3) TOME_ADDLN(3); else if (nv <= 4) TOME_ADDLN(4);
+  else if (nv <= 6) TOME_ADDLN(6); else if (nv <= 8) TOME_ADDLN(8);
+  else return set_error(TOME_ERR_UNSUPPORTED, "tome_add_layernorm: c=%d too wide", c);
+#undef TOME_ADDLN
+  TOME_LAUNCH_CHECK("add_layernorm_kernel");
+  return TOME_OK;
+}
+
+int launch_add_layernorm(const void* a, const void* b, int dtype, long long rows, int c, const void* w, const void* bias,
+                         float eps, void* sum_out, void* normed, cudaStream_t st) {
+  const int e = dtype == TOME_F32 ? 4 : 8;
+  if (c % e != 0 || !aligned16(a) || !aligned16(b) || !aligned16(w) || (bias && !aligned16(bias)) || !aligned16(sum_out) || !aligned16(normed))
+    return set_error(TOME_ERR_ALIGN, "tome_add_layernorm: needs 16-byte aligned buffers and c %% %d == 0", e);
+  if (dtype == TOME_F32) return launch_add_ln_t<float>(a, b, rows, c, w, bias, eps, sum_out, normed, st);
+  if (dtype == TOME_BF16) return launch_add_ln_t<__nv_bfloat16>(a, b, rows, c, w, bias, eps, sum_out, normed, st);
+  return set_error(TOME_ERR_DTYPE, "tome_add_layernorm: unsupported dtype %d", dtype);
+}
+
 int launch_merge_source(const tome_plan* plan, const float* source, int n0, float thr, float* out, cudaStream_t st) {
   const int nout = plan->n - plan->r;
   if (source) {

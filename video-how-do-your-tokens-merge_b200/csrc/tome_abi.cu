@@ -61,6 +61,7 @@ int launch_merge(const tome_plan*, const void*, int, int, const View&, const flo
                  float*, float*, cudaStream_t, const void*, const void*, float, void*, const View*);
 int launch_merge_source(const tome_plan*, const float*, int, float, float*, cudaStream_t);
 int launch_unmerge(const tome_plan*, const void*, int, int, void*, cudaStream_t);
+int launch_add_layernorm(const void*, const void*, int, long long, int, const void*, const void*, float, void*, void*, cudaStream_t);
 
 static int check_plan(const tome_plan* p, const char* who) {
   if (!p) return set_error(TOME_ERR_ARG, "%s: plan is NULL", who);
@@ -206,6 +207,14 @@ int tome_merge_source(const tome_plan* plan, const float* source, int32_t n0, fl
   TOME_CHECK_ARG(source || n0 == plan->n, "tome_merge_source: implicit identity needs n0 == n (n0=%d n=%d)", n0, plan->n);
   TOME_CHECK_ARG(n0 > 0, "tome_merge_source: n0=%d", n0);
   return launch_merge_source(plan, source, n0, hybrid_threshold, out, (cudaStream_t)stream);
+}
+
+int tome_add_layernorm(const void* a, const void* b, int32_t dtype, int64_t rows, int32_t c, const void* ln_weight,
+                       const void* ln_bias, float ln_eps, void* sum_out, void* normed_out, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(a && b && ln_weight && sum_out && normed_out && rows > 0 && c > 0, "tome_add_layernorm: NULL pointer or empty shape");
+  return launch_add_layernorm(a, b, dtype, rows, c, ln_weight, ln_bias, ln_eps, sum_out, normed_out, (cudaStream_t)stream);
 }
 
 int tome_unmerge(const tome_plan* plan, const void* x, int32_t dtype, int32_t c, void* out, void* stream) {

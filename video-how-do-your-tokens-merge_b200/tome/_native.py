@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 TOME_F32, TOME_BF16 = 0, 1
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -27,7 +27,7 @@ _MODES = {"wavg": MODE_WAVG, "sum": MODE_SUM, "mean": MODE_MEAN, "max": MODE_AMA
 
 EXPORTS = (
     "tome_abi_version", "tome_last_error", "tome_launch_count", "tome_device_check", "tome_match_workspace_bytes", "tome_match", "tome_match_heads",
-    "tome_rowmax", "tome_select_workspace_bytes", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_source",
+    "tome_rowmax", "tome_select_workspace_bytes", "tome_select", "tome_merge", "tome_merge_norm", "tome_add_layernorm", "tome_merge_source",
     "tome_unmerge",
 )
 
@@ -86,9 +86,10 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.tome_merge_norm.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_i32, ctypes.POINTER(TomeViewC), c_vp, c_i32,
                                     c_f32, c_vp, ctypes.POINTER(TomeViewC), c_vp, c_vp, c_vp, c_vp, c_f32, c_vp,
                                     ctypes.POINTER(TomeViewC), c_vp]
+    lib.tome_add_layernorm.argtypes = [c_vp, c_vp, c_i32, ctypes.c_int64, c_i32, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp]
     lib.tome_merge_source.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_f32, c_vp, c_vp]
     lib.tome_unmerge.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_i32, c_vp, c_vp]
-    for name in ("tome_device_check", "tome_match", "tome_match_heads", "tome_rowmax", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_source",
+    for name in ("tome_device_check", "tome_match", "tome_match_heads", "tome_rowmax", "tome_select", "tome_merge", "tome_merge_norm", "tome_add_layernorm", "tome_merge_source",
                  "tome_unmerge"):
         getattr(lib, name).restype = c_i32
     if lib.tome_abi_version() != ABI_VERSION:
@@ -403,6 +404,23 @@ def merge_frames(plan: DevicePlan, x: torch.Tensor, frames: int, mode: str, size
                                    out[:, 1:].data_ptr(), ctypes.byref(ov), size_out.data_ptr(), logsize_out.data_ptr(),
                                    wp, bp, eps, normed[:, 1:].data_ptr(), ctypes.byref(nv), _stream(x)), lib)
     return out, size_out, logsize_out, normed
+
+
+def add_layernorm(a: torch.Tensor, b: torch.Tensor, norm):
+    """(a + b, LayerNorm(a + b)) in one pass; ``norm=(weight, bias, eps)``.  a, b contiguous, same shape."""
+    lib = load_library()
+    _require_cuda(a, "a")
+    if a.shape != b.shape or a.dtype != b.dtype:
+        raise RuntimeError("tome_b200: add_layernorm needs two tensors of the same shape and dtype")
+    a, b = a.contiguous(), b.contiguous()
+    c = a.shape[-1]
+    wp, bp, eps = _norm_args(norm, a)
+    with torch.cuda.device(a.device):
+        s = torch.empty_like(a)
+        y = torch.empty_like(a)
+        _check(lib.tome_add_layernorm(a.data_ptr(), b.data_ptr(), _dtype_code(a), a.numel() // c, c, wp, bp, eps,
+                                      s.data_ptr(), y.data_ptr(), _stream(a)), lib)
+    return s, y
 
 
 def merge_source(plan: DevicePlan, source: Optional[torch.Tensor], hybrid_threshold: Optional[float] = None

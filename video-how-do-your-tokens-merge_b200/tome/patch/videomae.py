@@ -49,6 +49,43 @@ def _normed_or(norm, x, info):
     return y if y is not None and y.shape == x.shape else norm(x)
 
 
+def _norm1_or(block, x, info):
+    """norm1(x): taken from the previous block's fused residual-add + LayerNorm when it was made for
+    exactly this tensor and this LayerNorm."""
+    pre = info.pop("normed1", None)
+    if pre is not None and pre[0] is x and pre[1] is block.norm1:
+        return pre[2]
+    return block.norm1(x)
+
+
+def _close_block(block, x, y, info):
+    """``x + y`` at the end of a block (videomae.py:22).  On the CUDA inference path the LayerNorm that opens
+    the NEXT block (its norm1) is applied in the same pass (``tome_add_layernorm``) and parked in
+    ``info["normed1"]``; the chain block -> next block's norm1 is rebuilt at every model forward."""
+    nxt = (info.get("next_norm1") or {}).get(id(block))
+    fn = fusable_norm(nxt, x) if nxt is not None else None
+    if fn is None or y.shape != x.shape or y.dtype != x.dtype or block.training:       # eval: drop_path is identity
+        return x + block.drop_path(y)
+    from tome import _native
+    s, normed = _native.add_layernorm(x, y, fn)
+    info["normed1"] = (s, nxt, normed)
+    return s
+
+
+def link_blocks(blocks, info):
+    """id(block) -> the LayerNorm the following block opens with; blocks listed twice are left out."""
+    chain, seen = {}, set()
+    blocks = list(blocks)
+    for cur, nxt in zip(blocks[:-1], blocks[1:]):
+        if id(cur) in seen:
+            chain[id(cur)] = None
+        else:
+            chain[id(cur)] = getattr(nxt, "norm1", None)
+        seen.add(id(cur))
+    info["next_norm1"] = chain
+    info["normed1"] = None
+
+
 class ToMeBlockMixin:
     """videomae.py:13-30."""
 
@@ -56,11 +93,11 @@ class ToMeBlockMixin:
         info = self._tome_info
         attn_size = info["size"] if info["prop_attn"] else None
         attn_bias = info.get("log_size") if info["prop_attn"] else None
-        attn, metric = self.attn(self.norm1(x), attn_size, info["head_aggregation"], attn_bias)
+        attn, metric = self.attn(_norm1_or(self, x, info), attn_size, info["head_aggregation"], attn_bias)
         if self.gamma_1 is None:
             x = x + self.drop_path(attn)
             x = self.reduction_function(metric, x, info, norm=self.norm2)
-            x = x + self.drop_path(self.mlp(_normed_or(self.norm2, x, info)))
+            x = _close_block(self, x, self.mlp(_normed_or(self.norm2, x, info)), info)
         else:
             x = x + self.drop_path(self.gamma_1 * attn)
             x = self.reduction_function(metric, x, info, norm=self.norm2)
@@ -75,7 +112,7 @@ class ToMeDuplicateBlockMixin:
         info = self._tome_info
         attn_size = info["size"] if info["prop_attn"] else None
         attn_bias = info.get("log_size") if info["prop_attn"] else None
-        _, metric = self.attn(self.norm1(x), attn_size, info["head_aggregation"], attn_bias)
+        _, metric = self.attn(_norm1_or(self, x, info), attn_size, info["head_aggregation"], attn_bias)
         return self.reduction_function(metric, x, info)
 
 
@@ -232,6 +269,7 @@ def make_tome_class(transformer_class):
             self._tome_info["log_size"] = None
             self._tome_info["normed"] = None
             self._tome_info["source"] = None
+            link_blocks(self.model.blocks, self._tome_info)
             return super().forward(*args, **kwdargs)
 
     return ToMeVisionTransformer
