@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 7
+#define TOME_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define TOME_API __attribute__((visibility("default")))
@@ -180,6 +180,18 @@ TOME_API int tome_merge_source(const tome_plan* plan, const float* source, int32
 TOME_API int tome_add_layernorm(const void* a, const void* b, int32_t dtype, int64_t rows, int32_t c,
                        const void* ln_weight, const void* ln_bias, float ln_eps, void* sum_out,
                        void* normed_out, void* stream);
+
+/* Caller-side piece of proportional attention (tome/patch/videomae.py:62-63,
+ * vivit.py:103-104, timesformer.py:72-74: attn + log(size) of the key token).  q and k heads carry spare
+ * channels d, d+1 (host-padded); this writes k[b, t, h, d..d+1] = two-term split of log_size / scale
+ * (0 for the `lead` leading class tokens) so that  scale * (q . k)  over the padded head equals
+ * scale * (q . k) + log(size_key)  and the attention kernel needs no mask.  When q != NULL its channels
+ * d, d+1 are set to 1 (0 for the leading tokens, whose logits take no bias); with q == NULL they must
+ * already hold 1.  log_size: (b, n - lead) fp32; element strides in units of `dtype`. */
+TOME_API int tome_attn_key_bias(const float* log_size, int32_t b, int32_t n, int32_t lead, int32_t heads, int32_t d,
+                       float scale, int32_t dtype, void* k, int64_t k_stride_b, int64_t k_stride_n,
+                       int64_t k_stride_h, void* q, int64_t q_stride_b, int64_t q_stride_n, int64_t q_stride_h,
+                       void* stream);
 
 /* unmerge (merge.py:87-100): x (bm, n - r, c) -> out (bm, n, c); contiguous tensors. */
 TOME_API int tome_unmerge(const tome_plan* plan, const void* x, int32_t dtype, int32_t c, void* out,

@@ -381,3 +381,42 @@ def test_add_layernorm_matches_two_passes(native, dtype, shape):
     torch.testing.assert_close(y2.float(), want2, **tol)
     with pytest.raises(RuntimeError):
         native.add_layernorm(a, b[:, :-1], (w, bias, 1e-6))
+
+
+@pytest.mark.parametrize("lead", [0, 1])
+@pytest.mark.parametrize("shape", [(2, 12, 392, 64), (3, 3, 197, 32)])
+def test_prop_attention_key_bias_equals_masked_attention(native, shape, lead):
+    """tome.attention: log(size) folded into two spare q/k channels (tome_attn_key_bias) + unmasked fused
+    attention == the reference's masked formulation (videomae.py:62-63; timesformer.py:72-74 with lead=1),
+    to bf16 round-off, and the key tensor handed to the matching is the plain projection."""
+    from tome import attention as A
+    B, H, N, d = shape
+    C = H * d
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn(B, N, C, device="cuda", generator=gen).to(torch.bfloat16)
+    w = (0.05 * torch.randn(3 * C, C, device="cuda", generator=gen)).to(torch.bfloat16)
+    bias = (0.1 * torch.randn(3 * C, device="cuda", generator=gen)).to(torch.bfloat16)
+    size = torch.randint(1, 30, (B, N - lead, 1), device="cuda", generator=gen).float()
+    owner = torch.nn.Module().eval()
+    wq, wk, wv = w.chunk(3, 0)
+    bq, bk, bv = bias.chunk(3, 0)
+    with torch.no_grad():
+        ctx, k = A.attention(x, owner, H, d, d ** -0.5, size.log(), wq, wk, wv, bq, bk, bv, lead=lead)
+        qkv = torch.nn.functional.linear(x, w, bias)
+        q0, k0, v0 = qkv.reshape(B, N, 3, H, d).permute(2, 0, 3, 1, 4)
+        assert torch.equal(k, k0)
+        mask = torch.zeros(B, 1, N, N, device="cuda")
+        mask[:, :, lead:, lead:] = size.log()[:, None, None, :, 0]
+        want = torch.nn.functional.scaled_dot_product_attention(q0.float(), k0.float(), v0.float(), attn_mask=mask, scale=d ** -0.5)
+        want = want.transpose(1, 2).reshape(B, N, C)
+        base = torch.nn.functional.scaled_dot_product_attention(q0, k0, v0, attn_mask=mask.to(torch.bfloat16), scale=d ** -0.5)
+        base = base.transpose(1, 2).reshape(B, N, C).float()
+    err = (ctx.float() - want).abs().max().item()
+    err_masked_bf16 = (base - want).abs().max().item()
+    print(f"[prop-attn] {shape} lead={lead}: folded {err:.2e} vs masked bf16 {err_masked_bf16:.2e}")
+    assert err < max(2 * err_masked_bf16, 4e-3)
+    # the cached padded weight is rebuilt when a source tensor changes in place
+    w.mul_(2.0)
+    with torch.no_grad():
+        ctx2, _ = A.attention(x, owner, H, d, d ** -0.5, size.log(), wq, wk, wv, bq, bk, bv, lead=lead)
+    assert not torch.equal(ctx2, ctx)

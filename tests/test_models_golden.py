@@ -84,7 +84,8 @@ def test_cuda_path_fp32_vs_reference_goldens(case):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", [c for c in G.MODEL_CASES if c["name"] in ("videomae_merge", "timesformer_merge", "motionformer_merge")],
+@pytest.mark.parametrize("case", [c for c in G.MODEL_CASES if c["name"] in ("videomae_merge", "videomae_propattn_dec", "videomae_hybrid", "timesformer_merge",
+                                                                       "timesformer_hybrid", "motionformer_merge")],
                          ids=lambda c: c["name"])
 def test_cuda_path_bf16_within_tolerance(case):
     plain, merged, size = _run(case, "cuda", torch.bfloat16, contextlib.nullcontext())
@@ -131,3 +132,14 @@ def test_vivit_cuda_vs_cpu_port_and_hf():
         print(f"[model-parity] vivit {kw}: max rel err vs CPU port = {err:.2e}")
         assert err < 2e-3
         assert gpu._tome_info["size"].shape == cpu._tome_info["size"].shape
+        # bf16: proportional attention goes through the folded key bias (tome/attention.py)
+        half = hostmodels.ViViT(num_classes=10, **cfg).eval()
+        half.load_state_dict(ours.state_dict())
+        half = half.cuda().to(torch.bfloat16)
+        tome.patch.vivit(half, **kw)
+        half.r = r
+        with torch.no_grad():
+            got16 = half([clip.cuda().to(torch.bfloat16)]).float().cpu()
+        err16 = float((got16 - want).abs().max() / want.abs().max())
+        print(f"[model-parity] vivit {kw}: max rel err bf16 = {err16:.2e}")
+        assert err16 < 3e-2

@@ -62,6 +62,8 @@ int launch_merge(const tome_plan*, const void*, int, int, const View&, const flo
 int launch_merge_source(const tome_plan*, const float*, int, float, float*, cudaStream_t);
 int launch_unmerge(const tome_plan*, const void*, int, int, void*, cudaStream_t);
 int launch_add_layernorm(const void*, const void*, int, long long, int, const void*, const void*, float, void*, void*, cudaStream_t);
+int launch_key_bias(const float*, int, int, int, int, int, float, int, void*, long long, long long, long long, void*, long long,
+                    long long, long long, cudaStream_t);
 
 static int check_plan(const tome_plan* p, const char* who) {
   if (!p) return set_error(TOME_ERR_ARG, "%s: plan is NULL", who);
@@ -215,6 +217,17 @@ int tome_add_layernorm(const void* a, const void* b, int32_t dtype, int64_t rows
   if (rc) return rc;
   TOME_CHECK_ARG(a && b && ln_weight && sum_out && normed_out && rows > 0 && c > 0, "tome_add_layernorm: NULL pointer or empty shape");
   return launch_add_layernorm(a, b, dtype, rows, c, ln_weight, ln_bias, ln_eps, sum_out, normed_out, (cudaStream_t)stream);
+}
+
+int tome_attn_key_bias(const float* log_size, int32_t b, int32_t n, int32_t lead, int32_t heads, int32_t d, float scale,
+                       int32_t dtype, void* k, int64_t k_sb, int64_t k_sn, int64_t k_sh, void* q, int64_t q_sb, int64_t q_sn,
+                       int64_t q_sh, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(log_size && k && b > 0 && heads > 0 && d > 0 && lead >= 0 && n > lead && scale > 0.f,
+                 "tome_attn_key_bias: NULL pointer or bad shape (b=%d n=%d lead=%d heads=%d d=%d scale=%g)", b, n, lead, heads, d, (double)scale);
+  return launch_key_bias(log_size, b, n, lead, heads, d, 1.0f / scale, dtype, k, k_sb, k_sn, k_sh, q, q_sb, q_sn, q_sh,
+                         (cudaStream_t)stream);
 }
 
 int tome_unmerge(const tome_plan* plan, const void* x, int32_t dtype, int32_t c, void* out, void* stream) {

@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 TOME_F32, TOME_BF16 = 0, 1
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -28,7 +28,7 @@ _MODES = {"wavg": MODE_WAVG, "sum": MODE_SUM, "mean": MODE_MEAN, "max": MODE_AMA
 EXPORTS = (
     "tome_abi_version", "tome_last_error", "tome_launch_count", "tome_device_check", "tome_match_workspace_bytes", "tome_match", "tome_match_heads",
     "tome_rowmax", "tome_select_workspace_bytes", "tome_select", "tome_merge", "tome_merge_norm", "tome_add_layernorm", "tome_merge_source",
-    "tome_unmerge",
+    "tome_attn_key_bias", "tome_unmerge",
 )
 
 
@@ -88,9 +88,12 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
                                     ctypes.POINTER(TomeViewC), c_vp]
     lib.tome_add_layernorm.argtypes = [c_vp, c_vp, c_i32, ctypes.c_int64, c_i32, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp]
     lib.tome_merge_source.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_f32, c_vp, c_vp]
+    c_i64 = ctypes.c_int64
+    lib.tome_attn_key_bias.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_i32, c_vp, c_i64, c_i64, c_i64,
+                                       c_vp, c_i64, c_i64, c_i64, c_vp]
     lib.tome_unmerge.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_i32, c_vp, c_vp]
     for name in ("tome_device_check", "tome_match", "tome_match_heads", "tome_rowmax", "tome_select", "tome_merge", "tome_merge_norm", "tome_add_layernorm", "tome_merge_source",
-                 "tome_unmerge"):
+                 "tome_attn_key_bias", "tome_unmerge"):
         getattr(lib, name).restype = c_i32
     if lib.tome_abi_version() != ABI_VERSION:
         raise RuntimeError(f"tome_b200: ABI version {lib.tome_abi_version()} != expected {ABI_VERSION}; rebuild")
@@ -421,6 +424,23 @@ def add_layernorm(a: torch.Tensor, b: torch.Tensor, norm):
         _check(lib.tome_add_layernorm(a.data_ptr(), b.data_ptr(), _dtype_code(a), a.numel() // c, c, wp, bp, eps,
                                       s.data_ptr(), y.data_ptr(), _stream(a)), lib)
     return s, y
+
+
+def attn_key_bias(log_size: torch.Tensor, k: torch.Tensor, q: Optional[torch.Tensor], d: int, scale: float, lead: int = 0):
+    """Write the two-term split of log_size / scale into channels d, d+1 of every key head (in place);
+    k, q: (B, H, N, d + pad) views with unit channel stride; log_size (B, N - lead) fp32."""
+    lib = load_library()
+    _require_cuda(k, "k")
+    B, H, N, da = k.shape
+    if da < d + 2 or k.stride(3) != 1 or (q is not None and (q.shape != k.shape or q.stride(3) != 1 or q.dtype != k.dtype)):
+        raise RuntimeError("tome_b200: attn_key_bias needs (B, H, N, >= d + 2) q/k views with unit channel stride")
+    if log_size.dtype != torch.float32 or log_size.numel() != B * (N - lead) or log_size.device != k.device:
+        raise RuntimeError("tome_b200: attn_key_bias needs fp32 log_size of shape (B, N - lead) on k's device")
+    log_size = log_size.contiguous()
+    qp = (None, 0, 0, 0) if q is None else (q.data_ptr(), q.stride(0), q.stride(2), q.stride(1))
+    with torch.cuda.device(k.device):
+        _check(lib.tome_attn_key_bias(log_size.data_ptr(), B, N, int(lead), H, int(d), float(scale), _dtype_code(k),
+                                      k.data_ptr(), k.stride(0), k.stride(2), k.stride(1), *qp, _stream(k)), lib)
 
 
 def merge_source(plan: DevicePlan, source: Optional[torch.Tensor], hybrid_threshold: Optional[float] = None

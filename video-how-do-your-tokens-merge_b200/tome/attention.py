@@ -1,0 +1,75 @@
+"""Proportional attention without a mask.
+
+The reference adds ``size.log()`` of the key token to the attention logits
+(tome/patch/videomae.py:62-63, vivit.py:103-104, timesformer.py:72-74).  Passed to fused attention as an
+``attn_mask`` that costs 7x (a (B, 1, N, N) bias forces the masked kernels: 331 us instead of 46 us at
+B=8, N=1568 on a B200).  A key-only bias is a rank-1 term, so it can ride inside the contraction:
+
+    scale * q.k_j + b_j  ==  scale * [q, 1, 1] . [k_j, hi_j, lo_j],      hi_j + lo_j = b_j / scale
+
+Each q/k head is padded from d to d + 8 channels by zero rows in a cached copy of the QKV weight (q's two
+live spare channels are produced as 1 by the GEMM's bias), ``tome_attn_key_bias`` drops the two-term
+split of ``log(size) / scale`` into k's spare channels, and cuDNN's flash attention runs unmasked
+(d_qk = d + 8, d_v = d; 100 us at the shape above).  Inference, CUDA, bf16 only -- anything else takes
+the reference's masked formulation in the callers.
+"""
+import torch
+import torch.nn.functional as F
+
+PAD = 8          # spare channels per q/k head: keeps 16-byte alignment for bf16, two of them are used
+
+
+def usable(x: torch.Tensor, module) -> bool:
+    return (x.is_cuda and x.dtype == torch.bfloat16 and not torch.is_grad_enabled() and not module.training)
+
+
+def _key_of(tensors):
+    return tuple((t.data_ptr(), t._version, t.dtype, t.device) if t is not None else None for t in tensors)
+
+
+def padded_qkv(owner, heads, d, wq, wk, wv, bq=None, bk=None, bv=None):
+    """(weight, bias) of the padded QKV projection, cached on ``owner`` until a source tensor changes.
+    Output columns: heads x (d + PAD) for q, the same for k, heads x d for v."""
+    key = _key_of((wq, wk, wv, bq, bk, bv))
+    cached = getattr(owner, "_tome_padded_qkv", None)
+    if cached is not None and cached[0] == key:
+        return cached[1], cached[2]
+    c = wq.shape[1]
+    da = d + PAD
+    kw = dict(dtype=wq.dtype, device=wq.device)
+
+    def pad_w(w):
+        out = torch.zeros(heads, da, c, **kw)
+        out[:, :d] = w.detach().reshape(heads, d, c)
+        return out.reshape(heads * da, c)
+
+    def pad_b(b, ones):
+        out = torch.zeros(heads, da, **kw)
+        if b is not None:
+            out[:, :d] = b.detach().reshape(heads, d)
+        if ones:
+            out[:, d:d + 2] = 1
+        return out.reshape(heads * da)
+
+    weight = torch.cat((pad_w(wq), pad_w(wk), wv.detach()), 0).contiguous()
+    bias = torch.cat((pad_b(bq, True), pad_b(bk, False),
+                      bv.detach() if bv is not None else torch.zeros(heads * d, **kw)), 0).contiguous()
+    owner._tome_padded_qkv = (key, weight, bias)
+    return weight, bias
+
+
+def attention(x, owner, heads, d, scale, log_size, wq, wk, wv, bq=None, bk=None, bv=None, lead=0):
+    """Attention over x (B, N, C) with ``log_size`` (B, N - lead[, 1]) fp32 added to the logits of the
+    non-leading keys (and, when lead > 0, only for the non-leading queries).  Returns the context
+    (B, N, heads * d) and the key tensor (B, heads, N, d) the matching metric is taken from."""
+    from tome import _native
+    B, N, _ = x.shape
+    da = d + PAD
+    weight, bias = padded_qkv(owner, heads, d, wq, wk, wv, bq, bk, bv)
+    qkv = F.linear(x, weight, bias)
+    q = qkv[..., :heads * da].view(B, N, heads, da).transpose(1, 2)
+    k = qkv[..., heads * da:2 * heads * da].view(B, N, heads, da).transpose(1, 2)
+    v = qkv[..., 2 * heads * da:].view(B, N, heads, d).transpose(1, 2)
+    _native.attn_key_bias(log_size.reshape(B, N - lead), k, q if lead else None, d, scale, lead)
+    ctx = F.scaled_dot_product_attention(q, k, v, scale=scale)
+    return ctx.transpose(1, 2).reshape(B, N, heads * d), k[..., :d]

@@ -15,6 +15,7 @@ import torch.nn.functional as F
 
 from tome.merge import (Drop, Merge, bipartite_soft_matching, bipartite_soft_matching_drop,
                         bipartite_soft_matching_hybrid, merge_source, merge_wavg)
+from tome import attention as prop_attention
 from tome.patch.videomae import _normed_or, _swap, fusable_norm, lazy_head_mean
 from tome.utils import parse_r
 
@@ -53,6 +54,17 @@ class ToMeAttentionMixin:
 
     def forward(self, x, size: torch.Tensor = None, log_size: torch.Tensor = None):
         B, N, C = x.shape
+        if size is not None and self.with_qkv and prop_attention.usable(x, self):
+            # attn[:, :, 1:, 1:] += log(size) (timesformer.py:72-74) folded into the contraction: the class key
+            # carries bias 0 and the class query's bias channels are 0
+            if log_size is None:
+                log_size = size.log()
+            wq, wk, wv = self.qkv.weight.chunk(3, 0)
+            bq, bk, bv = self.qkv.bias.chunk(3, 0) if self.qkv.bias is not None else (None, None, None)
+            x, k = prop_attention.attention(x, self, self.num_heads, C // self.num_heads, self.scale, log_size.float(),
+                                            wq, wk, wv, bq, bk, bv, lead=1)
+            x = self.proj_drop(self.proj(x))
+            return x, lazy_head_mean(k[:, :, 1:, :])
         if self.with_qkv:
             qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
             q, k, v = qkv[0], qkv[1], qkv[2]

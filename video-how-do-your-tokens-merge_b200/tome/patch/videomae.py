@@ -19,6 +19,7 @@ import torch.nn.functional as F
 from tome.merge import (Merge, bipartite_soft_matching, bipartite_soft_matching_drop,
                         bipartite_soft_matching_hybrid, merge_source, merge_wavg)
 from tome.utils import parse_r
+from tome import attention as prop_attention
 
 
 def lazy_head_mean(k, frames=1):
@@ -133,18 +134,26 @@ class ToMeAttentionMixin:
                     self._tome_qkv_bias = torch.cat((self.q_bias, torch.zeros_like(self.v_bias), self.v_bias)).detach()
                     self._tome_qkv_bias_key = key
                 qkv_bias = self._tome_qkv_bias
-        qkv = F.linear(input=x, weight=self.qkv.weight, bias=qkv_bias)
-        qkv = qkv.reshape(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4)
-        q, k, v = qkv[0], qkv[1], qkv[2]
-
-        bias = None
-        if size is not None:                     # proportional attention (videomae.py:62-63)
+        if size is not None and prop_attention.usable(x, self):
+            # proportional attention (videomae.py:62-63) with the key bias folded into the contraction
             if log_size is None:
                 log_size = size.log()
-            bias = log_size[:, None, None, :, 0].to(q.dtype).expand(B, 1, N, N)
-        drop = self.attn_drop.p if self.training else 0.0
-        x = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, dropout_p=drop, scale=self.scale)
-        x = x.transpose(1, 2).reshape(B, N, -1)
+            wq, wk, wv = self.qkv.weight.chunk(3, 0)
+            d = wq.shape[0] // self.num_heads
+            x, k = prop_attention.attention(x, self, self.num_heads, d, self.scale, log_size.float(), wq, wk, wv,
+                                            self.q_bias, None, self.v_bias)
+        else:
+            qkv = F.linear(input=x, weight=self.qkv.weight, bias=qkv_bias)
+            qkv = qkv.reshape(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4)
+            q, k, v = qkv[0], qkv[1], qkv[2]
+            bias = None
+            if size is not None:                 # proportional attention (videomae.py:62-63)
+                if log_size is None:
+                    log_size = size.log()
+                bias = log_size[:, None, None, :, 0].to(q.dtype).expand(B, 1, N, N)
+            drop = self.attn_drop.p if self.training else 0.0
+            x = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, dropout_p=drop, scale=self.scale)
+            x = x.transpose(1, 2).reshape(B, N, -1)
         x = self.proj_drop(self.proj(x))
 
         if head_aggregation == 'mean':

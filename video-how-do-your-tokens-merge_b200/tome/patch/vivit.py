@@ -16,6 +16,7 @@ import torch.nn.functional as F
 
 from tome.merge import (Merge, bipartite_soft_matching, bipartite_soft_matching_drop,
                         bipartite_soft_matching_hybrid, merge_source, merge_wavg)
+from tome import attention as prop_attention
 from tome.patch.videomae import _normed_or, _swap, _wavg, lazy_head_mean
 from tome.utils import parse_r
 
@@ -61,16 +62,24 @@ class ToMeVivitSelfAttentionMixin:
     def forward(self, hidden_states, size=None, head_aggregation='mean', log_size=None, **kwargs):
         B, N, _ = hidden_states.shape
         h, d = self.num_attention_heads, self.attention_head_size
-        q = self.query(hidden_states).view(B, N, h, d).transpose(1, 2)
-        k = self.key(hidden_states).view(B, N, h, d).transpose(1, 2)
-        v = self.value(hidden_states).view(B, N, h, d).transpose(1, 2)
-        bias = None
-        if size is not None:                             # proportional attention (vivit.py:103-104)
+        if size is not None and prop_attention.usable(hidden_states, self):
+            # proportional attention (vivit.py:103-104) with the key bias folded into the contraction
             if log_size is None:
                 log_size = size.log()
-            bias = log_size[:, None, None, :, 0].to(q.dtype).expand(B, 1, N, N)
-        ctx = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, scale=d ** -0.5)
-        ctx = ctx.transpose(1, 2).reshape(B, N, h * d)
+            ctx, k = prop_attention.attention(hidden_states, self, h, d, d ** -0.5, log_size.float(),
+                                              self.query.weight, self.key.weight, self.value.weight,
+                                              self.query.bias, self.key.bias, self.value.bias)
+        else:
+            q = self.query(hidden_states).view(B, N, h, d).transpose(1, 2)
+            k = self.key(hidden_states).view(B, N, h, d).transpose(1, 2)
+            v = self.value(hidden_states).view(B, N, h, d).transpose(1, 2)
+            bias = None
+            if size is not None:                         # proportional attention (vivit.py:103-104)
+                if log_size is None:
+                    log_size = size.log()
+                bias = log_size[:, None, None, :, 0].to(q.dtype).expand(B, 1, N, N)
+            ctx = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, scale=d ** -0.5)
+            ctx = ctx.transpose(1, 2).reshape(B, N, h * d)
         if head_aggregation == 'mean':
             metric = lazy_head_mean(k)
         elif head_aggregation == 'concat':
