@@ -236,6 +236,7 @@ class HeadMeanMetric:
         self.heads = h
         self.dtype, self.device = keys.dtype, keys.device
         self.is_cuda = keys.is_cuda
+        self.prefetched = None        # (r, class_token, distill_token, plan, stream) from tome.merge.prefetch_matching
 
     def size(self, i):
         return self.shape[i]

@@ -58,9 +58,10 @@ def padded_qkv(owner, heads, d, wq, wk, wv, bq=None, bk=None, bv=None):
     return weight, bias
 
 
-def attention(x, owner, heads, d, scale, log_size, wq, wk, wv, bq=None, bk=None, bv=None, lead=0):
+def attention(x, owner, heads, d, scale, log_size, wq, wk, wv, bq=None, bk=None, bv=None, lead=0, on_keys=None):
     """Attention over x (B, N, C) with ``log_size`` (B, N - lead[, 1]) fp32 added to the logits of the
-    non-leading keys (and, when lead > 0, only for the non-leading queries).  Returns the context
+    non-leading keys (and, when lead > 0, only for the non-leading queries).  ``on_keys(k)`` is called as
+    soon as the key tensor exists.  Returns the context
     (B, N, heads * d) and the key tensor (B, heads, N, d) the matching metric is taken from."""
     from tome import _native
     B, N, _ = x.shape
@@ -70,6 +71,23 @@ def attention(x, owner, heads, d, scale, log_size, wq, wk, wv, bq=None, bk=None,
     q = qkv[..., :heads * da].view(B, N, heads, da).transpose(1, 2)
     k = qkv[..., heads * da:2 * heads * da].view(B, N, heads, da).transpose(1, 2)
     v = qkv[..., 2 * heads * da:].view(B, N, heads, d).transpose(1, 2)
+    if on_keys is not None:          # e.g. start the matching on K before the attention kernel is enqueued
+        on_keys(k[..., :d])
     _native.attn_key_bias(log_size.reshape(B, N - lead), k, q if lead else None, d, scale, lead)
     ctx = F.scaled_dot_product_attention(q, k, v, scale=scale)
     return ctx.transpose(1, 2).reshape(B, N, heads * d), k[..., :d]
+
+
+def early_metric(module, k, head_aggregation="mean", frames=1):
+    """The head-mean matching metric of K (videomae.py:72-73 ...), with match + select already started on
+    a side stream when the module knows its block's reduction (``_tome_info``): the plan is then ready by
+    the time the block asks for it (tome.merge.prefetch_matching)."""
+    from tome.patch.videomae import lazy_head_mean
+    from tome.merge import prefetch_matching
+    metric = lazy_head_mean(k, frames)
+    info = getattr(module, "_tome_info", None)
+    if info is not None and head_aggregation == "mean" and info.get("mode") in ("merge", "drop", "hybrid"):
+        rs = info.get("r")
+        if isinstance(rs, list) and rs and rs[0] > 0:
+            prefetch_matching(metric, rs[0], info["class_token"], info["distill_token"])
+    return metric

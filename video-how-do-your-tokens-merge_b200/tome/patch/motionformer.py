@@ -12,11 +12,12 @@ import torch.nn.functional as F
 from tome.merge import (Drop, Merge, bipartite_soft_matching, bipartite_soft_matching_drop,
                         bipartite_soft_matching_hybrid)
 from tome.patch.timesformer import _frames_back, _frames_view, _merge_frames_generic
+from tome import attention as prop_attention
 from tome.patch.videomae import _normed_or, _swap, fusable_norm, lazy_head_mean
 from tome.utils import parse_r
 
 
-def trajectory_attention(mod, x, num_frames, log_size=None):
+def trajectory_attention(mod, x, num_frames, log_size=None, on_keys=None):
     """vit_helper.py:146-267 (approx == 'none').  x (B, 1 + F*P, C), tokens '(f n)'.
     ``log_size`` (B, F*P) adds the proportional-attention key bias in the flat key order
     (tome/patch/motionformer.py:105-112).  Returns (out, k_) with k_ (B, h, F*P, d)."""
@@ -25,6 +26,8 @@ def trajectory_attention(mod, x, num_frames, log_size=None):
     P = (N - 1) // Fr
     d = C // h
     q, k, v = mod.qkv(x).reshape(B, N, 3, h, d).permute(2, 0, 3, 1, 4)        # each (B, h, N, d)
+    if on_keys is not None:              # K exists: the matching can start beside the attention kernels
+        on_keys(k[:, :, 1:])
     cls_out = F.scaled_dot_product_attention(q[:, :, 0:1], k, v, scale=mod.scale)  # cls attends to everything
     cls_out = cls_out.transpose(1, 2).reshape(B, 1, C)
     q_, k_, v_ = q[:, :, 1:], k[:, :, 1:], v[:, :, 1:]
@@ -81,9 +84,11 @@ class ToMeTrajectoryAttentionMixin:
                 log_size = size.log()
             # '(b f) s i -> b (s f) i': key j of the flat token axis gets log size[(b, j % F), j // F]
             flat = log_size[..., 0].reshape(B, Fr, S).transpose(1, 2).reshape(B, S * Fr)
-        out, k_ = trajectory_attention(self, x, Fr, flat)
-        # '(b h) (s f) d -> (b f) h s d' then mean over heads (motionformer.py:143-144)
-        return out, None, lazy_head_mean(k_, frames=Fr)
+        # metric: '(b h) (s f) d -> (b f) h s d' then mean over heads (motionformer.py:143-144)
+        early = {}
+        out, k_ = trajectory_attention(self, x, Fr, flat, on_keys=lambda keys: early.update(
+            metric=prop_attention.early_metric(self, keys, frames=Fr)))
+        return out, None, early["metric"]
 
 
 def motionformer_merge(metric, x, _tome_info, num_frames, norm=None):
@@ -227,3 +232,4 @@ def apply_patch(model, trace_source: bool = False, prop_attn: bool = True, mode:
             module.reduction_function = reduction_function
         elif _is_traj_attention(module):
             _swap(module, ToMeTrajectoryAttentionMixin, "ToMe")
+            module._tome_info = model._tome_info

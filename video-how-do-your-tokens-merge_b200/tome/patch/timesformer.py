@@ -61,15 +61,18 @@ class ToMeAttentionMixin:
                 log_size = size.log()
             wq, wk, wv = self.qkv.weight.chunk(3, 0)
             bq, bk, bv = self.qkv.bias.chunk(3, 0) if self.qkv.bias is not None else (None, None, None)
-            x, k = prop_attention.attention(x, self, self.num_heads, C // self.num_heads, self.scale, log_size.float(),
-                                            wq, wk, wv, bq, bk, bv, lead=1)
+            early = {}
+            x, k = prop_attention.attention(
+                x, self, self.num_heads, C // self.num_heads, self.scale, log_size.float(), wq, wk, wv, bq, bk, bv, lead=1,
+                on_keys=lambda keys: early.update(metric=prop_attention.early_metric(self, keys[:, :, 1:, :])))
             x = self.proj_drop(self.proj(x))
-            return x, lazy_head_mean(k[:, :, 1:, :])
+            return x, early["metric"]
         if self.with_qkv:
             qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
             q, k, v = qkv[0], qkv[1], qkv[2]
         else:
             q = k = v = x.reshape(B, N, self.num_heads, C // self.num_heads).permute(0, 2, 1, 3)
+        metric = prop_attention.early_metric(self, k[:, :, 1:, :])          # k.mean(1)[:, 1:, :], matching started
         bias = None
         if size is not None:       # attn[:, :, 1:, 1:] += log(size): neither the cls query nor the cls key is biased
             if log_size is None:
@@ -82,7 +85,7 @@ class ToMeAttentionMixin:
         x = x.transpose(1, 2).reshape(B, N, C)
         if self.with_qkv:
             x = self.proj_drop(self.proj(x))
-        return x, lazy_head_mean(k[:, :, 1:, :])                       # k.mean(1)[:, 1:, :]
+        return x, metric
 
 
 def _frames_view(x, B, T, P):
@@ -239,3 +242,4 @@ def apply_patch(model_wrapper, trace_source: bool = False, prop_attn: bool = Tru
             module._tome_info = model_wrapper._tome_info
             module.reduction_function = reduction_function
             _swap(module.attn, ToMeAttentionMixin, "ToMe")      # spatial attention only (timesformer.py:224)
+            module.attn._tome_info = model_wrapper._tome_info

@@ -134,6 +134,12 @@ class ToMeAttentionMixin:
                     self._tome_qkv_bias = torch.cat((self.q_bias, torch.zeros_like(self.v_bias), self.v_bias)).detach()
                     self._tome_qkv_bias_key = key
                 qkv_bias = self._tome_qkv_bias
+        early = {}
+
+        def on_keys(keys):               # K exists: start match + select beside the attention kernel
+            if head_aggregation == 'mean':
+                early["metric"] = prop_attention.early_metric(self, keys)
+
         if size is not None and prop_attention.usable(x, self):
             # proportional attention (videomae.py:62-63) with the key bias folded into the contraction
             if log_size is None:
@@ -141,11 +147,12 @@ class ToMeAttentionMixin:
             wq, wk, wv = self.qkv.weight.chunk(3, 0)
             d = wq.shape[0] // self.num_heads
             x, k = prop_attention.attention(x, self, self.num_heads, d, self.scale, log_size.float(), wq, wk, wv,
-                                            self.q_bias, None, self.v_bias)
+                                            self.q_bias, None, self.v_bias, on_keys=on_keys)
         else:
             qkv = F.linear(input=x, weight=self.qkv.weight, bias=qkv_bias)
             qkv = qkv.reshape(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4)
             q, k, v = qkv[0], qkv[1], qkv[2]
+            on_keys(k)
             bias = None
             if size is not None:                 # proportional attention (videomae.py:62-63)
                 if log_size is None:
@@ -157,7 +164,7 @@ class ToMeAttentionMixin:
         x = self.proj_drop(self.proj(x))
 
         if head_aggregation == 'mean':
-            metric = lazy_head_mean(k)
+            metric = early["metric"]
         elif head_aggregation == 'concat':
             metric = k.transpose(1, 2).reshape(B, N, -1)       # == cat(k.split(1, dim=1), -1).squeeze(1)
         else:
@@ -328,3 +335,4 @@ def apply_patch(model_wrapper, trace_source: bool = False, prop_attn: bool = Fal
             module.reduction_function = reduction_function
         elif _is_attention(module):
             _swap(module, ToMeAttentionMixin, "ToMe")
+            module._tome_info = model_wrapper._tome_info

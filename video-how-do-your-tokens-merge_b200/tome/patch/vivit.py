@@ -62,16 +62,23 @@ class ToMeVivitSelfAttentionMixin:
     def forward(self, hidden_states, size=None, head_aggregation='mean', log_size=None, **kwargs):
         B, N, _ = hidden_states.shape
         h, d = self.num_attention_heads, self.attention_head_size
+        early = {}
+
+        def on_keys(keys):               # K exists: start match + select beside the attention kernel
+            if head_aggregation == 'mean':
+                early["metric"] = prop_attention.early_metric(self, keys)
+
         if size is not None and prop_attention.usable(hidden_states, self):
             # proportional attention (vivit.py:103-104) with the key bias folded into the contraction
             if log_size is None:
                 log_size = size.log()
             ctx, k = prop_attention.attention(hidden_states, self, h, d, d ** -0.5, log_size.float(),
                                               self.query.weight, self.key.weight, self.value.weight,
-                                              self.query.bias, self.key.bias, self.value.bias)
+                                              self.query.bias, self.key.bias, self.value.bias, on_keys=on_keys)
         else:
             q = self.query(hidden_states).view(B, N, h, d).transpose(1, 2)
             k = self.key(hidden_states).view(B, N, h, d).transpose(1, 2)
+            on_keys(k)
             v = self.value(hidden_states).view(B, N, h, d).transpose(1, 2)
             bias = None
             if size is not None:                         # proportional attention (vivit.py:103-104)
@@ -81,7 +88,7 @@ class ToMeVivitSelfAttentionMixin:
             ctx = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, scale=d ** -0.5)
             ctx = ctx.transpose(1, 2).reshape(B, N, h * d)
         if head_aggregation == 'mean':
-            metric = lazy_head_mean(k)
+            metric = early["metric"]
         elif head_aggregation == 'concat':
             metric = k.transpose(1, 2).reshape(B, N, h * d)
         else:
@@ -243,3 +250,4 @@ def apply_patch(model_wrapper, trace_source: bool = False, prop_attn: bool = Tru
             _swap(module, ToMeVivitAttentionMixin, "ToMe")
         elif _is_self_attention(module):
             _swap(module, ToMeVivitSelfAttentionMixin, "ToMe")
+            module._tome_info = model_wrapper._tome_info
