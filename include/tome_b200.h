@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 8
+#define TOME_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define TOME_API __attribute__((visibility("default")))
@@ -168,6 +168,17 @@ TOME_API int tome_merge_norm(const tome_plan* plan, const void* x, int32_t dtype
                     void* out, const tome_view* out_view, float* size_out, float* logsize_out,
                     const void* ln_weight, const void* ln_bias, float ln_eps, void* normed_out,
                     const tome_view* normed_view, void* stream);
+
+/* tome_merge_norm whose input rows are the sum of two tensors: every row read is round(x + residual)
+ * (`residual` laid out like x), i.e. the block's `x = x + attn(...)` (tome/patch/videomae.py:19-20) is taken
+ * inside the merge instead of in a pass of its own; results are bit-identical to merging the
+ * materialised sum.  residual == NULL: as tome_merge_norm.  ln_weight / normed_out may both be NULL
+ * (no fused LayerNorm).  16-byte aligned rows only. */
+TOME_API int tome_merge_add_norm(const tome_plan* plan, const void* x, const void* residual, int32_t dtype, int32_t c,
+                        const tome_view* x_view, const float* size_in, int32_t mode, float hybrid_threshold,
+                        void* out, const tome_view* out_view, float* size_out, float* logsize_out,
+                        const void* ln_weight, const void* ln_bias, float ln_eps, void* normed_out,
+                        const tome_view* normed_view, void* stream);
 
 /* merge_source (merge.py:372-384): source (bm, n, n0) fp32 0/1 adjacency, 'max' reduce.
  * source == NULL means the implicit identity (n0 == n), generated on the fly. */

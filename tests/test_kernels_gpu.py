@@ -420,3 +420,31 @@ def test_prop_attention_key_bias_equals_masked_attention(native, shape, lead):
     with torch.no_grad():
         ctx2, _ = A.attention(x, owner, H, d, d ** -0.5, size.log(), wq, wk, wv, bq, bk, bv, lead=lead)
     assert not torch.equal(ctx2, ctx)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", ["tokens_tsf", "tokens_hybrid", "gauss_cls_distill"])
+def test_fused_residual_equals_merging_the_sum(native, name, dtype):
+    """tome_merge_add_norm: merging (x, residual) in one pass is bit-identical to merging the materialised
+    x + residual -- merged rows, sizes, log sizes and the fused LayerNorm."""
+    case = util.CASE_BY_NAME[name]
+    g = util.golden(case["name"])
+    metric, x, size = util.case_arrays(case)
+    dp = _device_plan_like_reference(native, case, g)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    c = 768
+    xd = torch.randn(case["bm"], case["n"], c, device="cuda", generator=gen).to(dtype)
+    rd = torch.randn(case["bm"], case["n"], c, device="cuda", generator=gen).to(dtype)
+    w = (1 + 0.1 * torch.randn(c, device="cuda", generator=gen)).to(dtype)
+    b = (0.1 * torch.randn(c, device="cuda", generator=gen)).to(dtype)
+    sz = _dev(size) if size is not None else None
+    thr = case.get("threshold")
+    want = native.merge(dp, xd + rd, "wavg", size=sz, want_size=True, norm=(w, b, 1e-6), hybrid_threshold=thr)
+    got = native.merge(dp, xd, "wavg", size=sz, want_size=True, norm=(w, b, 1e-6), residual=rd, hybrid_threshold=thr)
+    for a_, b_ in zip(got, want):
+        assert torch.equal(a_, b_)
+    got2 = native.merge(dp, xd, "wavg", size=sz, want_size=True, residual=rd, hybrid_threshold=thr)
+    for a_, b_ in zip(got2, want[:3]):
+        assert torch.equal(a_, b_)
+    with pytest.raises(RuntimeError):
+        native.merge(dp, xd, "wavg", residual=rd[:, :-1])

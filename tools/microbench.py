@@ -72,6 +72,15 @@ def main():
     out["merge_wavg_cold"] = dict(us=med, us_best=best, GBps=alg / med / 1e3, frac=alg / med / 1e3 / peak, alg_bytes=alg)
     med, best = graph_time([lambda: _native.merge(plan, xs[0], "wavg", size=size, want_size=True) for _ in range(8)])
     out["merge_wavg_warm"] = dict(us=med, us_best=best, GBps=alg / med / 1e3)
+    # the block-level fusions around the merge: LayerNorm after, residual add before
+    w = torch.ones(c, device=dev, dtype=dt); bb = torch.zeros(c, device=dev, dtype=dt)
+    rs = [torch.randn(bm, n, c, device=dev, dtype=dt, generator=g) for _ in range(nrot)]
+    med, best = graph_time([lambda i=i: _native.merge(plan, xs[i], "wavg", size=size, want_size=True, norm=(w, bb, 1e-6)) for i in range(nrot)])
+    out["merge_wavg_norm_cold"] = dict(us=med, us_best=best)
+    med, best = graph_time([lambda i=i: _native.merge(plan, xs[i], "wavg", size=size, want_size=True, norm=(w, bb, 1e-6), residual=rs[i]) for i in range(nrot)])
+    out["merge_wavg_add_norm_cold"] = dict(us=med, us_best=best)
+    med, best = graph_time([lambda i=i: _native.merge(plan, xs[i] + rs[i], "wavg", size=size, want_size=True, norm=(w, bb, 1e-6)) for i in range(nrot)])
+    out["torch_add_then_merge_wavg_norm_cold"] = dict(us=med, us_best=best)
     flops = 2.0 * bm * na * (n // 2) * cm
     for algo, name in ((2, "match_tc"), (1, "match_exact")):
         med, best = graph_time([lambda i=i: _native.match(ms[i % nrot], bool(a.cls), algo=algo) for i in range(8)])

@@ -22,6 +22,7 @@ struct MergeArgs {
   const float* node_max;
   const int *unm_idx, *b_off, *b_src, *b_head;
   const void* x;
+  const void* res;       // optional residual, same layout as x: every input row is round_T(x + res)
   View xv;
   const float* size_in;
   void* out;
@@ -240,12 +241,16 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 
-template <typename T, int NV, int WARPS, int MINB, bool LN>
+// RES: the rows are the sum of two tensors (the block's residual add, tome/patch/videomae.py:19-20:
+// x = x + attn(...) right before the reduction) -- added here instead of in a separate pass; each element
+// is rounded to T first, so the result is bit-identical to merging the materialised sum.
+template <typename T, int NV, int WARPS, int MINB, bool LN, bool RES>
 __global__ void __launch_bounds__(WARPS * 32, MINB) merge_gather_kernel(MergeArgs a) {
   constexpr int E = Pack<T>::E;
   constexpr bool kCopyIfNoSrc = sizeof(T) == 2;   // bf16: round(fp32(x*s)/s) == x -> kept tokens are plain copies
   constexpr int SLOT = NV * 32;                   // 16-byte groups per staged row
-  extern __shared__ uint4 stage[];                // WARPS x 2 x SLOT
+  constexpr int NSLOT = RES ? 4 : 2;              // source pair of x (+ source pair of the residual)
+  extern __shared__ uint4 stage[];                // WARPS x NSLOT x SLOT
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // grid = (batch, row blocks), row blocks walked from the END of the output: CTAs are dispatched in
   // blockIdx order, so the B-token rows (the only ones that may carry a reduction) start first and
@@ -255,6 +260,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) merge_gather_kernel(MergeArg
   const int n = a.n, na = na_of(n), nb = nb_of(n), r = a.r, nu = na - r, nout = n - r;
   if (o >= nout) return;
   const T* xb = reinterpret_cast<const T*>(a.x) + a.xv.batch_offset(b);
+  const T* rb = RES ? reinterpret_cast<const T*>(a.res) + a.xv.batch_offset(b) : nullptr;
   const int nvec = a.c / E;
   const bool wavg = a.mode == TOME_MODE_WAVG;
 
@@ -269,21 +275,43 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) merge_gather_kernel(MergeArg
     if (a.mode != TOME_MODE_DROP) head = __ldg(reinterpret_cast<const int4*>(a.b_head) + (long long)b * nb + idx);
   }
   const int nsrc = head.x;
-  uint4* mine = stage + (size_t)warp * 2 * SLOT;
+  uint4* mine = stage + (size_t)warp * NSLOT * SLOT;
   // hop 2: own row into registers, first two source rows into shared memory
   uint4 raw[NV];
   {
     const uint4* row = reinterpret_cast<const uint4*>(xb + (long long)tok * a.xv.sn);
+    uint4 raw2[RES ? NV : 1];
 #pragma unroll
     for (int v = 0; v < NV; ++v) { const int i = v * 32 + lane; if (i < nvec) raw[v] = ld_stream_u4(row + i); }
+    if (RES) {
+      const uint4* row2 = reinterpret_cast<const uint4*>(rb + (long long)tok * a.xv.sn);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) { const int i = v * 32 + lane; if (i < nvec) raw2[RES ? v : 0] = ld_stream_u4(row2 + i); }
+    }
     if (nsrc > 0) {
-      const uint4* s0 = reinterpret_cast<const uint4*>(xb + (long long)(2 * head.y) * a.xv.sn);
-      const uint4* s1 = reinterpret_cast<const uint4*>(xb + (long long)(2 * head.z) * a.xv.sn);
+      const long long o0 = (long long)(2 * head.y) * a.xv.sn, o1 = (long long)(2 * head.z) * a.xv.sn;
+      const uint4* s0 = reinterpret_cast<const uint4*>(xb + o0);
+      const uint4* s1 = reinterpret_cast<const uint4*>(xb + o1);
       for (int i = lane; i < nvec; i += 32) {
         cp_async16(mine + i, s0 + i);
         if (nsrc > 1) cp_async16(mine + SLOT + i, s1 + i);
+        if (RES) {
+          cp_async16(mine + 2 * SLOT + i, reinterpret_cast<const uint4*>(rb + o0) + i);
+          if (nsrc > 1) cp_async16(mine + 3 * SLOT + i, reinterpret_cast<const uint4*>(rb + o1) + i);
+        }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    if (RES) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        float f[E], g[E];
+        Pack<T>::unpack(raw[v], f);
+        Pack<T>::unpack(raw2[RES ? v : 0], g);
+#pragma unroll
+        for (int e = 0; e < E; ++e) f[e] = __fadd_rn(f[e], g[e]);
+        raw[v] = Pack<T>::pack(f);               // rounded to T: what x + attn holds in the reference
+      }
     }
   }
   const float* szb = a.size_in ? a.size_in + (long long)b * n : nullptr;
@@ -342,11 +370,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) merge_gather_kernel(MergeArg
         __syncwarp();
         const int a0 = k0 < 32 ? __shfl_sync(0xffffffffu, k_ai, k0 & 31) : __ldg(bsrc + k0);
         const int a1 = (k0 + 1 < nsrc) ? ((k0 + 1) < 32 ? __shfl_sync(0xffffffffu, k_ai, (k0 + 1) & 31) : __ldg(bsrc + k0 + 1)) : a0;
-        const uint4* s0 = reinterpret_cast<const uint4*>(xb + (long long)(2 * a0) * a.xv.sn);
-        const uint4* s1 = reinterpret_cast<const uint4*>(xb + (long long)(2 * a1) * a.xv.sn);
+        const long long o0 = (long long)(2 * a0) * a.xv.sn, o1 = (long long)(2 * a1) * a.xv.sn;
+        const uint4* s0 = reinterpret_cast<const uint4*>(xb + o0);
+        const uint4* s1 = reinterpret_cast<const uint4*>(xb + o1);
         for (int i = lane; i < nvec; i += 32) {
           cp_async16(mine + i, s0 + i);
           if (k0 + 1 < nsrc) cp_async16(mine + SLOT + i, s1 + i);
+          if (RES) {
+            cp_async16(mine + 2 * SLOT + i, reinterpret_cast<const uint4*>(rb + o0) + i);
+            if (k0 + 1 < nsrc) cp_async16(mine + 3 * SLOT + i, reinterpret_cast<const uint4*>(rb + o1) + i);
+          }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
       }
@@ -363,6 +396,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) merge_gather_kernel(MergeArg
             if (i < nvec) {
               float f[E];
               Pack<T>::unpack(mine[kk * SLOT + i], f);
+              if (RES) {
+                float g[E];
+                Pack<T>::unpack(mine[(2 + kk) * SLOT + i], g);
+#pragma unroll
+                for (int e = 0; e < E; ++e) f[e] = __fadd_rn(f[e], g[e]);
+                Pack<T>::unpack(Pack<T>::pack(f), f);        // round the sum to T first
+              }
 #pragma unroll
               for (int e = 0; e < E; ++e) {
                 if (a.mode == TOME_MODE_AMAX) accv[v][e] = nanmax(accv[v][e], f[e]);
@@ -516,15 +556,25 @@ static int launch_gather_inst(const MergeArgs& a, cudaStream_t st) {
   const int nout = a.n - a.r;
   dim3 grid(a.bm, (nout + WARPS - 1) / WARPS);
   if (grid.y > 65535) return set_error(TOME_ERR_UNSUPPORTED, "tome_merge: too many output rows per batch element (%d)", nout);
-  const size_t smem = (size_t)WARPS * 2 * NV * 32 * sizeof(uint4);
+  const size_t smem = (size_t)WARPS * (a.res ? 4 : 2) * NV * 32 * sizeof(uint4);
   static bool attr = false;
-  if (!attr && smem > 48 * 1024) {
-    TOME_CUDA(cudaFuncSetAttribute(merge_gather_kernel<T, NV, WARPS, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TOME_CUDA(cudaFuncSetAttribute(merge_gather_kernel<T, NV, WARPS, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (!attr) {
+    const int big = (int)((size_t)WARPS * 4 * NV * 32 * sizeof(uint4));
+    if (big > 48 * 1024) {
+      TOME_CUDA(cudaFuncSetAttribute(merge_gather_kernel<T, NV, WARPS, MINB, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+      TOME_CUDA(cudaFuncSetAttribute(merge_gather_kernel<T, NV, WARPS, MINB, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+      TOME_CUDA(cudaFuncSetAttribute(merge_gather_kernel<T, NV, WARPS, MINB, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+      TOME_CUDA(cudaFuncSetAttribute(merge_gather_kernel<T, NV, WARPS, MINB, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    }
     attr = true;
   }
-  if (a.normed) merge_gather_kernel<T, NV, WARPS, MINB, true><<<grid, WARPS * 32, smem, st>>>(a);
-  else merge_gather_kernel<T, NV, WARPS, MINB, false><<<grid, WARPS * 32, smem, st>>>(a);
+  if (a.res) {
+    if (a.normed) merge_gather_kernel<T, NV, WARPS, MINB, true, true><<<grid, WARPS * 32, smem, st>>>(a);
+    else merge_gather_kernel<T, NV, WARPS, MINB, false, true><<<grid, WARPS * 32, smem, st>>>(a);
+  } else {
+    if (a.normed) merge_gather_kernel<T, NV, WARPS, MINB, true, false><<<grid, WARPS * 32, smem, st>>>(a);
+    else merge_gather_kernel<T, NV, WARPS, MINB, false, false><<<grid, WARPS * 32, smem, st>>>(a);
+  }
   TOME_LAUNCH_CHECK("merge_gather_kernel");
   return TOME_OK;
 }
@@ -539,13 +589,16 @@ static int launch_merge_gather(const MergeArgs& a, cudaStream_t st) {
   if (nv <= 4) return launch_gather_inst<T, 4, WARPS, MINB>(a, st);
   if (nv <= 6) return launch_gather_inst<T, 6, WARPS, MINB>(a, st);
   if (nv <= 8) return launch_gather_inst<T, 8, WARPS, MINB>(a, st);
+  if (a.res) return set_error(TOME_ERR_UNSUPPORTED, "tome_merge: the fused residual needs c <= %d", 8 * 32 * E);
   return launch_merge_scalar<T>(a, st);     // very wide rows: chunked generic kernel
 }
 
 int launch_merge(const tome_plan* plan, const void* x, int dtype, int c, const View& xv, const float* size_in,
                  int mode, float thr, void* out, const View& ov, float* size_out, float* logsize_out,
-                 cudaStream_t st, const void* ln_w, const void* ln_b, float ln_eps, void* normed, const View* nv) {
+                 cudaStream_t st, const void* ln_w, const void* ln_b, float ln_eps, void* normed, const View* nv,
+                 const void* residual) {
   MergeArgs a;
+  a.res = residual;
   a.ln_w = ln_w; a.ln_b = ln_b; a.ln_eps = ln_eps; a.normed = normed; a.nv = nv ? *nv : ov;
   a.bm = plan->bm; a.n = plan->n; a.r = plan->r; a.distill = plan->distill_token; a.c = c; a.mode = mode;
   a.hybrid = (thr == thr) ? 1 : 0; a.thr = thr; a.node_max = plan->node_max;
@@ -555,6 +608,7 @@ int launch_merge(const tome_plan* plan, const void* x, int dtype, int c, const V
   if (dtype == TOME_F32) {
     const bool vec = c % 4 == 0 && aligned16(x) && aligned16(out) && view_vec_ok(xv, 4) && view_vec_ok(ov, 4);
     if (!vec && normed) return set_error(TOME_ERR_ALIGN, "tome_merge_norm: fused LayerNorm needs 16-byte aligned rows (c %% 4 == 0)");
+    if (residual && (!vec || !aligned16(residual))) return set_error(TOME_ERR_ALIGN, "tome_merge: the fused residual needs 16-byte aligned rows (c %% 4 == 0)");
     if (normed && (c > 4 * 32 * 8 || !aligned16(ln_w) || (ln_b && !aligned16(ln_b)) || !aligned16(normed) || !view_vec_ok(a.nv, 4)))
       return set_error(TOME_ERR_UNSUPPORTED, "tome_merge_norm: c=%d too wide or LayerNorm buffers misaligned", c);
     if (!vec) return launch_merge_scalar<float>(a, st);
@@ -564,6 +618,7 @@ int launch_merge(const tome_plan* plan, const void* x, int dtype, int c, const V
   } else if (dtype == TOME_BF16) {
     const bool vec = c % 8 == 0 && aligned16(x) && aligned16(out) && view_vec_ok(xv, 8) && view_vec_ok(ov, 8);
     if (!vec && normed) return set_error(TOME_ERR_ALIGN, "tome_merge_norm: fused LayerNorm needs 16-byte aligned rows (c %% 8 == 0)");
+    if (residual && (!vec || !aligned16(residual))) return set_error(TOME_ERR_ALIGN, "tome_merge: the fused residual needs 16-byte aligned rows (c %% 8 == 0)");
     if (normed && (c > 8 * 32 * 8 || !aligned16(ln_w) || (ln_b && !aligned16(ln_b)) || !aligned16(normed) || !view_vec_ok(a.nv, 8)))
       return set_error(TOME_ERR_UNSUPPORTED, "tome_merge_norm: c=%d too wide or LayerNorm buffers misaligned", c);
     if (!vec) return launch_merge_scalar<__nv_bfloat16>(a, st);
@@ -672,7 +727,7 @@ int launch_merge_source(const tome_plan* plan, const float* source, int n0, floa
   const int nout = plan->n - plan->r;
   if (source) {
     View xv{(long long)plan->n * n0, 0, n0, 1}, ov{(long long)nout * n0, 0, n0, 1};
-    return launch_merge(plan, source, TOME_F32, n0, xv, nullptr, TOME_MODE_AMAX, thr, out, ov, nullptr, nullptr, st, nullptr, nullptr, 0.f, nullptr, nullptr);
+    return launch_merge(plan, source, TOME_F32, n0, xv, nullptr, TOME_MODE_AMAX, thr, out, ov, nullptr, nullptr, st, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr);
   }
   MergeArgs a{};
   a.bm = plan->bm; a.n = plan->n; a.r = plan->r; a.distill = plan->distill_token; a.c = plan->n;

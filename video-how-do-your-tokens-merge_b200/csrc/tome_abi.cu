@@ -58,7 +58,7 @@ int launch_match_tc(const void*, int, int, int, int, const View&, int, int, floa
 size_t select_workspace(int bm, int n);
 int launch_select(const tome_plan*, void*, size_t, cudaStream_t);
 int launch_merge(const tome_plan*, const void*, int, int, const View&, const float*, int, float, void*, const View&,
-                 float*, float*, cudaStream_t, const void*, const void*, float, void*, const View*);
+                 float*, float*, cudaStream_t, const void*, const void*, float, void*, const View*, const void*);
 int launch_merge_source(const tome_plan*, const float*, int, float, float*, cudaStream_t);
 int launch_unmerge(const tome_plan*, const void*, int, int, void*, cudaStream_t);
 int launch_add_layernorm(const void*, const void*, int, long long, int, const void*, const void*, float, void*, void*, cudaStream_t);
@@ -177,26 +177,36 @@ int tome_merge(const tome_plan* plan, const void* x, int32_t dtype, int32_t c, c
   TOME_CHECK_ARG(x != out, "tome_merge: in-place merge is not supported");
   const View xv = make_view(x_view, plan->n, c), ov = make_view(out_view, plan->n - plan->r, c);
   return launch_merge(plan, x, dtype, c, xv, size_in, mode, hybrid_threshold, out, ov, size_out, logsize_out,
-                      (cudaStream_t)stream, nullptr, nullptr, 0.f, nullptr, nullptr);
+                      (cudaStream_t)stream, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr);
 }
 
 int tome_merge_norm(const tome_plan* plan, const void* x, int32_t dtype, int32_t c, const tome_view* x_view,
                     const float* size_in, int32_t mode, float hybrid_threshold, void* out, const tome_view* out_view,
                     float* size_out, float* logsize_out, const void* ln_weight, const void* ln_bias, float ln_eps,
                     void* normed_out, const tome_view* normed_view, void* stream) {
+  return tome_merge_add_norm(plan, x, nullptr, dtype, c, x_view, size_in, mode, hybrid_threshold, out, out_view, size_out,
+                             logsize_out, ln_weight, ln_bias, ln_eps, normed_out, normed_view, stream);
+}
+
+int tome_merge_add_norm(const tome_plan* plan, const void* x, const void* residual, int32_t dtype, int32_t c,
+                        const tome_view* x_view, const float* size_in, int32_t mode, float hybrid_threshold, void* out,
+                        const tome_view* out_view, float* size_out, float* logsize_out, const void* ln_weight,
+                        const void* ln_bias, float ln_eps, void* normed_out, const tome_view* normed_view, void* stream) {
   int rc = ensure_device_ok();
   if (rc) return rc;
   rc = check_plan(plan, "tome_merge_norm");
   if (rc) return rc;
   TOME_CHECK_ARG(x && out && c > 0, "tome_merge_norm: NULL tensor or c=%d", c);
-  TOME_CHECK_ARG(ln_weight && normed_out, "tome_merge_norm: LayerNorm weight and normed_out are required");
+  TOME_CHECK_ARG((ln_weight != nullptr) == (normed_out != nullptr), "tome_merge_norm: LayerNorm weight and normed_out go together");
+  TOME_CHECK_ARG(ln_weight || residual, "tome_merge_norm: nothing to fuse (use tome_merge)");
+  TOME_CHECK_ARG(residual != out && residual != normed_out, "tome_merge_norm: buffers must not alias");
   TOME_CHECK_ARG(mode >= TOME_MODE_WAVG && mode <= TOME_MODE_DROP, "tome_merge_norm: unknown mode %d", mode);
   TOME_CHECK_ARG(mode == TOME_MODE_WAVG || size_in == nullptr, "tome_merge_norm: size_in is only meaningful for TOME_MODE_WAVG");
   TOME_CHECK_ARG(x != out && x != normed_out && out != normed_out, "tome_merge_norm: buffers must not alias");
   const View xv = make_view(x_view, plan->n, c), ov = make_view(out_view, plan->n - plan->r, c);
   const View nv = make_view(normed_view, plan->n - plan->r, c);
   return launch_merge(plan, x, dtype, c, xv, size_in, mode, hybrid_threshold, out, ov, size_out, logsize_out,
-                      (cudaStream_t)stream, ln_weight, ln_bias, ln_eps, normed_out, &nv);
+                      (cudaStream_t)stream, ln_weight, ln_bias, ln_eps, normed_out, &nv, residual);
 }
 
 int tome_merge_source(const tome_plan* plan, const float* source, int32_t n0, float hybrid_threshold, float* out,

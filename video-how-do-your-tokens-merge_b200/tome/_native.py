@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 TOME_F32, TOME_BF16 = 0, 1
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -27,7 +27,7 @@ _MODES = {"wavg": MODE_WAVG, "sum": MODE_SUM, "mean": MODE_MEAN, "max": MODE_AMA
 
 EXPORTS = (
     "tome_abi_version", "tome_last_error", "tome_launch_count", "tome_device_check", "tome_match_workspace_bytes", "tome_match", "tome_match_heads",
-    "tome_rowmax", "tome_select_workspace_bytes", "tome_select", "tome_merge", "tome_merge_norm", "tome_add_layernorm", "tome_merge_source",
+    "tome_rowmax", "tome_select_workspace_bytes", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_add_norm", "tome_add_layernorm", "tome_merge_source",
     "tome_attn_key_bias", "tome_unmerge",
 )
 
@@ -86,13 +86,16 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.tome_merge_norm.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_i32, ctypes.POINTER(TomeViewC), c_vp, c_i32,
                                     c_f32, c_vp, ctypes.POINTER(TomeViewC), c_vp, c_vp, c_vp, c_vp, c_f32, c_vp,
                                     ctypes.POINTER(TomeViewC), c_vp]
+    lib.tome_merge_add_norm.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_vp, c_i32, c_i32, ctypes.POINTER(TomeViewC), c_vp,
+                                        c_i32, c_f32, c_vp, ctypes.POINTER(TomeViewC), c_vp, c_vp, c_vp, c_vp, c_f32, c_vp,
+                                        ctypes.POINTER(TomeViewC), c_vp]
     lib.tome_add_layernorm.argtypes = [c_vp, c_vp, c_i32, ctypes.c_int64, c_i32, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp]
     lib.tome_merge_source.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_f32, c_vp, c_vp]
     c_i64 = ctypes.c_int64
     lib.tome_attn_key_bias.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_i32, c_vp, c_i64, c_i64, c_i64,
                                        c_vp, c_i64, c_i64, c_i64, c_vp]
     lib.tome_unmerge.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_i32, c_vp, c_vp]
-    for name in ("tome_device_check", "tome_match", "tome_match_heads", "tome_rowmax", "tome_select", "tome_merge", "tome_merge_norm", "tome_add_layernorm", "tome_merge_source",
+    for name in ("tome_device_check", "tome_match", "tome_match_heads", "tome_rowmax", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_add_norm", "tome_add_layernorm", "tome_merge_source",
                  "tome_attn_key_bias", "tome_unmerge"):
         getattr(lib, name).restype = c_i32
     if lib.tome_abi_version() != ABI_VERSION:
@@ -313,10 +316,12 @@ def _norm_args(norm, x):
 
 
 def merge(plan: DevicePlan, x: torch.Tensor, mode: str, size: Optional[torch.Tensor] = None,
-          hybrid_threshold: Optional[float] = None, want_size: bool = False, norm=None):
+          hybrid_threshold: Optional[float] = None, want_size: bool = False, norm=None,
+          residual: Optional[torch.Tensor] = None):
     """Kernel 3.  x (bm, n, c) -> (bm, n - r, c).  mode in wavg/sum/mean/max/amax/drop.
     Returns out, or (out, size_out, logsize_out) when ``want_size``; with ``norm=(weight, bias, eps)``
-    the LayerNorm of the merged rows is produced in the same pass and appended to the result."""
+    the LayerNorm of the merged rows is produced in the same pass and appended to the result; with
+    ``residual`` (same shape as x) the rows merged are ``x + residual`` (rounded to x's dtype)."""
     lib = load_library()
     _require_cuda(x, "x")
     if x.dim() != 3 or x.shape[0] != plan.bm or x.shape[1] != plan.n:
@@ -345,16 +350,29 @@ def merge(plan: DevicePlan, x: torch.Tensor, mode: str, size: Optional[torch.Ten
             sp = size.data_ptr()
         xv, ov = _view_of(x), _view_of(out)
         normed = None
-        if norm is None:
+        if norm is None and residual is None:
             _check(lib.tome_merge(plan.c_ptr(), x.data_ptr(), _dtype_code(x), c, ctypes.byref(xv), sp, m, thr,
                                   out.data_ptr(), ctypes.byref(ov), so, lo, _stream(x)), lib)
         else:
-            wp, bp, eps = _norm_args(norm, x)
-            normed = torch.empty_like(out)
-            nv = _view_of(normed)
-            _check(lib.tome_merge_norm(plan.c_ptr(), x.data_ptr(), _dtype_code(x), c, ctypes.byref(xv), sp, m, thr,
-                                       out.data_ptr(), ctypes.byref(ov), so, lo, wp, bp, eps, normed.data_ptr(),
-                                       ctypes.byref(nv), _stream(x)), lib)
+            rp = None
+            if residual is not None:
+                if residual.shape != x.shape or residual.dtype != x.dtype or residual.device != x.device:
+                    raise RuntimeError("tome_b200: residual must have x's shape, dtype and device")
+                if residual.stride() != x.stride():
+                    residual = residual.contiguous() if x.is_contiguous() else residual.clone(memory_format=torch.preserve_format)
+                    if residual.stride() != x.stride():
+                        raise RuntimeError("tome_b200: residual must be laid out like x")
+                rp = residual.data_ptr()
+            wp = bp = npz = None
+            eps = 0.0
+            nv = ov
+            if norm is not None:
+                wp, bp, eps = _norm_args(norm, x)
+                normed = torch.empty_like(out)
+                nv, npz = _view_of(normed), normed.data_ptr()
+            _check(lib.tome_merge_add_norm(plan.c_ptr(), x.data_ptr(), rp, _dtype_code(x), c, ctypes.byref(xv), sp, m, thr,
+                                           out.data_ptr(), ctypes.byref(ov), so, lo, wp, bp, eps, npz,
+                                           ctypes.byref(nv), _stream(x)), lib)
     res = (out, size_out, logsize_out) if want_size else (out,)
     if norm is not None:
         res = res + (normed,)

@@ -113,10 +113,12 @@ class Merge(_PlanCallable):
     def __call__(self, x: torch.Tensor, mode="mean") -> torch.Tensor:      # merge.py:75-85 / 316-334
         return _native.merge(self.plan, x, mode, hybrid_threshold=self.threshold)
 
-    def wavg(self, x, size=None, norm=None):
+    def wavg(self, x, size=None, norm=None, residual=None):
         """Fused merge_wavg: (x', size' (bm, n', 1) fp32, log size' (bm, n', 1) fp32); with
-        ``norm=(weight, bias, eps)`` also LayerNorm(x') from the same pass as a 4th result."""
-        res = _native.merge(self.plan, x, "wavg", size=size, hybrid_threshold=self.threshold, want_size=True, norm=norm)
+        ``norm=(weight, bias, eps)`` also LayerNorm(x') from the same pass as a 4th result; with
+        ``residual`` the tokens merged are ``x + residual`` (the block's residual add, same pass)."""
+        res = _native.merge(self.plan, x, "wavg", size=size, hybrid_threshold=self.threshold, want_size=True, norm=norm,
+                            residual=residual)
         out, s, ls = res[:3]
         return (out, s[..., None], ls[..., None]) + tuple(res[3:])
 

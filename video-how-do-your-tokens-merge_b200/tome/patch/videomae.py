@@ -96,8 +96,8 @@ class ToMeBlockMixin:
         attn_bias = info.get("log_size") if info["prop_attn"] else None
         attn, metric = self.attn(_norm1_or(self, x, info), attn_size, info["head_aggregation"], attn_bias)
         if self.gamma_1 is None:
-            x = x + self.drop_path(attn)
-            x = self.reduction_function(metric, x, info, norm=self.norm2)
+            # x = x + attn, then the reduction: the add is taken inside the merge kernel when it can be
+            x = self.reduction_function(metric, x, info, norm=self.norm2, residual=self.drop_path(attn))
             x = _close_block(self, x, self.mlp(_normed_or(self.norm2, x, info)), info)
         else:
             x = x + self.drop_path(self.gamma_1 * attn)
@@ -172,38 +172,53 @@ class ToMeAttentionMixin:
         return x, metric
 
 
-def _wavg(merge, x, info, norm):
+def _fusable_residual(x, residual):
+    return (residual is not None and x.is_cuda and not torch.is_grad_enabled() and residual.shape == x.shape
+            and residual.dtype == x.dtype and x.dtype in (torch.float32, torch.bfloat16) and x.is_contiguous()
+            and x.shape[-1] % (8 if x.dtype == torch.bfloat16 else 4) == 0
+            and x.shape[-1] <= (2048 if x.dtype == torch.bfloat16 else 1024))
+
+
+def _wavg(merge, x, info, norm, residual=None):
     """merge_wavg through the fused kernel: x', sizes, log sizes and (when the following LayerNorm is
-    fusable) LayerNorm(x') stashed in info["normed"] for the block to pick up."""
+    fusable) LayerNorm(x') stashed in info["normed"] for the block to pick up.  ``residual``: the tokens
+    merged are x + residual, added inside the kernel."""
     fn = fusable_norm(norm, x) if norm is not None else None
-    res = merge.wavg(x, info["size"], norm=fn)
+    res = merge.wavg(x, info["size"], norm=fn, residual=residual)
     info["size"], info["log_size"] = res[1], res[2]
     info["normed"] = res[3] if fn is not None else None
     return res[0]
 
 
-def videomae_merge(metric, x, _tome_info, norm=None):
-    """videomae.py:80-100."""
+def videomae_merge(metric, x, _tome_info, norm=None, residual=None):
+    """videomae.py:80-100.  ``residual``: the block's pending ``x = x + residual`` (videomae.py:19), folded
+    into the merge kernel when that is possible, applied up front otherwise."""
     _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
     if r > 0:
         merge, _ = bipartite_soft_matching(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
                                            _tome_info["mode"])
+        if residual is not None and not (isinstance(merge, Merge) and _fusable_residual(x, residual)):
+            x, residual = x + residual, None
         if _tome_info["trace_source"]:
             _tome_info["source"] = merge_source(merge, x, _tome_info["source"])
         pre_merge = x.size(1)
         if isinstance(merge, Merge):
-            x = _wavg(merge, x, _tome_info, norm)
+            x = _wavg(merge, x, _tome_info, norm, residual)
         else:
             x, _tome_info["size"] = merge_wavg(merge, x, _tome_info["size"])
             _tome_info["log_size"] = None
         if _tome_info['verbose']:
             print(f'Merged {pre_merge} to {x.size(1)} tokens')
+    elif residual is not None:
+        x = x + residual
     return x
 
 
-def videomae_drop(metric, x, _tome_info, norm=None):
+def videomae_drop(metric, x, _tome_info, norm=None, residual=None):
     """videomae.py:103-126."""
+    if residual is not None:
+        x = x + residual
     _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
     if r > 0:
@@ -225,23 +240,27 @@ def videomae_drop(metric, x, _tome_info, norm=None):
     return x
 
 
-def videomae_hybrid(metric, x, _tome_info, norm=None):
+def videomae_hybrid(metric, x, _tome_info, norm=None, residual=None):
     """videomae.py:129-151."""
     _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
     if r > 0:
         merge, _ = bipartite_soft_matching_hybrid(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
                                                   _tome_info["mode"], _tome_info["threshold"])
+        if residual is not None and not (isinstance(merge, Merge) and _fusable_residual(x, residual)):
+            x, residual = x + residual, None
         if _tome_info["trace_source"]:
             _tome_info["source"] = merge_source(merge, x, _tome_info["source"])
         pre_merge = x.size(1)
         if isinstance(merge, Merge):
-            x = _wavg(merge, x, _tome_info, norm)
+            x = _wavg(merge, x, _tome_info, norm, residual)
         else:
             x, _tome_info["size"] = merge_wavg(merge, x, _tome_info["size"])
             _tome_info["log_size"] = None
         if _tome_info['verbose']:
             print(f'Merged {pre_merge} to {x.size(1)} tokens')
+    elif residual is not None:
+        x = x + residual
     return x
 
 
