@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--match-algo", type=int, default=0, help="0 auto, 1 exact SIMT, 2 tcgen05")
-    ap.add_argument("--cpu-clips", type=int, default=1, help="clips per CPU-baseline step")
+    ap.add_argument("--cpu-clips", type=int, default=8, help="clips per CPU-baseline step (default: the GPU arm's batch)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-micro", action="store_true")
     return ap.parse_args()
@@ -190,7 +190,12 @@ def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return 0
-    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
+    # exactly K timed steps after W warm-up steps, each a bounded sample of the workload: as many clips per
+    # step (up to the GPU arm's batch) as keeps the whole run near two minutes on this box's cores
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    probe, _ = time_cpu_reference(argparse.Namespace(**{**vars(args), "cpu_clips": 1}), steps=1, warmup=1)
+    per_clip = 1.0 / probe["value"]
+    args.cpu_clips = int(max(1, min(args.batch, 120.0 / ((steps + warmup) * per_clip))))
     cb, mean = time_cpu_reference(args, steps, warmup)
     line = {
         "impl": "reference", "metric": "clips_per_sec", "value": cb["value"], "unit": "clips/s",
@@ -210,10 +215,10 @@ def workload_config(args, cpu=False):
         "workload": "VideoMAE ViT-B 16x224 (tubelet 2x16x16, 1568 tokens, 12 layers, 400 classes), ToMe "
                     f"mode={args.mode} r=({args.r},{args.schedule:g}) prop_attn={bool(args.prop_attn)}, "
                     "synthetic torch.rand clips, random-init weights (seed 0)",
-        "clips_per_gpu_per_step": args.cpu_clips if cpu else args.batch,
+        "clips_per_gpu_per_step": args.batch,
         "token_schedule": [n for n, _ in token_schedule(args)],
         "parallelism": f"dp{args.gpus}",
-        "cuda_graph": (not args.no_graph) and not cpu,
+        "cuda_graph": not args.no_graph,
         "l2": "each step reads a different resident input batch (4 x 38.5 MB rotate) and 172 MB of bf16 weights: "
               "working set > 126 MB L2",
     }
@@ -288,7 +293,11 @@ def micro_kernels(args, device, dtype):
     flops = 2.0 * bm * na * (n // 2) * cm
     res["match"] = {"us_mean": m_mean, "us_median": m_med, "algorithmic_gflop": flops / 1e9,
                     "tflops_algorithmic": flops / (m_mean * 1e-6) / 1e12, "algo": args.match_algo or "auto",
-                    "kernels": "split_rows_kernel + match_tc_kernel (3xTF32 tcgen05, exact refine fused)"}
+                    "kernels": "split_rows_kernel + match_tc_kernel (bf16 h.h+h.m+m.h on tcgen05, exact fp64 refine in the epilogue)"}
+    ks = [torch.randn(bm, n, 3, 12, cm, device=device, dtype=dtype, generator=g).permute(2, 0, 3, 1, 4)[1] for _ in range(4)]
+    p_mean, p_med = graph_time([lambda i=i: _native.plan_build(_native.HeadMeanMetric(ks[i % 4]), r) for i in range(8)])
+    res["plan_build_heads12"] = {"us_mean": p_mean, "us_median": p_med,
+                                 "kernels": "tome_plan_build on the lazy head-mean of K (12 heads): split_rows + match_tc + rank + finish"}
     s_mean, s_med = graph_time([lambda: _native.select(nm, ni, n, r) for _ in range(8)])
     res["select"] = {"us_mean": s_mean, "us_median": s_med, "kernels": "rank_kernel + finish_kernel"}
     c_mean, _ = graph_time([lambda i=i: xs[i].clone() for i in range(nrot)])
@@ -432,7 +441,7 @@ def run_ours(args):
     if rank == 0 and not args.skip_micro:
         roofline, kernels = micro_kernels(args, device, dtype)
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
-        cpu_baseline, _ = time_cpu_reference(args, steps=2, warmup=1)
+        cpu_baseline, _ = time_cpu_reference(args, steps=8, warmup=2)       # ~10 s of host work
     if world > 1:
         torch.distributed.barrier()
 

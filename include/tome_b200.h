@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 9
+#define TOME_ABI_VERSION 10
 
 #if defined(__GNUC__)
 #define TOME_API __attribute__((visibility("default")))
@@ -143,6 +143,19 @@ TOME_API int tome_rowmax(const float* scores, int32_t bm, int32_t na, int32_t nb
  * a_map / b_off / b_src / b_head.  plan->r must already be the effective r (> 0). */
 TOME_API size_t tome_select_workspace_bytes(int32_t bm, int32_t n);
 TOME_API int tome_select(const tome_plan* plan, void* workspace, size_t workspace_bytes, void* stream);
+
+/* --- kernels 1 + 2 in one call (merge.py:49-73: everything bipartite_soft_matching computes) ---------
+ * Matching on `metric` (heads == 1: (bm, n, cm) through `view`; heads > 1: the head-mean of K as in
+ * tome_match_heads) followed by the selection: one ABI call, one workspace.  bm, n, r, class/distill flags
+ * and every output buffer come from `plan`; plan->node_max / node_idx are OUTPUTS of this call. */
+TOME_API size_t tome_plan_build_workspace_bytes(int32_t bm, int32_t n, int32_t cm);
+TOME_API int tome_plan_build(const void* metric, int32_t dtype, int32_t heads, int64_t stride_h, const tome_view* view,
+                    int32_t cm, int32_t algo, const tome_plan* plan, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* Diagnostics for tests: geometry of the tensor-core pass for a shape -- out5 = {column tiles, BN, byte
+ * offset of tile_max in the workspace, byte offset of tile_cnt, 1 if the exact refine is fused}. */
+TOME_API void tome_match_tc_describe(int32_t bm, int32_t n, int32_t cm, int64_t* out5);
 
 /* --- kernel 3: merge (merge.py:75-85, 260-269, 316-334, 355-369) ----------------------
  * x: (bm, n, c) -> out: (bm, n - r, c), same dtype.  Output token order is the

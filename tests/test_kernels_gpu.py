@@ -256,16 +256,11 @@ def test_errors_are_loud(native):
         merge(x.cpu())                                          # CPU tensor: no fallback
 
 
-def _tc_layout(bm, n, cm):
-    """Mirror of csrc/match_sm100.cu::tc_geometry / workspace carving (test-only)."""
+def _tc_layout(native, bm, n, cm):
+    """Geometry and workspace carving of the tensor-core pass, as the library reports it."""
     na, nb = (n + 1) // 2, n // 2
-    n_ct = (nb + 255) // 256
-    bn = max(16, (((nb + n_ct - 1) // n_ct) + 15) // 16 * 16)
-    a256 = lambda x: (x + 255) // 256 * 256
-    rows = bm * na * n_ct
-    off_max = a256(2 * bm * n * cm * 4)
-    off_cnt = off_max + a256(rows * 4)
-    return na, nb, n_ct, bn, rows, off_max, off_cnt
+    n_ct, bn, off_max, off_cnt, _ = native.match_tc_describe(bm, n, cm)
+    return na, nb, n_ct, bn, bm * na * n_ct, off_max, off_cnt
 
 
 @pytest.mark.parametrize("name", ["config1_m1p", "config1_m1", "tokens_tsf", "vivit_layer0"])
@@ -279,11 +274,11 @@ def test_tensor_core_pass_really_prunes(native, name, monkeypatch):
     bm, n, cm = metric.shape
     monkeypatch.setenv("TOME_TC_NO_FUSED_REFINE", "1")      # the streamed path leaves its pruning record in the workspace
     nm, ni, ws = native.match(_dev(metric), cls, False, algo=2, _return_workspace=True)
-    na, nb, n_ct, bn, rows, off_max, off_cnt = _tc_layout(bm, n, cm)
+    na, nb, n_ct, bn, rows, off_max, off_cnt = _tc_layout(native, bm, n, cm)
     tile_max = ws[off_max:off_max + rows * 4].view(torch.float32).view(bm, na, n_ct).cpu().numpy()
     tile_cnt = ws[off_cnt:off_cnt + rows * 4].view(torch.int32).view(bm, na, n_ct).cpu().numpy()
     s = O.scores(metric, cls, False)
-    eps = 4e-6 + 2e-7 * cm
+    eps = 5e-5 + 2e-7 * cm
     lo = 1 if cls else 0
     for c in range(n_ct):
         true = s[:, lo:, c * bn:min(nb, (c + 1) * bn)].max(-1)
@@ -291,8 +286,8 @@ def test_tensor_core_pass_really_prunes(native, name, monkeypatch):
     cnt = tile_cnt[:, lo:]
     assert (cnt == 255).sum() == 0, "no overflow expected on tie-free data"
     assert cnt.min() >= 1
-    assert (cnt == 1).mean() > (0.98 if cm <= 64 else 0.9), (cnt == 1).mean()
-    # measured error of the 3xTF32 pass, for DESIGN.md
+    assert (cnt == 1).mean() > (0.97 if cm <= 64 else 0.9), (cnt == 1).mean()
+    # measured error of the 3-product bf16 pass, for DESIGN.md
     err = 0.0
     for c in range(n_ct):
         true = s[:, lo:, c * bn:min(nb, (c + 1) * bn)].max(-1)
@@ -448,3 +443,26 @@ def test_fused_residual_equals_merging_the_sum(native, name, dtype):
         assert torch.equal(a_, b_)
     with pytest.raises(RuntimeError):
         native.merge(dp, xd, "wavg", residual=rd[:, :-1])
+
+
+@pytest.mark.parametrize("path", ["fused", "rank_kernels", "exact_simt"])
+@pytest.mark.parametrize("case", ALL_ACTIVE, ids=lambda c: c["name"])
+def test_plan_build_bit_exact_vs_oracle(native, case, path, monkeypatch):
+    """tome_plan_build (kernel 1's packed keys decoded by the one-launch sort-based select) gives the
+    oracle's node_max / node_idx / src / unm / dst bits; so do the rank-by-counting select kernels it
+    replaces (kept for very long sequences) and the exact SIMT matching."""
+    metric, _, _ = util.case_arrays(case)
+    cls, dis = bool(case.get("cls")), bool(case.get("distill"))
+    plan = _oracle_plan(case, metric)
+    if path == "rank_kernels":
+        monkeypatch.setenv("TOME_SELECT_RANK", "1")
+    dp = native.plan_build(_dev(metric), plan.r, cls, dis, algo=1 if path == "exact_simt" else 0)
+    np.testing.assert_array_equal(dp.node_idx.cpu().numpy(), plan.node_idx)
+    np.testing.assert_array_equal(dp.node_max.cpu().numpy().view(np.uint32), plan.node_max.view(np.uint32))
+    np.testing.assert_array_equal(dp.src_idx.cpu().numpy(), plan.src_idx)
+    np.testing.assert_array_equal(dp.unm_idx.cpu().numpy(), plan.unm_idx)
+    np.testing.assert_array_equal(dp.dst_idx.cpu().numpy(), plan.dst_idx)
+    # the CSR the merge kernel gathers through is the same whichever select built it
+    ref = native.select(_dev(plan.node_max), _dev(plan.node_idx), case["n"], plan.r, cls, dis)
+    for name in ("a_map", "b_off", "b_src", "b_head"):
+        assert torch.equal(getattr(dp, name), getattr(ref, name)), name

@@ -88,6 +88,10 @@ def main():
     ks = [torch.randn(bm, n, 3, 12, cm, device=dev, dtype=dt, generator=g).permute(2, 0, 3, 1, 4)[1] for _ in range(4)]
     med, best = graph_time([lambda i=i: _native.match_heads(_native.HeadMeanMetric(ks[i % 4]), bool(a.cls)) for i in range(8)])
     out["match_heads12"] = dict(us=med, us_best=best)
+    med, best = graph_time([lambda i=i: _native.plan_build(_native.HeadMeanMetric(ks[i % 4]), r, bool(a.cls)) for i in range(8)])
+    out["plan_build_heads12"] = dict(us=med, us_best=best)
+    med, best = graph_time([lambda i=i: _native.plan_build(ms[i % nrot], r, bool(a.cls)) for i in range(8)])
+    out["plan_build"] = dict(us=med, us_best=best)
     med, best = graph_time([lambda i=i: _native.match(ks[i % 4].mean(1), bool(a.cls)) for i in range(8)])
     out["torch_mean_then_match"] = dict(us=med, us_best=best)
     med, best = graph_time([lambda: _native.select(nm, ni, n, r, bool(a.cls)) for _ in range(8)])

@@ -5,12 +5,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "video-how-do-your-tokens-merge_b200")]
 import torch
 from tome import _native
-bm, n, cm = 8, 1568, 64
+bm, n, cm = 8, int(sys.argv[1]) if len(sys.argv) > 1 else 1568, 64
 g = torch.Generator(device="cuda").manual_seed(0)
 ms = [torch.randn(bm, n, cm, device="cuda", generator=g) for _ in range(3)]
 for m in ms: _native.match(m, algo=2)
 torch.cuda.synchronize()
-ncta = 4 * 7 * bm
+n_ct = _native.match_tc_describe(bm, n, cm)[0]
+ncta = n_ct * (((n + 1) // 2 + 127) // 128) * bm
+print("grid: %d column tiles x %d row strips x %d = %d CTAs, BN = %d" % (n_ct, ncta // n_ct // bm, bm, ncta, _native.match_tc_describe(bm, n, cm)[1]))
 tr = torch.zeros(ncta * 16, dtype=torch.int64, device="cuda")
 os.environ["TOME_TC_TRACE"] = str(tr.data_ptr())
 _native.match(ms[1], algo=2)

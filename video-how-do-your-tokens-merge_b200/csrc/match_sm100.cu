@@ -3,20 +3,25 @@
 // (norm, div, strided bmm that materialises a (bm, N/2, N/2) score tensor, two masked
 // fills, max).  The score matrix never leaves TMEM.
 //
-// Three launches:
-//   1. split_rows_kernel   one warp per token: fp64 sum of squares -> fp32 norm ->
-//                          mhat = fp32(x / norm), written as hi (tf32-exact top bits) and
-//                          lo = mhat - hi (exact) in the A-rows-then-B-rows layout TMA reads.
-//   2. match_tc_kernel     per (128 A rows) x (BN <= 256 B rows) x batch tile: TMA
-//                          (SWIZZLE_128B, K-major) -> 3xTF32 tcgen05.mma
-//                          (hi.hi + hi.lo + lo.hi, fp32 accumulate in TMEM) ->
-//                          epilogue straight out of TMEM: per row the approximate max and
-//                          every column within a proven error window of it (<= KCAND, else
-//                          "overflow").
-//   3. refine_rows_kernel  per A row: exact canonical score (fp64 FMA over mhat, same order
-//                          as match_exact.cu) of the few candidates -> node_max / node_idx.
-// The tensor-core pass only prunes; every reported bit comes from step 3, so this path and
-// the exact kernel agree bit for bit (tests/test_kernels_gpu.py).
+//   1. split_rows_kernel   one warp per token: (head-mean of K,) fp64 sum of squares -> fp32 norm ->
+//                          mhat = fp32(x / norm), written as fp32 (the exact operand) and as a two-term
+//                          bf16 split h = bf16(mhat), m = bf16(mhat - h) in the A-rows-then-B-rows
+//                          layout TMA reads.
+//   2. match_tc_kernel     per (128 A rows) x (BN <= 256 B rows) x batch tile: TMA (SWIZZLE_128B, K-major)
+//                          -> tcgen05.mma kind::f16 on the bf16 split (h.h + h.m + m.h, fp32 accumulate
+//                          in TMEM: an approximation with a PROVEN error bound) -> epilogue straight out
+//                          of TMEM: per row the approximate max and every column within the error window
+//                          of it (<= KCAND, else "overflow"), then the EXACT canonical score (fp64 FMA
+//                          over the fp32 mhat rows) of those few candidates, atomicMax of the packed
+//                          (score, ~column) key across column tiles.
+//   3. refine_rows_kernel  wide metrics only (cm > 128): the exact scoring as its own warp-per-row pass.
+// The tensor-core pass only prunes; every reported bit comes from the exact scoring, so this path and
+// match_exact.cu agree bit for bit (tests/test_kernels_gpu.py).
+//
+// Why bf16 x 3 and not tf32 x 3 (the first version, profiles/r01_match_notes.md): half the operand bytes,
+// one 128-byte swizzle row per 64 channels (Cm = 64 is ONE k-block), so a (128 x 112) tile is 60 KB of
+// shared memory and 128 TMEM columns -- three CTAs per SM, the whole layer-0 grid (392 CTAs) resident at
+// once instead of two waves of 172 KB CTAs.  The pruning window is 3.5x wider, still ~1 candidate/row.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -25,8 +30,8 @@
 namespace tome {
 
 constexpr int TC_BM = 128;        // A rows per tile == UMMA M == TMEM lanes
-constexpr int TC_BK = 32;         // fp32 per k-block == one 128-byte swizzle row
-constexpr int TC_UK = 8;          // UMMA K for kind::tf32
+constexpr int TC_BK = 64;         // bf16 per k-block == one 128-byte swizzle row
+constexpr int TC_UK = 16;         // UMMA K for kind::f16
 constexpr int KCAND = 4;          // candidates kept per (row, column tile)
 constexpr int TC_THREADS = 192;   // warp0 TMA, warp1 MMA + TMEM alloc, warps 2..5 epilogue
 constexpr int CNT_OVERFLOW = 255;
@@ -34,13 +39,15 @@ constexpr int CNT_OVERFLOW = 255;
 struct TcParams {
   int bm, n, na, nb, cm, cls, distill;
   int BN, n_ct, stages, num_kb, tmem_cols;
-  int rows_total;          // bm * n : row offset of the "lo" half of the split buffer
+  int rows_total;          // bm * n : row offset of the "m" plane of the bf16 split buffer
   float window;            // 2 * error bound of the tensor-core pass
-  float* tile_max;         // (bm, na, n_ct)            [streamed-K path only]
+  float* tile_max;         // (bm, na, n_ct)            [separate-refine path only]
   int* tile_cnt;           // (bm, na, n_ct)
   int* tile_cand;          // (bm, na, n_ct, KCAND)
-  int resident;            // all k-blocks stay in shared memory -> exact refine fused in the epilogue
-  unsigned long long* keys;  // (bm, na) packed (score key, ~column), atomicMax across column tiles
+  int fused_refine;        // exact scoring of the candidates in the epilogue (cm <= 128)
+  const float* mhat;       // (bm * n, cm) fp32 normalised rows, A rows then B rows per batch element
+  unsigned int* approx;    // (bm, na) orderable approximate row max over the tiles published so far (filter)
+  unsigned long long* keys;  // (bm, na) packed (exact score key, ~column), atomicMax across column tiles
   int* strip_count;        // (bm, row tiles) arrivals; last column tile of a strip decodes the keys
   float* node_max;         // (bm, na)
   int* node_idx;           // (bm, na)
@@ -48,79 +55,109 @@ struct TcParams {
 };
 
 // ---------------------------------------------------------------------------------------------
-// 1. normalise + hi/lo split
+// 1. normalise + split
 // ---------------------------------------------------------------------------------------------
 // `heads` > 1: the metric is the head-mean of K (tome/patch/videomae.py:72-73 `k.mean(1)`), taken here
 // instead of in a separate reduction kernel: element (b, t, k) = mean_h keys[b, h, t, k], rounded to
 // the input dtype first (what the reference's k.mean(1) tensor holds), then normalised.
+// Each lane owns channel PAIRS (2 lane + 64 q): one 4-byte (bf16) / 8-byte (fp32) load per head covers
+// a 64-channel head row per warp instruction.
+__device__ __forceinline__ float2 ld_pair(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ float2 ld_pair(const __nv_bfloat16* p) {
+  const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p));
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+}
+
+template <typename T>
+__device__ __forceinline__ float2 metric_pair(const T* src, int heads, long long stride_h, int k) {
+  if (heads == 1) return ld_pair(src + k);
+  float2 s = make_float2(0.f, 0.f);       // heads added in order; 1/H multiply like ATen's MeanOps
+  int h = 0;
+  for (; h + 12 <= heads; h += 12) {      // ViT-B's 12 heads: every load in flight before the first add
+    float2 a[12];
+#pragma unroll
+    for (int u = 0; u < 12; ++u) a[u] = ld_pair(src + (long long)(h + u) * stride_h + k);
+#pragma unroll
+    for (int u = 0; u < 12; ++u) { s.x += a[u].x; s.y += a[u].y; }      // adds stay sequential in h
+  }
+  for (; h + 4 <= heads; h += 4) {        // four loads in flight, adds kept sequential
+    const float2 a0 = ld_pair(src + (long long)(h + 0) * stride_h + k);
+    const float2 a1 = ld_pair(src + (long long)(h + 1) * stride_h + k);
+    const float2 a2 = ld_pair(src + (long long)(h + 2) * stride_h + k);
+    const float2 a3 = ld_pair(src + (long long)(h + 3) * stride_h + k);
+    s.x = (((s.x + a0.x) + a1.x) + a2.x) + a3.x;
+    s.y = (((s.y + a0.y) + a1.y) + a2.y) + a3.y;
+  }
+  for (; h < heads; ++h) {
+    const float2 a = ld_pair(src + (long long)h * stride_h + k);
+    s.x += a.x; s.y += a.y;
+  }
+  const float inv = 1.0f / (float)heads;
+  s.x *= inv; s.y *= inv;
+  if (sizeof(T) == 2) {
+    s.x = __bfloat162float(__float2bfloat16_rn(s.x));
+    s.y = __bfloat162float(__float2bfloat16_rn(s.y));
+  }
+  return s;
+}
+
+__device__ __forceinline__ void store_split(float2 m, __nv_bfloat16* h_row, __nv_bfloat16* m_row, float* f_row, int k) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(m.x, m.y);
+  const float2 hf = __bfloat1622float2(h);
+  *reinterpret_cast<__nv_bfloat162*>(h_row + k) = h;
+  *reinterpret_cast<__nv_bfloat162*>(m_row + k) = __floats2bfloat162_rn(m.x - hf.x, m.y - hf.y);   // differences are exact
+  *reinterpret_cast<float2*>(f_row + k) = m;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) split_rows_kernel(const T* __restrict__ metric, View v, int heads, long long stride_h,
-                                                         int bm, int n, int cm, float* __restrict__ split,
-                                                         unsigned long long* __restrict__ keys,
-                                                         int* __restrict__ strip_count, int n_strips) {
+                                                         int bm, int n, int cm, __nv_bfloat16* __restrict__ hm,
+                                                         float* __restrict__ mhat, unsigned long long* __restrict__ keys,
+                                                         unsigned int* __restrict__ approx, int* __restrict__ strip_count,
+                                                         int n_strips) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= bm * n) return;
   const int b = warp / n, t = warp - b * n, na = na_of(n);
   if (lane == 0) {
-    if (!(t & 1)) keys[(long long)b * na + (t >> 1)] = 0ull;
+    if (!(t & 1)) { keys[(long long)b * na + (t >> 1)] = 0ull; approx[(long long)b * na + (t >> 1)] = 0u; }
     if (warp < n_strips) strip_count[warp] = 0;
   }
   const T* src = metric + v.batch_offset(b) + (long long)t * v.sn;
   const int row = (t & 1) ? na + (t >> 1) : (t >> 1);
-  float* hi = split + ((long long)b * n + row) * cm;
-  float* lo = hi + (long long)bm * n * cm;
-  auto value = [&](int k) -> float {
-    if (heads == 1) return ld_as_float(src + k);
-    float s = 0.f;                 // heads added in order; 1/H multiply like ATen's MeanOps
-    int h = 0;
-    for (; h + 4 <= heads; h += 4) {          // four loads in flight, adds kept sequential
-      const float a0 = ld_as_float(src + (long long)(h + 0) * stride_h + k);
-      const float a1 = ld_as_float(src + (long long)(h + 1) * stride_h + k);
-      const float a2 = ld_as_float(src + (long long)(h + 2) * stride_h + k);
-      const float a3 = ld_as_float(src + (long long)(h + 3) * stride_h + k);
-      s = ((s + a0) + a1) + a2;
-      s = s + a3;
-    }
-    for (; h < heads; ++h) s += ld_as_float(src + (long long)h * stride_h + k);
-    s = s * (1.0f / (float)heads);
-    if (sizeof(T) == 2) s = __bfloat162float(__float2bfloat16_rn(s));
-    return s;
-  };
-  if (cm <= 128) {                 // whole row in registers: one pass over global memory
-    float x[4];
+  const long long ro = ((long long)b * n + row) * cm;
+  __nv_bfloat16* h_row = hm + ro;
+  __nv_bfloat16* m_row = h_row + (long long)bm * n * cm;
+  float* f_row = mhat + ro;
+  if (cm <= 256) {                 // whole row in registers: one pass over global memory
+    float2 x[4];
     double ss = 0.0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int k = lane + 32 * q;
-      x[q] = k < cm ? value(k) : 0.f;
-      ss = fma((double)x[q], (double)x[q], ss);
+      const int k = 2 * lane + 64 * q;
+      x[q] = k < cm ? metric_pair(src, heads, stride_h, k) : make_float2(0.f, 0.f);
+      ss = fma((double)x[q].x, (double)x[q].x, ss);
+      ss = fma((double)x[q].y, (double)x[q].y, ss);
     }
     ss = warp_sum(ss);
     const float norm = (float)sqrt(ss);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int k = lane + 32 * q;
-      if (k < cm) {
-        const float m = __fdiv_rn(x[q], norm);
-        const float h = __uint_as_float(__float_as_uint(m) & 0xFFFFE000u);
-        hi[k] = h;
-        lo[k] = m - h;             // exact: fewer than 24 significant bits remain
-      }
+      const int k = 2 * lane + 64 * q;
+      if (k < cm) store_split(make_float2(__fdiv_rn(x[q].x, norm), __fdiv_rn(x[q].y, norm)), h_row, m_row, f_row, k);
     }
     return;
   }
   double ss = 0.0;
-  for (int k = lane; k < cm; k += 32) {
-    const double x = (double)value(k);
-    ss = fma(x, x, ss);
+  for (int k = 2 * lane; k < cm; k += 64) {
+    const float2 x = metric_pair(src, heads, stride_h, k);
+    ss = fma((double)x.x, (double)x.x, ss);
+    ss = fma((double)x.y, (double)x.y, ss);
   }
   ss = warp_sum(ss);
   const float norm = (float)sqrt(ss);
-  for (int k = lane; k < cm; k += 32) {
-    const float m = __fdiv_rn(value(k), norm);
-    const float h = __uint_as_float(__float_as_uint(m) & 0xFFFFE000u);
-    hi[k] = h;
-    lo[k] = m - h;
+  for (int k = 2 * lane; k < cm; k += 64) {
+    const float2 x = metric_pair(src, heads, stride_h, k);
+    store_split(make_float2(__fdiv_rn(x.x, norm), __fdiv_rn(x.y, norm)), h_row, m_row, f_row, k);
   }
 }
 
@@ -158,11 +195,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -205,14 +242,6 @@ __device__ __forceinline__ float fmax_nan(float a, float b) {     // NaN-propaga
   asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
   return r;
 }
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-// byte offset of the 16-byte chunk holding k..k+3 (k % 4 == 0, k < 32) of row r in a SWIZZLE_128B tile
-__device__ __forceinline__ uint32_t sw128_off(int r, int k) { return (uint32_t)r * 128u + ((((uint32_t)k >> 2) ^ ((uint32_t)r & 7u)) << 4); }
-
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
 //   [0,14) start address >> 4, [16,30) LBO >> 4 (unused for swizzled K-major),
 //   [32,46) SBO >> 4 = 1024 B between 8-row groups, [46,48) version = 1, [61,64) layout = 2.
@@ -228,28 +257,76 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // ---------------------------------------------------------------------------------------------
 // 2. TMA -> tcgen05 -> TMEM epilogue
 // ---------------------------------------------------------------------------------------------
-// Exact canonical score of (tile row r, tile column c) from the SWIZZLE_128B stage buffers
-// (all k-blocks resident): same fp64 FMA order as match_exact.cu / refine_rows_kernel.
-__device__ __forceinline__ float exact_from_smem(uint32_t base, uint32_t stage_bytes, uint32_t a_bytes, uint32_t b_bytes,
-                                                 int num_kb, int r, int c) {
+// Exact canonical scores from the fp32 normalised rows: every product is exact in fp64, the sum is
+// fp64 (the order of the fp64 additions is not part of the score definition), one
+// rounding to fp32 at the end.
+//
+// warp_exact32: lane r owns A row `a_blk + r * cm` and wants its score against B row `brows + col * cm`
+// (`act`: this lane has work).  One thread per row reading its two 256-byte rows cost 5.9 us per CTA
+// (32 scattered sectors per load instruction), and a warp walking the rows one at a time 12.5 us (32
+// dependent L2 round trips) -- profiles/r01_match_notes.md.  Here the warp takes EIGHT work items per pass,
+// four lanes per item: a lane loads every fourth 16-byte chunk of the row pair (the four lanes cover 64
+// contiguous bytes per instruction), all loads of a pass are issued before the first use, and the sum
+// needs two shuffles.  Items are the set bits of the ballot, compacted, so the usual 4-5 active rows of
+// a warp (the cross-tile filter below removes the rest) take ONE pass.  cm <= 128, cm % 4 == 0.
+__device__ __forceinline__ double pair_dot(const float* __restrict__ a, const float* __restrict__ b, int cm, int lane) {
   double acc = 0.0;
-  for (int kb = 0; kb < num_kb; ++kb) {
-    const uint32_t st = base + (uint32_t)kb * stage_bytes;
-#pragma unroll
-    for (int k = 0; k < TC_BK; k += 4) {
-      const uint32_t oa = sw128_off(r, k), ob = sw128_off(c, k);
-      const float4 ah = lds128(st + oa), al = lds128(st + a_bytes + oa);
-      const float4 bh = lds128(st + 2u * a_bytes + ob), bl = lds128(st + 2u * a_bytes + b_bytes + ob);
-      acc = fma((double)(ah.x + al.x), (double)(bh.x + bl.x), acc);
-      acc = fma((double)(ah.y + al.y), (double)(bh.y + bl.y), acc);
-      acc = fma((double)(ah.z + al.z), (double)(bh.z + bl.z), acc);
-      acc = fma((double)(ah.w + al.w), (double)(bh.w + bl.w), acc);
-    }
+  for (int k = 2 * lane; k < cm; k += 64) {
+    const float2 x = __ldg(reinterpret_cast<const float2*>(a + k)), y = __ldg(reinterpret_cast<const float2*>(b + k));
+    acc = fma((double)x.x, (double)y.x, acc);
+    acc = fma((double)x.y, (double)y.y, acc);
   }
-  return (float)acc;
+  return acc;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__device__ __forceinline__ float warp_exact32(const float* __restrict__ a_blk, const float* __restrict__ brows, int cm,
+                                              bool act, int col, int lane) {
+  const unsigned full = 0xffffffffu;
+  const unsigned actmask = __ballot_sync(full, act);
+  float mine = 0.f;
+  const int items = __popc(actmask);
+  if (items == 0) return mine;
+  const int sub = lane & 3;                      // which quarter of the 16-byte chunks of a row this lane reads
+  const int nchunk = cm >> 2;                    // 16-byte chunks per row
+  const int my_item = __popc(actmask & ((1u << lane) - 1u));     // position of this lane's own row in the work list
+#pragma unroll 1
+  for (int g = 0; 8 * g < items; ++g) {
+    const int item = 8 * g + (lane >> 2);        // the work item this lane helps with in this pass
+    const bool on = item < items;
+    const int r = on ? (int)__fns(actmask, 0, item + 1) : 0;     // its row: the item-th set bit
+    const int c = __shfl_sync(full, col, r);
+    const float4* ap = reinterpret_cast<const float4*>(a_blk + (long long)r * cm);
+    const float4* bp = reinterpret_cast<const float4*>(brows + (long long)c * cm);
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll 1
+    for (int f0 = 0; f0 < nchunk; f0 += 16) {    // 16 chunks (64 channels) per step: 4 chunks per lane
+      float4 x[4], y[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int f = f0 + 4 * t + sub;
+        const bool ok = on && f < nchunk;
+        x[t] = ok ? __ldg(ap + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        y[t] = ok ? __ldg(bp + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        acc0 = fma((double)x[t].x, (double)y[t].x, acc0);
+        acc1 = fma((double)x[t].y, (double)y[t].y, acc1);
+        acc2 = fma((double)x[t].z, (double)y[t].z, acc2);
+        acc3 = fma((double)x[t].w, (double)y[t].w, acc3);
+      }
+    }
+    double sum = (acc0 + acc1) + (acc2 + acc3);
+    sum += __shfl_xor_sync(full, sum, 1);
+    sum += __shfl_xor_sync(full, sum, 2);
+    // item 8g + u of the pass was summed by lanes 4u .. 4u+3; its owner fetches it
+    const double res = __shfl_sync(full, sum, (my_item & 7) << 2);
+    if (act && (my_item >> 3) == g) mine = (float)res;
+  }
+  return mine;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 3)
 match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -258,7 +335,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (threadIdx.x == 0) TC_TRACE(0);
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024-byte alignment
   const uint32_t a_bytes = TC_BM * 128u, b_bytes = (uint32_t)p.BN * 128u;
-  const uint32_t stage_bytes = 2u * (a_bytes + b_bytes);
+  const uint32_t stage_bytes = 2u * (a_bytes + b_bytes);            // A h | A m | B h | B m
   const uint32_t bars = base + (uint32_t)p.stages * stage_bytes;    // full[stages] | empty[stages] | tmem_full | tmem_ptr
   const uint32_t bar_full = bars, bar_empty = bars + 8u * p.stages, bar_tmem = bars + 16u * p.stages;
   const uint32_t tmem_slot = bar_tmem + 8u;
@@ -281,7 +358,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const uint32_t tmem_base = *tmem_slot_ptr;
   if (threadIdx.x == 0) TC_TRACE(1);
 
-  const int row_a = b * p.n + it * TC_BM;               // rows of the split buffer (hi half)
+  const int row_a = b * p.n + it * TC_BM;               // rows of the split buffer (h plane)
   const int row_b = b * p.n + p.na + jt * p.BN;
 
   if (warp == 0) {
@@ -291,16 +368,16 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         mbar_wait(bar_empty + 8u * s, ((kb / p.stages) & 1) ^ 1);
         const uint32_t st = base + (uint32_t)s * stage_bytes, full = bar_full + 8u * s;
         mbar_expect_tx(full, stage_bytes);
-        tma_load_2d(st, &map_a, kb * TC_BK, row_a, full);                                   // A hi
-        tma_load_2d(st + a_bytes, &map_a, kb * TC_BK, row_a + p.rows_total, full);          // A lo
-        tma_load_2d(st + 2u * a_bytes, &map_b, kb * TC_BK, row_b, full);                    // B hi
-        tma_load_2d(st + 2u * a_bytes + b_bytes, &map_b, kb * TC_BK, row_b + p.rows_total, full);  // B lo
+        tma_load_2d(st, &map_a, kb * TC_BK, row_a, full);                                   // A h
+        tma_load_2d(st + a_bytes, &map_a, kb * TC_BK, row_a + p.rows_total, full);          // A m
+        tma_load_2d(st + 2u * a_bytes, &map_b, kb * TC_BK, row_b, full);                    // B h
+        tma_load_2d(st + 2u * a_bytes + b_bytes, &map_b, kb * TC_BK, row_b + p.rows_total, full);  // B m
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // instruction descriptor: D fp32, A/B tf32, both K-major, N = BN, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       for (int kb = 0; kb < p.num_kb; ++kb) {
         const int s = kb % p.stages;
         mbar_wait(bar_full + 8u * s, (kb / p.stages) & 1);
@@ -308,14 +385,14 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (kb == 0) TC_TRACE(2);
         if (kb == p.num_kb - 1) TC_TRACE(3);
         const uint32_t st = base + (uint32_t)s * stage_bytes;
-        const uint64_t a_hi = make_sw128_desc(st), a_lo = make_sw128_desc(st + a_bytes);
-        const uint64_t b_hi = make_sw128_desc(st + 2u * a_bytes), b_lo = make_sw128_desc(st + 2u * a_bytes + b_bytes);
+        const uint64_t a_h = make_sw128_desc(st), a_m = make_sw128_desc(st + a_bytes);
+        const uint64_t b_h = make_sw128_desc(st + 2u * a_bytes), b_m = make_sw128_desc(st + 2u * a_bytes + b_bytes);
 #pragma unroll
         for (int k = 0; k < TC_BK / TC_UK; ++k) {
-          const uint64_t adv = (uint64_t)((k * TC_UK * 4) >> 4);     // +32 bytes inside the swizzle row
-          umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
-          umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
-          umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
+          const uint64_t adv = (uint64_t)((k * TC_UK * 2) >> 4);     // +32 bytes inside the swizzle row
+          umma_bf16(tmem_base, a_h + adv, b_h + adv, idesc, (kb | k) ? 1u : 0u);
+          umma_bf16(tmem_base, a_h + adv, b_m + adv, idesc, 1u);
+          umma_bf16(tmem_base, a_m + adv, b_h + adv, idesc, 1u);
         }
         umma_commit(bar_empty + 8u * s);      // frees the stage when these MMAs retire
       }
@@ -333,24 +410,23 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     tc_fence_after();
     if (threadIdx.x == 64) TC_TRACE(5);
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    // pass 1: approximate row max over the valid columns, remembering the max of every 32-column
-    // chunk.  max.NaN propagates NaN, so a NaN anywhere (zero-norm row) surfaces in m.
+    // pass 1: approximate row max over the valid columns.  max.NaN propagates NaN, so a NaN anywhere
+    // (zero-norm row) surfaces in m.
     constexpr int MAXCH = 8;                   // BN <= 256
-    float chmax[MAXCH];
-#pragma unroll
-    for (int q = 0; q < MAXCH; ++q) chmax[q] = -INFINITY;
     float m = -INFINITY;
 #pragma unroll
-    for (int q = 0; q < MAXCH; ++q) {
-      const int c = q * 32;
+    for (int ch = 0; ch < MAXCH; ++ch) {
+      const int c = ch * 32;
       if (c < ncol) {                          // warp-uniform
         float cm = -INFINITY;
         if (c + 32 <= ncol) {
           float v[32];
           tmem_ld32(taddr + (uint32_t)c, v);
           if (mask0 && c == 0) v[0] = -INFINITY;
+          float part[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};      // four independent max chains
 #pragma unroll
-          for (int e = 0; e < 32; ++e) cm = fmax_nan(cm, v[e]);
+          for (int e = 0; e < 32; ++e) part[e & 3] = fmax_nan(part[e & 3], v[e]);
+          cm = fmax_nan(fmax_nan(part[0], part[1]), fmax_nan(part[2], part[3]));
         } else {
           for (int cc = c; cc < ncol; cc += 16) {
             float v[16];
@@ -360,11 +436,12 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             for (int e = 0; e < 16; ++e) cm = fmax_nan(cm, (cc + e < ncol) ? v[e] : -INFINITY);
           }
         }
-        chmax[q] = cm;
         m = fmax_nan(m, cm);
       }
     }
     const bool has_nan = (m != m);
+    // publish this tile's approximate row max: tiles that later see a clearly better one skip their exact work
+    if (p.fused_refine && i < p.na && !has_nan) atomicMax(p.approx + (long long)b * p.na + i, orderable_key(m));
     if (threadIdx.x == 64) TC_TRACE(6);
     // pass 2: every column within the error window of the max is a candidate.  Branch-free: one bit
     // per column (a divergent scan with a dynamically indexed candidate list cost 5.6 us per CTA,
@@ -372,8 +449,8 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const float thr = m - p.window;
     uint32_t bits[MAXCH];
 #pragma unroll
-    for (int q = 0; q < MAXCH; ++q) {
-      const int c = q * 32;
+    for (int ch = 0; ch < MAXCH; ++ch) {
+      const int c = ch * 32;
       uint32_t bm_ = 0u;
       if (c < ncol && !has_nan) {              // warp-uniform
         if (c + 32 <= ncol) {
@@ -394,18 +471,21 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           }
         }
       }
-      bits[q] = bm_;
+      bits[ch] = bm_;
     }
     if (threadIdx.x == 64) TC_TRACE(11);
+    // cross-tile filter (see below): the read-back is issued here so that its latency hides behind the extraction
+    unsigned int peer_key = 0u;
+    if (p.fused_refine && i < p.na && !has_nan) peer_key = __ldcg(p.approx + (long long)b * p.na + i);
     int cnt = 0, filled = 0, cand[KCAND];
 #pragma unroll
     for (int e = 0; e < KCAND; ++e) cand[e] = 0;
 #pragma unroll
-    for (int q = 0; q < MAXCH; ++q) {
-      uint32_t w = bits[q];
+    for (int ch = 0; ch < MAXCH; ++ch) {
+      uint32_t w = bits[ch];
       cnt += __popc(w);
       while (w != 0u && filled < KCAND) {        // rare per (lane, chunk): a real branch beats a predicated chain
-        const int col = q * 32 + __ffs(w) - 1;
+        const int col = ch * 32 + __ffs(w) - 1;
         w &= w - 1u;
         if (filled == 0) cand[0] = col;
         else if (filled == 1) cand[1] = col;
@@ -416,46 +496,64 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
     if (threadIdx.x == 64) TC_TRACE(7);
     const bool overflow = has_nan || cnt > KCAND;
-    if (!p.resident) {
-      if (i < p.na) {
+    if (!p.fused_refine) {
+      if (i < p.na) {                          // this tile's pruning record for the row (refine_rows_kernel reads it)
         const long long o = ((long long)b * p.na + i) * p.n_ct + jt;
         p.tile_max[o] = m;
         p.tile_cnt[o] = overflow ? CNT_OVERFLOW : cnt;
-#pragma unroll
-        for (int s = 0; s < KCAND; ++s) p.tile_cand[o * KCAND + s] = j0 + cand[s];
+        *reinterpret_cast<int4*>(p.tile_cand + o * KCAND) = make_int4(j0 + cand[0], j0 + cand[1], j0 + cand[2], j0 + cand[3]);
       }
-    } else if (i < p.na) {
-      // exact refine straight from the operand tiles still sitting in shared memory
-      for (int s = 0; s < p.num_kb; ++s) mbar_wait(bar_full + 8u * s, 0);     // acquire the TMA writes
-      unsigned long long best = 0ull;
-      if (p.cls && i == 0) {
-        best = pack_best(-INFINITY, 0);
-      } else if (overflow) {
+    } else {
+      // Exact scoring of the survivors from the fp32 rows (L2-resident: split_rows just wrote them),
+      // warp-cooperatively.  Cross-tile filter first: the other column tiles of this row strip run at the
+      // same time and have published their approximate maxima; if one of them beats ours by more than the
+      // window, this tile cannot hold the row's max and its exact work is skipped.  The filter is purely
+      // opportunistic -- a tile that has not published yet just means some exact work that loses the
+      // atomicMax below -- so the result does not depend on timing.
+      const bool valid = i < p.na, cls_row = p.cls && i == 0;
+      bool skip = false;
+      if (valid && !has_nan) skip = key_to_float(peer_key) > m + p.window;
+      const float* a_blk = p.mhat + ((long long)b * p.n + it * TC_BM + q * 32) * p.cm;
+      const float* brows = p.mhat + ((long long)b * p.n + p.na + j0) * p.cm;
+      unsigned long long best = cls_row ? pack_best(-INFINITY, 0) : 0ull;
+      const bool need = valid && !cls_row && !overflow && !skip;
+      const int rounds = __reduce_max_sync(0xffffffffu, need ? cnt : 0);
+      for (int sidx = 0; sidx < rounds; ++sidx) {
+        const bool act = need && sidx < cnt;
+        const int col = sidx == 0 ? cand[0] : sidx == 1 ? cand[1] : sidx == 2 ? cand[2] : cand[3];
+        const float sc = warp_exact32(a_blk, brows, p.cm, act, col, lane);
+        if (act) {
+          const unsigned long long k = pack_best(sc, j0 + col);
+          best = k > best ? k : best;
+        }
+      }
+      unsigned ov = __ballot_sync(0xffffffffu, valid && !cls_row && overflow && !skip);
+      while (ov) {                               // too many near-ties (or NaN) in this row: score the whole tile
+        const int r = __ffs(ov) - 1;
+        ov &= ov - 1u;
         for (int cc = 0; cc < ncol; ++cc) {
-          const float sc = (mask0 && cc == 0) ? -INFINITY : exact_from_smem(base, stage_bytes, a_bytes, b_bytes, p.num_kb, row, cc);
-          const unsigned long long k = pack_best(sc, j0 + cc);
-          best = k > best ? k : best;
-        }
-      } else {
-        for (int s = 0; s < cnt; ++s) {
-          const float sc = exact_from_smem(base, stage_bytes, a_bytes, b_bytes, p.num_kb, row, cand[s]);
-          const unsigned long long k = pack_best(sc, j0 + cand[s]);
-          best = k > best ? k : best;
+          double acc = pair_dot(a_blk + (long long)r * p.cm, brows + (long long)cc * p.cm, p.cm, lane);
+          acc = warp_sum(acc);
+          if (lane == r) {
+            const float sc = (mask0 && cc == 0) ? -INFINITY : (float)acc;
+            const unsigned long long k = pack_best(sc, j0 + cc);
+            best = k > best ? k : best;
+          }
         }
       }
-      atomicMax(p.keys + (long long)b * p.na + i, best);
+      if (valid && best != 0ull) atomicMax(p.keys + (long long)b * p.na + i, best);
     }
   }
   if (threadIdx.x == 64) TC_TRACE(8);
   tc_fence_before();
-  if (p.resident) __threadfence();
+  if (p.fused_refine) __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) TC_TRACE(9);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
-  if (p.resident) {
+  if (p.fused_refine) {
     // last column tile of this (batch, row strip) turns the packed keys into node_max / node_idx
     if (threadIdx.x == 0) {
       const int strip = b * gridDim.y + it;
@@ -478,51 +576,50 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------
-// 3. exact refine (streamed-K path): canonical fp64 score of the surviving candidates
+// 3. exact refine as its own pass (wide metrics): canonical fp64 score of the surviving candidates
 // ---------------------------------------------------------------------------------------------
-// One WARP per A row: lanes stride k, so every candidate costs four coalesced row reads (hi/lo of A and
-// B) and a warp reduction.  (The first version used one thread per row: at Cm = 768 its uncoalesced,
-// serial 768-step loops took 400 us.)  fp64 partial sums per lane, then a butterfly: the order of the
-// fp64 additions is not part of the score definition (it can move the fp32-rounded result only when
-// the fp64 sum lies within ~1e-16 of a rounding boundary).
-__device__ __forceinline__ float exact_score_warp(const float* __restrict__ ah, const float* __restrict__ al,
-                                                  const float* __restrict__ bh, const float* __restrict__ bl, int cm, int lane) {
+// One WARP per A row: lanes stride k, so every candidate costs two coalesced row reads and a warp
+// reduction.  (The first version used one thread per row: at Cm = 768 its uncoalesced, serial 768-step
+// loops took 400 us.)  fp64 partial sums per lane, then a butterfly: the order of the fp64 additions
+// is not part of the score definition (it can move the fp32-rounded result only when the fp64 sum lies
+// within ~1e-16 of a rounding boundary).
+__device__ __forceinline__ float exact_score_warp(const float* __restrict__ a, const float* __restrict__ b, int cm, int lane) {
   double acc = 0.0;
-  for (int k = lane; k < cm; k += 32) acc = fma((double)(ah[k] + al[k]), (double)(bh[k] + bl[k]), acc);
+  for (int k = lane; k < cm; k += 32) acc = fma((double)a[k], (double)b[k], acc);
   acc = warp_sum(acc);
   return (float)acc;
 }
 
-__global__ void __launch_bounds__(256) refine_rows_kernel(const float* __restrict__ split, TcParams p,
-                                                          float* __restrict__ node_max, int* __restrict__ node_idx) {
+__global__ void __launch_bounds__(256) refine_rows_kernel(TcParams p, float* __restrict__ node_max, int* __restrict__ node_idx) {
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t >= p.bm * p.na) return;
   const int b = t / p.na, i = t - b * p.na;
-  if (p.cls && i == 0) { if (lane == 0) { node_max[t] = -INFINITY; node_idx[t] = 0; } return; }
-  const long long lo_off = (long long)p.rows_total * p.cm;
-  const float* ah = split + ((long long)b * p.n + i) * p.cm;
-  const float* bbase = split + ((long long)b * p.n + p.na) * p.cm;
-  const long long o = (long long)t * p.n_ct;
-  float big = -INFINITY;
-  for (int c = 0; c < p.n_ct; ++c) big = fmaxf(big, p.tile_max[o + c]);
-  const float thr = big - p.window;
   unsigned long long best = 0ull;
-  for (int c = 0; c < p.n_ct; ++c) {
-    const int cnt = p.tile_cnt[o + c];
-    if (cnt == CNT_OVERFLOW) {            // too many near-ties (or NaN): score the whole column tile exactly
-      const int je = min(p.nb, (c + 1) * p.BN);
-      for (int j = c * p.BN; j < je; ++j) {
-        const float s = (p.distill && j == 0) ? -INFINITY
-                                              : exact_score_warp(ah, ah + lo_off, bbase + (long long)j * p.cm, bbase + (long long)j * p.cm + lo_off, p.cm, lane);
-        const unsigned long long k = pack_best(s, j);
-        best = k > best ? k : best;
-      }
-    } else if (p.tile_max[o + c] >= thr) {
-      for (int s = 0; s < cnt; ++s) {
-        const int j = p.tile_cand[(o + c) * KCAND + s];
-        const float sc = exact_score_warp(ah, ah + lo_off, bbase + (long long)j * p.cm, bbase + (long long)j * p.cm + lo_off, p.cm, lane);
-        const unsigned long long k = pack_best(sc, j);
-        best = k > best ? k : best;
+  if (p.cls && i == 0) {
+    best = pack_best(-INFINITY, 0);
+  } else {
+    const float* arow = p.mhat + ((long long)b * p.n + i) * p.cm;
+    const float* bbase = p.mhat + ((long long)b * p.n + p.na) * p.cm;
+    const long long o = (long long)t * p.n_ct;
+    float big = -INFINITY;
+    for (int c = 0; c < p.n_ct; ++c) big = fmaxf(big, p.tile_max[o + c]);
+    const float thr = big - p.window;
+    for (int c = 0; c < p.n_ct; ++c) {
+      const int cnt = p.tile_cnt[o + c];
+      if (cnt == CNT_OVERFLOW) {            // too many near-ties (or NaN): score the whole column tile exactly
+        const int je = min(p.nb, (c + 1) * p.BN);
+        for (int j = c * p.BN; j < je; ++j) {
+          const float s = (p.distill && j == 0) ? -INFINITY : exact_score_warp(arow, bbase + (long long)j * p.cm, p.cm, lane);
+          const unsigned long long k = pack_best(s, j);
+          best = k > best ? k : best;
+        }
+      } else if (p.tile_max[o + c] >= thr) {
+        for (int s = 0; s < cnt; ++s) {
+          const int j = p.tile_cand[(o + c) * KCAND + s];
+          const float sc = exact_score_warp(arow, bbase + (long long)j * p.cm, p.cm, lane);
+          const unsigned long long k = pack_best(sc, j);
+          best = k > best ? k : best;
+        }
       }
     }
   }
@@ -543,43 +640,77 @@ static int env_int(const char* name, int dflt) {
 static void tc_geometry(int bm, int n, int cm, TcParams& p) {
   p.bm = bm; p.n = n; p.na = na_of(n); p.nb = nb_of(n); p.cm = cm;
   p.num_kb = (cm + TC_BK - 1) / TC_BK;
-  int n_ct = (p.nb + 255) / 256;
-  const int forced = env_int("TOME_TC_NCT", 0);          // tuning knob (bench sweeps)
+  const int n_rt = (p.na + TC_BM - 1) / TC_BM;
+  // column tiles: 128 wide by default (60-64 KB of operands: three CTAs per SM); narrower, down to 64,
+  // while the whole grid would otherwise leave SM slots empty
+  int n_ct = (p.nb + 127) / 128;
+  const int want = (2 * 148) / (bm * n_rt > 0 ? bm * n_rt : 1);
+  const int n_ct_max = (p.nb + 63) / 64;
+  if (want > n_ct) n_ct = want < n_ct_max ? want : n_ct_max;
+  const int forced = env_int("TOME_TC_NCT", 0);          // tuning knob (bench sweeps, tests)
   if (forced > 0) n_ct = forced > (p.nb + 15) / 16 ? (p.nb + 15) / 16 : forced;
   if (n_ct < (p.nb + 255) / 256) n_ct = (p.nb + 255) / 256;
-  p.n_ct = n_ct;
-  int bn = (p.nb + p.n_ct - 1) / p.n_ct;
+  if (n_ct < 1) n_ct = 1;
+  int bn = (p.nb + n_ct - 1) / n_ct;
   bn = (bn + 15) & ~15;
   p.BN = bn < 16 ? 16 : bn;
   p.n_ct = (p.nb + p.BN - 1) / p.BN;
   const int stage_bytes = 2 * (TC_BM + p.BN) * 128;
-  int st = (216 * 1024) / stage_bytes;
+  int st = (200 * 1024) / stage_bytes;
   st = st > 4 ? 4 : st;
   p.stages = st > p.num_kb ? p.num_kb : st;
-  p.resident = (p.num_kb <= p.stages) && !env_int("TOME_TC_NO_FUSED_REFINE", 0);
+  p.fused_refine = (cm <= 128) && !env_int("TOME_TC_NO_FUSED_REFINE", 0);
   p.tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
-  // error bound of hi.hi + hi.lo + lo.hi with fp32 accumulation on unit vectors:
-  // 3 * 2^-20 (dropped lo.lo + truncated lo) + (3 cm / 8) accumulations * 2^-22, with margin
-  const float eps = 4e-6f + 2e-7f * (float)cm;
+  // error bound of h.h + h.m + m.h on unit vectors: x = h + m + l with |l| <= 2^-16 |x|, so the
+  // three dropped products (m.m, l.b, a.l) are <= 3 * 2^-16 = 4.6e-5 by Cauchy-Schwarz; the bf16 products
+  // are exact in fp32 and the (3 cm / 16) fp32 accumulations add <= 2^-22 each; margin on top
+  const float eps = 5e-5f + 2e-7f * (float)cm;
   p.window = 2.0f * eps;
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+struct TcLayout { size_t hm, mhat, tile_max, tile_cnt, tile_cand, keys, approx, strips, total; };
+
+static TcLayout tc_layout(int bm, int n, const TcParams& p) {
+  TcLayout l;
+  const size_t elems = (size_t)bm * n * p.cm, rows = (size_t)bm * p.na * p.n_ct;
+  const size_t strips = (size_t)bm * ((p.na + TC_BM - 1) / TC_BM);
+  size_t o = 0;
+  l.hm = o;        o += align256(2 * elems * sizeof(__nv_bfloat16));
+  l.mhat = o;      o += align256(elems * sizeof(float));
+  l.tile_max = o;  o += align256(rows * 4);
+  l.tile_cnt = o;  o += align256(rows * 4);
+  l.tile_cand = o; o += align256(rows * 4 * KCAND);
+  l.keys = o;      o += align256((size_t)bm * p.na * 8);
+  l.approx = o;    o += align256((size_t)bm * p.na * 4);
+  l.strips = o;    o += align256(strips * 4);
+  l.total = o;
+  return l;
+}
+
 size_t match_tc_workspace(int bm, int n, int cm) {
   TcParams p;
   tc_geometry(bm, n, cm, p);
-  const size_t rows = (size_t)bm * p.na * p.n_ct;
-  const size_t strips = (size_t)bm * ((p.na + TC_BM - 1) / TC_BM);
-  return align256((size_t)2 * bm * n * cm * sizeof(float)) + align256(rows * 4) + align256(rows * 4) +
-         align256(rows * 4 * KCAND) + align256((size_t)bm * p.na * 8) + align256(strips * 4);
+  return tc_layout(bm, n, p).total;
+}
+
+// Test/diagnostic hook: {n_ct, BN, byte offset of tile_max, byte offset of tile_cnt, fused_refine} so that
+// tests can read the tensor-core pass's pruning record without mirroring the geometry.
+void match_tc_describe(int bm, int n, int cm, long long out[5]) {
+  TcParams p;
+  tc_geometry(bm, n, cm, p);
+  const TcLayout l = tc_layout(bm, n, p);
+  out[0] = p.n_ct; out[1] = p.BN; out[2] = (long long)l.tile_max; out[3] = (long long)l.tile_cnt; out[4] = p.fused_refine;
 }
 
 bool match_tc_supported(int dtype, int bm, int n, int cm, const View& v, const void* metric) {
-  (void)metric; (void)v;
   if (dtype != TOME_F32 && dtype != TOME_BF16) return false;
-  if (cm % 4 != 0 || cm < 4 || cm > 4096) return false;          // TMA: 16-byte row pitch
+  if (cm % 8 != 0 || cm < 8 || cm > 4096) return false;          // TMA: 16-byte row pitch of the bf16 planes
   if (n < 2 || (long long)bm * n * 2 > 0x7fffffffLL) return false;
+  // split_rows reads channel pairs: every row must start on a pair boundary
+  const uintptr_t pair = dtype == TOME_F32 ? 8 : 4;
+  if (((uintptr_t)metric % pair) || (v.sbo & 1) || (v.sbi & 1) || (v.sn & 1)) return false;
   return true;
 }
 
@@ -599,14 +730,14 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int make_map(CUtensorMap* map, float* base, int rows, int cm, int box_rows) {
+static int make_map(CUtensorMap* map, void* base, long long rows, int cm, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error(TOME_ERR_CUDA, "tome_match: cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)cm, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cm * sizeof(float)};
+  cuuint64_t strides[1] = {(cuuint64_t)cm * sizeof(__nv_bfloat16)};
   cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(TOME_ERR_CUDA, "tome_match: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return TOME_OK;
@@ -617,32 +748,37 @@ int launch_match_tc(const void* metric, int dtype, int bm, int n, int cm, const 
                     long long stride_h) {
   if (ws_bytes < match_tc_workspace(bm, n, cm))
     return set_error(TOME_ERR_WORKSPACE, "tome_match: workspace %zu < %zu bytes", ws_bytes, match_tc_workspace(bm, n, cm));
+  if (((uintptr_t)ws & 255) != 0) return set_error(TOME_ERR_ALIGN, "tome_match: workspace must be 256-byte aligned");
+  if (stride_h & 1) return set_error(TOME_ERR_ALIGN, "tome_match_heads: head stride must be even");
   TcParams p;
   tc_geometry(bm, n, cm, p);
+  const TcLayout l = tc_layout(bm, n, p);
   p.cls = cls; p.distill = distill; p.rows_total = bm * n;
   p.node_max = node_max; p.node_idx = node_idx;
   p.trace = getenv("TOME_TC_TRACE") ? (long long*)strtoull(getenv("TOME_TC_TRACE"), nullptr, 0) : nullptr;
   const int n_rt = (p.na + TC_BM - 1) / TC_BM;
   char* w = (char*)ws;
-  float* split = (float*)w;                      w += align256((size_t)2 * bm * n * cm * sizeof(float));
-  const size_t rows = (size_t)bm * p.na * p.n_ct;
-  p.tile_max = (float*)w;                        w += align256(rows * 4);
-  p.tile_cnt = (int*)w;                          w += align256(rows * 4);
-  p.tile_cand = (int*)w;                         w += align256(rows * 4 * KCAND);
-  p.keys = (unsigned long long*)w;               w += align256((size_t)bm * p.na * 8);
-  p.strip_count = (int*)w;
+  __nv_bfloat16* hm = (__nv_bfloat16*)(w + l.hm);
+  float* mhat = (float*)(w + l.mhat);
+  p.mhat = mhat;
+  p.tile_max = (float*)(w + l.tile_max);
+  p.tile_cnt = (int*)(w + l.tile_cnt);
+  p.tile_cand = (int*)(w + l.tile_cand);
+  p.keys = (unsigned long long*)(w + l.keys);
+  p.approx = (unsigned int*)(w + l.approx);
+  p.strip_count = (int*)(w + l.strips);
 
   const int blocks = (int)(((long long)bm * n * 32 + 255) / 256);
   if (dtype == TOME_F32)
-    split_rows_kernel<float><<<blocks, 256, 0, st>>>((const float*)metric, v, heads, stride_h, bm, n, cm, split, p.keys, p.strip_count, bm * n_rt);
+    split_rows_kernel<float><<<blocks, 256, 0, st>>>((const float*)metric, v, heads, stride_h, bm, n, cm, hm, mhat, p.keys, p.approx, p.strip_count, bm * n_rt);
   else
-    split_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)metric, v, heads, stride_h, bm, n, cm, split, p.keys, p.strip_count, bm * n_rt);
+    split_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)metric, v, heads, stride_h, bm, n, cm, hm, mhat, p.keys, p.approx, p.strip_count, bm * n_rt);
   TOME_LAUNCH_CHECK("split_rows_kernel");
 
   alignas(64) CUtensorMap map_a, map_b;
-  int rc = make_map(&map_a, split, 2 * bm * n, cm, TC_BM);
+  int rc = make_map(&map_a, hm, 2LL * bm * n, cm, TC_BM);
   if (rc) return rc;
-  rc = make_map(&map_b, split, 2 * bm * n, cm, p.BN);
+  rc = make_map(&map_b, hm, 2LL * bm * n, cm, p.BN);
   if (rc) return rc;
   const size_t smem = (size_t)p.stages * 2 * (TC_BM + p.BN) * 128 + 16 * p.stages + 16 + 1024;
   static bool smem_set = false;
@@ -653,9 +789,9 @@ int launch_match_tc(const void* metric, int dtype, int bm, int n, int cm, const 
   dim3 grid(p.n_ct, n_rt, bm);
   match_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
   TOME_LAUNCH_CHECK("match_tc_kernel");
-  if (!p.resident) {
+  if (!p.fused_refine) {
     const long long total = (long long)bm * p.na * 32;
-    refine_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(split, p, node_max, node_idx);
+    refine_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p, node_max, node_idx);
     TOME_LAUNCH_CHECK("refine_rows_kernel");
   }
   return TOME_OK;

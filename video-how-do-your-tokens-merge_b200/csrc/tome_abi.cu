@@ -55,6 +55,7 @@ int launch_rowmax(const float*, int, int, int, int, int, float*, int*, cudaStrea
 size_t match_tc_workspace(int bm, int n, int cm);
 bool match_tc_supported(int dtype, int bm, int n, int cm, const View& v, const void* metric);
 int launch_match_tc(const void*, int, int, int, int, const View&, int, int, float*, int*, void*, size_t, cudaStream_t, int, long long);
+void match_tc_describe(int, int, int, long long[5]);
 size_t select_workspace(int bm, int n);
 int launch_select(const tome_plan*, void*, size_t, cudaStream_t);
 int launch_merge(const tome_plan*, const void*, int, int, const View&, const float*, int, float, void*, const View&,
@@ -119,7 +120,7 @@ int tome_match(const void* metric, int32_t dtype, int32_t bm, int32_t n, int32_t
     algo = match_tc_supported(dtype, bm, n, cm, v, metric) ? TOME_MATCH_TCGEN05 : TOME_MATCH_EXACT_SIMT;
   if (algo == TOME_MATCH_TCGEN05) {
     if (!match_tc_supported(dtype, bm, n, cm, v, metric))
-      return set_error(TOME_ERR_UNSUPPORTED, "tome_match: tcgen05 path needs contiguous fp32/bf16 metric, cm %% 32 == 0, cm <= 1024 (got cm=%d)", cm);
+      return set_error(TOME_ERR_UNSUPPORTED, "tome_match: tcgen05 path needs an fp32/bf16 metric with cm %% 8 == 0, cm <= 4096 and even strides (got cm=%d)", cm);
     return launch_match_tc(metric, dtype, bm, n, cm, v, class_token, distill_token, node_max, node_idx, workspace,
                            workspace_bytes, st, 1, 0);
   }
@@ -139,9 +140,60 @@ int tome_match_heads(const void* keys, int32_t dtype, int32_t bm, int32_t heads,
   TOME_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "tome_match_heads: workspace must be 256-byte aligned");
   const View v = make_view(view, n, cm);
   if (!match_tc_supported(dtype, bm, n, cm, v, keys))
-    return set_error(TOME_ERR_UNSUPPORTED, "tome_match_heads: needs cm %% 4 == 0 (got cm=%d); average the heads and call tome_match", cm);
+    return set_error(TOME_ERR_UNSUPPORTED, "tome_match_heads: needs cm %% 8 == 0 and even strides (got cm=%d); average the heads and call tome_match", cm);
   return launch_match_tc(keys, dtype, bm, n, cm, v, class_token, distill_token, node_max, node_idx, workspace,
                          workspace_bytes, (cudaStream_t)stream, heads, stride_h);
+}
+
+static size_t align256_(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t tome_plan_build_workspace_bytes(int32_t bm, int32_t n, int32_t cm) {
+  if (bm <= 0 || n <= 0 || cm <= 0) return 0;
+  return align256_(tome_match_workspace_bytes(bm, n, cm, TOME_MATCH_AUTO)) + align256_(select_workspace(bm, n));
+}
+
+void tome_match_tc_describe(int32_t bm, int32_t n, int32_t cm, int64_t* out5) {
+  long long o[5];
+  match_tc_describe(bm, n, cm, o);
+  for (int i = 0; i < 5; ++i) out5[i] = o[i];
+}
+
+int tome_plan_build(const void* metric, int32_t dtype, int32_t heads, int64_t stride_h, const tome_view* view, int32_t cm,
+                    int32_t algo, const tome_plan* plan, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  rc = check_plan(plan, "tome_plan_build");
+  if (rc) return rc;
+  const int bm = plan->bm, n = plan->n;
+  TOME_CHECK_ARG(metric && workspace && cm > 0 && heads >= 1 && n >= 2, "tome_plan_build: NULL pointer or bad shape (heads=%d n=%d cm=%d)", heads, n, cm);
+  TOME_CHECK_ARG(heads == 1 || view, "tome_plan_build: a head-mean metric needs an explicit view");
+  if (dtype != TOME_F32 && dtype != TOME_BF16) return set_error(TOME_ERR_DTYPE, "tome_plan_build: unsupported dtype %d", dtype);
+  TOME_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "tome_plan_build: workspace must be 256-byte aligned");
+  if (workspace_bytes < tome_plan_build_workspace_bytes(bm, n, cm))
+    return set_error(TOME_ERR_WORKSPACE, "tome_plan_build: workspace %zu < %zu bytes", workspace_bytes, tome_plan_build_workspace_bytes(bm, n, cm));
+  const size_t match_bytes = align256_(tome_match_workspace_bytes(bm, n, cm, TOME_MATCH_AUTO));
+  void* select_ws = (char*)workspace + match_bytes;
+  const size_t select_bytes = workspace_bytes - match_bytes;
+  const View v = make_view(view, n, cm);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* node_max = const_cast<float*>(plan->node_max);
+  int32_t* node_idx = const_cast<int32_t*>(plan->node_idx);
+  const bool tc_ok = match_tc_supported(dtype, bm, n, cm, v, metric);
+  if (algo == TOME_MATCH_AUTO) algo = tc_ok ? TOME_MATCH_TCGEN05 : TOME_MATCH_EXACT_SIMT;
+  if (algo == TOME_MATCH_TCGEN05) {
+    if (!tc_ok)
+      return set_error(TOME_ERR_UNSUPPORTED, "tome_plan_build: tcgen05 path needs cm %% 8 == 0, cm <= 4096 and even strides (got cm=%d)", cm);
+    rc = launch_match_tc(metric, dtype, bm, n, cm, v, plan->class_token, plan->distill_token, node_max, node_idx, workspace,
+                         match_bytes, st, heads, stride_h);
+    if (rc) return rc;
+    return launch_select(plan, select_ws, select_bytes, st);
+  }
+  if (algo != TOME_MATCH_EXACT_SIMT) return set_error(TOME_ERR_ARG, "tome_plan_build: unknown algo %d", algo);
+  if (heads != 1) return set_error(TOME_ERR_UNSUPPORTED, "tome_plan_build: the exact SIMT path takes a materialised metric (heads == 1)");
+  rc = launch_match_exact(metric, dtype, bm, n, cm, v, plan->class_token, plan->distill_token, node_max, node_idx, workspace,
+                          match_bytes, st);
+  if (rc) return rc;
+  return launch_select(plan, select_ws, select_bytes, st);
 }
 
 int tome_rowmax(const float* scores, int32_t bm, int32_t na, int32_t nb, int32_t class_token, int32_t distill_token,

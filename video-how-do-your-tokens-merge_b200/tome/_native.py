@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 TOME_F32, TOME_BF16 = 0, 1
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -27,6 +27,7 @@ _MODES = {"wavg": MODE_WAVG, "sum": MODE_SUM, "mean": MODE_MEAN, "max": MODE_AMA
 
 EXPORTS = (
     "tome_abi_version", "tome_last_error", "tome_launch_count", "tome_device_check", "tome_match_workspace_bytes", "tome_match", "tome_match_heads",
+    "tome_plan_build_workspace_bytes", "tome_plan_build", "tome_match_tc_describe",
     "tome_rowmax", "tome_select_workspace_bytes", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_add_norm", "tome_add_layernorm", "tome_merge_source",
     "tome_attn_key_bias", "tome_unmerge",
 )
@@ -86,6 +87,13 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.tome_merge_norm.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_i32, ctypes.POINTER(TomeViewC), c_vp, c_i32,
                                     c_f32, c_vp, ctypes.POINTER(TomeViewC), c_vp, c_vp, c_vp, c_vp, c_f32, c_vp,
                                     ctypes.POINTER(TomeViewC), c_vp]
+    lib.tome_plan_build_workspace_bytes.restype = ctypes.c_size_t
+    lib.tome_plan_build_workspace_bytes.argtypes = [c_i32, c_i32, c_i32]
+    lib.tome_plan_build.argtypes = [c_vp, c_i32, c_i32, ctypes.c_int64, ctypes.POINTER(TomeViewC), c_i32, c_i32,
+                                    ctypes.POINTER(TomePlanC), c_vp, ctypes.c_size_t, c_vp]
+    lib.tome_plan_build.restype = c_i32
+    lib.tome_match_tc_describe.restype = None
+    lib.tome_match_tc_describe.argtypes = [c_i32, c_i32, c_i32, ctypes.POINTER(ctypes.c_int64)]
     lib.tome_merge_add_norm.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_vp, c_i32, c_i32, ctypes.POINTER(TomeViewC), c_vp,
                                         c_i32, c_f32, c_vp, ctypes.POINTER(TomeViewC), c_vp, c_vp, c_vp, c_vp, c_f32, c_vp,
                                         ctypes.POINTER(TomeViewC), c_vp]
@@ -259,13 +267,9 @@ def match_heads(metric: "HeadMeanMetric", class_token=False, distill_token=False
     k = metric.keys
     _require_cuda(k, "keys")
     bm, n, cm = metric.shape
-    if k.dtype not in (torch.float32, torch.bfloat16) or k.stride(3) != 1 or cm % 4 != 0:
+    if k.stride(3) != 1 or not _tc_friendly(k, cm, (k.stride(0), k.stride(1), k.stride(2))):
         return match(metric.materialize(), class_token, distill_token)
-    f = metric.frames
-    if f == 1:
-        view = TomeViewC(k.stride(0), 0, k.stride(2), 1)
-    else:                                   # batch (b f): b steps by stride(0), f by one token; tokens step by f
-        view = TomeViewC(k.stride(0), k.stride(2), f * k.stride(2), f)
+    view = _heads_view(metric)
     na = (n + 1) // 2
     with torch.cuda.device(k.device):
         node_max = torch.empty(bm, na, dtype=torch.float32, device=k.device)
@@ -276,6 +280,62 @@ def match_heads(metric: "HeadMeanMetric", class_token=False, distill_token=False
                                     k.stride(1), int(bool(class_token)), int(bool(distill_token)),
                                     node_max.data_ptr(), node_idx.data_ptr(), ws.data_ptr(), ws_bytes, _stream(k)), lib)
     return node_max, node_idx
+
+
+def _heads_view(metric: "HeadMeanMetric") -> "TomeViewC":
+    k, f = metric.keys, metric.frames
+    if f == 1:
+        return TomeViewC(k.stride(0), 0, k.stride(2), 1)
+    return TomeViewC(k.stride(0), k.stride(2), f * k.stride(2), f)   # batch (b f): b by stride(0), f by one token
+
+
+def _tc_friendly(t: torch.Tensor, cm: int, strides) -> bool:
+    """What the tensor-core path needs of its input: channel pairs aligned, 16-byte bf16 planes."""
+    pair = 2 * t.element_size()
+    return (t.dtype in (torch.float32, torch.bfloat16) and cm % 8 == 0 and t.data_ptr() % pair == 0
+            and all(int(s) % 2 == 0 for s in strides))
+
+
+def plan_build(metric, r: int, class_token=False, distill_token=False, algo: int = MATCH_AUTO) -> DevicePlan:
+    """Kernels 1 + 2 in one call (``tome_plan_build``): ``metric`` is a (bm, n, cm) tensor or a lazy
+    HeadMeanMetric; ``r`` the effective r (> 0).  Returns the plan with node_max / node_idx filled in."""
+    lib = load_library()
+    heads_mode = isinstance(metric, HeadMeanMetric)
+    if heads_mode:
+        k = metric.keys
+        _require_cuda(k, "keys")
+        bm, n, cm = metric.shape
+        if k.stride(3) != 1 or not _tc_friendly(k, cm, (k.stride(0), k.stride(1), k.stride(2))) or algo == MATCH_EXACT_SIMT:
+            return plan_build(metric.materialize(), r, class_token, distill_token, algo)
+        src, view, heads, stride_h = k, _heads_view(metric), metric.heads, k.stride(1)
+    else:
+        _require_cuda(metric, "metric")
+        if metric.dim() != 3:
+            raise RuntimeError(f"tome_b200: metric must be (batch, tokens, channels); got {tuple(metric.shape)}")
+        if metric.dtype not in (torch.float32, torch.bfloat16):
+            metric = metric.float()
+        if metric.stride(2) != 1:
+            metric = metric.contiguous()
+        bm, n, cm = metric.shape
+        src, view, heads, stride_h = metric, _view_of(metric), 1, 0
+    na = (n + 1) // 2
+    dev = src.device
+    with torch.cuda.device(dev):
+        node_max = torch.empty(bm, na, dtype=torch.float32, device=dev)
+        node_idx = torch.empty(bm, na, dtype=torch.int32, device=dev)
+        plan = DevicePlan(bm, n, r, class_token, distill_token, node_max, node_idx)
+        ws_bytes = lib.tome_plan_build_workspace_bytes(bm, n, cm)
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        _check(lib.tome_plan_build(src.data_ptr(), _dtype_code(src), heads, stride_h, ctypes.byref(view), cm, algo,
+                                   plan.c_ptr(), ws.data_ptr(), ws_bytes, _stream(src)), lib)
+    return plan
+
+
+def match_tc_describe(bm: int, n: int, cm: int):
+    """(column tiles, BN, byte offset of tile_max, byte offset of tile_cnt, fused refine?) -- tests only."""
+    out = (ctypes.c_int64 * 5)()
+    load_library().tome_match_tc_describe(bm, n, cm, out)
+    return tuple(int(v) for v in out)
 
 
 def rowmax(scores: torch.Tensor, class_token=False, distill_token=False) -> Tuple[torch.Tensor, torch.Tensor]:

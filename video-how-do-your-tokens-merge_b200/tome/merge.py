@@ -87,11 +87,8 @@ def _make_plan(metric, r, class_token, distill_token, random_scores: bool) -> "_
             len_a, len_b = (length + 1) // 2, length // 2
             scores = torch.rand(size=(metric.size(0), len_a, len_b), device=metric.device)
             node_max, node_idx = _native.rowmax(scores, class_token, distill_token)
-        elif isinstance(metric, _native.HeadMeanMetric):
-            node_max, node_idx = _native.match_heads(metric, class_token, distill_token)
-        else:
-            node_max, node_idx = _native.match(metric, class_token, distill_token)
-        return _native.select(node_max, node_idx, metric.shape[1], r, class_token, distill_token)
+            return _native.select(node_max, node_idx, metric.shape[1], r, class_token, distill_token)
+        return _native.plan_build(metric, r, class_token, distill_token)        # kernels 1 + 2, one ABI call
 
 
 class _PlanCallable:
