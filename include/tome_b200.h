@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 10
+#define TOME_ABI_VERSION 11
 
 #if defined(__GNUC__)
 #define TOME_API __attribute__((visibility("default")))
@@ -204,6 +204,11 @@ TOME_API int tome_merge_source(const tome_plan* plan, const float* source, int32
 TOME_API int tome_add_layernorm(const void* a, const void* b, int32_t dtype, int64_t rows, int32_t c,
                        const void* ln_weight, const void* ln_bias, float ln_eps, void* sum_out,
                        void* normed_out, void* stream);
+/* Same with `b` broadcast over the batch: b has b_rows rows and row i of `a` takes b[i % b_rows] -- the
+ * position-embedding add in front of the first block (videomae builder:276-278). */
+TOME_API int tome_add_rows_layernorm(const void* a, const void* b, int64_t b_rows, int32_t dtype, int64_t rows, int32_t c,
+                            const void* ln_weight, const void* ln_bias, float ln_eps, void* sum_out,
+                            void* normed_out, void* stream);
 
 /* Caller-side piece of proportional attention (tome/patch/videomae.py:62-63,
  * vivit.py:103-104, timesformer.py:72-74: attn + log(size) of the key token).  q and k heads carry spare
@@ -216,6 +221,14 @@ TOME_API int tome_attn_key_bias(const float* log_size, int32_t b, int32_t n, int
                        float scale, int32_t dtype, void* k, int64_t k_stride_b, int64_t k_stride_n,
                        int64_t k_stride_h, void* q, int64_t q_stride_b, int64_t q_stride_n, int64_t q_stride_h,
                        void* stream);
+
+/* Caller-side data format: the tubelet embedding of the four models is a Conv3d whose
+ * kernel equals its stride (slowfast/models/videomae_video_model_builder.py:138-160), i.e. a GEMM over
+ * non-overlapping tubelets.  x (b, c, t, h, w) contiguous -> out (b, (t/tt)(h/ph)(w/pw), c*tt*ph*pw), token
+ * order (t', h', w'), feature order (c, tt, ph, pw) = the flattened conv weight's; in_dtype -> out_dtype
+ * conversion (fp32 clips to a bf16 model) happens in the same pass.  pw % 8 == 0. */
+TOME_API int tome_patchify(const void* x, int32_t in_dtype, int32_t b, int32_t c, int32_t t, int32_t h, int32_t w,
+                  int32_t tt, int32_t ph, int32_t pw, void* out, int32_t out_dtype, void* stream);
 
 /* unmerge (merge.py:87-100): x (bm, n - r, c) -> out (bm, n, c); contiguous tensors. */
 TOME_API int tome_unmerge(const tome_plan* plan, const void* x, int32_t dtype, int32_t c, void* out,

@@ -466,3 +466,33 @@ def test_plan_build_bit_exact_vs_oracle(native, case, path, monkeypatch):
     ref = native.select(_dev(plan.node_max), _dev(plan.node_idx), case["n"], plan.r, cls, dis)
     for name in ("a_map", "b_off", "b_src", "b_head"):
         assert torch.equal(getattr(dp, name), getattr(ref, name)), name
+
+
+@pytest.mark.parametrize("dtypes", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16)])
+def test_patchify_equals_permute_and_conv(native, dtypes):
+    """tome_patchify: the tubelet rows equal torch's reshape/permute (bit for bit, cast included), and the
+    GEMM over them equals the Conv3d the reference runs (videomae builder:138-160)."""
+    din, dout = dtypes
+    gen = torch.Generator(device="cuda").manual_seed(6)
+    B, C, T, H, W, tt, ph, pw = 2, 3, 4, 32, 48, 2, 16, 16
+    x = torch.rand(B, C, T, H, W, device="cuda", generator=gen).to(din)
+    got = native.patchify(x, tt, ph, pw, dout)
+    want = x.reshape(B, C, T // tt, tt, H // ph, ph, W // pw, pw).permute(0, 2, 4, 6, 1, 3, 5, 7)
+    want = want.reshape(B, (T // tt) * (H // ph) * (W // pw), C * tt * ph * pw).to(dout)
+    assert torch.equal(got, want)
+    if din == dout == torch.float32:
+        conv = torch.nn.Conv3d(C, 8, (tt, ph, pw), (tt, ph, pw)).cuda()
+        ref = conv(x).flatten(2).transpose(1, 2)
+        out = torch.nn.functional.linear(got, conv.weight.reshape(8, -1), conv.bias)
+        torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_add_layernorm_broadcasts_the_position_embedding(native):
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    a = torch.randn(4, 50, 768, device="cuda", generator=gen).to(torch.bfloat16)
+    pos = torch.randn(1, 50, 768, device="cuda", generator=gen).to(torch.bfloat16)
+    w = torch.ones(768, device="cuda", dtype=torch.bfloat16)
+    s, y = native.add_layernorm(a, pos, (w, None, 1e-6))
+    assert torch.equal(s, a + pos)
+    want = torch.nn.functional.layer_norm((a + pos).float(), (768,), w.float(), None, 1e-6)
+    torch.testing.assert_close(y.float(), want, rtol=1.6e-2, atol=1.6e-2)

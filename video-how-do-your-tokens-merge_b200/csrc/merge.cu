@@ -636,16 +636,17 @@ int launch_merge(const tome_plan* plan, const void* x, int dtype, int c, const V
 // at the bench shape); here one warp per row adds, writes the sum, and normalises it while it is
 // still in registers.
 template <typename T, int NV>
-__global__ void __launch_bounds__(256) add_layernorm_kernel(const T* __restrict__ a, const T* __restrict__ b2, long long rows,
-                                                           int c, const T* __restrict__ w, const T* __restrict__ bias, float eps,
-                                                           T* __restrict__ sum_out, T* __restrict__ normed) {
+__global__ void __launch_bounds__(256) add_layernorm_kernel(const T* __restrict__ a, const T* __restrict__ b2, long long b_rows,
+                                                           long long rows, int c, const T* __restrict__ w,
+                                                           const T* __restrict__ bias, float eps, T* __restrict__ sum_out,
+                                                           T* __restrict__ normed) {
   constexpr int E = Pack<T>::E;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int nvec = c / E;
   const uint4* ar = reinterpret_cast<const uint4*>(a + row * c);
-  const uint4* br = reinterpret_cast<const uint4*>(b2 + row * c);
+  const uint4* br = reinterpret_cast<const uint4*>(b2 + (row % b_rows) * c);
   uint4 va[NV], vb[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) { const int i = v * 32 + lane; if (i < nvec) { va[v] = ld_stream_u4(ar + i); vb[v] = ld_stream_u4(br + i); } }
@@ -699,12 +700,12 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const T* __restrict_
 }
 
 template <typename T>
-static int launch_add_ln_t(const void* a, const void* b, long long rows, int c, const void* w, const void* bias, float eps,
-                           void* sum_out, void* normed, cudaStream_t st) {
+static int launch_add_ln_t(const void* a, const void* b, long long b_rows, long long rows, int c, const void* w, const void* bias,
+                           float eps, void* sum_out, void* normed, cudaStream_t st) {
   constexpr int E = Pack<T>::E;
   const int nv = (c / E + 31) / 32;
   const unsigned grid = (unsigned)((rows + 7) / 8);
-#define TOME_ADDLN(NV_) add_layernorm_kernel<T, NV_><<<grid, 256, 0, st>>>((const T*)a, (const T*)b, rows, c, (const T*)w, (const T*)bias, eps, (T*)sum_out, (T*)normed)
+#define TOME_ADDLN(NV_) add_layernorm_kernel<T, NV_><<<grid, 256, 0, st>>>((const T*)a, (const T*)b, b_rows, rows, c, (const T*)w, (const T*)bias, eps, (T*)sum_out, (T*)normed)
   if (nv <= 1) TOME_ADDLN(1); else if (nv <= 2) TOME_ADDLN(2); else if (nv <= 3) TOME_ADDLN(3); else if (nv <= 4) TOME_ADDLN(4);
   else if (nv <= 6) TOME_ADDLN(6); else if (nv <= 8) TOME_ADDLN(8);
   else return set_error(TOME_ERR_UNSUPPORTED, "tome_add_layernorm: c=%d too wide", c);
@@ -713,13 +714,13 @@ static int launch_add_ln_t(const void* a, const void* b, long long rows, int c, 
   return TOME_OK;
 }
 
-int launch_add_layernorm(const void* a, const void* b, int dtype, long long rows, int c, const void* w, const void* bias,
-                         float eps, void* sum_out, void* normed, cudaStream_t st) {
+int launch_add_layernorm(const void* a, const void* b, long long b_rows, int dtype, long long rows, int c, const void* w,
+                         const void* bias, float eps, void* sum_out, void* normed, cudaStream_t st) {
   const int e = dtype == TOME_F32 ? 4 : 8;
   if (c % e != 0 || !aligned16(a) || !aligned16(b) || !aligned16(w) || (bias && !aligned16(bias)) || !aligned16(sum_out) || !aligned16(normed))
     return set_error(TOME_ERR_ALIGN, "tome_add_layernorm: needs 16-byte aligned buffers and c %% %d == 0", e);
-  if (dtype == TOME_F32) return launch_add_ln_t<float>(a, b, rows, c, w, bias, eps, sum_out, normed, st);
-  if (dtype == TOME_BF16) return launch_add_ln_t<__nv_bfloat16>(a, b, rows, c, w, bias, eps, sum_out, normed, st);
+  if (dtype == TOME_F32) return launch_add_ln_t<float>(a, b, b_rows, rows, c, w, bias, eps, sum_out, normed, st);
+  if (dtype == TOME_BF16) return launch_add_ln_t<__nv_bfloat16>(a, b, b_rows, rows, c, w, bias, eps, sum_out, normed, st);
   return set_error(TOME_ERR_DTYPE, "tome_add_layernorm: unsupported dtype %d", dtype);
 }
 

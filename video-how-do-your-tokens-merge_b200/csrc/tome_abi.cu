@@ -62,7 +62,8 @@ int launch_merge(const tome_plan*, const void*, int, int, const View&, const flo
                  float*, float*, cudaStream_t, const void*, const void*, float, void*, const View*, const void*);
 int launch_merge_source(const tome_plan*, const float*, int, float, float*, cudaStream_t);
 int launch_unmerge(const tome_plan*, const void*, int, int, void*, cudaStream_t);
-int launch_add_layernorm(const void*, const void*, int, long long, int, const void*, const void*, float, void*, void*, cudaStream_t);
+int launch_add_layernorm(const void*, const void*, long long, int, long long, int, const void*, const void*, float, void*, void*, cudaStream_t);
+int launch_patchify(const void*, int, int, int, int, int, int, int, int, int, void*, int, cudaStream_t);
 int launch_key_bias(const float*, int, int, int, int, int, float, int, void*, long long, long long, long long, void*, long long,
                     long long, long long, cudaStream_t);
 
@@ -275,10 +276,25 @@ int tome_merge_source(const tome_plan* plan, const float* source, int32_t n0, fl
 
 int tome_add_layernorm(const void* a, const void* b, int32_t dtype, int64_t rows, int32_t c, const void* ln_weight,
                        const void* ln_bias, float ln_eps, void* sum_out, void* normed_out, void* stream) {
+  return tome_add_rows_layernorm(a, b, rows, dtype, rows, c, ln_weight, ln_bias, ln_eps, sum_out, normed_out, stream);
+}
+
+int tome_add_rows_layernorm(const void* a, const void* b, int64_t b_rows, int32_t dtype, int64_t rows, int32_t c,
+                            const void* ln_weight, const void* ln_bias, float ln_eps, void* sum_out, void* normed_out,
+                            void* stream) {
   int rc = ensure_device_ok();
   if (rc) return rc;
-  TOME_CHECK_ARG(a && b && ln_weight && sum_out && normed_out && rows > 0 && c > 0, "tome_add_layernorm: NULL pointer or empty shape");
-  return launch_add_layernorm(a, b, dtype, rows, c, ln_weight, ln_bias, ln_eps, sum_out, normed_out, (cudaStream_t)stream);
+  TOME_CHECK_ARG(a && b && ln_weight && sum_out && normed_out && rows > 0 && c > 0 && b_rows > 0 && b_rows <= rows,
+                 "tome_add_layernorm: NULL pointer or empty shape");
+  return launch_add_layernorm(a, b, b_rows, dtype, rows, c, ln_weight, ln_bias, ln_eps, sum_out, normed_out, (cudaStream_t)stream);
+}
+
+int tome_patchify(const void* x, int32_t in_dtype, int32_t b, int32_t c, int32_t t, int32_t h, int32_t w, int32_t tt, int32_t ph,
+                  int32_t pw, void* out, int32_t out_dtype, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(x && out && b > 0 && c > 0 && t > 0 && h > 0 && w > 0 && tt > 0 && ph > 0 && pw > 0, "tome_patchify: NULL pointer or empty shape");
+  return launch_patchify(x, in_dtype, b, c, t, h, w, tt, ph, pw, out, out_dtype, (cudaStream_t)stream);
 }
 
 int tome_attn_key_bias(const float* log_size, int32_t b, int32_t n, int32_t lead, int32_t heads, int32_t d, float scale,

@@ -100,8 +100,16 @@ class PatchEmbed(nn.Module):                            # builder:138-160
         # kernel == stride, so the tubelet conv is one GEMM over non-overlapping patches: cuDNN's
         # implicit-GEMM Conv3d ran as an fp32 SIMT kernel (22% of the forward, profiles/r01_launches_v1).
         tt, (ph, pw) = self.tubelet_size, self.patch_size
-        x = x.reshape(B, C, T // tt, tt, H // ph, ph, W // pw, pw).permute(0, 2, 4, 6, 1, 3, 5, 7)
-        x = x.reshape(B, (T // tt) * (H // ph) * (W // pw), C * tt * ph * pw)
+        wdt = self.proj.weight.dtype
+        if (not torch.is_grad_enabled() and pw % 8 == 0 and x.dtype in (torch.float32, torch.bfloat16)
+                and wdt in (torch.float32, torch.bfloat16)):
+            # one coalesced pass (tome_patchify, cast to the weight dtype included) instead of torch's generic
+            # 8-d strided copy, which ran at a sixth of HBM speed (profiles/r01b)
+            from tome import _native
+            x = _native.patchify(x, tt, ph, pw, wdt)
+        else:
+            x = x.reshape(B, C, T // tt, tt, H // ph, ph, W // pw, pw).permute(0, 2, 4, 6, 1, 3, 5, 7)
+            x = x.reshape(B, (T // tt) * (H // ph) * (W // pw), C * tt * ph * pw)
         return F.linear(x, self.proj.weight.reshape(self.proj.out_channels, -1), self.proj.bias)
 
 
@@ -168,8 +176,23 @@ class VisionTransformer(nn.Module):                     # builder:177-305
         x = x[0]                                        # builder:273 -- input is a list of pathways
         x = self.patch_embed(x)
         if self.pos_embed is not None:
-            x = x + self.pos_embed.to(dtype=x.dtype, device=x.device)
-        x = self.pos_drop(x)
+            pos = self.pos_embed.to(dtype=x.dtype, device=x.device)
+            info = getattr(self.blocks[0], "_tome_info", None) if len(self.blocks) else None
+            fused = None
+            if info is not None and not self.training and isinstance(self.pos_drop, nn.Dropout):
+                # ToMe-patched CUDA inference: the position-embedding add and the first block's norm1 in one
+                # pass (tome_add_rows_layernorm); the block picks the normalised tokens up from _tome_info
+                from tome.patch.videomae import fusable_norm
+                fn = fusable_norm(self.blocks[0].norm1, x)
+                if fn is not None and pos.shape[1:] == x.shape[1:]:
+                    from tome import _native
+                    x, normed = _native.add_layernorm(x, pos, fn)
+                    info["normed1"] = (x, self.blocks[0].norm1, normed)
+                    fused = True
+            if fused is None:
+                x = x + pos
+        if self.training:                               # identity in eval (and keeps x the tensor norm1 was taken of)
+            x = self.pos_drop(x)
         for blk in self.blocks:
             x = blk(x)
         x = self.norm(x)

@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 TOME_F32, TOME_BF16 = 0, 1
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -28,8 +28,8 @@ _MODES = {"wavg": MODE_WAVG, "sum": MODE_SUM, "mean": MODE_MEAN, "max": MODE_AMA
 EXPORTS = (
     "tome_abi_version", "tome_last_error", "tome_launch_count", "tome_device_check", "tome_match_workspace_bytes", "tome_match", "tome_match_heads",
     "tome_plan_build_workspace_bytes", "tome_plan_build", "tome_match_tc_describe",
-    "tome_rowmax", "tome_select_workspace_bytes", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_add_norm", "tome_add_layernorm", "tome_merge_source",
-    "tome_attn_key_bias", "tome_unmerge",
+    "tome_rowmax", "tome_select_workspace_bytes", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_add_norm", "tome_add_layernorm", "tome_add_rows_layernorm",
+    "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_unmerge",
 )
 
 
@@ -98,13 +98,16 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
                                         c_i32, c_f32, c_vp, ctypes.POINTER(TomeViewC), c_vp, c_vp, c_vp, c_vp, c_f32, c_vp,
                                         ctypes.POINTER(TomeViewC), c_vp]
     lib.tome_add_layernorm.argtypes = [c_vp, c_vp, c_i32, ctypes.c_int64, c_i32, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp]
+    lib.tome_add_rows_layernorm.argtypes = [c_vp, c_vp, ctypes.c_int64, c_i32, ctypes.c_int64, c_i32, c_vp, c_vp, c_f32, c_vp,
+                                            c_vp, c_vp]
+    lib.tome_patchify.argtypes = [c_vp, c_i32] + [c_i32] * 8 + [c_vp, c_i32, c_vp]
     lib.tome_merge_source.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_f32, c_vp, c_vp]
     c_i64 = ctypes.c_int64
     lib.tome_attn_key_bias.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_i32, c_vp, c_i64, c_i64, c_i64,
                                        c_vp, c_i64, c_i64, c_i64, c_vp]
     lib.tome_unmerge.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_i32, c_vp, c_vp]
-    for name in ("tome_device_check", "tome_match", "tome_match_heads", "tome_rowmax", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_add_norm", "tome_add_layernorm", "tome_merge_source",
-                 "tome_attn_key_bias", "tome_unmerge"):
+    for name in ("tome_device_check", "tome_match", "tome_match_heads", "tome_rowmax", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_add_norm", "tome_add_layernorm", "tome_add_rows_layernorm",
+                 "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_unmerge"):
         getattr(lib, name).restype = c_i32
     if lib.tome_abi_version() != ABI_VERSION:
         raise RuntimeError(f"tome_b200: ABI version {lib.tome_abi_version()} != expected {ABI_VERSION}; rebuild")
@@ -489,20 +492,40 @@ def merge_frames(plan: DevicePlan, x: torch.Tensor, frames: int, mode: str, size
 
 
 def add_layernorm(a: torch.Tensor, b: torch.Tensor, norm):
-    """(a + b, LayerNorm(a + b)) in one pass; ``norm=(weight, bias, eps)``.  a, b contiguous, same shape."""
+    """(a + b, LayerNorm(a + b)) in one pass; ``norm=(weight, bias, eps)``.  b has a's shape, or a's shape
+    without (or with a unit) batch axis, in which case it is broadcast over the batch (position embedding)."""
     lib = load_library()
     _require_cuda(a, "a")
-    if a.shape != b.shape or a.dtype != b.dtype:
-        raise RuntimeError("tome_b200: add_layernorm needs two tensors of the same shape and dtype")
-    a, b = a.contiguous(), b.contiguous()
     c = a.shape[-1]
+    if b.dim() == a.dim() and b.shape[0] == 1 and a.shape[0] != 1:
+        b = b[0]
+    if a.dtype != b.dtype or b.device != a.device or (b.shape != a.shape and tuple(b.shape) != tuple(a.shape[1:])):
+        raise RuntimeError("tome_b200: add_layernorm needs b of a's shape, or of a's shape without the batch axis, same dtype")
+    a, b = a.contiguous(), b.contiguous()
     wp, bp, eps = _norm_args(norm, a)
     with torch.cuda.device(a.device):
         s = torch.empty_like(a)
         y = torch.empty_like(a)
-        _check(lib.tome_add_layernorm(a.data_ptr(), b.data_ptr(), _dtype_code(a), a.numel() // c, c, wp, bp, eps,
-                                      s.data_ptr(), y.data_ptr(), _stream(a)), lib)
+        _check(lib.tome_add_rows_layernorm(a.data_ptr(), b.data_ptr(), b.numel() // c, _dtype_code(a), a.numel() // c, c,
+                                           wp, bp, eps, s.data_ptr(), y.data_ptr(), _stream(a)), lib)
     return s, y
+
+
+def patchify(x: torch.Tensor, tubelet: int, ph: int, pw: int, out_dtype: torch.dtype) -> torch.Tensor:
+    """(B, C, T, H, W) clip -> (B, tokens, C * tubelet * ph * pw) tubelet rows in ``out_dtype`` (one pass, cast
+    included): the operand of the tubelet-embedding GEMM."""
+    lib = load_library()
+    _require_cuda(x, "x")
+    codes = {torch.float32: TOME_F32, torch.bfloat16: TOME_BF16}
+    if x.dtype not in codes or out_dtype not in codes or x.dim() != 5:
+        raise RuntimeError("tome_b200: patchify takes a 5-d fp32/bf16 clip")
+    x = x.contiguous()
+    B, C, T, H, W = x.shape
+    with torch.cuda.device(x.device):
+        out = torch.empty(B, (T // tubelet) * (H // ph) * (W // pw), C * tubelet * ph * pw, dtype=out_dtype, device=x.device)
+        _check(lib.tome_patchify(x.data_ptr(), codes[x.dtype], B, C, T, H, W, tubelet, ph, pw, out.data_ptr(),
+                                 codes[out_dtype], _stream(x)), lib)
+    return out
 
 
 def attn_key_bias(log_size: torch.Tensor, k: torch.Tensor, q: Optional[torch.Tensor], d: int, scale: float, lead: int = 0):
