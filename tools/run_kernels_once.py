@@ -1,5 +1,7 @@
 #!/usr/bin/env python3
-"""Run each hot-path kernel a few times at the bench's layer-0 shape (for ncu captures)."""
+"""Run each hot-path kernel a few times at the bench's layer-0 shape, the way the patched block calls them
+(for ncu captures): tome_plan_build on the lazy head-mean of K, then the merge with the residual add
+and the LayerNorm fused in; plus the plain merge_wavg the roofline line is quoted on."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "video-how-do-your-tokens-merge_b200")]
@@ -8,13 +10,16 @@ from tome import _native
 
 dt = torch.bfloat16 if (len(sys.argv) < 2 or sys.argv[1] == "bf16") else torch.float32
 bm = 8 if dt == torch.bfloat16 else 4
-n, c, cm, r = 1568, 768, 64, 100
+n, c, cm, r, heads = 1568, 768, 64, 100, 12
 g = torch.Generator(device="cuda").manual_seed(0)
 xs = [torch.randn(bm, n, c, device="cuda", dtype=dt, generator=g) for _ in range(12)]
-ms = [torch.randn(bm, n, cm, device="cuda", dtype=dt, generator=g) for _ in range(4)]
+rs = [torch.randn(bm, n, c, device="cuda", dtype=dt, generator=g) for _ in range(12)]
+ks = [torch.randn(bm, n, 3, heads, cm, device="cuda", dtype=dt, generator=g).permute(2, 0, 3, 1, 4)[1] for _ in range(4)]
+w = torch.ones(c, device="cuda", dtype=dt)
+b = torch.zeros(c, device="cuda", dtype=dt)
 for i in range(6):
-    nm, ni = _native.match(ms[i % 4])
-    plan = _native.select(nm, ni, n, r)
+    plan = _native.plan_build(_native.HeadMeanMetric(ks[i % 4]), r)
     out = _native.merge(plan, xs[i], "wavg", want_size=True)
+    out2 = _native.merge(plan, xs[i + 6], "wavg", want_size=True, norm=(w, b, 1e-6), residual=rs[i])
 torch.cuda.synchronize()
 print("ok")
