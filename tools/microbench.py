@@ -81,6 +81,8 @@ def main():
     out["merge_wavg_add_norm_cold"] = dict(us=med, us_best=best)
     med, best = graph_time([lambda i=i: _native.merge(plan, xs[i] + rs[i], "wavg", size=size, want_size=True, norm=(w, bb, 1e-6)) for i in range(nrot)])
     out["torch_add_then_merge_wavg_norm_cold"] = dict(us=med, us_best=best)
+    med, best = graph_time([lambda i=i: _native.add_layernorm(xs[i], rs[i], (w, bb, 1e-6)) for i in range(nrot)])
+    out["add_layernorm_cold"] = dict(us=med, us_best=best, GBps=3 * bm * n * c * e / med / 1e3)
     flops = 2.0 * bm * na * (n // 2) * cm
     for algo, name in ((2, "match_tc"), (1, "match_exact")):
         med, best = graph_time([lambda i=i: _native.match(ms[i % nrot], bool(a.cls), algo=algo) for i in range(8)])

@@ -623,13 +623,12 @@ int launch_merge(const tome_plan* plan, const void* x, int dtype, int c, const V
     if (normed && (c > 8 * 32 * 8 || !aligned16(ln_w) || (ln_b && !aligned16(ln_b)) || !aligned16(normed) || !view_vec_ok(a.nv, 8)))
       return set_error(TOME_ERR_UNSUPPORTED, "tome_merge_norm: c=%d too wide or LayerNorm buffers misaligned", c);
     if (!vec) return launch_merge_scalar<__nv_bfloat16>(a, st);
-    if (variant == 1) return launch_merge_gather<__nv_bfloat16, 4, 8>(a, st);
+    if (variant == 1) return launch_merge_gather<__nv_bfloat16, 8, 4>(a, st);     // the first shipped shape: 256-thread CTAs
     if (variant == 2) return launch_merge_gather<__nv_bfloat16, 8, 3>(a, st);
-    if (variant == 3) return launch_merge_gather<__nv_bfloat16, 8, 5>(a, st);
-    if (variant == 4) return launch_merge_gather<__nv_bfloat16, 8, 2>(a, st);
-    // two input rows per output row: 64 registers spill (20.6 us at the bench shape), 85 do not (17.2 us)
-    if (residual && variant == 0) return launch_merge_gather<__nv_bfloat16, 8, 3>(a, st);
-    return launch_merge_gather<__nv_bfloat16, 8, 4>(a, st);
+    // 64-thread CTAs at <= 85 registers: a CTA retires with its slowest warp, so small CTAs keep the copy warps
+    // from queueing behind the few reducing ones, and the two-input (residual) rows do not spill.
+    // merge 7.6 -> 7.3 us, + LayerNorm 12.5 -> 11.7, + residual 20.6 -> 15.6 (profiles/r01_merge_notes.md)
+    return launch_merge_gather<__nv_bfloat16, 2, 12>(a, st);
   }
   return set_error(TOME_ERR_DTYPE, "tome_merge: unsupported dtype %d", dtype);
 }
@@ -708,8 +707,10 @@ static int launch_add_ln_t(const void* a, const void* b, long long b_rows, long 
                            float eps, void* sum_out, void* normed, cudaStream_t st) {
   constexpr int E = Pack<T>::E;
   const int nv = (c / E + 31) / 32;
-  const unsigned grid = (unsigned)((rows + 7) / 8);
-#define TOME_ADDLN(NV_) add_layernorm_kernel<T, NV_><<<grid, 256, 0, st>>>((const T*)a, (const T*)b, b_rows, rows, c, (const T*)w, (const T*)bias, eps, (T*)sum_out, (T*)normed)
+  static const int threads = getenv("TOME_ADDLN_THREADS") ? atoi(getenv("TOME_ADDLN_THREADS")) : 64;   // tuning knob; 256: 13.4 us, 64: 12.5 us
+  const int rows_per_cta = threads / 32;
+  const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
+#define TOME_ADDLN(NV_) add_layernorm_kernel<T, NV_><<<grid, threads, 0, st>>>((const T*)a, (const T*)b, b_rows, rows, c, (const T*)w, (const T*)bias, eps, (T*)sum_out, (T*)normed)
   if (nv <= 1) TOME_ADDLN(1); else if (nv <= 2) TOME_ADDLN(2); else if (nv <= 3) TOME_ADDLN(3); else if (nv <= 4) TOME_ADDLN(4);
   else if (nv <= 6) TOME_ADDLN(6); else if (nv <= 8) TOME_ADDLN(8);
   else return set_error(TOME_ERR_UNSUPPORTED, "tome_add_layernorm: c=%d too wide", c);
