@@ -278,17 +278,28 @@ def micro_kernels(args, device, dtype):
     res = {}
     nm, ni = _native.match(ms[0], algo=args.match_algo)
     plan = _native.select(nm, ni, n, r)
-    mean_us, med_us = graph_time([lambda i=i: _native.merge(plan, xs[i], "wavg", want_size=True) for i in range(nrot)])
     na = (n + 1) // 2
-    alg_bytes = bm * (n * c * e + (n - r) * c * e + (n - r) * 8 + na * 12)
+    # The merge as the patched block runs it (tome/patch/videomae.py): the block's `x + attn` on the way in,
+    # merge_wavg + sizes + log sizes, and the block's norm2 on the way out -- ONE launch of merge_gather_kernel.
+    rs = [torch.randn(bm, n, c, device=device, dtype=dtype, generator=g) for _ in range(nrot)]
+    lw = torch.ones(c, device=device, dtype=dtype)
+    lb = torch.zeros(c, device=device, dtype=dtype)
+    mean_us, med_us = graph_time([lambda i=i: _native.merge(plan, xs[i], "wavg", want_size=True, norm=(lw, lb, 1e-6),
+                                                            residual=rs[i]) for i in range(nrot)])
+    alg_bytes = bm * (2 * n * c * e + 2 * (n - r) * c * e + (n - r) * 8 + na * 12)
     achieved = alg_bytes / (mean_us * 1e-6) / 1e9
-    roofline = {"kernel": "merge_gather_kernel (merge_wavg + size + log size, layer-0 shape "
-                          f"Bm={bm} N={n} C={c} r={r} {args.dtype})",
+    roofline = {"kernel": "merge_gather_kernel<LN, RES> (residual add + merge_wavg + size + log size + LayerNorm, as the "
+                          f"patched block launches it; layer-0 shape Bm={bm} N={n} C={c} r={r} {args.dtype})",
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": MERGE_DRAM_TRAFFIC_NCU.get((bm, args.dtype)), "algorithmic_bytes": alg_bytes,
                 "us_mean": mean_us, "us_median": med_us, "peak_source": peak_src,
-                "timing": f"{nrot} launches over rotating inputs ({nrot * bm * n * c * e >> 20} MiB > L2) captured in "
+                "timing": f"{nrot} launches over rotating inputs (2 x {nrot * bm * n * c * e >> 20} MiB > L2) captured in "
                           "one CUDA graph, cuda events around the replay, / launches"}
+    p_mean, p_med = graph_time([lambda i=i: _native.merge(plan, xs[i], "wavg", want_size=True) for i in range(nrot)])
+    p_bytes = bm * (n * c * e + (n - r) * c * e + (n - r) * 8 + na * 12)
+    res["merge_wavg_plain"] = {"us_mean": p_mean, "us_median": p_med, "algorithmic_bytes": p_bytes,
+                               "GBps": p_bytes / (p_mean * 1e-6) / 1e9, "frac": p_bytes / (p_mean * 1e-6) / 1e9 / hbm_peak,
+                               "kernels": "merge_gather_kernel (merge_wavg + size + log size only: tome.merge.merge_wavg)"}
     m_mean, m_med = graph_time([lambda i=i: _native.match(ms[i % nrot], algo=args.match_algo) for i in range(8)])
     flops = 2.0 * bm * na * (n // 2) * cm
     res["match"] = {"us_mean": m_mean, "us_median": m_med, "algorithmic_gflop": flops / 1e9,
@@ -305,9 +316,10 @@ def micro_kernels(args, device, dtype):
     return roofline, res
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of merge_gather_kernel from the committed
-# `ncu --set full` capture (profiles/r01_merge_gather_ncu.txt); writes stay in L2 at this size.
-MERGE_DRAM_TRAFFIC_NCU = {(8, "bf16"): 19434752}   # 19.43 MB read + 0 B written back (18 MB of writes stay in the 126 MB L2)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of merge_gather_kernel<LN, RES> from the committed
+# `ncu --set full` capture (profiles/r01c_hotpath_ncu.txt): 43.58 MB read (x + residual; the rest of the 74.8
+# algorithmic MB are writes) + 2.81 MB written back -- most of the 36 MB of output stays in the 126 MB L2.
+MERGE_DRAM_TRAFFIC_NCU = {(8, "bf16"): 43581184 + 2807040}
 
 
 def run_ours(args):
