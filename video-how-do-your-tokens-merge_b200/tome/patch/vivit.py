@@ -17,7 +17,7 @@ import torch.nn.functional as F
 from tome.merge import (Merge, bipartite_soft_matching, bipartite_soft_matching_drop,
                         bipartite_soft_matching_hybrid, merge_source, merge_wavg)
 from tome import attention as prop_attention
-from tome.patch.videomae import _normed_or, _swap, _wavg, lazy_head_mean
+from tome.patch.videomae import _fusable_residual, _normed_or, _swap, _wavg, lazy_head_mean
 from tome.utils import parse_r
 
 
@@ -30,8 +30,9 @@ class ToMeVivitLayerMixin:
         attn_bias = info.get("log_size") if info["prop_attn"] else None
         attention_output, metric = self.attention(self.layernorm_before(hidden_states), attn_size,
                                                   info["head_aggregation"], attn_bias)
-        hidden_states = attention_output + hidden_states                       # first residual
-        hidden_states = self.reduction_function(metric, hidden_states, info, norm=self.layernorm_after)
+        # first residual (attention_output + hidden_states), taken inside the merge kernel when it can be
+        hidden_states = self.reduction_function(metric, hidden_states, info, norm=self.layernorm_after,
+                                                residual=attention_output)
         layer_output = self.output(self.intermediate(_normed_or(self.layernorm_after, hidden_states, info)), hidden_states)
         return (layer_output,) if self._tome_tuple_api else layer_output
 
@@ -96,28 +97,34 @@ class ToMeVivitSelfAttentionMixin:
         return ctx, metric
 
 
-def vivit_merge(metric, x, _tome_info, norm=None):
+def vivit_merge(metric, x, _tome_info, norm=None, residual=None):
     """vivit.py:133-153."""
     _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
     if r > 0:
         merge, _ = bipartite_soft_matching(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
                                            _tome_info["mode"])
+        if residual is not None and not (isinstance(merge, Merge) and _fusable_residual(x, residual)):
+            x, residual = residual + x, None
         if _tome_info["trace_source"]:
             _tome_info["source"] = merge_source(merge, x, _tome_info["source"])
         pre_merge = x.size(1)
         if isinstance(merge, Merge):
-            x = _wavg(merge, x, _tome_info, norm)
+            x = _wavg(merge, x, _tome_info, norm, residual)
         else:
             x, _tome_info["size"] = merge_wavg(merge, x, _tome_info["size"])
             _tome_info["log_size"] = None
         if _tome_info['verbose']:
             print(f'Merged {pre_merge} to {x.size(1)} tokens')
+    elif residual is not None:
+        x = residual + x
     return x
 
 
-def vivit_drop(metric, x, _tome_info, norm=None):
+def vivit_drop(metric, x, _tome_info, norm=None, residual=None):
     """vivit.py:156-179."""
+    if residual is not None:
+        x = residual + x
     _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
     if r > 0:
@@ -139,23 +146,27 @@ def vivit_drop(metric, x, _tome_info, norm=None):
     return x
 
 
-def vivit_hybrid(metric, x, _tome_info, norm=None):
+def vivit_hybrid(metric, x, _tome_info, norm=None, residual=None):
     """vivit.py:182-204."""
     _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
     if r > 0:
         merge, _ = bipartite_soft_matching_hybrid(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
                                                   _tome_info["mode"], _tome_info["threshold"])
+        if residual is not None and not (isinstance(merge, Merge) and _fusable_residual(x, residual)):
+            x, residual = residual + x, None
         if _tome_info["trace_source"]:
             _tome_info["source"] = merge_source(merge, x, _tome_info["source"])
         pre_merge = x.size(1)
         if isinstance(merge, Merge):
-            x = _wavg(merge, x, _tome_info, norm)
+            x = _wavg(merge, x, _tome_info, norm, residual)
         else:
             x, _tome_info["size"] = merge_wavg(merge, x, _tome_info["size"])
             _tome_info["log_size"] = None
         if _tome_info['verbose']:
             print(f'Merged {pre_merge} to {x.size(1)} tokens')
+    elif residual is not None:
+        x = residual + x
     return x
 
 
