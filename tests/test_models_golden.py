@@ -143,3 +143,31 @@ def test_vivit_cuda_vs_cpu_port_and_hf():
         err16 = float((got16 - want).abs().max() / want.abs().max())
         print(f"[model-parity] vivit {kw}: max rel err bf16 = {err16:.2e}")
         assert err16 < 3e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["videomae_merge", "timesformer_merge"])
+def test_training_step_gradients_match_cpu_port(name):
+    """Training with ToMe (tools/train_net.py:727-741): gradients through the CUDA merge path (kernel forward,
+    unmerge-based backward) equal autograd through the reference's closures (CPU port) on the same model."""
+    import tome
+    case = next(c for c in G.MODEL_CASES if c["name"] == name)
+    torch.manual_seed(0)
+    clip = G.clip_for(case)
+    grads = {}
+    for dev in ("cpu", "cuda"):
+        model = G.seeded_fill(G.build_ours(case).eval()).to(dev)
+        getattr(tome.patch, case["model"])(model, **case["kw"])
+        model.r = case["r"]
+        ctx = port_backend() if dev == "cpu" else contextlib.nullcontext()
+        with ctx:
+            out = model([clip.to(dev)])
+            out.square().sum().backward()
+        grads[dev] = {k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None}
+    assert grads["cuda"].keys() == grads["cpu"].keys() and len(grads["cpu"]) > 10
+    worst = 0.0
+    for k, g in grads["cpu"].items():
+        err = float((grads["cuda"][k] - g).abs().max() / g.abs().max().clamp_min(1e-12))
+        worst = max(worst, err)
+    print(f"[model-parity] {name}: max rel grad err = {worst:.2e}")
+    assert worst < 5e-3, worst

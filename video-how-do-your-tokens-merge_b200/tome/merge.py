@@ -106,14 +106,75 @@ class _PlanCallable:
     node_max = property(lambda self: self.plan.node_max)
 
 
+class _MergeGrad(torch.autograd.Function):
+    """Backward of the merge kernel: the reference trains through its gather /
+    scatter_reduce closures (tools/train_net.py:727-741).  Every input token t lands in exactly one output
+    slot, with weight 1 (sum / drop), 1 / count (mean) or size_t / size'_slot (merge_wavg), so the gradient is
+    the kernel's own inverse map -- ``tome_unmerge`` of grad_out -- times that weight; tokens that do not
+    reach the output (dropped sources; destinations a hybrid threshold zeroed, merge.py:326) get zero."""
+
+    @staticmethod
+    def forward(ctx, x, plan, mode, size, threshold):
+        if plan.distill_token:
+            raise NotImplementedError("tome_b200: merge backward with a distillation token is not supported")
+        if mode in ("max", "amax"):
+            raise NotImplementedError("tome_b200: merge backward is not defined for the amax mode")
+        want = mode == "wavg"
+        res = _native.merge(plan, x.detach(), mode, size=size, hybrid_threshold=threshold, want_size=want)
+        out, size_out, logsize_out = (res if want else (res, None, None))
+        ctx.plan, ctx.mode, ctx.threshold = plan, mode, threshold
+        ctx.save_for_backward(size, size_out)
+        if want:
+            ctx.mark_non_differentiable(size_out, logsize_out)
+            return out, size_out, logsize_out
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out, *unused):
+        plan, mode, thr = ctx.plan, ctx.mode, ctx.threshold
+        size, size_out = ctx.saved_tensors
+        bm, n, r = plan.bm, plan.n, plan.r
+        na, nb = (n + 1) // 2, n // 2
+        g = _native.unmerge(plan, grad_out.contiguous())                     # (bm, n, c): grad of the slot each token fed
+        dev = g.device
+        if mode == "wavg":
+            s_in = torch.ones(bm, n, 1, device=dev) if size is None else size.reshape(bm, n, 1).float()
+            s_slot = _native.unmerge(plan, size_out.reshape(bm, n - r, 1).contiguous())
+            g = g * (s_in / s_slot).to(g.dtype)
+        elif mode == "mean":
+            cnt = torch.ones(bm, n - r, 1, device=dev)
+            cnt[:, na - r:, 0] += plan.b_head[:, :, 0].float()
+            g = g / _native.unmerge(plan, cnt).to(g.dtype)
+        if mode == "drop":                                                   # sources are discarded (merge.py:260-269)
+            g[torch.arange(bm, device=dev)[:, None], 2 * plan.src_idx.long()] = 0
+        elif thr is not None and thr == thr:                                 # hybrid: destinations hit by an under-threshold edge
+            low = (plan.node_max.gather(1, plan.src_idx.long()) < thr)
+            hit = torch.zeros(bm, nb, device=dev).scatter_add_(1, plan.dst_idx.long(), low.float()) > 0
+            g[:, 1::2][hit] = 0
+        return g, None, None, None, None
+
+
+def _needs_grad(x: torch.Tensor) -> bool:
+    return torch.is_grad_enabled() and x.requires_grad
+
+
 class Merge(_PlanCallable):
     def __call__(self, x: torch.Tensor, mode="mean") -> torch.Tensor:      # merge.py:75-85 / 316-334
+        if _needs_grad(x):
+            return _MergeGrad.apply(x, self.plan, mode, None, self.threshold)
         return _native.merge(self.plan, x, mode, hybrid_threshold=self.threshold)
 
     def wavg(self, x, size=None, norm=None, residual=None):
         """Fused merge_wavg: (x', size' (bm, n', 1) fp32, log size' (bm, n', 1) fp32); with
         ``norm=(weight, bias, eps)`` also LayerNorm(x') from the same pass as a 4th result; with
         ``residual`` the tokens merged are ``x + residual`` (the block's residual add, same pass)."""
+        if _needs_grad(x):                         # training: kernel forward, unmerge-based backward; no fusions
+            if residual is not None:
+                x = x + residual
+            out, s, ls = _MergeGrad.apply(x, self.plan, "wavg", size, self.threshold)
+            res = (out, s, ls) + ((torch.nn.functional.layer_norm(out, (out.shape[-1],), norm[0], norm[1], norm[2]),)
+                                  if norm is not None else ())
+            return (res[0], s[..., None], ls[..., None]) + tuple(res[3:])
         res = _native.merge(self.plan, x, "wavg", size=size, hybrid_threshold=self.threshold, want_size=True, norm=norm,
                             residual=residual)
         out, s, ls = res[:3]
@@ -126,6 +187,16 @@ class Merge(_PlanCallable):
         """merge_wavg on a (B, 1 + P*T, C) class-token + '(p t)' tensor whose matching batch is (b t):
         the TimeSformer / Motionformer case, rearranges folded into addressing.
         Returns (x' (B, 1 + P'*T, C), size' (B*T, P', 1), log size' (B*T, P', 1))."""
+        if _needs_grad(x):                         # training: the reference's rearranges, differentiable merge
+            B, L, C = x.shape
+            T = int(frames)
+            P = (L - 1) // T
+            xs = x[:, 1:].reshape(B, P, T, C).transpose(1, 2).reshape(B * T, P, C)
+            out, s, ls = self.wavg(xs, size)[:3]
+            Pn = out.size(1)
+            y = torch.cat((x[:, :1], out.reshape(B, T, Pn, C).transpose(1, 2).reshape(B, Pn * T, C)), 1)
+            extra = (torch.nn.functional.layer_norm(y, (C,), norm[0], norm[1], norm[2]),) if norm is not None else ()
+            return (y, s, ls) + extra
         res = _native.merge_frames(self.plan, x, frames, "wavg", size=size, hybrid_threshold=self.threshold, norm=norm)
         out, s, ls = res[:3]
         return (out, s[..., None], ls[..., None]) + tuple(res[3:])
@@ -140,10 +211,19 @@ class Drop(_PlanCallable):
     und_idx = property(lambda self: self.plan.unm_idx.long()[..., None])
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:                    # merge.py:260-269
+        if _needs_grad(x):
+            return _MergeGrad.apply(x, self.plan, "drop", None, None)
         return _native.merge(self.plan, x, "drop")
 
     def frames(self, x, frames):
         """drop on the (B, 1 + P*T, C) layout (see Merge.wavg_frames)."""
+        if _needs_grad(x):
+            B, L, C = x.shape
+            T = int(frames)
+            P = (L - 1) // T
+            out = self(x[:, 1:].reshape(B, P, T, C).transpose(1, 2).reshape(B * T, P, C))
+            Pn = out.size(1)
+            return torch.cat((x[:, :1], out.reshape(B, T, Pn, C).transpose(1, 2).reshape(B, Pn * T, C)), 1)
         return _native.merge_frames(self.plan, x, frames, "drop")[0]
 
 
