@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 11
+#define TOME_ABI_VERSION 12
 
 #if defined(__GNUC__)
 #define TOME_API __attribute__((visibility("default")))
@@ -229,6 +229,15 @@ TOME_API int tome_attn_key_bias(const float* log_size, int32_t b, int32_t n, int
  * conversion (fp32 clips to a bf16 model) happens in the same pass.  pw % 8 == 0. */
 TOME_API int tome_patchify(const void* x, int32_t in_dtype, int32_t b, int32_t c, int32_t t, int32_t h, int32_t w,
                   int32_t tt, int32_t ph, int32_t pw, void* out, int32_t out_dtype, void* stream);
+
+/* Caller-side fusion: the first half of the block's MLP right after the merge
+ * (videomae builder:40-56: fc1 -> nn.GELU -> fc2), out = GELU_erf(x @ W^T + bias) from ONE tcgen05 GEMM whose
+ * epilogue applies bias and activation, instead of a library GEMM plus an elementwise pass over the (m, n)
+ * tensor.  bf16 only: x (m, k) with rows `x_row_stride` elements apart, W (n, k) and out (m, n) contiguous,
+ * bias (n) or NULL; fp32 accumulation; the pre-activation is rounded to bf16 before the GELU, as the two
+ * separate ops would.  gelu == 0: bias only.  n % 256 == 0, k % 8 == 0. */
+TOME_API int tome_linear_gelu(const void* x, const void* w, const void* bias, int32_t m, int32_t n, int32_t k,
+                     int64_t x_row_stride, int32_t gelu, void* out, void* stream);
 
 /* unmerge (merge.py:87-100): x (bm, n - r, c) -> out (bm, n, c); contiguous tensors. */
 TOME_API int tome_unmerge(const tome_plan* plan, const void* x, int32_t dtype, int32_t c, void* out,

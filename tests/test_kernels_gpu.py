@@ -557,3 +557,29 @@ def test_merge_backward_matches_reference_autograd(native, name):
         b = xs.cuda().requires_grad_(True)
         (our_drop(b) * wgt.cuda()).sum().backward()
         torch.testing.assert_close(b.grad.cpu(), a.grad, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(300, 256, 64), (12544, 3072, 768), (3744, 3072, 768), (129, 512, 200)])
+@pytest.mark.parametrize("gelu", [True, False])
+def test_linear_gelu_matches_linear_then_gelu(native, shape, gelu):
+    """tome_linear_gelu (tcgen05 GEMM, bias + erf GELU in the epilogue) against F.linear followed by F.gelu on
+    the same bf16 tensors: the two GEMMs accumulate in different orders, so outputs may differ by one bf16
+    ulp of the pre-activation; against the fp32 reference both are equally close."""
+    m, n, k = shape
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn(m, k, device="cuda", generator=gen).to(torch.bfloat16)
+    w = (torch.randn(n, k, device="cuda", generator=gen) * k ** -0.5).to(torch.bfloat16)
+    b = (0.1 * torch.randn(n, device="cuda", generator=gen)).to(torch.bfloat16)
+    with torch.no_grad():
+        assert native.linear_gelu_supported(x, w, b)
+    got = native.linear_gelu(x, w, b, gelu=gelu).float()
+    pre = torch.nn.functional.linear(x, w, b)
+    lib = (torch.nn.functional.gelu(pre) if gelu else pre).float()
+    ref = x.float() @ w.float().t() + b.float()
+    ref = torch.nn.functional.gelu(ref) if gelu else ref
+    err_ours, err_lib = (got - ref).abs().max().item(), (lib - ref).abs().max().item()
+    print(f"[linear-gelu] {shape} gelu={gelu}: max err vs fp32 ours {err_ours:.3e} library {err_lib:.3e}")
+    assert err_ours <= 1.5 * err_lib + 1e-3
+    assert (got - lib).abs().max().item() <= 4e-2
+    got3 = native.linear_gelu(x.reshape(1, m, k), w, None, gelu=gelu)
+    assert got3.shape == (1, m, n)

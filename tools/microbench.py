@@ -83,6 +83,20 @@ def main():
     out["torch_add_then_merge_wavg_norm_cold"] = dict(us=med, us_best=best)
     med, best = graph_time([lambda i=i: _native.add_layernorm(xs[i], rs[i], (w, bb, 1e-6)) for i in range(nrot)])
     out["add_layernorm_cold"] = dict(us=med, us_best=best, GBps=3 * bm * n * c * e / med / 1e3)
+    if dt == torch.bfloat16:      # the MLP's first half: library GEMM + GELU pass vs the fused tcgen05 kernel
+        for toks in (n, 1068, 768, 468):
+            xm = torch.randn(bm * toks, c, device=dev, dtype=dt, generator=g)
+            w1 = (torch.randn(4 * c, c, device=dev, generator=g) * c ** -0.5).to(dt)
+            b1 = torch.zeros(4 * c, device=dev, dtype=dt)
+            fl = 2.0 * bm * toks * c * 4 * c
+            med, best = graph_time([lambda: torch.nn.functional.gelu(torch.nn.functional.linear(xm, w1, b1)) for _ in range(4)])
+            out[f"torch_linear_then_gelu_{toks}"] = dict(us=med, us_best=best, tflops=fl / med / 1e6)
+            med, best = graph_time([lambda: torch.nn.functional.linear(xm, w1, b1) for _ in range(4)])
+            out[f"torch_linear_{toks}"] = dict(us=med, us_best=best, tflops=fl / med / 1e6)
+            med, best = graph_time([lambda: _native.linear_gelu(xm, w1, b1) for _ in range(4)])
+            out[f"linear_gelu_fused_{toks}"] = dict(us=med, us_best=best, tflops=fl / med / 1e6)
+            med, best = graph_time([lambda: _native.linear_gelu(xm, w1, b1, gelu=False) for _ in range(4)])
+            out[f"linear_fused_nogelu_{toks}"] = dict(us=med, us_best=best, tflops=fl / med / 1e6)
     flops = 2.0 * bm * na * (n // 2) * cm
     for algo, name in ((2, "match_tc"), (1, "match_exact")):
         med, best = graph_time([lambda i=i: _native.match(ms[i % nrot], bool(a.cls), algo=algo) for i in range(8)])

@@ -1,0 +1,222 @@
+// Caller-side fusion ("MLP right after the merge"): out = GELU(x @ W^T + bias) in one
+// kernel -- the first half of every block's MLP (slowfast/models/videomae_video_model_builder.py:40-56:
+// fc1 -> nn.GELU (erf) -> fc2).  With a library GEMM the activation is a separate elementwise pass over
+// the (tokens, 4C) tensor: 154 MB of traffic per block at the bench shape, 11 % of the whole forward
+// (profiles/r01d_launch_summary.txt).  Here it rides in the GEMM's epilogue.
+//
+// bf16 in / bf16 out, fp32 accumulation in TMEM.  Persistent CTAs (one per SM) walk 128 x 256 output tiles:
+//   warp 0      TMA producer: A (128 x 64) and W (256 x 64) boxes, SWIZZLE_128B, 4-stage mbarrier ring that
+//               keeps running across tiles
+//   warp 1      TMEM allocator (all 512 columns = two 128 x 256 fp32 accumulators) + single-thread MMA issuer:
+//               4 x tcgen05.mma kind::f16 (M 128, N 256, K 16) per stage, tcgen05.commit frees the stage /
+//               publishes the accumulator
+//   warps 2-9   epilogue, two warps per TMEM lane quarter (128 columns each): tcgen05.ld -> + bias -> round to
+//               bf16 (what F.linear would have stored) -> erf GELU in fp32 (|error| <= 2e-7) -> bf16 -> a per-warp
+//               swizzled shared-memory box -> TMA store (each lane owns a ROW of the tile, so direct stores were 32
+//               scattered 16-byte pieces per instruction and capped the whole kernel at 68 us).
+//               Accumulator t+1 is being filled while accumulator t is drained.
+#include <math.h>
+
+#include "tc_ptx.cuh"
+
+namespace tome {
+
+constexpr int LG_BM = 128, LG_BN = 256, LG_BK = 64, LG_STAGES = 4;
+constexpr int LG_THREADS = 320;                       // TMA, MMA, 8 epilogue warps
+constexpr uint32_t LG_A_BYTES = LG_BM * 128u, LG_B_BYTES = LG_BN * 128u, LG_STAGE_BYTES = LG_A_BYTES + LG_B_BYTES;
+constexpr uint32_t LG_OBOX_BYTES = 32u * 128u;        // one epilogue warp's output box: 32 rows x 64 bf16 columns
+
+struct LinearGeluParams {
+  int m, n, k, num_kb, tiles_n, tiles;
+  const __nv_bfloat16* bias;                          // (n) or NULL
+  __nv_bfloat16* out;                                 // (m, n) row-major
+  int gelu;                                           // 0: plain linear (bias only)
+};
+
+// erf GELU.  libdevice's erff is two branches and ~50 instructions: with 32 k elements per tile the epilogue then
+// takes longer than the tile's MMAs (90 us for the whole GEMM against 68 us without the activation).  Branch-free
+// instead: Abramowitz & Stegun 7.1.26, erfc(|z|) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2), t = 1 / (1 + p |z|),
+// |error| <= 1.5e-7 -- four orders below the bf16 rounding of the result -- one MUFU.RCP, one MUFU.EX2, 8 FMAs.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float erfc_abs = poly * t * __expf(-z * z);          // erfc(|z|)
+  const float cdf2 = x >= 0.f ? 2.0f - erfc_abs : erfc_abs;   // 1 + erf(x / sqrt 2)
+  return 0.5f * x * cdf2;
+}
+
+__global__ void __launch_bounds__(LG_THREADS, 1)
+linear_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                   const __grid_constant__ CUtensorMap map_o, const LinearGeluParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t obox = base + LG_STAGES * LG_STAGE_BYTES;             // 8 x 4 KB, 1024-byte aligned
+  const uint32_t bars = obox + 8u * LG_OBOX_BYTES;
+  const uint32_t bar_full = bars, bar_empty = bars + 8u * LG_STAGES;
+  const uint32_t bar_tfull = bars + 16u * LG_STAGES, bar_tempty = bar_tfull + 16u;
+  const uint32_t tmem_slot = bar_tempty + 16u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LG_STAGES; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+        const int mt = t / p.tiles_n, nt = t - mt * p.tiles_n;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const uint32_t s = it % LG_STAGES, ph = (it / LG_STAGES) & 1u;
+          mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+          const uint32_t st = base + s * LG_STAGE_BYTES, full = bar_full + 8u * s;
+          mbar_expect_tx(full, LG_STAGE_BYTES);
+          tma_load_2d(st, &map_a, kb * LG_BK, mt * LG_BM, full);
+          tma_load_2d(st + LG_A_BYTES, &map_w, kb * LG_BK, nt * LG_BN, full);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B bf16, both K-major, N = 256, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LG_BN >> 3) << 17) | ((uint32_t)(LG_BM >> 4) << 24);
+      uint32_t it = 0, tl = 0;
+      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++tl) {
+        const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+        mbar_wait(bar_tempty + 8u * acc, aph ^ 1u);            // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)LG_BN;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const uint32_t s = it % LG_STAGES, ph = (it / LG_STAGES) & 1u;
+          mbar_wait(bar_full + 8u * s, ph);
+          tc_fence_after();
+          const uint32_t st = base + s * LG_STAGE_BYTES;
+          const uint64_t a_desc = make_sw128_desc(st), b_desc = make_sw128_desc(st + LG_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < LG_BK / 16; ++k) {
+            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);   // +32 bytes inside the swizzle row
+            umma_bf16(d_tmem, a_desc + adv, b_desc + adv, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8u * s);
+        }
+        umma_commit(bar_tfull + 8u * acc);
+      }
+    }
+  } else {
+    const int q = warp & 3;                            // TMEM lane quarter this warp may touch
+    const int half = (warp - 2) >> 2;                  // which 128 of the tile's 256 columns
+    uint32_t tl = 0;
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++tl) {
+      const int mt = t / p.tiles_n, nt = t - mt * p.tiles_n;
+      const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+      mbar_wait(bar_tfull + 8u * acc, aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * (uint32_t)LG_BN + (uint32_t)(half * 128) + ((uint32_t)(q * 32) << 16);
+      const __nv_bfloat16* brow = p.bias ? p.bias + nt * LG_BN + half * 128 : nullptr;
+      const uint32_t mybox = obox + (uint32_t)(warp - 2) * LG_OBOX_BYTES;
+#pragma unroll 1
+      for (int bx = 0; bx < 2; ++bx) {                 // two 64-column boxes per warp and tile
+        // the previous TMA store out of this box must have finished READING shared memory
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+#pragma unroll 1
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const int c = bx * 2 + c2;                   // 32-column chunk of this warp's 128 columns
+          float v[32];
+          tmem_ld32(taddr + (uint32_t)(c * 32), v);
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            float bf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (brow) {
+              const uint4 bw = __ldg(reinterpret_cast<const uint4*>(brow + c * 32 + g4 * 8));
+              const uint32_t w[4] = {bw.x, bw.y, bw.z, bw.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { bf[2 * i] = __uint_as_float(w[i] << 16); bf[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+            }
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float x0 = v[g4 * 8 + 2 * i] + bf[2 * i], x1 = v[g4 * 8 + 2 * i + 1] + bf[2 * i + 1];
+              if (p.gelu) {
+                // round to bf16 first: the value F.linear would have stored and nn.GELU would have read
+                x0 = gelu_erf(__bfloat162float(__float2bfloat16_rn(x0)));
+                x1 = gelu_erf(__bfloat162float(__float2bfloat16_rn(x1)));
+              }
+              const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+              w[i] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            // row = lane, 16-byte chunk j of the 128-byte box row, SWIZZLE_128B: chunk ^ (row & 7)
+            const uint32_t j = (uint32_t)(c2 * 4 + g4);
+            const uint32_t dst = mybox + (uint32_t)lane * 128u + ((j ^ ((uint32_t)lane & 7u)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          const int col = nt * LG_BN + half * 128 + bx * 64, row0 = mt * LG_BM + q * 32;
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                       ::"l"(&map_o), "r"(col), "r"(row0), "r"(mybox) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tempty + 8u * acc) : "memory");
+    }
+  }
+  if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every store has landed
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+int launch_linear_gelu(const void* x, const void* w, const void* bias, int m, int n, int k, long long x_row_stride, int gelu,
+                       void* out, cudaStream_t st) {
+  if (n % LG_BN != 0 || k % 8 != 0 || k < 8 || m < 1)
+    return set_error(TOME_ERR_UNSUPPORTED, "tome_linear_gelu: needs n %% %d == 0 and k %% 8 == 0 (m=%d n=%d k=%d)", LG_BN, m, n, k);
+  if (((uintptr_t)x & 15) || ((uintptr_t)w & 15) || ((uintptr_t)out & 15) || (bias && ((uintptr_t)bias & 15)) || (x_row_stride % 8))
+    return set_error(TOME_ERR_ALIGN, "tome_linear_gelu: 16-byte aligned tensors and row strides required");
+  alignas(64) CUtensorMap map_a, map_w;
+  int rc = make_bf16_map(&map_a, x, m, k, x_row_stride, LG_BM, "tome_linear_gelu");
+  if (rc) return rc;
+  rc = make_bf16_map(&map_w, w, n, k, k, LG_BN, "tome_linear_gelu");
+  if (rc) return rc;
+  alignas(64) CUtensorMap map_o;
+  rc = make_bf16_map(&map_o, out, m, n, n, 32, "tome_linear_gelu");
+  if (rc) return rc;
+  LinearGeluParams p;
+  p.m = m; p.n = n; p.k = k; p.num_kb = (k + LG_BK - 1) / LG_BK;
+  p.tiles_n = n / LG_BN; p.tiles = ((m + LG_BM - 1) / LG_BM) * p.tiles_n;
+  p.bias = (const __nv_bfloat16*)bias; p.out = (__nv_bfloat16*)out; p.gelu = gelu;
+  const size_t smem = (size_t)LG_STAGES * LG_STAGE_BYTES + 8 * LG_OBOX_BYTES + 16 * LG_STAGES + 32 + 16 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    TOME_CUDA(cudaFuncSetAttribute(linear_gelu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  const int grid = p.tiles < sm_count() ? p.tiles : sm_count();
+  linear_gelu_kernel<<<grid, LG_THREADS, smem, st>>>(map_a, map_w, map_o, p);
+  TOME_LAUNCH_CHECK("linear_gelu_kernel");
+  return TOME_OK;
+}
+
+}  // namespace tome

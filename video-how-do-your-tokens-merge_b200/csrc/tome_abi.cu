@@ -63,6 +63,7 @@ int launch_merge(const tome_plan*, const void*, int, int, const View&, const flo
 int launch_merge_source(const tome_plan*, const float*, int, float, float*, cudaStream_t);
 int launch_unmerge(const tome_plan*, const void*, int, int, void*, cudaStream_t);
 int launch_add_layernorm(const void*, const void*, long long, int, long long, int, const void*, const void*, float, void*, void*, cudaStream_t);
+int launch_linear_gelu(const void*, const void*, const void*, int, int, int, long long, int, void*, cudaStream_t);
 int launch_patchify(const void*, int, int, int, int, int, int, int, int, int, void*, int, cudaStream_t);
 int launch_key_bias(const float*, int, int, int, int, int, float, int, void*, long long, long long, long long, void*, long long,
                     long long, long long, cudaStream_t);
@@ -287,6 +288,15 @@ int tome_add_rows_layernorm(const void* a, const void* b, int64_t b_rows, int32_
   TOME_CHECK_ARG(a && b && ln_weight && sum_out && normed_out && rows > 0 && c > 0 && b_rows > 0 && b_rows <= rows,
                  "tome_add_layernorm: NULL pointer or empty shape");
   return launch_add_layernorm(a, b, b_rows, dtype, rows, c, ln_weight, ln_bias, ln_eps, sum_out, normed_out, (cudaStream_t)stream);
+}
+
+int tome_linear_gelu(const void* x, const void* w, const void* bias, int32_t m, int32_t n, int32_t k, int64_t x_row_stride,
+                     int32_t gelu, void* out, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(x && w && out && m > 0 && n > 0 && k > 0 && x_row_stride >= k, "tome_linear_gelu: NULL pointer or bad shape");
+  TOME_CHECK_ARG(x != out, "tome_linear_gelu: in-place is not supported");
+  return launch_linear_gelu(x, w, bias, m, n, k, x_row_stride, gelu, out, (cudaStream_t)stream);
 }
 
 int tome_patchify(const void* x, int32_t in_dtype, int32_t b, int32_t c, int32_t t, int32_t h, int32_t w, int32_t tt, int32_t ph,

@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 TOME_F32, TOME_BF16 = 0, 1
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -29,7 +29,7 @@ EXPORTS = (
     "tome_abi_version", "tome_last_error", "tome_launch_count", "tome_device_check", "tome_match_workspace_bytes", "tome_match", "tome_match_heads",
     "tome_plan_build_workspace_bytes", "tome_plan_build", "tome_match_tc_describe",
     "tome_rowmax", "tome_select_workspace_bytes", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_add_norm", "tome_add_layernorm", "tome_add_rows_layernorm",
-    "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_unmerge",
+    "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_linear_gelu", "tome_unmerge",
 )
 
 
@@ -101,13 +101,14 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.tome_add_rows_layernorm.argtypes = [c_vp, c_vp, ctypes.c_int64, c_i32, ctypes.c_int64, c_i32, c_vp, c_vp, c_f32, c_vp,
                                             c_vp, c_vp]
     lib.tome_patchify.argtypes = [c_vp, c_i32] + [c_i32] * 8 + [c_vp, c_i32, c_vp]
+    lib.tome_linear_gelu.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, ctypes.c_int64, c_i32, c_vp, c_vp]
     lib.tome_merge_source.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_f32, c_vp, c_vp]
     c_i64 = ctypes.c_int64
     lib.tome_attn_key_bias.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_i32, c_vp, c_i64, c_i64, c_i64,
                                        c_vp, c_i64, c_i64, c_i64, c_vp]
     lib.tome_unmerge.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_i32, c_vp, c_vp]
     for name in ("tome_device_check", "tome_match", "tome_match_heads", "tome_rowmax", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_add_norm", "tome_add_layernorm", "tome_add_rows_layernorm",
-                 "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_unmerge"):
+                 "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_linear_gelu", "tome_unmerge"):
         getattr(lib, name).restype = c_i32
     if lib.tome_abi_version() != ABI_VERSION:
         raise RuntimeError(f"tome_b200: ABI version {lib.tome_abi_version()} != expected {ABI_VERSION}; rebuild")
@@ -509,6 +510,28 @@ def add_layernorm(a: torch.Tensor, b: torch.Tensor, norm):
         _check(lib.tome_add_rows_layernorm(a.data_ptr(), b.data_ptr(), b.numel() // c, _dtype_code(a), a.numel() // c, c,
                                            wp, bp, eps, s.data_ptr(), y.data_ptr(), _stream(a)), lib)
     return s, y
+
+
+def linear_gelu_supported(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> bool:
+    return (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and weight.is_contiguous()
+            and weight.shape[0] % 256 == 0 and weight.shape[1] % 8 == 0 and x.shape[-1] == weight.shape[1]
+            and (bias is None or (bias.dtype == torch.bfloat16 and bias.is_contiguous())) and not torch.is_grad_enabled())
+
+
+def linear_gelu(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], gelu: bool = True) -> torch.Tensor:
+    """GELU_erf(x @ weight^T + bias) from one tcgen05 GEMM with the activation in its epilogue (bf16)."""
+    lib = load_library()
+    _require_cuda(x, "x")
+    k = x.shape[-1]
+    x2 = x.reshape(-1, k)
+    if x2.stride(1) != 1 or x2.stride(0) % 8 != 0:
+        x2 = x2.contiguous()
+    m, n = x2.shape[0], weight.shape[0]
+    with torch.cuda.device(x.device):
+        out = torch.empty(m, n, dtype=x.dtype, device=x.device)
+        _check(lib.tome_linear_gelu(x2.data_ptr(), weight.data_ptr(), None if bias is None else bias.data_ptr(), m, n, k,
+                                    x2.stride(0), int(bool(gelu)), out.data_ptr(), _stream(x)), lib)
+    return out.reshape(*x.shape[:-1], n)
 
 
 def patchify(x: torch.Tensor, tubelet: int, ph: int, pw: int, out_dtype: torch.dtype) -> torch.Tensor:
