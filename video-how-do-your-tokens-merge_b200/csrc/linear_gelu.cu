@@ -10,7 +10,7 @@
 //   warp 1      TMEM allocator (all 512 columns = two 128 x 256 fp32 accumulators) + single-thread MMA issuer:
 //               4 x tcgen05.mma kind::f16 (M 128, N 256, K 16) per stage, tcgen05.commit frees the stage /
 //               publishes the accumulator
-//   warps 2-9   epilogue, two warps per TMEM lane quarter (128 columns each): tcgen05.ld -> + bias -> round to
+//   warps 2-17  epilogue, four warps per TMEM lane quarter (64 columns each): tcgen05.ld -> + bias -> round to
 //               bf16 (what F.linear would have stored) -> erf GELU in fp32 (|error| <= 2e-7) -> bf16 -> a per-warp
 //               swizzled shared-memory box -> TMA store (each lane owns a ROW of the tile, so direct stores were 32
 //               scattered 16-byte pieces per instruction and capped the whole kernel at 68 us).
@@ -21,8 +21,9 @@
 
 namespace tome {
 
-constexpr int LG_BM = 128, LG_BN = 256, LG_BK = 64, LG_STAGES = 4;
-constexpr int LG_THREADS = 320;                       // TMA, MMA, 8 epilogue warps
+constexpr int LG_BM = 128, LG_BN = 256, LG_BK = 64, LG_STAGES = 3;
+constexpr int LG_EPI_WARPS = 16;                      // four per TMEM lane quarter, 64 columns each
+constexpr int LG_THREADS = 64 + 32 * LG_EPI_WARPS;    // TMA, MMA, epilogue warps
 constexpr uint32_t LG_A_BYTES = LG_BM * 128u, LG_B_BYTES = LG_BN * 128u, LG_STAGE_BYTES = LG_A_BYTES + LG_B_BYTES;
 constexpr uint32_t LG_OBOX_BYTES = 32u * 128u;        // one epilogue warp's output box: 32 rows x 64 bf16 columns
 
@@ -55,8 +56,8 @@ linear_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t obox = base + LG_STAGES * LG_STAGE_BYTES;             // 8 x 4 KB, 1024-byte aligned
-  const uint32_t bars = obox + 8u * LG_OBOX_BYTES;
+  const uint32_t obox = base + LG_STAGES * LG_STAGE_BYTES;             // one 4 KB box per epilogue warp, 1024-byte aligned
+  const uint32_t bars = obox + (uint32_t)LG_EPI_WARPS * LG_OBOX_BYTES;
   const uint32_t bar_full = bars, bar_empty = bars + 8u * LG_STAGES;
   const uint32_t bar_tfull = bars + 16u * LG_STAGES, bar_tempty = bar_tfull + 16u;
   const uint32_t tmem_slot = bar_tempty + 16u;
@@ -64,7 +65,7 @@ linear_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < LG_STAGES; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, LG_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -119,61 +120,57 @@ linear_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
   } else {
     const int q = warp & 3;                            // TMEM lane quarter this warp may touch
-    const int half = (warp - 2) >> 2;                  // which 128 of the tile's 256 columns
+    const int part = (warp - 2) >> 2;                  // which 64 of the tile's 256 columns
+    const uint32_t mybox = obox + (uint32_t)(warp - 2) * LG_OBOX_BYTES;
     uint32_t tl = 0;
     for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++tl) {
       const int mt = t / p.tiles_n, nt = t - mt * p.tiles_n;
       const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
       mbar_wait(bar_tfull + 8u * acc, aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * (uint32_t)LG_BN + (uint32_t)(half * 128) + ((uint32_t)(q * 32) << 16);
-      const __nv_bfloat16* brow = p.bias ? p.bias + nt * LG_BN + half * 128 : nullptr;
-      const uint32_t mybox = obox + (uint32_t)(warp - 2) * LG_OBOX_BYTES;
+      const uint32_t taddr = tmem_base + acc * (uint32_t)LG_BN + (uint32_t)(part * 64) + ((uint32_t)(q * 32) << 16);
+      const __nv_bfloat16* brow = p.bias ? p.bias + nt * LG_BN + part * 64 : nullptr;
+      // the previous TMA store out of this warp's box must have finished READING shared memory
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
 #pragma unroll 1
-      for (int bx = 0; bx < 2; ++bx) {                 // two 64-column boxes per warp and tile
-        // the previous TMA store out of this box must have finished READING shared memory
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncwarp();
-#pragma unroll 1
-        for (int c2 = 0; c2 < 2; ++c2) {
-          const int c = bx * 2 + c2;                   // 32-column chunk of this warp's 128 columns
-          float v[32];
-          tmem_ld32(taddr + (uint32_t)(c * 32), v);
+      for (int c = 0; c < 2; ++c) {                    // two 32-column chunks = one 64-column box
+        float v[32];
+        tmem_ld32(taddr + (uint32_t)(c * 32), v);
 #pragma unroll
-          for (int g4 = 0; g4 < 4; ++g4) {
-            float bf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (brow) {
-              const uint4 bw = __ldg(reinterpret_cast<const uint4*>(brow + c * 32 + g4 * 8));
-              const uint32_t w[4] = {bw.x, bw.y, bw.z, bw.w};
+        for (int g4 = 0; g4 < 4; ++g4) {
+          float bf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (brow) {
+            const uint4 bw = __ldg(reinterpret_cast<const uint4*>(brow + c * 32 + g4 * 8));
+            const uint32_t w[4] = {bw.x, bw.y, bw.z, bw.w};
 #pragma unroll
-              for (int i = 0; i < 4; ++i) { bf[2 * i] = __uint_as_float(w[i] << 16); bf[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
-            }
-            uint32_t w[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float x0 = v[g4 * 8 + 2 * i] + bf[2 * i], x1 = v[g4 * 8 + 2 * i + 1] + bf[2 * i + 1];
-              if (p.gelu) {
-                // round to bf16 first: the value F.linear would have stored and nn.GELU would have read
-                x0 = gelu_erf(__bfloat162float(__float2bfloat16_rn(x0)));
-                x1 = gelu_erf(__bfloat162float(__float2bfloat16_rn(x1)));
-              }
-              const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-              w[i] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-            // row = lane, 16-byte chunk j of the 128-byte box row, SWIZZLE_128B: chunk ^ (row & 7)
-            const uint32_t j = (uint32_t)(c2 * 4 + g4);
-            const uint32_t dst = mybox + (uint32_t)lane * 128u + ((j ^ ((uint32_t)lane & 7u)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+            for (int i = 0; i < 4; ++i) { bf[2 * i] = __uint_as_float(w[i] << 16); bf[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
           }
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float x0 = v[g4 * 8 + 2 * i] + bf[2 * i], x1 = v[g4 * 8 + 2 * i + 1] + bf[2 * i + 1];
+            if (p.gelu) {
+              // round to bf16 first: the value F.linear would have stored and nn.GELU would have read
+              x0 = gelu_erf(__bfloat162float(__float2bfloat16_rn(x0)));
+              x1 = gelu_erf(__bfloat162float(__float2bfloat16_rn(x1)));
+            }
+            const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+            w[i] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          // row = lane, 16-byte chunk j of the 128-byte box row, SWIZZLE_128B: chunk ^ (row & 7)
+          const uint32_t j = (uint32_t)(c * 4 + g4);
+          const uint32_t dst = mybox + (uint32_t)lane * 128u + ((j ^ ((uint32_t)lane & 7u)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA engine
-        __syncwarp();
-        if (lane == 0) {
-          const int col = nt * LG_BN + half * 128 + bx * 64, row0 = mt * LG_BM + q * 32;
-          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                       ::"l"(&map_o), "r"(col), "r"(row0), "r"(mybox) : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        const int col = nt * LG_BN + part * 64, row0 = mt * LG_BM + q * 32;
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                     ::"l"(&map_o), "r"(col), "r"(row0), "r"(mybox) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       tc_fence_before();
       __syncwarp();
@@ -207,7 +204,7 @@ int launch_linear_gelu(const void* x, const void* w, const void* bias, int m, in
   p.m = m; p.n = n; p.k = k; p.num_kb = (k + LG_BK - 1) / LG_BK;
   p.tiles_n = n / LG_BN; p.tiles = ((m + LG_BM - 1) / LG_BM) * p.tiles_n;
   p.bias = (const __nv_bfloat16*)bias; p.out = (__nv_bfloat16*)out; p.gelu = gelu;
-  const size_t smem = (size_t)LG_STAGES * LG_STAGE_BYTES + 8 * LG_OBOX_BYTES + 16 * LG_STAGES + 32 + 16 + 1024;
+  const size_t smem = (size_t)LG_STAGES * LG_STAGE_BYTES + LG_EPI_WARPS * LG_OBOX_BYTES + 16 * LG_STAGES + 32 + 16 + 1024;
   static bool attr = false;
   if (!attr) {
     TOME_CUDA(cudaFuncSetAttribute(linear_gelu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -12,6 +12,9 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+FUSED_MLP_MIN_ROWS = 4096
+
+
 class Mlp(nn.Module):                                   # builder:40-56
     def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
         super().__init__()
@@ -23,6 +26,13 @@ class Mlp(nn.Module):                                   # builder:40-56
         self.drop = nn.Dropout(drop)
 
     def forward(self, x):
+        if (not self.training and x.is_cuda and x.dtype == torch.bfloat16 and isinstance(self.act, nn.GELU)
+                and self.act.approximate == "none" and x.numel() // x.shape[-1] >= FUSED_MLP_MIN_ROWS):
+            # fc1 + bias + erf GELU from one tcgen05 GEMM (tome_linear_gelu) instead of a library GEMM plus an
+            # elementwise pass over the (tokens, 4C) tensor; pays off from ~4 k rows (tools/microbench.py)
+            from tome import _native
+            if _native.linear_gelu_supported(x, self.fc1.weight, self.fc1.bias):
+                return self.drop(self.fc2(_native.linear_gelu(x, self.fc1.weight, self.fc1.bias)))
         return self.drop(self.fc2(self.act(self.fc1(x))))
 
 
