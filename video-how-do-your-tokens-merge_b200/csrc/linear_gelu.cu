@@ -38,16 +38,23 @@ struct LinearGeluParams {
 // takes longer than the tile's MMAs (90 us for the whole GEMM against 68 us without the activation).  Branch-free
 // instead: Abramowitz & Stegun 7.1.26, erfc(|z|) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2), t = 1 / (1 + p |z|),
 // |error| <= 1.5e-7 -- four orders below the bf16 rounding of the result -- one MUFU.RCP, one MUFU.EX2, 8 FMAs.
+__device__ __forceinline__ float exp2f_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f));
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(t, poly, 1.421413741f);
   poly = fmaf(t, poly, -0.284496736f);
   poly = fmaf(t, poly, 0.254829592f);
-  const float erfc_abs = poly * t * __expf(-z * z);          // erfc(|z|)
-  const float cdf2 = x >= 0.f ? 2.0f - erfc_abs : erfc_abs;   // 1 + erf(x / sqrt 2)
-  return 0.5f * x * cdf2;
+  // u = 0.5 |x| erfc(|x| / sqrt 2) = 0.5 |x| poly t exp2(-x^2 log2(e) / 2);  GELU(x) = max(x, 0) - u
+  const float e = exp2f_approx(x * x * -0.72134752044448170368f);
+  const float u = (0.5f * ax) * (poly * t) * e;
+  return fmaxf(x, 0.f) - u;
 }
 
 __global__ void __launch_bounds__(LG_THREADS, 1)
@@ -133,10 +140,13 @@ linear_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       // the previous TMA store out of this warp's box must have finished READING shared memory
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncwarp();
-#pragma unroll 1
+      float vv[2][32];                                 // both 32-column chunks in flight: one TMEM round trip per tile
+      tmem_ld32_nowait(taddr, vv[0]);
+      tmem_ld32_nowait(taddr + 32u, vv[1]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
       for (int c = 0; c < 2; ++c) {                    // two 32-column chunks = one 64-column box
-        float v[32];
-        tmem_ld32(taddr + (uint32_t)(c * 32), v);
+        float (&v)[32] = vv[c];
 #pragma unroll
         for (int g4 = 0; g4 < 4; ++g4) {
           float bf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};

@@ -12,7 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
-FUSED_MLP_MIN_ROWS = 4096
+FUSED_MLP_MIN_ROWS = 2048
 
 
 class Mlp(nn.Module):                                   # builder:40-56
@@ -29,7 +29,7 @@ class Mlp(nn.Module):                                   # builder:40-56
         if (not self.training and x.is_cuda and x.dtype == torch.bfloat16 and isinstance(self.act, nn.GELU)
                 and self.act.approximate == "none" and x.numel() // x.shape[-1] >= FUSED_MLP_MIN_ROWS):
             # fc1 + bias + erf GELU from one tcgen05 GEMM (tome_linear_gelu) instead of a library GEMM plus an
-            # elementwise pass over the (tokens, 4C) tensor; pays off from ~4 k rows (tools/microbench.py)
+            # elementwise pass over the (tokens, 4C) tensor; pays off from a few thousand rows (tools/microbench.py)
             from tome import _native
             if _native.linear_gelu_supported(x, self.fc1.weight, self.fc1.bias):
                 return self.drop(self.fc2(_native.linear_gelu(x, self.fc1.weight, self.fc1.bias)))
