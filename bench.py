@@ -311,6 +311,23 @@ def micro_kernels(args, device, dtype):
                                  "kernels": "tome_plan_build on the lazy head-mean of K (12 heads): split_rows + match_tc + rank + finish"}
     s_mean, s_med = graph_time([lambda: _native.select(nm, ni, n, r) for _ in range(8)])
     res["select"] = {"us_mean": s_mean, "us_median": s_med, "kernels": "rank_kernel + finish_kernel"}
+    if dtype == torch.bfloat16:
+        # caller-side tensor-core kernel: the MLP's fc1 + bias + erf GELU as one tcgen05 GEMM,
+        # against the library GEMM + elementwise GELU it replaces, at the layer-0 shape
+        tf_peak = float(peaks.get("bf16_tflops", 1662.0))
+        xm = torch.randn(bm * n, c, device=device, dtype=dtype, generator=g)
+        w1 = (torch.randn(4 * c, c, device=device, generator=g) * c ** -0.5).to(dtype)
+        b1 = torch.zeros(4 * c, device=device, dtype=dtype)
+        fl = 2.0 * bm * n * c * 4 * c
+        f_mean, f_med = graph_time([lambda: _native.linear_gelu(xm, w1, b1) for _ in range(4)])
+        t_mean, t_med = graph_time([lambda: torch.nn.functional.gelu(torch.nn.functional.linear(xm, w1, b1)) for _ in range(4)])
+        res["linear_gelu"] = {"us_mean": f_mean, "us_median": f_med, "algorithmic_gflop": fl / 1e9,
+                              "roofline": {"bound": "tensor", "achieved": fl / (f_mean * 1e-6) / 1e12, "peak": tf_peak,
+                                           "unit": "TFLOP/s", "frac": fl / (f_mean * 1e-6) / 1e12 / tf_peak,
+                                           "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)"},
+                              "library_gemm_plus_gelu_us": t_mean,
+                              "kernels": "linear_gelu_kernel (persistent tcgen05 GEMM 128x256x64, TMEM double-buffered, "
+                                         "bias + erf GELU + TMA store in the epilogue)"}
     c_mean, _ = graph_time([lambda i=i: xs[i].clone() for i in range(nrot)])
     res["torch_clone_same_bytes"] = {"us_mean": c_mean, "GBps": 2 * bm * n * c * e / (c_mean * 1e-6) / 1e9}
     return roofline, res

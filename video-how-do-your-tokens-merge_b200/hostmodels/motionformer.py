@@ -16,6 +16,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+from .videomae import fused_fc1_gelu  # noqa: E402
+
 class Mlp(nn.Module):
     def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
         super().__init__()
@@ -27,7 +29,8 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x):
-        return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+        h = fused_fc1_gelu(self, x)                     # tome_linear_gelu on the CUDA bf16 inference path
+        return self.drop(self.fc2(self.drop(h if h is not None else self.act(self.fc1(x)))))
 
 
 from tome.patch.motionformer import trajectory_attention  # noqa: E402  (shared with the ToMe patch)

@@ -26,14 +26,20 @@ class Mlp(nn.Module):                                   # builder:40-56
         self.drop = nn.Dropout(drop)
 
     def forward(self, x):
-        if (not self.training and x.is_cuda and x.dtype == torch.bfloat16 and isinstance(self.act, nn.GELU)
-                and self.act.approximate == "none" and x.numel() // x.shape[-1] >= FUSED_MLP_MIN_ROWS):
-            # fc1 + bias + erf GELU from one tcgen05 GEMM (tome_linear_gelu) instead of a library GEMM plus an
-            # elementwise pass over the (tokens, 4C) tensor; pays off from a few thousand rows (tools/microbench.py)
-            from tome import _native
-            if _native.linear_gelu_supported(x, self.fc1.weight, self.fc1.bias):
-                return self.drop(self.fc2(_native.linear_gelu(x, self.fc1.weight, self.fc1.bias)))
-        return self.drop(self.fc2(self.act(self.fc1(x))))
+        h = fused_fc1_gelu(self, x)
+        return self.drop(self.fc2(h if h is not None else self.act(self.fc1(x))))
+
+
+def fused_fc1_gelu(mlp, x):
+    """``act(fc1(x))`` of an fc1 -> nn.GELU (erf) -> fc2 MLP from ONE tcgen05 GEMM with bias and activation in its
+    epilogue (``tome_linear_gelu``) instead of a library GEMM plus an elementwise pass over the (tokens, 4C)
+    tensor.  CUDA bf16 inference only, from a few thousand rows (tools/microbench.py); None otherwise."""
+    if (not mlp.training and x.is_cuda and x.dtype == torch.bfloat16 and isinstance(mlp.act, nn.GELU)
+            and mlp.act.approximate == "none" and x.numel() // x.shape[-1] >= FUSED_MLP_MIN_ROWS):
+        from tome import _native
+        if _native.linear_gelu_supported(x, mlp.fc1.weight, mlp.fc1.bias):
+            return _native.linear_gelu(x, mlp.fc1.weight, mlp.fc1.bias)
+    return None
 
 
 class Attention(nn.Module):                             # builder:59-103
