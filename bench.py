@@ -70,22 +70,52 @@ def dist_env():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md), sampled every few ms through
+    NVML from a thread (the timed region of a default run is ~70 ms: nvidia-smi's own polling loop is too slow
+    to land a sample in it); falls back to `nvidia-smi -lms` when NVML is unavailable."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index):
         self.gpu_index, self.rows, self.proc = gpu_index, [], None
+        self.samples, self.max_mhz, self.stop_flag, self.thread, self.source = [], None, False, None, None
+
+    def _nvml_loop(self, nv, handle):
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                self.samples.append((float(mhz), int(get(handle))))
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def __enter__(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(self.gpu_index).uuid)
+            try:
+                handle = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                handle = nv.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.source = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            self.source = "nvidia-smi"
         except Exception:
             self.proc = None
         return self
@@ -95,6 +125,9 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def __exit__(self, *a):
+        self.stop_flag = True
+        if self.source == "nvml" and self.thread is not None:
+            self.thread.join(timeout=1)
         if self.proc is not None:
             time.sleep(0.15)
             self.proc.terminate()
@@ -104,7 +137,12 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
+        sm, mx, reasons = [], self.max_mhz or 0, set()
+        for mhz, mask in self.samples:
+            sm.append(mhz)
+            for name, bit in self.BITS.items():
+                if mask & bit:
+                    reasons.add(name)
         for row in self.rows:
             f = [s.strip() for s in row.split(",")]
             if len(f) < 8:
@@ -118,7 +156,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": self.source}
 
 
 def build_videomae(device, dtype, args):
