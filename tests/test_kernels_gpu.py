@@ -583,3 +583,26 @@ def test_linear_gelu_matches_linear_then_gelu(native, shape, gelu):
     assert (got - lib).abs().max().item() <= 4e-2
     got3 = native.linear_gelu(x.reshape(1, m, k), w, None, gelu=gelu)
     assert got3.shape == (1, m, n)
+
+
+def test_side_stream_matching_gives_the_same_plan(native, monkeypatch):
+    """tome.merge.prefetch_matching (TOME_PREFETCH=1: kernels 1 + 2 on a side stream as soon as K exists) hands
+    bipartite_soft_matching the same plan as the in-line path, for the same (r, class token) request only."""
+    import tome
+    gen = torch.Generator(device="cuda").manual_seed(10)
+    k = torch.randn(2, 197, 3, 12, 64, device="cuda", generator=gen).to(torch.bfloat16).permute(2, 0, 3, 1, 4)[1]
+    base, _ = tome.merge.bipartite_soft_matching(native.HeadMeanMetric(k), 40, True)
+    monkeypatch.setenv("TOME_PREFETCH", "1")
+    with torch.no_grad():
+        m = native.HeadMeanMetric(k)
+        tome.merge.prefetch_matching(m, 40, True)
+        assert m.prefetched is not None
+        pre, _ = tome.merge.bipartite_soft_matching(m, 40, True)
+        assert m.prefetched is None
+        m2 = native.HeadMeanMetric(k)
+        tome.merge.prefetch_matching(m2, 40, True)
+        other, _ = tome.merge.bipartite_soft_matching(m2, 30, True)      # different r: the parked plan is not used
+    torch.cuda.synchronize()
+    for name in ("src_idx", "unm_idx", "dst_idx", "b_head"):
+        assert torch.equal(getattr(pre.plan, name), getattr(base.plan, name)), name
+    assert other.plan.r == 30
