@@ -71,6 +71,9 @@ linear_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_w);
+    prefetch_tensormap(&map_o);
     for (int s = 0; s < LG_STAGES; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, LG_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

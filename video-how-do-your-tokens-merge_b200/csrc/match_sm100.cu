@@ -252,6 +252,8 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   volatile int* is_last_ptr = reinterpret_cast<volatile int*>(gen_base + (tmem_slot + 4u - base));
 
   if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
     for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
     mbar_init(bar_tmem, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
