@@ -377,6 +377,14 @@ def micro_kernels(args, device, dtype):
 MERGE_DRAM_TRAFFIC_NCU = {(8, "bf16"): 38726912 + 1131264}
 
 
+# share of one step's kernel time per kernel, from the committed ncu launch list of this command
+# (profiles/r01e_launch_summary.txt; cold-cache and serialised, so shares, not absolutes)
+STEP_SHARES_NCU = {"source": "profiles/r01e_launch_summary.txt", "cuBLAS GEMMs": 0.307, "cuDNN attention": 0.230,
+                   "linear_gelu_kernel": 0.185, "match_tc_kernel": 0.065, "merge_gather_kernel<LN,RES>": 0.062,
+                   "add_layernorm_kernel": 0.049, "split_rows_kernel": 0.032, "rank_kernel": 0.024, "finish_kernel": 0.023,
+                   "patchify_kernel": 0.011, "libtome_b200 total": 0.451}
+
+
 def run_ours(args):
     rank, local, world = dist_env()
     if not torch.cuda.is_available():
@@ -526,7 +534,13 @@ def run_ours(args):
                     "note": "pinned fp32 clips -> H2D on a copy stream (double-buffered) -> bf16 cast + forward -> logits D2H"},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+            "roofline": roofline,
+            # the caller-side tensor-core kernel (fc1 + GELU), the largest single kernel of libtome_b200 in the step
+            "roofline_tensor": (dict(kernels["linear_gelu"]["roofline"], kernel=kernels["linear_gelu"]["kernels"],
+                                     us_mean=kernels["linear_gelu"]["us_mean"])
+                                if kernels and "linear_gelu" in kernels else None),
+            "step_shares_ncu": STEP_SHARES_NCU,
+            "kernels": kernels, "cpu_baseline": cpu_baseline,
             "match_algo": "auto" if not args.match_algo else args.match_algo,
             "top1_sample": top1[:4].tolist(),
         }

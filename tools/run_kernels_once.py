@@ -21,5 +21,12 @@ for i in range(6):
     plan = _native.plan_build(_native.HeadMeanMetric(ks[i % 4]), r)
     out = _native.merge(plan, xs[i], "wavg", want_size=True)
     out2 = _native.merge(plan, xs[i + 6], "wavg", want_size=True, norm=(w, b, 1e-6), residual=rs[i])
+# the MLP's first half (fc1 + bias + erf GELU, one tcgen05 GEMM) on the merged tokens
+xm = torch.randn(bm * (n - r), c, device="cuda", dtype=dt, generator=g)
+w1 = (torch.randn(4 * c, c, device="cuda", generator=g) * c ** -0.5).to(dt)
+b1 = torch.zeros(4 * c, device="cuda", dtype=dt)
+if dt == torch.bfloat16:
+    for i in range(3):
+        h = _native.linear_gelu(xm, w1, b1)
 torch.cuda.synchronize()
 print("ok")

@@ -21,11 +21,11 @@
 
 namespace tome {
 
-constexpr int LG_BM = 128, LG_BN = 256, LG_BK = 64, LG_STAGES = 3;
+constexpr int LG_BM = 128, LG_BN = 256, LG_BK = 64, LG_STAGES = 4;
 constexpr int LG_EPI_WARPS = 16;                      // four per TMEM lane quarter, 64 columns each
 constexpr int LG_THREADS = 64 + 32 * LG_EPI_WARPS;    // TMA, MMA, epilogue warps
 constexpr uint32_t LG_A_BYTES = LG_BM * 128u, LG_B_BYTES = LG_BN * 128u, LG_STAGE_BYTES = LG_A_BYTES + LG_B_BYTES;
-constexpr uint32_t LG_OBOX_BYTES = 32u * 128u;        // one epilogue warp's output box: 32 rows x 64 bf16 columns
+constexpr uint32_t LG_OBOX_BYTES = 32u * 64u;         // one epilogue warp's output box: 32 rows x 32 bf16 columns (SWIZZLE_64B)
 
 struct LinearGeluParams {
   int m, n, k, num_kb, tiles_n, tiles;
@@ -63,7 +63,7 @@ linear_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t obox = base + LG_STAGES * LG_STAGE_BYTES;             // one 4 KB box per epilogue warp, 1024-byte aligned
+  const uint32_t obox = base + LG_STAGES * LG_STAGE_BYTES;             // one 2 KB box per epilogue warp
   const uint32_t bars = obox + (uint32_t)LG_EPI_WARPS * LG_OBOX_BYTES;
   const uint32_t bar_full = bars, bar_empty = bars + 8u * LG_STAGES;
   const uint32_t bar_tfull = bars + 16u * LG_STAGES, bar_tempty = bar_tfull + 16u;
@@ -140,16 +140,14 @@ linear_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * (uint32_t)LG_BN + (uint32_t)(part * 64) + ((uint32_t)(q * 32) << 16);
       const __nv_bfloat16* brow = p.bias ? p.bias + nt * LG_BN + part * 64 : nullptr;
-      // the previous TMA store out of this warp's box must have finished READING shared memory
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncwarp();
       float vv[2][32];                                 // both 32-column chunks in flight: one TMEM round trip per tile
       tmem_ld32_nowait(taddr, vv[0]);
       tmem_ld32_nowait(taddr + 32u, vv[1]);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {                    // two 32-column chunks = one 64-column box
+      for (int c = 0; c < 2; ++c) {                    // two 32-column chunks, one 2 KB box and one TMA store each
         float (&v)[32] = vv[c];
+        uint4 packed[4];
 #pragma unroll
         for (int g4 = 0; g4 < 4; ++g4) {
           float bf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -171,19 +169,26 @@ linear_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
             w[i] = *reinterpret_cast<const uint32_t*>(&h);
           }
-          // row = lane, 16-byte chunk j of the 128-byte box row, SWIZZLE_128B: chunk ^ (row & 7)
-          const uint32_t j = (uint32_t)(c * 4 + g4);
-          const uint32_t dst = mybox + (uint32_t)lane * 128u + ((j ^ ((uint32_t)lane & 7u)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+          packed[g4] = make_uint4(w[0], w[1], w[2], w[3]);
         }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA engine
-      __syncwarp();
-      if (lane == 0) {
-        const int col = nt * LG_BN + part * 64, row0 = mt * LG_BM + q * 32;
-        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                     ::"l"(&map_o), "r"(col), "r"(row0), "r"(mybox) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // the previous TMA store out of this warp's box must have finished READING shared memory
+        // (waited for only now: the arithmetic above ran beside it)
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) {
+          // row = lane, 16-byte chunk g4 of the 64-byte box row, SWIZZLE_64B: chunk ^ ((row >> 1) & 3)
+          const uint32_t dst = mybox + (uint32_t)lane * 64u + ((((uint32_t)g4) ^ (((uint32_t)lane >> 1) & 3u)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[g4].x), "r"(packed[g4].y), "r"(packed[g4].z), "r"(packed[g4].w) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          const int col = nt * LG_BN + part * 64 + c * 32, row0 = mt * LG_BM + q * 32;
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                       ::"l"(&map_o), "r"(col), "r"(row0), "r"(mybox) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -211,7 +216,7 @@ int launch_linear_gelu(const void* x, const void* w, const void* bias, int m, in
   rc = make_bf16_map(&map_w, w, n, k, k, LG_BN, "tome_linear_gelu");
   if (rc) return rc;
   alignas(64) CUtensorMap map_o;
-  rc = make_bf16_map(&map_o, out, m, n, n, 32, "tome_linear_gelu");
+  rc = make_bf16_map(&map_o, out, m, n, n, 32, "tome_linear_gelu", 32);
   if (rc) return rc;
   LinearGeluParams p;
   p.m = m; p.n = n; p.k = k; p.num_kb = (k + LG_BK - 1) / LG_BK;

@@ -133,15 +133,16 @@ inline EncodeTiledFn get_encode_tiled() {
 
 // 2-D bf16 tensor (rows, cols) with unit column stride, boxes of 64 columns (one 128-byte swizzle row) x box_rows.
 inline int make_bf16_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long row_stride_elems,
-                         int box_rows, const char* who) {
+                         int box_rows, const char* who, int box_cols = 64) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return set_error(TOME_ERR_CUDA, "%s: cuTensorMapEncodeTiled is not available from the driver", who);
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)row_stride_elems * sizeof(__nv_bfloat16)};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};      // 64 columns: SWIZZLE_128B rows; 32: SWIZZLE_64B
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(TOME_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed with CUresult %d", who, (int)r);
   return TOME_OK;
