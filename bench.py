@@ -475,6 +475,22 @@ def run_ours(args):
         main = torch.cuda.current_stream()
         copied = [torch.cuda.Event() for _ in range(2)]
         consumed = [torch.cuda.Event() for _ in range(2)]
+        # one captured forward per staging buffer, reading the fp32 clips where the H2D copy put them: the cast to the
+        # model dtype happens inside tome_patchify, so there is no separate device-side cast / copy pass
+        e2e_graphs, e2e_outs = [None, None], [None, None]
+        if graph is not None:
+            for j in range(2):
+                stage[j].copy_(host_in[j])
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    model([stage[j]])
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                e2e_graphs[j] = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(e2e_graphs[j]):
+                    e2e_outs[j] = model([stage[j]]).float()
+            torch.cuda.synchronize()
 
         def e2e_loop(k):
             for i in range(k + 1):
@@ -487,13 +503,12 @@ def run_ours(args):
                 if i >= 1:                    # run step i-1
                     j = i - 1
                     main.wait_event(copied[j % 2])
-                    static_in.copy_(stage[j % 2])          # fp32 -> model dtype on device
-                    consumed[j % 2].record(main)
                     if graph is not None:
-                        graph.replay()
-                        o = static_out
+                        e2e_graphs[j % 2].replay()
+                        o = e2e_outs[j % 2]
                     else:
-                        o = forward()
+                        o = model([stage[j % 2]]).float()
+                    consumed[j % 2].record(main)
                     if world > 1:
                         torch.distributed.all_gather_into_tensor(logits_all, o)
                     host_out.copy_(o, non_blocking=True)
@@ -531,7 +546,7 @@ def run_ours(args):
             "clocks": clocks.summary(),
             "e2e": {"value": total_clips / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": B * NUM_CLASSES * 4, "ms_per_step": ms_e2e / args.steps,
-                    "note": "pinned fp32 clips -> H2D on a copy stream (double-buffered) -> bf16 cast + forward -> logits D2H"},
+                    "note": "pinned fp32 clips -> H2D on a copy stream (double-buffered) -> forward (tome_patchify casts to bf16) -> logits D2H"},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "roofline": roofline,
