@@ -606,3 +606,43 @@ def test_side_stream_matching_gives_the_same_plan(native, monkeypatch):
     for name in ("src_idx", "unm_idx", "dst_idx", "b_head"):
         assert torch.equal(getattr(pre.plan, name), getattr(base.plan, name)), name
     assert other.plan.r == 30
+
+
+@pytest.mark.parametrize("cm", [64, 256])
+@pytest.mark.parametrize("cls", [False, True])
+def test_zero_norm_tokens_give_nan_like_the_reference(native, cls, cm):
+    """The reference has no eps in its normalisation (merge.py:51): a zero metric row becomes NaN, NaN wins every
+    max it takes part in (first NaN column) and sorts above +inf.  The tensor-core path used to HANG on such a
+    row (a lane-divergent tcgen05.ld); it must give the oracle's bits, as the exact SIMT path does.  Seen in the
+    wild: HuggingFace-initialised ViViT has a zero class token and zero position embeddings."""
+    import warnings
+    gen = torch.Generator().manual_seed(11)
+    metric = torch.randn(2, 300, cm, generator=gen)
+    metric[0, 0] = 0          # an A token (the class token when cls)
+    metric[0, 7] = 0          # a B token: every A row of batch 0 sees a NaN in column 3
+    metric[1, 10] = 0         # an A token that is not the class token
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        onm, oni = O.match(metric.numpy(), cls, False)
+    for algo in (1, 2):
+        nm, ni = native.match(metric.cuda(), cls, False, algo=algo)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(ni.cpu().numpy(), oni)
+        np.testing.assert_array_equal(np.isnan(nm.cpu().numpy()), np.isnan(onm))
+        ok = ~np.isnan(onm)
+        np.testing.assert_array_equal(nm.cpu().numpy()[ok], onm[ok])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        plan = O.bipartite_soft_matching(metric.numpy(), 40, cls, False)
+    dp = native.plan_build(metric.cuda(), plan.r, cls, False)
+    np.testing.assert_array_equal(dp.src_idx.cpu().numpy(), plan.src_idx)
+    np.testing.assert_array_equal(dp.unm_idx.cpu().numpy(), plan.unm_idx)
+    np.testing.assert_array_equal(dp.dst_idx.cpu().numpy(), plan.dst_idx)
+    # and through the lazy head-mean path (bf16 K with a zero token)
+    k = torch.randn(2, 197, 3, 12, 64, generator=gen).to(torch.bfloat16)
+    k[:, 0, 1] = 0
+    kd = k.cuda().permute(2, 0, 3, 1, 4)[1]
+    nm2, ni2 = native.match_heads(native.HeadMeanMetric(kd), cls, False)
+    nm3, ni3 = native.match(kd.float().mean(1).to(torch.bfloat16).contiguous(), cls, False, algo=1)
+    torch.cuda.synchronize()
+    assert torch.equal(ni2, ni3) and torch.equal(torch.isnan(nm2), torch.isnan(nm3))

@@ -362,7 +362,10 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     for (int ch = 0; ch < MAXCH; ++ch) {
       const int c = ch * 32;
       uint32_t bm_ = 0u;
-      if (c < ncol && !has_nan) {              // warp-uniform
+      // warp-uniform condition only: tcgen05.ld is .sync.aligned, every lane must execute it.  (A per-lane
+      // `!has_nan` here hung the kernel as soon as one row of the strip was NaN -- a zero-norm token.)  With a NaN
+      // threshold every comparison below is false, so a NaN row gets no candidates and goes the overflow way.
+      if (c < ncol) {
         if (c + 32 <= ncol) {
           float v[32];
           tmem_ld32(taddr + (uint32_t)c, v);
