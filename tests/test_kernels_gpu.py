@@ -646,3 +646,25 @@ def test_zero_norm_tokens_give_nan_like_the_reference(native, cls, cm):
     nm3, ni3 = native.match(kd.float().mean(1).to(torch.bfloat16).contiguous(), cls, False, algo=1)
     torch.cuda.synchronize()
     assert torch.equal(ni2, ni3) and torch.equal(torch.isnan(nm2), torch.isnan(nm3))
+
+
+@pytest.mark.parametrize("cls", [False, True])
+def test_tiny_token_counts_down_to_two(native, cls):
+    """The ViViT r sweep (experiments.sh:395-428) drives the token count down to 2-3 in the last layers: every n
+    from 2 up, r clamped to its maximum, through tome_plan_build and the merge, against the oracle."""
+    gen = torch.Generator().manual_seed(12)
+    for n in (2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 65):
+        metric = torch.randn(3, n, 64, generator=gen)
+        x = torch.randn(3, n, 32, generator=gen)
+        plan = O.bipartite_soft_matching(metric.numpy(), 10 ** 6, cls, False)
+        if plan is None or plan.r <= 0:
+            continue
+        dp = native.plan_build(metric.cuda(), plan.r, cls, False)
+        np.testing.assert_array_equal(dp.node_idx.cpu().numpy(), plan.node_idx, err_msg=f"n={n}")
+        np.testing.assert_array_equal(dp.src_idx.cpu().numpy(), plan.src_idx, err_msg=f"n={n}")
+        np.testing.assert_array_equal(dp.unm_idx.cpu().numpy(), plan.unm_idx, err_msg=f"n={n}")
+        np.testing.assert_array_equal(dp.dst_idx.cpu().numpy(), plan.dst_idx, err_msg=f"n={n}")
+        out, so, _ = native.merge(dp, x.cuda(), "wavg", want_size=True)
+        want, want_s = O.merge_wavg(plan, x.numpy(), None)
+        np.testing.assert_array_equal(out.cpu().numpy(), want, err_msg=f"n={n}")
+        np.testing.assert_array_equal(so.cpu().numpy(), want_s.reshape(so.shape), err_msg=f"n={n}")
