@@ -41,11 +41,18 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--models", default="videomae,timesformer,motionformer,vivit")
+    ap.add_argument("--r", type=int, default=None, help="override the ToMe r of every model")
+    ap.add_argument("--schedule", type=float, default=0.0, help="r inflection (-1 decreasing, 0 constant, +1 increasing)")
+    ap.add_argument("--mode", default=None, help="merge | drop | hybrid | random_merge | random_drop")
     a = ap.parse_args()
     dev = torch.device("cuda")
     out = {}
     for name in a.models.split(","):
         build, frames, r, kw = CONFIGS[name]
+        if a.r is not None:
+            r = (a.r, a.schedule)
+        if a.mode is not None:
+            kw = dict(kw, mode=a.mode, threshold=0.6)
         torch.manual_seed(0)
         model = build().eval()
         if name == "motionformer":            # as constructed every frame embeds identically (zeroed 3-D patch weight,
