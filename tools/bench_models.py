@@ -63,7 +63,18 @@ def main():
         res = {}
         with torch.no_grad():
             res["plain_ms"] = timed(lambda: model([clip]), a.iters)
-            print(name, "plain", res["plain_ms"], flush=True)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                model([clip])
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g0 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g0):
+                static0 = model([clip])
+            res["plain_graph_ms"] = timed(g0.replay, a.iters)
+            del g0, static0
+            print(name, "plain", res["plain_ms"], res["plain_graph_ms"], flush=True)
             getattr(tome.patch, name)(model, **kw)
             model.r = r
             logits = model([clip]).float()
@@ -84,7 +95,7 @@ def main():
             res["tome_graph_ms"] = timed(g.replay, a.iters)
             same = (static.float().argmax(-1) == logits.argmax(-1)).float().mean().item()
             res["graph_top1_agree"] = same
-        for k in ("plain_ms", "tome_ms", "tome_graph_ms"):
+        for k in ("plain_ms", "plain_graph_ms", "tome_ms", "tome_graph_ms"):
             res[k.replace("_ms", "_clips_per_s")] = a.batch / res[k] * 1e3
         out[name] = res
         print(name, json.dumps(res), flush=True)
