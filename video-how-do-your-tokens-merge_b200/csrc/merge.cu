@@ -604,7 +604,6 @@ int launch_merge(const tome_plan* plan, const void* x, int dtype, int c, const V
   a.hybrid = (thr == thr) ? 1 : 0; a.thr = thr; a.node_max = plan->node_max;
   a.unm_idx = plan->unm_idx; a.b_off = plan->b_off; a.b_src = plan->b_src; a.b_head = plan->b_head;
   a.x = x; a.xv = xv; a.size_in = size_in; a.out = out; a.ov = ov; a.size_out = size_out; a.logsize_out = logsize_out;
-  const int variant = getenv("TOME_MERGE_VARIANT") ? atoi(getenv("TOME_MERGE_VARIANT")) : 0;   // tuning knob
   if (dtype == TOME_F32) {
     const bool vec = c % 4 == 0 && aligned16(x) && aligned16(out) && view_vec_ok(xv, 4) && view_vec_ok(ov, 4);
     if (!vec && normed) return set_error(TOME_ERR_ALIGN, "tome_merge_norm: fused LayerNorm needs 16-byte aligned rows (c %% 4 == 0)");
@@ -612,9 +611,7 @@ int launch_merge(const tome_plan* plan, const void* x, int dtype, int c, const V
     if (normed && (c > 4 * 32 * 8 || !aligned16(ln_w) || (ln_b && !aligned16(ln_b)) || !aligned16(normed) || !view_vec_ok(a.nv, 4)))
       return set_error(TOME_ERR_UNSUPPORTED, "tome_merge_norm: c=%d too wide or LayerNorm buffers misaligned", c);
     if (!vec) return launch_merge_scalar<float>(a, st);
-    if (variant == 1) return launch_merge_gather<float, 8, 3>(a, st);
-    if (variant == 2) return launch_merge_gather<float, 8, 2>(a, st);
-    if (residual && variant == 0) return launch_merge_gather<float, 4, 4>(a, st);
+    if (residual) return launch_merge_gather<float, 4, 4>(a, st);      // two input rows per output row: more registers
     return launch_merge_gather<float, 4, 6>(a, st);
   } else if (dtype == TOME_BF16) {
     const bool vec = c % 8 == 0 && aligned16(x) && aligned16(out) && view_vec_ok(xv, 8) && view_vec_ok(ov, 8);
@@ -623,8 +620,6 @@ int launch_merge(const tome_plan* plan, const void* x, int dtype, int c, const V
     if (normed && (c > 8 * 32 * 8 || !aligned16(ln_w) || (ln_b && !aligned16(ln_b)) || !aligned16(normed) || !view_vec_ok(a.nv, 8)))
       return set_error(TOME_ERR_UNSUPPORTED, "tome_merge_norm: c=%d too wide or LayerNorm buffers misaligned", c);
     if (!vec) return launch_merge_scalar<__nv_bfloat16>(a, st);
-    if (variant == 1) return launch_merge_gather<__nv_bfloat16, 8, 4>(a, st);     // the first shipped shape: 256-thread CTAs
-    if (variant == 2) return launch_merge_gather<__nv_bfloat16, 8, 3>(a, st);
     // 64-thread CTAs at <= 85 registers: a CTA retires with its slowest warp, so small CTAs keep the copy warps
     // from queueing behind the few reducing ones, and the two-input (residual) rows do not spill.
     // merge 7.6 -> 7.3 us, + LayerNorm 12.5 -> 11.7, + residual 20.6 -> 15.6 (profiles/r01_merge_notes.md)
