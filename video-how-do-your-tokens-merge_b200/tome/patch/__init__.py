@@ -1,12 +1,14 @@
-"""Same names as the reference's tome/patch/__init__.py:1-11."""
-from .vivit import apply_patch as vivit
-from .vivit import apply_duplicate_patch as duplicate_vivit
-from .timesformer import apply_patch as timesformer
-from .timesformer import apply_duplicate_patch as duplicate_timesformer
-from .motionformer import apply_patch as motionformer
-from .motionformer import apply_duplicate_patch as duplicate_motionformer
-from .videomae import apply_patch as videomae
-from .videomae import apply_duplicate_patch as duplicate_videomae
+"""``tome.patch.<model>(model)`` and ``tome.patch.duplicate_<model>(model, layer, quantity)`` for the four
+video transformers -- the public names of the reference's tome/patch package, bound to the sm_100a path."""
+from . import motionformer as _motionformer
+from . import timesformer as _timesformer
+from . import videomae as _videomae
+from . import vivit as _vivit
 
-__all__ = ['vivit', 'duplicate_vivit', 'timesformer', 'duplicate_timesformer',
-           'motionformer', 'duplicate_motionformer', 'videomae', 'duplicate_videomae']
+_MODELS = {"videomae": _videomae, "timesformer": _timesformer, "motionformer": _motionformer, "vivit": _vivit}
+__all__ = []
+for _name, _module in _MODELS.items():
+    globals()[_name] = _module.apply_patch
+    globals()["duplicate_" + _name] = _module.apply_duplicate_patch
+    __all__ += [_name, "duplicate_" + _name]
+del _name, _module
