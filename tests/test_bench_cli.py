@@ -26,7 +26,7 @@ def test_our_arm_refuses_to_run_without_a_gpu():
 
 
 def test_committed_bench_lines_carry_the_contract_keys():
-    for name in ("r01e_bench_n1.json", "r01e_bench_n2.json", "r01e_bench_n4.json"):
+    for name in ("r01e_bench_n1.json", "r01e_bench_n2.json", "r01e_bench_n4.json", "r01e_bench_n8.json"):
         d = json.load(open(os.path.join(ROOT, "profiles", name)))
         for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                     "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches"):
