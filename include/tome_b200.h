@@ -53,7 +53,7 @@ typedef enum tome_dtype { TOME_F32 = 0, TOME_BF16 = 1 } tome_dtype;
 typedef enum tome_match_algo {
   TOME_MATCH_AUTO = 0,
   TOME_MATCH_EXACT_SIMT = 1,  /* fp64 CUDA-core tiles; any shape                          */
-  TOME_MATCH_TCGEN05 = 2      /* 3xTF32 tcgen05/TMEM pass + exact fp64 candidate refine   */
+  TOME_MATCH_TCGEN05 = 2      /* bf16 h.h+h.m+m.h tcgen05/TMEM pass + exact fp64 refine    */
 } tome_match_algo;
 
 /* tome_merge reduction (merge.py:75 `mode`, plus the fused / drop forms). */
