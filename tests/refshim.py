@@ -121,3 +121,50 @@ def build_reference_motionformer(num_classes, num_frames, depth=12):
                           ATTN_DROPOUT=0.0, POS_EMBED="separate", ATTN_LAYER="trajectory",
                           USE_ORIGINAL_TRAJ_ATTN_CODE=True, APPROX_ATTN_TYPE="none", APPROX_ATTN_DIM=128))
     return mb.Motionformer(cfg)
+
+
+def build_reference_vivit(num_classes, num_frames=32, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                          intermediate_size=3072):
+    """The reference's ViViT wrapper + the installed HuggingFace modules, given back the pre-4.4x layer API the
+    reference patch (tome/patch/vivit.py:17-130) was written against.  Nothing of the reference is re-stated:
+    ``ViViT.forward`` (vivit_video_model_builder.py:33-60) and the whole tome patch run as they lie; the shim only
+      * builds ``VivitConfig`` by keyword (builder:17 passes it positionally, which transformers 5.5 rejects; the
+        values are configs/vivit/kinetics/tome_vivit_8x32_224.json's),
+      * gives ``VivitSelfAttention`` the ``transpose_for_scores`` / ``dropout`` members the patch calls (vivit.py:93-110),
+      * runs the encoder as the old API did: ``layer(hidden_states, head_mask, output_attentions)[0]``.
+    Call inside ``reference_modules()``."""
+    import slowfast.models.vivit_video_model_builder as vb
+    from transformers import VivitConfig, VivitModel
+    from transformers.modeling_outputs import BaseModelOutput
+    from transformers.models.vivit.modeling_vivit import VivitEncoder, VivitSelfAttention
+
+    class OldApiEncoder(VivitEncoder):
+        def forward(self, hidden_states, **kwargs):
+            for layer_module in self.layer:
+                if hasattr(layer_module, "_tome_info"):       # patched: the old tuple-returning signature
+                    hidden_states = layer_module(hidden_states, None, False)[0]
+                else:
+                    hidden_states = layer_module(hidden_states)
+            return BaseModelOutput(last_hidden_state=hidden_states)
+
+    def transpose_for_scores(self, x):
+        return x.view(x.size()[:-1] + (self.num_attention_heads, self.attention_head_size)).permute(0, 2, 1, 3)
+
+    class ShimViViT(vb.ViViT):
+        def __init__(self):
+            config = VivitConfig(image_size=224, num_frames=num_frames, tubelet_size=[2, 16, 16], num_channels=3,
+                                 hidden_size=hidden_size, num_hidden_layers=num_hidden_layers,
+                                 num_attention_heads=num_attention_heads, intermediate_size=intermediate_size,
+                                 hidden_act="gelu_fast", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                                 initializer_range=0.02, layer_norm_eps=1e-6, qkv_bias=True)
+            vb.VivitPreTrainedModel.__init__(self, config)
+            self.num_labels = num_classes
+            self.vivit = VivitModel(config, add_pooling_layer=False)
+            self.classifier = torch.nn.Linear(config.hidden_size, num_classes)
+            self.vivit.encoder.__class__ = OldApiEncoder
+            for m in self.vivit.modules():
+                if isinstance(m, VivitSelfAttention):
+                    m.dropout = torch.nn.Dropout(m.dropout_prob)
+                    m.transpose_for_scores = types.MethodType(transpose_for_scores, m)
+
+    return ShimViViT()

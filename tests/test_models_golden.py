@@ -4,8 +4,11 @@ weights are rebuilt from the same seeded stream.
 
   * CPU (`-m "not gpu"`): host models + our tome.patch host logic with the merge calls routed to
     oracle/torch_port.py.
-  * GPU (`-m gpu`): the same models with the sm_100a kernels, fp32 (1e-5-class agreement unless a
-    near-tie flips, bounded below) and bf16 (1e-2, top-1 identical) -- the north_star tolerances."""
+  * GPU (`-m gpu`): the same models with the sm_100a kernels, free-running: fp32 within 1e-5 relative and
+    top-1 identical (the north_star bar; no near-tie flips on these seeds), bf16 top-1 identical and within the
+    bound below (these toy models use 0.08-std weights, four times a real initialisation, which makes bf16
+    attention noisier than ViT-B: the 1e-2 bf16 bar is asserted at full size in tests/test_fullsize_parity.py).
+All four architectures, ViViT included (reference patch run through tests/refshim.py::build_reference_vivit)."""
 import contextlib
 import importlib.util
 import os
@@ -20,6 +23,9 @@ _spec = importlib.util.spec_from_file_location("make_model_golden", os.path.join
 G = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(G)
 GOLD = dict(np.load(os.path.join(HERE, "golden", "models.npz")))
+
+
+BF16_TOY_TOL = 3e-2      # toy widths with 0.08-std weights; the 1e-2 bar is asserted on ViT-B (test_fullsize_parity.py)
 
 
 @contextlib.contextmanager
@@ -75,9 +81,7 @@ def test_cuda_path_fp32_vs_reference_goldens(case):
     gold = GOLD[case["name"] + "/tome"]
     err = np.abs(merged.numpy() - gold).max() / max(np.abs(gold).max(), 1e-6)
     print(f"[model-parity] {case['name']}: max rel err fp32 = {err:.2e}")
-    # GPU attention / GEMM rounding differs from the CPU reference in the last ulps, which can flip a
-    # near-tied match; everything else must agree to fp32 round-off
-    assert err < 2e-3, err
+    assert err < 1e-5, err                      # north_star: 1e-5 relative in fp32
     assert (merged.argmax(-1).numpy() == gold.argmax(-1)).all()
     assert size.shape == GOLD[case["name"] + "/size"].shape
     assert float(size.sum()) == float(GOLD[case["name"] + "/size"].sum()) or case["kw"].get("mode") in ("hybrid", "drop")
@@ -85,20 +89,22 @@ def test_cuda_path_fp32_vs_reference_goldens(case):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", [c for c in G.MODEL_CASES if c["name"] in ("videomae_merge", "videomae_propattn_dec", "videomae_hybrid", "timesformer_merge",
-                                                                       "timesformer_hybrid", "motionformer_merge")],
+                                                                       "timesformer_hybrid", "motionformer_merge", "vivit_merge",
+                                                                       "vivit_hybrid")],
                          ids=lambda c: c["name"])
 def test_cuda_path_bf16_within_tolerance(case):
     plain, merged, size = _run(case, "cuda", torch.bfloat16, contextlib.nullcontext())
     gold = GOLD[case["name"] + "/tome"]
     err = np.abs(merged.numpy() - gold).max() / max(np.abs(gold).max(), 1e-6)
     print(f"[model-parity] {case['name']}: max rel err bf16 = {err:.2e}")
-    assert err < 3e-2, err
+    assert err < BF16_TOY_TOL, err
+    assert (merged.argmax(-1).numpy() == gold.argmax(-1)).all()
 
 
 @pytest.mark.gpu
 def test_vivit_cuda_vs_cpu_port_and_hf():
-    """ViViT has no runnable reference here (parity unpinned): check the host model
-    against HuggingFace's own VivitModel and the CUDA ToMe path against the CPU port."""
+    """ViViT beyond the reference-made goldens (vivit_* cases above): the host model against HuggingFace's own
+    VivitModel (installed transformers), and the CUDA ToMe path against the CPU port on more settings."""
     import hostmodels
     import tome
     torch.manual_seed(0)
