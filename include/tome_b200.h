@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 12
+#define TOME_ABI_VERSION 13
 
 #if defined(__GNUC__)
 #define TOME_API __attribute__((visibility("default")))
@@ -46,6 +46,9 @@ typedef enum tome_status {
   TOME_ERR_ARCH = -6,         /* device is not compute capability 10.x                   */
   TOME_ERR_UNSUPPORTED = -7   /* valid request this build cannot serve                   */
 } tome_status;
+
+/* Largest matching batch (clips, or clips * frames) one call takes: it rides on gridDim.y / gridDim.z. */
+#define TOME_MAX_BATCH 65535
 
 typedef enum tome_dtype { TOME_F32 = 0, TOME_BF16 = 1 } tome_dtype;
 
@@ -242,6 +245,28 @@ TOME_API int tome_linear_gelu(const void* x, const void* w, const void* bias, in
 /* unmerge (merge.py:87-100): x (bm, n - r, c) -> out (bm, n, c); contiguous tensors. */
 TOME_API int tome_unmerge(const tome_plan* plan, const void* x, int32_t dtype, int32_t c, void* out,
                  void* stream);
+
+/* --- matching between two arbitrary token sets --------------------------------------------------------
+ * The upstream-ToMe variants the reference keeps: kth_bipartite_soft_matching (tome/merge.py:105-158: every
+ * k-th token is a destination, the rest are sources) and random_bipartite_soft_matching (merge.py:161-212: r
+ * random sources).  tok_of_row (int32, batch element b at tok_of_row + b * tok_stride_b; stride 0 = shared)
+ * lists token indices: rows [0, ra) the A / source set, rows [ra, ra + nb) the B / destination set.
+ * tome_match_sets: canonical scores (as tome_match) of every A row against every B row; node_max / node_idx
+ *   (bm, ra): best B ROW per A row, lowest on ties (merge.py:135 / 190 `scores.max(dim=-1)`).
+ * tome_group_reduce: out (bm, nb, c) contiguous = every B row reduced with the A rows assigned to it by
+ *   dst_idx (bm, ra), include_self, in the reference CPU order (itself, then ascending k), fp32 arithmetic
+ *   -- `dst.scatter_reduce(-2, dst_idx, src, reduce=mode)`, merge.py:141 / 196.  mode: SUM, MEAN or AMAX.
+ * tome_gather_rows: out[b, t] = x[b, map[b, t]] (zeros where map < 0) -- the unmerge of both variants
+ *   (merge.py:145-156, 200-210) once the caller has composed the row map. */
+TOME_API size_t tome_match_sets_workspace_bytes(int32_t bm, int32_t ra, int32_t nb, int32_t cm);
+TOME_API int tome_match_sets(const void* metric, int32_t dtype, int32_t bm, int32_t n, int32_t cm, const tome_view* view,
+                    const int32_t* tok_of_row, int64_t tok_stride_b, int32_t ra, int32_t nb, float* node_max,
+                    int32_t* node_idx, void* workspace, size_t workspace_bytes, void* stream);
+TOME_API int tome_group_reduce(const void* x, int32_t dtype, int32_t bm, int32_t n, int32_t c, const tome_view* x_view,
+                      const int32_t* tok_of_row, int64_t tok_stride_b, int32_t ra, int32_t nb, const int32_t* dst_idx,
+                      int32_t mode, void* out, void* stream);
+TOME_API int tome_gather_rows(const void* x, int32_t dtype, int32_t bm, int32_t n_in, int32_t c, const int32_t* map,
+                     int32_t n_out, void* out, void* stream);
 
 #ifdef __cplusplus
 }

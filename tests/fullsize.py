@@ -102,14 +102,18 @@ def compare_plans(plans, lists):
             first = i
             nm = rec["node_max"]
             for b in range(src.shape[0]):
-                for ours, ref, bad in ((src[b], rec["src"][b], ds[b]), (unm[b], rec["unm"][b], du[b])):
-                    if p.class_token and ours is unm[b]:
-                        # ascending-index lists: compare as sets, each token that changed side against the boundary
+                for ours, ref, bad, by_index in ((src[b], rec["src"][b], ds[b], False), (unm[b], rec["unm"][b], du[b], bool(p.class_token))):
+                    if not bad.any():
+                        continue
+                    if by_index:
+                        # ascending-index lists (merge.py:71-73): compare as sets -- every token that changed side of
+                        # the src / unm boundary against the boundary value (the reference's r-th best node_max)
                         moved = np.setxor1d(ours, ref)
+                        moved = moved[moved != 0]                       # the class token (key -inf) never moves
                         edge = nm[b][rec["src"][b][-1]]
                         if len(moved):
                             margin = max(margin, float(np.abs(nm[b][moved] - edge).max()))
-                    elif bad.any():
+                    else:
                         margin = max(margin, float(np.abs(nm[b][ours[bad]] - nm[b][ref[bad]]).max()))
                 if dd[b].any():
                     margin = max(margin, float(rec["gap2"][b][src[b][dd[b]]].max()))
@@ -123,6 +127,9 @@ def run_case(case, dtype=torch.float32, forced=False, device="cuda"):
     name = case["name"]
     model = G.seeded_fill(G.build_ours(case).eval(), wstd=case["wstd"]).to(device=device, dtype=dtype)
     clip = G.clip_for(case).to(device=device, dtype=dtype)
+    with torch.no_grad():
+        plain = model([clip]).float().cpu().numpy()
+    plain_err = float(np.abs(plain - g[name + "/plain"]).max() / np.abs(g[name + "/plain"]).max())
     getattr(tome.patch, case["model"])(model, **case["kw"])
     model.r = case["r"]
     lists, plans = layer_lists(name), []
@@ -132,7 +139,7 @@ def run_case(case, dtype=torch.float32, forced=False, device="cuda"):
     first, diffs, margin = compare_plans(plans, lists)
     size = model._tome_info["size"].float().cpu().numpy()
     return dict(name=name, dtype=str(dtype).replace("torch.", ""), forced=forced,
-                err=float(np.abs(logits - want).max() / np.abs(want).max()),
+                err=float(np.abs(logits - want).max() / np.abs(want).max()), unpatched_err=plain_err,
                 top1_same=bool((logits.argmax(-1) == want.argmax(-1)).all()),
                 top1_margin=float(np.sort(want, -1)[:, -1].min() - np.sort(want, -1)[:, -2].max()) / float(np.abs(want).max()),
                 first_divergent_layer=first, differing_entries=diffs, overturned_margin=margin, layers=len(lists),

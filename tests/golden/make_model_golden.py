@@ -41,6 +41,12 @@ MODEL_CASES = [
     dict(name="vivit_drop", model="vivit", frames=8, r=(60, -1), kw=dict(mode="drop", prop_attn=False)),
     dict(name="vivit_hybrid", model="vivit", frames=8, r=60, kw=dict(mode="hybrid", threshold=0.4)),
     dict(name="vivit_concat_noprop", model="vivit", frames=8, r=[60, 0, 200], kw=dict(head_aggregation="concat", prop_attn=False)),
+    # layer duplication ablation (tools/test_net.py:270-283: duplicate_<model>(model, layer, quantity), THEN the patch,
+    # r = [0] * layer + [R] * quantity + [0] * rest)
+    dict(name="videomae_duplicate", model="videomae", frames=4, r=[0, 40, 40, 0], kw=dict(), duplicate=(1, 2)),
+    dict(name="timesformer_duplicate", model="timesformer", frames=4, r=[0, 18, 18, 0], kw=dict(), duplicate=(1, 2)),
+    dict(name="motionformer_duplicate", model="motionformer", frames=8, r=[0, 18, 18, 18, 0], kw=dict(), duplicate=(1, 3)),
+    dict(name="vivit_duplicate", model="vivit", frames=8, r=[0, 60, 60, 0], kw=dict(prop_attn=False), duplicate=(1, 2)),
 ]
 
 # BASELINE.json configs 2-5 at full size: ViT-B, 12 layers, 12 heads, 400 classes; r / mode as experiments.sh uses them
@@ -206,6 +212,8 @@ def run_reference(case, trace=False):
         ref = seeded_fill(build_reference(case).eval(), wstd=case.get("wstd", 0.08))
         with torch.no_grad():
             plain = ref([clip]).clone()
+        if case.get("duplicate"):
+            getattr(ref_tome.patch, "duplicate_" + case["model"])(ref, *case["duplicate"])
         getattr(ref_tome.patch, case["model"])(ref, **case["kw"])
         ref.r = case["r"]
         layers = None

@@ -87,3 +87,39 @@ def test_api_surface_matches_reference():
                      "merge_wavg", "merge_source", "kth_bipartite_soft_matching", "random_bipartite_soft_matching"):
             assert (list(inspect.signature(getattr(ref, name)).parameters)
                     == list(inspect.signature(getattr(tome.merge, name)).parameters)), name
+
+
+def test_benchmark_helper_keeps_the_reference_signature_and_protocol():
+    """tome/utils.py:15-24 of the reference: same positional parameters (``use_fp16`` included), images/s for a 3-d
+    input size, frames/s for a 4-d one, runs on any device; our additions are keyword-only."""
+    import tome
+    params = inspect.signature(tome.utils.benchmark).parameters
+    assert list(params)[:8] == ["model", "device", "input_size", "batch_size", "runs", "throw_out", "use_fp16", "verbose"]
+    assert all(params[k].kind is inspect.Parameter.KEYWORD_ONLY for k in list(params)[8:])
+    assert params["input_size"].default == (3, 224, 224) and params["batch_size"].default == 64
+
+    calls = []
+
+    class Probe(torch.nn.Module):
+        def forward(self, x):
+            calls.append(type(x))
+            return x[0].sum() if isinstance(x, list) else x.sum()
+
+    thr = tome.utils.benchmark(Probe(), device="cpu", input_size=(3, 4, 8, 8), batch_size=2, runs=8, throw_out=0.25)
+    assert thr > 0 and len(calls) == 8 and calls[0] is torch.Tensor
+    tome.utils.benchmark(Probe(), device="cpu", input_size=(3, 8, 8), batch_size=2, runs=4, as_pathways=True)
+    assert calls[-1] is list
+
+
+def test_vivit_patch_rejects_what_the_fused_attention_cannot_honour():
+    import hostmodels
+    import tome
+    m = hostmodels.ViViT(num_classes=4, num_frames=4, hidden_size=32, num_hidden_layers=1, num_attention_heads=2,
+                         intermediate_size=64).eval()
+    tome.patch.vivit(m)
+    layer = m.vivit.encoder.layer[0]
+    x = torch.zeros(1, 393, 32)
+    with pytest.raises(NotImplementedError, match="head_mask"):
+        layer(x, head_mask=torch.ones(2))
+    with pytest.raises(NotImplementedError, match="output_attentions"):
+        layer(x, output_attentions=True)

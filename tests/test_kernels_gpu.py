@@ -445,17 +445,14 @@ def test_fused_residual_equals_merging_the_sum(native, name, dtype):
         native.merge(dp, xd, "wavg", residual=rd[:, :-1])
 
 
-@pytest.mark.parametrize("path", ["fused", "rank_kernels", "exact_simt"])
+@pytest.mark.parametrize("path", ["fused", "exact_simt"])
 @pytest.mark.parametrize("case", ALL_ACTIVE, ids=lambda c: c["name"])
-def test_plan_build_bit_exact_vs_oracle(native, case, path, monkeypatch):
-    """tome_plan_build (kernel 1's packed keys decoded by the one-launch sort-based select) gives the
-    oracle's node_max / node_idx / src / unm / dst bits; so do the rank-by-counting select kernels it
-    replaces (kept for very long sequences) and the exact SIMT matching."""
+def test_plan_build_bit_exact_vs_oracle(native, case, path):
+    """tome_plan_build (kernels 1 + 2 in one ABI call) gives the oracle's node_max / node_idx / src / unm / dst
+    bits, with the tcgen05 matching and with the exact SIMT matching."""
     metric, _, _ = util.case_arrays(case)
     cls, dis = bool(case.get("cls")), bool(case.get("distill"))
     plan = _oracle_plan(case, metric)
-    if path == "rank_kernels":
-        monkeypatch.setenv("TOME_SELECT_RANK", "1")
     dp = native.plan_build(_dev(metric), plan.r, cls, dis, algo=1 if path == "exact_simt" else 0)
     np.testing.assert_array_equal(dp.node_idx.cpu().numpy(), plan.node_idx)
     np.testing.assert_array_equal(dp.node_max.cpu().numpy().view(np.uint32), plan.node_max.view(np.uint32))
@@ -668,3 +665,102 @@ def test_tiny_token_counts_down_to_two(native, cls):
         want, want_s = O.merge_wavg(plan, x.numpy(), None)
         np.testing.assert_array_equal(out.cpu().numpy(), want, err_msg=f"n={n}")
         np.testing.assert_array_equal(so.cpu().numpy(), want_s.reshape(so.shape), err_msg=f"n={n}")
+
+
+# ---- the upstream-ToMe set matchers (merge.py:105-212) against goldens made by the reference functions ----
+def _sets_golden():
+    import importlib.util
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_sets_golden", os.path.join(here, "make_sets_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    import sys
+    sys.path.insert(0, here)
+    spec.loader.exec_module(mod)
+    return mod, dict(np.load(os.path.join(here, "sets.npz")))
+
+
+_SETS_MOD, _SETS_GOLD = _sets_golden()
+
+
+@pytest.mark.parametrize("case", _SETS_MOD.SET_CASES, ids=lambda c: c["name"])
+def test_kth_and_random_matchers_vs_reference(native, case, monkeypatch):
+    """kth_ / random_bipartite_soft_matching on tome_match_sets / tome_group_reduce / tome_gather_rows: the
+    destination of every source, merge(sum / mean / amax) and unmerge equal what the reference functions
+    produced on CPU, fp32 bit for bit (same reduction order: destination first, then sources ascending)."""
+    import tome.merge as M
+    metric, x, rand = _SETS_MOD.inputs(case)
+    g, name = _SETS_GOLD, case["name"]
+    if case["kind"] == "kth":
+        merge, unmerge = M.kth_bipartite_soft_matching(metric.cuda(), case["k"])
+    else:
+        real_rand = torch.rand
+        monkeypatch.setattr(torch, "rand", lambda *a, **k: rand.clone().to(k.get("device", "cpu")))
+        merge, unmerge = M.random_bipartite_soft_matching(metric.cuda(), case["r"])
+        monkeypatch.setattr(torch, "rand", real_rand)
+    np.testing.assert_array_equal(merge.dst_idx[..., 0].cpu().numpy(), g[name + "/dst_idx"])
+    for mode in ("mean", "sum", "amax"):
+        got = merge(x.cuda(), mode=mode).cpu().numpy()
+        np.testing.assert_array_equal(got.view(np.uint32), g[f"{name}/merge_{mode}"].view(np.uint32), err_msg=mode)
+    got = unmerge(merge(x.cuda(), mode="mean")).cpu().numpy()
+    np.testing.assert_array_equal(got.view(np.uint32), g[name + "/unmerge"].view(np.uint32))
+    # bf16 rows: fp32 accumulation, one rounding
+    half = merge(x.cuda().bfloat16(), mode="mean").float().cpu().numpy()
+    np.testing.assert_allclose(half, g[name + "/merge_mean"], rtol=2e-2, atol=2e-2)
+    assert M.kth_bipartite_soft_matching(metric.cuda(), 1) == (M.do_nothing, M.do_nothing)
+    assert M.random_bipartite_soft_matching(metric.cuda(), 0) == (M.do_nothing, M.do_nothing)
+
+
+def test_unmerge_backward_is_merge_sum(native):
+    """The reference's unmerge (gather + scatter, merge.py:87-100) is differentiable; ours runs tome_unmerge forward
+    and the merge kernel in 'sum' mode backward.  Checked against autograd through the CPU port's unmerge."""
+    import tome.merge as M
+    from oracle import torch_port as P
+    case = util.CASE_BY_NAME["gauss_odd"]
+    metric, x, _ = util.case_arrays(case)
+    merge, unmerge = M.bipartite_soft_matching(_dev(metric), case["r"])
+    pm, pu = P.bipartite_soft_matching(torch.from_numpy(metric), case["r"])
+    P_STABLE = P.STABLE
+    y = torch.from_numpy(x)[:, :case["n"] - merge.r].clone()
+    w = torch.randn(case["bm"], case["n"], case["c"], generator=torch.Generator().manual_seed(5))
+    yc = y.clone().requires_grad_(True)
+    (pu(yc) * w).sum().backward()
+    yg = y.cuda().requires_grad_(True)
+    out = unmerge(yg)
+    assert out.requires_grad
+    (out * w.cuda()).sum().backward()
+    assert P_STABLE == P.STABLE
+    if np.array_equal(merge.src_idx.cpu().numpy(), pm.match.src_idx.numpy()) and \\
+            np.array_equal(merge.unm_idx.cpu().numpy(), pm.match.unm_idx.numpy()):
+        torch.testing.assert_close(yg.grad.cpu(), yc.grad, rtol=1e-6, atol=1e-6)
+    # adjoint identity holds whatever the plan: <unmerge(y), w> == <y, merge_sum(w)>
+    lhs = float((unmerge(y.cuda()) * w.cuda()).double().sum())
+    rhs = float((y.cuda() * merge(w.cuda(), mode="sum")).double().sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+
+
+def test_batch_beyond_the_grid_limit_is_a_clear_error(native):
+    metric = torch.zeros(65536, 4, 8, device="cuda")
+    with pytest.raises(RuntimeError, match="split the batch"):
+        native.match(metric)
+    with pytest.raises(RuntimeError, match="split the batch"):
+        native.plan_build(metric, 1)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two visible GPUs")
+def test_second_device_in_the_same_process(native):
+    """Function attributes (> 48 KB dynamic shared memory opt-in) are per device: after running on cuda:0 the same
+    process must be able to run the tcgen05 matching, the select and the fused MLP GEMM on cuda:1."""
+    case = util.CASE_BY_NAME["config1_m1p"]
+    metric, _, _ = util.case_arrays(case)
+    plans = []
+    for dev in (0, 1):
+        with torch.cuda.device(dev):
+            native.device_check(dev)
+            plans.append(native.plan_build(torch.from_numpy(metric).cuda(dev), 100))
+            a = torch.randn(4096, 768, device=f"cuda:{dev}", dtype=torch.bfloat16)
+            w = torch.randn(3072, 768, device=f"cuda:{dev}", dtype=torch.bfloat16)
+            native.linear_gelu(a, w, None)
+            torch.cuda.synchronize(dev)
+    assert torch.equal(plans[0].src_idx.cpu(), plans[1].src_idx.cpu())
+    assert torch.equal(plans[0].dst_idx.cpu(), plans[1].dst_idx.cpu())

@@ -54,6 +54,8 @@ def _run(case, device, dtype, backend_ctx):
     clip = G.clip_for(case).to(device=device, dtype=dtype)
     with torch.no_grad():
         plain = model([clip]).float().cpu()
+    if case.get("duplicate"):            # tools/test_net.py:270-283: duplicate first, then patch
+        getattr(tome.patch, "duplicate_" + case["model"])(model, *case["duplicate"])
     getattr(tome.patch, case["model"])(model, **case["kw"])
     model.r = case["r"]
     with backend_ctx, torch.no_grad():

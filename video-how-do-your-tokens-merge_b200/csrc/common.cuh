@@ -33,6 +33,20 @@ void count_launch();
 int ensure_device_ok();   // TOME_OK if the current device is sm_100
 int sm_count();
 
+// Function attributes (the opt-in to > 48 KB of dynamic shared memory) are per DEVICE: a process that launches
+// on cuda:0 and later on cuda:1 must set them on both.  One flag per device; setting an attribute twice is
+// harmless, so a race between two host threads is benign.
+struct PerDeviceOnce {
+  unsigned char done[64] = {};
+  bool first_time() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = 1;
+    return true;
+  }
+};
+
 // ---- geometry -----------------------------------------------------------------------------
 __host__ __device__ inline int na_of(int n) { return (n + 1) >> 1; }
 __host__ __device__ inline int nb_of(int n) { return n >> 1; }

@@ -223,11 +223,9 @@ int launch_linear_gelu(const void* x, const void* w, const void* bias, int m, in
   p.tiles_n = n / LG_BN; p.tiles = ((m + LG_BM - 1) / LG_BM) * p.tiles_n;
   p.bias = (const __nv_bfloat16*)bias; p.out = (__nv_bfloat16*)out; p.gelu = gelu;
   const size_t smem = (size_t)LG_STAGES * LG_STAGE_BYTES + LG_EPI_WARPS * LG_OBOX_BYTES + 16 * LG_STAGES + 32 + 16 + 1024;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first_time())
     TOME_CUDA(cudaFuncSetAttribute(linear_gelu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
   const int grid = p.tiles < sm_count() ? p.tiles : sm_count();
   linear_gelu_kernel<<<grid, LG_THREADS, smem, st>>>(map_a, map_w, map_o, p);
   TOME_LAUNCH_CHECK("linear_gelu_kernel");

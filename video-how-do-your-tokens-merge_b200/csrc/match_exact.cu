@@ -35,12 +35,13 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const T* __restrict__ me
 // ---- 64x64 score tile per CTA, 4x4 fp64 accumulators per thread ---------------------------
 constexpr int TM = 64, TN = 64, KC = 32;
 
-__global__ void __launch_bounds__(256) match_exact_kernel(const float* __restrict__ mhat, int n, int cm,
+// rows = na + nb normalised rows per batch element, the A rows first (the even/odd split of merge.py:52, or any
+// two token sets: sets.cu)
+__global__ void __launch_bounds__(256) match_exact_kernel(const float* __restrict__ mhat, int n, int na, int nb, int cm,
                                                           int cls, int distill,
                                                           unsigned long long* __restrict__ keys) {
   __shared__ float As[KC][TM + 1];
   __shared__ float Bs[KC][TN + 1];
-  const int na = na_of(n), nb = nb_of(n);
   const int b = blockIdx.z;
   const int i0 = blockIdx.y * TM, j0 = blockIdx.x * TN;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -134,6 +135,18 @@ __global__ void __launch_bounds__(128) rowmax_kernel(const float* __restrict__ s
 }
 
 // ---- host ---------------------------------------------------------------------------------
+int launch_match_exact_tiles(const float* mhat, int bm, int rows, int na, int nb, int cm, int cls, int distill,
+                             unsigned long long* keys, float* node_max, int* node_idx, cudaStream_t st) {
+  dim3 grid((nb + TN - 1) / TN, (na + TM - 1) / TM, bm);
+  if (grid.z > 65535) return set_error(TOME_ERR_UNSUPPORTED, "tome_match: matching batch %d > 65535", bm);
+  match_exact_kernel<<<grid, 256, 0, st>>>(mhat, rows, na, nb, cm, cls, distill, keys);
+  TOME_LAUNCH_CHECK("match_exact_kernel");
+  const int total = bm * na;
+  decode_keys_kernel<<<(total + 255) / 256, 256, 0, st>>>(keys, total, node_max, node_idx);
+  TOME_LAUNCH_CHECK("decode_keys_kernel");
+  return TOME_OK;
+}
+
 size_t match_exact_workspace(int bm, int n, int cm) {
   size_t mh = (size_t)bm * n * cm * sizeof(float);
   mh = (mh + 255) & ~(size_t)255;
@@ -157,13 +170,7 @@ int launch_match_exact(const void* metric, int dtype, int bm, int n, int cm, con
   else
     prep_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)metric, v, bm, n, cm, mhat, keys);
   TOME_LAUNCH_CHECK("prep_rows_kernel");
-  dim3 grid((nb + TN - 1) / TN, (na + TM - 1) / TM, bm);
-  match_exact_kernel<<<grid, 256, 0, st>>>(mhat, n, cm, cls, distill, keys);
-  TOME_LAUNCH_CHECK("match_exact_kernel");
-  const int total = bm * na;
-  decode_keys_kernel<<<(total + 255) / 256, 256, 0, st>>>(keys, total, node_max, node_idx);
-  TOME_LAUNCH_CHECK("decode_keys_kernel");
-  return TOME_OK;
+  return launch_match_exact_tiles(mhat, bm, n, na, nb, cm, cls, distill, keys, node_max, node_idx, st);
 }
 
 int launch_rowmax(const float* scores, int bm, int na, int nb, int cls, int distill, float* node_max,

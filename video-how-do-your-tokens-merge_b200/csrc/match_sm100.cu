@@ -665,11 +665,9 @@ int launch_match_tc(const void* metric, int dtype, int bm, int n, int cm, const 
   rc = make_bf16_map(&map_b, hm, 2LL * bm * n, cm, cm, p.BN, "tome_match");
   if (rc) return rc;
   const size_t smem = (size_t)p.stages * 2 * (TC_BM + p.BN) * 128 + 16 * p.stages + 16 + 1024;
-  static bool smem_set = false;
-  if (!smem_set) {
+  static PerDeviceOnce smem_set;
+  if (smem_set.first_time())
     TOME_CUDA(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    smem_set = true;
-  }
   dim3 grid(p.n_ct, n_rt, bm);
   match_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
   TOME_LAUNCH_CHECK("match_tc_kernel");

@@ -557,8 +557,8 @@ static int launch_gather_inst(const MergeArgs& a, cudaStream_t st) {
   dim3 grid(a.bm, (nout + WARPS - 1) / WARPS);
   if (grid.y > 65535) return set_error(TOME_ERR_UNSUPPORTED, "tome_merge: too many output rows per batch element (%d)", nout);
   const size_t smem = (size_t)WARPS * (a.res ? 4 : 2) * NV * 32 * sizeof(uint4);
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first_time()) {
     const int big = (int)((size_t)WARPS * 4 * NV * 32 * sizeof(uint4));
     if (big > 48 * 1024) {
       TOME_CUDA(cudaFuncSetAttribute(merge_gather_kernel<T, NV, WARPS, MINB, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -566,7 +566,6 @@ static int launch_gather_inst(const MergeArgs& a, cudaStream_t st) {
       TOME_CUDA(cudaFuncSetAttribute(merge_gather_kernel<T, NV, WARPS, MINB, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
       TOME_CUDA(cudaFuncSetAttribute(merge_gather_kernel<T, NV, WARPS, MINB, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     }
-    attr = true;
   }
   if (a.res) {
     if (a.normed) merge_gather_kernel<T, NV, WARPS, MINB, true, true><<<grid, WARPS * 32, smem, st>>>(a);
@@ -702,7 +701,12 @@ static int launch_add_ln_t(const void* a, const void* b, long long b_rows, long 
                            float eps, void* sum_out, void* normed, cudaStream_t st) {
   constexpr int E = Pack<T>::E;
   const int nv = (c / E + 31) / 32;
-  static const int threads = getenv("TOME_ADDLN_THREADS") ? atoi(getenv("TOME_ADDLN_THREADS")) : 64;   // tuning knob; 256: 13.4 us, 64: 12.5 us
+  static const int threads = [] {                   // tuning knob; 256: 13.4 us, 64: 12.5 us.  Whole warps, 32..256.
+    const char* e = getenv("TOME_ADDLN_THREADS");
+    int t = e ? atoi(e) : 64;
+    t = (t / 32) * 32;
+    return t < 32 ? 32 : (t > 256 ? 256 : t);
+  }();
   const int rows_per_cta = threads / 32;
   const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
 #define TOME_ADDLN(NV_) add_layernorm_kernel<T, NV_><<<grid, threads, 0, st>>>((const T*)a, (const T*)b, b_rows, rows, c, (const T*)w, (const T*)bias, eps, (T*)sum_out, (T*)normed)

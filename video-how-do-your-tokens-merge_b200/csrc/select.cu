@@ -158,11 +158,10 @@ int launch_select(const tome_plan* plan, void* ws, size_t ws_bytes, cudaStream_t
   const size_t sm_fin = ((size_t)2 * nb + 1 + r) * sizeof(int);
   if (sm_rank > 200 * 1024 || sm_fin > 200 * 1024)
     return set_error(TOME_ERR_UNSUPPORTED, "tome_select: n=%d needs more shared memory than one SM has", n);
-  static bool attr_set = false;   // raising the opt-in limit is idempotent; races are benign
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first_time()) {
     TOME_CUDA(cudaFuncSetAttribute(rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     TOME_CUDA(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   dim3 grid((na + RANK_ROWS - 1) / RANK_ROWS, bm);
   rank_kernel<<<grid, RANK_ROWS * RANK_WARPS, sm_rank, st>>>(p, (int*)ws);

@@ -68,9 +68,16 @@ int launch_patchify(const void*, int, int, int, int, int, int, int, int, int, vo
 int launch_key_bias(const float*, int, int, int, int, int, float, int, void*, long long, long long, long long, void*, long long,
                     long long, long long, cudaStream_t);
 
+size_t match_sets_workspace(int bm, int rows, int ra, int cm);
+int launch_match_sets(const void*, int, int, int, const View&, const int*, long long, int, int, float*, int*, void*, size_t, cudaStream_t);
+int launch_group_reduce(const void*, int, int, int, const View&, const int*, long long, int, int, const int*, int, void*, cudaStream_t);
+int launch_gather_rows(const void*, int, int, int, int, const int*, int, void*, cudaStream_t);
+
 static int check_plan(const tome_plan* p, const char* who) {
   if (!p) return set_error(TOME_ERR_ARG, "%s: plan is NULL", who);
   if (p->bm <= 0 || p->n < 2) return set_error(TOME_ERR_ARG, "%s: bad plan shape bm=%d n=%d", who, p->bm, p->n);
+  if (p->bm > TOME_MAX_BATCH)       // the matching batch rides on gridDim.y / gridDim.z of several kernels
+    return set_error(TOME_ERR_UNSUPPORTED, "%s: matching batch %d > %d; split the batch", who, p->bm, TOME_MAX_BATCH);
   const int prot = (p->class_token ? 1 : 0) + (p->distill_token ? 1 : 0);
   if (p->r <= 0 || p->r > (p->n - prot) / 2)
     return set_error(TOME_ERR_ARG, "%s: plan->r=%d is not an effective r for n=%d (max %d)", who, p->r, p->n, (p->n - prot) / 2);
@@ -114,6 +121,7 @@ int tome_match(const void* metric, int32_t dtype, int32_t bm, int32_t n, int32_t
   if (rc) return rc;
   TOME_CHECK_ARG(metric && node_max && node_idx && workspace, "tome_match: NULL pointer argument");
   TOME_CHECK_ARG(bm > 0 && n >= 2 && cm > 0, "tome_match: bad shape bm=%d n=%d cm=%d", bm, n, cm);
+  if (bm > TOME_MAX_BATCH) return set_error(TOME_ERR_UNSUPPORTED, "tome_match: matching batch %d > %d; split the batch", bm, TOME_MAX_BATCH);
   if (dtype != TOME_F32 && dtype != TOME_BF16) return set_error(TOME_ERR_DTYPE, "tome_match: unsupported dtype %d", dtype);
   TOME_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "tome_match: workspace must be 256-byte aligned");
   const View v = make_view(view, n, cm);
@@ -138,6 +146,7 @@ int tome_match_heads(const void* keys, int32_t dtype, int32_t bm, int32_t heads,
   if (rc) return rc;
   TOME_CHECK_ARG(keys && node_max && node_idx && workspace && view, "tome_match_heads: NULL pointer argument");
   TOME_CHECK_ARG(bm > 0 && n >= 2 && cm > 0 && heads >= 1, "tome_match_heads: bad shape bm=%d heads=%d n=%d cm=%d", bm, heads, n, cm);
+  if (bm > TOME_MAX_BATCH) return set_error(TOME_ERR_UNSUPPORTED, "tome_match_heads: matching batch %d > %d; split the batch", bm, TOME_MAX_BATCH);
   if (dtype != TOME_F32 && dtype != TOME_BF16) return set_error(TOME_ERR_DTYPE, "tome_match_heads: unsupported dtype %d", dtype);
   TOME_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "tome_match_heads: workspace must be 256-byte aligned");
   const View v = make_view(view, n, cm);
@@ -204,6 +213,7 @@ int tome_rowmax(const float* scores, int32_t bm, int32_t na, int32_t nb, int32_t
   if (rc) return rc;
   TOME_CHECK_ARG(scores && node_max && node_idx, "tome_rowmax: NULL pointer argument");
   TOME_CHECK_ARG(bm > 0 && na > 0 && nb > 0, "tome_rowmax: bad shape bm=%d na=%d nb=%d", bm, na, nb);
+  if (bm > TOME_MAX_BATCH) return set_error(TOME_ERR_UNSUPPORTED, "tome_rowmax: matching batch %d > %d; split the batch", bm, TOME_MAX_BATCH);
   return launch_rowmax(scores, bm, na, nb, class_token, distill_token, node_max, node_idx, (cudaStream_t)stream);
 }
 
@@ -325,6 +335,46 @@ int tome_unmerge(const tome_plan* plan, const void* x, int32_t dtype, int32_t c,
   if (rc) return rc;
   TOME_CHECK_ARG(x && out && c > 0, "tome_unmerge: NULL tensor or c=%d", c);
   return launch_unmerge(plan, x, dtype, c, out, (cudaStream_t)stream);
+}
+
+size_t tome_match_sets_workspace_bytes(int32_t bm, int32_t ra, int32_t nb, int32_t cm) {
+  if (bm <= 0 || ra <= 0 || nb <= 0 || cm <= 0) return 0;
+  return match_sets_workspace(bm, ra + nb, ra, cm);
+}
+
+int tome_match_sets(const void* metric, int32_t dtype, int32_t bm, int32_t n, int32_t cm, const tome_view* view,
+                    const int32_t* tok_of_row, int64_t tok_stride_b, int32_t ra, int32_t nb, float* node_max,
+                    int32_t* node_idx, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(metric && tok_of_row && node_max && node_idx && workspace, "tome_match_sets: NULL pointer argument");
+  TOME_CHECK_ARG(bm > 0 && n > 0 && cm > 0 && ra > 0 && nb > 0 && ra + nb <= n, "tome_match_sets: bad shape bm=%d n=%d cm=%d ra=%d nb=%d", bm, n, cm, ra, nb);
+  if (dtype != TOME_F32 && dtype != TOME_BF16) return set_error(TOME_ERR_DTYPE, "tome_match_sets: unsupported dtype %d", dtype);
+  TOME_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "tome_match_sets: workspace must be 256-byte aligned");
+  return launch_match_sets(metric, dtype, bm, cm, make_view(view, n, cm), tok_of_row, tok_stride_b, ra, nb, node_max, node_idx,
+                           workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int tome_group_reduce(const void* x, int32_t dtype, int32_t bm, int32_t n, int32_t c, const tome_view* x_view,
+                      const int32_t* tok_of_row, int64_t tok_stride_b, int32_t ra, int32_t nb, const int32_t* dst_idx,
+                      int32_t mode, void* out, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(x && tok_of_row && dst_idx && out, "tome_group_reduce: NULL pointer argument");
+  TOME_CHECK_ARG(bm > 0 && c > 0 && ra > 0 && nb > 0 && ra + nb <= n, "tome_group_reduce: bad shape bm=%d n=%d c=%d ra=%d nb=%d", bm, n, c, ra, nb);
+  TOME_CHECK_ARG(mode == TOME_MODE_SUM || mode == TOME_MODE_MEAN || mode == TOME_MODE_AMAX, "tome_group_reduce: mode %d is not sum / mean / amax", mode);
+  if (dtype != TOME_F32 && dtype != TOME_BF16) return set_error(TOME_ERR_DTYPE, "tome_group_reduce: unsupported dtype %d", dtype);
+  return launch_group_reduce(x, dtype, bm, c, make_view(x_view, n, c), tok_of_row, tok_stride_b, ra, nb, dst_idx, mode, out,
+                             (cudaStream_t)stream);
+}
+
+int tome_gather_rows(const void* x, int32_t dtype, int32_t bm, int32_t n_in, int32_t c, const int32_t* map, int32_t n_out,
+                     void* out, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(x && map && out && bm > 0 && n_in > 0 && n_out > 0 && c > 0, "tome_gather_rows: bad argument");
+  if (dtype != TOME_F32 && dtype != TOME_BF16) return set_error(TOME_ERR_DTYPE, "tome_gather_rows: unsupported dtype %d", dtype);
+  return launch_gather_rows(x, dtype, bm, n_in, c, map, n_out, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 TOME_F32, TOME_BF16 = 0, 1
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -30,6 +30,7 @@ EXPORTS = (
     "tome_plan_build_workspace_bytes", "tome_plan_build", "tome_match_tc_describe",
     "tome_rowmax", "tome_select_workspace_bytes", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_add_norm", "tome_add_layernorm", "tome_add_rows_layernorm",
     "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_linear_gelu", "tome_unmerge",
+    "tome_match_sets_workspace_bytes", "tome_match_sets", "tome_group_reduce", "tome_gather_rows",
 )
 
 
@@ -107,8 +108,16 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.tome_attn_key_bias.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_i32, c_vp, c_i64, c_i64, c_i64,
                                        c_vp, c_i64, c_i64, c_i64, c_vp]
     lib.tome_unmerge.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_i32, c_vp, c_vp]
+    lib.tome_match_sets_workspace_bytes.restype = c_sz
+    lib.tome_match_sets_workspace_bytes.argtypes = [c_i32, c_i32, c_i32, c_i32]
+    lib.tome_match_sets.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(TomeViewC), c_vp, c_i64, c_i32, c_i32,
+                                    c_vp, c_vp, c_vp, c_sz, c_vp]
+    lib.tome_group_reduce.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(TomeViewC), c_vp, c_i64, c_i32, c_i32,
+                                      c_vp, c_i32, c_vp, c_vp]
+    lib.tome_gather_rows.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp]
     for name in ("tome_device_check", "tome_match", "tome_match_heads", "tome_rowmax", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_add_norm", "tome_add_layernorm", "tome_add_rows_layernorm",
-                 "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_linear_gelu", "tome_unmerge"):
+                 "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_linear_gelu", "tome_unmerge",
+                 "tome_match_sets", "tome_group_reduce", "tome_gather_rows"):
         getattr(lib, name).restype = c_i32
     if lib.tome_abi_version() != ABI_VERSION:
         raise RuntimeError(f"tome_b200: ABI version {lib.tome_abi_version()} != expected {ABI_VERSION}; rebuild")
@@ -596,4 +605,71 @@ def unmerge(plan: DevicePlan, x: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(x.device):
         out = torch.empty(bm, plan.n, c, dtype=x.dtype, device=x.device)
         _check(lib.tome_unmerge(plan.c_ptr(), x.data_ptr(), _dtype_code(x), c, out.data_ptr(), _stream(x)), lib)
+    return out
+
+
+class TokenSets:
+    """Two token sets as index lists into the token axis (``tome_match_sets`` / ``tome_group_reduce``): ``a_tok`` the
+    sources, ``b_tok`` the destinations; (ra,) / (nb,) shared by the batch, or (bm, ra) / (bm, nb) per element."""
+
+    def __init__(self, a_tok: torch.Tensor, b_tok: torch.Tensor):
+        self.ra, self.nb = a_tok.shape[-1], b_tok.shape[-1]
+        self.per_batch = a_tok.dim() == 2
+        self.rows = torch.cat((a_tok, b_tok), -1).to(torch.int32).contiguous()
+        self.stride_b = self.ra + self.nb if self.per_batch else 0
+
+
+def match_sets(metric: torch.Tensor, sets: TokenSets) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Best destination ROW (and its canonical score) for every source row: (bm, ra) fp32, (bm, ra) int32."""
+    lib = load_library()
+    _require_cuda(metric, "metric")
+    if metric.dtype not in (torch.float32, torch.bfloat16):
+        metric = metric.float()
+    if metric.stride(2) != 1:
+        metric = metric.contiguous()
+    bm, n, cm = metric.shape
+    dev = metric.device
+    with torch.cuda.device(dev):
+        node_max = torch.empty(bm, sets.ra, dtype=torch.float32, device=dev)
+        node_idx = torch.empty(bm, sets.ra, dtype=torch.int32, device=dev)
+        ws_bytes = lib.tome_match_sets_workspace_bytes(bm, sets.ra, sets.nb, cm)
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        view = _view_of(metric)
+        _check(lib.tome_match_sets(metric.data_ptr(), _dtype_code(metric), bm, n, cm, ctypes.byref(view), sets.rows.data_ptr(),
+                                   sets.stride_b, sets.ra, sets.nb, node_max.data_ptr(), node_idx.data_ptr(), ws.data_ptr(),
+                                   ws_bytes, _stream(metric)), lib)
+    return node_max, node_idx
+
+
+def group_reduce(x: torch.Tensor, sets: TokenSets, dst_idx: torch.Tensor, mode: str) -> torch.Tensor:
+    """(bm, nb, c): every destination row reduced with the source rows ``dst_idx`` assigns to it (include_self)."""
+    lib = load_library()
+    _require_cuda(x, "x")
+    if mode not in ("sum", "mean", "max", "amax"):
+        raise RuntimeError(f"tome_b200: group_reduce mode must be sum / mean / amax, got {mode!r}")
+    _dtype_code(x)
+    if x.stride(2) != 1:
+        x = x.contiguous()
+    bm, n, c = x.shape
+    with torch.cuda.device(x.device):
+        out = torch.empty(bm, sets.nb, c, dtype=x.dtype, device=x.device)
+        view = _view_of(x)
+        _check(lib.tome_group_reduce(x.data_ptr(), _dtype_code(x), bm, n, c, ctypes.byref(view), sets.rows.data_ptr(),
+                                     sets.stride_b, sets.ra, sets.nb, dst_idx.data_ptr(), _MODES[mode], out.data_ptr(),
+                                     _stream(x)), lib)
+    return out
+
+
+def gather_rows(x: torch.Tensor, row_map: torch.Tensor) -> torch.Tensor:
+    """out[b, t] = x[b, row_map[b, t]] (zeros where the map is negative); row_map (bm, n_out) int32."""
+    lib = load_library()
+    _require_cuda(x, "x")
+    x = x.contiguous()
+    row_map = row_map.to(torch.int32).contiguous()
+    bm, n_in, c = x.shape
+    n_out = row_map.shape[1]
+    with torch.cuda.device(x.device):
+        out = torch.empty(bm, n_out, c, dtype=x.dtype, device=x.device)
+        _check(lib.tome_gather_rows(x.data_ptr(), _dtype_code(x), bm, n_in, c, row_map.data_ptr(), n_out, out.data_ptr(),
+                                    _stream(x)), lib)
     return out

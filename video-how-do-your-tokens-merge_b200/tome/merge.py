@@ -202,8 +202,26 @@ class Merge(_PlanCallable):
         return (out, s[..., None], ls[..., None]) + tuple(res[3:])
 
 
+class _UnmergeGrad(torch.autograd.Function):
+    """unmerge copies merged slot s to every token that fed it (merge.py:87-100: gather + scatter), so its adjoint
+    sums the gradients of those tokens back into the slot: the merge kernel in 'sum' mode."""
+
+    @staticmethod
+    def forward(ctx, x, plan):
+        ctx.plan = plan
+        return _native.unmerge(plan, x.detach())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return _native.merge(ctx.plan, grad_out.contiguous(), "sum"), None
+
+
 class Unmerge(_PlanCallable):
     def __call__(self, x: torch.Tensor) -> torch.Tensor:                    # merge.py:87-100
+        if _needs_grad(x):
+            if self.plan.distill_token:
+                raise NotImplementedError("tome_b200: unmerge backward with a distillation token is not supported")
+            return _UnmergeGrad.apply(x, self.plan)
         return _native.unmerge(self.plan, x)
 
 
@@ -291,61 +309,56 @@ def merge_source(merge: Callable, x: torch.Tensor, source: torch.Tensor = None) 
 
 
 # ---- upstream-ToMe variants with no caller in the reference (merge.py:105-212) -------------
+# Both match two ARBITRARY token sets (sources -> destinations) and merge EVERY source.  Here a set is an index
+# list into the token axis (``_native.TokenSets``) and the work runs in three kernels of the C ABI:
+# ``tome_match_sets`` (canonical scores, best destination per source, lowest index on ties), ``tome_group_reduce``
+# (the out-of-place scatter_reduce with include_self, reference CPU order) and ``tome_gather_rows`` (unmerge).
+class _SetMerge:
+    def __init__(self, sets, dst_row):
+        self.sets, self.dst_row = sets, dst_row
+        self.dst_idx = dst_row.long()[..., None]          # what the reference closure captures
+
+    def __call__(self, x: torch.Tensor, mode="mean") -> torch.Tensor:
+        return _native.group_reduce(x, self.sets, self.dst_row, mode)
+
+
+class _SetUnmerge:
+    def __init__(self, row_of_token):
+        self.row_of_token = row_of_token                  # (bm, tokens out): merged row each original token reads
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        return _native.gather_rows(x, self.row_of_token)
+
+
 def kth_bipartite_soft_matching(metric: torch.Tensor, k: int) -> Tuple[Callable, Callable]:
+    """Every k-th token is a destination, the k - 1 before it are sources (merge.py:105-158); tokens / k remain.
+    A ragged tail (tokens % k) is ignored, as in the reference."""
     if k <= 1:
         return do_nothing, do_nothing
-
-    def split(x):
-        t_rnd = (x.shape[1] // k) * k
-        x = x[:, :t_rnd, :].view(x.shape[0], -1, k, x.shape[2])
-        return x[:, :, :k - 1, :].contiguous().view(x.shape[0], -1, x.shape[-1]), x[:, :, k - 1, :]
-
+    bm, n, _ = metric.shape
+    groups = n // k
+    dev = metric.device
+    token = torch.arange(groups * k, device=dev, dtype=torch.int32).view(groups, k)
+    sets = _native.TokenSets(token[:, :k - 1].reshape(-1), token[:, k - 1])
     with torch.no_grad():
-        metric = metric / metric.norm(dim=-1, keepdim=True)
-        a, b = split(metric)
-        r = a.shape[1]
-        dst_idx = (a @ b.transpose(-1, -2)).argmax(dim=-1)[..., None]
-
-    def merge(x, mode="mean"):
-        src, dst = split(x)
-        n, _, c = src.shape
-        return dst.scatter_reduce(-2, dst_idx.expand(n, r, c), src, reduce=mode)
-
-    def unmerge(x):
-        n, _, c = x.shape
-        src = x.gather(dim=-2, index=dst_idx.expand(n, r, c)).to(x.dtype).view(n, -1, k - 1, c)
-        return torch.cat([src, x.view(n, -1, 1, c)], dim=-2).contiguous().view(n, -1, c)
-
-    return merge, unmerge
+        _, dst_row = _native.match_sets(metric, sets)
+    own = torch.arange(groups, device=dev, dtype=torch.int32).expand(bm, groups)
+    row_of_token = torch.cat((dst_row.view(bm, groups, k - 1), own[..., None]), dim=2).reshape(bm, groups * k)
+    return _SetMerge(sets, dst_row), _SetUnmerge(row_of_token)
 
 
 def random_bipartite_soft_matching(metric: torch.Tensor, r: int) -> Tuple[Callable, Callable]:
+    """r randomly chosen sources, everything else a destination (merge.py:161-212); tokens - r remain.  The
+    draw is the reference's own call (``torch.rand(B, N, 1)`` on metric's device), so the same generator state
+    gives the same partition."""
     if r <= 0:
         return do_nothing, do_nothing
+    bm, n, _ = metric.shape
+    dev = metric.device
     with torch.no_grad():
-        B, N, _ = metric.shape
-        rand_idx = torch.rand(B, N, 1, device=metric.device).argsort(dim=1)
-        a_idx, b_idx = rand_idx[:, :r, :], rand_idx[:, r:, :]
-
-        def split(x):
-            C = x.shape[-1]
-            return x.gather(dim=1, index=a_idx.expand(B, r, C)), x.gather(dim=1, index=b_idx.expand(B, N - r, C))
-
-        metric = metric / metric.norm(dim=-1, keepdim=True)
-        a, b = split(metric)
-        dst_idx = (a @ b.transpose(-1, -2)).argmax(dim=-1)[..., None]
-
-    def merge(x, mode="mean"):
-        src, dst = split(x)
-        C = src.shape[-1]
-        return dst.scatter_reduce(-2, dst_idx.expand(B, r, C), src, reduce=mode)
-
-    def unmerge(x):
-        C = x.shape[-1]
-        src = x.gather(dim=-2, index=dst_idx.expand(B, r, C))
-        out = torch.zeros(B, N, C, device=x.device, dtype=x.dtype)
-        out.scatter_(dim=-2, index=a_idx.expand(B, r, C), src=src)
-        out.scatter_(dim=-2, index=b_idx.expand(B, N - r, C), src=x)
-        return out
-
-    return merge, unmerge
+        order = torch.rand(bm, n, 1, device=dev).argsort(dim=1)[..., 0]
+        sets = _native.TokenSets(order[:, :r], order[:, r:])
+        _, dst_row = _native.match_sets(metric, sets)
+        rows = torch.cat((dst_row, torch.arange(n - r, device=dev, dtype=torch.int32).expand(bm, n - r)), dim=1)
+        row_of_token = torch.empty(bm, n, device=dev, dtype=torch.int32).scatter_(1, order, rows)
+    return _SetMerge(sets, dst_row), _SetUnmerge(row_of_token)

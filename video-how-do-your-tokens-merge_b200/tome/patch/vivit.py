@@ -21,10 +21,20 @@ from tome.patch.videomae import _fusable_residual, _normed_or, _swap, _wavg, laz
 from tome.utils import parse_r
 
 
+def _reject_unsupported(head_mask, output_attentions):
+    """The reference multiplies the attention probabilities by ``head_mask`` and can return them (vivit.py:113-128);
+    the fused attention here never materialises them, so asking for either is an error, not a silent no-op."""
+    if head_mask is not None:
+        raise NotImplementedError("tome.patch.vivit: head_mask is not supported by the fused attention path")
+    if output_attentions:
+        raise NotImplementedError("tome.patch.vivit: output_attentions=True is not supported (probabilities are never materialised)")
+
+
 class ToMeVivitLayerMixin:
     """vivit.py:17-47."""
 
     def forward(self, hidden_states, head_mask=None, output_attentions=False, **kwargs):
+        _reject_unsupported(head_mask, output_attentions)
         info = self._tome_info
         attn_size = info["size"] if info["prop_attn"] else None
         attn_bias = info.get("log_size") if info["prop_attn"] else None
@@ -41,6 +51,7 @@ class ToMeDuplicateVivitLayerMixin:
     """vivit.py:50-66."""
 
     def forward(self, hidden_states, head_mask=None, output_attentions=False, **kwargs):
+        _reject_unsupported(head_mask, output_attentions)
         info = self._tome_info
         attn_size = info["size"] if info["prop_attn"] else None
         attn_bias = info.get("log_size") if info["prop_attn"] else None
@@ -86,7 +97,10 @@ class ToMeVivitSelfAttentionMixin:
                 if log_size is None:
                     log_size = size.log()
                 bias = log_size[:, None, None, :, 0].to(q.dtype).expand(B, 1, N, N)
-            ctx = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, scale=d ** -0.5)
+            # attention-probability dropout in training (vivit.py:110: self.dropout(attention_probs))
+            p_drop = self.dropout.p if isinstance(getattr(self, "dropout", None), torch.nn.Dropout) else float(getattr(self, "dropout_prob", 0.0))
+            ctx = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, scale=d ** -0.5,
+                                                 dropout_p=p_drop if self.training else 0.0)
             ctx = ctx.transpose(1, 2).reshape(B, N, h * d)
         if head_aggregation == 'mean':
             metric = early["metric"]
