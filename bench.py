@@ -4,12 +4,20 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 Workload (configs[1]): VideoMAE ViT-B 16x224, ToMe merge mode, constant r schedule
-(model.r = (r, 0), r = 100), 8 synthetic clips per GPU, random-init weights, bf16 model,
-fp32 matching.  A step = one forward of one batch through the patched model.  Prints ONE JSON
-line (see the task contract): clips/s with inputs resident in HBM (`value`), the same
-through host buffers (`e2e`), the roofline of the dominant hot-path kernel (merge_wavg,
-HBM-bound), and the CPU baseline (oracle/torch_port.py, the reference's ATen call mix,
-timed on this box's host cores).
+(model.r = (r, 0), r = 100), 8 synthetic clips per GPU, random-init weights.  A step = one forward of
+one batch through the patched model.  Prints ONE JSON line (see the task contract):
+  * `value` / `e2e`: clips/s of the fp32 model -- the reference's own precision (its benchmark,
+    slowfast/utils/model_benchmark.py:21-45, runs fp32 without autocast; TF32 stays off like torch's
+    default) -- with inputs resident in HBM, and through pinned host buffers (uint8 frames -> H2D ->
+    forward -> logits D2H);
+  * `bf16`: the same two numbers for the bf16 model (fp32 matching), a named extra;
+  * `models`: clips/s of the other BASELINE.json configs at this run's GPU count -- TimeSformer bf16 r=18
+    (config 3), Motionformer r=18 (config 4), ViViT r in {0, 300, 1568} and hybrid 0.4 (config 5);
+  * `roofline`: the dominant hot-path kernel (the fused merge: residual add + merge_wavg + sizes + LayerNorm,
+    HBM-bound) at the layer-0 shape with inputs AND outputs rotating through more than L2, plus the figure
+    weighted over the 12 layer shapes of the token schedule;
+  * `cpu_baseline`: the reference's CPU path (oracle/torch_port.py, kind "port") on this box's host cores:
+    whole model, and the config-1 microbench (matching + merge_wavg at B=4, N=1568).
 
 Multi-GPU: pure data parallelism, one process per GPU (torchrun), weights replicated from
 the same seed, no collective on the data path; logits are all-gathered once per step over
@@ -50,12 +58,14 @@ def parse_args():
     ap.add_argument("--schedule", type=float, default=0.0, help="r inflection: 0 const, -1 decreasing, +1 increasing")
     ap.add_argument("--mode", default="merge")
     ap.add_argument("--prop-attn", type=int, default=0, help="VideoMAE default False (videomae.py:173)")
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--dtype", default="fp32", choices=["bf16", "fp32"],
+                    help="precision of the HEADLINE line (value / e2e); the other one is reported as a named extra")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--match-algo", type=int, default=0, help="0 auto, 1 exact SIMT, 2 tcgen05")
     ap.add_argument("--cpu-clips", type=int, default=8, help="clips per CPU-baseline step (default: the GPU arm's batch)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-micro", action="store_true")
+    ap.add_argument("--skip-models", action="store_true", help="leave out the `models` key (configs 3-5)")
     return ap.parse_args()
 
 
@@ -159,17 +169,45 @@ class ClockSampler:
                 "samples": len(sm), "source": self.source}
 
 
-def build_videomae(device, dtype, args):
+MODELS = {
+    # name: (frames, r, patch kwargs)  -- BASELINE.json configs 2-5, r / mode as experiments.sh:17-18,124-126,395-428
+    "videomae": (16, (100, 0.0), dict(prop_attn=False)),
+    "timesformer": (8, (18, 0.0), dict()),
+    "motionformer": (16, (18, 0.0), dict()),
+    "vivit": (32, (300, 0.0), dict()),
+}
+
+
+def build_model(name, device, dtype, r=None, patch_kw=None, args=None):
+    """Host model (random init, seed 0) + tome.patch.<name>; ``r`` None = unpatched."""
     import hostmodels
     import tome
     torch.manual_seed(0)
-    model = hostmodels.VideoMAE(arch="vit_base_patch16_224", num_classes=NUM_CLASSES, num_frames=FRAMES,
-                                tubelet_size=2, use_mean_pooling=True, init_scale=0.001).eval()
-    model = model.to(device=device, dtype=dtype)
-    tome.patch.videomae(model, trace_source=False, prop_attn=bool(args.prop_attn), mode=args.mode,
-                        head_aggregation="mean", threshold=0.8)
-    model.r = (args.r, args.schedule)
+    frames = MODELS[name][0]
+    if name == "videomae":
+        model = hostmodels.VideoMAE(arch="vit_base_patch16_224", num_classes=NUM_CLASSES, num_frames=frames,
+                                    tubelet_size=2, use_mean_pooling=True, init_scale=0.001)
+    elif name == "timesformer":
+        model = hostmodels.TimeSformer(num_classes=NUM_CLASSES, num_frames=frames)
+    elif name == "motionformer":
+        model = hostmodels.Motionformer(num_classes=NUM_CLASSES, num_frames=frames)
+        # as constructed every frame embeds identically (zeroed 3-D patch weight, zero temp_embed: SURVEY.md 8a quirks)
+        torch.nn.init.trunc_normal_(model.patch_embed_3d.proj.weight, std=0.02)
+        torch.nn.init.trunc_normal_(model.temp_embed, std=0.02)
+    elif name == "vivit":
+        model = hostmodels.ViViT(num_classes=NUM_CLASSES, num_frames=frames)
+    else:
+        raise KeyError(name)
+    model = model.eval().to(device=device, dtype=dtype)
+    if r is not None:
+        getattr(tome.patch, name)(model, trace_source=False, **(patch_kw or {}))
+        model.r = r
     return model
+
+
+def build_videomae(device, dtype, args):
+    return build_model("videomae", device, dtype, (args.r, args.schedule),
+                       dict(prop_attn=bool(args.prop_attn), mode=args.mode, head_aggregation="mean", threshold=0.8))
 
 
 def token_schedule(args, depth=12, n0=1568):
@@ -221,6 +259,31 @@ def time_cpu_reference(args, steps, warmup):
                       f"oracle/torch_port.py merge path, {mean * 1e3:.0f} ms/step"}, mean
 
 
+def time_cpu_config1():
+    """SURVEY.md 8(d) config 1 on the host cores: bipartite_soft_matching + merge_wavg of the reference's ATen call
+    mix (oracle/torch_port.py) at B=4, N=1568, C=768, r=100 -- M1: metric = x (Cm = 768, the literal BASELINE
+    shape), M1': metric (4, 1568, 64) (the in-model k.mean(1) shape).  3 warm-up + 20 timed, median."""
+    from oracle import torch_port as P
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(4, 1568, 768, generator=g)
+    m64 = torch.randn(4, 1568, 64, generator=g)
+    out = {"cores": cores, "torch_threads": torch.get_num_threads(), "shape": "B=4 N=1568 C=768 r=100 fp32",
+           "protocol": "3 warm-up + 20 timed, median; oracle/torch_port.py (kind port)"}
+    for key, metric in (("M1_metric_is_x_cm768", x), ("M1p_cm64", m64)):
+        ts = []
+        for i in range(23):
+            t0 = time.perf_counter()
+            merge, _ = P.bipartite_soft_matching(metric, 100)
+            P.merge_wavg(merge, x)
+            ts.append(time.perf_counter() - t0)
+        ts = sorted(ts[3:])
+        med = ts[len(ts) // 2]
+        out[key] = {"ms": med * 1e3, "clips_per_s": 4 / med}
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # reference arm
 # ------------------------------------------------------------------------------------------
@@ -257,8 +320,8 @@ def workload_config(args, cpu=False):
         "token_schedule": [n for n, _ in token_schedule(args)],
         "parallelism": f"dp{args.gpus}",
         "cuda_graph": not args.no_graph,
-        "l2": "each step reads a different resident input batch (4 x 38.5 MB rotate) and 172 MB of bf16 weights: "
-              "working set > 126 MB L2",
+        "l2": "each step reads a different resident input batch (4 rotate) and the model's weights (344 MB fp32 / "
+              "172 MB bf16): working set > 126 MB L2",
     }
 
 
@@ -294,61 +357,131 @@ def graph_time(fns, reps=20):
     return sum(ts) / len(ts), ts[len(ts) // 2]
 
 
-def micro_kernels(args, device, dtype):
-    """Device time of the hot-path kernels at the workload's layer-0 shape.  Each kernel is
-    captured once per rotating input (inputs total > L2, so every launch reads cold HBM like the
-    first touch in a forward) in one CUDA graph; time per launch = replay time / launches, CUDA
-    events on the replaying stream.  Returns (roofline dict for merge_wavg, per-kernel dict)."""
-    from tome import _native
-    peaks = {}
+def load_peaks():
     try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
-        pass
+        return {}
+
+
+def merge_alg_bytes(bm, n, r, c, e, fused):
+    """Algorithmic bytes of one merge launch (DESIGN.md section 4 / SURVEY.md 8d kernel 3): read x (and the residual)
+    once, write x' (and LayerNorm(x')) once, sizes in / out + log sizes, plan indices."""
+    na = (n + 1) // 2
+    k = 2 if fused else 1
+    return bm * (k * n * c * e + k * (n - r) * c * e + (n - r) * 8 + na * 12)
+
+
+class MergeBench:
+    """The fused merge launch of the patched block (tome/patch/videomae.py: `x + attn` on the way in, merge_wavg +
+    sizes + log sizes, norm2 on the way out -- ONE merge_gather_kernel<LN, RES>) at one (n, r), with inputs AND
+    outputs rotating through more than the 126 MB L2: every launch reads cold HBM and its output lines are
+    evicted to HBM by the launches that follow, so bytes / time is an HBM figure, not an L2 one."""
+
+    def __init__(self, device, dtype, bm, n, r, c=768, cm=64, fused=True, seed=1):
+        from tome import _native
+        self.native, self.fused = _native, fused
+        e = 2 if dtype == torch.bfloat16 else 4
+        self.bytes = merge_alg_bytes(bm, n, r, c, e, fused)
+        per_launch_out = bm * (n - r) * c * e
+        self.nrot = max(3, int(math.ceil(1.5 * L2_BYTES / per_launch_out)))
+        g = torch.Generator(device=device).manual_seed(seed)
+        rnd = lambda *s: torch.randn(*s, device=device, dtype=dtype, generator=g)      # noqa: E731
+        self.xs = [rnd(bm, n, c) for _ in range(self.nrot)]
+        self.rs = [rnd(bm, n, c) for _ in range(self.nrot)] if fused else None
+        self.outs = [(torch.empty(bm, n - r, c, device=device, dtype=dtype), torch.empty(bm, n - r, device=device),
+                      torch.empty(bm, n - r, device=device),
+                      torch.empty(bm, n - r, c, device=device, dtype=dtype) if fused else None) for _ in range(self.nrot)]
+        self.plan = _native.plan_build(torch.randn(bm, n, cm, device=device, generator=g), r)
+        self.lw = torch.ones(c, device=device, dtype=dtype)
+        self.lb = torch.zeros(c, device=device, dtype=dtype)
+        self.note = (f"{self.nrot} launches over rotating inputs and outputs ({self.nrot * per_launch_out >> 20} MiB of outputs > L2) "
+                     "captured in one CUDA graph, CUDA events around the replay, / launches")
+
+    def launch(self, i):
+        if self.fused:
+            return self.native.merge(self.plan, self.xs[i], "wavg", want_size=True, norm=(self.lw, self.lb, 1e-6),
+                                     residual=self.rs[i], out=self.outs[i])
+        return self.native.merge(self.plan, self.xs[i], "wavg", want_size=True, out=self.outs[i][:3])
+
+    def time(self, reps=20):
+        return graph_time([lambda i=i: self.launch(i) for i in range(self.nrot)], reps=reps)
+
+
+def measured_traffic(bm, n, r, dtype_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused merge kernel, from THIS round's ncu
+    capture if one was committed (profiles/r02_merge_traffic.json, written by tools/ncu_traffic.py); None otherwise."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r02_merge_traffic.json")))
+    except Exception:
+        return None, None
+    for e in rec.get("entries", []):
+        if (e.get("bm"), e.get("n"), e.get("r"), e.get("dtype")) == (bm, n, r, dtype_name):
+            return e.get("dram_bytes_per_launch"), {k: e.get(k) for k in ("source", "mode", "dram_bytes_read", "dram_bytes_write", "launches")}
+    return None, None
+
+
+def micro_kernels(args, device, dtype):
+    """Device time of the hot-path kernels at the workload's shapes.  Returns (roofline dict for the fused merge,
+    per-kernel dict)."""
+    from tome import _native
+    peaks = load_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    dname = "bf16" if dtype == torch.bfloat16 else "fp32"
     bm, n, c, cm, r = args.batch, 1568, 768, 64, min(args.r, 784)
-    e = 2 if dtype == torch.bfloat16 else 4
-    nrot = max(2, int(math.ceil(1.5 * L2_BYTES / (bm * n * c * e))))
-    g = torch.Generator(device=device).manual_seed(1)
-    xs = [torch.randn(bm, n, c, device=device, dtype=dtype, generator=g) for _ in range(nrot)]
-    ms = [torch.randn(bm, n, cm, device=device, dtype=dtype, generator=g) for _ in range(nrot)]
-    res = {}
-    nm, ni = _native.match(ms[0], algo=args.match_algo)
-    plan = _native.select(nm, ni, n, r)
     na = (n + 1) // 2
-    # The merge as the patched block runs it (tome/patch/videomae.py): the block's `x + attn` on the way in,
-    # merge_wavg + sizes + log sizes, and the block's norm2 on the way out -- ONE launch of merge_gather_kernel.
-    rs = [torch.randn(bm, n, c, device=device, dtype=dtype, generator=g) for _ in range(nrot)]
-    lw = torch.ones(c, device=device, dtype=dtype)
-    lb = torch.zeros(c, device=device, dtype=dtype)
-    mean_us, med_us = graph_time([lambda i=i: _native.merge(plan, xs[i], "wavg", want_size=True, norm=(lw, lb, 1e-6),
-                                                            residual=rs[i]) for i in range(nrot)])
-    alg_bytes = bm * (2 * n * c * e + 2 * (n - r) * c * e + (n - r) * 8 + na * 12)
-    achieved = alg_bytes / (mean_us * 1e-6) / 1e9
+    res = {}
+    mb = MergeBench(device, dtype, bm, n, r, c, cm, fused=True)
+    mean_us, med_us = mb.time()
+    achieved = mb.bytes / (mean_us * 1e-6) / 1e9
+    traffic, traffic_src = measured_traffic(bm, n, r, dname)
     roofline = {"kernel": "merge_gather_kernel<LN, RES> (residual add + merge_wavg + size + log size + LayerNorm, as the "
-                          f"patched block launches it; layer-0 shape Bm={bm} N={n} C={c} r={r} {args.dtype})",
+                          f"patched block launches it; layer-0 shape Bm={bm} N={n} C={c} r={r} {dname})",
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": MERGE_DRAM_TRAFFIC_NCU.get((bm, args.dtype)), "algorithmic_bytes": alg_bytes,
-                "us_mean": mean_us, "us_median": med_us, "peak_source": peak_src,
-                "timing": f"{nrot} launches over rotating inputs (2 x {nrot * bm * n * c * e >> 20} MiB > L2) captured in "
-                          "one CUDA graph, cuda events around the replay, / launches"}
-    p_mean, p_med = graph_time([lambda i=i: _native.merge(plan, xs[i], "wavg", want_size=True) for i in range(nrot)])
-    p_bytes = bm * (n * c * e + (n - r) * c * e + (n - r) * 8 + na * 12)
-    res["merge_wavg_plain"] = {"us_mean": p_mean, "us_median": p_med, "algorithmic_bytes": p_bytes,
-                               "GBps": p_bytes / (p_mean * 1e-6) / 1e9, "frac": p_bytes / (p_mean * 1e-6) / 1e9 / hbm_peak,
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": mb.bytes,
+                "us_mean": mean_us, "us_median": med_us, "peak_source": peak_src, "timing": mb.note}
+    del mb
+    # the same launch over the 12 layer shapes of the token schedule: sum of bytes / sum of time
+    tot_b, tot_us, per_layer = 0, 0.0, []
+    for (ln, lr) in token_schedule(args):
+        if lr <= 0:
+            continue
+        lb = MergeBench(device, dtype, bm, ln, lr, c, cm, fused=True, seed=ln)
+        l_mean, _ = lb.time(reps=10)
+        per_layer.append({"n": ln, "r": lr, "us": l_mean, "frac": lb.bytes / (l_mean * 1e-6) / 1e9 / hbm_peak})
+        tot_b += lb.bytes
+        tot_us += l_mean
+        del lb
+    roofline["schedule_weighted"] = {"achieved": tot_b / (tot_us * 1e-6) / 1e9, "frac": tot_b / (tot_us * 1e-6) / 1e9 / hbm_peak,
+                                     "us_total": tot_us, "algorithmic_bytes_total": tot_b, "layers": per_layer}
+    pb = MergeBench(device, dtype, bm, n, r, c, cm, fused=False)
+    p_mean, p_med = pb.time()
+    res["merge_wavg_plain"] = {"us_mean": p_mean, "us_median": p_med, "algorithmic_bytes": pb.bytes,
+                               "GBps": pb.bytes / (p_mean * 1e-6) / 1e9, "frac": pb.bytes / (p_mean * 1e-6) / 1e9 / hbm_peak,
                                "kernels": "merge_gather_kernel (merge_wavg + size + log size only: tome.merge.merge_wavg)"}
-    m_mean, m_med = graph_time([lambda i=i: _native.match(ms[i % nrot], algo=args.match_algo) for i in range(8)])
+    del pb
+    g = torch.Generator(device=device).manual_seed(2)
+    ms = [torch.randn(bm, n, cm, device=device, dtype=dtype, generator=g) for _ in range(8)]
+    m_mean, m_med = graph_time([lambda i=i: _native.match(ms[i], algo=args.match_algo) for i in range(8)])
     flops = 2.0 * bm * na * (n // 2) * cm
+    tf_sus = float(peaks.get("bf16_tflops_sustained", 1417.0))
     res["match"] = {"us_mean": m_mean, "us_median": m_med, "algorithmic_gflop": flops / 1e9,
                     "tflops_algorithmic": flops / (m_mean * 1e-6) / 1e12, "algo": args.match_algo or "auto",
-                    "kernels": "split_rows_kernel + match_tc_kernel (bf16 h.h+h.m+m.h on tcgen05, exact fp64 refine in the epilogue)"}
+                    "kernels": "kernel 1 (tome_match): normalise + bf16-split tcgen05 contraction + exact fp64 refine"}
     ks = [torch.randn(bm, n, 3, 12, cm, device=device, dtype=dtype, generator=g).permute(2, 0, 3, 1, 4)[1] for _ in range(4)]
-    p_mean, p_med = graph_time([lambda i=i: _native.plan_build(_native.HeadMeanMetric(ks[i % 4]), r) for i in range(8)])
-    res["plan_build_heads12"] = {"us_mean": p_mean, "us_median": p_med,
-                                 "kernels": "tome_plan_build on the lazy head-mean of K (12 heads): split_rows + match_tc + rank + finish"}
+    for (ln, lr) in ((n, r), (468, min(r, 234))):
+        kl = [k[:, :, :ln] for k in ks]
+        p_mean, p_med = graph_time([lambda i=i: _native.plan_build(_native.HeadMeanMetric(kl[i % 4]), lr) for i in range(8)])
+        # bound of kernels 1 + 2 together: the K read (12 heads) + plan written, and the contraction on the tensor pipe
+        kb = bm * ln * 12 * cm * (2 if dtype == torch.bfloat16 else 4) + bm * ((ln + 1) // 2) * 24
+        fl = 2.0 * bm * ((ln + 1) // 2) * (ln // 2) * cm
+        bound_us = max(kb / (hbm_peak * 1e9), fl / (tf_sus * 1e12)) * 1e6
+        res[f"plan_build_heads12_n{ln}"] = {"us_mean": p_mean, "us_median": p_med, "bound_us": bound_us, "frac_of_bound": bound_us / p_mean,
+                                            "kernels": "tome_plan_build on the lazy head-mean of K (12 heads): kernels 1 + 2"}
+    nm, ni = _native.match(ms[0], algo=args.match_algo)
     s_mean, s_med = graph_time([lambda: _native.select(nm, ni, n, r) for _ in range(8)])
-    res["select"] = {"us_mean": s_mean, "us_median": s_med, "kernels": "rank_kernel + finish_kernel"}
+    res["select"] = {"us_mean": s_mean, "us_median": s_med, "kernels": "kernel 2 (tome_select)"}
     if dtype == torch.bfloat16:
         # caller-side tensor-core kernel (SURVEY 8f-f2): the MLP's fc1 + bias + erf GELU as one tcgen05 GEMM,
         # against the library GEMM + elementwise GELU it replaces, at the layer-0 shape
@@ -366,23 +499,168 @@ def micro_kernels(args, device, dtype):
                               "library_gemm_plus_gelu_us": t_mean,
                               "kernels": "linear_gelu_kernel (persistent tcgen05 GEMM 128x256x64, TMEM double-buffered, "
                                          "bias + erf GELU + TMA store in the epilogue)"}
-    c_mean, _ = graph_time([lambda i=i: xs[i].clone() for i in range(nrot)])
-    res["torch_clone_same_bytes"] = {"us_mean": c_mean, "GBps": 2 * bm * n * c * e / (c_mean * 1e-6) / 1e9}
+    xs = [torch.randn(bm, n, c, device=device, dtype=dtype, generator=g) for _ in range(12)]
+    ys = [torch.empty_like(xs[0]) for _ in range(12)]
+    c_mean, _ = graph_time([lambda i=i: ys[i].copy_(xs[i]) for i in range(12)])
+    e = 2 if dtype == torch.bfloat16 else 4
+    res["torch_copy_same_shape"] = {"us_mean": c_mean, "GBps": 2 * bm * n * c * e / (c_mean * 1e-6) / 1e9}
     return roofline, res
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of merge_gather_kernel<LN, RES> from the committed
-# `ncu --set full` capture (profiles/r01d_hotpath_ncu.txt): 38.73 MB read (x + residual, the input half of the
-# 74.8 algorithmic MB) + 1.13 MB written back -- the 36 MB of output mostly stay in the 126 MB L2 under ncu.
-MERGE_DRAM_TRAFFIC_NCU = {(8, "bf16"): 38726912 + 1131264}
+def capture(fn):
+    """Warm `fn` on a side stream, then capture it into a CUDA graph; returns (graph, static output)."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = fn()
+    return graph, out
 
 
-# share of one step's kernel time per kernel, from the committed ncu launch list of this command
-# (profiles/r01e_launch_summary.txt; cold-cache and serialised, so shares, not absolutes)
-STEP_SHARES_NCU = {"source": "profiles/r01e_launch_summary.txt", "cuBLAS GEMMs": 0.307, "cuDNN attention": 0.230,
-                   "linear_gelu_kernel": 0.185, "match_tc_kernel": 0.065, "merge_gather_kernel<LN,RES>": 0.062,
-                   "add_layernorm_kernel": 0.049, "split_rows_kernel": 0.032, "rank_kernel": 0.024, "finish_kernel": 0.023,
-                   "patchify_kernel": 0.011, "libtome_b200 total": 0.451}
+def measure_forward(model, frames, dtype, args, device, rank, world, steps, warmup, want_e2e, sample_clocks=False):
+    """clips/s of one patched model: `value` with inputs resident in HBM (rotating through 4 batches) and, when
+    ``want_e2e``, through pinned host buffers.  Exactly `steps` timed steps after `warmup` (>= 3) untimed ones,
+    barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks."""
+    from tome import _native
+    B, nrot = args.batch, 4
+    g = torch.Generator(device=device).manual_seed(1234 + rank)
+    resident = [torch.rand(B, 3, frames, CROP, CROP, device=device, generator=g).to(dtype) for _ in range(nrot)]
+    static_in = torch.empty_like(resident[0])
+    logits_all = torch.empty(world * B, NUM_CLASSES, device=device, dtype=torch.float32) if world > 1 else None
+
+    def forward():
+        return model([static_in]).float()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    res = {}
+    with torch.no_grad():
+        launches_before = _native.launch_count()
+        static_in.copy_(resident[0])
+        out = forward()
+        res["launches_per_step"] = _native.launch_count() - launches_before
+        for i in range(3):
+            static_in.copy_(resident[i % nrot])
+            out = forward()
+        torch.cuda.synchronize()
+        graph, static_out = (None, None) if args.no_graph else capture(forward)
+
+        def step(i):
+            static_in.copy_(resident[i % nrot], non_blocking=True)
+            if graph is not None:
+                graph.replay()
+                o = static_out
+            else:
+                o = forward()
+            if world > 1:
+                torch.distributed.all_gather_into_tensor(logits_all, o)
+            return o
+
+        for i in range(max(warmup, 3)):
+            step(i)
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with (ClockSampler(device.index) if sample_clocks else contextlib.nullcontext()) as clocks:
+            barrier()
+            start.record()
+            for i in range(steps):
+                out = step(i)
+            end.record()
+            barrier()
+        res["ms"] = start.elapsed_time(end)
+        res["clocks"] = clocks.summary() if sample_clocks else None
+        res["top1"] = out.argmax(-1)[:4].tolist()
+        del graph, static_out
+
+        if want_e2e:
+            # pinned uint8 frames (what a decoder hands over) -> H2D on a copy stream, double-buffered -> forward
+            # (tome_patchify converts value / 255 to the model dtype in its own pass) -> logits D2H
+            host_in = [torch.randint(0, 256, (B, 3, frames, CROP, CROP), dtype=torch.uint8).pin_memory() for _ in range(2)]
+            host_out = torch.empty(B, NUM_CLASSES, dtype=torch.float32).pin_memory()
+            stage = [torch.empty(B, 3, frames, CROP, CROP, device=device, dtype=torch.uint8) for _ in range(2)]
+            copy_stream = torch.cuda.Stream()
+            main = torch.cuda.current_stream()
+            copied = [torch.cuda.Event() for _ in range(2)]
+            consumed = [torch.cuda.Event() for _ in range(2)]
+            graphs, outs = [None, None], [None, None]
+            if not args.no_graph:
+                for j in range(2):
+                    stage[j].copy_(host_in[j])
+                    graphs[j], outs[j] = capture(lambda j=j: model([stage[j]]).float())
+                torch.cuda.synchronize()
+
+            def e2e_loop(k):
+                for i in range(k + 1):
+                    if i < k:                     # prefetch step i's clips on the copy stream
+                        with torch.cuda.stream(copy_stream):
+                            if i >= 2:
+                                copy_stream.wait_event(consumed[i % 2])
+                            stage[i % 2].copy_(host_in[i % 2], non_blocking=True)
+                            copied[i % 2].record(copy_stream)
+                    if i >= 1:                    # run step i-1
+                        j = i - 1
+                        main.wait_event(copied[j % 2])
+                        if graphs[j % 2] is not None:
+                            graphs[j % 2].replay()
+                            o = outs[j % 2]
+                        else:
+                            o = model([stage[j % 2]]).float()
+                        consumed[j % 2].record(main)
+                        if world > 1:
+                            torch.distributed.all_gather_into_tensor(logits_all, o)
+                        host_out.copy_(o, non_blocking=True)
+
+            e2e_loop(max(warmup, 3))
+            barrier()
+            s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s2.record()
+            e2e_loop(steps)
+            e2.record()
+            barrier()
+            res["ms_e2e"] = s2.elapsed_time(e2)
+            res["h2d"] = B * 3 * frames * CROP * CROP
+            res["d2h"] = B * NUM_CLASSES * 4
+            del graphs, outs
+    keys = [k for k in ("ms", "ms_e2e") if k in res]
+    t = torch.tensor([res[k] for k in keys], device=device, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    for k, v in zip(keys, t.tolist()):
+        res[k] = v
+    del resident, static_in
+    torch.cuda.empty_cache()
+    return res
+
+
+def other_models(args, device, rank, world):
+    """BASELINE.json configs 3-5 at this run's GPU count (weak scaling, `batch` clips per GPU): clips/s through the
+    CUDA-graph forward, inputs resident in HBM, 10 timed steps after 3 warm-up.  Config 3 is bf16 by BASELINE's own
+    wording; the others are given at the reference's precision (fp32) and in bf16."""
+    runs = [("timesformer", torch.bfloat16, MODELS["timesformer"][1], {}, "config 3: TimeSformer divST 8x224, r=18 per frame, bf16")]
+    for dt in (torch.float32, torch.bfloat16):
+        runs.append(("motionformer", dt, MODELS["motionformer"][1], {}, "config 4: Motionformer 16x224 trajectory attention, r=18 per frame"))
+    for dt in (torch.float32, torch.bfloat16):
+        runs.append(("vivit", dt, None, {}, "config 5: ViViT-B 32x224, r=0 (unpatched)"))
+        runs.append(("vivit", dt, (300, 0.0), {}, "config 5: ViViT-B, merge r=300"))
+        runs.append(("vivit", dt, (1568, 0.0), {}, "config 5: ViViT-B, merge r=max (1568)"))
+        runs.append(("vivit", dt, (300, 0.0), dict(mode="hybrid", threshold=0.4), "config 5: ViViT-B, hybrid r=300 threshold 0.4"))
+    out = []
+    for name, dt, r, kw, label in runs:
+        model = build_model(name, device, dt, r, kw)
+        m = measure_forward(model, MODELS[name][0], dt, args, device, rank, world, steps=10, warmup=3, want_e2e=False)
+        out.append({"config": label, "model": name, "dtype": "bf16" if dt == torch.bfloat16 else "fp32",
+                    "r": list(r) if r else None, "mode": kw.get("mode", "merge") if r else None,
+                    "clips_per_s": world * args.batch * 10 / (m["ms"] * 1e-3), "ms_per_step": m["ms"] / 10,
+                    "clips_per_gpu_per_step": args.batch, "steps": 10, "warmup": 3})
+        del model
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args):
@@ -396,168 +674,67 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     from tome import _native
     _native.device_check(local)
-    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     if args.match_algo:
         orig_match = _native.match
         _native.match = lambda metric, c=False, d=False, algo=0: orig_match(metric, c, d, algo=args.match_algo)
-    model = build_videomae(device, dtype, args)
+    args.warmup = max(args.warmup, 3)
+    head_dtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
+    other_dtype = torch.bfloat16 if args.dtype == "fp32" else torch.float32
     B = args.batch
-    nrot = 4
-    g = torch.Generator(device=device).manual_seed(1234 + rank)
-    resident = [torch.rand(B, 3, FRAMES, CROP, CROP, device=device, generator=g).to(dtype) for _ in range(nrot)]
-    static_in = torch.empty_like(resident[0])
-    logits_all = torch.empty(world * B, NUM_CLASSES, device=device, dtype=torch.float32) if world > 1 else None
 
-    def forward():
-        return model([static_in]).float()
+    model = build_videomae(device, head_dtype, args)
+    head = measure_forward(model, FRAMES, head_dtype, args, device, rank, world, args.steps, args.warmup, want_e2e=True,
+                           sample_clocks=True)
+    del model
+    torch.cuda.empty_cache()
+    model = build_videomae(device, other_dtype, args)
+    other = measure_forward(model, FRAMES, other_dtype, args, device, rank, world, args.steps, args.warmup, want_e2e=True)
+    del model
+    torch.cuda.empty_cache()
+    models = None if args.skip_models else other_models(args, device, rank, world)
 
-    # warm-up (eager: lazy init, cuBLAS handles, kernel attribute setup), then graph capture
-    launches_before = _native.launch_count()
-    with torch.no_grad():
-        static_in.copy_(resident[0])
-        out = forward()
-        launches_per_step = _native.launch_count() - launches_before
-        for i in range(max(args.warmup, 3)):
-            static_in.copy_(resident[i % nrot])
-            out = forward()
-        torch.cuda.synchronize()
-        graph = None
-        if not args.no_graph:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                forward()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                static_out = forward()
-        else:
-            static_out = None
-
-        def step(i):
-            static_in.copy_(resident[i % nrot], non_blocking=True)
-            if graph is not None:
-                graph.replay()
-                o = static_out
-            else:
-                o = forward()
-            if world > 1:
-                torch.distributed.all_gather_into_tensor(logits_all, o)
-            return o
-
-        for i in range(args.warmup):
-            step(i)
-        torch.cuda.synchronize()
-
-        def barrier():
-            if world > 1:
-                torch.distributed.barrier()
-            torch.cuda.synchronize()
-
-        # ---- value: inputs resident in HBM -------------------------------------------------
-        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local) as clocks:
-            barrier()
-            start.record()
-            for i in range(args.steps):
-                out = step(i)
-            end.record()
-            barrier()
-        ms = start.elapsed_time(end)
-        top1 = out.argmax(-1)
-
-        # ---- e2e: pinned host clips -> H2D -> forward -> logits D2H, copies overlapped -----
-        host_in = [torch.rand(B, 3, FRAMES, CROP, CROP).pin_memory() for _ in range(2)]
-        host_out = torch.empty(B, NUM_CLASSES, dtype=torch.float32).pin_memory()
-        stage = [torch.empty(B, 3, FRAMES, CROP, CROP, device=device) for _ in range(2)]
-        copy_stream = torch.cuda.Stream()
-        main = torch.cuda.current_stream()
-        copied = [torch.cuda.Event() for _ in range(2)]
-        consumed = [torch.cuda.Event() for _ in range(2)]
-        # one captured forward per staging buffer, reading the fp32 clips where the H2D copy put them: the cast to the
-        # model dtype happens inside tome_patchify, so there is no separate device-side cast / copy pass
-        e2e_graphs, e2e_outs = [None, None], [None, None]
-        if graph is not None:
-            for j in range(2):
-                stage[j].copy_(host_in[j])
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    model([stage[j]])
-                torch.cuda.current_stream().wait_stream(side)
-                torch.cuda.synchronize()
-                e2e_graphs[j] = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(e2e_graphs[j]):
-                    e2e_outs[j] = model([stage[j]]).float()
-            torch.cuda.synchronize()
-
-        def e2e_loop(k):
-            for i in range(k + 1):
-                if i < k:                     # prefetch step i's clips on the copy stream
-                    with torch.cuda.stream(copy_stream):
-                        if i >= 2:
-                            copy_stream.wait_event(consumed[i % 2])
-                        stage[i % 2].copy_(host_in[i % 2], non_blocking=True)
-                        copied[i % 2].record(copy_stream)
-                if i >= 1:                    # run step i-1
-                    j = i - 1
-                    main.wait_event(copied[j % 2])
-                    if graph is not None:
-                        e2e_graphs[j % 2].replay()
-                        o = e2e_outs[j % 2]
-                    else:
-                        o = model([stage[j % 2]]).float()
-                    consumed[j % 2].record(main)
-                    if world > 1:
-                        torch.distributed.all_gather_into_tensor(logits_all, o)
-                    host_out.copy_(o, non_blocking=True)
-
-        e2e_loop(2)
-        barrier()
-        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s2.record()
-        e2e_loop(args.steps)
-        e2.record()
-        barrier()
-        ms_e2e = s2.elapsed_time(e2)
-
-    times = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
-    if world > 1:
-        torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
-    ms, ms_e2e = float(times[0]), float(times[1])
-
-    roofline, kernels, cpu_baseline = None, None, None
+    roofline = roofline_other = kernels = kernels_other = cpu_baseline = None
     if rank == 0 and not args.skip_micro:
-        roofline, kernels = micro_kernels(args, device, dtype)
+        roofline, kernels = micro_kernels(args, device, head_dtype)
+        roofline_other, kernels_other = micro_kernels(args, device, other_dtype)
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
         cpu_baseline, _ = time_cpu_reference(args, steps=8, warmup=2)       # ~10 s of host work
+        cpu_baseline["config1_microbench"] = time_cpu_config1()
     if world > 1:
         torch.distributed.barrier()
 
     if rank == 0:
         total_clips = world * B * args.steps
-        h2d = B * 3 * FRAMES * CROP * CROP * 4
+
+        def pair(m):
+            return {"value": total_clips / (m["ms"] * 1e-3), "ms_per_step": m["ms"] / args.steps,
+                    "e2e": {"value": total_clips / (m["ms_e2e"] * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": m["h2d"],
+                            "d2h_bytes_per_step": m["d2h"], "ms_per_step": m["ms_e2e"] / args.steps,
+                            "note": "pinned uint8 frames -> H2D on a copy stream (double-buffered) -> forward (tome_patchify converts "
+                                    "value / 255 to the model dtype) -> logits D2H"}}
+
+        hp, op = pair(head), pair(other)
+        name_h, name_o = ("f32", "bf16") if args.dtype == "fp32" else ("bf16", "f32")
+        kern_lg = (kernels or {}).get("linear_gelu") or (kernels_other or {}).get("linear_gelu")
         line = {
-            "metric": "clips_per_sec", "value": total_clips / (ms * 1e-3), "unit": "clips/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "metric": "clips_per_sec", "value": hp["value"], "unit": "clips/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": hp["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": name_h, "data": "synthetic",
             "config": workload_config(args),
-            "clocks": clocks.summary(),
-            "e2e": {"value": total_clips / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": B * NUM_CLASSES * 4, "ms_per_step": ms_e2e / args.steps,
-                    "note": "pinned fp32 clips -> H2D on a copy stream (double-buffered) -> forward (tome_patchify casts to bf16) -> logits D2H"},
-            "gpu_launches": launches_per_step * args.steps,
-            "gpu_launches_per_step": launches_per_step,
+            "clocks": head["clocks"],
+            "e2e": hp["e2e"],
+            "gpu_launches": head["launches_per_step"] * args.steps,
+            "gpu_launches_per_step": head["launches_per_step"],
+            name_o: dict(op, gpu_launches_per_step=other["launches_per_step"],
+                         note=f"the same workload with a {name_o} model (matching always runs in fp32)"),
+            "models": models,
             "roofline": roofline,
-            # the caller-side tensor-core kernel (fc1 + GELU), the largest single kernel of libtome_b200 in the step
-            "roofline_tensor": (dict(kernels["linear_gelu"]["roofline"], kernel=kernels["linear_gelu"]["kernels"],
-                                     us_mean=kernels["linear_gelu"]["us_mean"])
-                                if kernels and "linear_gelu" in kernels else None),
-            "step_shares_ncu": STEP_SHARES_NCU,
-            "kernels": kernels, "cpu_baseline": cpu_baseline,
+            "roofline_" + name_o: roofline_other,
+            # the caller-side tensor-core kernel (fc1 + GELU of the bf16 model), the largest single kernel of libtome_b200 there
+            "roofline_tensor": (dict(kern_lg["roofline"], kernel=kern_lg["kernels"], us_mean=kern_lg["us_mean"]) if kern_lg else None),
+            "kernels": kernels, "kernels_" + name_o: kernels_other, "cpu_baseline": cpu_baseline,
             "match_algo": "auto" if not args.match_algo else args.match_algo,
-            "top1_sample": top1[:4].tolist(),
+            "top1_sample": head["top1"],
         }
         print(json.dumps(line), flush=True)
     if world > 1:

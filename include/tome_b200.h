@@ -50,7 +50,7 @@ typedef enum tome_status {
 /* Largest matching batch (clips, or clips * frames) one call takes: it rides on gridDim.y / gridDim.z. */
 #define TOME_MAX_BATCH 65535
 
-typedef enum tome_dtype { TOME_F32 = 0, TOME_BF16 = 1 } tome_dtype;
+typedef enum tome_dtype { TOME_F32 = 0, TOME_BF16 = 1, TOME_U8 = 2 /* tome_patchify input only */ } tome_dtype;
 
 /* tome_match algorithm.  Both produce the SAME canonical node_max/node_idx bits. */
 typedef enum tome_match_algo {
@@ -229,7 +229,9 @@ TOME_API int tome_attn_key_bias(const float* log_size, int32_t b, int32_t n, int
  * kernel equals its stride (slowfast/models/videomae_video_model_builder.py:138-160), i.e. a GEMM over
  * non-overlapping tubelets.  x (b, c, t, h, w) contiguous -> out (b, (t/tt)(h/ph)(w/pw), c*tt*ph*pw), token
  * order (t', h', w'), feature order (c, tt, ph, pw) = the flattened conv weight's; in_dtype -> out_dtype
- * conversion (fp32 clips to a bf16 model) happens in the same pass.  pw % 8 == 0. */
+ * conversion (fp32 clips to a bf16 model) happens in the same pass.  in_dtype TOME_U8: decoder-style uint8
+ * frames, converted as value / 255 (what `x.float() / 255` gives), so a clip crosses PCIe at one byte per
+ * sample.  pw % 8 == 0. */
 TOME_API int tome_patchify(const void* x, int32_t in_dtype, int32_t b, int32_t c, int32_t t, int32_t h, int32_t w,
                   int32_t tt, int32_t ph, int32_t pw, void* out, int32_t out_dtype, void* stream);
 
@@ -238,7 +240,8 @@ TOME_API int tome_patchify(const void* x, int32_t in_dtype, int32_t b, int32_t c
  * epilogue applies bias and activation, instead of a library GEMM plus an elementwise pass over the (m, n)
  * tensor.  bf16 only: x (m, k) with rows `x_row_stride` elements apart, W (n, k) and out (m, n) contiguous,
  * bias (n) or NULL; fp32 accumulation; the pre-activation is rounded to bf16 before the GELU, as the two
- * separate ops would.  gelu == 0: bias only.  n % 256 == 0, k % 8 == 0. */
+ * separate ops would.  gelu == 0: bias only; 1: erf GELU (nn.GELU); 2: HuggingFace "gelu_fast"
+ * (0.5 x (1 + tanh(0.7978845608 x (1 + 0.044715 x^2))), ViViT's hidden_act).  n % 256 == 0, k % 8 == 0. */
 TOME_API int tome_linear_gelu(const void* x, const void* w, const void* bias, int32_t m, int32_t n, int32_t k,
                      int64_t x_row_stride, int32_t gelu, void* out, void* stream);
 

@@ -484,6 +484,38 @@ def test_patchify_equals_permute_and_conv(native, dtypes):
         torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("dout", [torch.float32, torch.bfloat16])
+def test_patchify_takes_uint8_frames(native, dout):
+    """Decoder-style uint8 clips: tome_patchify converts value / 255 in the same pass, bit-identical to
+    `x.float() / 255` followed by the fp32 / bf16 patchify (19 MB instead of 77 MB over PCIe per 8 clips)."""
+    gen = torch.Generator(device="cuda").manual_seed(8)
+    B, C, T, H, W, tt, ph, pw = 2, 3, 4, 32, 48, 2, 16, 16
+    x8 = torch.randint(0, 256, (B, C, T, H, W), device="cuda", generator=gen, dtype=torch.uint8)
+    got = native.patchify(x8, tt, ph, pw, dout)
+    want = native.patchify(x8.float() / 255, tt, ph, pw, dout)
+    assert torch.equal(got, want)
+    import hostmodels
+    m = hostmodels.VideoMAE(arch="vit_small_patch16_224", num_classes=7, num_frames=4).eval().cuda().to(dout)
+    clip = torch.randint(0, 256, (1, 3, 4, 224, 224), device="cuda", generator=gen, dtype=torch.uint8)
+    with torch.no_grad():
+        a, b = m([clip]), m([(clip.float() / 255).to(dout)])
+    torch.testing.assert_close(a, b, rtol=1e-5 if dout == torch.float32 else 2e-2, atol=1e-5 if dout == torch.float32 else 2e-2)
+
+
+def test_merge_writes_into_caller_owned_buffers(native):
+    case = util.CASE_BY_NAME["gauss_odd"]
+    metric, x, size = util.case_arrays(case)
+    dp = native.plan_build(_dev(metric), case["r"])
+    xd = _dev(x)
+    want = native.merge(dp, xd, "wavg", size=_dev(size), want_size=True)
+    bufs = (torch.empty_like(want[0]), torch.empty_like(want[1]), torch.empty_like(want[2]))
+    got = native.merge(dp, xd, "wavg", size=_dev(size), want_size=True, out=bufs)
+    assert all(g.data_ptr() == b.data_ptr() for g, b in zip(got, bufs))
+    assert all(torch.equal(g, w) for g, w in zip(got, want))
+    with pytest.raises(RuntimeError, match="out buffer"):
+        native.merge(dp, xd, "wavg", out=(torch.empty(1, 2, 3, device="cuda"),))
+
+
 def test_add_layernorm_broadcasts_the_position_embedding(native):
     gen = torch.Generator(device="cuda").manual_seed(7)
     a = torch.randn(4, 50, 768, device="cuda", generator=gen).to(torch.bfloat16)
@@ -557,7 +589,7 @@ def test_merge_backward_matches_reference_autograd(native, name):
 
 
 @pytest.mark.parametrize("shape", [(300, 256, 64), (12544, 3072, 768), (3744, 3072, 768), (129, 512, 200)])
-@pytest.mark.parametrize("gelu", [True, False])
+@pytest.mark.parametrize("gelu", [True, False, "gelu_fast"])
 def test_linear_gelu_matches_linear_then_gelu(native, shape, gelu):
     """tome_linear_gelu (tcgen05 GEMM, bias + erf GELU in the epilogue) against F.linear followed by F.gelu on
     the same bf16 tensors: the two GEMMs accumulate in different orders, so outputs may differ by one bf16
@@ -569,11 +601,12 @@ def test_linear_gelu_matches_linear_then_gelu(native, shape, gelu):
     b = (0.1 * torch.randn(n, device="cuda", generator=gen)).to(torch.bfloat16)
     with torch.no_grad():
         assert native.linear_gelu_supported(x, w, b)
+    from hostmodels.vivit import gelu_fast                   # HF FastGELUActivation, ViViT's hidden_act
+    act = {True: torch.nn.functional.gelu, False: (lambda t: t), "gelu_fast": gelu_fast}[gelu]
     got = native.linear_gelu(x, w, b, gelu=gelu).float()
     pre = torch.nn.functional.linear(x, w, b)
-    lib = (torch.nn.functional.gelu(pre) if gelu else pre).float()
-    ref = x.float() @ w.float().t() + b.float()
-    ref = torch.nn.functional.gelu(ref) if gelu else ref
+    lib = act(pre).float()
+    ref = act(x.float() @ w.float().t() + b.float())
     err_ours, err_lib = (got - ref).abs().max().item(), (lib - ref).abs().max().item()
     print(f"[linear-gelu] {shape} gelu={gelu}: max err vs fp32 ours {err_ours:.3e} library {err_lib:.3e}")
     assert err_ours <= 1.5 * err_lib + 1e-3

@@ -31,7 +31,7 @@ struct LinearGeluParams {
   int m, n, k, num_kb, tiles_n, tiles;
   const __nv_bfloat16* bias;                          // (n) or NULL
   __nv_bfloat16* out;                                 // (m, n) row-major
-  int gelu;                                           // 0: plain linear (bias only)
+  int gelu;                                           // 0: plain linear (bias only), 1: erf GELU, 2: HF "gelu_fast" (tanh form)
 };
 
 // erf GELU.  libdevice's erff is two branches and ~50 instructions: with 32 k elements per tile the epilogue then
@@ -55,6 +55,15 @@ __device__ __forceinline__ float gelu_erf(float x) {
   const float e = exp2f_approx(x * x * -0.72134752044448170368f);
   const float u = (0.5f * ax) * (poly * t) * e;
   return fmaxf(x, 0.f) - u;
+}
+
+// HuggingFace FastGELUActivation (ViViT's hidden_act "gelu_fast", configs/vivit/kinetics/tome_vivit_8x32_224.json):
+// 0.5 x (1 + tanh(u)), u = 0.7978845608 x (1 + 0.044715 x^2)  ==  x / (1 + exp(-2u)).  One MUFU.EX2 + one MUFU.RCP,
+// evaluated in fp32 from the bf16-rounded pre-activation and rounded ONCE (the eager bf16 form rounds seven times).
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float u = x * 0.7978845608f * fmaf(0.044715f * x, x, 1.0f);
+  const float e = exp2f_approx(u * -2.8853900817779268f);        // exp(-2u)
+  return __fdividef(x, 1.0f + e);
 }
 
 __global__ void __launch_bounds__(LG_THREADS, 1)
@@ -161,10 +170,13 @@ linear_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float x0 = v[g4 * 8 + 2 * i] + bf[2 * i], x1 = v[g4 * 8 + 2 * i + 1] + bf[2 * i + 1];
-            if (p.gelu) {
+            if (p.gelu == 1) {
               // round to bf16 first: the value F.linear would have stored and nn.GELU would have read
               x0 = gelu_erf(__bfloat162float(__float2bfloat16_rn(x0)));
               x1 = gelu_erf(__bfloat162float(__float2bfloat16_rn(x1)));
+            } else if (p.gelu == 2) {
+              x0 = gelu_tanh_fast(__bfloat162float(__float2bfloat16_rn(x0)));
+              x1 = gelu_tanh_fast(__bfloat162float(__float2bfloat16_rn(x1)));
             }
             const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
             w[i] = *reinterpret_cast<const uint32_t*>(&h);

@@ -31,6 +31,17 @@ template <> struct In8<__nv_bfloat16> {
     for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
   }
 };
+// uint8 frames (what a video decoder hands over): value / 255, the division rounded like torch's `x.float() / 255`
+template <> struct In8<uint8_t> {
+  static __device__ __forceinline__ void load(const uint8_t* p, float (&f)[8]) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[i] = __fdiv_rn((float)((v.x >> (8 * i)) & 0xFFu), 255.0f);
+      f[4 + i] = __fdiv_rn((float)((v.y >> (8 * i)) & 0xFFu), 255.0f);
+    }
+  }
+};
 template <typename TO> struct Out8;
 template <> struct Out8<float> {
   static __device__ __forceinline__ void store(float* p, const float (&f)[8]) {
@@ -85,6 +96,8 @@ int launch_patchify(const void* x, int in_dtype, int b, int c, int t, int h, int
   else if (in_dtype == TOME_F32 && out_dtype == TOME_BF16) patchify_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(a);
   else if (in_dtype == TOME_BF16 && out_dtype == TOME_BF16) patchify_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(a);
   else if (in_dtype == TOME_BF16 && out_dtype == TOME_F32) patchify_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(a);
+  else if (in_dtype == TOME_U8 && out_dtype == TOME_BF16) patchify_kernel<uint8_t, __nv_bfloat16><<<grid, 256, 0, st>>>(a);
+  else if (in_dtype == TOME_U8 && out_dtype == TOME_F32) patchify_kernel<uint8_t, float><<<grid, 256, 0, st>>>(a);
   else return set_error(TOME_ERR_DTYPE, "tome_patchify: unsupported dtypes %d -> %d", in_dtype, out_dtype);
   TOME_LAUNCH_CHECK("patchify_kernel");
   return TOME_OK;

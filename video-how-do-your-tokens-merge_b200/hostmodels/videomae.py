@@ -111,13 +111,15 @@ class PatchEmbed(nn.Module):                            # builder:138-160
     def forward(self, x):
         B, C, T, H, W = x.shape
         assert (H, W) == self.img_size, f"Input image size ({H}*{W}) doesn't match model {self.img_size}."
+        if x.dtype == torch.uint8 and (self.training or not x.is_cuda or torch.is_grad_enabled()):
+            x = (x.float() / 255).to(self.proj.weight.dtype)        # decoder-style frames; on the CUDA path tome_patchify converts
         if self.training or not x.is_cuda:
             return self.proj(x).flatten(2).transpose(1, 2)
         # kernel == stride, so the tubelet conv is one GEMM over non-overlapping patches: cuDNN's
         # implicit-GEMM Conv3d ran as an fp32 SIMT kernel (22% of the forward, profiles/r01_launches_v1).
         tt, (ph, pw) = self.tubelet_size, self.patch_size
         wdt = self.proj.weight.dtype
-        if (not torch.is_grad_enabled() and pw % 8 == 0 and x.dtype in (torch.float32, torch.bfloat16)
+        if (not torch.is_grad_enabled() and pw % 8 == 0 and x.dtype in (torch.float32, torch.bfloat16, torch.uint8)
                 and wdt in (torch.float32, torch.bfloat16)):
             # one coalesced pass (tome_patchify, cast to the weight dtype included) instead of torch's generic
             # 8-d strided copy, which ran at a sixth of HBM speed (profiles/r01b)

@@ -108,6 +108,14 @@ class VivitIntermediate(nn.Module):
         self.intermediate_act_fn = gelu_fast if config.hidden_act == "gelu_fast" else F.gelu
 
     def forward(self, hidden_states):
+        x = hidden_states
+        if (self.intermediate_act_fn is gelu_fast and not self.training and x.is_cuda and x.dtype == torch.bfloat16
+                and x.numel() // x.shape[-1] >= 2048):
+            # dense + bias + gelu_fast from ONE tcgen05 GEMM (tome_linear_gelu): the eager form is a library GEMM
+            # plus seven elementwise passes over the (tokens, 4C) tensor, each rounding to bf16
+            from tome import _native
+            if _native.linear_gelu_supported(x, self.dense.weight, self.dense.bias):
+                return _native.linear_gelu(x, self.dense.weight, self.dense.bias, gelu="gelu_fast")
         return self.intermediate_act_fn(self.dense(hidden_states))
 
 

@@ -19,7 +19,7 @@ _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
 ABI_VERSION = 13
 
-TOME_F32, TOME_BF16 = 0, 1
+TOME_F32, TOME_BF16, TOME_U8 = 0, 1, 2
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
 MODE_WAVG, MODE_SUM, MODE_MEAN, MODE_AMAX, MODE_DROP = 0, 1, 2, 3, 4
 _MODES = {"wavg": MODE_WAVG, "sum": MODE_SUM, "mean": MODE_MEAN, "max": MODE_AMAX, "amax": MODE_AMAX,
@@ -390,13 +390,16 @@ def _norm_args(norm, x):
 
 def merge(plan: DevicePlan, x: torch.Tensor, mode: str, size: Optional[torch.Tensor] = None,
           hybrid_threshold: Optional[float] = None, want_size: bool = False, norm=None,
-          residual: Optional[torch.Tensor] = None):
+          residual: Optional[torch.Tensor] = None, out=None):
     """Kernel 3.  x (bm, n, c) -> (bm, n - r, c).  mode in wavg/sum/mean/max/amax/drop.
     Returns out, or (out, size_out, logsize_out) when ``want_size``; with ``norm=(weight, bias, eps)``
     the LayerNorm of the merged rows is produced in the same pass and appended to the result; with
-    ``residual`` (same shape as x) the rows merged are ``x + residual`` (rounded to x's dtype)."""
+    ``residual`` (same shape as x) the rows merged are ``x + residual`` (rounded to x's dtype).
+    ``out``: optional caller-owned (out, size_out, logsize_out, normed) buffers to write into instead of
+    allocating (entries may be None); the caller keeps them alive (C-ABI ownership rule)."""
     lib = load_library()
     _require_cuda(x, "x")
+    o_out, o_size, o_log, o_norm = (tuple(out) + (None,) * 4)[:4] if out is not None else (None,) * 4
     if x.dim() != 3 or x.shape[0] != plan.bm or x.shape[1] != plan.n:
         raise RuntimeError(f"tome_b200: merge expects x of shape ({plan.bm}, {plan.n}, c); got {tuple(x.shape)}")
     if x.dtype not in (torch.float32, torch.bfloat16):
@@ -408,12 +411,14 @@ def merge(plan: DevicePlan, x: torch.Tensor, mode: str, size: Optional[torch.Ten
     nout = n - plan.r
     thr = float("nan") if hybrid_threshold is None else float(hybrid_threshold)
     with torch.cuda.device(x.device):
-        out = torch.empty(bm, nout, c, dtype=x.dtype, device=x.device)
+        out = o_out if o_out is not None else torch.empty(bm, nout, c, dtype=x.dtype, device=x.device)
+        if out.shape != (bm, nout, c) or out.dtype != x.dtype or out.stride(2) != 1:
+            raise RuntimeError(f"tome_b200: out buffer must be ({bm}, {nout}, {c}) of x's dtype")
         size_out = logsize_out = None
         so = lo = None
         if want_size:
-            size_out = torch.empty(bm, nout, dtype=torch.float32, device=x.device)
-            logsize_out = torch.empty(bm, nout, dtype=torch.float32, device=x.device)
+            size_out = o_size if o_size is not None else torch.empty(bm, nout, dtype=torch.float32, device=x.device)
+            logsize_out = o_log if o_log is not None else torch.empty(bm, nout, dtype=torch.float32, device=x.device)
             so, lo = size_out.data_ptr(), logsize_out.data_ptr()
         sp = None
         if size is not None:
@@ -441,7 +446,7 @@ def merge(plan: DevicePlan, x: torch.Tensor, mode: str, size: Optional[torch.Ten
             nv = ov
             if norm is not None:
                 wp, bp, eps = _norm_args(norm, x)
-                normed = torch.empty_like(out)
+                normed = o_norm if o_norm is not None else torch.empty_like(out)
                 nv, npz = _view_of(normed), normed.data_ptr()
             _check(lib.tome_merge_add_norm(plan.c_ptr(), x.data_ptr(), rp, _dtype_code(x), c, ctypes.byref(xv), sp, m, thr,
                                            out.data_ptr(), ctypes.byref(ov), so, lo, wp, bp, eps, npz,
@@ -527,8 +532,12 @@ def linear_gelu_supported(x: torch.Tensor, weight: torch.Tensor, bias: Optional[
             and (bias is None or (bias.dtype == torch.bfloat16 and bias.is_contiguous())) and not torch.is_grad_enabled())
 
 
-def linear_gelu(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], gelu: bool = True) -> torch.Tensor:
-    """GELU_erf(x @ weight^T + bias) from one tcgen05 GEMM with the activation in its epilogue (bf16)."""
+_ACTS = {False: 0, None: 0, "none": 0, True: 1, "erf": 1, "gelu": 1, "gelu_fast": 2, "tanh_fast": 2}
+
+
+def linear_gelu(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], gelu=True) -> torch.Tensor:
+    """act(x @ weight^T + bias) from one tcgen05 GEMM with the activation in its epilogue (bf16).
+    ``gelu``: True / "erf" (nn.GELU), "gelu_fast" (HuggingFace FastGELUActivation, ViViT), False / None (bias only)."""
     lib = load_library()
     _require_cuda(x, "x")
     k = x.shape[-1]
@@ -539,7 +548,7 @@ def linear_gelu(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tens
     with torch.cuda.device(x.device):
         out = torch.empty(m, n, dtype=x.dtype, device=x.device)
         _check(lib.tome_linear_gelu(x2.data_ptr(), weight.data_ptr(), None if bias is None else bias.data_ptr(), m, n, k,
-                                    x2.stride(0), int(bool(gelu)), out.data_ptr(), _stream(x)), lib)
+                                    x2.stride(0), _ACTS[gelu], out.data_ptr(), _stream(x)), lib)
     return out.reshape(*x.shape[:-1], n)
 
 
@@ -548,9 +557,9 @@ def patchify(x: torch.Tensor, tubelet: int, ph: int, pw: int, out_dtype: torch.d
     included): the operand of the tubelet-embedding GEMM."""
     lib = load_library()
     _require_cuda(x, "x")
-    codes = {torch.float32: TOME_F32, torch.bfloat16: TOME_BF16}
-    if x.dtype not in codes or out_dtype not in codes or x.dim() != 5:
-        raise RuntimeError("tome_b200: patchify takes a 5-d fp32/bf16 clip")
+    codes = {torch.float32: TOME_F32, torch.bfloat16: TOME_BF16, torch.uint8: TOME_U8}
+    if x.dtype not in codes or out_dtype not in (torch.float32, torch.bfloat16) or x.dim() != 5:
+        raise RuntimeError("tome_b200: patchify takes a 5-d fp32 / bf16 / uint8 clip and writes fp32 or bf16")
     x = x.contiguous()
     B, C, T, H, W = x.shape
     with torch.cuda.device(x.device):
