@@ -763,8 +763,9 @@ def test_unmerge_backward_is_merge_sum(native):
     assert out.requires_grad
     (out * w.cuda()).sum().backward()
     assert P_STABLE == P.STABLE
-    if np.array_equal(merge.src_idx.cpu().numpy(), pm.match.src_idx.numpy()) and \\
-            np.array_equal(merge.unm_idx.cpu().numpy(), pm.match.unm_idx.numpy()):
+    same_plan = (np.array_equal(merge.src_idx.cpu().numpy(), pm.match.src_idx.numpy())
+                 and np.array_equal(merge.unm_idx.cpu().numpy(), pm.match.unm_idx.numpy()))
+    if same_plan:
         torch.testing.assert_close(yg.grad.cpu(), yc.grad, rtol=1e-6, atol=1e-6)
     # adjoint identity holds whatever the plan: <unmerge(y), w> == <y, merge_sum(w)>
     lhs = float((unmerge(y.cuda()) * w.cuda()).double().sum())

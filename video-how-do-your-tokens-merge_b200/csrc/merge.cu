@@ -92,6 +92,36 @@ template <> struct Vec<__nv_bfloat16, 1> {
 
 __device__ __forceinline__ float nanmax(float a, float b) { return (a != a || a > b) ? a : ((b != b) ? b : (a > b ? a : b)); }
 
+// Packed fp32 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2): two IEEE fp32 operations per issue slot, each lane rounded
+// exactly like its scalar form, so every bit-exactness guarantee below is unchanged.  The fused bf16 launch executed
+// 755 warp instructions per row and kept the issue slots 51 % busy with 31 % of the warps resident
+// (profiles/r02_merge_ncu.txt): it was short of issue slots, not of HBM bandwidth.
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tsub.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+
 // One warp per output row; NV vectors of E elements per lane per chunk.
 template <typename T, int E, int NV>
 __global__ void __launch_bounds__(256) merge_rows_kernel(MergeArgs a) {
@@ -309,7 +339,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) merge_gather_kernel(MergeArg
         Pack<T>::unpack(raw[v], f);
         Pack<T>::unpack(raw2[RES ? v : 0], g);
 #pragma unroll
-        for (int e = 0; e < E; ++e) f[e] = __fadd_rn(f[e], g[e]);
+        for (int e = 0; e < E; e += 2) {
+          const float2 t = add2(make_float2(f[e], f[e + 1]), make_float2(g[e], g[e + 1]));
+          f[e] = t.x; f[e + 1] = t.y;
+        }
         raw[v] = Pack<T>::pack(f);               // rounded to T: what x + attn holds in the reference
       }
     }
@@ -431,35 +464,41 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) merge_gather_kernel(MergeArg
   if (LN) {
     // fused LayerNorm over the row this warp holds: fp32 statistics of the ROUNDED row (what a separate
     // LayerNorm kernel would read back), two-pass variance, one more row written instead of a whole
-    // read-modify-write pass over x'
-    float sum = 0.f;
+    // read-modify-write pass over x'.  The row is unpacked ONCE and stays in registers as centred values;
+    // sums, centring and the affine map are packed f32x2 operations.
+    float2 d[NV][E / 2];
+    float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      const int i = v * 32 + lane;
-      if (i < nvec) {
-        float f[E];
-        Pack<T>::unpack(raw[v], f);
+      float f[E];
+      Pack<T>::unpack(raw[v], f);
+      const bool on = v * 32 + lane < nvec;
 #pragma unroll
-        for (int e = 0; e < E; ++e) sum += f[e];
+      for (int e = 0; e < E; e += 2) {
+        d[v][e / 2] = on ? make_float2(f[e], f[e + 1]) : make_float2(0.f, 0.f);
+        s2 = add2(s2, d[v][e / 2]);
       }
     }
+    float sum = s2.x + s2.y;
 #pragma unroll
     for (int of = 16; of > 0; of >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, of);
     const float mean = sum / (float)a.c;
-    float sq = 0.f;
+    const float2 mean2 = make_float2(mean, mean);
+    float2 q2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      const int i = v * 32 + lane;
-      if (i < nvec) {
-        float f[E];
-        Pack<T>::unpack(raw[v], f);
+      const bool on = v * 32 + lane < nvec;
 #pragma unroll
-        for (int e = 0; e < E; ++e) { const float d = f[e] - mean; sq = fmaf(d, d, sq); }
+      for (int e = 0; e < E / 2; ++e) {
+        d[v][e] = sub2(d[v][e], mean2);
+        if (on) q2 = fma2(d[v][e], d[v][e], q2);
       }
     }
+    float sq = q2.x + q2.y;
 #pragma unroll
     for (int of = 16; of > 0; of >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, of);
     const float rstd = rsqrtf(sq / (float)a.c + a.ln_eps);
+    const float2 rstd2 = make_float2(rstd, rstd);
     uint4* nrow = reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.normed) + a.nv.batch_offset(b) + (long long)o * a.nv.sn);
     const uint4* gw = reinterpret_cast<const uint4*>(a.ln_w);
     const uint4* gb = reinterpret_cast<const uint4*>(a.ln_b);
@@ -468,11 +507,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) merge_gather_kernel(MergeArg
       const int i = v * 32 + lane;
       if (i < nvec) {
         float f[E], w[E], bb[E];
-        Pack<T>::unpack(raw[v], f);
         Pack<T>::unpack(__ldg(gw + i), w);
         if (gb) Pack<T>::unpack(__ldg(gb + i), bb);
 #pragma unroll
-        for (int e = 0; e < E; ++e) f[e] = (f[e] - mean) * rstd * w[e] + (gb ? bb[e] : 0.f);
+        for (int e = 0; e < E; e += 2) {
+          const float2 g2 = mul2(make_float2(w[e], w[e + 1]), rstd2);
+          const float2 y = fma2(d[v][e / 2], g2, gb ? make_float2(bb[e], bb[e + 1]) : make_float2(0.f, 0.f));
+          f[e] = y.x; f[e + 1] = y.y;
+        }
         nrow[i] = Pack<T>::pack(f);
       }
     }
@@ -647,50 +689,65 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const T* __restrict_
   uint4 va[NV], vb[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) { const int i = v * 32 + lane; if (i < nvec) { va[v] = ld_stream_u4(ar + i); vb[v] = ld_stream_u4(br + i); } }
-  float sum = 0.f;
+  // the sum is rounded to T (what x + y holds in the reference), written out, and kept in registers as fp32 pairs for
+  // the statistics; packed f32x2 arithmetic throughout (see add2 / fma2 above)
+  float2 d[NV][E / 2];
+  float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const int i = v * 32 + lane;
-    if (i < nvec) {
-      float fa[E], fb[E];
-      Pack<T>::unpack(va[v], fa);
-      Pack<T>::unpack(vb[v], fb);
+    const bool on = i < nvec;
+    float fa[E], fb[E];
+    if (on) { Pack<T>::unpack(va[v], fa); Pack<T>::unpack(vb[v], fb); }
 #pragma unroll
-      for (int e = 0; e < E; ++e) fa[e] = fa[e] + fb[e];
-      va[v] = Pack<T>::pack(fa);                    // rounded to T: what x + y holds in the reference
-      Pack<T>::unpack(va[v], fa);
-#pragma unroll
-      for (int e = 0; e < E; ++e) sum += fa[e];
+    for (int e = 0; e < E; e += 2) {
+      const float2 t = on ? add2(make_float2(fa[e], fa[e + 1]), make_float2(fb[e], fb[e + 1])) : make_float2(0.f, 0.f);
+      fa[e] = t.x; fa[e + 1] = t.y;
+    }
+    if (on) {
+      va[v] = Pack<T>::pack(fa);
       reinterpret_cast<uint4*>(sum_out + row * c)[i] = va[v];
+      Pack<T>::unpack(va[v], fa);
+    }
+#pragma unroll
+    for (int e = 0; e < E; e += 2) {
+      d[v][e / 2] = on ? make_float2(fa[e], fa[e + 1]) : make_float2(0.f, 0.f);
+      s2 = add2(s2, d[v][e / 2]);
     }
   }
+  float sum = s2.x + s2.y;
 #pragma unroll
   for (int of = 16; of > 0; of >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, of);
   const float mean = sum / (float)c;
-  float sq = 0.f;
+  const float2 mean2 = make_float2(mean, mean);
+  float2 q2 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
-    const int i = v * 32 + lane;
-    if (i < nvec) {
-      float f[E];
-      Pack<T>::unpack(va[v], f);
+    const bool on = v * 32 + lane < nvec;
 #pragma unroll
-      for (int e = 0; e < E; ++e) { const float d = f[e] - mean; sq = fmaf(d, d, sq); }
+    for (int e = 0; e < E / 2; ++e) {
+      d[v][e] = sub2(d[v][e], mean2);
+      if (on) q2 = fma2(d[v][e], d[v][e], q2);
     }
   }
+  float sq = q2.x + q2.y;
 #pragma unroll
   for (int of = 16; of > 0; of >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, of);
   const float rstd = rsqrtf(sq / (float)c + eps);
+  const float2 rstd2 = make_float2(rstd, rstd);
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const int i = v * 32 + lane;
     if (i < nvec) {
       float f[E], wf[E], bf[E];
-      Pack<T>::unpack(va[v], f);
       Pack<T>::unpack(__ldg(reinterpret_cast<const uint4*>(w) + i), wf);
       if (bias) Pack<T>::unpack(__ldg(reinterpret_cast<const uint4*>(bias) + i), bf);
 #pragma unroll
-      for (int e = 0; e < E; ++e) f[e] = (f[e] - mean) * rstd * wf[e] + (bias ? bf[e] : 0.f);
+      for (int e = 0; e < E; e += 2) {
+        const float2 g2 = mul2(make_float2(wf[e], wf[e + 1]), rstd2);
+        const float2 y = fma2(d[v][e / 2], g2, bias ? make_float2(bf[e], bf[e + 1]) : make_float2(0.f, 0.f));
+        f[e] = y.x; f[e + 1] = y.y;
+      }
       reinterpret_cast<uint4*>(normed + row * c)[i] = Pack<T>::pack(f);
     }
   }
