@@ -149,12 +149,19 @@ TOME_API int tome_select(const tome_plan* plan, void* workspace, size_t workspac
 
 /* --- kernels 1 + 2 in one call (merge.py:49-73: everything bipartite_soft_matching computes) ---------
  * Matching on `metric` (heads == 1: (bm, n, cm) through `view`; heads > 1: the head-mean of K as in
- * tome_match_heads) followed by the selection: one ABI call, one workspace.  bm, n, r, class/distill flags
+ * tome_match_heads) followed by the selection: one ABI call, one workspace.  With algo == TOME_MATCH_AUTO,
+ * cm <= 64 (cm % 8 == 0), 16-byte aligned rows and at most 2048 A tokens this is ONE kernel launch: a thread-block
+ * cluster per batch element (csrc/plan_cluster.cu); other shapes, or an explicit algo, run the multi-launch chain.
+ * Both give the same bits.  bm, n, r, class/distill flags
  * and every output buffer come from `plan`; plan->node_max / node_idx are OUTPUTS of this call. */
 TOME_API size_t tome_plan_build_workspace_bytes(int32_t bm, int32_t n, int32_t cm);
 TOME_API int tome_plan_build(const void* metric, int32_t dtype, int32_t heads, int64_t stride_h, const tome_view* view,
                     int32_t cm, int32_t algo, const tome_plan* plan, void* workspace, size_t workspace_bytes,
                     void* stream);
+
+/* Diagnostics for tests: geometry of the one-launch cluster form of tome_plan_build for a shape -- out5 = {CTAs per
+ * cluster (0: the shape takes the multi-launch chain), A rows per CTA, B rows per CTA, tile width, shared memory bytes}. */
+TOME_API void tome_plan_cluster_describe(int32_t bm, int32_t n, int64_t* out5);
 
 /* Diagnostics for tests: geometry of the tensor-core pass for a shape -- out5 = {column tiles, BN, byte
  * offset of tile_max in the workspace, byte offset of tile_cnt, 1 if the exact refine is fused}. */

@@ -492,7 +492,8 @@ def test_patchify_takes_uint8_frames(native, dout):
     B, C, T, H, W, tt, ph, pw = 2, 3, 4, 32, 48, 2, 16, 16
     x8 = torch.randint(0, 256, (B, C, T, H, W), device="cuda", generator=gen, dtype=torch.uint8)
     got = native.patchify(x8, tt, ph, pw, dout)
-    want = native.patchify(x8.float() / 255, tt, ph, pw, dout)
+    # correctly rounded division, i.e. torch's CPU `x.float() / 255` (its CUDA kernel multiplies by fp32(1 / 255) instead)
+    want = native.patchify((x8.cpu().float() / 255).cuda(), tt, ph, pw, dout)
     assert torch.equal(got, want)
     import hostmodels
     m = hostmodels.VideoMAE(arch="vit_small_patch16_224", num_classes=7, num_frames=4).eval().cuda().to(dout)
@@ -798,3 +799,74 @@ def test_second_device_in_the_same_process(native):
             torch.cuda.synchronize(dev)
     assert torch.equal(plans[0].src_idx.cpu(), plans[1].src_idx.cpu())
     assert torch.equal(plans[0].dst_idx.cpu(), plans[1].dst_idx.cpu())
+
+
+# ---- kernels 1 + 2 as one cluster launch (csrc/plan_cluster.cu) against the multi-launch chain -------------------------
+_PC_SHAPES = [
+    # bm, n, cm, heads, dtype, cls, distill, r, forced cluster size (0 = the kernel's own choice)
+    (8, 1568, 64, 12, torch.bfloat16, False, False, 100, 0),      # the bench shape: VideoMAE-B layer 0
+    (8, 468, 64, 12, torch.bfloat16, False, False, 100, 0),       # ... and layer 11
+    (4, 1568, 64, 1, torch.float32, False, False, 100, 0),        # BASELINE config 1 (M1')
+    (2, 3137, 64, 12, torch.float32, True, False, 300, 0),        # ViViT-B layer 0: class token, odd n, 16-CTA clusters
+    (16, 196, 64, 12, torch.bfloat16, False, False, 18, 0),       # TimeSformer / Motionformer frames
+    (3, 77, 32, 1, torch.float32, False, False, 17, 0),
+    (2, 198, 64, 3, torch.float32, True, True, 30, 0),            # class + distillation token
+    (2, 198, 64, 3, torch.float32, True, True, 30, 4),
+    (2, 97, 16, 1, torch.float32, True, False, 24, 2),
+    (2, 9, 8, 1, torch.float32, False, False, 3, 4),              # more CTAs than row blocks: some own nothing
+    (2, 2, 8, 1, torch.float32, False, False, 1, 0),
+    (2, 3, 8, 1, torch.bfloat16, False, False, 1, 0),
+    (1, 1568, 64, 12, torch.bfloat16, False, False, 784, 8),      # r = every A token
+    (5, 600, 40, 6, torch.bfloat16, False, False, 150, 0),        # cm < 64: zero-padded channels
+]
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("shape", _PC_SHAPES, ids=lambda s: f"bm{s[0]}_n{s[1]}_cm{s[2]}_h{s[3]}_{'bf16' if s[4] == torch.bfloat16 else 'f32'}_cls{int(s[5])}{int(s[6])}_r{s[7]}_cs{s[8]}")
+def test_plan_cluster_equals_the_multi_launch_chain(native, shape, monkeypatch):
+    """tome_plan_build as ONE cluster launch gives, bit for bit, every output of the split_rows -> match_tc -> rank ->
+    finish chain (itself bit-exact against the oracle): node_max / node_idx, src / unm / dst, a_map and the CSR."""
+    bm, n, cm, heads, dtype, cls, dis, r, cs = shape
+    gen = torch.Generator(device="cuda").manual_seed(n * 7 + cm)
+    if heads > 1:
+        keys = torch.randn(bm, n, 3, heads, cm, device="cuda", generator=gen).to(dtype).permute(2, 0, 3, 1, 4)[1]
+        metric = native.HeadMeanMetric(keys)
+    else:
+        metric = torch.randn(bm, n, cm, device="cuda", generator=gen).to(dtype)
+    monkeypatch.setenv("TOME_PLAN_CLUSTER", "0")
+    want = native.plan_build(metric, r, cls, dis)
+    monkeypatch.setenv("TOME_PLAN_CLUSTER", "1")
+    if cs:
+        monkeypatch.setenv("TOME_PLAN_CS", str(cs))
+    geom = native.plan_cluster_describe(bm, n)
+    assert geom[0] >= max(cs, 1), geom                      # the shape really takes the cluster kernel
+    before = native.launch_count()
+    got = native.plan_build(metric, r, cls, dis)
+    assert native.launch_count() - before == 1              # one launch
+    torch.cuda.synchronize()
+    assert torch.equal(got.node_idx, want.node_idx)
+    assert torch.equal(got.node_max.view(torch.int32), want.node_max.view(torch.int32))
+    for name in ("src_idx", "unm_idx", "dst_idx", "a_map", "b_off", "b_src", "b_head"):
+        assert torch.equal(getattr(got, name), getattr(want, name)), name
+
+
+@pytest.mark.timeout(180)
+def test_plan_cluster_frames_view_and_zero_norm_rows(native, monkeypatch):
+    """Motionformer's '(b f)' regrouping of K (tome_view with inner = frames) and a zero-norm token (NaN scores, no eps:
+    merge.py:51) through the cluster kernel, against the chain."""
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    B, F, S, H, d = 2, 8, 196, 12, 64
+    keys = torch.randn(B, H, S * F, d, device="cuda", generator=gen).to(torch.bfloat16)
+    keys[0, :, 5 * F + 3] = 0          # token s=5 of frame 3: an odd token -> NaN column in that frame's matching
+    keys[1, :, 4 * F + 1] = 0          # token s=4 of frame 1: an even token -> NaN row
+    for frames in (F,):
+        metric = native.HeadMeanMetric(keys, frames)
+        monkeypatch.setenv("TOME_PLAN_CLUSTER", "0")
+        want = native.plan_build(metric, 18)
+        monkeypatch.setenv("TOME_PLAN_CLUSTER", "1")
+        got = native.plan_build(native.HeadMeanMetric(keys, frames), 18)
+        torch.cuda.synchronize()
+        assert torch.equal(got.node_idx, want.node_idx)
+        assert torch.equal(got.node_max.view(torch.int32), want.node_max.view(torch.int32))
+        for name in ("src_idx", "unm_idx", "dst_idx", "a_map", "b_off", "b_src", "b_head"):
+            assert torch.equal(getattr(got, name), getattr(want, name)), name

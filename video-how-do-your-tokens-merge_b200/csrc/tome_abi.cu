@@ -68,6 +68,10 @@ int launch_patchify(const void*, int, int, int, int, int, int, int, int, int, vo
 int launch_key_bias(const float*, int, int, int, int, int, float, int, void*, long long, long long, long long, void*, long long,
                     long long, long long, cudaStream_t);
 
+size_t plan_cluster_workspace(int bm, int n);
+bool plan_cluster_supported(int dtype, int bm, int n, int cm, int heads, const View& v, long long stride_h, const void* metric);
+int launch_plan_cluster(const void*, int, int, long long, const View&, int, const tome_plan*, void*, size_t, cudaStream_t);
+void plan_cluster_describe(int, int, long long[5]);
 size_t match_sets_workspace(int bm, int rows, int ra, int cm);
 int launch_match_sets(const void*, int, int, int, const View&, const int*, long long, int, int, float*, int*, void*, size_t, cudaStream_t);
 int launch_group_reduce(const void*, int, int, int, const View&, const int*, long long, int, int, const int*, int, void*, cudaStream_t);
@@ -160,7 +164,15 @@ static size_t align256_(size_t x) { return (x + 255) & ~(size_t)255; }
 
 size_t tome_plan_build_workspace_bytes(int32_t bm, int32_t n, int32_t cm) {
   if (bm <= 0 || n <= 0 || cm <= 0) return 0;
-  return align256_(tome_match_workspace_bytes(bm, n, cm, TOME_MATCH_AUTO)) + align256_(select_workspace(bm, n));
+  const size_t chain = align256_(tome_match_workspace_bytes(bm, n, cm, TOME_MATCH_AUTO)) + align256_(select_workspace(bm, n));
+  const size_t cluster = align256_(plan_cluster_workspace(bm, n));
+  return chain > cluster ? chain : cluster;
+}
+
+void tome_plan_cluster_describe(int32_t bm, int32_t n, int64_t* out5) {
+  long long o[5];
+  plan_cluster_describe(bm, n, o);
+  for (int i = 0; i < 5; ++i) out5[i] = o[i];
 }
 
 void tome_match_tc_describe(int32_t bm, int32_t n, int32_t cm, int64_t* out5) {
@@ -190,6 +202,10 @@ int tome_plan_build(const void* metric, int32_t dtype, int32_t heads, int64_t st
   float* node_max = const_cast<float*>(plan->node_max);
   int32_t* node_idx = const_cast<int32_t*>(plan->node_idx);
   const bool tc_ok = match_tc_supported(dtype, bm, n, cm, v, metric);
+  // one cluster launch for kernels 1 + 2 (plan_cluster.cu) whenever the shape fits; TOME_MATCH_TCGEN05 names the
+  // multi-launch tensor-core chain explicitly (kept for wide metrics and as a cross-check)
+  if (algo == TOME_MATCH_AUTO && plan_cluster_supported(dtype, bm, n, cm, heads, v, stride_h, metric))
+    return launch_plan_cluster(metric, dtype, heads, stride_h, v, cm, plan, workspace, workspace_bytes, st);
   if (algo == TOME_MATCH_AUTO) algo = tc_ok ? TOME_MATCH_TCGEN05 : TOME_MATCH_EXACT_SIMT;
   if (algo == TOME_MATCH_TCGEN05) {
     if (!tc_ok)

@@ -27,7 +27,7 @@ _MODES = {"wavg": MODE_WAVG, "sum": MODE_SUM, "mean": MODE_MEAN, "max": MODE_AMA
 
 EXPORTS = (
     "tome_abi_version", "tome_last_error", "tome_launch_count", "tome_device_check", "tome_match_workspace_bytes", "tome_match", "tome_match_heads",
-    "tome_plan_build_workspace_bytes", "tome_plan_build", "tome_match_tc_describe",
+    "tome_plan_build_workspace_bytes", "tome_plan_build", "tome_match_tc_describe", "tome_plan_cluster_describe",
     "tome_rowmax", "tome_select_workspace_bytes", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_add_norm", "tome_add_layernorm", "tome_add_rows_layernorm",
     "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_linear_gelu", "tome_unmerge",
     "tome_match_sets_workspace_bytes", "tome_match_sets", "tome_group_reduce", "tome_gather_rows",
@@ -93,6 +93,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.tome_plan_build.argtypes = [c_vp, c_i32, c_i32, ctypes.c_int64, ctypes.POINTER(TomeViewC), c_i32, c_i32,
                                     ctypes.POINTER(TomePlanC), c_vp, ctypes.c_size_t, c_vp]
     lib.tome_plan_build.restype = c_i32
+    lib.tome_plan_cluster_describe.restype = None
+    lib.tome_plan_cluster_describe.argtypes = [c_i32, c_i32, ctypes.POINTER(ctypes.c_int64)]
     lib.tome_match_tc_describe.restype = None
     lib.tome_match_tc_describe.argtypes = [c_i32, c_i32, c_i32, ctypes.POINTER(ctypes.c_int64)]
     lib.tome_merge_add_norm.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_vp, c_i32, c_i32, ctypes.POINTER(TomeViewC), c_vp,
@@ -348,6 +350,14 @@ def match_tc_describe(bm: int, n: int, cm: int):
     """(column tiles, BN, byte offset of tile_max, byte offset of tile_cnt, fused refine?) -- tests only."""
     out = (ctypes.c_int64 * 5)()
     load_library().tome_match_tc_describe(bm, n, cm, out)
+    return tuple(int(v) for v in out)
+
+
+def plan_cluster_describe(bm: int, n: int):
+    """(CTAs per cluster, A rows per CTA, B rows per CTA, tile width, smem bytes) of the one-launch plan kernel; CTAs = 0
+    when the shape takes the multi-launch chain -- tests only."""
+    out = (ctypes.c_int64 * 5)()
+    load_library().tome_plan_cluster_describe(bm, n, out)
     return tuple(int(v) for v in out)
 
 
