@@ -30,7 +30,7 @@ def _oracle_plan(case, metric):
     return O.bipartite_soft_matching(metric, case["r"], bool(case.get("cls")), bool(case.get("distill")))
 
 
-ALGOS = ["exact", "tc", "tc_streamed", "tc_nct5"]
+ALGOS = ["exact", "tc", "tc_streamed", "tc_nct5", "tc_pair_loads"]
 
 
 @pytest.mark.parametrize("algo", ALGOS)
@@ -45,6 +45,8 @@ def test_match_bit_exact_vs_oracle(native, case, algo, monkeypatch):
         monkeypatch.setenv("TOME_TC_NO_FUSED_REFINE", "1")
     if algo == "tc_nct5":
         monkeypatch.setenv("TOME_TC_NCT", "5")
+    if algo == "tc_pair_loads":             # the 4-byte-per-lane normalisation kernel (unaligned views take it)
+        monkeypatch.setenv("TOME_SPLIT_PAIRS", "1")
     nm, ni = native.match(_dev(metric), cls, dis, algo=1 if algo == "exact" else 2)
     onm, oni = O.match(metric, cls, dis)
     np.testing.assert_array_equal(ni.cpu().numpy(), oni)
@@ -445,14 +447,18 @@ def test_fused_residual_equals_merging_the_sum(native, name, dtype):
         native.merge(dp, xd, "wavg", residual=rd[:, :-1])
 
 
-@pytest.mark.parametrize("path", ["fused", "exact_simt"])
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("path", ["auto", "chain", "one_launch", "exact_simt"])
 @pytest.mark.parametrize("case", ALL_ACTIVE, ids=lambda c: c["name"])
-def test_plan_build_bit_exact_vs_oracle(native, case, path):
+def test_plan_build_bit_exact_vs_oracle(native, case, path, monkeypatch):
     """tome_plan_build (kernels 1 + 2 in one ABI call) gives the oracle's node_max / node_idx / src / unm / dst
-    bits, with the tcgen05 matching and with the exact SIMT matching."""
+    bits: as dispatched by default, as the four-launch tcgen05 chain, as the one-launch cluster kernel (forced for every
+    shape it supports) and with the exact SIMT matching."""
     metric, _, _ = util.case_arrays(case)
     cls, dis = bool(case.get("cls")), bool(case.get("distill"))
     plan = _oracle_plan(case, metric)
+    if path in ("chain", "one_launch"):
+        monkeypatch.setenv("TOME_PLAN_CLUSTER", "0" if path == "chain" else "1")
     dp = native.plan_build(_dev(metric), plan.r, cls, dis, algo=1 if path == "exact_simt" else 0)
     np.testing.assert_array_equal(dp.node_idx.cpu().numpy(), plan.node_idx)
     np.testing.assert_array_equal(dp.node_max.cpu().numpy().view(np.uint32), plan.node_max.view(np.uint32))

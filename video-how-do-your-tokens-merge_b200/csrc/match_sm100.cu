@@ -160,6 +160,117 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const T* __restrict__ m
   }
 }
 
+
+// The same normalisation, eight channels per lane: 16-byte loads, eight lanes per token and four tokens per warp, so a
+// warp has 4 x 12 head rows of 128 bytes in flight and a quarter of the load / address instructions per token (the pair
+// form above is issue-bound: 10.7 us under ncu at the bench shape, profiles/r01e_hotpath_ncu.txt).  Needs 16-byte aligned
+// rows and cm <= 64; everything else takes split_rows_kernel.
+template <typename T> struct Chunk8;
+template <> struct Chunk8<float> {
+  static constexpr int NB = 6;
+  struct Raw { float4 a, b; };
+  static __device__ __forceinline__ Raw load(const float* p) {
+    Raw r;
+    r.a = __ldg(reinterpret_cast<const float4*>(p));
+    r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    return r;
+  }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&f)[8]) {
+    f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w; f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+  }
+  static __device__ __forceinline__ float round_like_input(float x) { return x; }
+};
+template <> struct Chunk8<__nv_bfloat16> {
+  static constexpr int NB = 12;
+  typedef uint4 Raw;
+  static __device__ __forceinline__ Raw load(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  static __device__ __forceinline__ void unpack(const Raw& v, float (&f)[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+  }
+  static __device__ __forceinline__ float round_like_input(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) split_rows8_kernel(const T* __restrict__ metric, View v, int heads, long long stride_h,
+                                                          int bm, int n, int cm, __nv_bfloat16* __restrict__ hm,
+                                                          float* __restrict__ mhat, unsigned long long* __restrict__ keys,
+                                                          unsigned int* __restrict__ approx, int* __restrict__ strip_count,
+                                                          int n_strips) {
+  const int lane = threadIdx.x & 31, l8 = lane & 7, k0 = 8 * l8;
+  const long long token = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;      // eight lanes per token
+  const bool on = token < (long long)bm * n;
+  const int b = on ? (int)(token / n) : 0, t = on ? (int)(token - (long long)b * n) : 0, na = na_of(n);
+  if (on && l8 == 0) {
+    if (!(t & 1)) { keys[(long long)b * na + (t >> 1)] = 0ull; approx[(long long)b * na + (t >> 1)] = 0u; }
+    if (token < n_strips) strip_count[token] = 0;
+  }
+  float x[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) x[e] = 0.f;
+  if (on && k0 < cm) {
+    const T* src = metric + v.batch_offset(b) + (long long)t * v.sn + k0;
+    if (heads == 1) {
+      Chunk8<T>::unpack(Chunk8<T>::load(src), x);
+    } else {
+      constexpr int NB = Chunk8<T>::NB;
+      int h = 0;
+      for (; h + NB <= heads; h += NB) {        // every load of a batch in flight before the first add; adds sequential in h
+        typename Chunk8<T>::Raw a[NB];
+#pragma unroll
+        for (int u = 0; u < NB; ++u) a[u] = Chunk8<T>::load(src + (long long)(h + u) * stride_h);
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+          float f[8];
+          Chunk8<T>::unpack(a[u], f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] += f[e];
+        }
+      }
+      for (; h < heads; ++h) {
+        float f[8];
+        Chunk8<T>::unpack(Chunk8<T>::load(src + (long long)h * stride_h), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] += f[e];
+      }
+      const float inv = 1.0f / (float)heads;    // 1/H multiply like ATen's MeanOps, rounded to the input dtype like k.mean(1)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = Chunk8<T>::round_like_input(x[e] * inv);
+    }
+  }
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+  for (int e = 0; e < 8; e += 2) { s0 = fma((double)x[e], (double)x[e], s0); s1 = fma((double)x[e + 1], (double)x[e + 1], s1); }
+  double ss = s0 + s1;
+  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+  if (!on || k0 >= cm) return;
+  const float norm = (float)sqrt(ss);
+  float mh[8], hf[8], mf[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    mh[e] = __fdiv_rn(x[e], norm);
+    hf[e] = __bfloat162float(__float2bfloat16_rn(mh[e]));
+    mf[e] = mh[e] - hf[e];                      // exact
+  }
+  uint32_t hw[4], mw[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(hf[2 * i], hf[2 * i + 1]), mm = __floats2bfloat162_rn(mf[2 * i], mf[2 * i + 1]);
+    hw[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    mw[i] = *reinterpret_cast<const uint32_t*>(&mm);
+  }
+  const int row = (t & 1) ? na + (t >> 1) : (t >> 1);
+  const long long ro = ((long long)b * n + row) * cm + k0;
+  *reinterpret_cast<uint4*>(hm + ro) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  *reinterpret_cast<uint4*>(hm + (long long)bm * n * cm + ro) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+  float4* fr = reinterpret_cast<float4*>(mhat + ro);
+  fr[0] = make_float4(mh[0], mh[1], mh[2], mh[3]);
+  fr[1] = make_float4(mh[4], mh[5], mh[6], mh[7]);
+}
+
 #define TC_TRACE(slot) do { if (p.trace) p.trace[(((long long)b * gridDim.y + it) * gridDim.x + jt) * 16 + (slot)] = gtime(); } while (0)
 
 // ---------------------------------------------------------------------------------------------
@@ -652,12 +763,24 @@ int launch_match_tc(const void* metric, int dtype, int bm, int n, int cm, const 
   p.approx = (unsigned int*)(w + l.approx);
   p.strip_count = (int*)(w + l.strips);
 
-  const int blocks = (int)(((long long)bm * n * 32 + 255) / 256);
-  if (dtype == TOME_F32)
-    split_rows_kernel<float><<<blocks, 256, 0, st>>>((const float*)metric, v, heads, stride_h, bm, n, cm, hm, mhat, p.keys, p.approx, p.strip_count, bm * n_rt);
-  else
-    split_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)metric, v, heads, stride_h, bm, n, cm, hm, mhat, p.keys, p.approx, p.strip_count, bm * n_rt);
-  TOME_LAUNCH_CHECK("split_rows_kernel");
+  const long long vec = dtype == TOME_F32 ? 4 : 8;            // 16-byte loads of eight channels
+  const bool wide = cm <= 64 && !((uintptr_t)metric & 15) && v.sbo % vec == 0 && v.sbi % vec == 0 && v.sn % vec == 0 &&
+                    (heads == 1 || stride_h % vec == 0) && !env_int("TOME_SPLIT_PAIRS", 0);
+  if (wide) {
+    const int blocks8 = (int)(((long long)bm * n * 8 + 255) / 256);
+    if (dtype == TOME_F32)
+      split_rows8_kernel<float><<<blocks8, 256, 0, st>>>((const float*)metric, v, heads, stride_h, bm, n, cm, hm, mhat, p.keys, p.approx, p.strip_count, bm * n_rt);
+    else
+      split_rows8_kernel<__nv_bfloat16><<<blocks8, 256, 0, st>>>((const __nv_bfloat16*)metric, v, heads, stride_h, bm, n, cm, hm, mhat, p.keys, p.approx, p.strip_count, bm * n_rt);
+    TOME_LAUNCH_CHECK("split_rows8_kernel");
+  } else {
+    const int blocks = (int)(((long long)bm * n * 32 + 255) / 256);
+    if (dtype == TOME_F32)
+      split_rows_kernel<float><<<blocks, 256, 0, st>>>((const float*)metric, v, heads, stride_h, bm, n, cm, hm, mhat, p.keys, p.approx, p.strip_count, bm * n_rt);
+    else
+      split_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)metric, v, heads, stride_h, bm, n, cm, hm, mhat, p.keys, p.approx, p.strip_count, bm * n_rt);
+    TOME_LAUNCH_CHECK("split_rows_kernel");
+  }
 
   alignas(64) CUtensorMap map_a, map_b;
   int rc = make_bf16_map(&map_a, hm, 2LL * bm * n, cm, cm, TC_BM, "tome_match");

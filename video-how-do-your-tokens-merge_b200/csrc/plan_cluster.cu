@@ -742,7 +742,15 @@ size_t plan_cluster_workspace(int bm, int n) {
 }
 
 bool plan_cluster_supported(int dtype, int bm, int n, int cm, int heads, const View& v, long long stride_h, const void* metric) {
-  if (getenv("TOME_PLAN_CLUSTER") && atoi(getenv("TOME_PLAN_CLUSTER")) == 0) return false;
+  // Measured on a B200 (profiles/r02_plan_paths.txt, graph replay, bf16 keys of 12 heads): the one launch beats the
+  // four-launch chain while a batch element's A rows fit ONE 128-row tile (TimeSformer / Motionformer frames, the last
+  // ViViT layers: 20.8 / 17.6 / 14.0 us against 22.9 / 21.7 / 18.7 at n = 196 / 88 / 17), and loses beyond (39 against
+  // 26 us at n = 1568): a cluster per batch element reaches 64 of the 148 SMs, and both the normalisation (~800
+  // instructions per token and lane) and the TMEM read-out of the sweep (64 B/clk/SM) scale with the SMs in use.
+  // TOME_PLAN_CLUSTER=1 forces it for every shape it supports, =0 disables it.
+  const char* sw = getenv("TOME_PLAN_CLUSTER");
+  if (sw && atoi(sw) == 0) return false;
+  if (!(sw && atoi(sw) == 1) && na_of(n) > 128) return false;
   if (dtype != TOME_F32 && dtype != TOME_BF16) return false;
   if (cm > PC_K || cm % 8 != 0 || n < 2 || bm > TOME_MAX_BATCH) return false;
   const long long vec = dtype == TOME_F32 ? 4 : 8;               // 16-byte loads of eight channels
@@ -768,7 +776,13 @@ static int launch_pc_t(const CUtensorMap& map_b, const void* metric, const PcPar
   at[0].val.clusterDim.x = g.CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, plan_cluster_kernel<T>, map_b, (const T*)metric, p);
+  cudaError_t e;
+  if (g.CS == 1) {          // a batch element per CTA: a plain launch (every CTA is its own cluster; no cluster scheduling cost)
+    plan_cluster_kernel<T><<<cfg.gridDim, cfg.blockDim, cfg.dynamicSmemBytes, st>>>(map_b, (const T*)metric, p);
+    e = cudaGetLastError();
+  } else {
+    e = cudaLaunchKernelEx(&cfg, plan_cluster_kernel<T>, map_b, (const T*)metric, p);
+  }
   count_launch();
   if (e != cudaSuccess) return set_error(TOME_ERR_CUDA, "launch of plan_cluster_kernel failed: %s", cudaGetErrorString(e));
   return TOME_OK;
