@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 13
+#define TOME_ABI_VERSION 14
 
 #if defined(__GNUC__)
 #define TOME_API __attribute__((visibility("default")))
@@ -277,6 +277,29 @@ TOME_API int tome_group_reduce(const void* x, int32_t dtype, int32_t bm, int32_t
                       int32_t mode, void* out, void* stream);
 TOME_API int tome_gather_rows(const void* x, int32_t dtype, int32_t bm, int32_t n_in, int32_t c, const int32_t* map,
                      int32_t n_out, void* out, void* stream);
+
+/* --- `source` consumers and random modes ------------------------------------------
+ * Compact form of the reference's dense source matrix (tome/merge.py:372-384; tome/vis.py:55,102,146 read it as
+ * `source.argmax(dim=1)`): group (bm, n0) int32, group[b, t] = index of the merged token that holds original
+ * token t, -1 once the token is gone (drop modes, merge.py:260-269; destinations zeroed by a hybrid threshold,
+ * merge.py:326).  dense[b, s, t] == 1 exactly when group[b, t] == s.
+ * tome_source_compose: one block's update.  group_in == NULL is the implicit identity (n0 == plan->n).  drop != 0:
+ *   merged-away A tokens are discarded instead of joining their destination.  hybrid_threshold: NaN = off.
+ * tome_source_dense: the fp32 (bm, n_tokens, n0) matrix the reference API exposes, expanded on demand. */
+TOME_API int tome_source_compose(const tome_plan* plan, const int32_t* group_in, int32_t n0, int32_t drop,
+                        float hybrid_threshold, int32_t* group_out, void* stream);
+TOME_API int tome_source_dense(const int32_t* group, int32_t bm, int32_t n_tokens, int32_t n0, float* out, void* stream);
+
+/* random_merge / random_drop scores (merge.py:54-57, 235-238: torch.rand of shape (bm, na, nb), then max) from a
+ * counter-based Philox4x32-10 stream, fused with the masked row max / first argmax; the score tensor is never
+ * written unless scores_out (bm, na, nb) is given (tests).  key = seed; counter = (column / 4, A row, clip0 + b,
+ * call); score = (word >> 8) * 2^-24.  An edge's score therefore depends only on (seed, call, clip, row, column):
+ * not on the batch composition or on how clips are sharded over GPUs.  philox_state: DEVICE memory,
+ * {uint64 seed, uint64 call}; advance != 0 bumps `call` on the stream after the draw, so a captured CUDA graph
+ * draws fresh scores at every replay. */
+TOME_API int tome_random_rowmax(void* philox_state, int64_t clip0, int32_t bm, int32_t na, int32_t nb, int32_t class_token,
+                       int32_t distill_token, float* node_max, int32_t* node_idx, float* scores_out, int32_t advance,
+                       void* stream);
 
 #ifdef __cplusplus
 }

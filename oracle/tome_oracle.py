@@ -273,6 +273,47 @@ def merge_source(plan, x, source=None, hybrid_threshold=None):
 # ----------------------------------------------------------------------------------------
 # comparison helper used by the parity tests (gap-aware; SURVEY.md section 7, hard part 1)
 # ----------------------------------------------------------------------------------------
+
+# ---- random-mode scores: counter-based Philox4x32-10 ---------------------------------
+# The reference draws torch.rand((bm, na, nb)) (tome/merge.py:54-57, 235-238); the CUDA path can instead draw
+# from a Philox stream (include/tome_b200.h: tome_random_rowmax).  Algorithm: Salmon, Moraes, Dror, Shaw,
+# "Parallel random numbers: as easy as 1, 2, 3" (SC'11), philox4x32 with 10 rounds; pinned by the Random123
+# known-answer vectors in tests/test_oracle_golden.py.
+_PH_M0, _PH_M1, _PH_W0, _PH_W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+
+
+def philox4x32_10(counter: np.ndarray, key) -> np.ndarray:
+    """counter: (..., 4) uint32-valued array, key: (k0, k1).  Returns (..., 4) uint32."""
+    c = np.asarray(counter, dtype=np.uint64) & np.uint64(0xFFFFFFFF)
+    k0, k1 = int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(_PH_M0) * c[..., 0]
+        p1 = np.uint64(_PH_M1) * c[..., 2]
+        c = np.stack(((p1 >> np.uint64(32)) ^ c[..., 1] ^ np.uint64(k0), p1 & mask,
+                      (p0 >> np.uint64(32)) ^ c[..., 3] ^ np.uint64(k1), p0 & mask), axis=-1)
+        k0, k1 = (k0 + _PH_W0) & 0xFFFFFFFF, (k1 + _PH_W1) & 0xFFFFFFFF
+    return c.astype(np.uint32)
+
+
+def philox_scores(seed: int, call: int, clip0: int, bm: int, na: int, nb: int) -> np.ndarray:
+    """(bm, na, nb) fp32 scores of the stream: key = seed, counter = (column // 4, A row, clip0 + b, call),
+    score = (word >> 8) * 2^-24."""
+    quads = (nb + 3) // 4
+    ctr = np.zeros((bm, na, quads, 4), dtype=np.uint64)
+    ctr[..., 0] = np.arange(quads, dtype=np.uint64)[None, None, :]
+    ctr[..., 1] = np.arange(na, dtype=np.uint64)[None, :, None]
+    ctr[..., 2] = (np.uint64(clip0) + np.arange(bm, dtype=np.uint64))[:, None, None] & np.uint64(0xFFFFFFFF)
+    ctr[..., 3] = np.uint64(call & 0xFFFFFFFF)
+    words = philox4x32_10(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)).reshape(bm, na, quads * 4)[..., :nb]
+    return ((words >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
+
+
+def source_dense(group: np.ndarray, tokens: int) -> np.ndarray:
+    """Dense fp32 (bm, tokens, n0) matrix of a compact source map (group[b, t] = merged token of original t, -1 = gone)."""
+    return (group[:, None, :] == np.arange(tokens)[None, :, None]).astype(np.float32)
+
+
 def decisions_equivalent(ref_scores: np.ndarray, plan_a: Plan, plan_b: Plan, ulps: float = 8.0):
     """True when two plans differ only where the score margins are within ``ulps`` fp32 ulp.
 

@@ -876,3 +876,95 @@ def test_plan_cluster_frames_view_and_zero_norm_rows(native, monkeypatch):
         assert torch.equal(got.node_max.view(torch.int32), want.node_max.view(torch.int32))
         for name in ("src_idx", "unm_idx", "dst_idx", "a_map", "b_off", "b_src", "b_head"):
             assert torch.equal(getattr(got, name), getattr(want, name)), name
+
+
+# ---- compact source map and Philox random scores --------------------------------------
+@pytest.mark.parametrize("mode", ["merge", "hybrid", "drop"])
+@pytest.mark.parametrize("flags", [(False, False), (True, False), (True, True)], ids=["plain", "cls", "cls_distill"])
+def test_compact_source_map_equals_dense_source_chain(native, mode, flags):
+    """Three blocks of source tracking on the compact (bm, n0) int32 form; its dense expansion must be the matrix
+    the dense kernel path AND the oracle's merge_source (merge.py:372-384, pinned by the reference goldens) build."""
+    import tome
+    cls, dis = flags
+    g = torch.Generator().manual_seed(11)
+    bm, n, c = 3, 61, 16
+    x = torch.randn(bm, n, c, generator=g)
+    compact, dense, want = None, None, None
+    xs = x.numpy()
+    for layer, r in enumerate((9, 7, 30)):
+        metric = torch.randn(bm, xs.shape[1], 8, generator=g)
+        plan = O.bipartite_soft_matching(metric.numpy(), r, cls, dis)
+        xd = torch.from_numpy(xs).cuda()
+        if mode == "drop":
+            op = tome.merge.bipartite_soft_matching_drop(metric.cuda(), r, cls, dis)
+            compact = op.source_map(compact)
+            if dense is None:
+                dense = torch.eye(xs.shape[1], device="cuda")[None].expand(bm, -1, -1).contiguous()
+                want = np.broadcast_to(np.eye(xs.shape[1], dtype=np.float32), (bm, xs.shape[1], xs.shape[1]))
+            dense = op(dense)
+            want = O.drop(plan, want)
+            xs = O.drop(plan, xs)
+        else:
+            thr = 0.05 if mode == "hybrid" else None
+            if thr is None:
+                op, _ = tome.merge.bipartite_soft_matching(metric.cuda(), r, cls, dis)
+            else:
+                op, _ = tome.merge.bipartite_soft_matching_hybrid(metric.cuda(), r, cls, dis, threshold=thr)
+            compact = tome.merge.trace_source(op, xd, compact)
+            dense = tome.merge.merge_source(op, xd, dense)
+            want = O.merge_source(plan, xs, want, hybrid_threshold=thr)
+            xs = O.merge_wavg(plan, xs, None, hybrid_threshold=thr)[0]
+        assert isinstance(compact, native.SourceMap) and compact.tokens == xs.shape[1]
+        got = compact.dense().cpu().numpy()
+        np.testing.assert_array_equal(got, want, err_msg=f"layer {layer}")
+        np.testing.assert_array_equal(dense.cpu().numpy(), want)
+        np.testing.assert_array_equal(O.source_dense(compact.group.cpu().numpy(), compact.tokens), want)
+        # what tome/vis.py:55 asks of the matrix
+        np.testing.assert_array_equal(compact.argmax(dim=1).cpu().numpy(), want.argmax(axis=1))
+    if mode == "hybrid":
+        assert (compact.group < 0).any(), "the threshold should have dropped some destinations in this case"
+
+
+def test_philox_random_scores_match_oracle_and_do_not_depend_on_sharding(native):
+    """tome_random_rowmax: the raw draw equals the numpy Philox4x32-10 stream bit for bit, the fused row max equals
+    the masked max of the materialised draw, `call` advances on the stream, and a clip's scores do not depend on
+    which batch (rank) it rides in."""
+    seed, bm, na, nb = 0x1234_5678_9ABC_DEF0, 5, 37, 35
+    st = native.PhiloxStream(seed, "cuda")
+    nm, ni, sc = native.random_rowmax(st, bm, na, nb, True, True, want_scores=True)
+    want = O.philox_scores(seed, 0, 0, bm, na, nb)
+    np.testing.assert_array_equal(sc.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    masked = want.copy()
+    masked[:, 0, :] = -np.inf
+    masked[:, :, 0] = -np.inf
+    onm, oni = O.rowmax(masked)
+    np.testing.assert_array_equal(ni.cpu().numpy(), oni)
+    np.testing.assert_array_equal(nm.cpu().numpy(), onm)
+    assert st.calls() == 1
+    _, _, sc1 = native.random_rowmax(st, bm, na, nb, want_scores=True)
+    np.testing.assert_array_equal(sc1.cpu().numpy(), O.philox_scores(seed, 1, 0, bm, na, nb))
+    # a rank holding clips 3..4 of the global batch draws what a single GPU holding all five draws for them
+    shard = native.PhiloxStream(seed, "cuda", clip_offset=3)
+    _, _, sc_shard = native.random_rowmax(shard, 2, na, nb, want_scores=True)
+    np.testing.assert_array_equal(sc_shard.cpu().numpy(), want[3:5])
+
+
+def test_random_modes_on_the_philox_stream(native):
+    import tome
+    x = torch.randn(4, 90, 8, device="cuda")
+    try:
+        tome.merge.philox_seed(99)
+        merge, _ = tome.merge.bipartite_soft_matching(x, 11, mode="random_merge")
+        scores = O.philox_scores(99, 0, 0, 4, 45, 45)
+        plan = O.bipartite_soft_matching(x.cpu().numpy(), 11, given_scores=scores)
+        np.testing.assert_array_equal(merge.plan.src_idx.cpu().numpy(), plan.src_idx)
+        np.testing.assert_array_equal(merge.plan.dst_idx.cpu().numpy(), plan.dst_idx)
+        drop = tome.merge.bipartite_soft_matching_drop(x, 11, mode="random_drop")          # second call of the stream
+        plan2 = O.bipartite_soft_matching(x.cpu().numpy(), 11, given_scores=O.philox_scores(99, 1, 0, 4, 45, 45))
+        np.testing.assert_array_equal(drop(x).cpu().numpy(), O.drop(plan2, x.cpu().numpy()))
+        # re-seeding replays the stream
+        tome.merge.philox_seed(99)
+        again, _ = tome.merge.bipartite_soft_matching(x, 11, mode="random_merge")
+        assert torch.equal(again.plan.src_idx, merge.plan.src_idx)
+    finally:
+        tome.merge.philox_seed(None)

@@ -48,6 +48,9 @@ def port_backend():
             setattr(mod, n, f)
 
 
+_LAST_INFO = [None]          # _tome_info of the most recent _run (source tests)
+
+
 def _run(case, device, dtype, backend_ctx):
     import tome
     model = G.seeded_fill(G.build_ours(case).eval()).to(device=device, dtype=dtype)
@@ -60,6 +63,7 @@ def _run(case, device, dtype, backend_ctx):
     model.r = case["r"]
     with backend_ctx, torch.no_grad():
         merged = model([clip]).float().cpu()
+    _LAST_INFO[0] = model._tome_info
     return plain, merged, model._tome_info["size"].float().cpu()
 
 
@@ -179,3 +183,38 @@ def test_training_step_gradients_match_cpu_port(name):
         worst = max(worst, err)
     print(f"[model-parity] {name}: max rel grad err = {worst:.2e}")
     assert worst < 5e-3, worst
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["videomae_merge", "videomae_hybrid", "timesformer_drop", "timesformer_merge", "motionformer_merge",
+                                  "vivit_merge", "vivit_drop"])
+def test_traced_source_compact_path_equals_dense_path(name, monkeypatch):
+    """trace_source=True: the patches track the compact group map per block and expand it once after
+    the forward; `_tome_info['source']` must be the dense matrix the per-block dense kernels (tome_merge_source, pinned
+    against the reference's merge_source goldens) build, and -- merge modes -- its row sums are the token sizes."""
+    import tome
+    from tome import _native
+    case = dict(next(c for c in G.MODEL_CASES if c["name"] == name))
+    case["kw"] = dict(case["kw"], trace_source=True)
+    plain, merged, size = _run(case, "cuda", torch.float32, contextlib.nullcontext())
+    model_info = _LAST_INFO[0]
+    src = model_info["source"]
+    assert torch.is_tensor(src) and src.dtype == torch.float32 and src.dim() == 3
+    assert isinstance(model_info["source_map"], _native.SourceMap)
+    assert src.shape[:2] == model_info["size"].shape[:2]
+    assert float(src.sum(1).max()) <= 1.0                      # an original token lives in at most one merged token
+    if case["kw"].get("mode", "merge") == "merge":
+        torch.testing.assert_close(src.sum(-1), model_info["size"][..., 0].float(), rtol=0, atol=0)
+
+    def dense_trace(op, x, source, drop=False):                # the reference's per-block dense form on the dense kernels
+        if drop:
+            if source is None:
+                n, t = x.shape[0], x.shape[1]
+                source = torch.eye(t, device=x.device)[None].expand(n, t, t)
+            return op(source.contiguous())
+        return tome.merge.merge_source(op, x, source)
+    for mn in ("tome.patch.videomae", "tome.patch.timesformer", "tome.patch.motionformer", "tome.patch.vivit"):
+        monkeypatch.setattr(sys.modules[mn], "trace_source", dense_trace)
+    plain2, merged2, _ = _run(case, "cuda", torch.float32, contextlib.nullcontext())
+    assert torch.equal(merged, merged2)
+    assert torch.equal(_LAST_INFO[0]["source"], src)

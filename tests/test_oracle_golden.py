@@ -91,3 +91,19 @@ def test_orderable_key_is_monotone():
     k = O.orderable_u32(v)
     assert k[2] == k[3]
     assert np.all(np.diff(k.astype(np.int64)[[0, 1, 2, 4, 5, 6, 7, 8]]) > 0)
+
+
+def test_philox_oracle_known_answers():
+    """Random123's philox4x32-10 known-answer vectors (kat_vectors: zeros, all ones, digits of pi) pin the stream
+    the random_* modes can draw from (oracle.philox_scores <-> tome_random_rowmax)."""
+    def words(ctr, key):
+        return [int(v) for v in O.philox4x32_10(np.array(ctr), key)]
+    assert words([0, 0, 0, 0], (0, 0)) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert words([0xffffffff] * 4, (0xffffffff, 0xffffffff)) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert words([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], (0xa4093822, 0x299f31d0)) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    s = O.philox_scores(5, 2, 1, 2, 3, 6)
+    assert s.dtype == np.float32 and s.shape == (2, 3, 6) and (s >= 0).all() and (s < 1).all()
+    # column quad q of (row i, clip c, call k) is ONE counter: (q, i, c, k)
+    w = O.philox4x32_10(np.array([1, 2, 2, 2]), (5, 0))
+    np.testing.assert_array_equal(s[1, 2, 4:6], ((w[:2] >> 8).astype(np.float32) * np.float32(2.0 ** -24)))

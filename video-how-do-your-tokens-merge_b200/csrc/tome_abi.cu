@@ -76,6 +76,9 @@ size_t match_sets_workspace(int bm, int rows, int ra, int cm);
 int launch_match_sets(const void*, int, int, int, const View&, const int*, long long, int, int, float*, int*, void*, size_t, cudaStream_t);
 int launch_group_reduce(const void*, int, int, int, const View&, const int*, long long, int, int, const int*, int, void*, cudaStream_t);
 int launch_gather_rows(const void*, int, int, int, int, const int*, int, void*, cudaStream_t);
+int launch_source_compose(const tome_plan*, const int*, int, int, float, int*, cudaStream_t);
+int launch_source_dense(const int*, int, int, int, float*, cudaStream_t);
+int launch_random_rowmax(void*, long long, int, int, int, int, int, float*, int*, float*, int, cudaStream_t);
 
 static int check_plan(const tome_plan* p, const char* who) {
   if (!p) return set_error(TOME_ERR_ARG, "%s: plan is NULL", who);
@@ -391,6 +394,37 @@ int tome_gather_rows(const void* x, int32_t dtype, int32_t bm, int32_t n_in, int
   TOME_CHECK_ARG(x && map && out && bm > 0 && n_in > 0 && n_out > 0 && c > 0, "tome_gather_rows: bad argument");
   if (dtype != TOME_F32 && dtype != TOME_BF16) return set_error(TOME_ERR_DTYPE, "tome_gather_rows: unsupported dtype %d", dtype);
   return launch_gather_rows(x, dtype, bm, n_in, c, map, n_out, out, (cudaStream_t)stream);
+}
+
+int tome_source_compose(const tome_plan* plan, const int32_t* group_in, int32_t n0, int32_t drop, float hybrid_threshold,
+                        int32_t* group_out, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  rc = check_plan(plan, "tome_source_compose");
+  if (rc) return rc;
+  TOME_CHECK_ARG(group_out && n0 > 0, "tome_source_compose: NULL output or n0=%d", n0);
+  TOME_CHECK_ARG(group_in || n0 == plan->n, "tome_source_compose: implicit identity needs n0 == n (n0=%d n=%d)", n0, plan->n);
+  return launch_source_compose(plan, group_in, n0, drop, hybrid_threshold, group_out, (cudaStream_t)stream);
+}
+
+int tome_source_dense(const int32_t* group, int32_t bm, int32_t n_tokens, int32_t n0, float* out, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(group && out && bm > 0 && n_tokens > 0 && n0 > 0, "tome_source_dense: NULL pointer or empty shape");
+  if (bm > TOME_MAX_BATCH) return set_error(TOME_ERR_UNSUPPORTED, "tome_source_dense: matching batch %d > %d; split the batch", bm, TOME_MAX_BATCH);
+  return launch_source_dense(group, bm, n_tokens, n0, out, (cudaStream_t)stream);
+}
+
+int tome_random_rowmax(void* philox_state, int64_t clip0, int32_t bm, int32_t na, int32_t nb, int32_t class_token,
+                       int32_t distill_token, float* node_max, int32_t* node_idx, float* scores_out, int32_t advance, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(philox_state && node_max && node_idx, "tome_random_rowmax: NULL pointer argument");
+  TOME_CHECK_ARG(bm > 0 && na > 0 && nb > 0 && clip0 >= 0, "tome_random_rowmax: bad shape bm=%d na=%d nb=%d", bm, na, nb);
+  TOME_CHECK_ARG(((uintptr_t)philox_state & 7) == 0, "tome_random_rowmax: philox_state must be 8-byte aligned");
+  if (bm > TOME_MAX_BATCH) return set_error(TOME_ERR_UNSUPPORTED, "tome_random_rowmax: matching batch %d > %d; split the batch", bm, TOME_MAX_BATCH);
+  return launch_random_rowmax(philox_state, clip0, bm, na, nb, class_token, distill_token, node_max, node_idx, scores_out, advance,
+                              (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 TOME_F32, TOME_BF16, TOME_U8 = 0, 1, 2
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -31,6 +31,7 @@ EXPORTS = (
     "tome_rowmax", "tome_select_workspace_bytes", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_add_norm", "tome_add_layernorm", "tome_add_rows_layernorm",
     "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_linear_gelu", "tome_unmerge",
     "tome_match_sets_workspace_bytes", "tome_match_sets", "tome_group_reduce", "tome_gather_rows",
+    "tome_source_compose", "tome_source_dense", "tome_random_rowmax",
 )
 
 
@@ -117,6 +118,11 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.tome_group_reduce.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(TomeViewC), c_vp, c_i64, c_i32, c_i32,
                                       c_vp, c_i32, c_vp, c_vp]
     lib.tome_gather_rows.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp]
+    lib.tome_source_compose.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_i32, c_f32, c_vp, c_vp]
+    lib.tome_source_dense.argtypes = [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]
+    lib.tome_random_rowmax.argtypes = [c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp]
+    for name in ("tome_source_compose", "tome_source_dense", "tome_random_rowmax"):
+        getattr(lib, name).restype = c_i32
     for name in ("tome_device_check", "tome_match", "tome_match_heads", "tome_rowmax", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_add_norm", "tome_add_layernorm", "tome_add_rows_layernorm",
                  "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_linear_gelu", "tome_unmerge",
                  "tome_match_sets", "tome_group_reduce", "tome_gather_rows"):
@@ -612,6 +618,82 @@ def merge_source(plan: DevicePlan, source: Optional[torch.Tensor], hybrid_thresh
         _check(lib.tome_merge_source(plan.c_ptr(), sp, n0, thr, out.data_ptr(),
                                      torch.cuda.current_stream(dev).cuda_stream), lib)
     return out
+
+
+class SourceMap:
+    """Compact form of the reference's dense source matrix (merge.py:372-384): ``group`` (bm, n0) int32 names the
+    merged token that holds each original token (-1: dropped).  ``dense()`` expands to the fp32 (bm, tokens, n0)
+    0/1 matrix the reference API exposes; ``argmax(dim=1)`` -- what tome/vis.py:55,102,146 asks of it -- is the
+    group map itself."""
+
+    def __init__(self, group: torch.Tensor, tokens: int):
+        self.group, self.tokens = group, int(tokens)
+
+    shape = property(lambda self: torch.Size((self.group.shape[0], self.tokens, self.group.shape[1])))
+    device = property(lambda self: self.group.device)
+
+    def dense(self) -> torch.Tensor:
+        lib = load_library()
+        bm, n0 = self.group.shape
+        with torch.cuda.device(self.group.device):
+            out = torch.empty(bm, self.tokens, n0, dtype=torch.float32, device=self.group.device)
+            _check(lib.tome_source_dense(self.group.data_ptr(), bm, self.tokens, n0, out.data_ptr(), _stream(self.group)), lib)
+        return out
+
+    def argmax(self, dim: int = 1) -> torch.Tensor:
+        if dim != 1:
+            return self.dense().argmax(dim=dim)
+        return self.group.clamp(min=0).long()          # an all-zero column's argmax is 0, as torch's is
+
+    def __getitem__(self, item):
+        return self.dense()[item]
+
+
+def source_compose(plan: DevicePlan, source: Optional["SourceMap"], drop: bool = False,
+                   hybrid_threshold: Optional[float] = None) -> "SourceMap":
+    """One block's update of the compact source map."""
+    lib = load_library()
+    thr = float("nan") if hybrid_threshold is None else float(hybrid_threshold)
+    dev = plan.device
+    with torch.cuda.device(dev):
+        if source is None:
+            n0, gp = plan.n, None
+        else:
+            if source.tokens != plan.n or source.group.shape[0] != plan.bm:
+                raise RuntimeError(f"tome_b200: source map of {source.group.shape[0]} x {source.tokens} tokens does not match "
+                                   f"the plan ({plan.bm} x {plan.n})")
+            n0, gp = source.group.shape[1], source.group.data_ptr()
+        out = torch.empty(plan.bm, n0, dtype=torch.int32, device=dev)
+        _check(lib.tome_source_compose(plan.c_ptr(), gp, n0, int(bool(drop)), thr, out.data_ptr(),
+                                       torch.cuda.current_stream(dev).cuda_stream), lib)
+    return SourceMap(out, plan.n - plan.r)
+
+
+class PhiloxStream:
+    """Device-resident (seed, call) pair of the random-score stream (include/tome_b200.h: tome_random_rowmax)."""
+
+    def __init__(self, seed: int, device, clip_offset: int = 0):
+        self.seed, self.clip_offset = int(seed) & (2 ** 64 - 1), int(clip_offset)
+        words = [self.seed & 0x7FFFFFFFFFFFFFFF if self.seed < 2 ** 63 else self.seed - 2 ** 64, 0]
+        self.state = torch.tensor(words, dtype=torch.int64, device=device)
+
+    def calls(self) -> int:
+        return int(self.state[1].item())
+
+
+def random_rowmax(stream: "PhiloxStream", bm: int, na: int, nb: int, class_token=False, distill_token=False,
+                  want_scores: bool = False, advance: bool = True):
+    lib = load_library()
+    dev = stream.state.device
+    with torch.cuda.device(dev):
+        node_max = torch.empty(bm, na, dtype=torch.float32, device=dev)
+        node_idx = torch.empty(bm, na, dtype=torch.int32, device=dev)
+        scores = torch.empty(bm, na, nb, dtype=torch.float32, device=dev) if want_scores else None
+        _check(lib.tome_random_rowmax(stream.state.data_ptr(), stream.clip_offset, bm, na, nb, int(bool(class_token)),
+                                      int(bool(distill_token)), node_max.data_ptr(), node_idx.data_ptr(),
+                                      None if scores is None else scores.data_ptr(), int(bool(advance)),
+                                      torch.cuda.current_stream(dev).cuda_stream), lib)
+    return (node_max, node_idx, scores) if want_scores else (node_max, node_idx)
 
 
 def unmerge(plan: DevicePlan, x: torch.Tensor) -> torch.Tensor:

@@ -37,6 +37,18 @@ def _effective_r(metric: torch.Tensor, r: int, class_token: bool, distill_token:
 
 
 _SIDE_STREAMS = {}          # device index -> the stream early matching runs on
+_PHILOX = {}                # device index -> _native.PhiloxStream, once philox_seed() has been called
+
+
+def philox_seed(seed: Optional[int], clip_offset: int = 0) -> None:
+    """Draw the scores of the random_* modes (merge.py:54-57, 235-238) from the library's counter-based Philox
+    stream instead of ``torch.rand``: an edge's score then depends only on (seed, call number, clip_offset + clip,
+    row, column) -- independent of the batch composition and of how clips are sharded over GPUs (give each rank its
+    first clip's global index as ``clip_offset``) -- and the (bm, na, nb) score tensor is never materialised.
+    ``seed=None`` goes back to the reference's own ``torch.rand`` call (the default)."""
+    _PHILOX.clear()
+    if seed is not None:
+        _PHILOX["seed"] = (int(seed), int(clip_offset))
 
 
 def prefetch_matching(metric, r: int, class_token: bool = False, distill_token: bool = False) -> None:
@@ -85,8 +97,15 @@ def _make_plan(metric, r, class_token, distill_token, random_scores: bool) -> "_
         if random_scores:                          # merge.py:54-57: same torch.rand call, same generator
             length = metric.size(1)
             len_a, len_b = (length + 1) // 2, length // 2
-            scores = torch.rand(size=(metric.size(0), len_a, len_b), device=metric.device)
-            node_max, node_idx = _native.rowmax(scores, class_token, distill_token)
+            if "seed" in _PHILOX:
+                dev = metric.device
+                stream = _PHILOX.get(dev.index)
+                if stream is None:
+                    stream = _PHILOX[dev.index] = _native.PhiloxStream(_PHILOX["seed"][0], dev, _PHILOX["seed"][1])
+                node_max, node_idx = _native.random_rowmax(stream, metric.size(0), len_a, len_b, class_token, distill_token)
+            else:
+                scores = torch.rand(size=(metric.size(0), len_a, len_b), device=metric.device)
+                node_max, node_idx = _native.rowmax(scores, class_token, distill_token)
             return _native.select(node_max, node_idx, metric.shape[1], r, class_token, distill_token)
         return _native.plan_build(metric, r, class_token, distill_token)        # kernels 1 + 2, one ABI call
 
@@ -181,7 +200,13 @@ class Merge(_PlanCallable):
         return (out, s[..., None], ls[..., None]) + tuple(res[3:])
 
     def source(self, source=None):
+        if isinstance(source, _native.SourceMap):      # compact form stays compact
+            return _native.source_compose(self.plan, source, False, self.threshold)
         return _native.merge_source(self.plan, source, self.threshold)
+
+    def source_map(self, source=None):
+        """merge_source on the compact form: ``source`` is a SourceMap or None (identity)."""
+        return _native.source_compose(self.plan, source, False, self.threshold)
 
     def wavg_frames(self, x, frames, size=None, norm=None):
         """merge_wavg on a (B, 1 + P*T, C) class-token + '(p t)' tensor whose matching batch is (b t):
@@ -232,6 +257,10 @@ class Drop(_PlanCallable):
         if _needs_grad(x):
             return _MergeGrad.apply(x, self.plan, "drop", None, None)
         return _native.merge(self.plan, x, "drop")
+
+    def source_map(self, source=None):
+        """The drop closure applied to the compact source form (dropped tokens get group -1)."""
+        return _native.source_compose(self.plan, source, True, None)
 
     def frames(self, x, frames):
         """drop on the (B, 1 + P*T, C) layout (see Merge.wavg_frames)."""
@@ -302,10 +331,45 @@ def merge_source(merge: Callable, x: torch.Tensor, source: torch.Tensor = None) 
     """Source adjacency tracking (merge.py:372-384)."""
     if isinstance(merge, Merge):
         return merge.source(source)
+    if isinstance(source, _native.SourceMap):
+        return source                      # do_nothing: no tokens moved
     if source is None:
         n, t, _ = x.shape
         source = torch.eye(t, device=x.device)[None, ...].expand(n, t, t)
     return merge(source, mode="max")
+
+
+# ---- compact source tracing used by the patches (SURVEY.md 8f-f4) ---------------------------------------
+def trace_source(op, x: torch.Tensor, source, drop: bool = False):
+    """One block's ``merge_source`` (merge.py:372-384) / ``drop(source)`` (videomae.py:118-122) on the compact
+    form: returns a ``_native.SourceMap``.  The patched model expands it to the reference's dense fp32 matrix
+    once, at the end of the forward (``finish_source``), instead of re-reducing a (bm, n, n0) matrix per block.
+    A dense ``source`` tensor (a caller that started in the reference's form) stays dense."""
+    if isinstance(op, (Merge, Drop)):
+        if torch.is_tensor(source):
+            return op(source.contiguous()) if isinstance(op, Drop) else op.source(source)
+        return op.source_map(source)
+    if op is do_nothing or isinstance(op, tuple):        # r clamped to 0: nothing moves
+        if source is None:
+            n, t = x.shape[0], x.shape[1]
+            source = _native.SourceMap(torch.arange(t, device=x.device, dtype=torch.int32).expand(n, t).contiguous(), t)
+        return source
+    # a foreign callable (the tests route the patches to a CPU port of the reference): the reference's dense form
+    if drop:
+        if source is None:
+            n, t, _ = x.shape
+            source = torch.eye(t, device=x.device)[None, ...].expand(n, t, t)
+        return op(source.contiguous())
+    return merge_source(op, x, source)
+
+
+def finish_source(info: dict) -> None:
+    """``_tome_info['source']`` as the reference leaves it -- dense (bm, tokens, n0) fp32 -- with the compact map
+    kept beside it as ``_tome_info['source_map']``."""
+    src = info.get("source")
+    if isinstance(src, _native.SourceMap):
+        info["source_map"] = src
+        info["source"] = src.dense()
 
 
 # ---- upstream-ToMe variants with no caller in the reference (merge.py:105-212) -------------

@@ -10,7 +10,7 @@ import torch
 import torch.nn.functional as F
 
 from tome.merge import (Drop, Merge, bipartite_soft_matching, bipartite_soft_matching_drop,
-                        bipartite_soft_matching_hybrid)
+                        bipartite_soft_matching_hybrid, finish_source, trace_source)
 from tome.patch.timesformer import _frames_back, _frames_view, _merge_frames_generic
 from tome import attention as prop_attention
 from tome.patch.videomae import _normed_or, _swap, fusable_norm, lazy_head_mean
@@ -102,7 +102,7 @@ def motionformer_merge(metric, x, _tome_info, num_frames, norm=None):
                                            _tome_info["mode"])
         if isinstance(merge, Merge):
             if _tome_info["trace_source"]:
-                _tome_info["source"] = merge.source(_tome_info["source"])
+                _tome_info["source"] = trace_source(merge, None, _tome_info["source"])
             fn = fusable_norm(norm, x) if norm is not None else None
             res = merge.wavg_frames(x, T, _tome_info["size"], norm=fn)
             x, _tome_info["size"], _tome_info["log_size"] = res[0], res[1], res[2]
@@ -126,9 +126,7 @@ def motionformer_drop(metric, x, _tome_info, num_frames, norm=None):
         if isinstance(drop, tuple):
             return x
         if _tome_info["trace_source"]:
-            if _tome_info["source"] is None:
-                _tome_info["source"] = torch.eye(P, device=x.device)[None, ...].expand(B * T, P, P)
-            _tome_info["source"] = drop(_tome_info["source"].contiguous())
+            _tome_info["source"] = trace_source(drop, x.new_empty((B * T, P, 0)), _tome_info["source"], drop=True)
         if isinstance(drop, Drop):
             x = drop.frames(x, T)
         else:
@@ -152,7 +150,7 @@ def motionformer_hybrid(metric, x, _tome_info, num_frames, norm=None):
                                                   _tome_info["mode"], _tome_info["threshold"])
         if isinstance(merge, Merge):
             if _tome_info["trace_source"]:
-                _tome_info["source"] = merge.source(_tome_info["source"])
+                _tome_info["source"] = trace_source(merge, None, _tome_info["source"])
             fn = fusable_norm(norm, x) if norm is not None else None
             res = merge.wavg_frames(x, T, _tome_info["size"], norm=fn)
             x, _tome_info["size"], _tome_info["log_size"] = res[0], res[1], res[2]
@@ -186,7 +184,9 @@ def make_tome_class(transformer_class):
             self._tome_info["log_size"] = None
             self._tome_info["normed"] = None
             self._tome_info["source"] = None
-            return super().forward(*args, **kwdargs)
+            out = super().forward(*args, **kwdargs)
+            finish_source(self._tome_info)          # compact source map -> the reference's dense matrix, once
+            return out
 
     return ToMeVisionTransformer
 

@@ -14,7 +14,8 @@ import torch
 import torch.nn.functional as F
 
 from tome.merge import (Drop, Merge, bipartite_soft_matching, bipartite_soft_matching_drop,
-                        bipartite_soft_matching_hybrid, merge_source, merge_wavg)
+                        bipartite_soft_matching_hybrid, finish_source, merge_source, merge_wavg,
+                        trace_source)
 from tome import attention as prop_attention
 from tome.patch.videomae import _normed_or, _swap, fusable_norm, lazy_head_mean
 from tome.utils import parse_r
@@ -101,7 +102,7 @@ def _frames_back(cls, y, B, T):
 def _merge_frames_generic(merge, x, info, B, T, P):
     cls, merged_x = x[:, 0:1, :], _frames_view(x, B, T, P)
     if info["trace_source"]:
-        info["source"] = merge_source(merge, merged_x, info["source"])
+        info["source"] = trace_source(merge, merged_x, info["source"])
     merged_x, info["size"] = merge_wavg(merge, merged_x, info["size"])
     info["log_size"] = None
     return _frames_back(cls, merged_x, B, T)
@@ -117,7 +118,7 @@ def timesformer_merge(metric, x, _tome_info, B, T, num_spatial_tokens, norm=None
         pre_merge = num_spatial_tokens
         if isinstance(merge, Merge):
             if _tome_info["trace_source"]:
-                _tome_info["source"] = merge.source(_tome_info["source"])
+                _tome_info["source"] = trace_source(merge, None, _tome_info["source"])
             fn = fusable_norm(norm, x) if norm is not None else None
             res = merge.wavg_frames(x, T, _tome_info["size"], norm=fn)
             x, _tome_info["size"], _tome_info["log_size"] = res[0], res[1], res[2]
@@ -139,10 +140,7 @@ def timesformer_drop(metric, x, _tome_info, B, T, num_spatial_tokens, norm=None)
         if isinstance(drop, tuple):
             return x
         if _tome_info["trace_source"]:
-            if _tome_info["source"] is None:
-                t = num_spatial_tokens
-                _tome_info["source"] = torch.eye(t, device=x.device)[None, ...].expand(B * T, t, t)
-            _tome_info["source"] = drop(_tome_info["source"].contiguous())
+            _tome_info["source"] = trace_source(drop, x.new_empty((B * T, num_spatial_tokens, 0)), _tome_info["source"], drop=True)
         pre_drop = num_spatial_tokens
         if isinstance(drop, Drop):
             x = drop.frames(x, T)
@@ -166,7 +164,7 @@ def timesformer_hybrid(metric, x, _tome_info, B, T, num_spatial_tokens, norm=Non
         pre_merge = num_spatial_tokens
         if isinstance(merge, Merge):
             if _tome_info["trace_source"]:
-                _tome_info["source"] = merge.source(_tome_info["source"])
+                _tome_info["source"] = trace_source(merge, None, _tome_info["source"])
             fn = fusable_norm(norm, x) if norm is not None else None
             res = merge.wavg_frames(x, T, _tome_info["size"], norm=fn)
             x, _tome_info["size"], _tome_info["log_size"] = res[0], res[1], res[2]
@@ -196,7 +194,9 @@ def make_tome_class(transformer_class):
             self._tome_info["log_size"] = None
             self._tome_info["normed"] = None
             self._tome_info["source"] = None
-            return super().forward(*args, **kwdargs)
+            out = super().forward(*args, **kwdargs)
+            finish_source(self._tome_info)          # compact source map -> the reference's dense matrix, once
+            return out
 
     return ToMeVisionTransformer
 

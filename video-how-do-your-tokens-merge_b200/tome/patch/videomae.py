@@ -17,7 +17,8 @@ import torch
 import torch.nn.functional as F
 
 from tome.merge import (Merge, bipartite_soft_matching, bipartite_soft_matching_drop,
-                        bipartite_soft_matching_hybrid, merge_source, merge_wavg)
+                        bipartite_soft_matching_hybrid, finish_source, merge_source, merge_wavg,
+                        trace_source)
 from tome.utils import parse_r
 from tome import attention as prop_attention
 
@@ -201,7 +202,7 @@ def videomae_merge(metric, x, _tome_info, norm=None, residual=None):
         if residual is not None and not (isinstance(merge, Merge) and _fusable_residual(x, residual)):
             x, residual = x + residual, None
         if _tome_info["trace_source"]:
-            _tome_info["source"] = merge_source(merge, x, _tome_info["source"])
+            _tome_info["source"] = trace_source(merge, x, _tome_info["source"])
         pre_merge = x.size(1)
         if isinstance(merge, Merge):
             x = _wavg(merge, x, _tome_info, norm, residual)
@@ -227,10 +228,7 @@ def videomae_drop(metric, x, _tome_info, norm=None, residual=None):
         if isinstance(drop, tuple):              # r clamped to 0 (reference returns a tuple there)
             return x
         if _tome_info["trace_source"]:
-            if _tome_info["source"] is None:
-                n, t, _ = x.shape
-                _tome_info["source"] = torch.eye(t, device=x.device)[None, ...].expand(n, t, t)
-            _tome_info["source"] = drop(_tome_info["source"].contiguous())
+            _tome_info["source"] = trace_source(drop, x, _tome_info["source"], drop=True)
         pre_drop = x.size(1)
         x = drop(x)
         _tome_info["size"] = torch.ones((x.size(0), x.size(1), 1), device=x.device)
@@ -250,7 +248,7 @@ def videomae_hybrid(metric, x, _tome_info, norm=None, residual=None):
         if residual is not None and not (isinstance(merge, Merge) and _fusable_residual(x, residual)):
             x, residual = x + residual, None
         if _tome_info["trace_source"]:
-            _tome_info["source"] = merge_source(merge, x, _tome_info["source"])
+            _tome_info["source"] = trace_source(merge, x, _tome_info["source"])
         pre_merge = x.size(1)
         if isinstance(merge, Merge):
             x = _wavg(merge, x, _tome_info, norm, residual)
@@ -305,7 +303,9 @@ def make_tome_class(transformer_class):
             self._tome_info["normed"] = None
             self._tome_info["source"] = None
             link_blocks(self.model.blocks, self._tome_info)
-            return super().forward(*args, **kwdargs)
+            out = super().forward(*args, **kwdargs)
+            finish_source(self._tome_info)          # compact source map -> the reference's dense matrix, once
+            return out
 
     return ToMeVisionTransformer
 
