@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 14
+#define TOME_ABI_VERSION 16
 
 #if defined(__GNUC__)
 #define TOME_API __attribute__((visibility("default")))
@@ -203,6 +203,17 @@ TOME_API int tome_merge_add_norm(const tome_plan* plan, const void* x, const voi
                         const void* ln_weight, const void* ln_bias, float ln_eps, void* normed_out,
                         const tome_view* normed_view, void* stream);
 
+/* tome_merge_add_norm with the residual addressed through its OWN view.  TimeSformer / Motionformer hold the
+ * residual stream as 'b (p t) m' behind a class token (x_view.inner = T) while the spatial attention's output is
+ * '(b t) (1 + p) m' (tome/patch/timesformer.py:44-48, motionformer.py:24-27): the reference rearranges and cats it
+ * back before adding; here the add happens inside the merge, each tensor read in place.  residual_view == NULL:
+ * laid out like x. */
+TOME_API int tome_merge_add_norm_rv(const tome_plan* plan, const void* x, const void* residual, const tome_view* residual_view,
+                           int32_t dtype, int32_t c, const tome_view* x_view, const float* size_in, int32_t mode,
+                           float hybrid_threshold, void* out, const tome_view* out_view, float* size_out, float* logsize_out,
+                           const void* ln_weight, const void* ln_bias, float ln_eps, void* normed_out,
+                           const tome_view* normed_view, void* stream);
+
 /* merge_source (merge.py:372-384): source (bm, n, n0) fp32 0/1 adjacency, 'max' reduce.
  * source == NULL means the implicit identity (n0 == n), generated on the fly. */
 TOME_API int tome_merge_source(const tome_plan* plan, const float* source, int32_t n0,
@@ -220,6 +231,17 @@ TOME_API int tome_add_rows_layernorm(const void* a, const void* b, int64_t b_row
                             const void* ln_weight, const void* ln_bias, float ln_eps, void* sum_out,
                             void* normed_out, void* stream);
 
+/* The same add + LayerNorm through (b, p, t) row views, for the divided space-time blocks (SURVEY.md 8f-f2;
+ * tome/patch/timesformer.py:38-56, slowfast/models/timesformer.py:115-153): row (b, p, t), b < nb, p < np, t < nt, of
+ * each tensor lives at base + b*strides[0] + p*strides[1] + t*strides[2] (elements), so the hops between the
+ * '(b p) t' (temporal attention), '(b t) (1 + p)' (spatial attention) and 'b (1 + p t)' (residual stream) row orders
+ * are addressing instead of rearrange / cat copies.  sum_out = a + b (b == NULL: a) and / or
+ * normed_out = LayerNorm(sum) * w + bias; either output may be NULL. */
+TOME_API int tome_rows_add_layernorm(const void* a, const int64_t* a_strides, const void* b, const int64_t* b_strides,
+                            int32_t dtype, int32_t nb, int32_t np, int32_t nt, int32_t c, const void* ln_weight,
+                            const void* ln_bias, float ln_eps, void* sum_out, const int64_t* sum_strides,
+                            void* normed_out, const int64_t* normed_strides, void* stream);
+
 /* Caller-side piece of proportional attention (tome/patch/videomae.py:62-63,
  * vivit.py:103-104, timesformer.py:72-74: attn + log(size) of the key token).  q and k heads carry spare
  * channels d, d+1 (host-padded); this writes k[b, t, h, d..d+1] = two-term split of log_size / scale
@@ -231,6 +253,15 @@ TOME_API int tome_attn_key_bias(const float* log_size, int32_t b, int32_t n, int
                        float scale, int32_t dtype, void* k, int64_t k_stride_b, int64_t k_stride_n,
                        int64_t k_stride_h, void* q, int64_t q_stride_b, int64_t q_stride_n, int64_t q_stride_h,
                        void* stream);
+
+/* Caller-side attention over SHORT sequences: softmax(scale * q k^T) v for `seqs` independent
+ * sequences of n_tok <= 32 tokens and `heads` heads of dimension d = 64 -- TimeSformer's temporal attention on
+ * '(b p) t' rows (slowfast/models/timesformer.py:118-123), 18 816 problems of 8 x 8 per call at the bench shape,
+ * which tile-based flash kernels run at a few percent of HBM speed.  q / k / v element (s, t, h, c) lives at
+ * base + s*seq_stride + t*tok_stride + h*d + c (the QKV GEMM's output is read in place); out (seqs, n_tok, heads, d)
+ * contiguous, same dtype (fp32 / bf16); fp32 scores, softmax and accumulation. */
+TOME_API int tome_attn_short(const void* q, const void* k, const void* v, int32_t dtype, int64_t seqs, int32_t n_tok,
+                    int32_t heads, int32_t d, int64_t seq_stride, int64_t tok_stride, float scale, void* out, void* stream);
 
 /* Caller-side data format: the tubelet embedding of the four models is a Conv3d whose
  * kernel equals its stride (slowfast/models/videomae_video_model_builder.py:138-160), i.e. a GEMM over

@@ -905,7 +905,7 @@ def test_compact_source_map_equals_dense_source_chain(native, mode, flags):
             want = O.drop(plan, want)
             xs = O.drop(plan, xs)
         else:
-            thr = 0.05 if mode == "hybrid" else None
+            thr = 0.85 if mode == "hybrid" else None
             if thr is None:
                 op, _ = tome.merge.bipartite_soft_matching(metric.cuda(), r, cls, dis)
             else:
@@ -968,3 +968,89 @@ def test_random_modes_on_the_philox_stream(native):
         assert torch.equal(again.plan.src_idx, merge.plan.src_idx)
     finally:
         tome.merge.philox_seed(None)
+
+
+# ---- the callers either side of the path in the divided space-time blocks -------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_rows_add_layernorm_through_views(native, dtype):
+    """tome_rows_add_layernorm on the three row orders of a TimeSformer block (timesformer.py:38-56): same bits as the
+    contiguous tome_add_layernorm on materialised copies, and torch's add + layer_norm within rounding."""
+    g = torch.Generator().manual_seed(5)
+    B, P, T, C = 2, 7, 4, 64
+    x = torch.randn(B, 1 + P * T, C, generator=g).to("cuda", dtype)
+    tf = torch.randn(B, P, T, C, generator=g).to("cuda", dtype)
+    w = (1 + 0.1 * torch.randn(C, generator=g)).to("cuda", dtype)
+    b = (0.1 * torch.randn(C, generator=g)).to("cuda", dtype)
+    norm = (w, b, 1e-6)
+    x4 = x[:, 1:].unflatten(1, (P, T))
+    # (1) LayerNorm only, '(b p) t' output
+    nt = torch.empty(B, P, T, C, device="cuda", dtype=dtype)
+    native.rows_add_layernorm(x4, None, norm, None, nt)
+    want = torch.nn.functional.layer_norm(x[:, 1:].float(), (C,), w.float(), b.float(), 1e-6).reshape(B, P, T, C)
+    torch.testing.assert_close(nt.float(), want, rtol=2e-2 if dtype == torch.bfloat16 else 1e-5, atol=2e-2 if dtype == torch.bfloat16 else 1e-5)
+    # (2) add, sum into the residual-stream layout, LayerNorm into '(b t) (1 + p)' rows
+    xfull = torch.zeros_like(x)
+    ns = torch.zeros(B * T, 1 + P, C, device="cuda", dtype=dtype)
+    native.rows_add_layernorm(x4, tf, norm, xfull[:, 1:].unflatten(1, (P, T)), ns.view(B, T, 1 + P, C)[:, :, 1:].permute(0, 2, 1, 3))
+    s_ref, n_ref = native.add_layernorm(x[:, 1:].contiguous(), tf.reshape(B, P * T, C), norm)          # the contiguous kernel
+    assert torch.equal(xfull[:, 1:], s_ref)
+    assert torch.equal(xfull[:, 0], torch.zeros_like(xfull[:, 0]))                                        # class row untouched
+    got = ns.view(B, T, 1 + P, C)[:, :, 1:].permute(0, 2, 1, 3).reshape(B, P * T, C)
+    assert torch.equal(got, n_ref)
+    assert torch.equal(ns[:, 0], torch.zeros_like(ns[:, 0]))
+    torch.testing.assert_close(s_ref.float(), (x[:, 1:].float() + tf.reshape(B, P * T, C).float()).to(dtype).float())
+    # (3) sum only
+    only = torch.empty(B, P, T, C, device="cuda", dtype=dtype)
+    native.rows_add_layernorm(x4, tf, None, only, None)
+    assert torch.equal(only.reshape(B, P * T, C), s_ref)
+
+
+@pytest.mark.parametrize("mode", ["merge", "hybrid", "drop"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_merge_frames_with_the_spatial_residual_in_its_own_layout(native, mode, dtype):
+    """merge on 'b (1 + p t)' tokens with the spatial attention's '(b t) (1 + p)' output added inside the kernel
+    (tome_merge_add_norm_rv) == the reference's rearrange + cat + add (timesformer.py:46-48) followed by the merge."""
+    import tome
+    g = torch.Generator().manual_seed(9)
+    B, T, P, C = 2, 4, 22, 64
+    x = torch.randn(B, 1 + P * T, C, generator=g).to("cuda", dtype)
+    res_s = torch.randn(B * T, 1 + P, C, generator=g).to("cuda", dtype)
+    cls = torch.randn(B, C, generator=g).to("cuda", dtype)
+    metric = torch.randn(B * T, P, 16, generator=g).cuda()
+    size = torch.randint(1, 4, (B * T, P, 1), generator=g).float().cuda()
+    w = (1 + 0.1 * torch.randn(C, generator=g)).to("cuda", dtype)
+    bb = (0.1 * torch.randn(C, generator=g)).to("cuda", dtype)
+    full = torch.empty_like(x)
+    full[:, 0] = cls
+    full[:, 1:] = x[:, 1:] + res_s[:, 1:].reshape(B, T, P, C).transpose(1, 2).reshape(B, P * T, C)
+    if mode == "drop":
+        op = tome.merge.bipartite_soft_matching_drop(metric, 6)
+        got = op.frames(x, T, residual=res_s, cls=cls)
+        want = op.frames(full, T)
+        assert torch.equal(got, want)
+        return
+    if mode == "hybrid":
+        op, _ = tome.merge.bipartite_soft_matching_hybrid(metric, 6, threshold=0.7)
+    else:
+        op, _ = tome.merge.bipartite_soft_matching(metric, 6)
+    got = op.wavg_frames(x, T, size, norm=(w, bb, 1e-6), residual=res_s, cls=cls)
+    want = op.wavg_frames(full, T, size, norm=(w, bb, 1e-6))
+    for a, b_ in zip(got, want):
+        assert torch.equal(a, b_)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("tn", [8, 5, 32])
+def test_attn_short_matches_softmax_attention(native, dtype, tn):
+    """tome_attn_short (TimeSformer's temporal attention, slowfast/models/timesformer.py:76-84 on '(b p) t' rows) against
+    the eager softmax formulation in fp64."""
+    g = torch.Generator().manual_seed(tn)
+    seqs, H, d = 37, 3, 64
+    qkv = torch.randn(seqs, tn, 3 * H * d, generator=g).to("cuda", dtype)
+    out = native.attn_short(qkv, H, d ** -0.5)
+    q, k, v = qkv.double().reshape(seqs, tn, 3, H, d).permute(2, 0, 3, 1, 4)
+    want = ((q @ k.transpose(-1, -2)) * d ** -0.5).softmax(-1) @ v
+    want = want.transpose(1, 2).reshape(seqs, tn, H * d)
+    tol = 1e-2 if dtype == torch.bfloat16 else 2e-6
+    torch.testing.assert_close(out.double(), want, rtol=tol, atol=tol)
+    assert native.attn_short_usable(qkv[..., :H * d], H) and not native.attn_short_usable(torch.zeros(2, 33, H * d, device="cuda"), H)

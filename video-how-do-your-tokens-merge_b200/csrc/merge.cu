@@ -22,8 +22,9 @@ struct MergeArgs {
   const float* node_max;
   const int *unm_idx, *b_off, *b_src, *b_head;
   const void* x;
-  const void* res;       // optional residual, same layout as x: every input row is round_T(x + res)
+  const void* res;       // optional residual: every input row is round_T(x + res)
   View xv;
+  View rv;               // addressing of the residual (== xv unless the caller gave it its own view)
   const float* size_in;
   void* out;
   View ov;
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) merge_gather_kernel(MergeArg
   const int n = a.n, na = na_of(n), nb = nb_of(n), r = a.r, nu = na - r, nout = n - r;
   if (o >= nout) return;
   const T* xb = reinterpret_cast<const T*>(a.x) + a.xv.batch_offset(b);
-  const T* rb = RES ? reinterpret_cast<const T*>(a.res) + a.xv.batch_offset(b) : nullptr;
+  const T* rb = RES ? reinterpret_cast<const T*>(a.res) + a.rv.batch_offset(b) : nullptr;
   const int nvec = a.c / E;
   const bool wavg = a.mode == TOME_MODE_WAVG;
 
@@ -314,20 +315,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) merge_gather_kernel(MergeArg
 #pragma unroll
     for (int v = 0; v < NV; ++v) { const int i = v * 32 + lane; if (i < nvec) raw[v] = ld_stream_u4(row + i); }
     if (RES) {
-      const uint4* row2 = reinterpret_cast<const uint4*>(rb + (long long)tok * a.xv.sn);
+      const uint4* row2 = reinterpret_cast<const uint4*>(rb + (long long)tok * a.rv.sn);
 #pragma unroll
       for (int v = 0; v < NV; ++v) { const int i = v * 32 + lane; if (i < nvec) raw2[RES ? v : 0] = ld_stream_u4(row2 + i); }
     }
     if (nsrc > 0) {
       const long long o0 = (long long)(2 * head.y) * a.xv.sn, o1 = (long long)(2 * head.z) * a.xv.sn;
+      const long long q0 = (long long)(2 * head.y) * a.rv.sn, q1 = (long long)(2 * head.z) * a.rv.sn;
       const uint4* s0 = reinterpret_cast<const uint4*>(xb + o0);
       const uint4* s1 = reinterpret_cast<const uint4*>(xb + o1);
       for (int i = lane; i < nvec; i += 32) {
         cp_async16(mine + i, s0 + i);
         if (nsrc > 1) cp_async16(mine + SLOT + i, s1 + i);
         if (RES) {
-          cp_async16(mine + 2 * SLOT + i, reinterpret_cast<const uint4*>(rb + o0) + i);
-          if (nsrc > 1) cp_async16(mine + 3 * SLOT + i, reinterpret_cast<const uint4*>(rb + o1) + i);
+          cp_async16(mine + 2 * SLOT + i, reinterpret_cast<const uint4*>(rb + q0) + i);
+          if (nsrc > 1) cp_async16(mine + 3 * SLOT + i, reinterpret_cast<const uint4*>(rb + q1) + i);
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -404,14 +406,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) merge_gather_kernel(MergeArg
         const int a0 = k0 < 32 ? __shfl_sync(0xffffffffu, k_ai, k0 & 31) : __ldg(bsrc + k0);
         const int a1 = (k0 + 1 < nsrc) ? ((k0 + 1) < 32 ? __shfl_sync(0xffffffffu, k_ai, (k0 + 1) & 31) : __ldg(bsrc + k0 + 1)) : a0;
         const long long o0 = (long long)(2 * a0) * a.xv.sn, o1 = (long long)(2 * a1) * a.xv.sn;
+        const long long q0 = (long long)(2 * a0) * a.rv.sn, q1 = (long long)(2 * a1) * a.rv.sn;
         const uint4* s0 = reinterpret_cast<const uint4*>(xb + o0);
         const uint4* s1 = reinterpret_cast<const uint4*>(xb + o1);
         for (int i = lane; i < nvec; i += 32) {
           cp_async16(mine + i, s0 + i);
           if (k0 + 1 < nsrc) cp_async16(mine + SLOT + i, s1 + i);
           if (RES) {
-            cp_async16(mine + 2 * SLOT + i, reinterpret_cast<const uint4*>(rb + o0) + i);
-            if (k0 + 1 < nsrc) cp_async16(mine + 3 * SLOT + i, reinterpret_cast<const uint4*>(rb + o1) + i);
+            cp_async16(mine + 2 * SLOT + i, reinterpret_cast<const uint4*>(rb + q0) + i);
+            if (k0 + 1 < nsrc) cp_async16(mine + 3 * SLOT + i, reinterpret_cast<const uint4*>(rb + q1) + i);
           }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -637,9 +640,10 @@ static int launch_merge_gather(const MergeArgs& a, cudaStream_t st) {
 int launch_merge(const tome_plan* plan, const void* x, int dtype, int c, const View& xv, const float* size_in,
                  int mode, float thr, void* out, const View& ov, float* size_out, float* logsize_out,
                  cudaStream_t st, const void* ln_w, const void* ln_b, float ln_eps, void* normed, const View* nv,
-                 const void* residual) {
+                 const void* residual, const View* rv) {
   MergeArgs a;
   a.res = residual;
+  a.rv = rv ? *rv : xv;
   a.ln_w = ln_w; a.ln_b = ln_b; a.ln_eps = ln_eps; a.normed = normed; a.nv = nv ? *nv : ov;
   a.bm = plan->bm; a.n = plan->n; a.r = plan->r; a.distill = plan->distill_token; a.c = c; a.mode = mode;
   a.hybrid = (thr == thr) ? 1 : 0; a.thr = thr; a.node_max = plan->node_max;
@@ -648,7 +652,7 @@ int launch_merge(const tome_plan* plan, const void* x, int dtype, int c, const V
   if (dtype == TOME_F32) {
     const bool vec = c % 4 == 0 && aligned16(x) && aligned16(out) && view_vec_ok(xv, 4) && view_vec_ok(ov, 4);
     if (!vec && normed) return set_error(TOME_ERR_ALIGN, "tome_merge_norm: fused LayerNorm needs 16-byte aligned rows (c %% 4 == 0)");
-    if (residual && (!vec || !aligned16(residual))) return set_error(TOME_ERR_ALIGN, "tome_merge: the fused residual needs 16-byte aligned rows (c %% 4 == 0)");
+    if (residual && (!vec || !aligned16(residual) || !view_vec_ok(a.rv, 4))) return set_error(TOME_ERR_ALIGN, "tome_merge: the fused residual needs 16-byte aligned rows (c %% 4 == 0)");
     if (normed && (c > 4 * 32 * 8 || !aligned16(ln_w) || (ln_b && !aligned16(ln_b)) || !aligned16(normed) || !view_vec_ok(a.nv, 4)))
       return set_error(TOME_ERR_UNSUPPORTED, "tome_merge_norm: c=%d too wide or LayerNorm buffers misaligned", c);
     if (!vec) return launch_merge_scalar<float>(a, st);
@@ -657,7 +661,7 @@ int launch_merge(const tome_plan* plan, const void* x, int dtype, int c, const V
   } else if (dtype == TOME_BF16) {
     const bool vec = c % 8 == 0 && aligned16(x) && aligned16(out) && view_vec_ok(xv, 8) && view_vec_ok(ov, 8);
     if (!vec && normed) return set_error(TOME_ERR_ALIGN, "tome_merge_norm: fused LayerNorm needs 16-byte aligned rows (c %% 8 == 0)");
-    if (residual && (!vec || !aligned16(residual))) return set_error(TOME_ERR_ALIGN, "tome_merge: the fused residual needs 16-byte aligned rows (c %% 8 == 0)");
+    if (residual && (!vec || !aligned16(residual) || !view_vec_ok(a.rv, 8))) return set_error(TOME_ERR_ALIGN, "tome_merge: the fused residual needs 16-byte aligned rows (c %% 8 == 0)");
     if (normed && (c > 8 * 32 * 8 || !aligned16(ln_w) || (ln_b && !aligned16(ln_b)) || !aligned16(normed) || !view_vec_ok(a.nv, 8)))
       return set_error(TOME_ERR_UNSUPPORTED, "tome_merge_norm: c=%d too wide or LayerNorm buffers misaligned", c);
     if (!vec) return launch_merge_scalar<__nv_bfloat16>(a, st);
@@ -785,11 +789,147 @@ int launch_add_layernorm(const void* a, const void* b, long long b_rows, int dty
   return set_error(TOME_ERR_DTYPE, "tome_add_layernorm: unsupported dtype %d", dtype);
 }
 
+// ---- caller-side fusion for the divided space-time blocks: add + LayerNorm through (b, p, t) row views --------
+// TimeSformer / Motionformer keep tokens as 'b (p t) m' behind a class token and hop between three row orders per
+// block: '(b p) t' for the temporal attention, '(b t) (1 + p)' for the spatial attention, 'b (1 + p t)' for the
+// residual stream (tome/patch/timesformer.py:38-56, slowfast/models/timesformer.py:115-153).  The reference pays a
+// rearrange / cat copy at every hop plus separate add and LayerNorm passes.  Here row (b, p, t) of each tensor is
+// base + b*sb + p*sp + t*st, so one pass reads a (+ b), writes the sum in the layout of the residual stream and the
+// LayerNorm in the layout of the NEXT consumer.  Arithmetic identical to add_layernorm_kernel.
+struct Rows3 { long long sb, sp, st; };
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) rows3_add_layernorm_kernel(const T* __restrict__ a, Rows3 av, const T* __restrict__ b2, Rows3 bv,
+                                                                 int P, int Tn, long long rows, int c, const T* __restrict__ w,
+                                                                 const T* __restrict__ bias, float eps, T* __restrict__ sum_out,
+                                                                 Rows3 sv, T* __restrict__ normed, Rows3 nv) {
+  constexpr int E = Pack<T>::E;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long long bp = row / Tn;
+  const int t = (int)(row - bp * Tn);
+  const long long bb = bp / P;
+  const int pp = (int)(bp - bb * P);
+  const int nvec = c / E;
+  const uint4* ar = reinterpret_cast<const uint4*>(a + bb * av.sb + pp * av.sp + t * av.st);
+  const uint4* br = b2 ? reinterpret_cast<const uint4*>(b2 + bb * bv.sb + pp * bv.sp + t * bv.st) : nullptr;
+  uint4 va[NV], vb[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int i = v * 32 + lane;
+    if (i < nvec) { va[v] = ld_stream_u4(ar + i); if (br) vb[v] = ld_stream_u4(br + i); }
+  }
+  float2 d[NV][E / 2];
+  float2 s2 = make_float2(0.f, 0.f);
+  uint4* srow = sum_out ? reinterpret_cast<uint4*>(sum_out + bb * sv.sb + pp * sv.sp + t * sv.st) : nullptr;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int i = v * 32 + lane;
+    const bool on = i < nvec;
+    float fa[E], fb[E];
+    if (on) {
+      Pack<T>::unpack(va[v], fa);
+      if (br) {
+        Pack<T>::unpack(vb[v], fb);
+#pragma unroll
+        for (int e = 0; e < E; e += 2) {
+          const float2 s = add2(make_float2(fa[e], fa[e + 1]), make_float2(fb[e], fb[e + 1]));
+          fa[e] = s.x; fa[e + 1] = s.y;
+        }
+        va[v] = Pack<T>::pack(fa);               // the sum rounded to T, as x + y holds it
+        Pack<T>::unpack(va[v], fa);
+      }
+      if (srow) srow[i] = va[v];
+    }
+#pragma unroll
+    for (int e = 0; e < E; e += 2) {
+      d[v][e / 2] = on ? make_float2(fa[e], fa[e + 1]) : make_float2(0.f, 0.f);
+      s2 = add2(s2, d[v][e / 2]);
+    }
+  }
+  if (!normed) return;
+  float sum = s2.x + s2.y;
+#pragma unroll
+  for (int of = 16; of > 0; of >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, of);
+  const float mean = sum / (float)c;
+  const float2 mean2 = make_float2(mean, mean);
+  float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const bool on = v * 32 + lane < nvec;
+#pragma unroll
+    for (int e = 0; e < E / 2; ++e) {
+      d[v][e] = sub2(d[v][e], mean2);
+      if (on) q2 = fma2(d[v][e], d[v][e], q2);
+    }
+  }
+  float sq = q2.x + q2.y;
+#pragma unroll
+  for (int of = 16; of > 0; of >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, of);
+  const float rstd = rsqrtf(sq / (float)c + eps);
+  const float2 rstd2 = make_float2(rstd, rstd);
+  uint4* nrow = reinterpret_cast<uint4*>(normed + bb * nv.sb + pp * nv.sp + t * nv.st);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int i = v * 32 + lane;
+    if (i < nvec) {
+      float f[E], wf[E], bf[E];
+      Pack<T>::unpack(__ldg(reinterpret_cast<const uint4*>(w) + i), wf);
+      if (bias) Pack<T>::unpack(__ldg(reinterpret_cast<const uint4*>(bias) + i), bf);
+#pragma unroll
+      for (int e = 0; e < E; e += 2) {
+        const float2 g2 = mul2(make_float2(wf[e], wf[e + 1]), rstd2);
+        const float2 y = fma2(d[v][e / 2], g2, bias ? make_float2(bf[e], bf[e + 1]) : make_float2(0.f, 0.f));
+        f[e] = y.x; f[e + 1] = y.y;
+      }
+      nrow[i] = Pack<T>::pack(f);
+    }
+  }
+}
+
+template <typename T>
+static int launch_rows3_t(const void* a, const Rows3& av, const void* b, const Rows3& bv, int P, int Tn, long long rows, int c,
+                          const void* w, const void* bias, float eps, void* sum_out, const Rows3& sv, void* normed, const Rows3& nv,
+                          cudaStream_t st) {
+  constexpr int E = Pack<T>::E;
+  const int nvv = (c / E + 31) / 32;
+  const int threads = 64, rows_per_cta = threads / 32;
+  const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
+#define TOME_ROWS3(NV_) rows3_add_layernorm_kernel<T, NV_><<<grid, threads, 0, st>>>((const T*)a, av, (const T*)b, bv, P, Tn, rows, c, (const T*)w, (const T*)bias, eps, (T*)sum_out, sv, (T*)normed, nv)
+  if (nvv <= 1) TOME_ROWS3(1); else if (nvv <= 2) TOME_ROWS3(2); else if (nvv <= 3) TOME_ROWS3(3); else if (nvv <= 4) TOME_ROWS3(4);
+  else if (nvv <= 6) TOME_ROWS3(6); else if (nvv <= 8) TOME_ROWS3(8);
+  else return set_error(TOME_ERR_UNSUPPORTED, "tome_rows_add_layernorm: c=%d too wide", c);
+#undef TOME_ROWS3
+  TOME_LAUNCH_CHECK("rows3_add_layernorm_kernel");
+  return TOME_OK;
+}
+
+static bool rows3_ok(const long long* v, int e) { return v[0] % e == 0 && v[1] % e == 0 && v[2] % e == 0; }
+
+int launch_rows_add_layernorm(const void* a, const long long* av, const void* b, const long long* bv, int dtype, int B, int P, int Tn, int c,
+                              const void* w, const void* bias, float eps, void* sum_out, const long long* sv, void* normed,
+                              const long long* nv, cudaStream_t st) {
+  const int e = dtype == TOME_F32 ? 4 : 8;
+  const long long zero[3] = {0, 0, 0};
+  if (!b) bv = zero;
+  if (!sum_out) sv = zero;
+  if (!normed) nv = zero;
+  if (c % e != 0 || !aligned16(a) || (b && !aligned16(b)) || (normed && (!aligned16(w) || (bias && !aligned16(bias)) || !aligned16(normed))) ||
+      (sum_out && !aligned16(sum_out)) || !rows3_ok(av, e) || !rows3_ok(bv, e) || !rows3_ok(sv, e) || !rows3_ok(nv, e))
+    return set_error(TOME_ERR_ALIGN, "tome_rows_add_layernorm: needs 16-byte aligned rows and c %% %d == 0", e);
+  const Rows3 A{av[0], av[1], av[2]}, Bv{bv[0], bv[1], bv[2]}, S{sv[0], sv[1], sv[2]}, N{nv[0], nv[1], nv[2]};
+  const long long rows = (long long)B * P * Tn;
+  if (dtype == TOME_F32) return launch_rows3_t<float>(a, A, b, Bv, P, Tn, rows, c, w, bias, eps, sum_out, S, normed, N, st);
+  if (dtype == TOME_BF16) return launch_rows3_t<__nv_bfloat16>(a, A, b, Bv, P, Tn, rows, c, w, bias, eps, sum_out, S, normed, N, st);
+  return set_error(TOME_ERR_DTYPE, "tome_rows_add_layernorm: unsupported dtype %d", dtype);
+}
+
 int launch_merge_source(const tome_plan* plan, const float* source, int n0, float thr, float* out, cudaStream_t st) {
   const int nout = plan->n - plan->r;
   if (source) {
     View xv{(long long)plan->n * n0, 0, n0, 1}, ov{(long long)nout * n0, 0, n0, 1};
-    return launch_merge(plan, source, TOME_F32, n0, xv, nullptr, TOME_MODE_AMAX, thr, out, ov, nullptr, nullptr, st, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr);
+    return launch_merge(plan, source, TOME_F32, n0, xv, nullptr, TOME_MODE_AMAX, thr, out, ov, nullptr, nullptr, st, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, nullptr);
   }
   MergeArgs a{};
   a.bm = plan->bm; a.n = plan->n; a.r = plan->r; a.distill = plan->distill_token; a.c = plan->n;

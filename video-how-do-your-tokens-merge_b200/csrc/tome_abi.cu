@@ -59,7 +59,9 @@ void match_tc_describe(int, int, int, long long[5]);
 size_t select_workspace(int bm, int n);
 int launch_select(const tome_plan*, void*, size_t, cudaStream_t);
 int launch_merge(const tome_plan*, const void*, int, int, const View&, const float*, int, float, void*, const View&,
-                 float*, float*, cudaStream_t, const void*, const void*, float, void*, const View*, const void*);
+                 float*, float*, cudaStream_t, const void*, const void*, float, void*, const View*, const void*, const View*);
+int launch_rows_add_layernorm(const void*, const long long*, const void*, const long long*, int, int, int, int, int, const void*, const void*,
+                              float, void*, const long long*, void*, const long long*, cudaStream_t);
 int launch_merge_source(const tome_plan*, const float*, int, float, float*, cudaStream_t);
 int launch_unmerge(const tome_plan*, const void*, int, int, void*, cudaStream_t);
 int launch_add_layernorm(const void*, const void*, long long, int, long long, int, const void*, const void*, float, void*, void*, cudaStream_t);
@@ -76,6 +78,7 @@ size_t match_sets_workspace(int bm, int rows, int ra, int cm);
 int launch_match_sets(const void*, int, int, int, const View&, const int*, long long, int, int, float*, int*, void*, size_t, cudaStream_t);
 int launch_group_reduce(const void*, int, int, int, const View&, const int*, long long, int, int, const int*, int, void*, cudaStream_t);
 int launch_gather_rows(const void*, int, int, int, int, const int*, int, void*, cudaStream_t);
+int launch_attn_short(const void*, const void*, const void*, int, long long, int, int, int, long long, long long, float, void*, cudaStream_t);
 int launch_source_compose(const tome_plan*, const int*, int, int, float, int*, cudaStream_t);
 int launch_source_dense(const int*, int, int, int, float*, cudaStream_t);
 int launch_random_rowmax(void*, long long, int, int, int, int, int, float*, int*, float*, int, cudaStream_t);
@@ -260,7 +263,7 @@ int tome_merge(const tome_plan* plan, const void* x, int32_t dtype, int32_t c, c
   TOME_CHECK_ARG(x != out, "tome_merge: in-place merge is not supported");
   const View xv = make_view(x_view, plan->n, c), ov = make_view(out_view, plan->n - plan->r, c);
   return launch_merge(plan, x, dtype, c, xv, size_in, mode, hybrid_threshold, out, ov, size_out, logsize_out,
-                      (cudaStream_t)stream, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr);
+                      (cudaStream_t)stream, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, nullptr);
 }
 
 int tome_merge_norm(const tome_plan* plan, const void* x, int32_t dtype, int32_t c, const tome_view* x_view,
@@ -275,6 +278,14 @@ int tome_merge_add_norm(const tome_plan* plan, const void* x, const void* residu
                         const tome_view* x_view, const float* size_in, int32_t mode, float hybrid_threshold, void* out,
                         const tome_view* out_view, float* size_out, float* logsize_out, const void* ln_weight,
                         const void* ln_bias, float ln_eps, void* normed_out, const tome_view* normed_view, void* stream) {
+  return tome_merge_add_norm_rv(plan, x, residual, nullptr, dtype, c, x_view, size_in, mode, hybrid_threshold, out, out_view, size_out,
+                                logsize_out, ln_weight, ln_bias, ln_eps, normed_out, normed_view, stream);
+}
+
+int tome_merge_add_norm_rv(const tome_plan* plan, const void* x, const void* residual, const tome_view* residual_view, int32_t dtype,
+                           int32_t c, const tome_view* x_view, const float* size_in, int32_t mode, float hybrid_threshold, void* out,
+                           const tome_view* out_view, float* size_out, float* logsize_out, const void* ln_weight,
+                           const void* ln_bias, float ln_eps, void* normed_out, const tome_view* normed_view, void* stream) {
   int rc = ensure_device_ok();
   if (rc) return rc;
   rc = check_plan(plan, "tome_merge_norm");
@@ -288,8 +299,24 @@ int tome_merge_add_norm(const tome_plan* plan, const void* x, const void* residu
   TOME_CHECK_ARG(x != out && x != normed_out && out != normed_out, "tome_merge_norm: buffers must not alias");
   const View xv = make_view(x_view, plan->n, c), ov = make_view(out_view, plan->n - plan->r, c);
   const View nv = make_view(normed_view, plan->n - plan->r, c);
+  const View rv = residual_view ? make_view(residual_view, plan->n, c) : xv;
   return launch_merge(plan, x, dtype, c, xv, size_in, mode, hybrid_threshold, out, ov, size_out, logsize_out,
-                      (cudaStream_t)stream, ln_weight, ln_bias, ln_eps, normed_out, &nv, residual);
+                      (cudaStream_t)stream, ln_weight, ln_bias, ln_eps, normed_out, &nv, residual, &rv);
+}
+
+int tome_rows_add_layernorm(const void* a, const int64_t* a_strides, const void* b, const int64_t* b_strides, int32_t dtype, int32_t nb,
+                            int32_t np, int32_t nt, int32_t c, const void* ln_weight, const void* ln_bias, float ln_eps, void* sum_out,
+                            const int64_t* sum_strides, void* normed_out, const int64_t* normed_strides, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(a && a_strides && nb > 0 && np > 0 && nt > 0 && c > 0, "tome_rows_add_layernorm: NULL input or empty shape");
+  TOME_CHECK_ARG(sum_out || normed_out, "tome_rows_add_layernorm: nothing to write");
+  TOME_CHECK_ARG((!b || b_strides) && (!sum_out || sum_strides) && (!normed_out || (normed_strides && ln_weight)),
+                 "tome_rows_add_layernorm: a tensor without its strides (or LayerNorm without a weight)");
+  static_assert(sizeof(long long) == sizeof(int64_t), "stride type");
+  return launch_rows_add_layernorm(a, (const long long*)a_strides, b, (const long long*)b_strides, dtype, nb, np, nt, c, ln_weight, ln_bias,
+                                   ln_eps, sum_out, (const long long*)sum_strides, normed_out, (const long long*)normed_strides,
+                                   (cudaStream_t)stream);
 }
 
 int tome_merge_source(const tome_plan* plan, const float* source, int32_t n0, float hybrid_threshold, float* out,
@@ -425,6 +452,15 @@ int tome_random_rowmax(void* philox_state, int64_t clip0, int32_t bm, int32_t na
   if (bm > TOME_MAX_BATCH) return set_error(TOME_ERR_UNSUPPORTED, "tome_random_rowmax: matching batch %d > %d; split the batch", bm, TOME_MAX_BATCH);
   return launch_random_rowmax(philox_state, clip0, bm, na, nb, class_token, distill_token, node_max, node_idx, scores_out, advance,
                               (cudaStream_t)stream);
+}
+
+int tome_attn_short(const void* q, const void* k, const void* v, int32_t dtype, int64_t seqs, int32_t n_tok, int32_t heads, int32_t d,
+                    int64_t seq_stride, int64_t tok_stride, float scale, void* out, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(q && k && v && out && seqs > 0 && n_tok > 0 && heads > 0 && d > 0, "tome_attn_short: NULL pointer or empty shape");
+  TOME_CHECK_ARG(seqs * heads * n_tok < (1LL << 38), "tome_attn_short: too many rows");
+  return launch_attn_short(q, k, v, dtype, seqs, n_tok, heads, d, seq_stride, tok_stride, scale, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

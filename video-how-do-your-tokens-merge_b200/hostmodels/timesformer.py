@@ -42,6 +42,12 @@ class Attention(nn.Module):                             # timesformer.py:57-88
 
     def forward(self, x):
         B, N, C = x.shape
+        if self.with_qkv and x.is_cuda:
+            from tome import _native
+            if _native.attn_short_usable(x, self.num_heads):
+                # the temporal attention's 8-token sequences: one streaming pass over the QKV GEMM's output
+                # (tome_attn_short) instead of a tiled flash kernel at a few percent of HBM speed
+                return self.proj_drop(self.proj(_native.attn_short(self.qkv(x), self.num_heads, self.scale)))
         if self.with_qkv:
             qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
             q, k, v = qkv[0], qkv[1], qkv[2]

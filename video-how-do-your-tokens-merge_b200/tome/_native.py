@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 14
+ABI_VERSION = 16
 
 TOME_F32, TOME_BF16, TOME_U8 = 0, 1, 2
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -31,7 +31,7 @@ EXPORTS = (
     "tome_rowmax", "tome_select_workspace_bytes", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_add_norm", "tome_add_layernorm", "tome_add_rows_layernorm",
     "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_linear_gelu", "tome_unmerge",
     "tome_match_sets_workspace_bytes", "tome_match_sets", "tome_group_reduce", "tome_gather_rows",
-    "tome_source_compose", "tome_source_dense", "tome_random_rowmax",
+    "tome_source_compose", "tome_source_dense", "tome_random_rowmax", "tome_merge_add_norm_rv", "tome_rows_add_layernorm", "tome_attn_short",
 )
 
 
@@ -121,7 +121,15 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.tome_source_compose.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_i32, c_i32, c_f32, c_vp, c_vp]
     lib.tome_source_dense.argtypes = [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]
     lib.tome_random_rowmax.argtypes = [c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp]
-    for name in ("tome_source_compose", "tome_source_dense", "tome_random_rowmax"):
+    lib.tome_merge_add_norm_rv.argtypes = [ctypes.POINTER(TomePlanC), c_vp, c_vp, ctypes.POINTER(TomeViewC), c_i32, c_i32,
+                                           ctypes.POINTER(TomeViewC), c_vp, c_i32, c_f32, c_vp, ctypes.POINTER(TomeViewC), c_vp, c_vp,
+                                           c_vp, c_vp, c_f32, c_vp, ctypes.POINTER(TomeViewC), c_vp]
+    p_i64 = ctypes.POINTER(ctypes.c_int64)
+    lib.tome_rows_add_layernorm.argtypes = [c_vp, p_i64, c_vp, p_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_f32, c_vp, p_i64,
+                                            c_vp, p_i64, c_vp]
+    lib.tome_attn_short.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_i64, c_i64, c_f32, c_vp, c_vp]
+    for name in ("tome_source_compose", "tome_source_dense", "tome_random_rowmax", "tome_merge_add_norm_rv", "tome_rows_add_layernorm",
+                 "tome_attn_short"):
         getattr(lib, name).restype = c_i32
     for name in ("tome_device_check", "tome_match", "tome_match_heads", "tome_rowmax", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_add_norm", "tome_add_layernorm", "tome_add_rows_layernorm",
                  "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_linear_gelu", "tome_unmerge",
@@ -474,14 +482,19 @@ def merge(plan: DevicePlan, x: torch.Tensor, mode: str, size: Optional[torch.Ten
 
 
 def merge_frames(plan: DevicePlan, x: torch.Tensor, frames: int, mode: str, size: Optional[torch.Tensor] = None,
-                 hybrid_threshold: Optional[float] = None, norm=None):
+                 hybrid_threshold: Optional[float] = None, norm=None, residual: Optional[torch.Tensor] = None,
+                 cls: Optional[torch.Tensor] = None):
     """Kernel 3 on TimeSformer / Motionformer token layout, without the rearrange copies.
 
     x is (B, 1 + P*T, C): a class token followed by tokens ordered '(p t)'.  The plan's matching batch
     is (b t) with P tokens each -- the reference reaches that with
     ``rearrange(x[:, 1:], 'b (p t) m -> (b t) p m')`` before and ``'(b t) p m -> b (p t) m'`` + ``cat`` with
     the class token after (tome/patch/timesformer.py:88-107, motionformer.py:150-168).  Here both are
-    addressing (tome_view with inner = T): returns (out (B, 1 + P'*T, C), size' (B*T, P'), log size')."""
+    addressing (tome_view with inner = T): returns (out (B, 1 + P'*T, C), size' (B*T, P'), log size').
+
+    ``residual`` (B*T, 1 + P, C): the spatial attention's output in ITS layout ('(b t) (1 + p)'); the patch tokens
+    merged are x + residual, added inside the kernel (the reference: rearrange, cat, add -- timesformer.py:46-48).
+    ``cls`` (B, C): the class-token row of the output (default: x's)."""
     lib = load_library()
     _require_cuda(x, "x")
     T = int(frames)
@@ -498,7 +511,7 @@ def merge_frames(plan: DevicePlan, x: torch.Tensor, frames: int, mode: str, size
     thr = float("nan") if hybrid_threshold is None else float(hybrid_threshold)
     with torch.cuda.device(x.device):
         out = torch.empty(B, 1 + Pn * T, C, dtype=x.dtype, device=x.device)
-        out[:, 0] = x[:, 0]
+        out[:, 0] = x[:, 0] if cls is None else cls
         size_out = torch.empty(B * T, Pn, dtype=torch.float32, device=x.device)
         logsize_out = torch.empty(B * T, Pn, dtype=torch.float32, device=x.device)
         sp = None
@@ -507,19 +520,62 @@ def merge_frames(plan: DevicePlan, x: torch.Tensor, frames: int, mode: str, size
             sp = size.data_ptr()
         xv = TomeViewC(x.stride(0), x.stride(1), T * x.stride(1), T)
         ov = TomeViewC(out.stride(0), out.stride(1), T * out.stride(1), T)
-        if norm is None:
+        if norm is None and residual is None:
             _check(lib.tome_merge(plan.c_ptr(), x[:, 1:].data_ptr(), _dtype_code(x), C, ctypes.byref(xv), sp, m, thr,
                                   out[:, 1:].data_ptr(), ctypes.byref(ov), size_out.data_ptr(), logsize_out.data_ptr(),
                                   _stream(x)), lib)
             return out, size_out, logsize_out
-        wp, bp, eps = _norm_args(norm, x)
-        normed = torch.empty_like(out)
-        normed[:, 0] = torch.nn.functional.layer_norm(out[:, 0], (C,), norm[0], norm[1], eps)     # class token row
-        nv = TomeViewC(normed.stride(0), normed.stride(1), T * normed.stride(1), T)
-        _check(lib.tome_merge_norm(plan.c_ptr(), x[:, 1:].data_ptr(), _dtype_code(x), C, ctypes.byref(xv), sp, m, thr,
-                                   out[:, 1:].data_ptr(), ctypes.byref(ov), size_out.data_ptr(), logsize_out.data_ptr(),
-                                   wp, bp, eps, normed[:, 1:].data_ptr(), ctypes.byref(nv), _stream(x)), lib)
-    return out, size_out, logsize_out, normed
+        rp, rv = None, None
+        if residual is not None:
+            if tuple(residual.shape) != (B * T, 1 + P, C) or residual.dtype != x.dtype or residual.device != x.device:
+                raise RuntimeError(f"tome_b200: merge_frames residual must be ({B * T}, {1 + P}, {C}) of x's dtype; got {tuple(residual.shape)}")
+            if residual.stride(2) != 1:
+                residual = residual.contiguous()
+            rp = residual[:, 1:].data_ptr()
+            rv = ctypes.byref(TomeViewC(residual.stride(0), 0, residual.stride(1), 1))     # batch (b t), tokens p
+        wp = bp = npz = None
+        eps, normed, nv = 0.0, None, None
+        if norm is not None:
+            wp, bp, eps = _norm_args(norm, x)
+            normed = torch.empty_like(out)
+            normed[:, 0] = torch.nn.functional.layer_norm(out[:, 0], (C,), norm[0], norm[1], eps)     # class token row
+            nv = ctypes.byref(TomeViewC(normed.stride(0), normed.stride(1), T * normed.stride(1), T))
+            npz = normed[:, 1:].data_ptr()
+        _check(lib.tome_merge_add_norm_rv(plan.c_ptr(), x[:, 1:].data_ptr(), rp, rv, _dtype_code(x), C, ctypes.byref(xv), sp, m,
+                                          thr, out[:, 1:].data_ptr(), ctypes.byref(ov), size_out.data_ptr(),
+                                          logsize_out.data_ptr(), wp, bp, eps, npz, nv, _stream(x)), lib)
+    return (out, size_out, logsize_out) + ((normed,) if norm is not None else ())
+
+
+def _strides3(t: torch.Tensor):
+    return (ctypes.c_int64 * 3)(*[int(v) for v in t.stride()[:3]])
+
+
+def rows_add_layernorm(a: torch.Tensor, b: Optional[torch.Tensor], norm, sum_out: Optional[torch.Tensor],
+                       normed_out: Optional[torch.Tensor]):
+    """sum_out = a + b, normed_out = LayerNorm(sum) through (B, P, T, C) VIEWS (include/tome_b200.h:
+    tome_rows_add_layernorm): every argument is a 4-d view with unit channel stride -- ``x[:, 1:].unflatten(1, (P, T))``,
+    a permuted '(b t) (1 + p)' buffer ... -- so the row-order hops of the divided space-time blocks cost nothing.
+    ``b``, ``sum_out`` or ``normed_out`` may be None."""
+    lib = load_library()
+    _require_cuda(a, "a")
+    B, P, T, C = a.shape
+    for t in (b, sum_out, normed_out):
+        if t is not None and (tuple(t.shape) != (B, P, T, C) or t.stride(3) != 1 or t.dtype != a.dtype or t.device != a.device):
+            raise RuntimeError("tome_b200: rows_add_layernorm needs (B, P, T, C) views of one dtype with unit channel stride")
+    if a.stride(3) != 1:
+        raise RuntimeError("tome_b200: rows_add_layernorm needs unit channel stride")
+    wp = bp = None
+    eps = 0.0
+    if normed_out is not None:
+        wp, bp, eps = _norm_args(norm, a)
+    with torch.cuda.device(a.device):
+        _check(lib.tome_rows_add_layernorm(a.data_ptr(), _strides3(a), None if b is None else b.data_ptr(),
+                                           None if b is None else _strides3(b), _dtype_code(a), B, P, T, C, wp, bp, eps,
+                                           None if sum_out is None else sum_out.data_ptr(),
+                                           None if sum_out is None else _strides3(sum_out),
+                                           None if normed_out is None else normed_out.data_ptr(),
+                                           None if normed_out is None else _strides3(normed_out), _stream(a)), lib)
 
 
 def add_layernorm(a: torch.Tensor, b: torch.Tensor, norm):
@@ -566,6 +622,30 @@ def linear_gelu(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tens
         _check(lib.tome_linear_gelu(x2.data_ptr(), weight.data_ptr(), None if bias is None else bias.data_ptr(), m, n, k,
                                     x2.stride(0), _ACTS[gelu], out.data_ptr(), _stream(x)), lib)
     return out.reshape(*x.shape[:-1], n)
+
+
+def attn_short_usable(x: torch.Tensor, heads: int) -> bool:
+    """tome_attn_short serves this (seqs, n_tok, C) attention input: CUDA inference, <= 32 tokens, head dim 64."""
+    return (x.is_cuda and not torch.is_grad_enabled() and x.dim() == 3 and x.shape[1] <= 32 and x.shape[2] == 64 * heads
+            and x.dtype in (torch.float32, torch.bfloat16))
+
+
+def attn_short(qkv: torch.Tensor, heads: int, scale: float) -> torch.Tensor:
+    """softmax(scale q k^T) v per sequence and head, straight from the QKV GEMM's output (seqs, n_tok, 3 * heads * 64)
+    (channel order (3, heads, d), as ``qkv.reshape(B, N, 3, H, d)`` reads it); returns (seqs, n_tok, heads * 64)."""
+    lib = load_library()
+    _require_cuda(qkv, "qkv")
+    qkv = qkv.contiguous()
+    seqs, tn, c3 = qkv.shape
+    c = c3 // 3
+    d = c // heads
+    esz = qkv.element_size()
+    with torch.cuda.device(qkv.device):
+        out = torch.empty(seqs, tn, c, dtype=qkv.dtype, device=qkv.device)
+        base = qkv.data_ptr()
+        _check(lib.tome_attn_short(base, base + c * esz, base + 2 * c * esz, _dtype_code(qkv), seqs, tn, heads, d, tn * c3, c3,
+                                   float(scale), out.data_ptr(), _stream(qkv)), lib)
+    return out
 
 
 def patchify(x: torch.Tensor, tubelet: int, ph: int, pw: int, out_dtype: torch.dtype) -> torch.Tensor:

@@ -208,10 +208,12 @@ class Merge(_PlanCallable):
         """merge_source on the compact form: ``source`` is a SourceMap or None (identity)."""
         return _native.source_compose(self.plan, source, False, self.threshold)
 
-    def wavg_frames(self, x, frames, size=None, norm=None):
+    def wavg_frames(self, x, frames, size=None, norm=None, residual=None, cls=None):
         """merge_wavg on a (B, 1 + P*T, C) class-token + '(p t)' tensor whose matching batch is (b t):
         the TimeSformer / Motionformer case, rearranges folded into addressing.
-        Returns (x' (B, 1 + P'*T, C), size' (B*T, P', 1), log size' (B*T, P', 1))."""
+        Returns (x' (B, 1 + P'*T, C), size' (B*T, P', 1), log size' (B*T, P', 1)).
+        ``residual`` ((B*T, 1 + P, C), the spatial attention's output in its own layout) is added to the patch
+        tokens inside the kernel and ``cls`` (B, C) becomes the class row (inference path only)."""
         if _needs_grad(x):                         # training: the reference's rearranges, differentiable merge
             B, L, C = x.shape
             T = int(frames)
@@ -222,7 +224,8 @@ class Merge(_PlanCallable):
             y = torch.cat((x[:, :1], out.reshape(B, T, Pn, C).transpose(1, 2).reshape(B, Pn * T, C)), 1)
             extra = (torch.nn.functional.layer_norm(y, (C,), norm[0], norm[1], norm[2]),) if norm is not None else ()
             return (y, s, ls) + extra
-        res = _native.merge_frames(self.plan, x, frames, "wavg", size=size, hybrid_threshold=self.threshold, norm=norm)
+        res = _native.merge_frames(self.plan, x, frames, "wavg", size=size, hybrid_threshold=self.threshold, norm=norm,
+                                   residual=residual, cls=cls)
         out, s, ls = res[:3]
         return (out, s[..., None], ls[..., None]) + tuple(res[3:])
 
@@ -262,7 +265,7 @@ class Drop(_PlanCallable):
         """The drop closure applied to the compact source form (dropped tokens get group -1)."""
         return _native.source_compose(self.plan, source, True, None)
 
-    def frames(self, x, frames):
+    def frames(self, x, frames, residual=None, cls=None):
         """drop on the (B, 1 + P*T, C) layout (see Merge.wavg_frames)."""
         if _needs_grad(x):
             B, L, C = x.shape
@@ -271,7 +274,7 @@ class Drop(_PlanCallable):
             out = self(x[:, 1:].reshape(B, P, T, C).transpose(1, 2).reshape(B * T, P, C))
             Pn = out.size(1)
             return torch.cat((x[:, :1], out.reshape(B, T, Pn, C).transpose(1, 2).reshape(B, Pn * T, C)), 1)
-        return _native.merge_frames(self.plan, x, frames, "drop")[0]
+        return _native.merge_frames(self.plan, x, frames, "drop", residual=residual, cls=cls)[0]
 
 
 def bipartite_soft_matching(

@@ -21,6 +21,38 @@ from tome.patch.videomae import _normed_or, _swap, fusable_norm, lazy_head_mean
 from tome.utils import parse_r
 
 
+def _fused_block_ok(block, x):
+    """The divided space-time block can run on the view-aware kernels: CUDA inference, fusable LayerNorms."""
+    return (x.is_cuda and not torch.is_grad_enabled() and not block.training and x.is_contiguous()
+            and all(fusable_norm(getattr(block, n, None), x) is not None for n in ("temporal_norm1", "norm1", "norm2"))
+            and isinstance(getattr(block, "temporal_fc", None), torch.nn.Linear))
+
+
+def _ln(norm):
+    return norm.weight, norm.bias, norm.eps
+
+
+def _apply_spatial_residual(x, res_s, cls, B, T, P):
+    """x (B, 1 + P*T, C) with a stale class row; res_s (B*T, 1 + P, C): the reference's rearrange + cat + add
+    (timesformer.py:46-48) for the paths the merge kernel does not take (r == 0, foreign merge callables)."""
+    C = x.size(2)
+    out = torch.empty_like(x)
+    out[:, 0] = cls
+    out[:, 1:] = x[:, 1:] + res_s[:, 1:, :].reshape(B, T, P, C).transpose(1, 2).reshape(B, P * T, C)
+    return out
+
+
+def link_temporal(blocks, info):
+    """id(block) -> temporal_norm1 of the block that follows it (the LayerNorm its closing add can feed)."""
+    chain, seen = {}, set()
+    blocks = list(blocks)
+    for cur, nxt in zip(blocks[:-1], blocks[1:]):
+        chain[id(cur)] = None if id(cur) in seen else getattr(nxt, "temporal_norm1", None)
+        seen.add(id(cur))
+    info["next_temporal_norm1"] = chain
+    info["normed_t"] = None
+
+
 class ToMeBlockMixin:
     """timesformer.py:12-57."""
 
@@ -33,6 +65,9 @@ class ToMeBlockMixin:
         if self.attention_type in ['space_only', 'joint_space_time']:
             x = x + self.drop_path(self.attn(self.norm1(x))[0])
             return x + self.drop_path(self.mlp(self.norm2(x)))
+        if _fused_block_ok(self, x):
+            return self._forward_fused(x, B, T, P, C, info, attn_size, attn_bias)
+        info["normed_t"] = None
         # temporal attention (un-patched): 'b (p t) m -> (b p) t m'
         xt = x[:, 1:, :].reshape(B * P, T, C)
         res_t = self.drop_path(self.temporal_attn(self.temporal_norm1(xt))).reshape(B, P * T, C)
@@ -48,6 +83,44 @@ class ToMeBlockMixin:
         x = torch.cat((init_cls, xt), 1) + torch.cat((cls, res), 1)
         x = self.reduction_function(metric, x, info, B, T, P, norm=self.norm2)
         return x + self.drop_path(self.mlp(_normed_or(self.norm2, x, info)))
+
+    def _forward_fused(self, x, B, T, P, C, info, attn_size, attn_bias):
+        """The same block with every rearrange / cat / add / LayerNorm hop between the three row orders done as
+        addressing inside tome_rows_add_layernorm and the merge kernel: per block the residual
+        stream is read and written four times instead of ~fourteen."""
+        from tome import _native
+        x4 = x[:, 1:].unflatten(1, (P, T))                                   # (B, P, T, C) view of the patch tokens
+        pre = info.pop("normed_t", None)
+        if pre is not None and pre[0] is x and pre[1] is self.temporal_norm1:
+            nt = pre[2]                                                      # made by the previous block's closing add
+        else:
+            nt = torch.empty(B, P, T, C, dtype=x.dtype, device=x.device)     # '(b p) t' rows for the temporal attention
+            _native.rows_add_layernorm(x4, None, _ln(self.temporal_norm1), None, nt)
+        res_t = self.temporal_attn(nt.view(B * P, T, C))
+        tf = self.temporal_fc(res_t).view(B, P, T, C)
+        # xt = x + temporal_fc(...) written into the residual stream's layout, norm1(xt) into '(b t) (1 + p)' rows
+        xfull = torch.empty_like(x)                                          # class row filled by the merge (or below)
+        ns = torch.empty(B * T, 1 + P, C, dtype=x.dtype, device=x.device)
+        ns4 = ns.view(B, T, 1 + P, C)
+        _native.rows_add_layernorm(x4, tf, _ln(self.norm1), xfull[:, 1:].unflatten(1, (P, T)), ns4[:, :, 1:].permute(0, 2, 1, 3))
+        init_cls = x[:, 0]
+        ns4[:, :, 0] = self.norm1(init_cls)[:, None]                         # class token replicated per frame
+        res_s, metric = self.attn(ns, attn_size, attn_bias)
+        cls = init_cls + res_s.view(B, T, 1 + P, C)[:, :, 0].mean(1)         # class token averaged over frames
+        x = self.reduction_function(metric, xfull, info, B, T, P, norm=self.norm2, residual=res_s, cls=cls)
+        y = self.mlp(_normed_or(self.norm2, x, info))
+        # x + mlp(...) and the NEXT block's temporal_norm1 in one pass
+        nxt = (info.get("next_temporal_norm1") or {}).get(id(self))
+        if nxt is None or fusable_norm(nxt, x) is None:
+            return x + y
+        Pn = (x.size(1) - 1) // T
+        s = torch.empty_like(x)
+        nt = torch.empty(B, Pn, T, C, dtype=x.dtype, device=x.device)
+        _native.rows_add_layernorm(x[:, 1:].unflatten(1, (Pn, T)), y[:, 1:].unflatten(1, (Pn, T)), _ln(nxt),
+                                   s[:, 1:].unflatten(1, (Pn, T)), nt)
+        s[:, 0] = x[:, 0] + y[:, 0]
+        info["normed_t"] = (s, nxt, nt)
+        return s
 
 
 class ToMeAttentionMixin:
@@ -108,8 +181,9 @@ def _merge_frames_generic(merge, x, info, B, T, P):
     return _frames_back(cls, merged_x, B, T)
 
 
-def timesformer_merge(metric, x, _tome_info, B, T, num_spatial_tokens, norm=None):
-    """timesformer.py:85-109."""
+def timesformer_merge(metric, x, _tome_info, B, T, num_spatial_tokens, norm=None, residual=None, cls=None):
+    """timesformer.py:85-109.  ``residual`` / ``cls``: the pending spatial-attention add (timesformer.py:46-48),
+    taken inside the merge kernel when it runs."""
     _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
     if r > 0:
@@ -120,30 +194,38 @@ def timesformer_merge(metric, x, _tome_info, B, T, num_spatial_tokens, norm=None
             if _tome_info["trace_source"]:
                 _tome_info["source"] = trace_source(merge, None, _tome_info["source"])
             fn = fusable_norm(norm, x) if norm is not None else None
-            res = merge.wavg_frames(x, T, _tome_info["size"], norm=fn)
+            res = merge.wavg_frames(x, T, _tome_info["size"], norm=fn, residual=residual, cls=cls)
             x, _tome_info["size"], _tome_info["log_size"] = res[0], res[1], res[2]
             _tome_info["normed"] = res[3] if fn is not None else None
         else:
+            if residual is not None:
+                x = _apply_spatial_residual(x, residual, cls, B, T, num_spatial_tokens)
             x = _merge_frames_generic(merge, x, _tome_info, B, T, num_spatial_tokens)
         if _tome_info['verbose']:
             print(f'Merged {pre_merge} to {(x.size(1) - 1) // T} tokens')
+    elif residual is not None:
+        x = _apply_spatial_residual(x, residual, cls, B, T, num_spatial_tokens)
     return x
 
 
-def timesformer_drop(metric, x, _tome_info, B, T, num_spatial_tokens, norm=None):
+def timesformer_drop(metric, x, _tome_info, B, T, num_spatial_tokens, norm=None, residual=None, cls=None):
     """timesformer.py:112-140."""
     _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
+    if r <= 0 and residual is not None:
+        return _apply_spatial_residual(x, residual, cls, B, T, num_spatial_tokens)
     if r > 0:
         drop = bipartite_soft_matching_drop(metric, r, _tome_info["class_token"], _tome_info["distill_token"],
                                             _tome_info["mode"])
+        if residual is not None and not isinstance(drop, Drop):
+            x, residual = _apply_spatial_residual(x, residual, cls, B, T, num_spatial_tokens), None
         if isinstance(drop, tuple):
             return x
         if _tome_info["trace_source"]:
             _tome_info["source"] = trace_source(drop, x.new_empty((B * T, num_spatial_tokens, 0)), _tome_info["source"], drop=True)
         pre_drop = num_spatial_tokens
         if isinstance(drop, Drop):
-            x = drop.frames(x, T)
+            x = drop.frames(x, T, residual=residual, cls=cls)
         else:
             x = _frames_back(x[:, 0:1, :], drop(_frames_view(x, B, T, num_spatial_tokens)), B, T)
         Pn = (x.size(1) - 1) // T
@@ -154,7 +236,7 @@ def timesformer_drop(metric, x, _tome_info, B, T, num_spatial_tokens, norm=None)
     return x
 
 
-def timesformer_hybrid(metric, x, _tome_info, B, T, num_spatial_tokens, norm=None):
+def timesformer_hybrid(metric, x, _tome_info, B, T, num_spatial_tokens, norm=None, residual=None, cls=None):
     """timesformer.py:143-167."""
     _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
@@ -166,13 +248,17 @@ def timesformer_hybrid(metric, x, _tome_info, B, T, num_spatial_tokens, norm=Non
             if _tome_info["trace_source"]:
                 _tome_info["source"] = trace_source(merge, None, _tome_info["source"])
             fn = fusable_norm(norm, x) if norm is not None else None
-            res = merge.wavg_frames(x, T, _tome_info["size"], norm=fn)
+            res = merge.wavg_frames(x, T, _tome_info["size"], norm=fn, residual=residual, cls=cls)
             x, _tome_info["size"], _tome_info["log_size"] = res[0], res[1], res[2]
             _tome_info["normed"] = res[3] if fn is not None else None
         else:
+            if residual is not None:
+                x = _apply_spatial_residual(x, residual, cls, B, T, num_spatial_tokens)
             x = _merge_frames_generic(merge, x, _tome_info, B, T, num_spatial_tokens)
         if _tome_info['verbose']:
             print(f'Merged {pre_merge} to {(x.size(1) - 1) // T} tokens')
+    elif residual is not None:
+        x = _apply_spatial_residual(x, residual, cls, B, T, num_spatial_tokens)
     return x
 
 
@@ -194,6 +280,7 @@ def make_tome_class(transformer_class):
             self._tome_info["log_size"] = None
             self._tome_info["normed"] = None
             self._tome_info["source"] = None
+            link_temporal(self.model.blocks, self._tome_info)
             out = super().forward(*args, **kwdargs)
             finish_source(self._tome_info)          # compact source map -> the reference's dense matrix, once
             return out
