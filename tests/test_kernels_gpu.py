@@ -448,17 +448,20 @@ def test_fused_residual_equals_merging_the_sum(native, name, dtype):
 
 
 @pytest.mark.timeout(180)
-@pytest.mark.parametrize("path", ["auto", "chain", "one_launch", "exact_simt"])
+@pytest.mark.parametrize("path", ["auto", "chain", "chain_two_select", "one_launch", "exact_simt"])
 @pytest.mark.parametrize("case", ALL_ACTIVE, ids=lambda c: c["name"])
 def test_plan_build_bit_exact_vs_oracle(native, case, path, monkeypatch):
     """tome_plan_build (kernels 1 + 2 in one ABI call) gives the oracle's node_max / node_idx / src / unm / dst
-    bits: as dispatched by default, as the four-launch tcgen05 chain, as the one-launch cluster kernel (forced for every
-    shape it supports) and with the exact SIMT matching."""
+    bits: as dispatched by default, as the three-launch tcgen05 chain (normalise, match, one-launch select on the packed
+    keys), as the same chain with the rank + finish pair, as the one-launch cluster kernel (forced for every shape it
+    supports) and with the exact SIMT matching."""
     metric, _, _ = util.case_arrays(case)
     cls, dis = bool(case.get("cls")), bool(case.get("distill"))
     plan = _oracle_plan(case, metric)
-    if path in ("chain", "one_launch"):
-        monkeypatch.setenv("TOME_PLAN_CLUSTER", "0" if path == "chain" else "1")
+    if path in ("chain", "chain_two_select", "one_launch"):
+        monkeypatch.setenv("TOME_PLAN_CLUSTER", "1" if path == "one_launch" else "0")
+    if path == "chain_two_select":
+        monkeypatch.setenv("TOME_SELECT_TWO", "1")
     dp = native.plan_build(_dev(metric), plan.r, cls, dis, algo=1 if path == "exact_simt" else 0)
     np.testing.assert_array_equal(dp.node_idx.cpu().numpy(), plan.node_idx)
     np.testing.assert_array_equal(dp.node_max.cpu().numpy().view(np.uint32), plan.node_max.view(np.uint32))
@@ -466,6 +469,7 @@ def test_plan_build_bit_exact_vs_oracle(native, case, path, monkeypatch):
     np.testing.assert_array_equal(dp.unm_idx.cpu().numpy(), plan.unm_idx)
     np.testing.assert_array_equal(dp.dst_idx.cpu().numpy(), plan.dst_idx)
     # the CSR the merge kernel gathers through is the same whichever select built it
+    monkeypatch.setenv("TOME_SELECT_TWO", "0" if path == "chain_two_select" else "1")
     ref = native.select(_dev(plan.node_max), _dev(plan.node_idx), case["n"], plan.r, cls, dis)
     for name in ("a_map", "b_off", "b_src", "b_head"):
         assert torch.equal(getattr(dp, name), getattr(ref, name)), name
@@ -1053,4 +1057,5 @@ def test_attn_short_matches_softmax_attention(native, dtype, tn):
     want = want.transpose(1, 2).reshape(seqs, tn, H * d)
     tol = 1e-2 if dtype == torch.bfloat16 else 2e-6
     torch.testing.assert_close(out.double(), want, rtol=tol, atol=tol)
-    assert native.attn_short_usable(qkv[..., :H * d], H) and not native.attn_short_usable(torch.zeros(2, 33, H * d, device="cuda"), H)
+    with torch.no_grad():
+        assert native.attn_short_usable(qkv[..., :H * d], H) and not native.attn_short_usable(torch.zeros(2, 33, H * d, device="cuda"), H)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Time tome_plan_build (kernels 1 + 2) per path at the shapes of the four models: the multi-launch chain, the chain with
-the one-launch cluster select, and the one-launch cluster plan kernel.  CUDA-graph replay, rotating inputs.
+the one-launch select (threshold published through global memory), and the one-launch cluster plan kernel.  CUDA-graph replay, rotating inputs.
     python tools/plan_paths.py > profiles/r02_plan_paths.txt"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -18,9 +18,9 @@ SHAPES = [  # label, bm, n, r, class token
     ("TimeSformer layer 6", 64, 88, 18, False),
     ("TimeSformer layer 10", 64, 17, 8, False),
 ]
-PATHS = [("chain (split + match_tc + rank + finish)", dict(TOME_PLAN_CLUSTER="0", TOME_SELECT_CLUSTER="0")),
-         ("chain with one-launch select", dict(TOME_PLAN_CLUSTER="0", TOME_SELECT_CLUSTER="1")),
-         ("one-launch plan kernel", dict(TOME_PLAN_CLUSTER="1", TOME_SELECT_CLUSTER="0"))]
+PATHS = [("chain (split + match_tc + rank + finish)", dict(TOME_PLAN_CLUSTER="0", TOME_SELECT_TWO="1")),
+         ("chain with one-launch select (split + match_tc + select_one)", dict(TOME_PLAN_CLUSTER="0", TOME_SELECT_TWO="0")),
+         ("one-launch plan kernel", dict(TOME_PLAN_CLUSTER="1", TOME_SELECT_TWO="0"))]
 dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(0)
 for label, bm, n, r, cls in SHAPES:

@@ -570,14 +570,14 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   }
   if (threadIdx.x == 64) TC_TRACE(8);
   tc_fence_before();
-  if (p.fused_refine) __threadfence();
+  if (p.fused_refine && p.node_max) __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) TC_TRACE(9);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
-  if (p.fused_refine) {
+  if (p.fused_refine && p.node_max) {      // node_max == NULL: the selection kernel consumes the packed keys directly
     // last column tile of this (batch, row strip) turns the packed keys into node_max / node_idx
     if (threadIdx.x == 0) {
       const int strip = b * gridDim.y + it;
@@ -708,7 +708,7 @@ static TcLayout tc_layout(int bm, int n, const TcParams& p) {
   l.tile_cand = o; o += align256(rows * 4 * KCAND);
   l.keys = o;      o += align256((size_t)bm * p.na * 8);
   l.approx = o;    o += align256((size_t)bm * p.na * 4);
-  l.strips = o;    o += align256(strips * 4);
+  l.strips = o;    o += align256((size_t)bm * 8 + strips * 4);     // [bm x u64 select flags][strip arrival counters]
   l.total = o;
   return l;
 }
@@ -728,6 +728,12 @@ void match_tc_describe(int bm, int n, int cm, long long out[5]) {
   out[0] = p.n_ct; out[1] = p.BN; out[2] = (long long)l.tile_max; out[3] = (long long)l.tile_cnt; out[4] = p.fused_refine;
 }
 
+bool match_tc_fused_refine(int bm, int n, int cm) {
+  TcParams p;
+  tc_geometry(bm, n, cm, p);
+  return p.fused_refine != 0;
+}
+
 bool match_tc_supported(int dtype, int bm, int n, int cm, const View& v, const void* metric) {
   if (dtype != TOME_F32 && dtype != TOME_BF16) return false;
   if (cm % 8 != 0 || cm < 8 || cm > 4096) return false;          // TMA: 16-byte row pitch of the bf16 planes
@@ -740,7 +746,7 @@ bool match_tc_supported(int dtype, int bm, int n, int cm, const View& v, const v
 
 int launch_match_tc(const void* metric, int dtype, int bm, int n, int cm, const View& v, int cls, int distill,
                     float* node_max, int* node_idx, void* ws, size_t ws_bytes, cudaStream_t st, int heads,
-                    long long stride_h) {
+                    long long stride_h, unsigned long long** packed_out, unsigned long long** flags_out) {
   if (ws_bytes < match_tc_workspace(bm, n, cm))
     return set_error(TOME_ERR_WORKSPACE, "tome_match: workspace %zu < %zu bytes", ws_bytes, match_tc_workspace(bm, n, cm));
   if (((uintptr_t)ws & 255) != 0) return set_error(TOME_ERR_ALIGN, "tome_match: workspace must be 256-byte aligned");
@@ -761,7 +767,11 @@ int launch_match_tc(const void* metric, int dtype, int bm, int n, int cm, const 
   p.tile_cand = (int*)(w + l.tile_cand);
   p.keys = (unsigned long long*)(w + l.keys);
   p.approx = (unsigned int*)(w + l.approx);
-  p.strip_count = (int*)(w + l.strips);
+  int* zero_base = (int*)(w + l.strips);                  // flags + counters, zeroed by the normalisation kernel
+  p.strip_count = zero_base + 2 * bm;
+  const int zero_ints = 2 * bm + bm * n_rt;
+  if (packed_out) *packed_out = p.keys;
+  if (flags_out) *flags_out = (unsigned long long*)zero_base;
 
   const long long vec = dtype == TOME_F32 ? 4 : 8;            // 16-byte loads of eight channels
   const bool wide = cm <= 64 && !((uintptr_t)metric & 15) && v.sbo % vec == 0 && v.sbi % vec == 0 && v.sn % vec == 0 &&
@@ -769,16 +779,16 @@ int launch_match_tc(const void* metric, int dtype, int bm, int n, int cm, const 
   if (wide) {
     const int blocks8 = (int)(((long long)bm * n * 8 + 255) / 256);
     if (dtype == TOME_F32)
-      split_rows8_kernel<float><<<blocks8, 256, 0, st>>>((const float*)metric, v, heads, stride_h, bm, n, cm, hm, mhat, p.keys, p.approx, p.strip_count, bm * n_rt);
+      split_rows8_kernel<float><<<blocks8, 256, 0, st>>>((const float*)metric, v, heads, stride_h, bm, n, cm, hm, mhat, p.keys, p.approx, zero_base, zero_ints);
     else
-      split_rows8_kernel<__nv_bfloat16><<<blocks8, 256, 0, st>>>((const __nv_bfloat16*)metric, v, heads, stride_h, bm, n, cm, hm, mhat, p.keys, p.approx, p.strip_count, bm * n_rt);
+      split_rows8_kernel<__nv_bfloat16><<<blocks8, 256, 0, st>>>((const __nv_bfloat16*)metric, v, heads, stride_h, bm, n, cm, hm, mhat, p.keys, p.approx, zero_base, zero_ints);
     TOME_LAUNCH_CHECK("split_rows8_kernel");
   } else {
     const int blocks = (int)(((long long)bm * n * 32 + 255) / 256);
     if (dtype == TOME_F32)
-      split_rows_kernel<float><<<blocks, 256, 0, st>>>((const float*)metric, v, heads, stride_h, bm, n, cm, hm, mhat, p.keys, p.approx, p.strip_count, bm * n_rt);
+      split_rows_kernel<float><<<blocks, 256, 0, st>>>((const float*)metric, v, heads, stride_h, bm, n, cm, hm, mhat, p.keys, p.approx, zero_base, zero_ints);
     else
-      split_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)metric, v, heads, stride_h, bm, n, cm, hm, mhat, p.keys, p.approx, p.strip_count, bm * n_rt);
+      split_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)metric, v, heads, stride_h, bm, n, cm, hm, mhat, p.keys, p.approx, zero_base, zero_ints);
     TOME_LAUNCH_CHECK("split_rows_kernel");
   }
 

@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -54,7 +55,11 @@ int launch_match_exact(const void*, int, int, int, int, const View&, int, int, f
 int launch_rowmax(const float*, int, int, int, int, int, float*, int*, cudaStream_t);
 size_t match_tc_workspace(int bm, int n, int cm);
 bool match_tc_supported(int dtype, int bm, int n, int cm, const View& v, const void* metric);
-int launch_match_tc(const void*, int, int, int, int, const View&, int, int, float*, int*, void*, size_t, cudaStream_t, int, long long);
+int launch_match_tc(const void*, int, int, int, int, const View&, int, int, float*, int*, void*, size_t, cudaStream_t, int, long long,
+                    unsigned long long**, unsigned long long**);
+int launch_select_one(const tome_plan*, const unsigned long long*, unsigned long long*, cudaStream_t);
+bool match_tc_fused_refine(int bm, int n, int cm);
+bool select_two_launches();
 void match_tc_describe(int, int, int, long long[5]);
 size_t select_workspace(int bm, int n);
 int launch_select(const tome_plan*, void*, size_t, cudaStream_t);
@@ -142,7 +147,7 @@ int tome_match(const void* metric, int32_t dtype, int32_t bm, int32_t n, int32_t
     if (!match_tc_supported(dtype, bm, n, cm, v, metric))
       return set_error(TOME_ERR_UNSUPPORTED, "tome_match: tcgen05 path needs an fp32/bf16 metric with cm %% 8 == 0, cm <= 4096 and even strides (got cm=%d)", cm);
     return launch_match_tc(metric, dtype, bm, n, cm, v, class_token, distill_token, node_max, node_idx, workspace,
-                           workspace_bytes, st, 1, 0);
+                           workspace_bytes, st, 1, 0, nullptr, nullptr);
   }
   if (algo != TOME_MATCH_EXACT_SIMT) return set_error(TOME_ERR_ARG, "tome_match: unknown algo %d", algo);
   return launch_match_exact(metric, dtype, bm, n, cm, v, class_token, distill_token, node_max, node_idx, workspace,
@@ -163,7 +168,7 @@ int tome_match_heads(const void* keys, int32_t dtype, int32_t bm, int32_t heads,
   if (!match_tc_supported(dtype, bm, n, cm, v, keys))
     return set_error(TOME_ERR_UNSUPPORTED, "tome_match_heads: needs cm %% 8 == 0 and even strides (got cm=%d); average the heads and call tome_match", cm);
   return launch_match_tc(keys, dtype, bm, n, cm, v, class_token, distill_token, node_max, node_idx, workspace,
-                         workspace_bytes, (cudaStream_t)stream, heads, stride_h);
+                         workspace_bytes, (cudaStream_t)stream, heads, stride_h, nullptr, nullptr);
 }
 
 static size_t align256_(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -216,8 +221,17 @@ int tome_plan_build(const void* metric, int32_t dtype, int32_t heads, int64_t st
   if (algo == TOME_MATCH_TCGEN05) {
     if (!tc_ok)
       return set_error(TOME_ERR_UNSUPPORTED, "tome_plan_build: tcgen05 path needs cm %% 8 == 0, cm <= 4096 and even strides (got cm=%d)", cm);
+    // three launches: normalise -> tensor-core match (packed keys only) -> one-launch select, which decodes the packed keys
+    // itself and whose threshold flags the normalisation kernel zeroed; TOME_SELECT_TWO=1 keeps the rank + finish pair
+    if (!select_two_launches() && match_tc_fused_refine(bm, n, cm)) {
+      unsigned long long *packed = nullptr, *flags = nullptr;
+      rc = launch_match_tc(metric, dtype, bm, n, cm, v, plan->class_token, plan->distill_token, nullptr, nullptr, workspace,
+                           match_bytes, st, heads, stride_h, &packed, &flags);
+      if (rc) return rc;
+      return launch_select_one(plan, packed, flags, st);
+    }
     rc = launch_match_tc(metric, dtype, bm, n, cm, v, plan->class_token, plan->distill_token, node_max, node_idx, workspace,
-                         match_bytes, st, heads, stride_h);
+                         match_bytes, st, heads, stride_h, nullptr, nullptr);
     if (rc) return rc;
     return launch_select(plan, select_ws, select_bytes, st);
   }

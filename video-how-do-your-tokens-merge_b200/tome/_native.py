@@ -627,7 +627,7 @@ def linear_gelu(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tens
 def attn_short_usable(x: torch.Tensor, heads: int) -> bool:
     """tome_attn_short serves this (seqs, n_tok, C) attention input: CUDA inference, <= 32 tokens, head dim 64."""
     return (x.is_cuda and not torch.is_grad_enabled() and x.dim() == 3 and x.shape[1] <= 32 and x.shape[2] == 64 * heads
-            and x.dtype in (torch.float32, torch.bfloat16))
+            and x.dtype in (torch.float32, torch.bfloat16) and os.environ.get("TOME_ATTN_SHORT", "1") != "0")
 
 
 def attn_short(qkv: torch.Tensor, heads: int, scale: float) -> torch.Tensor:

@@ -10,6 +10,8 @@ matching runs per frame on the P patch tokens (batch (b t), class token excluded
   * modules are matched structurally, so the reference's slowfast model and
     ``hostmodels.timesformer`` both patch.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -24,6 +26,7 @@ from tome.utils import parse_r
 def _fused_block_ok(block, x):
     """The divided space-time block can run on the view-aware kernels: CUDA inference, fusable LayerNorms."""
     return (x.is_cuda and not torch.is_grad_enabled() and not block.training and x.is_contiguous()
+            and os.environ.get("TOME_FUSED_BLOCKS", "1") != "0"
             and all(fusable_norm(getattr(block, n, None), x) is not None for n in ("temporal_norm1", "norm1", "norm2"))
             and isinstance(getattr(block, "temporal_fc", None), torch.nn.Linear))
 
