@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(RANK_ROWS * RANK_WARPS) select_one_kernel(Plan
   __shared__ int part[RANK_WARPS][RANK_ROWS][4];
   __shared__ Top2 part2[RANK_WARPS][RANK_ROWS];
   __shared__ unsigned long long s_thr;
+  __shared__ int s_cnt;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long ba = (long long)b * na;
   for (int j = threadIdx.x; j < na; j += blockDim.x) {
@@ -242,21 +243,40 @@ __global__ void __launch_bounds__(RANK_ROWS * RANK_WARPS) select_one_kernel(Plan
   }
   __syncthreads();                                          // also: part[][][0] has been read by everyone
   const unsigned long long thr = s_thr;
-  // ---- scan 2: CSR position of my source, the CSR row of "my" destination d = i, ascending position if class token
+  // ---- the r sources (keys >= threshold), compacted: the second scan walks r entries instead of na
+  unsigned long long* lk = sk2 + na + (na + 1) / 2;         // [r] rank keys of the sources   (after scol, 8-byte aligned)
+  int* lc = reinterpret_cast<int*>(lk + r);                // [r] their destinations
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  for (int j0 = 0; j0 < na; j0 += blockDim.x) {
+    const int j = j0 + threadIdx.x;
+    const bool sj = j < na && sk2[j] >= thr;
+    const unsigned m = __ballot_sync(0xffffffffu, sj);
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(&s_cnt, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (sj) {
+      const int at = base + __popc(m & ((1u << lane) - 1u));
+      lk[at] = sk2[j];
+      lc[at] = scol[j];
+    }
+  }
+  __syncthreads();
+  // ---- scan 2 over the sources: CSR position of my source, the CSR row of "my" destination d = i, and (class token)
+  //      the ascending position of my kept token = i - #{sources below i}
   const int d = i;                                          // this lane also owns B token d (d < nb)
   const bool is_src = i < na && rank < r;
-  int pos = 0, before = 0, ndst = 0, kept_below = 0;
+  int pos = 0, before = 0, ndst = 0, src_below = 0;
   Top2 t2{0ull, 0ull};
-#pragma unroll 2
-  for (int j = jb; j < je; ++j) {
-    const unsigned long long kj = sk2[j];
-    const int cj = scol[j];
-    const bool sj = kj >= thr;
-    pos += sj && (cj < mycol || (cj == mycol && kj > mine));
-    before += sj && cj < d;
-    if (sj && cj == d) { ++ndst; top2_push(t2, kj); }
-    kept_below += (!sj) && j < i;
+  for (int q = warp; q < r; q += RANK_WARPS) {
+    const unsigned long long kj = lk[q];
+    const int cj = lc[q];
+    pos += (cj < mycol || (cj == mycol && kj > mine));
+    before += cj < d;
+    if (cj == d) { ++ndst; top2_push(t2, kj); }
+    src_below += (int)(0xFFFFFFFFu - (uint32_t)(kj & 0xFFFFFFFFull)) < i;
   }
+  const int kept_below = src_below;                         // combined below: K = i - sum
   part[warp][lane][0] = pos; part[warp][lane][1] = before; part[warp][lane][2] = ndst; part[warp][lane][3] = kept_below;
   part2[warp][lane] = t2;
   __syncthreads();
@@ -271,7 +291,7 @@ __global__ void __launch_bounds__(RANK_ROWS * RANK_WARPS) select_one_kernel(Plan
       if (o.b) top2_push(m, o.b);
     }
     if (is_src) p.b_src[br + P] = i;
-    if (p.cls && i < na && !is_src) { p.unm_idx[bu + K] = i; p.a_map[ba + i] = K; }
+    if (p.cls && i < na && !is_src) { p.unm_idx[bu + i - K] = i; p.a_map[ba + i] = i - K; }
     if (d < nb) {
       const int s0 = m.a ? (int)(0xFFFFFFFFu - (uint32_t)(m.a & 0xFFFFFFFFull)) : 0;
       const int s1 = m.b ? (int)(0xFFFFFFFFu - (uint32_t)(m.b & 0xFFFFFFFFull)) : 0;
@@ -299,7 +319,7 @@ int launch_select_one(const tome_plan* plan, const unsigned long long* packed, u
   const int n = plan->n, na = na_of(n), r = plan->r, bm = plan->bm;
   PlanDev p{bm, n, r, plan->class_token, plan->distill_token, plan->node_max, plan->node_idx,
             plan->src_idx, plan->unm_idx, plan->dst_idx, plan->a_map, plan->b_off, plan->b_src, plan->b_head};
-  const size_t smem = (size_t)na * (sizeof(unsigned long long) + sizeof(int));
+  const size_t smem = ((size_t)na + (na + 1) / 2 + r + (r + 1) / 2 + 2) * sizeof(unsigned long long);     // keys, columns, source list
   if (smem > 200 * 1024) return set_error(TOME_ERR_UNSUPPORTED, "tome_select: n=%d needs more shared memory than one SM has", n);
   static PerDeviceOnce attr_set;
   if (attr_set.first_time())
