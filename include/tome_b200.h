@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 16
+#define TOME_ABI_VERSION 17
 
 #if defined(__GNUC__)
 #define TOME_API __attribute__((visibility("default")))
@@ -262,6 +262,21 @@ TOME_API int tome_attn_key_bias(const float* log_size, int32_t b, int32_t n, int
  * contiguous, same dtype (fp32 / bf16); fp32 scores, softmax and accumulation. */
 TOME_API int tome_attn_short(const void* q, const void* k, const void* v, int32_t dtype, int64_t seqs, int32_t n_tok,
                     int32_t heads, int32_t d, int64_t seq_stride, int64_t tok_stride, float scale, void* out, void* stream);
+
+/* Caller-side attention of Motionformer's trajectory attention (tome/patch/motionformer.py:105-115,
+ * slowfast/models/motionformer_vit_helper.py:196-243), bf16, head dimension 64.
+ * tome_frames_attention -- the space stage with the proportional-attention key bias: every one of the S = frames *
+ *   keys_per_frame patch queries attends to the keys of EACH frame separately,
+ *     xs[b, s, f, h*64 + c] = sum_p softmax_p(scale * q[b,h,s] . k[b,h,f,p] + key_bias[b, f*P + p]) * v[b,h,f,p][c],
+ *   on tcgen05 / TMEM / TMA.  qkv: the QKV GEMM's output (b, n, 3 * heads * 64), n = 1 + S tokens (class token first,
+ *   patch tokens in '(f p)' order), channel order (3, heads, 64), read in place; key_bias (b, S) fp32 or NULL;
+ *   xs (b, S, frames, heads*64); x_diag (b, S, heads*64) = xs[b, s, frame of s] or NULL.  keys_per_frame <= 256.
+ * tome_traj_temporal -- the temporal stage: out[r, h] = sum_f softmax_f(scale * q2[r,h] . k2[r,f,h]) * vals[r,f,h] for
+ *   rows r = (b, s); q2 / out (rows, heads*64), k2 / vals (rows, frames, heads*64), frames <= 32. */
+TOME_API int tome_frames_attention(const void* qkv, int32_t dtype, int32_t b, int32_t n, int32_t heads, int32_t d, int32_t frames,
+                          int32_t keys_per_frame, float scale, const float* key_bias, void* xs, void* x_diag, void* stream);
+TOME_API int tome_traj_temporal(const void* q2, const void* k2, const void* vals, int32_t dtype, int64_t rows, int32_t frames,
+                       int32_t heads, int32_t d, float scale, void* out, void* stream);
 
 /* Caller-side data format: the tubelet embedding of the four models is a Conv3d whose
  * kernel equals its stride (slowfast/models/videomae_video_model_builder.py:138-160), i.e. a GEMM over

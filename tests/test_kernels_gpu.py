@@ -1059,3 +1059,46 @@ def test_attn_short_matches_softmax_attention(native, dtype, tn):
     torch.testing.assert_close(out.double(), want, rtol=tol, atol=tol)
     with torch.no_grad():
         assert native.attn_short_usable(qkv[..., :H * d], H) and not native.attn_short_usable(torch.zeros(2, 33, H * d, device="cuda"), H)
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("with_bias", [False, True], ids=["plain", "prop_attn"])
+@pytest.mark.parametrize("P", [196, 178, 128, 37, 9])
+def test_frames_attention_matches_per_frame_softmax(native, P, with_bias):
+    """tome_frames_attention (tcgen05) against the eager formulation of Motionformer's space attention with the
+    proportional-attention key bias (tome/patch/motionformer.py:105-115) in fp64; bf16 inputs, probabilities rounded to
+    bf16 before P V as every fused attention kernel does."""
+    g = torch.Generator().manual_seed(P)
+    B, h, Fr, d = 2, 3, 4, 64
+    S, C = Fr * P, h * d
+    qkv = torch.randn(B, 1 + S, 3 * C, generator=g).to("cuda", torch.bfloat16)
+    bias = (torch.randint(1, 6, (B, S), generator=g).float().log()).cuda() if with_bias else None
+    with torch.no_grad():
+        assert native.frames_attention_usable(qkv[..., :C], h, P)
+    xs, diag = native.frames_attention(qkv, h, Fr, d ** -0.5, bias)
+    q, k, v = qkv.double().reshape(B, 1 + S, 3, h, d).permute(2, 0, 3, 1, 4)          # (B, h, N, d)
+    q, k, v = q[:, :, 1:], k[:, :, 1:].reshape(B, h, Fr, P, d), v[:, :, 1:].reshape(B, h, Fr, P, d)
+    sc = torch.einsum("bhsd,bhfpd->bhsfp", q, k) * d ** -0.5
+    if bias is not None:
+        sc = sc + bias.double().reshape(B, 1, 1, Fr, P)
+    want = torch.einsum("bhsfp,bhfpd->bsfhd", sc.softmax(-1), v).reshape(B, S, Fr, C)
+    torch.testing.assert_close(xs.double(), want, rtol=2e-2, atol=6e-3)
+    frame = torch.arange(S, device="cuda") // P
+    assert torch.equal(diag, xs[:, torch.arange(S, device="cuda"), frame])
+
+
+def test_traj_temporal_matches_einsum_formulation(native):
+    """tome_traj_temporal against vit_helper.py:232-243 (softmax over frames of q2 . k2, values = xs) in fp64."""
+    g = torch.Generator().manual_seed(3)
+    B, S, Fr, h, d = 2, 77, 8, 3, 64
+    C = h * d
+    q2 = torch.randn(B, S, C, generator=g).to("cuda", torch.bfloat16)
+    k2 = torch.randn(B, S, Fr, C, generator=g).to("cuda", torch.bfloat16)
+    xs = torch.randn(B, S, Fr, C, generator=g).to("cuda", torch.bfloat16)
+    out = native.traj_temporal(q2, k2, xs, h, d ** -0.5)
+    qd = q2.double().reshape(B, S, h, d).transpose(1, 2) * d ** -0.5
+    kd = k2.double().reshape(B, S, Fr, h, d).permute(0, 3, 1, 2, 4)
+    vd = xs.double().reshape(B, S, Fr, h, d).permute(0, 3, 1, 2, 4)
+    attn = torch.einsum("bhsd,bhsfd->bhsf", qd, kd).softmax(-1)
+    want = torch.einsum("bhsf,bhsfd->bhsd", attn, vd).transpose(1, 2).reshape(B, S, C)
+    torch.testing.assert_close(out.double(), want, rtol=1e-2, atol=1e-2)

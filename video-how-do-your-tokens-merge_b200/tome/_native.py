@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 16
+ABI_VERSION = 17
 
 TOME_F32, TOME_BF16, TOME_U8 = 0, 1, 2
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -32,6 +32,7 @@ EXPORTS = (
     "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_linear_gelu", "tome_unmerge",
     "tome_match_sets_workspace_bytes", "tome_match_sets", "tome_group_reduce", "tome_gather_rows",
     "tome_source_compose", "tome_source_dense", "tome_random_rowmax", "tome_merge_add_norm_rv", "tome_rows_add_layernorm", "tome_attn_short",
+    "tome_frames_attention", "tome_traj_temporal",
 )
 
 
@@ -128,8 +129,10 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.tome_rows_add_layernorm.argtypes = [c_vp, p_i64, c_vp, p_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_f32, c_vp, p_i64,
                                             c_vp, p_i64, c_vp]
     lib.tome_attn_short.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_i64, c_i64, c_f32, c_vp, c_vp]
+    lib.tome_frames_attention.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp]
+    lib.tome_traj_temporal.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]
     for name in ("tome_source_compose", "tome_source_dense", "tome_random_rowmax", "tome_merge_add_norm_rv", "tome_rows_add_layernorm",
-                 "tome_attn_short"):
+                 "tome_attn_short", "tome_frames_attention", "tome_traj_temporal"):
         getattr(lib, name).restype = c_i32
     for name in ("tome_device_check", "tome_match", "tome_match_heads", "tome_rowmax", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_add_norm", "tome_add_layernorm", "tome_add_rows_layernorm",
                  "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_linear_gelu", "tome_unmerge",
@@ -645,6 +648,52 @@ def attn_short(qkv: torch.Tensor, heads: int, scale: float) -> torch.Tensor:
         base = qkv.data_ptr()
         _check(lib.tome_attn_short(base, base + c * esz, base + 2 * c * esz, _dtype_code(qkv), seqs, tn, heads, d, tn * c3, c3,
                                    float(scale), out.data_ptr(), _stream(qkv)), lib)
+    return out
+
+
+def frames_attention_usable(x: torch.Tensor, heads: int, keys_per_frame: int) -> bool:
+    """tome_frames_attention / tome_traj_temporal serve this trajectory-attention input: CUDA bf16 inference, head
+    dimension 64, at most 256 keys per frame."""
+    return (x.is_cuda and not torch.is_grad_enabled() and x.dtype == torch.bfloat16 and x.dim() == 3
+            and x.shape[2] == 64 * heads and 1 <= keys_per_frame <= 256 and os.environ.get("TOME_FRAMES_ATTN", "1") != "0")
+
+
+def frames_attention(qkv: torch.Tensor, heads: int, frames: int, scale: float, key_bias: Optional[torch.Tensor] = None,
+                     want_diag: bool = True):
+    """Space stage of the trajectory attention on the QKV GEMM's output (B, 1 + F*P, 3*heads*64): returns
+    xs (B, F*P, F, heads*64) and, with ``want_diag``, x_diag (B, F*P, heads*64) = xs[b, s, frame(s)].
+    ``key_bias`` (B, F*P) fp32: log size per key in the token order (proportional attention)."""
+    lib = load_library()
+    _require_cuda(qkv, "qkv")
+    qkv = qkv.contiguous()
+    B, N, c3 = qkv.shape
+    C = c3 // 3
+    S = N - 1
+    P = S // frames
+    if S != P * frames:
+        raise RuntimeError(f"tome_b200: frames_attention expects 1 + frames * P tokens; got {N} with {frames} frames")
+    bp = None
+    if key_bias is not None:
+        key_bias = key_bias.to(torch.float32).reshape(B, S).contiguous()
+        bp = key_bias.data_ptr()
+    with torch.cuda.device(qkv.device):
+        xs = torch.empty(B, S, frames, C, dtype=qkv.dtype, device=qkv.device)
+        diag = torch.empty(B, S, C, dtype=qkv.dtype, device=qkv.device) if want_diag else None
+        _check(lib.tome_frames_attention(qkv.data_ptr(), _dtype_code(qkv), B, N, heads, C // heads, frames, P, float(scale), bp,
+                                         xs.data_ptr(), None if diag is None else diag.data_ptr(), _stream(qkv)), lib)
+    return xs, diag
+
+
+def traj_temporal(q2: torch.Tensor, k2: torch.Tensor, vals: torch.Tensor, heads: int, scale: float) -> torch.Tensor:
+    """Temporal stage of the trajectory attention: q2 (B, S, C), k2 / vals (B, S, F, C) -> (B, S, C)."""
+    lib = load_library()
+    _require_cuda(q2, "q2")
+    q2, k2, vals = q2.contiguous(), k2.contiguous(), vals.contiguous()
+    B, S, F_, C = k2.shape
+    with torch.cuda.device(q2.device):
+        out = torch.empty(B, S, C, dtype=q2.dtype, device=q2.device)
+        _check(lib.tome_traj_temporal(q2.data_ptr(), k2.data_ptr(), vals.data_ptr(), _dtype_code(q2), B * S, F_, heads, C // heads,
+                                      float(scale), out.data_ptr(), _stream(q2)), lib)
     return out
 
 

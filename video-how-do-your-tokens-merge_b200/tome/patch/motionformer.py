@@ -25,6 +25,23 @@ def trajectory_attention(mod, x, num_frames, log_size=None, on_keys=None):
     Fr, h = num_frames, mod.num_heads
     P = (N - 1) // Fr
     d = C // h
+    from tome import _native
+    if d == 64 and _native.frames_attention_usable(x, h, P) and N == 1 + Fr * P and Fr <= 32:
+        # bf16 inference: both stages on the library's kernels (tome_frames_attention on tcgen05, tome_traj_temporal),
+        # q / k / v read in place from the QKV GEMM's output
+        qkv = mod.qkv(x)
+        q, k, v = qkv.view(B, N, 3, h, d).permute(2, 0, 3, 1, 4)
+        if on_keys is not None:
+            on_keys(k[:, :, 1:])
+        cls_out = F.scaled_dot_product_attention(q[:, :, 0:1], k, v, scale=mod.scale).transpose(1, 2).reshape(B, 1, C)
+        xs, x_diag = _native.frames_attention(qkv, h, Fr, mod.scale, log_size)
+        q2 = mod.proj_q(x_diag)
+        wkv, bkv = mod.proj_kv.weight, mod.proj_kv.bias
+        k2 = F.linear(xs, wkv[:C], None if bkv is None else bkv[:C])
+        vals = xs if mod.use_original_code else F.linear(xs, wkv[C:], None if bkv is None else bkv[C:])
+        out = _native.traj_temporal(q2, k2, vals, h, mod.scale)
+        out = mod.proj_drop(mod.proj(torch.cat((cls_out, out), dim=1)))
+        return out, k[:, :, 1:]
     q, k, v = mod.qkv(x).reshape(B, N, 3, h, d).permute(2, 0, 3, 1, 4)        # each (B, h, N, d)
     if on_keys is not None:              # K exists: the matching can start beside the attention kernels
         on_keys(k[:, :, 1:])
