@@ -29,7 +29,9 @@ constexpr int FA_THREADS = 192;
 constexpr int FA_HALF_KS = 8;       // k-steps (16 keys each) per half of the P tile: 128 keys, 32 KB
 
 struct FaParams {
-  int B, N, S, F, P, PB, heads;     // N = 1 + F * P tokens per clip (class token first), S = F * P queries
+  int B, N, S, F, P, PB, heads;     // N = tok0 + F * P tokens per clip, S = F * P queries (and keys)
+  int tok0;                         // leading tokens that are neither queries nor keys (Motionformer's class token: 1)
+  int nobias_q;                     // leading QUERIES whose logits take no key bias (TimeSformer's class token, timesformer.py:74)
   float scale_log2e;                // softmax scale * log2(e)
   const float* bias;                // (B, F * P) log size per key in the token order, or NULL
   __nv_bfloat16* xs;                // (B, S, F, heads * 64)
@@ -40,6 +42,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// shared-memory key bias as seen by one query row: padded keys stay -inf, unbiased rows (TimeSformer's class query) see 0
+__device__ __forceinline__ float key_bias(float b, bool) { return b; }     // the row's bias array is chosen once per row
+// Waits of this kernel last microseconds and there are six waiting warps per CTA: a tight try_wait loop took 40 % of all
+// issued instructions away from the softmax warps sharing the scheduler (profiles/r02_frames_attn_ncu.txt).  Back off.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, unsigned ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  do {
+    __nanosleep(ns);
+    if (++spins > (1u << 22)) __trap();
+  } while (!mbar_try_wait(bar, parity));
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -72,11 +86,11 @@ frames_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   const uint32_t kv_bytes = (uint32_t)p.PB * 128u;
   const uint32_t kv_pad = (kv_bytes + 1023u) & ~1023u;
   const uint32_t sm_q = base, sm_k = sm_q + FA_BM * 128u, sm_v = sm_k + kv_pad, sm_p = sm_v + kv_pad;   // P: 2 k-blocks x 16 KB
-  const uint32_t sm_bias = sm_p + 2u * FA_BM * 128u;                 // PB floats
-  const uint32_t bars = sm_bias + 1024u;
+  const uint32_t sm_bias = sm_p + 2u * FA_BM * 128u;                 // 2 x 256 floats
+  const uint32_t bars = sm_bias + 2048u;
   const uint32_t bar_q = bars, bar_k = bars + 8, bar_v = bars + 16, bar_s = bars + 24, bar_p0 = bars + 32, bar_p1 = bars + 40,
                  bar_pfree = bars + 48, bar_o = bars + 56, bar_sfree = bars + 64, tmem_slot = bars + 72;
-  float* bias_s = reinterpret_cast<float*>(gen + (sm_bias - base));
+  float* bias_all = reinterpret_cast<float*>(gen + (sm_bias - base));
   uint8_t* p_gen = gen + (sm_p - base);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
@@ -98,17 +112,17 @@ frames_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 
   const int nks = p.PB >> 4;                                   // k-steps of 16 keys per frame
   const int h0 = nks < FA_HALF_KS ? nks : FA_HALF_KS;          // k-steps in the first half of the P tile
-  const int row0 = b * p.N + 1;                                // first patch token of this clip in the (B*N, 3C) tensor
+  const int row0 = b * p.N + p.tok0;                           // first query / key token of this clip in the (B*N, 3C) tensor
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(bar_q, FA_BM * 128u);
       tma_load_2d(sm_q, &map_q, h * FA_D, row0 + qt * FA_BM, bar_q);
       for (int f = 0; f < p.F; ++f) {
-        if (f > 0) mbar_wait(bar_s, (f - 1) & 1);              // S(f-1) complete: the K buffer is free
+        if (f > 0) mbar_wait_sleep(bar_s, (f - 1) & 1, 64);              // S(f-1) complete: the K buffer is free
         mbar_expect_tx(bar_k, kv_bytes);
         tma_load_2d(sm_k, &map_kv, C + h * FA_D, row0 + f * p.P, bar_k);
-        if (f > 0) mbar_wait(bar_o, (f - 1) & 1);              // O(f-1) complete: the V buffer is free
+        if (f > 0) mbar_wait_sleep(bar_o, (f - 1) & 1, 64);              // O(f-1) complete: the V buffer is free
         mbar_expect_tx(bar_v, kv_bytes);
         tma_load_2d(sm_v, &map_kv, 2 * C + h * FA_D, row0 + f * p.P, bar_v);
       }
@@ -118,25 +132,25 @@ frames_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       // S = Q K^T: D fp32, A/B bf16, both K-major, M = 128, N = PB.   O = P V: B MN-major (bit 16), N = 64.
       const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.PB >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
       const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(FA_D >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
-      mbar_wait(bar_q, 0);
+      mbar_wait_sleep(bar_q, 0, 64);
       for (int f = 0; f < p.F; ++f) {
         const uint32_t ph = (uint32_t)(f & 1);
-        if (f > 0) mbar_wait(bar_sfree, (f - 1) & 1);          // O(f-1) has been read out of the columns S(f) lands in
-        mbar_wait(bar_k, ph);
+        if (f > 0) mbar_wait_sleep(bar_sfree, (f - 1) & 1, 64);          // O(f-1) has been read out of the columns S(f) lands in
+        mbar_wait_sleep(bar_k, ph, 64);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < FA_D / 16; ++k)
           umma_bf16(tmem_base, make_sw128_desc(sm_q + 32u * k), make_sw128_desc(sm_k + 32u * k), idesc1, k ? 1u : 0u);
         umma_commit(bar_s);
-        mbar_wait(bar_v, ph);
-        mbar_wait(bar_p0, ph);
+        mbar_wait_sleep(bar_v, ph, 64);
+        mbar_wait_sleep(bar_p0, ph, 64);
         tc_fence_after();
         for (int ks = 0; ks < h0; ++ks)
           umma_bf16(tmem_base, make_sw128_desc(sm_p + (uint32_t)(ks >> 2) * (FA_BM * 128u) + 32u * (ks & 3)),
                     make_sw128_mn_desc(sm_v + 2048u * ks), idesc2, ks ? 1u : 0u);
         if (nks > h0) {
           umma_commit(bar_pfree);
-          mbar_wait(bar_p1, ph);
+          mbar_wait_sleep(bar_p1, ph, 64);
           tc_fence_after();
           for (int ks = h0; ks < nks; ++ks)
             umma_bf16(tmem_base, make_sw128_desc(sm_p + (uint32_t)((ks - h0) >> 2) * (FA_BM * 128u) + 32u * ((ks - h0) & 3)),
@@ -153,77 +167,105 @@ frames_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const bool live = s < p.S;
     const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16);
     const float LOG2E = 1.4426950408889634f;
+    const bool biased = p.bias != nullptr && s >= p.nobias_q;  // per query row
+    const float* bias_s = bias_all + (biased ? 0 : 256);
     for (int f = 0; f < p.F; ++f) {
       const uint32_t ph = (uint32_t)(f & 1);
       // key bias of this frame (times log2 e); padded keys get -inf so they vanish from max, sum and P
       asm volatile("bar.sync 1, 128;" ::: "memory");           // everyone is done with the previous frame's bias
-      for (int j = st; j < p.PB; j += 128)
-        bias_s[j] = j < p.P ? (p.bias ? __ldg(p.bias + (long long)b * p.S + f * p.P + j) * LOG2E : 0.f) : -INFINITY;
+      for (int j = st; j < 256; j += 128) {                     // [0, 256): with the key bias; [256, 512): without (padding only)
+        bias_all[j] = j < p.P ? (p.bias ? __ldg(p.bias + (long long)b * p.S + f * p.P + j) * LOG2E : 0.f) : -INFINITY;
+        bias_all[256 + j] = j < p.P ? 0.f : -INFINITY;
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      mbar_wait(bar_s, ph);
+      mbar_wait_sleep(bar_s, ph, 32);
       tc_fence_after();
+      // k-steps of 16 columns, two TMEM loads in flight per wait (a version with 32-column units and both halves of a
+      // pair live spilled the parked probabilities to local memory and ran 1.5x slower: profiles/r02_frames_attn_ncu.txt)
       // pass 1: row maximum of t_j = s_j * scale * log2e + bias_j
       float m = -INFINITY;
-      for (int c = 0; c < p.PB; c += 16) {
-        float v[16];
-        tmem_ld16(taddr + (uint32_t)c, v);
+      for (int ks = 0; ks < nks; ks += 2) {
+        float va[16], vb[16];
+        const bool two = ks + 1 < nks;                         // warp-uniform
+        tmem_ld16_nowait(taddr + (uint32_t)(ks * 16), va);
+        if (two) tmem_ld16_nowait(taddr + (uint32_t)(ks * 16 + 16), vb);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const float4* b4p = reinterpret_cast<const float4*>(bias_s + ks * 16);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) m = fmaxf(m, fmaf(v[e], p.scale_log2e, bias_s[c + e]));
-      }
-      // pass 2: probabilities.  First half straight into the P tile, second half parked in registers until the
-      // MMAs of the first half have released the tile.
-      float l = 0.f;
-      for (int ks = 0; ks < h0; ++ks) {
-        float v[16];
-        tmem_ld16(taddr + (uint32_t)(ks * 16), v);
-        uint32_t w[8];
-#pragma unroll
-        for (int e = 0; e < 16; e += 2) {
-          const float p0 = ex2_approx(fmaf(v[e], p.scale_log2e, bias_s[ks * 16 + e]) - m);
-          const float p1 = ex2_approx(fmaf(v[e + 1], p.scale_log2e, bias_s[ks * 16 + e + 1]) - m);
-          l += p0 + p1;
-          w[e >> 1] = pack_bf16(p0, p1);
+        for (int e = 0; e < 16; e += 4) {
+          const float4 b4 = b4p[e >> 2];
+          m = fmaxf(m, fmaxf(fmaxf(fmaf(va[e], p.scale_log2e, b4.x), fmaf(va[e + 1], p.scale_log2e, b4.y)),
+                             fmaxf(fmaf(va[e + 2], p.scale_log2e, b4.z), fmaf(va[e + 3], p.scale_log2e, b4.w))));
         }
-        // K-major SWIZZLE_128B: k-block = ks / 4 (64 keys, 16 KB), row = 128 bytes, 16-byte chunk index XOR (row % 8)
-        uint8_t* rowp = p_gen + (size_t)(ks >> 2) * (FA_BM * 128) + (size_t)row * 128;
-        const int c0 = 2 * (ks & 3);
+        if (two) {
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            const float4 b4 = b4p[4 + (e >> 2)];
+            m = fmaxf(m, fmaxf(fmaxf(fmaf(vb[e], p.scale_log2e, b4.x), fmaf(vb[e + 1], p.scale_log2e, b4.y)),
+                               fmaxf(fmaf(vb[e + 2], p.scale_log2e, b4.z), fmaf(vb[e + 3], p.scale_log2e, b4.w))));
+          }
+        }
+      }
+      // pass 2: probabilities of one k-step -> 8 packed bf16 pairs; the row sum in two chains
+      float l0 = 0.f, l1 = 0.f;
+      auto probs16 = [&](const float (&v)[16], int ks, uint32_t (&w)[8]) {
+        const float4* b4p = reinterpret_cast<const float4*>(bias_s + ks * 16);
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          const float4 b4 = b4p[e >> 2];
+          const float p0 = ex2_approx(fmaf(v[e], p.scale_log2e, b4.x) - m);
+          const float p1 = ex2_approx(fmaf(v[e + 1], p.scale_log2e, b4.y) - m);
+          const float p2 = ex2_approx(fmaf(v[e + 2], p.scale_log2e, b4.z) - m);
+          const float p3 = ex2_approx(fmaf(v[e + 3], p.scale_log2e, b4.w) - m);
+          l0 += p0 + p1;
+          l1 += p2 + p3;
+          w[e >> 1] = pack_bf16(p0, p1);
+          w[(e >> 1) + 1] = pack_bf16(p2, p3);
+        }
+      };
+      // k-step `kp` of a half of the P tile: K-major SWIZZLE_128B, k-block = kp / 4 (64 keys, 16 KB), row = 128 bytes,
+      // 16-byte chunk index (2 * (kp % 4) + i) XOR (row % 8)
+      auto store16 = [&](int kp, const uint32_t (&w)[8]) {
+        uint8_t* rowp = p_gen + (size_t)(kp >> 2) * (FA_BM * 128) + (size_t)row * 128;
+        const int c0 = 2 * (kp & 3);
         *reinterpret_cast<uint4*>(rowp + (((c0) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         *reinterpret_cast<uint4*>(rowp + (((c0 + 1) ^ (row & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+      };
+      for (int ks = 0; ks < h0; ks += 2) {                     // first half straight into the P tile
+        float va[16], vb[16];
+        uint32_t w[8];
+        const bool two = ks + 1 < h0;
+        tmem_ld16_nowait(taddr + (uint32_t)(ks * 16), va);
+        if (two) tmem_ld16_nowait(taddr + (uint32_t)(ks * 16 + 16), vb);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        probs16(va, ks, w);
+        store16(ks, w);
+        if (two) { probs16(vb, ks + 1, w); store16(ks + 1, w); }
       }
       fence_async_smem();
       mbar_arrive(bar_p0);
       if (nks > h0) {
+        // second half parked in registers until the MMAs of the first half have released the tile
         uint32_t park[FA_HALF_KS][8];
 #pragma unroll
         for (int u = 0; u < FA_HALF_KS; ++u) {
-          const int ks = h0 + u;
-          if (ks < nks) {                                       // warp-uniform
-            float v[16];
-            tmem_ld16(taddr + (uint32_t)(ks * 16), v);
-#pragma unroll
-            for (int e = 0; e < 16; e += 2) {
-              const float p0 = ex2_approx(fmaf(v[e], p.scale_log2e, bias_s[ks * 16 + e]) - m);
-              const float p1 = ex2_approx(fmaf(v[e + 1], p.scale_log2e, bias_s[ks * 16 + e + 1]) - m);
-              l += p0 + p1;
-              park[u][e >> 1] = pack_bf16(p0, p1);
-            }
+          if (h0 + u < nks) {                                   // warp-uniform
+            float va[16];
+            tmem_ld16_nowait(taddr + (uint32_t)((h0 + u) * 16), va);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            probs16(va, h0 + u, park[u]);
           }
         }
-        mbar_wait(bar_pfree, ph);
+        mbar_wait_sleep(bar_pfree, ph, 32);
 #pragma unroll
-        for (int u = 0; u < FA_HALF_KS; ++u) {
-          if (h0 + u < nks) {
-            uint8_t* rowp = p_gen + (size_t)(u >> 2) * (FA_BM * 128) + (size_t)row * 128;
-            const int c0 = 2 * (u & 3);
-            *reinterpret_cast<uint4*>(rowp + (((c0) ^ (row & 7)) << 4)) = make_uint4(park[u][0], park[u][1], park[u][2], park[u][3]);
-            *reinterpret_cast<uint4*>(rowp + (((c0 + 1) ^ (row & 7)) << 4)) = make_uint4(park[u][4], park[u][5], park[u][6], park[u][7]);
-          }
-        }
+        for (int u = 0; u < FA_HALF_KS; ++u)
+          if (h0 + u < nks) store16(u, park[u]);
         fence_async_smem();
         mbar_arrive(bar_p1);
       }
+      const float l = l0 + l1;
       // output row: O / l, written once (128 contiguous bytes of the (B, S, F, C) tensor)
-      mbar_wait(bar_o, ph);
+      mbar_wait_sleep(bar_o, ph, 32);
       tc_fence_after();
       const float inv = 1.0f / l;
       float o0[32], o1[32];
@@ -335,13 +377,13 @@ __global__ void __launch_bounds__(128) traj_temporal_kernel(const __nv_bfloat16*
 
 // ---- host -------------------------------------------------------------------------------------------------------
 int launch_frames_attention(const void* qkv, int B, int N, int heads, int F, int P, float scale, const float* bias, void* xs,
-                            void* x_diag, cudaStream_t st) {
-  if (N != 1 + F * P) return set_error(TOME_ERR_ARG, "tome_frames_attention: N=%d != 1 + F*P (F=%d P=%d)", N, F, P);
+                            void* x_diag, int tok0, int nobias_q, cudaStream_t st) {
+  if (tok0 < 0 || N != tok0 + F * P) return set_error(TOME_ERR_ARG, "tome_frames_attention: N=%d != lead + F*P (lead=%d F=%d P=%d)", N, tok0, F, P);
   if (P < 1 || P > 256) return set_error(TOME_ERR_UNSUPPORTED, "tome_frames_attention: %d keys per frame (1..256)", P);
   if (((uintptr_t)qkv & 15) || ((uintptr_t)xs & 15) || (x_diag && ((uintptr_t)x_diag & 15)))
     return set_error(TOME_ERR_ALIGN, "tome_frames_attention: buffers must be 16-byte aligned");
   FaParams p;
-  p.B = B; p.N = N; p.S = F * P; p.F = F; p.P = P; p.PB = (P + 15) & ~15; p.heads = heads;
+  p.B = B; p.N = N; p.S = F * P; p.F = F; p.P = P; p.PB = (P + 15) & ~15; p.heads = heads; p.tok0 = tok0; p.nobias_q = nobias_q;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.bias = bias; p.xs = (__nv_bfloat16*)xs; p.x_diag = (__nv_bfloat16*)x_diag;
   const long long rows = (long long)B * N, cols = 3LL * heads * FA_D;
@@ -351,7 +393,7 @@ int launch_frames_attention(const void* qkv, int B, int N, int heads, int F, int
   rc = make_bf16_map(&map_kv, qkv, rows, cols, cols, p.PB, "tome_frames_attention");
   if (rc) return rc;
   const size_t kv_pad = ((size_t)p.PB * 128 + 1023) & ~(size_t)1023;
-  const size_t smem = 1024 + FA_BM * 128 + 2 * kv_pad + 2 * FA_BM * 128 + 1024 + 128;
+  const size_t smem = 1024 + FA_BM * 128 + 2 * kv_pad + 2 * FA_BM * 128 + 2048 + 128;
   static PerDeviceOnce once;
   if (once.first_time()) TOME_CUDA(cudaFuncSetAttribute(frames_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   dim3 grid((p.S + FA_BM - 1) / FA_BM, heads, B);

@@ -84,7 +84,7 @@ int launch_match_sets(const void*, int, int, int, const View&, const int*, long 
 int launch_group_reduce(const void*, int, int, int, const View&, const int*, long long, int, int, const int*, int, void*, cudaStream_t);
 int launch_gather_rows(const void*, int, int, int, int, const int*, int, void*, cudaStream_t);
 int launch_attn_short(const void*, const void*, const void*, int, long long, int, int, int, long long, long long, float, void*, cudaStream_t);
-int launch_frames_attention(const void*, int, int, int, int, int, float, const float*, void*, void*, cudaStream_t);
+int launch_frames_attention(const void*, int, int, int, int, int, float, const float*, void*, void*, int, int, cudaStream_t);
 int launch_traj_temporal(const void*, const void*, const void*, long long, int, int, float, void*, cudaStream_t);
 int launch_source_compose(const tome_plan*, const int*, int, int, float, int*, cudaStream_t);
 int launch_source_dense(const int*, int, int, int, float*, cudaStream_t);
@@ -480,12 +480,15 @@ int tome_attn_short(const void* q, const void* k, const void* v, int32_t dtype, 
 }
 
 int tome_frames_attention(const void* qkv, int32_t dtype, int32_t b, int32_t n, int32_t heads, int32_t d, int32_t frames,
-                          int32_t keys_per_frame, float scale, const float* key_bias, void* xs, void* x_diag, void* stream) {
+                          int32_t keys_per_frame, int32_t lead, int32_t unbiased_queries, float scale, const float* key_bias, void* xs,
+                          void* x_diag, void* stream) {
   int rc = ensure_device_ok();
   if (rc) return rc;
   TOME_CHECK_ARG(qkv && xs && b > 0 && n > 1 && heads > 0 && frames > 0 && keys_per_frame > 0, "tome_frames_attention: NULL pointer or empty shape");
   if (dtype != TOME_BF16 || d != 64) return set_error(TOME_ERR_UNSUPPORTED, "tome_frames_attention: bf16 with head dimension 64 only (dtype %d, d %d)", dtype, d);
-  return launch_frames_attention(qkv, b, n, heads, frames, keys_per_frame, scale, key_bias, xs, x_diag, (cudaStream_t)stream);
+  TOME_CHECK_ARG(lead >= 0 && unbiased_queries >= 0, "tome_frames_attention: negative lead");
+  return launch_frames_attention(qkv, b, n, heads, frames, keys_per_frame, scale, key_bias, xs, x_diag, lead, unbiased_queries,
+                                 (cudaStream_t)stream);
 }
 
 int tome_traj_temporal(const void* q2, const void* k2, const void* vals, int32_t dtype, int64_t rows, int32_t frames, int32_t heads,

@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 17
+ABI_VERSION = 18
 
 TOME_F32, TOME_BF16, TOME_U8 = 0, 1, 2
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -129,7 +129,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.tome_rows_add_layernorm.argtypes = [c_vp, p_i64, c_vp, p_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_f32, c_vp, p_i64,
                                             c_vp, p_i64, c_vp]
     lib.tome_attn_short.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_i64, c_i64, c_f32, c_vp, c_vp]
-    lib.tome_frames_attention.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp]
+    lib.tome_frames_attention.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp]
     lib.tome_traj_temporal.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]
     for name in ("tome_source_compose", "tome_source_dense", "tome_random_rowmax", "tome_merge_add_norm_rv", "tome_rows_add_layernorm",
                  "tome_attn_short", "tome_frames_attention", "tome_traj_temporal"):
@@ -659,19 +659,20 @@ def frames_attention_usable(x: torch.Tensor, heads: int, keys_per_frame: int) ->
 
 
 def frames_attention(qkv: torch.Tensor, heads: int, frames: int, scale: float, key_bias: Optional[torch.Tensor] = None,
-                     want_diag: bool = True):
-    """Space stage of the trajectory attention on the QKV GEMM's output (B, 1 + F*P, 3*heads*64): returns
+                     want_diag: bool = True, lead: int = 1, unbiased_queries: int = 0):
+    """Space stage of the trajectory attention on the QKV GEMM's output (B, lead + F*P, 3*heads*64): returns
     xs (B, F*P, F, heads*64) and, with ``want_diag``, x_diag (B, F*P, heads*64) = xs[b, s, frame(s)].
-    ``key_bias`` (B, F*P) fp32: log size per key in the token order (proportional attention)."""
+    ``key_bias`` (B, F*P) fp32: log size per key in the token order (proportional attention).  ``frames=1, lead=0``:
+    plain attention over <= 256 tokens with a key bias; the first ``unbiased_queries`` queries take no bias."""
     lib = load_library()
     _require_cuda(qkv, "qkv")
     qkv = qkv.contiguous()
     B, N, c3 = qkv.shape
     C = c3 // 3
-    S = N - 1
+    S = N - lead
     P = S // frames
     if S != P * frames:
-        raise RuntimeError(f"tome_b200: frames_attention expects 1 + frames * P tokens; got {N} with {frames} frames")
+        raise RuntimeError(f"tome_b200: frames_attention expects {lead} + frames * P tokens; got {N} with {frames} frames")
     bp = None
     if key_bias is not None:
         key_bias = key_bias.to(torch.float32).reshape(B, S).contiguous()
@@ -679,8 +680,9 @@ def frames_attention(qkv: torch.Tensor, heads: int, frames: int, scale: float, k
     with torch.cuda.device(qkv.device):
         xs = torch.empty(B, S, frames, C, dtype=qkv.dtype, device=qkv.device)
         diag = torch.empty(B, S, C, dtype=qkv.dtype, device=qkv.device) if want_diag else None
-        _check(lib.tome_frames_attention(qkv.data_ptr(), _dtype_code(qkv), B, N, heads, C // heads, frames, P, float(scale), bp,
-                                         xs.data_ptr(), None if diag is None else diag.data_ptr(), _stream(qkv)), lib)
+        _check(lib.tome_frames_attention(qkv.data_ptr(), _dtype_code(qkv), B, N, heads, C // heads, frames, P, int(lead),
+                                         int(unbiased_queries), float(scale), bp, xs.data_ptr(),
+                                         None if diag is None else diag.data_ptr(), _stream(qkv)), lib)
     return xs, diag
 
 

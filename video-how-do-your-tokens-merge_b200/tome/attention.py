@@ -65,6 +65,25 @@ def attention(x, owner, heads, d, scale, log_size, wq, wk, wv, bq=None, bk=None,
     (B, N, heads * d) and the key tensor (B, heads, N, d) the matching metric is taken from."""
     from tome import _native
     B, N, _ = x.shape
+    if d == 64 and N <= 256 and _native.frames_attention_usable(x, heads, N):
+        # one key block: the library's own tcgen05 attention takes the key bias directly (tome_frames_attention with a
+        # single "frame"), on the UNPADDED projection -- TimeSformer's 197-token spatial attention, the last ViViT layers
+        key = _key_of((wq, wk, wv, bq, bk, bv))
+        cached = getattr(owner, "_tome_plain_qkv", None)
+        if cached is None or cached[0] != key:
+            w = torch.cat((wq, wk, wv), 0).detach().contiguous()
+            zb = lambda t, ref: t.detach() if t is not None else torch.zeros(ref.shape[0], dtype=ref.dtype, device=ref.device)
+            bcat = None if (bq is None and bk is None and bv is None) else torch.cat((zb(bq, wq), zb(bk, wk), zb(bv, wv)), 0).contiguous()
+            cached = owner._tome_plain_qkv = (key, w, bcat)
+        qkv = F.linear(x, cached[1], cached[2])
+        k = qkv[..., heads * d:2 * heads * d].view(B, N, heads, d).transpose(1, 2)
+        if on_keys is not None:
+            on_keys(k)
+        kb = log_size.reshape(B, N - lead).float()
+        if lead:
+            kb = F.pad(kb, (lead, 0))
+        ctx, _ = _native.frames_attention(qkv, heads, 1, scale, kb, want_diag=False, lead=0, unbiased_queries=lead)
+        return ctx.view(B, N, heads * d), k
     da = d + PAD
     weight, bias = padded_qkv(owner, heads, d, wq, wk, wv, bq, bk, bv)
     qkv = F.linear(x, weight, bias)
