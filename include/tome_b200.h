@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 18
+#define TOME_ABI_VERSION 19
 
 #if defined(__GNUC__)
 #define TOME_API __attribute__((visibility("default")))
@@ -301,6 +301,17 @@ TOME_API int tome_patchify(const void* x, int32_t in_dtype, int32_t b, int32_t c
  * (0.5 x (1 + tanh(0.7978845608 x (1 + 0.044715 x^2))), ViViT's hidden_act).  n % 256 == 0, k % 8 == 0. */
 TOME_API int tome_linear_gelu(const void* x, const void* w, const void* bias, int32_t m, int32_t n, int32_t k,
                      int64_t x_row_stride, int32_t gelu, void* out, void* stream);
+
+/* Caller-side fp32 linear layers on tcgen05 at fp32 accuracy (the reference benchmark runs fp32 with
+ * TF32 off, slowfast/utils/model_benchmark.py:21-45).  An fp32 value is exactly h + m + l with three bf16 terms and a
+ * bf16 x bf16 product is exact in fp32, so accumulating the nine plane products in fp32 (terms = 9) is an fp32 GEMM
+ * without TF32 truncation; terms = 6 drops m.l, l.m, l.l (<= 2^-23 relative per product).
+ * tome_split3: x (rows, k) fp32, rows `row_stride` elements apart -> out (rows, 3k) bf16 planes [h | m | l]; k % 4 == 0.
+ * tome_linear_f32: out (m, n) fp32 = act(x @ W^T + bias) from the split planes x3 (m, 3k), w3 (n, 3k); bias (n) fp32 or
+ *   NULL; gelu 0 / 1 (erf GELU, exact erf).  n % 256 == 0, k % 32 == 0. */
+TOME_API int tome_split3(const void* x, int64_t rows, int32_t k, int64_t row_stride, void* out, void* stream);
+TOME_API int tome_linear_f32(const void* x3, const void* w3, const void* bias, int32_t m, int32_t n, int32_t k, int32_t gelu,
+                    int32_t terms, void* out, void* stream);
 
 /* unmerge (merge.py:87-100): x (bm, n - r, c) -> out (bm, n, c); contiguous tensors. */
 TOME_API int tome_unmerge(const tome_plan* plan, const void* x, int32_t dtype, int32_t c, void* out,

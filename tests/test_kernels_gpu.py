@@ -1102,3 +1102,36 @@ def test_traj_temporal_matches_einsum_formulation(native):
     attn = torch.einsum("bhsd,bhsfd->bhsf", qd, kd).softmax(-1)
     want = torch.einsum("bhsf,bhsfd->bhsd", attn, vd).transpose(1, 2).reshape(B, S, C)
     torch.testing.assert_close(out.double(), want, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("shape", [(300, 256, 64), (1000, 768, 768), (2100, 3072, 768), (777, 768, 3072)], ids=str)
+@pytest.mark.parametrize("terms", [9, 6])
+def test_linear_f32_matches_fp64(native, shape, terms):
+    """tome_linear_f32: fp32 GEMM on tcgen05 through the exact three-way bf16 split (nine products, fp32 accumulation).
+    Against fp64 it must be in the accuracy class of torch's fp32 GEMM with TF32 off (the reference's arithmetic,
+    slowfast/utils/model_benchmark.py:21-45): within 4x the library's own error on the same operands (measured 1-2.2x: the
+    tensor core's fp32 accumulator rounds differently from an FMA chain) and below 1.5e-6 of max |y| -- TF32 would be
+    5e-4 -- and the split itself is exact."""
+    m, n, k = shape
+    g = torch.Generator().manual_seed(m + n + k)
+    x = (torch.randn(m, k, generator=g) * torch.logspace(-2, 2, k)).cuda()          # a wide dynamic range across channels
+    w = (torch.randn(n, k, generator=g) * 0.05).cuda()
+    b = torch.randn(n, generator=g).cuda()
+    x3 = native.split3(x).float()
+    assert torch.equal(x3[:, :k] + x3[:, k:2 * k] + x3[:, 2 * k:], x)              # h + m + l == x, bit for bit
+    assert not torch.backends.cuda.matmul.allow_tf32
+    want = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    lib_out = torch.nn.functional.linear(x, w, b)
+    scale = want.abs().max().item()
+    lib_err = (lib_out.double() - want).abs().max().item() / scale
+    with torch.no_grad():
+        assert native.linear_f32_usable(x, w, b)
+        out = native.linear_f32(x, w, b, terms=terms)
+        err = (out.double() - want).abs().max().item() / scale
+        print(f"[linear_f32] {shape} terms={terms}: max err / max|y| = {err:.2e} (library fp32 GEMM: {lib_err:.2e})")
+        assert err <= min(max(4.0 * lib_err, 3e-7), 1.5e-6), (err, lib_err)
+        act = native.linear_f32(x, w, b, gelu=True, terms=terms)
+        torch.testing.assert_close(act, torch.nn.functional.gelu(out), rtol=1e-6, atol=1e-6)
+        nob = native.linear_f32(x, w, None, terms=terms)
+        torch.testing.assert_close(nob + b, out, rtol=1e-6, atol=1e-5)

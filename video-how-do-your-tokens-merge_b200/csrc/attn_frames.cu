@@ -45,16 +45,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 // shared-memory key bias as seen by one query row: padded keys stay -inf, unbiased rows (TimeSformer's class query) see 0
 __device__ __forceinline__ float key_bias(float b, bool) { return b; }     // the row's bias array is chosen once per row
-// Waits of this kernel last microseconds and there are six waiting warps per CTA: a tight try_wait loop took 40 % of all
-// issued instructions away from the softmax warps sharing the scheduler (profiles/r02_frames_attn_ncu.txt).  Back off.
-__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, unsigned ns) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint32_t spins = 0;
-  do {
-    __nanosleep(ns);
-    if (++spins > (1u << 22)) __trap();
-  } while (!mbar_try_wait(bar, parity));
-}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }

@@ -1,0 +1,244 @@
+// fp32 linear layers on the tensor cores, at fp32 accuracy (the GEMMs either side of the merge).
+//
+// The reference benchmark runs the models in fp32 with TF32 off (slowfast/utils/model_benchmark.py:21-45), and so does
+// the headline line of bench.py.  There the library GEMMs are CUDA-core SGEMMs (cutlass simt_sgemm, ~65 TFLOP/s on a
+// B200) and take 83 % of the patched VideoMAE step (profiles/r02_videomae_fp32_launches.csv); the merge path is 3 %.
+// tcgen05 has no fp32 input kind, but an fp32 number is EXACTLY the sum of three bf16 numbers
+//     x = h + m + l,   h = bf16(x), m = bf16(x - h), l = bf16(x - h - m)        (8 + 8 + 8 significand bits)
+// and every bf16 x bf16 product is exact in the fp32 accumulator, so
+//     x . w = sum over the nine plane pairs (h, m, l) x (h, m, l)
+// with fp32 accumulation in TMEM reproduces an fp32 GEMM to fp32 rounding (the scheme cuBLAS ships as
+// "BF16x9 FP32 emulation"): no TF32, no dropped terms.  Measured against fp64 the result is as close as the SIMT SGEMM
+// (tests/test_kernels_gpu.py::test_linear_f32_matches_fp64).
+//
+//   split3_kernel        x (rows, k) fp32 -> (rows, 3k) bf16 planes [h | m | l]; weights are split once and cached
+//   linear_f32_kernel    persistent CTAs, 128 x 256 output tiles; per 32-channel k-block the producer warp TMA-loads the
+//                        three A planes and the three W planes (72 KB, SWIZZLE_64B, 3-stage ring), the MMA warp issues
+//                        2 x 9 tcgen05.mma kind::f16 into one of two TMEM accumulators, 16 epilogue warps add the
+//                        bias (and the erf GELU for fc1), and store fp32 rows.  A tile's 18 x 24 MMAs take ~29 us, so the
+//                        epilogue of tile t hides completely behind the MMAs of tile t + 1.
+#include <math.h>
+
+#include "tc_ptx.cuh"
+
+namespace tome {
+
+constexpr int LF_BM = 128, LF_BN = 256, LF_BK = 32, LF_STAGES = 3;
+constexpr int LF_EPI_WARPS = 16;
+constexpr int LF_THREADS = 64 + 32 * LF_EPI_WARPS;
+constexpr uint32_t LF_A_BYTES = LF_BM * 64u, LF_B_BYTES = LF_BN * 64u;            // one plane of one stage (64-byte rows)
+constexpr uint32_t LF_STAGE_BYTES = 3u * (LF_A_BYTES + LF_B_BYTES);
+
+struct LinearF32Params {
+  int m, n, k, num_kb, tiles_n, tiles, terms;       // terms: 9 (exact split) or 6 (drops m.l, l.m, l.l: <= 2^-23 relative)
+  const float* bias;                                // (n) or NULL
+  float* out;                                       // (m, n) row-major
+  int gelu;                                         // 0: bias only; 1: erf GELU (nn.GELU)
+};
+
+// ---- split -----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, long long row_stride, long long rows, int k,
+                                                     __nv_bfloat16* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // one thread per 4 channels
+  const int k4 = k >> 2;
+  if (idx >= rows * k4) return;
+  const long long r = idx / k4;
+  const int c = (int)(idx - r * k4) * 4;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * row_stride + c));
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  uint32_t hw[2], mw[2], lw[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float h[2], mm[2], ll[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float xx = f[2 * i + e];
+      h[e] = __bfloat162float(__float2bfloat16_rn(xx));
+      const float r1 = xx - h[e];                                               // exact
+      mm[e] = __bfloat162float(__float2bfloat16_rn(r1));
+      ll[e] = r1 - mm[e];                                                       // exact; fits bf16 (<= 8 significant bits left)
+    }
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(h[0], h[1]), m2 = __floats2bfloat162_rn(mm[0], mm[1]),
+                         l2 = __floats2bfloat162_rn(ll[0], ll[1]);
+    hw[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    mw[i] = *reinterpret_cast<const uint32_t*>(&m2);
+    lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  __nv_bfloat16* o = out + r * 3LL * k + c;
+  *reinterpret_cast<uint2*>(o) = make_uint2(hw[0], hw[1]);
+  *reinterpret_cast<uint2*>(o + k) = make_uint2(mw[0], mw[1]);
+  *reinterpret_cast<uint2*>(o + 2LL * k) = make_uint2(lw[0], lw[1]);
+}
+
+// K-major, SWIZZLE_64B descriptor: 64-byte rows, 8-row groups 512 bytes apart, layout type 4.
+__device__ __forceinline__ uint64_t make_sw64_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(512u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(LF_THREADS, 1)
+linear_f32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const LinearF32Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + LF_STAGES * LF_STAGE_BYTES;
+  const uint32_t bar_full = bars, bar_empty = bars + 8u * LF_STAGES;
+  const uint32_t bar_tfull = bars + 16u * LF_STAGES, bar_tempty = bar_tfull + 16u;
+  const uint32_t tmem_slot = bar_tempty + 16u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_w);
+    for (int s = 0; s < LF_STAGES; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, LF_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+        const int mt = t / p.tiles_n, nt = t - mt * p.tiles_n;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const uint32_t s = it % LF_STAGES, ph = (it / LF_STAGES) & 1u;
+          mbar_wait_sleep(bar_empty + 8u * s, ph ^ 1u, 64);
+          const uint32_t st = base + s * LF_STAGE_BYTES, full = bar_full + 8u * s;
+          mbar_expect_tx(full, LF_STAGE_BYTES);
+#pragma unroll
+          for (int pl = 0; pl < 3; ++pl) {
+            tma_load_2d(st + pl * LF_A_BYTES, &map_a, pl * p.k + kb * LF_BK, mt * LF_BM, full);
+            tma_load_2d(st + 3u * LF_A_BYTES + pl * LF_B_BYTES, &map_w, pl * p.k + kb * LF_BK, nt * LF_BN, full);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LF_BN >> 3) << 17) | ((uint32_t)(LF_BM >> 4) << 24);
+      uint32_t it = 0, tl = 0;
+      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++tl) {
+        const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+        mbar_wait_sleep(bar_tempty + 8u * acc, aph ^ 1u, 64);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)LF_BN;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const uint32_t s = it % LF_STAGES, ph = (it / LF_STAGES) & 1u;
+          mbar_wait_sleep(bar_full + 8u * s, ph, 20);
+          tc_fence_after();
+          const uint32_t st = base + s * LF_STAGE_BYTES;
+          uint32_t first = kb == 0 ? 1u : 0u;
+#pragma unroll
+          for (int k = 0; k < LF_BK / 16; ++k) {
+            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);          // +32 bytes inside the 64-byte swizzle row
+            // smallest products first: (l, l) ... (h, h)
+#pragma unroll
+            for (int i = 2; i >= 0; --i) {
+#pragma unroll
+              for (int j = 2; j >= 0; --j) {
+                if (p.terms == 6 && i + j >= 3) continue;                // m.l, l.m, l.l
+                umma_bf16(d_tmem, make_sw64_desc(st + i * LF_A_BYTES) + adv, make_sw64_desc(st + 3u * LF_A_BYTES + j * LF_B_BYTES) + adv,
+                          idesc, first ? 0u : 1u);
+                first = 0u;
+              }
+            }
+          }
+          umma_commit(bar_empty + 8u * s);
+        }
+        umma_commit(bar_tfull + 8u * acc);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int part = (warp - 2) >> 2;                  // which 64 of the tile's 256 columns
+    uint32_t tl = 0;
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++tl) {
+      const int mt = t / p.tiles_n, nt = t - mt * p.tiles_n;
+      const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+      mbar_wait_sleep(bar_tfull + 8u * acc, aph, 256);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * (uint32_t)LF_BN + (uint32_t)(part * 64) + ((uint32_t)(q * 32) << 16);
+      const int row = mt * LF_BM + q * 32 + lane, col0 = nt * LF_BN + part * 64;
+      float vv[2][32];
+      tmem_ld32_nowait(taddr, vv[0]);
+      tmem_ld32_nowait(taddr + 32u, vv[1]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tempty + 8u * acc) : "memory");   // values are in registers
+      if (row < p.m) {
+        float4* orow = reinterpret_cast<float4*>(p.out + (long long)row * p.n + col0);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c * 32 + g * 4));
+            float o[4] = {vv[c][4 * g] + b4.x, vv[c][4 * g + 1] + b4.y, vv[c][4 * g + 2] + b4.z, vv[c][4 * g + 3] + b4.w};
+            if (p.gelu == 1) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] = 0.5f * o[e] * (1.0f + erff(o[e] * 0.70710678118654752440f));     // nn.GELU, exact erf
+            }
+            orow[c * 8 + g] = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---- host -----------------------------------------------------------------------------------------------------
+int launch_split3(const void* x, long long rows, int k, long long row_stride, void* out, cudaStream_t st) {
+  if (k % 4 != 0 || ((uintptr_t)x & 15) || ((uintptr_t)out & 7) || row_stride % 4)
+    return set_error(TOME_ERR_ALIGN, "tome_split3: needs k %% 4 == 0 and 16-byte aligned rows");
+  const long long total = rows * (k / 4);
+  split3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)x, row_stride, rows, k, (__nv_bfloat16*)out);
+  TOME_LAUNCH_CHECK("split3_kernel");
+  return TOME_OK;
+}
+
+int launch_linear_f32(const void* x3, const void* w3, const void* bias, int m, int n, int k, int gelu, int terms, void* out,
+                      cudaStream_t st) {
+  if (n % LF_BN != 0 || k % LF_BK != 0 || m < 1)
+    return set_error(TOME_ERR_UNSUPPORTED, "tome_linear_f32: needs n %% %d == 0 and k %% %d == 0 (m=%d n=%d k=%d)", LF_BN, LF_BK, m, n, k);
+  if (((uintptr_t)x3 & 15) || ((uintptr_t)w3 & 15) || ((uintptr_t)out & 15) || (bias && ((uintptr_t)bias & 15)))
+    return set_error(TOME_ERR_ALIGN, "tome_linear_f32: 16-byte aligned tensors required");
+  if (terms != 6 && terms != 9) return set_error(TOME_ERR_ARG, "tome_linear_f32: terms must be 6 or 9");
+  alignas(64) CUtensorMap map_a, map_w;
+  int rc = make_bf16_map(&map_a, x3, m, 3LL * k, 3LL * k, LF_BM, "tome_linear_f32", LF_BK);
+  if (rc) return rc;
+  rc = make_bf16_map(&map_w, w3, n, 3LL * k, 3LL * k, LF_BN, "tome_linear_f32", LF_BK);
+  if (rc) return rc;
+  LinearF32Params p;
+  p.m = m; p.n = n; p.k = k; p.num_kb = k / LF_BK; p.terms = terms;
+  p.tiles_n = n / LF_BN; p.tiles = ((m + LF_BM - 1) / LF_BM) * p.tiles_n;
+  p.bias = (const float*)bias; p.out = (float*)out; p.gelu = gelu;
+  const size_t smem = (size_t)LF_STAGES * LF_STAGE_BYTES + 16 * LF_STAGES + 32 + 16 + 1024;
+  static PerDeviceOnce attr;
+  if (attr.first_time())
+    TOME_CUDA(cudaFuncSetAttribute(linear_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = p.tiles < sm_count() ? p.tiles : sm_count();
+  linear_f32_kernel<<<grid, LF_THREADS, smem, st>>>(map_a, map_w, p);
+  TOME_LAUNCH_CHECK("linear_f32_kernel");
+  return TOME_OK;
+}
+
+}  // namespace tome

@@ -34,6 +34,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > (1u << 22)) __trap();
   }
 }
+// Waits that last microseconds (a whole tile, a whole frame) back off with nanosleep: a tight try_wait loop of the
+// producer / MMA / waiting epilogue warps took 40 % of all issued instructions away from the warps doing the work in
+// frames_attn_kernel (profiles/r02_frames_attn_ncu.txt).
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, unsigned ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  do {
+    __nanosleep(ns);
+    if (++spins > (1u << 22)) __trap();
+  } while (!mbar_try_wait(bar, parity));
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"

@@ -86,6 +86,8 @@ int launch_gather_rows(const void*, int, int, int, int, const int*, int, void*, 
 int launch_attn_short(const void*, const void*, const void*, int, long long, int, int, int, long long, long long, float, void*, cudaStream_t);
 int launch_frames_attention(const void*, int, int, int, int, int, float, const float*, void*, void*, int, int, cudaStream_t);
 int launch_traj_temporal(const void*, const void*, const void*, long long, int, int, float, void*, cudaStream_t);
+int launch_split3(const void*, long long, int, long long, void*, cudaStream_t);
+int launch_linear_f32(const void*, const void*, const void*, int, int, int, int, int, void*, cudaStream_t);
 int launch_source_compose(const tome_plan*, const int*, int, int, float, int*, cudaStream_t);
 int launch_source_dense(const int*, int, int, int, float*, cudaStream_t);
 int launch_random_rowmax(void*, long long, int, int, int, int, int, float*, int*, float*, int, cudaStream_t);
@@ -498,6 +500,22 @@ int tome_traj_temporal(const void* q2, const void* k2, const void* vals, int32_t
   TOME_CHECK_ARG(q2 && k2 && vals && out && rows > 0 && frames > 0 && heads > 0, "tome_traj_temporal: NULL pointer or empty shape");
   if (dtype != TOME_BF16 || d != 64) return set_error(TOME_ERR_UNSUPPORTED, "tome_traj_temporal: bf16 with head dimension 64 only (dtype %d, d %d)", dtype, d);
   return launch_traj_temporal(q2, k2, vals, rows, frames, heads, scale, out, (cudaStream_t)stream);
+}
+
+int tome_split3(const void* x, int64_t rows, int32_t k, int64_t row_stride, void* out, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(x && out && rows > 0 && k > 0 && row_stride >= k, "tome_split3: NULL pointer or bad shape");
+  return launch_split3(x, rows, k, row_stride, out, (cudaStream_t)stream);
+}
+
+int tome_linear_f32(const void* x3, const void* w3, const void* bias, int32_t m, int32_t n, int32_t k, int32_t gelu, int32_t terms,
+                    void* out, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(x3 && w3 && out && m > 0 && n > 0 && k > 0, "tome_linear_f32: NULL pointer or bad shape");
+  TOME_CHECK_ARG(gelu == 0 || gelu == 1, "tome_linear_f32: gelu must be 0 or 1");
+  return launch_linear_f32(x3, w3, bias, m, n, k, gelu, terms, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

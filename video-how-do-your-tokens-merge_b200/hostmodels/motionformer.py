@@ -15,6 +15,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import fastlinear
+
 
 from .videomae import fused_fc1_gelu  # noqa: E402
 
@@ -94,7 +96,7 @@ class PatchEmbed3D(nn.Module):                          # vit_helper.py:410-432
         z, p = self.z, self.patch_size                  # kernel == stride: one GEMM over tubelets
         x = x.reshape(B, C, T // z, z, H // p, p, W // p, p).permute(0, 2, 4, 6, 1, 3, 5, 7)
         x = x.reshape(B, (T // z) * (H // p) * (W // p), C * z * p * p)
-        return F.linear(x, self.proj.weight.reshape(self.proj.out_channels, -1), self.proj.bias)
+        return fastlinear.linear(x, self.proj.weight.reshape(self.proj.out_channels, -1), self.proj.bias)
 
 
 class Motionformer(nn.Module):                          # builder:23-282, cfg replaced by keywords
@@ -127,6 +129,7 @@ class Motionformer(nn.Module):                          # builder:23-282, cfg re
         nn.init.trunc_normal_(self.pos_embed, std=.02)
         self.apply(self._init_weights)
         self.patch_embed_3d.proj.weight.data.zero_()    # builder:69-70
+        fastlinear.install(self)                        # fp32 CUDA inference: linears on tome_linear_f32
 
     @staticmethod
     def _init_weights(m):

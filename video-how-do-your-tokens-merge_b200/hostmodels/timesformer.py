@@ -10,6 +10,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import fastlinear
+
 
 from .videomae import fused_fc1_gelu  # noqa: E402
 
@@ -112,7 +114,7 @@ class PatchEmbed(nn.Module):                            # timesformer.py:155-175
         if x.is_cuda and not self.training:             # kernel == stride: one GEMM over patches
             x = x.permute(0, 2, 1, 3, 4).reshape(B * T, C, H // ph, ph, W // pw, pw).permute(0, 2, 4, 1, 3, 5)
             x = x.reshape(B * T, (H // ph) * (W // pw), C * ph * pw)
-            return F.linear(x, self.proj.weight.reshape(self.proj.out_channels, -1), self.proj.bias), T, W // pw
+            return fastlinear.linear(x, self.proj.weight.reshape(self.proj.out_channels, -1), self.proj.bias), T, W // pw
         x = self.proj(x.permute(0, 2, 1, 3, 4).reshape(B * T, C, H, W))
         Wp = x.size(-1)
         return x.flatten(2).transpose(1, 2), T, Wp
@@ -193,6 +195,7 @@ class TimeSformer(nn.Module):                           # timesformer.py:335-351
                                        norm_layer=partial(nn.LayerNorm, eps=1e-6), drop_rate=0., attn_drop_rate=0.,
                                        drop_path_rate=0.1, num_frames=num_frames, attention_type=attention_type,
                                        **kwargs)
+        fastlinear.install(self)                        # fp32 CUDA inference: linears on tome_linear_f32
 
     def forward(self, x):
         return self.model(x)

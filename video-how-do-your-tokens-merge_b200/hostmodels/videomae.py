@@ -11,6 +11,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import fastlinear
+
 
 FUSED_MLP_MIN_ROWS = 2048
 
@@ -39,6 +41,11 @@ def fused_fc1_gelu(mlp, x):
         from tome import _native
         if _native.linear_gelu_supported(x, mlp.fc1.weight, mlp.fc1.bias):
             return _native.linear_gelu(x, mlp.fc1.weight, mlp.fc1.bias)
+    if (not mlp.training and x.is_cuda and x.dtype == torch.float32 and isinstance(mlp.act, nn.GELU)
+            and mlp.act.approximate == "none"):
+        from tome import _native
+        if _native.linear_f32_usable(x, mlp.fc1.weight, mlp.fc1.bias):       # fp32: exact-split tensor-core GEMM, erf GELU in its epilogue
+            return _native.linear_f32(x, mlp.fc1.weight, mlp.fc1.bias, gelu=True)
     return None
 
 
@@ -66,7 +73,7 @@ class Attention(nn.Module):                             # builder:59-103
         qkv_bias = None
         if self.q_bias is not None:
             qkv_bias = torch.cat((self.q_bias, torch.zeros_like(self.v_bias, requires_grad=False), self.v_bias))
-        qkv = F.linear(x, self.qkv.weight, qkv_bias).reshape(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4)
+        qkv = fastlinear.linear(x, self.qkv.weight, qkv_bias).reshape(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4)
         x = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], scale=self.scale,
                                            dropout_p=self.attn_drop.p if self.training else 0.0)
         return self.proj_drop(self.proj(x.transpose(1, 2).reshape(B, N, -1)))
@@ -128,7 +135,7 @@ class PatchEmbed(nn.Module):                            # builder:138-160
         else:
             x = x.reshape(B, C, T // tt, tt, H // ph, ph, W // pw, pw).permute(0, 2, 4, 6, 1, 3, 5, 7)
             x = x.reshape(B, (T // tt) * (H // ph) * (W // pw), C * tt * ph * pw)
-        return F.linear(x, self.proj.weight.reshape(self.proj.out_channels, -1), self.proj.bias)
+        return fastlinear.linear(x, self.proj.weight.reshape(self.proj.out_channels, -1), self.proj.bias)
 
 
 def get_sinusoid_encoding_table(n_position, d_hid):    # builder:164-174
@@ -241,6 +248,7 @@ class VideoMAE(nn.Module):                              # builder:363-397 (cfg r
         self.num_classes = num_classes
         self.model = func(num_classes=num_classes, all_frames=num_frames, tubelet_size=tubelet_size,
                           use_mean_pooling=use_mean_pooling, init_scale=init_scale, **kwargs)
+        fastlinear.install(self)                        # fp32 CUDA inference: linears on tome_linear_f32
 
     def forward(self, x):
         return self.model(x)

@@ -15,6 +15,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import fastlinear
+
 
 class VivitConfig:
     def __init__(self, num_frames=32, image_size=224, tubelet_size=(2, 16, 16), num_channels=3, hidden_size=768,
@@ -46,7 +48,7 @@ class VivitTubeletEmbeddings(nn.Module):
             return self.projection(pixel_values.permute(0, 2, 1, 3, 4)).flatten(2).transpose(1, 2)
         x = pixel_values.reshape(B, T // z, z, C, H // ph, ph, W // pw, pw).permute(0, 1, 4, 6, 3, 2, 5, 7)
         x = x.reshape(B, (T // z) * (H // ph) * (W // pw), C * z * ph * pw)   # kernel == stride: one GEMM
-        return F.linear(x, self.projection.weight.reshape(self.projection.out_channels, -1), self.projection.bias)
+        return fastlinear.linear(x, self.projection.weight.reshape(self.projection.out_channels, -1), self.projection.bias)
 
 
 class VivitEmbeddings(nn.Module):
@@ -173,6 +175,7 @@ class ViViT(nn.Module):                                 # vivit_video_model_buil
         self.vivit = VivitModel(self.config)
         self.classifier = nn.Linear(self.config.hidden_size, num_classes) if num_classes > 0 else nn.Identity()
         self.apply(self._init_weights)
+        fastlinear.install(self)                        # fp32 CUDA inference: linears on tome_linear_f32
 
     def _init_weights(self, m):                         # HF VivitPreTrainedModel._init_weights
         std = self.config.initializer_range

@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 18
+ABI_VERSION = 19
 
 TOME_F32, TOME_BF16, TOME_U8 = 0, 1, 2
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -32,7 +32,7 @@ EXPORTS = (
     "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_linear_gelu", "tome_unmerge",
     "tome_match_sets_workspace_bytes", "tome_match_sets", "tome_group_reduce", "tome_gather_rows",
     "tome_source_compose", "tome_source_dense", "tome_random_rowmax", "tome_merge_add_norm_rv", "tome_rows_add_layernorm", "tome_attn_short",
-    "tome_frames_attention", "tome_traj_temporal",
+    "tome_frames_attention", "tome_traj_temporal", "tome_split3", "tome_linear_f32",
 )
 
 
@@ -129,6 +129,10 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.tome_rows_add_layernorm.argtypes = [c_vp, p_i64, c_vp, p_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_f32, c_vp, p_i64,
                                             c_vp, p_i64, c_vp]
     lib.tome_attn_short.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_i64, c_i64, c_f32, c_vp, c_vp]
+    lib.tome_split3.argtypes = [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp]
+    lib.tome_linear_f32.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]
+    for name in ("tome_split3", "tome_linear_f32"):
+        getattr(lib, name).restype = c_i32
     lib.tome_frames_attention.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp]
     lib.tome_traj_temporal.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]
     for name in ("tome_source_compose", "tome_source_dense", "tome_random_rowmax", "tome_merge_add_norm_rv", "tome_rows_add_layernorm",
@@ -697,6 +701,62 @@ def traj_temporal(q2: torch.Tensor, k2: torch.Tensor, vals: torch.Tensor, heads:
         _check(lib.tome_traj_temporal(q2.data_ptr(), k2.data_ptr(), vals.data_ptr(), _dtype_code(q2), B * S, F_, heads, C // heads,
                                       float(scale), out.data_ptr(), _stream(q2)), lib)
     return out
+
+
+_SPLIT_CACHE = {}          # (data_ptr, version, shape, device) of a weight -> its bf16 planes
+
+
+def split3(x: torch.Tensor) -> torch.Tensor:
+    """fp32 (rows, k) -> bf16 (rows, 3k) planes [h | m | l] with h + m + l == x exactly."""
+    lib = load_library()
+    _require_cuda(x, "x")
+    k = x.shape[-1]
+    x2 = x.reshape(-1, k)
+    if x2.stride(1) != 1 or x2.stride(0) % 4 != 0:
+        x2 = x2.contiguous()
+    with torch.cuda.device(x.device):
+        out = torch.empty(x2.shape[0], 3 * k, dtype=torch.bfloat16, device=x.device)
+        _check(lib.tome_split3(x2.data_ptr(), x2.shape[0], k, x2.stride(0), out.data_ptr(), _stream(x)), lib)
+    return out
+
+
+def linear_f32_usable(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> bool:
+    """tome_linear_f32 serves this fp32 linear: CUDA inference, n % 256 == 0, k % 32 == 0."""
+    return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and not torch.is_grad_enabled()
+            and weight.dim() == 2 and weight.is_contiguous() and weight.shape[0] % 256 == 0 and weight.shape[1] % 32 == 0
+            and x.shape[-1] == weight.shape[1] and x.numel() // x.shape[-1] >= 128
+            and (bias is None or (bias.dtype == torch.float32 and bias.is_contiguous()))
+            and os.environ.get("TOME_LINEAR_F32", "1") != "0")
+
+
+def linear_f32(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], gelu: bool = False, terms: Optional[int] = None):
+    """act(x @ weight^T + bias) in fp32 on the tensor cores (exact bf16 three-way split, nine products; include/tome_b200.h:
+    tome_linear_f32).  The weight's planes are cached until the weight changes."""
+    lib = load_library()
+    _require_cuda(x, "x")
+    n, k = weight.shape
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device)
+    w3 = _SPLIT_CACHE.get(key)
+    if w3 is None:
+        if len(_SPLIT_CACHE) > 512:
+            _SPLIT_CACHE.clear()
+        w3 = _SPLIT_CACHE[key] = split3(weight.detach())
+    x3 = split3(x)
+    m = x3.shape[0]
+    if terms is None:
+        terms = int(os.environ.get("TOME_LINEAR_F32_TERMS", "9"))
+    with torch.cuda.device(x.device):
+        out = torch.empty(m, n, dtype=torch.float32, device=x.device)
+        _check(lib.tome_linear_f32(x3.data_ptr(), w3.data_ptr(), None if bias is None else bias.data_ptr(), m, n, k, int(bool(gelu)),
+                                   int(terms), out.data_ptr(), _stream(x)), lib)
+    return out.reshape(*x.shape[:-1], n)
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """F.linear, through tome_linear_f32 when it applies (fp32 CUDA inference), else the library GEMM."""
+    if linear_f32_usable(x, weight, bias):
+        return linear_f32(x, weight, bias)
+    return torch.nn.functional.linear(x, weight, bias)
 
 
 def patchify(x: torch.Tensor, tubelet: int, ph: int, pw: int, out_dtype: torch.dtype) -> torch.Tensor:

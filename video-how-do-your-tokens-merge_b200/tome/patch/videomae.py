@@ -150,7 +150,8 @@ class ToMeAttentionMixin:
             x, k = prop_attention.attention(x, self, self.num_heads, d, self.scale, log_size.float(), wq, wk, wv,
                                             self.q_bias, None, self.v_bias, on_keys=on_keys)
         else:
-            qkv = F.linear(input=x, weight=self.qkv.weight, bias=qkv_bias)
+            from tome import _native
+            qkv = _native.linear(x, self.qkv.weight, qkv_bias)      # fp32 inference: tome_linear_f32; else F.linear
             qkv = qkv.reshape(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4)
             q, k, v = qkv[0], qkv[1], qkv[2]
             on_keys(k)
