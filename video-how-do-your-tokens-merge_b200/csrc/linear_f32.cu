@@ -14,9 +14,12 @@
 //   split3_kernel        x (rows, k) fp32 -> (rows, 3k) bf16 planes [h | m | l]; weights are split once and cached
 //   linear_f32_kernel    persistent CTAs, 128 x 256 output tiles; per 32-channel k-block the producer warp TMA-loads the
 //                        three A planes and the three W planes (72 KB, SWIZZLE_64B, 3-stage ring), the MMA warp issues
-//                        2 x 9 tcgen05.mma kind::f16 into one of two TMEM accumulators, 16 epilogue warps add the
-//                        bias (and the erf GELU for fc1), and store fp32 rows.  A tile's 18 x 24 MMAs take ~29 us, so the
-//                        epilogue of tile t hides completely behind the MMAs of tile t + 1.
+//                        2 x 9 tcgen05.mma kind::f16 into one of two TMEM accumulators.  The tensor core's fp32
+//                        accumulator does not round like an FMA chain: the error of a single long accumulation grows
+//                        linearly with k (4x the SGEMM's at k = 3072).  So an accumulator only ever holds 256 channels
+//                        (8 k-blocks, 144 MMAs); the eight epilogue warps pull each finished chunk out of TMEM and add it,
+//                        round-to-nearest, to the tile's running sum in registers while the next chunk accumulates in the
+//                        other TMEM buffer; bias (and the erf GELU for fc1) at the end, fp32 rows stored directly.
 #include <math.h>
 
 #include "tc_ptx.cuh"
@@ -24,7 +27,8 @@
 namespace tome {
 
 constexpr int LF_BM = 128, LF_BN = 256, LF_BK = 32, LF_STAGES = 3;
-constexpr int LF_EPI_WARPS = 16;
+constexpr int LF_EPI_WARPS = 8;                       // two per TMEM lane quarter, 128 columns each
+constexpr int LF_CHUNK_KB = 8;                        // k-blocks (256 channels) accumulated in TMEM before the sum moves to registers
 constexpr int LF_THREADS = 64 + 32 * LF_EPI_WARPS;
 constexpr uint32_t LF_A_BYTES = LF_BM * 64u, LF_B_BYTES = LF_BN * 64u;            // one plane of one stage (64-byte rows)
 constexpr uint32_t LF_STAGE_BYTES = 3u * (LF_A_BYTES + LF_B_BYTES);
@@ -128,65 +132,80 @@ linear_f32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LF_BN >> 3) << 17) | ((uint32_t)(LF_BM >> 4) << 24);
-      uint32_t it = 0, tl = 0;
-      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++tl) {
-        const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
-        mbar_wait_sleep(bar_tempty + 8u * acc, aph ^ 1u, 64);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (uint32_t)LF_BN;
-        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-          const uint32_t s = it % LF_STAGES, ph = (it / LF_STAGES) & 1u;
-          mbar_wait_sleep(bar_full + 8u * s, ph, 20);
+      uint32_t it = 0, cl = 0;                                   // k-block and chunk counters across tiles
+      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+        for (int kb0 = 0; kb0 < p.num_kb; kb0 += LF_CHUNK_KB, ++cl) {
+          const uint32_t acc = cl & 1u, aph = (cl >> 1) & 1u;
+          mbar_wait_sleep(bar_tempty + 8u * acc, aph ^ 1u, 64);   // the epilogue has pulled the previous chunk out of this buffer
           tc_fence_after();
-          const uint32_t st = base + s * LF_STAGE_BYTES;
-          uint32_t first = kb == 0 ? 1u : 0u;
+          const uint32_t d_tmem = tmem_base + acc * (uint32_t)LF_BN;
+          const int kb1 = min(p.num_kb, kb0 + LF_CHUNK_KB);
+          for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            const uint32_t s = it % LF_STAGES, ph = (it / LF_STAGES) & 1u;
+            mbar_wait_sleep(bar_full + 8u * s, ph, 20);
+            tc_fence_after();
+            const uint32_t st = base + s * LF_STAGE_BYTES;
+            uint32_t first = kb == kb0 ? 1u : 0u;
 #pragma unroll
-          for (int k = 0; k < LF_BK / 16; ++k) {
-            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);          // +32 bytes inside the 64-byte swizzle row
-            // smallest products first: (l, l) ... (h, h)
+            for (int k = 0; k < LF_BK / 16; ++k) {
+              const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);        // +32 bytes inside the 64-byte swizzle row
+              // smallest products first: (l, l) ... (h, h)
 #pragma unroll
-            for (int i = 2; i >= 0; --i) {
+              for (int i = 2; i >= 0; --i) {
 #pragma unroll
-              for (int j = 2; j >= 0; --j) {
-                if (p.terms == 6 && i + j >= 3) continue;                // m.l, l.m, l.l
-                umma_bf16(d_tmem, make_sw64_desc(st + i * LF_A_BYTES) + adv, make_sw64_desc(st + 3u * LF_A_BYTES + j * LF_B_BYTES) + adv,
-                          idesc, first ? 0u : 1u);
-                first = 0u;
+                for (int j = 2; j >= 0; --j) {
+                  if (p.terms == 6 && i + j >= 3) continue;              // m.l, l.m, l.l
+                  umma_bf16(d_tmem, make_sw64_desc(st + i * LF_A_BYTES) + adv,
+                            make_sw64_desc(st + 3u * LF_A_BYTES + j * LF_B_BYTES) + adv, idesc, first ? 0u : 1u);
+                  first = 0u;
+                }
               }
             }
+            umma_commit(bar_empty + 8u * s);
           }
-          umma_commit(bar_empty + 8u * s);
+          umma_commit(bar_tfull + 8u * acc);
         }
-        umma_commit(bar_tfull + 8u * acc);
       }
     }
   } else {
     const int q = warp & 3;
-    const int part = (warp - 2) >> 2;                  // which 64 of the tile's 256 columns
-    uint32_t tl = 0;
-    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++tl) {
+    const int part = (warp - 2) >> 2;                  // which 128 of the tile's 256 columns
+    uint32_t cl = 0;
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
       const int mt = t / p.tiles_n, nt = t - mt * p.tiles_n;
-      const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
-      mbar_wait_sleep(bar_tfull + 8u * acc, aph, 256);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * (uint32_t)LF_BN + (uint32_t)(part * 64) + ((uint32_t)(q * 32) << 16);
-      const int row = mt * LF_BM + q * 32 + lane, col0 = nt * LF_BN + part * 64;
-      float vv[2][32];
-      tmem_ld32_nowait(taddr, vv[0]);
-      tmem_ld32_nowait(taddr + 32u, vv[1]);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tempty + 8u * acc) : "memory");   // values are in registers
+      float sum[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int e = 0; e < 32; ++e) sum[c][e] = 0.f;
+      for (int kb0 = 0; kb0 < p.num_kb; kb0 += LF_CHUNK_KB, ++cl) {
+        const uint32_t acc = cl & 1u, aph = (cl >> 1) & 1u;
+        mbar_wait_sleep(bar_tfull + 8u * acc, aph, 128);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * (uint32_t)LF_BN + (uint32_t)(part * 128) + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+        for (int c = 0; c < 4; c += 2) {
+          float va[32], vb[32];
+          tmem_ld32_nowait(taddr + (uint32_t)(32 * c), va);
+          tmem_ld32_nowait(taddr + (uint32_t)(32 * c + 32), vb);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int e = 0; e < 32; ++e) { sum[c][e] += va[e]; sum[c + 1][e] += vb[e]; }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tempty + 8u * acc) : "memory");
+      }
+      const int row = mt * LF_BM + q * 32 + lane, col0 = nt * LF_BN + part * 128;
       if (row < p.m) {
         float4* orow = reinterpret_cast<float4*>(p.out + (long long)row * p.n + col0);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < 4; ++c) {
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c * 32 + g * 4));
-            float o[4] = {vv[c][4 * g] + b4.x, vv[c][4 * g + 1] + b4.y, vv[c][4 * g + 2] + b4.z, vv[c][4 * g + 3] + b4.w};
+            float o[4] = {sum[c][4 * g] + b4.x, sum[c][4 * g + 1] + b4.y, sum[c][4 * g + 2] + b4.z, sum[c][4 * g + 3] + b4.w};
             if (p.gelu == 1) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) o[e] = 0.5f * o[e] * (1.0f + erff(o[e] * 0.70710678118654752440f));     // nn.GELU, exact erf

@@ -10,6 +10,7 @@ from __future__ import annotations
 import ctypes
 import math
 import os
+import weakref
 from typing import Optional, Tuple
 
 import torch
@@ -703,7 +704,20 @@ def traj_temporal(q2: torch.Tensor, k2: torch.Tensor, vals: torch.Tensor, heads:
     return out
 
 
-_SPLIT_CACHE = {}          # (data_ptr, version, shape, device) of a weight -> its bf16 planes
+_SPLIT_CACHE = {}          # id(weight) -> (weak reference to the weight, (version, address), its bf16 planes)
+
+
+def _cached_planes(weight: torch.Tensor) -> torch.Tensor:
+    """The weight's split planes, valid while this very tensor object is alive and unmodified.  Keyed by identity with a
+    liveness check, never by address alone: a freed model's weight address is reused by the next model's weights."""
+    k = id(weight)
+    stamp = (weight._version, weight.data_ptr())
+    hit = _SPLIT_CACHE.get(k)
+    if hit is not None and hit[0]() is weight and hit[1] == stamp:
+        return hit[2]
+    w3 = split3(weight.detach())
+    _SPLIT_CACHE[k] = (weakref.ref(weight, lambda _r, k=k: _SPLIT_CACHE.pop(k, None)), stamp, w3)
+    return w3
 
 
 def split3(x: torch.Tensor) -> torch.Tensor:
@@ -735,12 +749,7 @@ def linear_f32(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     lib = load_library()
     _require_cuda(x, "x")
     n, k = weight.shape
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device)
-    w3 = _SPLIT_CACHE.get(key)
-    if w3 is None:
-        if len(_SPLIT_CACHE) > 512:
-            _SPLIT_CACHE.clear()
-        w3 = _SPLIT_CACHE[key] = split3(weight.detach())
+    w3 = _cached_planes(weight)
     x3 = split3(x)
     m = x3.shape[0]
     if terms is None:
