@@ -320,6 +320,10 @@ def workload_config(args, cpu=False):
         "token_schedule": [n for n, _ in token_schedule(args)],
         "parallelism": f"dp{args.gpus}",
         "cuda_graph": not args.no_graph,
+        "fp32_arithmetic": "fp32 model, TF32 off everywhere (torch default, as slowfast/utils/model_benchmark.py runs it); the "
+                           "host model's linear layers run on tcgen05 through the exact three-way bf16 split (nine products, fp32 "
+                           "accumulation: tome_linear_f32, fp32-GEMM accuracy, tests/test_kernels_gpu.py::test_linear_f32_matches_fp64); "
+                           "TOME_LINEAR_F32=0 gives the library SGEMMs",
         "l2": "each step reads a different resident input batch (4 rotate) and the model's weights (344 MB fp32 / "
               "172 MB bf16): working set > 126 MB L2",
     }
@@ -499,6 +503,38 @@ def micro_kernels(args, device, dtype):
                               "library_gemm_plus_gelu_us": t_mean,
                               "kernels": "linear_gelu_kernel (persistent tcgen05 GEMM 128x256x64, TMEM double-buffered, "
                                          "bias + erf GELU + TMA store in the epilogue)"}
+    if dtype == torch.float32:
+        # caller-side tensor-core kernel of the fp32 model: the QKV projection as an exact-split (nine bf16 plane products)
+        # tcgen05 GEMM, against the library's fp32 GEMM (TF32 off) it replaces.  `achieved` counts the nine MMA products.
+        tf_peak = float(peaks.get("bf16_tflops", 1662.0))
+        xm = [torch.randn(bm * n, c, device=device, generator=g) for _ in range(3)]
+        wq = torch.randn(3 * c, c, device=device, generator=g) * c ** -0.5
+        bq = torch.zeros(3 * c, device=device)
+        fl = 2.0 * bm * n * c * 3 * c
+        with torch.no_grad():
+            f_mean, f_med = graph_time([lambda i=i: _native.linear_f32(xm[i % 3], wq, bq) for i in range(3)])
+            s_mean2, _ = graph_time([lambda i=i: _native.split3(xm[i % 3]) for i in range(3)])
+            t_mean, _ = graph_time([lambda i=i: torch.nn.functional.linear(xm[i % 3], wq, bq) for i in range(3)])
+        mma_us = f_mean - s_mean2
+        res["linear_f32"] = {"us_mean": f_mean, "us_median": f_med, "split_us": s_mean2, "algorithmic_gflop": fl / 1e9,
+                             "fp32_tflops_incl_split": fl / (f_mean * 1e-6) / 1e12, "library_fp32_gemm_us": t_mean,
+                             "library_fp32_tflops": fl / (t_mean * 1e-6) / 1e12,
+                             "roofline": {"bound": "tensor", "achieved": 9 * fl / (mma_us * 1e-6) / 1e12, "peak": tf_peak,
+                                          "unit": "TFLOP/s", "frac": 9 * fl / (mma_us * 1e-6) / 1e12 / tf_peak,
+                                          "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)",
+                                          "note": "nine bf16 plane products per fp32 product; time = linear_f32 minus the activation split"},
+                             "kernels": "split3_kernel + linear_f32_kernel (persistent tcgen05 GEMM 128x256x32 on the exact three-way "
+                                        "bf16 split, 256-channel accumulation chunks summed in registers)"}
+    if dtype == torch.bfloat16:
+        # Motionformer's space attention (config 4) at its layer-0 shape: per-frame softmax attention with the key bias
+        qk = [torch.randn(bm, 1 + 8 * 196, 3 * c, device=device, generator=g).to(dtype) for _ in range(3)]
+        kb = torch.rand(bm, 8 * 196, device=device, generator=g)
+        a_mean, a_med = graph_time([lambda i=i: _native.frames_attention(qk[i % 3], 12, 8, 0.125, kb) for i in range(3)])
+        afl = 4.0 * bm * 12 * (8 * 196) ** 2 * 64
+        res["frames_attention"] = {"us_mean": a_mean, "us_median": a_med, "algorithmic_gflop": afl / 1e9,
+                                   "tflops_algorithmic": afl / (a_mean * 1e-6) / 1e12,
+                                   "kernels": "frames_attn_kernel (tcgen05 / TMEM / TMA per-frame attention, Motionformer layer 0: "
+                                              "8 frames x 196 keys, 12 heads)"}
     xs = [torch.randn(bm, n, c, device=device, dtype=dtype, generator=g) for _ in range(12)]
     ys = [torch.empty_like(xs[0]) for _ in range(12)]
     c_mean, _ = graph_time([lambda i=i: ys[i].copy_(xs[i]) for i in range(12)])
@@ -716,6 +752,7 @@ def run_ours(args):
         hp, op = pair(head), pair(other)
         name_h, name_o = ("f32", "bf16") if args.dtype == "fp32" else ("bf16", "f32")
         kern_lg = (kernels or {}).get("linear_gelu") or (kernels_other or {}).get("linear_gelu")
+        kern_lf = (kernels or {}).get("linear_f32") or (kernels_other or {}).get("linear_f32")
         line = {
             "metric": "clips_per_sec", "value": hp["value"], "unit": "clips/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": hp["ms_per_step"], "higher_is_better": True,
@@ -732,6 +769,8 @@ def run_ours(args):
             "roofline_" + name_o: roofline_other,
             # the caller-side tensor-core kernel (fc1 + GELU of the bf16 model), the largest single kernel of libtome_b200 there
             "roofline_tensor": (dict(kern_lg["roofline"], kernel=kern_lg["kernels"], us_mean=kern_lg["us_mean"]) if kern_lg else None),
+            # the same for the fp32 model: its linear layers as exact-split tensor-core GEMMs
+            "roofline_tensor_f32": (dict(kern_lf["roofline"], kernel=kern_lf["kernels"], us_mean=kern_lf["us_mean"]) if kern_lf else None),
             "kernels": kernels, "kernels_" + name_o: kernels_other, "cpu_baseline": cpu_baseline,
             "match_algo": "auto" if not args.match_algo else args.match_algo,
             "top1_sample": head["top1"],
