@@ -1135,3 +1135,39 @@ def test_linear_f32_matches_fp64(native, shape, terms):
         torch.testing.assert_close(act, torch.nn.functional.gelu(out), rtol=1e-6, atol=1e-6)
         nob = native.linear_f32(x, w, None, terms=terms)
         torch.testing.assert_close(nob + b, out, rtol=1e-6, atol=1e-5)
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("with_bias", [False, True], ids=["plain", "prop_attn"])
+@pytest.mark.parametrize("N", [1568, 468, 196, 100])
+def test_attention_f32_matches_fp64(native, N, with_bias):
+    """tome_attention_f32 (exact-split tcgen05 flash attention) against fp64 softmax attention; its error must be in the class of
+    torch's own fp32 attention on the same operands (tome/patch/videomae.py:58-68 in the fp32 models)."""
+    g = torch.Generator().manual_seed(N)
+    B, h, d = 2, 3, 64
+    C = h * d
+    qkv = (torch.randn(B, N, 3 * C, generator=g) * 2.0).cuda()
+    bias = (torch.randint(1, 8, (B, N), generator=g).float().log()).cuda() if with_bias else None
+    q, k, v = qkv.double().reshape(B, N, 3, h, d).permute(2, 0, 3, 1, 4)
+    sc = (q @ k.transpose(-1, -2)) * d ** -0.5
+    if bias is not None:
+        sc = sc + bias.double()[:, None, None, :]
+    want = (sc.softmax(-1) @ v).transpose(1, 2).reshape(B, N, C)
+    qf, kf, vf = qkv.reshape(B, N, 3, h, d).permute(2, 0, 3, 1, 4)
+    mask = None if bias is None else bias[:, None, None, :].expand(B, 1, N, N)
+    lib = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf, attn_mask=mask, scale=d ** -0.5).transpose(1, 2).reshape(B, N, C)
+    scale = want.abs().max().item()
+    lib_err = (lib.double() - want).abs().max().item() / scale
+    with torch.no_grad():
+        assert native.attention_f32_usable(qkv, h, bias)
+        out = native.attention_f32(qkv, h, d ** -0.5, bias)
+    err = (out.double() - want).abs().max().item() / scale
+    print(f"[attention_f32] N={N} bias={with_bias}: max err / max|y| = {err:.2e} (torch fp32 attention: {lib_err:.2e})")
+    assert err <= max(4.0 * lib_err, 1e-6), (err, lib_err)
+    if with_bias:                                             # unbiased leading query (TimeSformer's class token)
+        with torch.no_grad():
+            out1 = native.attention_f32(qkv, h, d ** -0.5, bias, unbiased_queries=1)
+        sc0 = (q @ k.transpose(-1, -2)) * d ** -0.5
+        want0 = (sc0.softmax(-1) @ v).transpose(1, 2).reshape(B, N, C)
+        torch.testing.assert_close(out1[:, 0].double(), want0[:, 0], rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(out1[:, 1:], out[:, 1:])

@@ -1,0 +1,287 @@
+// fp32 attention on the tensor cores, at fp32 accuracy: softmax(scale * q k^T + key bias) v for the fp32
+// models -- the reference benchmark runs fp32 with TF32 off (slowfast/utils/model_benchmark.py:21-45) -- where torch's
+// fused fp32 attention was 42 % of the patched VideoMAE step once the linear layers had moved to tcgen05
+// (profiles/r02_videomae_fp32_launches_after.csv).  Same idea as linear_f32.cu: q, k, v arrive as exact three-way bf16
+// splits (h + m + l == x, tome_split3 of the QKV GEMM's output) and every bf16 product is exact in the fp32 accumulator.
+//     S = Q K^T   six plane products  (h.h, h.m, m.h, m.m, h.l, l.h : what is dropped is <= 3 * 2^-24 |q||k|)
+//     P           fp32 softmax numerators, split exactly into three bf16 planes in registers
+//     O = P V     six plane products, V consumed as TMA wrote it (rows = keys: MN-major B operand)
+// Flash-style: one CTA per (128 queries, head, clip) walks the keys in blocks of 64 with a running maximum; the block's
+// scores are read out of TMEM ONCE (64 values per thread), the block's P V lands in its own TMEM columns and is folded
+// into the row's fp32 accumulator in registers with the usual rescale, so no accumulator is ever rescaled in TMEM.
+//   warp 0      TMA producer: Q planes once, then K / V planes of each key block (2-stage ring, SWIZZLE_128B);
+//   warp 1      MMA issuer: S(j + 1) is issued before waiting for P(j), so it runs beside the softmax of block j;
+//   warps 2-5   one thread per query row: scores -> max / exp2 / sum -> three P planes into swizzled shared memory ->
+//               accumulate O.
+#include "tc_ptx.cuh"
+
+namespace tome {
+
+constexpr int AF_BM = 128, AF_BKV = 64, AF_D = 64, AF_THREADS = 192;
+constexpr uint32_t AF_QP = AF_BM * 128u;            // one Q / P plane: 128 rows x 128 bytes
+constexpr uint32_t AF_KP = AF_BKV * 128u;           // one K / V plane of a key block: 64 rows x 128 bytes
+constexpr uint32_t AF_STAGE = 6u * AF_KP;           // K h,m,l | V h,m,l
+
+struct AfParams {
+  int B, N, heads, nblk, nobias_q;
+  float scale_log2e;
+  const float* bias;                                // (B, N) log size per key, or NULL
+  float* out;                                       // (B, N, heads * 64)
+};
+
+__device__ __forceinline__ float af_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void af_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ uint64_t af_desc_mn(uint32_t smem_addr) {     // MN-major SWIZZLE_128B (see attn_frames.cu)
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(1024u >> 4) << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t af_pack(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(AF_THREADS, 1)
+attn_f32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const AfParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int C = p.heads * AF_D, C3 = 3 * C;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sm_q = base, sm_kv = sm_q + 3u * AF_QP, sm_p = sm_kv + 2u * AF_STAGE, bars = sm_p + 3u * AF_QP;
+  const uint32_t bar_q = bars, bar_full = bars + 8, bar_empty = bars + 24, bar_s = bars + 40, bar_sfree = bars + 56,
+                 bar_p = bars + 72, bar_o = bars + 80, tmem_slot = bars + 88;
+  uint8_t* p_gen = gen + (sm_p - base);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_q);
+    prefetch_tensormap(&map_kv);
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1);
+      mbar_init(bar_s + 8u * s, 1); mbar_init(bar_sfree + 8u * s, 128);
+    }
+    mbar_init(bar_p, 128); mbar_init(bar_o, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int row0 = b * p.N;
+  const int nb = p.nblk;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_q, 3u * AF_QP);
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) tma_load_2d(sm_q + pl * AF_QP, &map_q, pl * C3 + h * AF_D, row0 + qt * AF_BM, bar_q);
+      for (int j = 0; j < nb; ++j) {
+        const uint32_t s = (uint32_t)(j & 1), k = (uint32_t)(j >> 1);
+        if (k >= 1) mbar_wait_sleep(bar_empty + 8u * s, (k - 1) & 1u, 64);
+        const uint32_t st = sm_kv + s * AF_STAGE, full = bar_full + 8u * s;
+        mbar_expect_tx(full, AF_STAGE);
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+          tma_load_2d(st + pl * AF_KP, &map_kv, pl * C3 + C + h * AF_D, row0 + j * AF_BKV, full);
+          tma_load_2d(st + (3 + pl) * AF_KP, &map_kv, pl * C3 + 2 * C + h * AF_D, row0 + j * AF_BKV, full);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AF_BKV >> 3) << 17) | ((uint32_t)(AF_BM >> 4) << 24);
+      const uint32_t idesc_o = idesc_s | (1u << 16);                        // B MN-major, N = 64 as well
+      // plane pairs (query / P plane, key / V plane): h.h, h.m, m.h, m.m, h.l, l.h
+      const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
+      auto issue_s = [&](int j) {
+        const uint32_t s = (uint32_t)(j & 1), k = (uint32_t)(j >> 1);
+        mbar_wait_sleep(bar_full + 8u * s, k & 1u, 32);
+        if (k >= 1) mbar_wait_sleep(bar_sfree + 8u * s, (k - 1) & 1u, 32);    // the softmax has pulled the previous S out of this buffer
+        tc_fence_after();
+        const uint32_t st = sm_kv + s * AF_STAGE, d = tmem_base + s * 64u;
+        uint32_t first = 1u;
+#pragma unroll
+        for (int t = 5; t >= 0; --t) {                                       // smallest products first
+#pragma unroll
+          for (int ks = 0; ks < AF_D / 16; ++ks) {
+            umma_bf16(d, make_sw128_desc(sm_q + pa[t] * AF_QP + 32u * ks), make_sw128_desc(st + pb[t] * AF_KP + 32u * ks), idesc_s,
+                      first ? 0u : 1u);
+            first = 0u;
+          }
+        }
+        umma_commit(bar_s + 8u * s);
+      };
+      mbar_wait_sleep(bar_q, 0, 64);
+      issue_s(0);
+      for (int j = 0; j < nb; ++j) {
+        if (j + 1 < nb) issue_s(j + 1);
+        const uint32_t s = (uint32_t)(j & 1);
+        mbar_wait_sleep(bar_p, (uint32_t)(j & 1), 32);
+        tc_fence_after();
+        const uint32_t st = sm_kv + s * AF_STAGE, d = tmem_base + 128u;
+        uint32_t first = 1u;
+#pragma unroll
+        for (int t = 5; t >= 0; --t) {
+#pragma unroll
+          for (int ks = 0; ks < AF_BKV / 16; ++ks) {
+            umma_bf16(d, make_sw128_desc(sm_p + pa[t] * AF_QP + 32u * ks), af_desc_mn(st + (3 + pb[t]) * AF_KP + 2048u * ks), idesc_o,
+                      first ? 0u : 1u);
+            first = 0u;
+          }
+        }
+        umma_commit(bar_o);
+        umma_commit(bar_empty + 8u * s);
+      }
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const int s_idx = qt * AF_BM + row;                        // query token within the clip
+    const bool live = s_idx < p.N;
+    const bool biased = p.bias != nullptr && s_idx >= p.nobias_q;
+    const uint32_t tlane = (uint32_t)(q4 * 32) << 16;
+    const float* brow = p.bias ? p.bias + (long long)b * p.N : nullptr;
+    const float LOG2E = 1.4426950408889634f;
+    float m = -INFINITY, l = 0.f;
+    float oacc[AF_D];
+#pragma unroll
+    for (int e = 0; e < AF_D; ++e) oacc[e] = 0.f;
+    auto fold_o = [&]() {                                      // O_acc += the finished P V block (TMEM columns 128..191)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + tlane + 128u + 32u * c, v);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) oacc[32 * c + e] += v[e];
+      }
+    };
+    for (int j = 0; j < nb; ++j) {
+      const uint32_t sb = (uint32_t)(j & 1), k = (uint32_t)(j >> 1);
+      mbar_wait_sleep(bar_s + 8u * sb, k & 1u, 32);
+      tc_fence_after();
+      float t[AF_BKV];
+      tmem_ld32_nowait(tmem_base + tlane + sb * 64u, reinterpret_cast<float(&)[32]>(t[0]));
+      tmem_ld32_nowait(tmem_base + tlane + sb * 64u + 32u, reinterpret_cast<float(&)[32]>(t[32]));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      af_arrive(bar_sfree + 8u * sb);
+      // logits in log2 units, key bias, padding
+      const int key0 = j * AF_BKV;
+      float bmax = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < AF_BKV; e += 4) {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (biased && key0 + e + 3 < p.N) b4 = __ldg(reinterpret_cast<const float4*>(brow + key0 + e));
+        else if (biased) {
+          b4.x = key0 + e < p.N ? __ldg(brow + key0 + e) : 0.f;
+          b4.y = key0 + e + 1 < p.N ? __ldg(brow + key0 + e + 1) : 0.f;
+          b4.z = key0 + e + 2 < p.N ? __ldg(brow + key0 + e + 2) : 0.f;
+        }
+        t[e] = fmaf(t[e], p.scale_log2e, b4.x * LOG2E);
+        t[e + 1] = fmaf(t[e + 1], p.scale_log2e, b4.y * LOG2E);
+        t[e + 2] = fmaf(t[e + 2], p.scale_log2e, b4.z * LOG2E);
+        t[e + 3] = fmaf(t[e + 3], p.scale_log2e, b4.w * LOG2E);
+      }
+      if (key0 + AF_BKV > p.N) {                               // last block: keys beyond the clip
+#pragma unroll
+        for (int e = 0; e < AF_BKV; ++e) if (key0 + e >= p.N) t[e] = -INFINITY;
+      }
+#pragma unroll
+      for (int e = 0; e < AF_BKV; e += 4) bmax = fmaxf(bmax, fmaxf(fmaxf(t[e], t[e + 1]), fmaxf(t[e + 2], t[e + 3])));
+      const float m_new = fmaxf(m, bmax);
+      const float alpha = af_ex2(m - m_new);                   // 0 on the first block (m = -inf)
+      if (j > 0) {                                             // P V of the previous block: also frees the P tile
+        mbar_wait_sleep(bar_o, (uint32_t)((j - 1) & 1), 32);
+        tc_fence_after();
+        fold_o();
+      }
+#pragma unroll
+      for (int e = 0; e < AF_D; ++e) oacc[e] *= alpha;
+      l *= alpha;
+      m = m_new;
+      // probabilities, split exactly into three bf16 planes, into the K-major SWIZZLE_128B P tiles
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int ci = 0; ci < AF_BKV / 8; ++ci) {
+        uint32_t wh[4], wm[4], wl[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float p0 = af_ex2(t[8 * ci + 2 * i] - m_new), p1 = af_ex2(t[8 * ci + 2 * i + 1] - m_new);
+          l0 += p0; l1 += p1;
+          const float h0 = __bfloat162float(__float2bfloat16_rn(p0)), h1 = __bfloat162float(__float2bfloat16_rn(p1));
+          const float r0 = p0 - h0, r1 = p1 - h1;
+          const float m0 = __bfloat162float(__float2bfloat16_rn(r0)), m1 = __bfloat162float(__float2bfloat16_rn(r1));
+          wh[i] = af_pack(h0, h1);
+          wm[i] = af_pack(m0, m1);
+          wl[i] = af_pack(r0 - m0, r1 - m1);
+        }
+        uint8_t* dst = p_gen + (size_t)row * 128 + (((uint32_t)ci ^ ((uint32_t)row & 7u)) << 4);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+        *reinterpret_cast<uint4*>(dst + AF_QP) = make_uint4(wm[0], wm[1], wm[2], wm[3]);
+        *reinterpret_cast<uint4*>(dst + 2 * AF_QP) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+      }
+      l += l0 + l1;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();                                       // the O columns were read above: P V (j) may overwrite them
+      af_arrive(bar_p);
+    }
+    mbar_wait_sleep(bar_o, (uint32_t)((nb - 1) & 1), 32);
+    tc_fence_after();
+    fold_o();
+    if (live) {
+      const float inv = 1.0f / l;
+      float4* dst = reinterpret_cast<float4*>(p.out + ((long long)b * p.N + s_idx) * C + h * AF_D);
+#pragma unroll
+      for (int e = 0; e < AF_D / 4; ++e)
+        dst[e] = make_float4(oacc[4 * e] * inv, oacc[4 * e + 1] * inv, oacc[4 * e + 2] * inv, oacc[4 * e + 3] * inv);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+int launch_attention_f32(const void* qkv3, int B, int N, int heads, float scale, const float* bias, int nobias_q, void* out,
+                         cudaStream_t st) {
+  if (((uintptr_t)qkv3 & 15) || ((uintptr_t)out & 15) || (bias && ((uintptr_t)bias & 15)))
+    return set_error(TOME_ERR_ALIGN, "tome_attention_f32: buffers must be 16-byte aligned");
+  if (bias && (N & 3)) return set_error(TOME_ERR_ALIGN, "tome_attention_f32: a key bias needs n %% 4 == 0 rows of 16 bytes (n=%d)", N);
+  AfParams p;
+  p.B = B; p.N = N; p.heads = heads; p.nblk = (N + AF_BKV - 1) / AF_BKV; p.nobias_q = nobias_q;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.bias = bias; p.out = (float*)out;
+  const long long rows = (long long)B * N, cols = 9LL * heads * AF_D;
+  alignas(64) CUtensorMap map_q, map_kv;
+  int rc = make_bf16_map(&map_q, qkv3, rows, cols, cols, AF_BM, "tome_attention_f32");
+  if (rc) return rc;
+  rc = make_bf16_map(&map_kv, qkv3, rows, cols, cols, AF_BKV, "tome_attention_f32");
+  if (rc) return rc;
+  const size_t smem = 1024 + 3 * AF_QP + 2 * AF_STAGE + 3 * AF_QP + 128;
+  static PerDeviceOnce once;
+  if (once.first_time()) TOME_CUDA(cudaFuncSetAttribute(attn_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((N + AF_BM - 1) / AF_BM, heads, B);
+  if (grid.z > 65535) return set_error(TOME_ERR_UNSUPPORTED, "tome_attention_f32: batch %d > 65535", B);
+  attn_f32_kernel<<<grid, AF_THREADS, smem, st>>>(map_q, map_kv, p);
+  TOME_LAUNCH_CHECK("attn_f32_kernel");
+  return TOME_OK;
+}
+
+}  // namespace tome

@@ -73,7 +73,13 @@ class Attention(nn.Module):                             # builder:59-103
         qkv_bias = None
         if self.q_bias is not None:
             qkv_bias = torch.cat((self.q_bias, torch.zeros_like(self.v_bias, requires_grad=False), self.v_bias))
-        qkv = fastlinear.linear(x, self.qkv.weight, qkv_bias).reshape(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4)
+        qkv_flat = fastlinear.linear(x, self.qkv.weight, qkv_bias)
+        if x.is_cuda and x.dtype == torch.float32 and not self.training:
+            from tome import _native
+            if qkv_flat.shape[-1] == 3 * 64 * self.num_heads and _native.attention_f32_usable(qkv_flat, self.num_heads):
+                # fp32 inference: exact-split flash attention on tcgen05 (tome_attention_f32)
+                return self.proj_drop(self.proj(_native.attention_f32(qkv_flat, self.num_heads, self.scale)))
+        qkv = qkv_flat.reshape(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4)
         x = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], scale=self.scale,
                                            dropout_p=self.attn_drop.p if self.training else 0.0)
         return self.proj_drop(self.proj(x.transpose(1, 2).reshape(B, N, -1)))

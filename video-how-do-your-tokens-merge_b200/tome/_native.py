@@ -18,7 +18,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 19
+ABI_VERSION = 20
 
 TOME_F32, TOME_BF16, TOME_U8 = 0, 1, 2
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -33,7 +33,7 @@ EXPORTS = (
     "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_linear_gelu", "tome_unmerge",
     "tome_match_sets_workspace_bytes", "tome_match_sets", "tome_group_reduce", "tome_gather_rows",
     "tome_source_compose", "tome_source_dense", "tome_random_rowmax", "tome_merge_add_norm_rv", "tome_rows_add_layernorm", "tome_attn_short",
-    "tome_frames_attention", "tome_traj_temporal", "tome_split3", "tome_linear_f32",
+    "tome_frames_attention", "tome_traj_temporal", "tome_split3", "tome_linear_f32", "tome_attention_f32",
 )
 
 
@@ -132,7 +132,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.tome_attn_short.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_i64, c_i64, c_f32, c_vp, c_vp]
     lib.tome_split3.argtypes = [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp]
     lib.tome_linear_f32.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]
-    for name in ("tome_split3", "tome_linear_f32"):
+    lib.tome_attention_f32.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_i32, c_vp, c_vp]
+    for name in ("tome_split3", "tome_linear_f32", "tome_attention_f32"):
         getattr(lib, name).restype = c_i32
     lib.tome_frames_attention.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp]
     lib.tome_traj_temporal.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]
@@ -759,6 +760,32 @@ def linear_f32(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
         _check(lib.tome_linear_f32(x3.data_ptr(), w3.data_ptr(), None if bias is None else bias.data_ptr(), m, n, k, int(bool(gelu)),
                                    int(terms), out.data_ptr(), _stream(x)), lib)
     return out.reshape(*x.shape[:-1], n)
+
+
+def attention_f32_usable(qkv: torch.Tensor, heads: int, key_bias: Optional[torch.Tensor] = None) -> bool:
+    """tome_attention_f32 serves this (B, N, 3 * heads * 64) fp32 QKV tensor: CUDA inference, head dimension 64."""
+    return (qkv.is_cuda and qkv.dtype == torch.float32 and not torch.is_grad_enabled() and qkv.dim() == 3
+            and qkv.shape[2] == 3 * 64 * heads and qkv.shape[1] >= 64 and (key_bias is None or qkv.shape[1] % 4 == 0)
+            and os.environ.get("TOME_ATTENTION_F32", "1") != "0")
+
+
+def attention_f32(qkv: torch.Tensor, heads: int, scale: float, key_bias: Optional[torch.Tensor] = None,
+                  unbiased_queries: int = 0) -> torch.Tensor:
+    """softmax(scale q k^T + key_bias) v in fp32 accuracy on the tensor cores, from the QKV GEMM's output
+    (B, N, 3 * heads * 64) (channel order (3, heads, 64)); returns (B, N, heads * 64).  ``key_bias`` (B, N) fp32."""
+    lib = load_library()
+    _require_cuda(qkv, "qkv")
+    B, N, c3 = qkv.shape
+    x3 = split3(qkv.reshape(B * N, c3))
+    bp = None
+    if key_bias is not None:
+        key_bias = key_bias.to(torch.float32).reshape(B, N).contiguous()
+        bp = key_bias.data_ptr()
+    with torch.cuda.device(qkv.device):
+        out = torch.empty(B, N, c3 // 3, dtype=torch.float32, device=qkv.device)
+        _check(lib.tome_attention_f32(x3.data_ptr(), B, N, heads, c3 // 3 // heads, float(scale), bp, int(unbiased_queries),
+                                      out.data_ptr(), _stream(qkv)), lib)
+    return out
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:

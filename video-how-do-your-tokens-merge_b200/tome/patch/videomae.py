@@ -151,18 +151,21 @@ class ToMeAttentionMixin:
                                             self.q_bias, None, self.v_bias, on_keys=on_keys)
         else:
             from tome import _native
-            qkv = _native.linear(x, self.qkv.weight, qkv_bias)      # fp32 inference: tome_linear_f32; else F.linear
-            qkv = qkv.reshape(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4)
+            qkv_flat = _native.linear(x, self.qkv.weight, qkv_bias)      # fp32 inference: tome_linear_f32; else F.linear
+            qkv = qkv_flat.reshape(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4)
             q, k, v = qkv[0], qkv[1], qkv[2]
             on_keys(k)
-            bias = None
-            if size is not None:                 # proportional attention (videomae.py:62-63)
-                if log_size is None:
-                    log_size = size.log()
-                bias = log_size[:, None, None, :, 0].to(q.dtype).expand(B, 1, N, N)
-            drop = self.attn_drop.p if self.training else 0.0
-            x = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, dropout_p=drop, scale=self.scale)
-            x = x.transpose(1, 2).reshape(B, N, -1)
+            if size is not None and log_size is None:   # proportional attention (videomae.py:62-63)
+                log_size = size.log()
+            kb = None if size is None else log_size[..., 0]
+            if q.shape[-1] == 64 and _native.attention_f32_usable(qkv_flat, self.num_heads, kb):
+                # fp32 inference: exact-split flash attention on tcgen05, key bias taken directly
+                x = _native.attention_f32(qkv_flat, self.num_heads, self.scale, kb)
+            else:
+                bias = None if size is None else log_size[:, None, None, :, 0].to(q.dtype).expand(B, 1, N, N)
+                drop = self.attn_drop.p if self.training else 0.0
+                x = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, dropout_p=drop, scale=self.scale)
+                x = x.transpose(1, 2).reshape(B, N, -1)
         x = self.proj_drop(self.proj(x))
 
         if head_aggregation == 'mean':
