@@ -11,13 +11,16 @@
 // into the row's fp32 accumulator in registers with the usual rescale, so no accumulator is ever rescaled in TMEM.
 //   warp 0      TMA producer: Q planes once, then K / V planes of each key block (2-stage ring, SWIZZLE_128B);
 //   warp 1      MMA issuer: S(j + 1) is issued before waiting for P(j), so it runs beside the softmax of block j;
-//   warps 2-5   one thread per query row: scores -> max / exp2 / sum -> three P planes into swizzled shared memory ->
-//               accumulate O.
+//   warps 2-9   TWO threads per query row, 32 key columns of the block and 32 channels of O each (with one thread per row
+//               the single softmax warp per scheduler was the critical path: 657 us at N = 1568): scores -> row maximum
+//               (halves exchanged through shared memory, one named barrier per block) -> exp2 / sum -> three P planes into
+//               swizzled shared memory -> accumulate O.
 #include "tc_ptx.cuh"
 
 namespace tome {
 
-constexpr int AF_BM = 128, AF_BKV = 64, AF_D = 64, AF_THREADS = 192;
+constexpr int AF_BM = 128, AF_BKV = 64, AF_D = 64, AF_THREADS = 320;      // TMA, MMA, 2 x 4 softmax warps
+constexpr int AF_SM = 256;                                                  // softmax threads: two per query row
 constexpr uint32_t AF_QP = AF_BM * 128u;            // one Q / P plane: 128 rows x 128 bytes
 constexpr uint32_t AF_KP = AF_BKV * 128u;           // one K / V plane of a key block: 64 rows x 128 bytes
 constexpr uint32_t AF_STAGE = 6u * AF_KP;           // K h,m,l | V h,m,l
@@ -58,8 +61,9 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sm_q = base, sm_kv = sm_q + 3u * AF_QP, sm_p = sm_kv + 2u * AF_STAGE, bars = sm_p + 3u * AF_QP;
-  const uint32_t bar_q = bars, bar_full = bars + 8, bar_empty = bars + 24, bar_s = bars + 40, bar_sfree = bars + 56,
-                 bar_p = bars + 72, bar_o = bars + 80, tmem_slot = bars + 88;
+  const uint32_t bar_q = bars, bar_kfull = bars + 8, bar_kempty = bars + 24, bar_s = bars + 40, bar_sfree = bars + 56,
+                 bar_p = bars + 72, bar_o = bars + 80, tmem_slot = bars + 88, bar_vfull = bars + 96, bar_vempty = bars + 112,
+                 sm_xch = bars + 128;
   uint8_t* p_gen = gen + (sm_p - base);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
@@ -68,10 +72,11 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     prefetch_tensormap(&map_kv);
     mbar_init(bar_q, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1);
-      mbar_init(bar_s + 8u * s, 1); mbar_init(bar_sfree + 8u * s, 128);
+      mbar_init(bar_kfull + 8u * s, 1); mbar_init(bar_kempty + 8u * s, 1);
+      mbar_init(bar_vfull + 8u * s, 1); mbar_init(bar_vempty + 8u * s, 1);
+      mbar_init(bar_s + 8u * s, 1); mbar_init(bar_sfree + 8u * s, AF_SM);
     }
-    mbar_init(bar_p, 128); mbar_init(bar_o, 1);
+    mbar_init(bar_p, AF_SM); mbar_init(bar_o, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -90,16 +95,20 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_expect_tx(bar_q, 3u * AF_QP);
 #pragma unroll
       for (int pl = 0; pl < 3; ++pl) tma_load_2d(sm_q + pl * AF_QP, &map_q, pl * C3 + h * AF_D, row0 + qt * AF_BM, bar_q);
+      // K of a stage is free as soon as S (j) has been computed, V only after P V (j): separate barriers, so the K of block
+      // j + 2 is requested a whole iteration before it is needed (one barrier pair per stage exposed ~1.5 us of load
+      // latency per block: 637 us at N = 1568, tensor pipe 31 % busy -- profiles/r02_attn_f32_ncu.txt)
       for (int j = 0; j < nb; ++j) {
         const uint32_t s = (uint32_t)(j & 1), k = (uint32_t)(j >> 1);
-        if (k >= 1) mbar_wait_sleep(bar_empty + 8u * s, (k - 1) & 1u, 64);
-        const uint32_t st = sm_kv + s * AF_STAGE, full = bar_full + 8u * s;
-        mbar_expect_tx(full, AF_STAGE);
+        const uint32_t st = sm_kv + s * AF_STAGE;
+        if (k >= 1) mbar_wait_sleep(bar_kempty + 8u * s, (k - 1) & 1u, 32);
+        mbar_expect_tx(bar_kfull + 8u * s, 3u * AF_KP);
 #pragma unroll
-        for (int pl = 0; pl < 3; ++pl) {
-          tma_load_2d(st + pl * AF_KP, &map_kv, pl * C3 + C + h * AF_D, row0 + j * AF_BKV, full);
-          tma_load_2d(st + (3 + pl) * AF_KP, &map_kv, pl * C3 + 2 * C + h * AF_D, row0 + j * AF_BKV, full);
-        }
+        for (int pl = 0; pl < 3; ++pl) tma_load_2d(st + pl * AF_KP, &map_kv, pl * C3 + C + h * AF_D, row0 + j * AF_BKV, bar_kfull + 8u * s);
+        if (k >= 1) mbar_wait_sleep(bar_vempty + 8u * s, (k - 1) & 1u, 32);
+        mbar_expect_tx(bar_vfull + 8u * s, 3u * AF_KP);
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) tma_load_2d(st + (3 + pl) * AF_KP, &map_kv, pl * C3 + 2 * C + h * AF_D, row0 + j * AF_BKV, bar_vfull + 8u * s);
       }
     }
   } else if (warp == 1) {
@@ -108,83 +117,92 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const uint32_t idesc_o = idesc_s | (1u << 16);                        // B MN-major, N = 64 as well
       // plane pairs (query / P plane, key / V plane): h.h, h.m, m.h, m.m, h.l, l.h
       const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
+      // descriptors once: the issuing thread is a single lane and a freshly built descriptor pair cost ~16 instructions per
+      // MMA, as long as the MMA itself (24 per stage)
+      uint64_t dq[3], dp[3], dk[2][3], dv[2][3];
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) {
+        dq[pl] = make_sw128_desc(sm_q + pl * AF_QP);
+        dp[pl] = make_sw128_desc(sm_p + pl * AF_QP);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          dk[s][pl] = make_sw128_desc(sm_kv + s * AF_STAGE + pl * AF_KP);
+          dv[s][pl] = af_desc_mn(sm_kv + s * AF_STAGE + (3 + pl) * AF_KP);
+        }
+      }
       auto issue_s = [&](int j) {
         const uint32_t s = (uint32_t)(j & 1), k = (uint32_t)(j >> 1);
-        mbar_wait_sleep(bar_full + 8u * s, k & 1u, 32);
-        if (k >= 1) mbar_wait_sleep(bar_sfree + 8u * s, (k - 1) & 1u, 32);    // the softmax has pulled the previous S out of this buffer
+        mbar_wait(bar_kfull + 8u * s, k & 1u);
+        if (k >= 1) mbar_wait(bar_sfree + 8u * s, (k - 1) & 1u);             // the softmax has pulled the previous S out of this buffer
         tc_fence_after();
-        const uint32_t st = sm_kv + s * AF_STAGE, d = tmem_base + s * 64u;
+        const uint32_t d = tmem_base + s * 64u;
         uint32_t first = 1u;
 #pragma unroll
         for (int t = 5; t >= 0; --t) {                                       // smallest products first
 #pragma unroll
-          for (int ks = 0; ks < AF_D / 16; ++ks) {
-            umma_bf16(d, make_sw128_desc(sm_q + pa[t] * AF_QP + 32u * ks), make_sw128_desc(st + pb[t] * AF_KP + 32u * ks), idesc_s,
-                      first ? 0u : 1u);
+          for (int ks = 0; ks < AF_D / 16; ++ks) {                           // +32 bytes inside the swizzle row per k-step
+            umma_bf16(d, dq[pa[t]] + (uint64_t)(2 * ks), (s ? dk[1][pb[t]] : dk[0][pb[t]]) + (uint64_t)(2 * ks), idesc_s, first ? 0u : 1u);
             first = 0u;
           }
         }
         umma_commit(bar_s + 8u * s);
+        umma_commit(bar_kempty + 8u * s);
       };
-      mbar_wait_sleep(bar_q, 0, 64);
+      mbar_wait(bar_q, 0);
       issue_s(0);
       for (int j = 0; j < nb; ++j) {
         if (j + 1 < nb) issue_s(j + 1);
         const uint32_t s = (uint32_t)(j & 1);
-        mbar_wait_sleep(bar_p, (uint32_t)(j & 1), 32);
+        mbar_wait(bar_vfull + 8u * s, (uint32_t)((j >> 1) & 1));
+        mbar_wait(bar_p, (uint32_t)(j & 1));
         tc_fence_after();
-        const uint32_t st = sm_kv + s * AF_STAGE, d = tmem_base + 128u;
+        const uint32_t d = tmem_base + 128u;
         uint32_t first = 1u;
 #pragma unroll
         for (int t = 5; t >= 0; --t) {
 #pragma unroll
-          for (int ks = 0; ks < AF_BKV / 16; ++ks) {
-            umma_bf16(d, make_sw128_desc(sm_p + pa[t] * AF_QP + 32u * ks), af_desc_mn(st + (3 + pb[t]) * AF_KP + 2048u * ks), idesc_o,
-                      first ? 0u : 1u);
+          for (int ks = 0; ks < AF_BKV / 16; ++ks) {                         // P: +32 bytes per k-step; V: 16 keys = 2048 bytes
+            umma_bf16(d, dp[pa[t]] + (uint64_t)(2 * ks), (s ? dv[1][pb[t]] : dv[0][pb[t]]) + (uint64_t)(128 * ks), idesc_o, first ? 0u : 1u);
             first = 0u;
           }
         }
         umma_commit(bar_o);
-        umma_commit(bar_empty + 8u * s);
+        umma_commit(bar_vempty + 8u * s);
       }
     }
   } else {
     const int q4 = warp & 3;
+    const int half = (warp - 2) >> 2;                          // which 32 key columns of a block / 32 channels of O
     const int row = q4 * 32 + lane;
     const int s_idx = qt * AF_BM + row;                        // query token within the clip
     const bool live = s_idx < p.N;
     const bool biased = p.bias != nullptr && s_idx >= p.nobias_q;
     const uint32_t tlane = (uint32_t)(q4 * 32) << 16;
     const float* brow = p.bias ? p.bias + (long long)b * p.N : nullptr;
+    float* xch = reinterpret_cast<float*>(gen + (sm_xch - base));          // [2 blocks][2 halves][128 rows]
     const float LOG2E = 1.4426950408889634f;
     float m = -INFINITY, l = 0.f;
-    float oacc[AF_D];
+    float oacc[32];
 #pragma unroll
-    for (int e = 0; e < AF_D; ++e) oacc[e] = 0.f;
+    for (int e = 0; e < 32; ++e) oacc[e] = 0.f;
     auto fold_o = [&]() {                                      // O_acc += the finished P V block (TMEM columns 128..191)
+      float v[32];
+      tmem_ld32(tmem_base + tlane + 128u + 32u * half, v);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float v[32];
-        tmem_ld32(tmem_base + tlane + 128u + 32u * c, v);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) oacc[32 * c + e] += v[e];
-      }
+      for (int e = 0; e < 32; ++e) oacc[e] += v[e];
     };
     for (int j = 0; j < nb; ++j) {
       const uint32_t sb = (uint32_t)(j & 1), k = (uint32_t)(j >> 1);
-      mbar_wait_sleep(bar_s + 8u * sb, k & 1u, 32);
+      mbar_wait(bar_s + 8u * sb, k & 1u);
       tc_fence_after();
-      float t[AF_BKV];
-      tmem_ld32_nowait(tmem_base + tlane + sb * 64u, reinterpret_cast<float(&)[32]>(t[0]));
-      tmem_ld32_nowait(tmem_base + tlane + sb * 64u + 32u, reinterpret_cast<float(&)[32]>(t[32]));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float t[32];
+      tmem_ld32(tmem_base + tlane + sb * 64u + 32u * half, t);
       tc_fence_before();
       af_arrive(bar_sfree + 8u * sb);
       // logits in log2 units, key bias, padding
-      const int key0 = j * AF_BKV;
-      float bmax = -INFINITY;
+      const int key0 = j * AF_BKV + 32 * half;
 #pragma unroll
-      for (int e = 0; e < AF_BKV; e += 4) {
+      for (int e = 0; e < 32; e += 4) {
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (biased && key0 + e + 3 < p.N) b4 = __ldg(reinterpret_cast<const float4*>(brow + key0 + e));
         else if (biased) {
@@ -197,57 +215,70 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         t[e + 2] = fmaf(t[e + 2], p.scale_log2e, b4.z * LOG2E);
         t[e + 3] = fmaf(t[e + 3], p.scale_log2e, b4.w * LOG2E);
       }
-      if (key0 + AF_BKV > p.N) {                               // last block: keys beyond the clip
+      if (key0 + 32 > p.N) {                                   // last block: keys beyond the clip
 #pragma unroll
-        for (int e = 0; e < AF_BKV; ++e) if (key0 + e >= p.N) t[e] = -INFINITY;
+        for (int e = 0; e < 32; ++e) if (key0 + e >= p.N) t[e] = -INFINITY;
       }
+      float bmax = -INFINITY;
 #pragma unroll
-      for (int e = 0; e < AF_BKV; e += 4) bmax = fmaxf(bmax, fmaxf(fmaxf(t[e], t[e + 1]), fmaxf(t[e + 2], t[e + 3])));
-      const float m_new = fmaxf(m, bmax);
+      for (int e = 0; e < 32; e += 4) bmax = fmaxf(bmax, fmaxf(fmaxf(t[e], t[e + 1]), fmaxf(t[e + 2], t[e + 3])));
+      // the row's other half
+      xch[(sb * 2 + half) * AF_BM + row] = bmax;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      bmax = fmaxf(bmax, xch[(sb * 2 + (half ^ 1)) * AF_BM + row]);
+      const float m_new = fmaxf(m, bmax);                      // finite: the first half of every block holds a real key
       const float alpha = af_ex2(m - m_new);                   // 0 on the first block (m = -inf)
+      // probabilities, split exactly into three bf16 planes -- computed BEFORE waiting for the previous block's P V (which
+      // still reads the P tile), so the exponentials run beside those MMAs and only the stores wait
+      float l0 = 0.f, l1 = 0.f;
+      uint32_t wh[16], wm[16], wl[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float p0 = af_ex2(t[2 * i] - m_new), p1 = af_ex2(t[2 * i + 1] - m_new);
+        l0 += p0; l1 += p1;
+        const float h0 = __bfloat162float(__float2bfloat16_rn(p0)), h1 = __bfloat162float(__float2bfloat16_rn(p1));
+        const float r0 = p0 - h0, r1 = p1 - h1;
+        const float m0 = __bfloat162float(__float2bfloat16_rn(r0)), m1 = __bfloat162float(__float2bfloat16_rn(r1));
+        wh[i] = af_pack(h0, h1);
+        wm[i] = af_pack(m0, m1);
+        wl[i] = af_pack(r0 - m0, r1 - m1);
+      }
       if (j > 0) {                                             // P V of the previous block: also frees the P tile
-        mbar_wait_sleep(bar_o, (uint32_t)((j - 1) & 1), 32);
+        mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
         tc_fence_after();
         fold_o();
       }
 #pragma unroll
-      for (int e = 0; e < AF_D; ++e) oacc[e] *= alpha;
+      for (int e = 0; e < 32; ++e) oacc[e] *= alpha;
       l *= alpha;
       m = m_new;
-      // probabilities, split exactly into three bf16 planes, into the K-major SWIZZLE_128B P tiles
-      float l0 = 0.f, l1 = 0.f;
+      // K-major SWIZZLE_128B P tiles: row = 128 bytes, 16-byte chunk index (4 * half + cc) XOR (row % 8)
 #pragma unroll
-      for (int ci = 0; ci < AF_BKV / 8; ++ci) {
-        uint32_t wh[4], wm[4], wl[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float p0 = af_ex2(t[8 * ci + 2 * i] - m_new), p1 = af_ex2(t[8 * ci + 2 * i + 1] - m_new);
-          l0 += p0; l1 += p1;
-          const float h0 = __bfloat162float(__float2bfloat16_rn(p0)), h1 = __bfloat162float(__float2bfloat16_rn(p1));
-          const float r0 = p0 - h0, r1 = p1 - h1;
-          const float m0 = __bfloat162float(__float2bfloat16_rn(r0)), m1 = __bfloat162float(__float2bfloat16_rn(r1));
-          wh[i] = af_pack(h0, h1);
-          wm[i] = af_pack(m0, m1);
-          wl[i] = af_pack(r0 - m0, r1 - m1);
-        }
-        uint8_t* dst = p_gen + (size_t)row * 128 + (((uint32_t)ci ^ ((uint32_t)row & 7u)) << 4);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
-        *reinterpret_cast<uint4*>(dst + AF_QP) = make_uint4(wm[0], wm[1], wm[2], wm[3]);
-        *reinterpret_cast<uint4*>(dst + 2 * AF_QP) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+      for (int cc = 0; cc < 4; ++cc) {
+        const uint32_t ci = (uint32_t)(4 * half + cc);
+        uint8_t* dst = p_gen + (size_t)row * 128 + ((ci ^ ((uint32_t)row & 7u)) << 4);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(wh[4 * cc], wh[4 * cc + 1], wh[4 * cc + 2], wh[4 * cc + 3]);
+        *reinterpret_cast<uint4*>(dst + AF_QP) = make_uint4(wm[4 * cc], wm[4 * cc + 1], wm[4 * cc + 2], wm[4 * cc + 3]);
+        *reinterpret_cast<uint4*>(dst + 2 * AF_QP) = make_uint4(wl[4 * cc], wl[4 * cc + 1], wl[4 * cc + 2], wl[4 * cc + 3]);
       }
       l += l0 + l1;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();                                       // the O columns were read above: P V (j) may overwrite them
       af_arrive(bar_p);
     }
-    mbar_wait_sleep(bar_o, (uint32_t)((nb - 1) & 1), 32);
+    mbar_wait(bar_o, (uint32_t)((nb - 1) & 1));
     tc_fence_after();
     fold_o();
+    // the row sum of both halves (same running maximum, so the partial sums simply add)
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    xch[half * AF_BM + row] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l += xch[(half ^ 1) * AF_BM + row];
     if (live) {
       const float inv = 1.0f / l;
-      float4* dst = reinterpret_cast<float4*>(p.out + ((long long)b * p.N + s_idx) * C + h * AF_D);
+      float4* dst = reinterpret_cast<float4*>(p.out + ((long long)b * p.N + s_idx) * C + h * AF_D + 32 * half);
 #pragma unroll
-      for (int e = 0; e < AF_D / 4; ++e)
+      for (int e = 0; e < 8; ++e)
         dst[e] = make_float4(oacc[4 * e] * inv, oacc[4 * e + 1] * inv, oacc[4 * e + 2] * inv, oacc[4 * e + 3] * inv);
     }
   }
@@ -274,7 +305,7 @@ int launch_attention_f32(const void* qkv3, int B, int N, int heads, float scale,
   if (rc) return rc;
   rc = make_bf16_map(&map_kv, qkv3, rows, cols, cols, AF_BKV, "tome_attention_f32");
   if (rc) return rc;
-  const size_t smem = 1024 + 3 * AF_QP + 2 * AF_STAGE + 3 * AF_QP + 128;
+  const size_t smem = 1024 + 3 * AF_QP + 2 * AF_STAGE + 3 * AF_QP + 128 + 4 * AF_BM * sizeof(float);
   static PerDeviceOnce once;
   if (once.first_time()) TOME_CUDA(cudaFuncSetAttribute(attn_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((N + AF_BM - 1) / AF_BM, heads, B);
