@@ -317,7 +317,7 @@ TOME_API int tome_linear_f32(const void* x3, const void* w3, const void* bias, i
  * in the fp32 models): out (b, n, heads*64) fp32 = softmax(scale * q k^T + key_bias) v per head, flash-style (running
  * maximum over 64-key blocks), from qkv3 = tome_split3 of the QKV GEMM's output viewed (b*n, 3*heads*64), i.e.
  * (b*n, 9*heads*64) bf16 planes [h: q k v | m: q k v | l: q k v].  Six plane products for q k^T and six for P V with
- * P split exactly in registers.  key_bias (b, n) fp32 or NULL (n % 4 == 0 then); the first `unbiased_queries` queries
+ * P split exactly in registers.  key_bias (b, n) fp32 or NULL; the first `unbiased_queries` queries
  * take no bias (TimeSformer's class token). */
 TOME_API int tome_attention_f32(const void* qkv3, int32_t b, int32_t n, int32_t heads, int32_t d, float scale,
                        const float* key_bias, int32_t unbiased_queries, void* out, void* stream);

@@ -179,6 +179,7 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const bool biased = p.bias != nullptr && s_idx >= p.nobias_q;
     const uint32_t tlane = (uint32_t)(q4 * 32) << 16;
     const float* brow = p.bias ? p.bias + (long long)b * p.N : nullptr;
+    const bool bias_vec = (p.N & 3) == 0;
     float* xch = reinterpret_cast<float*>(gen + (sm_xch - base));          // [2 blocks][2 halves][128 rows]
     const float LOG2E = 1.4426950408889634f;
     float m = -INFINITY, l = 0.f;
@@ -204,8 +205,10 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
       for (int e = 0; e < 32; e += 4) {
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (biased && key0 + e + 3 < p.N) b4 = __ldg(reinterpret_cast<const float4*>(brow + key0 + e));
-        else if (biased) {
+        if (biased && bias_vec && key0 + e + 3 < p.N) b4 = __ldg(reinterpret_cast<const float4*>(brow + key0 + e));
+        else if (biased && key0 + e + 3 < p.N) {               // rows of the bias are not 16-byte aligned (n % 4 != 0)
+          b4.x = __ldg(brow + key0 + e); b4.y = __ldg(brow + key0 + e + 1); b4.z = __ldg(brow + key0 + e + 2); b4.w = __ldg(brow + key0 + e + 3);
+        } else if (biased) {
           b4.x = key0 + e < p.N ? __ldg(brow + key0 + e) : 0.f;
           b4.y = key0 + e + 1 < p.N ? __ldg(brow + key0 + e + 1) : 0.f;
           b4.z = key0 + e + 2 < p.N ? __ldg(brow + key0 + e + 2) : 0.f;
@@ -294,7 +297,6 @@ int launch_attention_f32(const void* qkv3, int B, int N, int heads, float scale,
                          cudaStream_t st) {
   if (((uintptr_t)qkv3 & 15) || ((uintptr_t)out & 15) || (bias && ((uintptr_t)bias & 15)))
     return set_error(TOME_ERR_ALIGN, "tome_attention_f32: buffers must be 16-byte aligned");
-  if (bias && (N & 3)) return set_error(TOME_ERR_ALIGN, "tome_attention_f32: a key bias needs n %% 4 == 0 rows of 16 bytes (n=%d)", N);
   AfParams p;
   p.B = B; p.N = N; p.heads = heads; p.nblk = (N + AF_BKV - 1) / AF_BKV; p.nobias_q = nobias_q;
   p.scale_log2e = scale * 1.4426950408889634f;

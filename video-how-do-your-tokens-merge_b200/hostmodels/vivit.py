@@ -76,6 +76,13 @@ class VivitSelfAttention(nn.Module):
 
     def forward(self, hidden_states, **kwargs):
         B = hidden_states.shape[0]
+        if hidden_states.is_cuda and hidden_states.dtype == torch.float32:
+            from tome import attention as prop_attention
+            if prop_attention.usable_f32(hidden_states, self, self.num_attention_heads, self.attention_head_size):
+                ctx, _ = prop_attention.attention_f32(hidden_states, self, self.num_attention_heads, self.attention_head_size,
+                                                      self.scaling, None, self.query.weight, self.key.weight, self.value.weight,
+                                                      self.query.bias, self.key.bias, self.value.bias)
+                return ctx, None
         shp = (B, -1, self.num_attention_heads, self.attention_head_size)
         q = self.query(hidden_states).view(*shp).transpose(1, 2)
         k = self.key(hidden_states).view(*shp).transpose(1, 2)

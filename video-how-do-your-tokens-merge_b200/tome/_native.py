@@ -765,7 +765,7 @@ def linear_f32(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
 def attention_f32_usable(qkv: torch.Tensor, heads: int, key_bias: Optional[torch.Tensor] = None) -> bool:
     """tome_attention_f32 serves this (B, N, 3 * heads * 64) fp32 QKV tensor: CUDA inference, head dimension 64."""
     return (qkv.is_cuda and qkv.dtype == torch.float32 and not torch.is_grad_enabled() and qkv.dim() == 3
-            and qkv.shape[2] == 3 * 64 * heads and qkv.shape[1] >= 64 and (key_bias is None or qkv.shape[1] % 4 == 0)
+            and qkv.shape[2] == 3 * 64 * heads and qkv.shape[1] >= 64
             and os.environ.get("TOME_ATTENTION_F32", "1") != "0")
 
 

@@ -13,6 +13,8 @@ split of ``log(size) / scale`` into k's spare channels, and cuDNN's flash attent
 (d_qk = d + 8, d_v = d; 100 us at the shape above).  Inference, CUDA, bf16 only -- anything else takes
 the reference's masked formulation in the callers.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -95,6 +97,55 @@ def attention(x, owner, heads, d, scale, log_size, wq, wk, wv, bq=None, bk=None,
     _native.attn_key_bias(log_size.reshape(B, N - lead), k, q if lead else None, d, scale, lead)
     ctx = F.scaled_dot_product_attention(q, k, v, scale=scale)
     return ctx.transpose(1, 2).reshape(B, N, heads * d), k[..., :d]
+
+
+def usable_f32(x: torch.Tensor, module, heads: int, d: int) -> bool:
+    """fp32 CUDA inference with 64-channel heads: QKV projection and attention on the exact-split tensor-core kernels."""
+    from tome import _native
+    return (x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled() and not module.training and d == 64
+            and x.dim() == 3 and x.shape[1] >= 64 and _native.linear_f32_usable(x, _PROBE.get(heads * d, x.device), None)
+            and os.environ.get("TOME_ATTENTION_F32", "1") != "0")
+
+
+class _Probe:
+    """A (3C, C) fp32 meta-shaped stand-in so linear_f32_usable can vet shapes without a real weight."""
+    def __init__(self):
+        self.cache = {}
+
+    def get(self, c, device):
+        key = (c, str(device))
+        if key not in self.cache:
+            self.cache[key] = torch.empty(3 * c, c, dtype=torch.float32, device=device)
+        return self.cache[key]
+
+
+_PROBE = _Probe()
+
+
+def attention_f32(x, owner, heads, d, scale, log_size, wq, wk, wv, bq=None, bk=None, bv=None, lead=0, on_keys=None):
+    """fp32 attention over x (B, N, C), ``log_size`` (B, N - lead[, 1]) or None added to the logits of the non-leading
+    keys (for the non-leading queries only when lead > 0): one exact-split QKV GEMM (``tome_linear_f32`` on the cached
+    concatenated weight) and ``tome_attention_f32``.  Returns (context (B, N, heads * d), keys (B, heads, N, d))."""
+    from tome import _native
+    B, N, _ = x.shape
+    key = _key_of((wq, wk, wv, bq, bk, bv))
+    cached = getattr(owner, "_tome_plain_qkv", None)
+    if cached is None or cached[0] != key:
+        w = torch.cat((wq, wk, wv), 0).detach().contiguous()
+        zb = lambda t, ref: t.detach() if t is not None else torch.zeros(ref.shape[0], dtype=ref.dtype, device=ref.device)
+        bcat = None if (bq is None and bk is None and bv is None) else torch.cat((zb(bq, wq), zb(bk, wk), zb(bv, wv)), 0).contiguous()
+        cached = owner._tome_plain_qkv = (key, w, bcat)
+    qkv = _native.linear(x, cached[1], cached[2])
+    k = qkv[..., heads * d:2 * heads * d].view(B, N, heads, d).transpose(1, 2)
+    if on_keys is not None:
+        on_keys(k)
+    kb = None
+    if log_size is not None:
+        kb = log_size.reshape(B, N - lead).float()
+        if lead:
+            kb = F.pad(kb, (lead, 0))
+    ctx = _native.attention_f32(qkv, heads, scale, kb, unbiased_queries=lead if kb is not None else 0)
+    return ctx, k
 
 
 def early_metric(module, k, head_aggregation="mean", frames=1):

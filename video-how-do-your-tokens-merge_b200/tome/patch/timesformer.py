@@ -144,6 +144,17 @@ class ToMeAttentionMixin:
                 on_keys=lambda keys: early.update(metric=prop_attention.early_metric(self, keys[:, :, 1:, :])))
             x = self.proj_drop(self.proj(x))
             return x, early["metric"]
+        if self.with_qkv and prop_attention.usable_f32(x, self, self.num_heads, C // self.num_heads):
+            # fp32 inference: exact-split tensor-core QKV GEMM + attention; the class query takes no bias (timesformer.py:74)
+            if size is not None and log_size is None:
+                log_size = size.log()
+            wq, wk, wv = self.qkv.weight.chunk(3, 0)
+            bq, bk, bv = self.qkv.bias.chunk(3, 0) if self.qkv.bias is not None else (None, None, None)
+            early = {}
+            x, k = prop_attention.attention_f32(
+                x, self, self.num_heads, C // self.num_heads, self.scale, None if size is None else log_size, wq, wk, wv, bq, bk, bv,
+                lead=1, on_keys=lambda keys: early.update(metric=prop_attention.early_metric(self, keys[:, :, 1:, :])))
+            return self.proj_drop(self.proj(x)), early["metric"]
         if self.with_qkv:
             qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
             q, k, v = qkv[0], qkv[1], qkv[2]

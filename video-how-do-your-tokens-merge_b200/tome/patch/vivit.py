@@ -88,6 +88,13 @@ class ToMeVivitSelfAttentionMixin:
             ctx, k = prop_attention.attention(hidden_states, self, h, d, d ** -0.5, log_size.float(),
                                               self.query.weight, self.key.weight, self.value.weight,
                                               self.query.bias, self.key.bias, self.value.bias, on_keys=on_keys)
+        elif prop_attention.usable_f32(hidden_states, self, h, d):
+            # fp32 inference: exact-split tensor-core QKV GEMM + flash attention with the key bias (tome_attention_f32)
+            if size is not None and log_size is None:
+                log_size = size.log()
+            ctx, k = prop_attention.attention_f32(hidden_states, self, h, d, d ** -0.5, None if size is None else log_size,
+                                                  self.query.weight, self.key.weight, self.value.weight,
+                                                  self.query.bias, self.key.bias, self.value.bias, on_keys=on_keys)
         else:
             q = self.query(hidden_states).view(B, N, h, d).transpose(1, 2)
             k = self.key(hidden_states).view(B, N, h, d).transpose(1, 2)
