@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 20
+#define TOME_ABI_VERSION 21
 
 #if defined(__GNUC__)
 #define TOME_API __attribute__((visibility("default")))
@@ -308,19 +308,22 @@ TOME_API int tome_linear_gelu(const void* x, const void* w, const void* bias, in
  * without TF32 truncation; terms = 6 drops m.l, l.m, l.l (<= 2^-23 relative per product).
  * tome_split3: x (rows, k) fp32, rows `row_stride` elements apart -> out (rows, 3k) bf16 planes [h | m | l]; k % 4 == 0.
  * tome_linear_f32: out (m, n) fp32 = act(x @ W^T + bias) from the split planes x3 (m, 3k), w3 (n, 3k); bias (n) fp32 or
- *   NULL; gelu 0 / 1 (erf GELU, exact erf).  n % 256 == 0, k % 32 == 0. */
+ *   NULL; gelu 0 / 1 (erf GELU, exact erf).  n % 256 == 0, k % 32 == 0.  out_planes (m, 3n) bf16: the result ALSO (or, with
+ *   out == NULL, ONLY) as split planes -- the operand of the next tome_linear_f32 / tome_attention_f32 without an fp32
+ *   round trip (fc1 -> fc2, qkv -> attention). */
 TOME_API int tome_split3(const void* x, int64_t rows, int32_t k, int64_t row_stride, void* out, void* stream);
 TOME_API int tome_linear_f32(const void* x3, const void* w3, const void* bias, int32_t m, int32_t n, int32_t k, int32_t gelu,
-                    int32_t terms, void* out, void* stream);
+                    int32_t terms, void* out, void* out_planes, void* stream);
 
 /* Caller-side fp32 attention on tcgen05 at fp32 accuracy (tome/patch/videomae.py:58-68, vivit.py:98-117
  * in the fp32 models): out (b, n, heads*64) fp32 = softmax(scale * q k^T + key_bias) v per head, flash-style (running
  * maximum over 64-key blocks), from qkv3 = tome_split3 of the QKV GEMM's output viewed (b*n, 3*heads*64), i.e.
  * (b*n, 9*heads*64) bf16 planes [h: q k v | m: q k v | l: q k v].  Six plane products for q k^T and six for P V with
  * P split exactly in registers.  key_bias (b, n) fp32 or NULL; the first `unbiased_queries` queries
- * take no bias (TimeSformer's class token). */
+ * take no bias (TimeSformer's class token).  out_planes (b*n, 3*heads*64) bf16: the context also / only as split planes
+ * (the output projection's operand). */
 TOME_API int tome_attention_f32(const void* qkv3, int32_t b, int32_t n, int32_t heads, int32_t d, float scale,
-                       const float* key_bias, int32_t unbiased_queries, void* out, void* stream);
+                       const float* key_bias, int32_t unbiased_queries, void* out, void* out_planes, void* stream);
 
 /* unmerge (merge.py:87-100): x (bm, n - r, c) -> out (bm, n, c); contiguous tensors. */
 TOME_API int tome_unmerge(const tome_plan* plan, const void* x, int32_t dtype, int32_t c, void* out,

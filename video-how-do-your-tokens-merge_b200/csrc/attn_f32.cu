@@ -29,7 +29,8 @@ struct AfParams {
   int B, N, heads, nblk, nobias_q;
   float scale_log2e;
   const float* bias;                                // (B, N) log size per key, or NULL
-  float* out;                                       // (B, N, heads * 64)
+  float* out;                                       // (B, N, heads * 64), or NULL
+  __nv_bfloat16* out3;                              // (B * N, 3 * heads * 64) bf16 planes of the same values (the projection's operand), or NULL
 };
 
 __device__ __forceinline__ float af_ex2(float x) {
@@ -279,10 +280,18 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     l += xch[(half ^ 1) * AF_BM + row];
     if (live) {
       const float inv = 1.0f / l;
-      float4* dst = reinterpret_cast<float4*>(p.out + ((long long)b * p.N + s_idx) * C + h * AF_D + 32 * half);
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        dst[e] = make_float4(oacc[4 * e] * inv, oacc[4 * e + 1] * inv, oacc[4 * e + 2] * inv, oacc[4 * e + 3] * inv);
+      for (int e = 0; e < 32; ++e) oacc[e] *= inv;
+      if (p.out) {
+        float4* dst = reinterpret_cast<float4*>(p.out + ((long long)b * p.N + s_idx) * C + h * AF_D + 32 * half);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dst[e] = make_float4(oacc[4 * e], oacc[4 * e + 1], oacc[4 * e + 2], oacc[4 * e + 3]);
+      }
+      if (p.out3) {
+        __nv_bfloat16* d3 = p.out3 + ((long long)b * p.N + s_idx) * 3 * C + h * AF_D + 32 * half;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) store_planes8(d3 + 8 * e, C, reinterpret_cast<const float(&)[8]>(oacc[8 * e]));
+      }
     }
   }
   tc_fence_before();
@@ -294,13 +303,14 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 }
 
 int launch_attention_f32(const void* qkv3, int B, int N, int heads, float scale, const float* bias, int nobias_q, void* out,
-                         cudaStream_t st) {
-  if (((uintptr_t)qkv3 & 15) || ((uintptr_t)out & 15) || (bias && ((uintptr_t)bias & 15)))
+                         void* out3, cudaStream_t st) {
+  if (!out && !out3) return set_error(TOME_ERR_ARG, "tome_attention_f32: no output");
+  if (((uintptr_t)qkv3 & 15) || ((uintptr_t)out & 15) || ((uintptr_t)out3 & 15) || (bias && ((uintptr_t)bias & 15)))
     return set_error(TOME_ERR_ALIGN, "tome_attention_f32: buffers must be 16-byte aligned");
   AfParams p;
   p.B = B; p.N = N; p.heads = heads; p.nblk = (N + AF_BKV - 1) / AF_BKV; p.nobias_q = nobias_q;
   p.scale_log2e = scale * 1.4426950408889634f;
-  p.bias = bias; p.out = (float*)out;
+  p.bias = bias; p.out = (float*)out; p.out3 = (__nv_bfloat16*)out3;
   const long long rows = (long long)B * N, cols = 9LL * heads * AF_D;
   alignas(64) CUtensorMap map_q, map_kv;
   int rc = make_bf16_map(&map_q, qkv3, rows, cols, cols, AF_BM, "tome_attention_f32");

@@ -36,7 +36,8 @@ constexpr uint32_t LF_STAGE_BYTES = 3u * (LF_A_BYTES + LF_B_BYTES);
 struct LinearF32Params {
   int m, n, k, num_kb, tiles_n, tiles, terms;       // terms: 9 (exact split) or 6 (drops m.l, l.m, l.l: <= 2^-23 relative)
   const float* bias;                                // (n) or NULL
-  float* out;                                       // (m, n) row-major
+  float* out;                                       // (m, n) row-major, or NULL
+  __nv_bfloat16* out3;                              // (m, 3n) bf16 planes of the same values (the next GEMM's operand), or NULL
   int gelu;                                         // 0: bias only; 1: erf GELU (nn.GELU)
 };
 
@@ -198,19 +199,26 @@ linear_f32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
       const int row = mt * LF_BM + q * 32 + lane, col0 = nt * LF_BN + part * 128;
       if (row < p.m) {
-        float4* orow = reinterpret_cast<float4*>(p.out + (long long)row * p.n + col0);
+        float4* orow = p.out ? reinterpret_cast<float4*>(p.out + (long long)row * p.n + col0) : nullptr;
+        __nv_bfloat16* prow = p.out3 ? p.out3 + (long long)row * 3 * p.n + col0 : nullptr;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c * 32 + g * 4));
-            float o[4] = {sum[c][4 * g] + b4.x, sum[c][4 * g + 1] + b4.y, sum[c][4 * g + 2] + b4.z, sum[c][4 * g + 3] + b4.w};
+          for (int g = 0; g < 8; g += 2) {
+            float o[8];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c * 32 + (g + u) * 4));
+              o[4 * u] = sum[c][4 * (g + u)] + b4.x; o[4 * u + 1] = sum[c][4 * (g + u) + 1] + b4.y;
+              o[4 * u + 2] = sum[c][4 * (g + u) + 2] + b4.z; o[4 * u + 3] = sum[c][4 * (g + u) + 3] + b4.w;
+            }
             if (p.gelu == 1) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) o[e] = 0.5f * o[e] * (1.0f + erff(o[e] * 0.70710678118654752440f));     // nn.GELU, exact erf
+              for (int e = 0; e < 8; ++e) o[e] = 0.5f * o[e] * (1.0f + erff(o[e] * 0.70710678118654752440f));     // nn.GELU, exact erf
             }
-            orow[c * 8 + g] = make_float4(o[0], o[1], o[2], o[3]);
+            if (orow) { orow[c * 8 + g] = make_float4(o[0], o[1], o[2], o[3]); orow[c * 8 + g + 1] = make_float4(o[4], o[5], o[6], o[7]); }
+            if (prow) store_planes8(prow + c * 32 + g * 4, p.n, o);       // the next GEMM's operand, no fp32 round trip
           }
         }
       }
@@ -235,10 +243,11 @@ int launch_split3(const void* x, long long rows, int k, long long row_stride, vo
 }
 
 int launch_linear_f32(const void* x3, const void* w3, const void* bias, int m, int n, int k, int gelu, int terms, void* out,
-                      cudaStream_t st) {
+                      void* out3, cudaStream_t st) {
   if (n % LF_BN != 0 || k % LF_BK != 0 || m < 1)
     return set_error(TOME_ERR_UNSUPPORTED, "tome_linear_f32: needs n %% %d == 0 and k %% %d == 0 (m=%d n=%d k=%d)", LF_BN, LF_BK, m, n, k);
-  if (((uintptr_t)x3 & 15) || ((uintptr_t)w3 & 15) || ((uintptr_t)out & 15) || (bias && ((uintptr_t)bias & 15)))
+  if (!out && !out3) return set_error(TOME_ERR_ARG, "tome_linear_f32: no output");
+  if (((uintptr_t)x3 & 15) || ((uintptr_t)w3 & 15) || ((uintptr_t)out & 15) || ((uintptr_t)out3 & 15) || (bias && ((uintptr_t)bias & 15)))
     return set_error(TOME_ERR_ALIGN, "tome_linear_f32: 16-byte aligned tensors required");
   if (terms != 6 && terms != 9) return set_error(TOME_ERR_ARG, "tome_linear_f32: terms must be 6 or 9");
   alignas(64) CUtensorMap map_a, map_w;
@@ -249,7 +258,7 @@ int launch_linear_f32(const void* x3, const void* w3, const void* bias, int m, i
   LinearF32Params p;
   p.m = m; p.n = n; p.k = k; p.num_kb = k / LF_BK; p.terms = terms;
   p.tiles_n = n / LF_BN; p.tiles = ((m + LF_BM - 1) / LF_BM) * p.tiles_n;
-  p.bias = (const float*)bias; p.out = (float*)out; p.gelu = gelu;
+  p.bias = (const float*)bias; p.out = (float*)out; p.out3 = (__nv_bfloat16*)out3; p.gelu = gelu;
   const size_t smem = (size_t)LF_STAGES * LF_STAGE_BYTES + 16 * LF_STAGES + 32 + 16 + 1024;
   static PerDeviceOnce attr;
   if (attr.first_time())

@@ -109,6 +109,25 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16])
         "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
       : "r"(taddr));
 }
+// Exact three-way bf16 split of eight fp32 values (h + m + l == x), stored as 16 bytes into each of the three planes of a
+// (rows, 3 * n) bf16 tensor: `dst` points at the h plane's element, the m and l planes are n and 2n elements further.
+__device__ __forceinline__ void store_planes8(__nv_bfloat16* dst, long long n, const float (&f)[8]) {
+  uint32_t hw[4], mw[4], lw[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float x0 = f[2 * i], x1 = f[2 * i + 1];
+    const float h0 = __bfloat162float(__float2bfloat16_rn(x0)), h1 = __bfloat162float(__float2bfloat16_rn(x1));
+    const float r0 = x0 - h0, r1 = x1 - h1;
+    const float m0 = __bfloat162float(__float2bfloat16_rn(r0)), m1 = __bfloat162float(__float2bfloat16_rn(r1));
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(h0, h1), mm = __floats2bfloat162_rn(m0, m1), ll = __floats2bfloat162_rn(r0 - m0, r1 - m1);
+    hw[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    mw[i] = *reinterpret_cast<const uint32_t*>(&mm);
+    lw[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  *reinterpret_cast<uint4*>(dst) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  *reinterpret_cast<uint4*>(dst + n) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+  *reinterpret_cast<uint4*>(dst + 2 * n) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
 __device__ __forceinline__ long long gtime() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

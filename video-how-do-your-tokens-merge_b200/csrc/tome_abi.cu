@@ -87,8 +87,8 @@ int launch_attn_short(const void*, const void*, const void*, int, long long, int
 int launch_frames_attention(const void*, int, int, int, int, int, float, const float*, void*, void*, int, int, cudaStream_t);
 int launch_traj_temporal(const void*, const void*, const void*, long long, int, int, float, void*, cudaStream_t);
 int launch_split3(const void*, long long, int, long long, void*, cudaStream_t);
-int launch_linear_f32(const void*, const void*, const void*, int, int, int, int, int, void*, cudaStream_t);
-int launch_attention_f32(const void*, int, int, int, float, const float*, int, void*, cudaStream_t);
+int launch_linear_f32(const void*, const void*, const void*, int, int, int, int, int, void*, void*, cudaStream_t);
+int launch_attention_f32(const void*, int, int, int, float, const float*, int, void*, void*, cudaStream_t);
 int launch_source_compose(const tome_plan*, const int*, int, int, float, int*, cudaStream_t);
 int launch_source_dense(const int*, int, int, int, float*, cudaStream_t);
 int launch_random_rowmax(void*, long long, int, int, int, int, int, float*, int*, float*, int, cudaStream_t);
@@ -511,21 +511,21 @@ int tome_split3(const void* x, int64_t rows, int32_t k, int64_t row_stride, void
 }
 
 int tome_linear_f32(const void* x3, const void* w3, const void* bias, int32_t m, int32_t n, int32_t k, int32_t gelu, int32_t terms,
-                    void* out, void* stream) {
+                    void* out, void* out_planes, void* stream) {
   int rc = ensure_device_ok();
   if (rc) return rc;
-  TOME_CHECK_ARG(x3 && w3 && out && m > 0 && n > 0 && k > 0, "tome_linear_f32: NULL pointer or bad shape");
+  TOME_CHECK_ARG(x3 && w3 && (out || out_planes) && m > 0 && n > 0 && k > 0, "tome_linear_f32: NULL pointer or bad shape");
   TOME_CHECK_ARG(gelu == 0 || gelu == 1, "tome_linear_f32: gelu must be 0 or 1");
-  return launch_linear_f32(x3, w3, bias, m, n, k, gelu, terms, out, (cudaStream_t)stream);
+  return launch_linear_f32(x3, w3, bias, m, n, k, gelu, terms, out, out_planes, (cudaStream_t)stream);
 }
 
 int tome_attention_f32(const void* qkv3, int32_t b, int32_t n, int32_t heads, int32_t d, float scale, const float* key_bias,
-                       int32_t unbiased_queries, void* out, void* stream) {
+                       int32_t unbiased_queries, void* out, void* out_planes, void* stream) {
   int rc = ensure_device_ok();
   if (rc) return rc;
-  TOME_CHECK_ARG(qkv3 && out && b > 0 && n > 0 && heads > 0 && unbiased_queries >= 0, "tome_attention_f32: NULL pointer or empty shape");
+  TOME_CHECK_ARG(qkv3 && (out || out_planes) && b > 0 && n > 0 && heads > 0 && unbiased_queries >= 0, "tome_attention_f32: NULL pointer or empty shape");
   if (d != 64) return set_error(TOME_ERR_UNSUPPORTED, "tome_attention_f32: head dimension %d (64 only)", d);
-  return launch_attention_f32(qkv3, b, n, heads, scale, key_bias, unbiased_queries, out, (cudaStream_t)stream);
+  return launch_attention_f32(qkv3, b, n, heads, scale, key_bias, unbiased_queries, out, out_planes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -9,6 +9,9 @@ import torch.nn.functional as F
 
 class TomeLinear(nn.Linear):
     def forward(self, x):
+        if not torch.is_tensor(x):          # _native.Planes: the previous exact-split kernel's output, already split
+            from tome import _native
+            return _native.linear_f32(x, self.weight, self.bias)
         if x.is_cuda and x.dtype == torch.float32 and not self.training:
             from tome import _native
             if _native.linear_f32_usable(x, self.weight, self.bias):
@@ -24,10 +27,12 @@ def install(model: nn.Module) -> nn.Module:
     return model
 
 
-def linear(x, weight, bias=None):
-    """F.linear for the host models' explicit GEMMs (tubelet embeddings, q/v-biased QKV)."""
+def linear(x, weight, bias=None, out="fp32"):
+    """F.linear for the host models' explicit GEMMs (tubelet embeddings, q/v-biased QKV).  ``out="both"`` also returns the
+    result's split planes (None when the library GEMM ran)."""
     if x.is_cuda and x.dtype == torch.float32:
         from tome import _native
         if _native.linear_f32_usable(x, weight, bias):
-            return _native.linear_f32(x, weight, bias)
-    return F.linear(x, weight, bias)
+            return _native.linear_f32(x, weight, bias, out=out)
+    y = F.linear(x, weight, bias)
+    return (y, None) if out == "both" else y

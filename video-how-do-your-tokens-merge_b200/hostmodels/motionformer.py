@@ -32,6 +32,8 @@ class Mlp(nn.Module):
 
     def forward(self, x):
         h = fused_fc1_gelu(self, x)                     # tome_linear_gelu on the CUDA bf16 inference path
+        if h is not None and not torch.is_tensor(h):        # split planes straight into fc2 (eval: dropout is the identity)
+            return self.drop(self.fc2(h))
         return self.drop(self.fc2(self.drop(h if h is not None else self.act(self.fc1(x)))))
 
 

@@ -45,7 +45,10 @@ def fused_fc1_gelu(mlp, x):
             and mlp.act.approximate == "none"):
         from tome import _native
         if _native.linear_f32_usable(x, mlp.fc1.weight, mlp.fc1.bias):       # fp32: exact-split tensor-core GEMM, erf GELU in its epilogue
-            return _native.linear_f32(x, mlp.fc1.weight, mlp.fc1.bias, gelu=True)
+            # fc2 is an exact-split GEMM too (fastlinear.TomeLinear): hand it the planes, skip the fp32 round trip
+            planes = (isinstance(mlp.fc2, fastlinear.TomeLinear) and not torch.is_grad_enabled()
+                      and _native.linear_f32_weight_ok(mlp.fc2.weight, mlp.fc2.bias))
+            return _native.linear_f32(x, mlp.fc1.weight, mlp.fc1.bias, gelu=True, out="planes" if planes else "fp32")
     return None
 
 
@@ -73,12 +76,15 @@ class Attention(nn.Module):                             # builder:59-103
         qkv_bias = None
         if self.q_bias is not None:
             qkv_bias = torch.cat((self.q_bias, torch.zeros_like(self.v_bias, requires_grad=False), self.v_bias))
-        qkv_flat = fastlinear.linear(x, self.qkv.weight, qkv_bias)
+        qkv_flat, qkv3 = fastlinear.linear(x, self.qkv.weight, qkv_bias, out="both")
         if x.is_cuda and x.dtype == torch.float32 and not self.training:
             from tome import _native
             if qkv_flat.shape[-1] == 3 * 64 * self.num_heads and _native.attention_f32_usable(qkv_flat, self.num_heads):
-                # fp32 inference: exact-split flash attention on tcgen05 (tome_attention_f32)
-                return self.proj_drop(self.proj(_native.attention_f32(qkv_flat, self.num_heads, self.scale)))
+                # fp32 inference: exact-split flash attention on tcgen05 (tome_attention_f32), planes in and out
+                keep = isinstance(self.proj, fastlinear.TomeLinear) and qkv3 is not None
+                ctx = _native.attention_f32(qkv3 if qkv3 is not None else qkv_flat, self.num_heads, self.scale,
+                                            out="planes" if keep else "fp32")
+                return self.proj_drop(self.proj(ctx))
         qkv = qkv_flat.reshape(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4)
         x = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], scale=self.scale,
                                            dropout_p=self.attn_drop.p if self.training else 0.0)

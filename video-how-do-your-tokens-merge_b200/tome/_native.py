@@ -18,7 +18,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 20
+ABI_VERSION = 21
 
 TOME_F32, TOME_BF16, TOME_U8 = 0, 1, 2
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -131,8 +131,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
                                             c_vp, p_i64, c_vp]
     lib.tome_attn_short.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_i64, c_i64, c_f32, c_vp, c_vp]
     lib.tome_split3.argtypes = [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp]
-    lib.tome_linear_f32.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]
-    lib.tome_attention_f32.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_i32, c_vp, c_vp]
+    lib.tome_linear_f32.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]
+    lib.tome_attention_f32.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_i32, c_vp, c_vp, c_vp]
     for name in ("tome_split3", "tome_linear_f32", "tome_attention_f32"):
         getattr(lib, name).restype = c_i32
     lib.tome_frames_attention.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp]
@@ -735,6 +735,14 @@ def split3(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def linear_f32_weight_ok(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> bool:
+    """The shape / dtype conditions tome_linear_f32 puts on a layer (n % 256 == 0, k % 32 == 0, fp32, contiguous)."""
+    return (weight.is_cuda and weight.dtype == torch.float32 and weight.dim() == 2 and weight.is_contiguous()
+            and weight.shape[0] % 256 == 0 and weight.shape[1] % 32 == 0
+            and (bias is None or (bias.dtype == torch.float32 and bias.is_contiguous()))
+            and os.environ.get("TOME_LINEAR_F32", "1") != "0")
+
+
 def linear_f32_usable(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> bool:
     """tome_linear_f32 serves this fp32 linear: CUDA inference, n % 256 == 0, k % 32 == 0."""
     return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and not torch.is_grad_enabled()
@@ -744,22 +752,50 @@ def linear_f32_usable(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torc
             and os.environ.get("TOME_LINEAR_F32", "1") != "0")
 
 
-def linear_f32(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], gelu: bool = False, terms: Optional[int] = None):
+class Planes:
+    """An fp32 tensor held as its exact three-way bf16 split: ``data`` (rows, 3 * k) = [h | m | l] planes with
+    h + m + l == x, ``shape`` the logical fp32 shape (..., k).  What tome_linear_f32 / tome_attention_f32 consume, and what
+    they can produce directly so that a GEMM -> GEMM / GEMM -> attention hand-over needs no fp32 round trip."""
+
+    def __init__(self, data: torch.Tensor, shape):
+        self.data, self.shape = data, tuple(shape)
+
+    device = property(lambda self: self.data.device)
+    is_cuda = True
+    dtype = torch.float32
+
+    def float(self) -> torch.Tensor:
+        k = self.shape[-1]
+        d = self.data.float()
+        return ((d[:, :k] + d[:, k:2 * k]) + d[:, 2 * k:]).reshape(self.shape)
+
+
+def linear_f32(x, weight: torch.Tensor, bias: Optional[torch.Tensor], gelu: bool = False, terms: Optional[int] = None,
+               out: str = "fp32"):
     """act(x @ weight^T + bias) in fp32 on the tensor cores (exact bf16 three-way split, nine products; include/tome_b200.h:
-    tome_linear_f32).  The weight's planes are cached until the weight changes."""
+    tome_linear_f32).  ``x``: an fp32 tensor or a ``Planes``; the weight's planes are cached until the weight changes.
+    ``out``: "fp32" (tensor), "planes" (``Planes`` only: the next exact-split kernel's operand) or "both"."""
     lib = load_library()
-    _require_cuda(x, "x")
     n, k = weight.shape
     w3 = _cached_planes(weight)
-    x3 = split3(x)
+    if isinstance(x, Planes):
+        x3, lead = x.data, x.shape[:-1]
+    else:
+        _require_cuda(x, "x")
+        x3, lead = split3(x), tuple(x.shape[:-1])
     m = x3.shape[0]
     if terms is None:
         terms = int(os.environ.get("TOME_LINEAR_F32_TERMS", "9"))
-    with torch.cuda.device(x.device):
-        out = torch.empty(m, n, dtype=torch.float32, device=x.device)
+    dev = x3.device
+    with torch.cuda.device(dev):
+        res = torch.empty(m, n, dtype=torch.float32, device=dev) if out in ("fp32", "both") else None
+        res3 = torch.empty(m, 3 * n, dtype=torch.bfloat16, device=dev) if out in ("planes", "both") else None
         _check(lib.tome_linear_f32(x3.data_ptr(), w3.data_ptr(), None if bias is None else bias.data_ptr(), m, n, k, int(bool(gelu)),
-                                   int(terms), out.data_ptr(), _stream(x)), lib)
-    return out.reshape(*x.shape[:-1], n)
+                                   int(terms), None if res is None else res.data_ptr(), None if res3 is None else res3.data_ptr(),
+                                   torch.cuda.current_stream(dev).cuda_stream), lib)
+    t = None if res is None else res.reshape(*lead, n)
+    p3 = None if res3 is None else Planes(res3, lead + (n,))
+    return t if out == "fp32" else p3 if out == "planes" else (t, p3)
 
 
 def attention_f32_usable(qkv: torch.Tensor, heads: int, key_bias: Optional[torch.Tensor] = None) -> bool:
@@ -769,23 +805,33 @@ def attention_f32_usable(qkv: torch.Tensor, heads: int, key_bias: Optional[torch
             and os.environ.get("TOME_ATTENTION_F32", "1") != "0")
 
 
-def attention_f32(qkv: torch.Tensor, heads: int, scale: float, key_bias: Optional[torch.Tensor] = None,
-                  unbiased_queries: int = 0) -> torch.Tensor:
+def attention_f32(qkv, heads: int, scale: float, key_bias: Optional[torch.Tensor] = None, unbiased_queries: int = 0,
+                  out: str = "fp32"):
     """softmax(scale q k^T + key_bias) v in fp32 accuracy on the tensor cores, from the QKV GEMM's output
-    (B, N, 3 * heads * 64) (channel order (3, heads, 64)); returns (B, N, heads * 64).  ``key_bias`` (B, N) fp32."""
+    (B, N, 3 * heads * 64) (channel order (3, heads, 64)) as an fp32 tensor or as ``Planes``; returns (B, N, heads * 64)
+    as a tensor, as ``Planes`` (out="planes": the projection's operand) or both.  ``key_bias`` (B, N) fp32."""
     lib = load_library()
-    _require_cuda(qkv, "qkv")
-    B, N, c3 = qkv.shape
-    x3 = split3(qkv.reshape(B * N, c3))
+    if isinstance(qkv, Planes):
+        B, N, c3 = qkv.shape
+        x3 = qkv.data
+    else:
+        _require_cuda(qkv, "qkv")
+        B, N, c3 = qkv.shape
+        x3 = split3(qkv.reshape(B * N, c3))
+    c = c3 // 3
     bp = None
     if key_bias is not None:
         key_bias = key_bias.to(torch.float32).reshape(B, N).contiguous()
         bp = key_bias.data_ptr()
-    with torch.cuda.device(qkv.device):
-        out = torch.empty(B, N, c3 // 3, dtype=torch.float32, device=qkv.device)
-        _check(lib.tome_attention_f32(x3.data_ptr(), B, N, heads, c3 // 3 // heads, float(scale), bp, int(unbiased_queries),
-                                      out.data_ptr(), _stream(qkv)), lib)
-    return out
+    dev = x3.device
+    with torch.cuda.device(dev):
+        res = torch.empty(B, N, c, dtype=torch.float32, device=dev) if out in ("fp32", "both") else None
+        res3 = torch.empty(B * N, 3 * c, dtype=torch.bfloat16, device=dev) if out in ("planes", "both") else None
+        _check(lib.tome_attention_f32(x3.data_ptr(), B, N, heads, c // heads, float(scale), bp, int(unbiased_queries),
+                                      None if res is None else res.data_ptr(), None if res3 is None else res3.data_ptr(),
+                                      torch.cuda.current_stream(dev).cuda_stream), lib)
+    p3 = None if res3 is None else Planes(res3, (B, N, c))
+    return res if out == "fp32" else p3 if out == "planes" else (res, p3)
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:

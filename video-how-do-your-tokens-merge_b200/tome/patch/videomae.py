@@ -151,7 +151,11 @@ class ToMeAttentionMixin:
                                             self.q_bias, None, self.v_bias, on_keys=on_keys)
         else:
             from tome import _native
-            qkv_flat = _native.linear(x, self.qkv.weight, qkv_bias)      # fp32 inference: tome_linear_f32; else F.linear
+            qkv3 = None
+            if _native.linear_f32_usable(x, self.qkv.weight, qkv_bias):   # fp32 inference: tome_linear_f32, result also as split planes
+                qkv_flat, qkv3 = _native.linear_f32(x, self.qkv.weight, qkv_bias, out="both")
+            else:
+                qkv_flat = F.linear(x, self.qkv.weight, qkv_bias)
             qkv = qkv_flat.reshape(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4)
             q, k, v = qkv[0], qkv[1], qkv[2]
             on_keys(k)
@@ -160,7 +164,9 @@ class ToMeAttentionMixin:
             kb = None if size is None else log_size[..., 0]
             if q.shape[-1] == 64 and _native.attention_f32_usable(qkv_flat, self.num_heads, kb):
                 # fp32 inference: exact-split flash attention on tcgen05, key bias taken directly
-                x = _native.attention_f32(qkv_flat, self.num_heads, self.scale, kb)
+                keep = qkv3 is not None and type(self.proj).__name__ == "TomeLinear"      # proj takes the planes directly
+                x = _native.attention_f32(qkv3 if qkv3 is not None else qkv_flat, self.num_heads, self.scale, kb,
+                                          out="planes" if keep else "fp32")
             else:
                 bias = None if size is None else log_size[:, None, None, :, 0].to(q.dtype).expand(B, 1, N, N)
                 drop = self.attn_drop.p if self.training else 0.0
