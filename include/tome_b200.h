@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 21
+#define TOME_ABI_VERSION 22
 
 #if defined(__GNUC__)
 #define TOME_API __attribute__((visibility("default")))
@@ -241,6 +241,15 @@ TOME_API int tome_rows_add_layernorm(const void* a, const int64_t* a_strides, co
                             int32_t dtype, int32_t nb, int32_t np, int32_t nt, int32_t c, const void* ln_weight,
                             const void* ln_bias, float ln_eps, void* sum_out, const int64_t* sum_strides,
                             void* normed_out, const int64_t* normed_strides, void* stream);
+
+/* The class-token rows of the divided space-time blocks (tome/patch/timesformer.py:41-48, 56), one small launch instead of
+ * ~10 on `batch` rows:  sum = a[b] (+ mean over t < mean_t of mean_src[b, t]) (+ add[b]), each step rounded to `dtype` like the
+ * separate ops; sum_out[b] = sum (optional); normed_out[b, rep] = LayerNorm(sum) * w + bias for rep < reps (the per-frame
+ * copies in front of the spatial attention; optional).  Strides in elements. */
+TOME_API int tome_cls_rows(const void* a, int64_t a_stride_b, const void* add, int64_t add_stride_b, const void* mean_src,
+                  int64_t mean_stride_b, int64_t mean_stride_t, int32_t mean_t, int32_t dtype, int32_t batch, int32_t c,
+                  void* sum_out, int64_t sum_stride_b, const void* ln_weight, const void* ln_bias, float ln_eps,
+                  void* normed_out, int64_t normed_stride_b, int64_t normed_stride_rep, int32_t reps, void* stream);
 
 /* Caller-side piece of proportional attention (tome/patch/videomae.py:62-63,
  * vivit.py:103-104, timesformer.py:72-74: attn + log(size) of the key token).  q and k heads carry spare

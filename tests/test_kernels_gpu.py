@@ -1009,6 +1009,51 @@ def test_rows_add_layernorm_through_views(native, dtype):
     assert torch.equal(only.reshape(B, P * T, C), s_ref)
 
 
+@pytest.mark.parametrize("C", [64, 96, 768])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_cls_rows_match_the_separate_torch_ops(native, dtype, C):
+    """tome_cls_rows on the three class-token steps of a divided space-time block (timesformer.py:41-48, 56) against the torch
+    ops it replaces: the adds bit for bit (each step rounds to the dtype), the frame mean and LayerNorm within rounding."""
+    g = torch.Generator().manual_seed(13)
+    B, T, P = 3, 8, 5
+    x = torch.randn(B, 1 + P * T, C, generator=g).to("cuda", dtype)
+    y = torch.randn(B, 1 + P * T, C, generator=g).to("cuda", dtype)
+    res_s = torch.randn(B * T, 1 + P, C, generator=g).to("cuda", dtype)
+    w = (1 + 0.1 * torch.randn(C, generator=g)).to("cuda", dtype)
+    b = (0.1 * torch.randn(C, generator=g)).to("cuda", dtype)
+    bf = dtype == torch.bfloat16
+    # (1) LayerNorm of the class row replicated into the '(b t) (1 + p)' buffer's class rows
+    ns = torch.zeros(B * T, 1 + P, C, device="cuda", dtype=dtype)
+    native.cls_rows(x[:, 0], norm=(w, b, 1e-6), normed_out=ns.view(B, T, 1 + P, C)[:, :, 0])
+    want = torch.nn.functional.layer_norm(x[:, 0].float(), (C,), w.float(), b.float(), 1e-6)
+    got = ns.view(B, T, 1 + P, C)[:, :, 0]
+    torch.testing.assert_close(got.float(), want[:, None].expand(B, T, C), rtol=2e-2 if bf else 1e-5, atol=2e-2 if bf else 1e-5)
+    assert torch.equal(got[:, 0], got[:, T - 1])
+    assert torch.equal(ns[:, 1:], torch.zeros_like(ns[:, 1:]))                                           # patch rows untouched
+    # (2) class row + mean over the frames of the spatial attention's class outputs
+    cls = torch.empty(B, C, device="cuda", dtype=dtype)
+    m = res_s.view(B, T, 1 + P, C)[:, :, 0]
+    native.cls_rows(x[:, 0], mean_src=m, sum_out=cls)
+    want = x[:, 0] + m.mean(1)
+    if bf:
+        assert torch.equal(cls, want)                                 # fp32 accumulation, one rounding: no order dependence left
+    else:
+        torch.testing.assert_close(cls, want, rtol=1e-6, atol=1e-6)
+    # (3) the closing residual add of the class row, written into the next residual stream
+    s = torch.zeros_like(x)
+    native.cls_rows(x[:, 0], add=y[:, 0], sum_out=s[:, 0])
+    assert torch.equal(s[:, 0], x[:, 0] + y[:, 0])
+    assert torch.equal(s[:, 1:], torch.zeros_like(s[:, 1:]))
+    # all three at once
+    both = torch.empty(B, C, device="cuda", dtype=dtype)
+    nb = torch.empty(B, 2, C, device="cuda", dtype=dtype)
+    native.cls_rows(x[:, 0], add=y[:, 0], mean_src=m, sum_out=both, norm=(w, b, 1e-6), normed_out=nb)
+    want = (x[:, 0] + m.mean(1)) + y[:, 0]
+    torch.testing.assert_close(both, want, rtol=0 if bf else 1e-6, atol=0 if bf else 1e-6)
+    torch.testing.assert_close(nb[:, 1].float(), torch.nn.functional.layer_norm(both.float(), (C,), w.float(), b.float(), 1e-6),
+                               rtol=2e-2 if bf else 1e-5, atol=2e-2 if bf else 1e-5)
+
+
 @pytest.mark.parametrize("mode", ["merge", "hybrid", "drop"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 def test_merge_frames_with_the_spatial_residual_in_its_own_layout(native, mode, dtype):

@@ -925,6 +925,132 @@ int launch_rows_add_layernorm(const void* a, const long long* av, const void* b,
   return set_error(TOME_ERR_DTYPE, "tome_rows_add_layernorm: unsupported dtype %d", dtype);
 }
 
+// ---- class-token rows of the divided space-time blocks -----------------------------------------------------------
+// The class token does not follow the (b, p, t) pattern of the patch tokens: per block the reference replicates its
+// LayerNorm over the frames, averages the spatial attention's T class outputs back into one row, and carries it through
+// the residual adds (tome/patch/timesformer.py:41-48, 56).  In torch that is ~10 launches on B rows per block; here one
+// warp per clip does  sum = a (+ add) (+ mean over t of m[b, t]),  each step rounded to T as the separate ops round,
+// writes it, and writes LayerNorm(sum) to `reps` destinations (the per-frame copies).
+struct ClsArgs {
+  const void *a, *add, *mean_src;
+  long long a_sb, add_sb, m_sb, m_st;      // element strides: batch (and frame for mean_src)
+  int mean_t;                              // frames averaged (0: no mean term)
+  void *sum_out, *normed_out;
+  long long s_sb, n_sb, n_sr;              // sum_out batch stride; normed_out batch / replica strides
+  int reps, c;
+  const void *ln_w, *ln_b;
+  float eps;
+};
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(32) cls_rows_kernel(ClsArgs g) {
+  constexpr int E = Pack<T>::E;
+  const int lane = threadIdx.x, b = blockIdx.x, nvec = g.c / E;
+  float f[NV][E];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int i = v * 32 + lane;
+    if (i < nvec) Pack<T>::unpack(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(g.a) + (long long)b * g.a_sb) + i), f[v]);
+    else
+#pragma unroll
+      for (int e = 0; e < E; ++e) f[v][e] = 0.f;
+  }
+  auto round_t = [&]() {                               // what a T-typed intermediate tensor would hold
+#pragma unroll
+    for (int v = 0; v < NV; ++v) Pack<T>::unpack(Pack<T>::pack(f[v]), f[v]);
+  };
+  if (g.mean_t > 0) {                                  // mean over frames: fp32 accumulation, one rounding (ATen's MeanOps)
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int i = v * 32 + lane;
+      if (i < nvec) {
+        float acc[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[e] = 0.f;
+        for (int t = 0; t < g.mean_t; ++t) {
+          float m[E];
+          Pack<T>::unpack(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(g.mean_src) + (long long)b * g.m_sb + (long long)t * g.m_st) + i), m);
+#pragma unroll
+          for (int e = 0; e < E; ++e) acc[e] += m[e];
+        }
+        const float inv = 1.0f / (float)g.mean_t;
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[e] *= inv;
+        Pack<T>::unpack(Pack<T>::pack(acc), acc);      // the mean tensor, rounded to T
+#pragma unroll
+        for (int e = 0; e < E; ++e) f[v][e] += acc[e];
+      }
+    }
+    round_t();
+  }
+  if (g.add) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int i = v * 32 + lane;
+      if (i < nvec) {
+        float m[E];
+        Pack<T>::unpack(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(g.add) + (long long)b * g.add_sb) + i), m);
+#pragma unroll
+        for (int e = 0; e < E; ++e) f[v][e] += m[e];
+      }
+    }
+    round_t();
+  }
+  if (g.sum_out) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int i = v * 32 + lane;
+      if (i < nvec) reinterpret_cast<uint4*>(reinterpret_cast<T*>(g.sum_out) + (long long)b * g.s_sb)[i] = Pack<T>::pack(f[v]);
+    }
+  }
+  if (!g.normed_out) return;
+  float sum = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int e = 0; e < E; ++e) sum += f[v][e];
+#pragma unroll
+  for (int of = 16; of > 0; of >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, of);
+  const float mean = sum / (float)g.c;
+  float sq = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const bool on = v * 32 + lane < nvec;
+#pragma unroll
+    for (int e = 0; e < E; ++e) { f[v][e] -= mean; if (on) sq = fmaf(f[v][e], f[v][e], sq); }
+  }
+#pragma unroll
+  for (int of = 16; of > 0; of >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, of);
+  const float rstd = rsqrtf(sq / (float)g.c + g.eps);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int i = v * 32 + lane;
+    if (i < nvec) {
+      float w[E], bb[E], y[E];
+      Pack<T>::unpack(__ldg(reinterpret_cast<const uint4*>(g.ln_w) + i), w);
+      if (g.ln_b) Pack<T>::unpack(__ldg(reinterpret_cast<const uint4*>(g.ln_b) + i), bb);
+#pragma unroll
+      for (int e = 0; e < E; ++e) y[e] = fmaf(f[v][e], w[e] * rstd, g.ln_b ? bb[e] : 0.f);
+      const uint4 packed = Pack<T>::pack(y);
+      for (int rr = 0; rr < g.reps; ++rr)
+        reinterpret_cast<uint4*>(reinterpret_cast<T*>(g.normed_out) + (long long)b * g.n_sb + (long long)rr * g.n_sr)[i] = packed;
+    }
+  }
+}
+
+int launch_cls_rows(const ClsArgs& g, int dtype, int batch, cudaStream_t st) {
+  const int e = dtype == TOME_F32 ? 4 : 8;
+  const int nv = (g.c / e + 31) / 32;
+  if (g.c % e != 0 || nv > 8) return set_error(TOME_ERR_UNSUPPORTED, "tome_cls_rows: c=%d (needs c %% %d == 0, c <= %d)", g.c, e, 8 * 32 * e);
+#define TOME_CLS(T_, NV_) cls_rows_kernel<T_, NV_><<<batch, 32, 0, st>>>(g)
+  if (dtype == TOME_F32) { if (nv <= 2) TOME_CLS(float, 2); else if (nv <= 4) TOME_CLS(float, 4); else if (nv <= 6) TOME_CLS(float, 6); else TOME_CLS(float, 8); }
+  else if (dtype == TOME_BF16) { if (nv <= 2) TOME_CLS(__nv_bfloat16, 2); else if (nv <= 3) TOME_CLS(__nv_bfloat16, 3); else if (nv <= 6) TOME_CLS(__nv_bfloat16, 6); else TOME_CLS(__nv_bfloat16, 8); }
+  else return set_error(TOME_ERR_DTYPE, "tome_cls_rows: unsupported dtype %d", dtype);
+#undef TOME_CLS
+  TOME_LAUNCH_CHECK("cls_rows_kernel");
+  return TOME_OK;
+}
+
 int launch_merge_source(const tome_plan* plan, const float* source, int n0, float thr, float* out, cudaStream_t st) {
   const int nout = plan->n - plan->r;
   if (source) {

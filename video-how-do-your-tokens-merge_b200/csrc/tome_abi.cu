@@ -89,6 +89,17 @@ int launch_traj_temporal(const void*, const void*, const void*, long long, int, 
 int launch_split3(const void*, long long, int, long long, void*, cudaStream_t);
 int launch_linear_f32(const void*, const void*, const void*, int, int, int, int, int, void*, void*, cudaStream_t);
 int launch_attention_f32(const void*, int, int, int, float, const float*, int, void*, void*, cudaStream_t);
+struct ClsArgs {
+  const void *a, *add, *mean_src;
+  long long a_sb, add_sb, m_sb, m_st;
+  int mean_t;
+  void *sum_out, *normed_out;
+  long long s_sb, n_sb, n_sr;
+  int reps, c;
+  const void *ln_w, *ln_b;
+  float eps;
+};
+int launch_cls_rows(const ClsArgs&, int, int, cudaStream_t);
 int launch_source_compose(const tome_plan*, const int*, int, int, float, int*, cudaStream_t);
 int launch_source_dense(const int*, int, int, int, float*, cudaStream_t);
 int launch_random_rowmax(void*, long long, int, int, int, int, int, float*, int*, float*, int, cudaStream_t);
@@ -526,6 +537,26 @@ int tome_attention_f32(const void* qkv3, int32_t b, int32_t n, int32_t heads, in
   TOME_CHECK_ARG(qkv3 && (out || out_planes) && b > 0 && n > 0 && heads > 0 && unbiased_queries >= 0, "tome_attention_f32: NULL pointer or empty shape");
   if (d != 64) return set_error(TOME_ERR_UNSUPPORTED, "tome_attention_f32: head dimension %d (64 only)", d);
   return launch_attention_f32(qkv3, b, n, heads, scale, key_bias, unbiased_queries, out, out_planes, (cudaStream_t)stream);
+}
+
+int tome_cls_rows(const void* a, int64_t a_stride_b, const void* add, int64_t add_stride_b, const void* mean_src, int64_t mean_stride_b,
+                  int64_t mean_stride_t, int32_t mean_t, int32_t dtype, int32_t batch, int32_t c, void* sum_out, int64_t sum_stride_b,
+                  const void* ln_weight, const void* ln_bias, float ln_eps, void* normed_out, int64_t normed_stride_b,
+                  int64_t normed_stride_rep, int32_t reps, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(a && batch > 0 && c > 0 && (sum_out || normed_out), "tome_cls_rows: NULL input or nothing to write");
+  TOME_CHECK_ARG(!normed_out || (ln_weight && reps > 0), "tome_cls_rows: LayerNorm output without a weight / replica count");
+  TOME_CHECK_ARG(!mean_src || mean_t > 0, "tome_cls_rows: mean source without a frame count");
+  const int e = dtype == TOME_F32 ? 4 : 8;
+  const uintptr_t al = (uintptr_t)a | (uintptr_t)add | (uintptr_t)mean_src | (uintptr_t)sum_out | (uintptr_t)normed_out | (uintptr_t)ln_weight | (uintptr_t)ln_bias;
+  if ((al & 15) || a_stride_b % e || add_stride_b % e || mean_stride_b % e || mean_stride_t % e || sum_stride_b % e || normed_stride_b % e || normed_stride_rep % e)
+    return set_error(TOME_ERR_ALIGN, "tome_cls_rows: 16-byte aligned rows required");
+  ClsArgs g;
+  g.a = a; g.add = add; g.mean_src = mean_src; g.a_sb = a_stride_b; g.add_sb = add_stride_b; g.m_sb = mean_stride_b; g.m_st = mean_stride_t;
+  g.mean_t = mean_src ? mean_t : 0; g.sum_out = sum_out; g.normed_out = normed_out; g.s_sb = sum_stride_b; g.n_sb = normed_stride_b;
+  g.n_sr = normed_stride_rep; g.reps = reps; g.c = c; g.ln_w = ln_weight; g.ln_b = ln_bias; g.eps = ln_eps;
+  return launch_cls_rows(g, dtype, batch, (cudaStream_t)stream);
 }
 
 }  // extern "C"

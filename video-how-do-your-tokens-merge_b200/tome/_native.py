@@ -18,7 +18,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 21
+ABI_VERSION = 22
 
 TOME_F32, TOME_BF16, TOME_U8 = 0, 1, 2
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -33,7 +33,7 @@ EXPORTS = (
     "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_linear_gelu", "tome_unmerge",
     "tome_match_sets_workspace_bytes", "tome_match_sets", "tome_group_reduce", "tome_gather_rows",
     "tome_source_compose", "tome_source_dense", "tome_random_rowmax", "tome_merge_add_norm_rv", "tome_rows_add_layernorm", "tome_attn_short",
-    "tome_frames_attention", "tome_traj_temporal", "tome_split3", "tome_linear_f32", "tome_attention_f32",
+    "tome_frames_attention", "tome_traj_temporal", "tome_split3", "tome_linear_f32", "tome_attention_f32", "tome_cls_rows",
 )
 
 
@@ -137,8 +137,10 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         getattr(lib, name).restype = c_i32
     lib.tome_frames_attention.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp]
     lib.tome_traj_temporal.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]
+    lib.tome_cls_rows.argtypes = [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_f32,
+                                  c_vp, c_i64, c_i64, c_i32, c_vp]
     for name in ("tome_source_compose", "tome_source_dense", "tome_random_rowmax", "tome_merge_add_norm_rv", "tome_rows_add_layernorm",
-                 "tome_attn_short", "tome_frames_attention", "tome_traj_temporal"):
+                 "tome_attn_short", "tome_frames_attention", "tome_traj_temporal", "tome_cls_rows"):
         getattr(lib, name).restype = c_i32
     for name in ("tome_device_check", "tome_match", "tome_match_heads", "tome_rowmax", "tome_select", "tome_merge", "tome_merge_norm", "tome_merge_add_norm", "tome_add_layernorm", "tome_add_rows_layernorm",
                  "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_linear_gelu", "tome_unmerge",
@@ -585,6 +587,35 @@ def rows_add_layernorm(a: torch.Tensor, b: Optional[torch.Tensor], norm, sum_out
                                            None if sum_out is None else _strides3(sum_out),
                                            None if normed_out is None else normed_out.data_ptr(),
                                            None if normed_out is None else _strides3(normed_out), _stream(a)), lib)
+
+
+def cls_rows(a: torch.Tensor, add: Optional[torch.Tensor] = None, mean_src: Optional[torch.Tensor] = None,
+             sum_out: Optional[torch.Tensor] = None, norm=None, normed_out: Optional[torch.Tensor] = None) -> None:
+    """The class-token rows of a divided space-time block in one launch (include/tome_b200.h: tome_cls_rows):
+    ``sum = a (+ mean_src.mean(1)) (+ add)`` on (B, C) row views, each step rounded to the dtype as the separate torch ops
+    round; ``sum_out`` (B, C) gets the sum, ``normed_out`` (B, reps, C) gets LayerNorm(sum) in every replica.  All arguments
+    are views with unit channel stride; ``mean_src`` is (B, T, C)."""
+    lib = load_library()
+    _require_cuda(a, "a")
+    B, C = a.shape
+    for t, nd in ((add, 2), (mean_src, 3), (sum_out, 2), (normed_out, 3)):
+        if t is not None and (t.dim() != nd or t.size(0) != B or t.size(-1) != C or t.stride(-1) != 1 or t.dtype != a.dtype
+                              or t.device != a.device):
+            raise RuntimeError("tome_b200: cls_rows needs (B, [T,] C) views of one dtype with unit channel stride")
+    if a.stride(1) != 1:
+        raise RuntimeError("tome_b200: cls_rows needs unit channel stride")
+    wp = bp = None
+    eps = 0.0
+    if normed_out is not None:
+        wp, bp, eps = _norm_args(norm, a)
+    with torch.cuda.device(a.device):
+        _check(lib.tome_cls_rows(
+            a.data_ptr(), a.stride(0), None if add is None else add.data_ptr(), 0 if add is None else add.stride(0),
+            None if mean_src is None else mean_src.data_ptr(), 0 if mean_src is None else mean_src.stride(0),
+            0 if mean_src is None else mean_src.stride(1), 0 if mean_src is None else mean_src.size(1), _dtype_code(a), B, C,
+            None if sum_out is None else sum_out.data_ptr(), 0 if sum_out is None else sum_out.stride(0), wp, bp, eps,
+            None if normed_out is None else normed_out.data_ptr(), 0 if normed_out is None else normed_out.stride(0),
+            0 if normed_out is None else normed_out.stride(1), 0 if normed_out is None else normed_out.size(1), _stream(a)), lib)
 
 
 def add_layernorm(a: torch.Tensor, b: torch.Tensor, norm):

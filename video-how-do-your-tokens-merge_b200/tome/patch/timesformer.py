@@ -107,9 +107,10 @@ class ToMeBlockMixin:
         ns4 = ns.view(B, T, 1 + P, C)
         _native.rows_add_layernorm(x4, tf, _ln(self.norm1), xfull[:, 1:].unflatten(1, (P, T)), ns4[:, :, 1:].permute(0, 2, 1, 3))
         init_cls = x[:, 0]
-        ns4[:, :, 0] = self.norm1(init_cls)[:, None]                         # class token replicated per frame
+        _native.cls_rows(init_cls, norm=_ln(self.norm1), normed_out=ns4[:, :, 0])   # class token replicated per frame
         res_s, metric = self.attn(ns, attn_size, attn_bias)
-        cls = init_cls + res_s.view(B, T, 1 + P, C)[:, :, 0].mean(1)         # class token averaged over frames
+        cls = torch.empty(B, C, dtype=x.dtype, device=x.device)              # class token averaged over frames
+        _native.cls_rows(init_cls, mean_src=res_s.view(B, T, 1 + P, C)[:, :, 0], sum_out=cls)
         x = self.reduction_function(metric, xfull, info, B, T, P, norm=self.norm2, residual=res_s, cls=cls)
         y = self.mlp(_normed_or(self.norm2, x, info))
         # x + mlp(...) and the NEXT block's temporal_norm1 in one pass
@@ -121,7 +122,7 @@ class ToMeBlockMixin:
         nt = torch.empty(B, Pn, T, C, dtype=x.dtype, device=x.device)
         _native.rows_add_layernorm(x[:, 1:].unflatten(1, (Pn, T)), y[:, 1:].unflatten(1, (Pn, T)), _ln(nxt),
                                    s[:, 1:].unflatten(1, (Pn, T)), nt)
-        s[:, 0] = x[:, 0] + y[:, 0]
+        _native.cls_rows(x[:, 0], add=y[:, 0], sum_out=s[:, 0])
         info["normed_t"] = (s, nxt, nt)
         return s
 
