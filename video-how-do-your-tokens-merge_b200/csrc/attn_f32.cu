@@ -15,6 +15,8 @@
 //               the single softmax warp per scheduler was the critical path: 657 us at N = 1568): scores -> row maximum
 //               (halves exchanged through shared memory, one named barrier per block) -> exp2 / sum -> three P planes into
 //               swizzled shared memory -> accumulate O.
+#include <cstdlib>
+
 #include "tc_ptx.cuh"
 
 namespace tome {
@@ -302,6 +304,268 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   }
 }
 
+// ---- the same attention with the A operands in tensor memory ------------------------------------------------------------
+// The kernel above is bound by the shared-memory port, not by the tensor pipe: an SS-mode 128 x 64 x 16 MMA reads 6 KB of
+// operands per 32-cycle slot (192 B / cycle against a 128 B / cycle port; profiles/r02_attn_f32_ncu.txt).  Both A operands
+// can live in tensor memory instead -- Q for the whole CTA (three planes x 32 columns, written once by the softmax threads
+// straight from global memory: no Q tile, no TMA for it) and P (three planes x 32 columns, written with tcgen05.st in the
+// layout the softmax threads already hold: lane = row, column c = keys 2c, 2c + 1) -- so every MMA reads only its 2 KB B
+// operand from shared memory and runs at the tensor pipe's floor.  The 96 KB of Q / P tiles that leaves pays for a third
+// K / V stage.  TMEM columns: S0 0..63 | S1 64..127 | O 128..191 | P h,m,l 192..287 | Q h,m,l 288..383 (512 allocated).
+constexpr int AT_NST = 3;
+constexpr uint32_t AT_S1 = 64u, AT_O = 128u, AT_P = 192u, AT_Q = 288u;
+
+// p -> exact bf16 planes of a pair of probabilities without the single-value F2F conversions (XU pipe, 16 / clk / SM: with 64 of
+// them per thread and block that pipe was as busy as the tensor pipe): the packed conversion is an ALU instruction and a
+// bf16 is the upper half of its fp32
+__device__ __forceinline__ void af_split_pair(float p0, float p1, uint32_t& wh, uint32_t& wm, uint32_t& wl) {
+  wh = af_pack(p0, p1);
+  const float r0 = p0 - __uint_as_float(wh << 16), r1 = p1 - __uint_as_float(wh & 0xffff0000u);
+  wm = af_pack(r0, r1);
+  wl = af_pack(r0 - __uint_as_float(wm << 16), r1 - __uint_as_float(wm & 0xffff0000u));
+}
+
+template <bool HAS_BIAS>
+__global__ void __launch_bounds__(AF_THREADS, 1)
+attn_f32_ts_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16* __restrict__ qkv3, const AfParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler, see the MMA warp
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int C = p.heads * AF_D, C3 = 3 * C;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sm_kv = base, bars = sm_kv + (uint32_t)AT_NST * AF_STAGE;
+  const uint32_t bar_q = bars, bar_p = bars + 8, bar_o = bars + 16, tmem_slot = bars + 24, bar_s = bars + 32, bar_sfree = bars + 48,
+                 bar_kfull = bars + 64, bar_kempty = bars + 96, bar_vfull = bars + 128, bar_vempty = bars + 160, sm_xch = bars + 192;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_kv);
+    mbar_init(bar_q, AF_SM); mbar_init(bar_p, AF_SM); mbar_init(bar_o, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_s + 8u * s, 1); mbar_init(bar_sfree + 8u * s, AF_SM); }
+    for (int s = 0; s < AT_NST; ++s) {
+      mbar_init(bar_kfull + 8u * s, 1); mbar_init(bar_kempty + 8u * s, 1);
+      mbar_init(bar_vfull + 8u * s, 1); mbar_init(bar_vempty + 8u * s, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int row0 = b * p.N;
+  const int nb = p.nblk;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int j = 0; j < nb; ++j) {
+        const uint32_t s = (uint32_t)(j % AT_NST), k = (uint32_t)(j / AT_NST);
+        const uint32_t st = sm_kv + s * AF_STAGE;
+        if (k >= 1) mbar_wait_sleep(bar_kempty + 8u * s, (k - 1) & 1u, 32);
+        mbar_expect_tx(bar_kfull + 8u * s, 3u * AF_KP);
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) tma_load_2d(st + pl * AF_KP, &map_kv, pl * C3 + C + h * AF_D, row0 + j * AF_BKV, bar_kfull + 8u * s);
+        if (k >= 1) mbar_wait_sleep(bar_vempty + 8u * s, (k - 1) & 1u, 32);
+        mbar_expect_tx(bar_vfull + 8u * s, 3u * AF_KP);
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) tma_load_2d(st + (3 + pl) * AF_KP, &map_kv, pl * C3 + 2 * C + h * AF_D, row0 + j * AF_BKV, bar_vfull + 8u * s);
+      }
+    }
+  } else if (warp == 1) {
+    // The MMA warp runs CONVERGED with warp-uniform operands and one elected lane issuing: written as `if (lane == 0)` the
+    // compiler cannot prove the operands uniform and wraps every tcgen05.mma in an ELECT / vote loop with register ->
+    // uniform-register moves -- ~70 cycles per MMA measured (profiles/r02_attn_f32_ncu.txt), twice the 32-cycle slot of a
+    // 128 x 64 x 16 MMA, and the issue of P V sits on the block-to-block critical path.  This form is one UTCHMMA per MMA.
+    const bool leader = elect_one_sync();
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AF_BKV >> 3) << 17) | ((uint32_t)(AF_BM >> 4) << 24);
+    const uint32_t idesc_o = idesc_s | (1u << 16);                          // B MN-major, N = 64 as well
+    const uint64_t dk0 = make_sw128_desc(sm_kv), dv0 = af_desc_mn(sm_kv + 3u * AF_KP);   // stage 0, plane h; a plane / stage further is
+    constexpr uint64_t PL = AF_KP >> 4, ST = AF_STAGE >> 4;                               // a constant in the address field
+    auto issue_s = [&](int j) {
+      const uint32_t s = (uint32_t)(j % AT_NST), k = (uint32_t)(j / AT_NST), sb = (uint32_t)(j & 1), kb = (uint32_t)(j >> 1);
+      mbar_wait(bar_kfull + 8u * s, k & 1u);
+      if (kb >= 1) mbar_wait(bar_sfree + 8u * sb, (kb - 1) & 1u);           // the softmax has pulled the previous S out of this buffer
+      tc_fence_after();
+      if (leader) {
+        const uint32_t d = tb + sb * AT_S1;
+        const uint64_t dk = dk0 + (uint64_t)s * ST;
+        // (query plane, key plane): l.h, h.l, m.m, m.h, h.m, h.h -- smallest products first; A: 8 columns per k-step,
+        // K: +32 bytes inside the swizzle row
+#define TOME_AT_S(QP_, KP_, ACC_)                                                                                        \
+        _Pragma("unroll") for (int ks = 0; ks < AF_D / 16; ++ks)                                                         \
+          umma_bf16_ts(d, tb + AT_Q + 32u * (QP_) + 8u * ks, dk + (KP_) * PL + (uint64_t)(2 * ks), idesc_s, (ACC_) || ks ? 1u : 0u);
+        TOME_AT_S(2, 0, 0) TOME_AT_S(0, 2, 1) TOME_AT_S(1, 1, 1) TOME_AT_S(1, 0, 1) TOME_AT_S(0, 1, 1) TOME_AT_S(0, 0, 1)
+#undef TOME_AT_S
+        umma_commit(bar_s + 8u * sb);
+        umma_commit(bar_kempty + 8u * s);
+      }
+      __syncwarp();
+    };
+    mbar_wait(bar_q, 0);
+    issue_s(0);
+    for (int j = 0; j < nb; ++j) {
+      if (j + 1 < nb) issue_s(j + 1);
+      const uint32_t s = (uint32_t)(j % AT_NST);
+      mbar_wait(bar_vfull + 8u * s, (uint32_t)((j / AT_NST) & 1));
+      mbar_wait(bar_p, (uint32_t)(j & 1));
+      tc_fence_after();
+      if (leader) {
+        const uint32_t d = tb + AT_O;
+        const uint64_t dv = dv0 + (uint64_t)s * ST;
+        // (P plane, V plane), same order; P: 8 columns per 16 keys; V: 16 keys = 2048 bytes
+#define TOME_AT_O(PP_, VP_, ACC_)                                                                                        \
+        _Pragma("unroll") for (int ks = 0; ks < AF_BKV / 16; ++ks)                                                       \
+          umma_bf16_ts(d, tb + AT_P + 32u * (PP_) + 8u * ks, dv + (VP_) * PL + (uint64_t)(128 * ks), idesc_o, (ACC_) || ks ? 1u : 0u);
+        TOME_AT_O(2, 0, 0) TOME_AT_O(0, 2, 1) TOME_AT_O(1, 1, 1) TOME_AT_O(1, 0, 1) TOME_AT_O(0, 1, 1) TOME_AT_O(0, 0, 1)
+#undef TOME_AT_O
+        umma_commit(bar_o);
+        umma_commit(bar_vempty + 8u * s);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int half = (warp - 2) >> 2;                          // which 32 key columns of a block / 32 channels of O
+    const int row = q4 * 32 + lane;
+    const int s_idx = qt * AF_BM + row;                        // query token within the clip
+    const bool live = s_idx < p.N;
+    const bool biased = p.bias != nullptr && s_idx >= p.nobias_q;
+    const uint32_t tlane = (uint32_t)(q4 * 32) << 16;
+    const float* brow = p.bias ? p.bias + (long long)b * p.N : nullptr;
+    const bool bias_vec = (p.N & 3) == 0;
+    float* xch = reinterpret_cast<float*>(gen + (sm_xch - base));          // [2 blocks][2 halves][128 rows]
+    const float LOG2E = 1.4426950408889634f;
+    {   // this row's query planes into tensor memory: 32 channels (64 bytes) per plane and thread; rows past the tensor are zero
+      const bool in = (long long)row0 + s_idx < (long long)p.B * p.N;
+      const uint4* src = reinterpret_cast<const uint4*>(qkv3 + ((long long)row0 + s_idx) * (3LL * C3) + h * AF_D + 32 * half);
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) {
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 v = in ? __ldg(src + (size_t)pl * (C3 / 8) + i) : make_uint4(0u, 0u, 0u, 0u);
+          w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+        tmem_st16(tmem_base + tlane + AT_Q + 32u * pl + 16u * half, w);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      af_arrive(bar_q);
+    }
+    float m = -INFINITY, l = 0.f;
+    float oacc[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) oacc[e] = 0.f;
+    auto fold_o = [&]() {                                      // O_acc += the finished P V block
+      float v[32];
+      tmem_ld32(tmem_base + tlane + AT_O + 32u * half, v);
+#pragma unroll
+      for (int e = 0; e < 32; ++e) oacc[e] += v[e];
+    };
+    for (int j = 0; j < nb; ++j) {
+      const uint32_t sb = (uint32_t)(j & 1), k = (uint32_t)(j >> 1);
+      mbar_wait(bar_s + 8u * sb, k & 1u);
+      tc_fence_after();
+      float t[32];
+      tmem_ld32(tmem_base + tlane + sb * AT_S1 + 32u * half, t);
+      tc_fence_before();
+      af_arrive(bar_sfree + 8u * sb);
+      const int key0 = j * AF_BKV + 32 * half;
+      if (HAS_BIAS) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (biased && bias_vec && key0 + e + 3 < p.N) b4 = __ldg(reinterpret_cast<const float4*>(brow + key0 + e));
+          else if (biased && key0 + e + 3 < p.N) {             // rows of the bias are not 16-byte aligned (n % 4 != 0)
+            b4.x = __ldg(brow + key0 + e); b4.y = __ldg(brow + key0 + e + 1); b4.z = __ldg(brow + key0 + e + 2); b4.w = __ldg(brow + key0 + e + 3);
+          } else if (biased) {
+            b4.x = key0 + e < p.N ? __ldg(brow + key0 + e) : 0.f;
+            b4.y = key0 + e + 1 < p.N ? __ldg(brow + key0 + e + 1) : 0.f;
+            b4.z = key0 + e + 2 < p.N ? __ldg(brow + key0 + e + 2) : 0.f;
+          }
+          t[e] = fmaf(t[e], p.scale_log2e, b4.x * LOG2E);
+          t[e + 1] = fmaf(t[e + 1], p.scale_log2e, b4.y * LOG2E);
+          t[e + 2] = fmaf(t[e + 2], p.scale_log2e, b4.z * LOG2E);
+          t[e + 3] = fmaf(t[e + 3], p.scale_log2e, b4.w * LOG2E);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) t[e] *= p.scale_log2e;    // (the reference's q * scale, in log2 units)
+      }
+      if (key0 + 32 > p.N) {                                   // last block: keys beyond the clip
+#pragma unroll
+        for (int e = 0; e < 32; ++e) if (key0 + e >= p.N) t[e] = -INFINITY;
+      }
+      float bmax = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) bmax = fmaxf(bmax, fmaxf(fmaxf(t[e], t[e + 1]), fmaxf(t[e + 2], t[e + 3])));
+      xch[(sb * 2 + half) * AF_BM + row] = bmax;               // the row's other half
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      bmax = fmaxf(bmax, xch[(sb * 2 + (half ^ 1)) * AF_BM + row]);
+      const float m_new = fmaxf(m, bmax);                      // finite: the first half of every block holds a real key
+      const float alpha = af_ex2(m - m_new);                   // 0 on the first block (m = -inf)
+      float l0 = 0.f, l1 = 0.f;
+      uint32_t wh[16], wm[16], wl[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float p0 = af_ex2(t[2 * i] - m_new), p1 = af_ex2(t[2 * i + 1] - m_new);
+        l0 += p0; l1 += p1;
+        af_split_pair(p0, p1, wh[i], wm[i], wl[i]);
+      }
+      if (j > 0) {                                             // P V of the previous block: also frees the P columns
+        mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+        fold_o();
+      }
+#pragma unroll
+      for (int e = 0; e < 32; ++e) oacc[e] *= alpha;
+      l *= alpha;
+      m = m_new;
+      // the three P planes: this thread's 32 keys are columns 16 * half .. + 15 of each plane (two keys per column)
+      tmem_st16(tmem_base + tlane + AT_P + 16u * half, wh);
+      tmem_st16(tmem_base + tlane + AT_P + 32u + 16u * half, wm);
+      tmem_st16(tmem_base + tlane + AT_P + 64u + 16u * half, wl);
+      l += l0 + l1;
+      tmem_st_wait();
+      tc_fence_before();                                       // the O columns were read above: P V (j) may overwrite them
+      af_arrive(bar_p);
+    }
+    mbar_wait(bar_o, (uint32_t)((nb - 1) & 1));
+    tc_fence_after();
+    fold_o();
+    asm volatile("bar.sync 1, 256;" ::: "memory");             // the row sum of both halves (same running maximum)
+    xch[half * AF_BM + row] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l += xch[(half ^ 1) * AF_BM + row];
+    if (live) {
+      const float inv = 1.0f / l;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) oacc[e] *= inv;
+      if (p.out) {
+        float4* dst = reinterpret_cast<float4*>(p.out + ((long long)b * p.N + s_idx) * C + h * AF_D + 32 * half);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dst[e] = make_float4(oacc[4 * e], oacc[4 * e + 1], oacc[4 * e + 2], oacc[4 * e + 3]);
+      }
+      if (p.out3) {
+        __nv_bfloat16* d3 = p.out3 + ((long long)b * p.N + s_idx) * 3 * C + h * AF_D + 32 * half;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) store_planes8(d3 + 8 * e, C, reinterpret_cast<const float(&)[8]>(oacc[8 * e]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 int launch_attention_f32(const void* qkv3, int B, int N, int heads, float scale, const float* bias, int nobias_q, void* out,
                          void* out3, cudaStream_t st) {
   if (!out && !out3) return set_error(TOME_ERR_ARG, "tome_attention_f32: no output");
@@ -317,11 +581,24 @@ int launch_attention_f32(const void* qkv3, int B, int N, int heads, float scale,
   if (rc) return rc;
   rc = make_bf16_map(&map_kv, qkv3, rows, cols, cols, AF_BKV, "tome_attention_f32");
   if (rc) return rc;
+  dim3 grid((N + AF_BM - 1) / AF_BM, heads, B);
+  if (grid.z > 65535) return set_error(TOME_ERR_UNSUPPORTED, "tome_attention_f32: batch %d > 65535", B);
+  static const bool ss_mode = [] { const char* e = getenv("TOME_ATTN_F32_SS"); return e && e[0] == '1'; }();
+  if (!ss_mode) {                                    // A operands (Q, P) in tensor memory
+    const size_t smem = 1024 + AT_NST * AF_STAGE + 192 + 4 * AF_BM * sizeof(float);
+    static PerDeviceOnce once;
+    if (once.first_time()) {
+      TOME_CUDA(cudaFuncSetAttribute(attn_f32_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      TOME_CUDA(cudaFuncSetAttribute(attn_f32_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (bias) attn_f32_ts_kernel<true><<<grid, AF_THREADS, smem, st>>>(map_kv, (const __nv_bfloat16*)qkv3, p);
+    else attn_f32_ts_kernel<false><<<grid, AF_THREADS, smem, st>>>(map_kv, (const __nv_bfloat16*)qkv3, p);
+    TOME_LAUNCH_CHECK("attn_f32_ts_kernel");
+    return TOME_OK;
+  }
   const size_t smem = 1024 + 3 * AF_QP + 2 * AF_STAGE + 3 * AF_QP + 128 + 4 * AF_BM * sizeof(float);
   static PerDeviceOnce once;
   if (once.first_time()) TOME_CUDA(cudaFuncSetAttribute(attn_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((N + AF_BM - 1) / AF_BM, heads, B);
-  if (grid.z > 65535) return set_error(TOME_ERR_UNSUPPORTED, "tome_attention_f32: batch %d > 65535", B);
   attn_f32_kernel<<<grid, AF_THREADS, smem, st>>>(map_q, map_kv, p);
   TOME_LAUNCH_CHECK("attn_f32_kernel");
   return TOME_OK;
