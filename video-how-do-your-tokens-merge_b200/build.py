@@ -19,7 +19,7 @@ SOURCES = ["tome_abi.cu", "match_exact.cu", "match_sm100.cu", "plan_cluster.cu",
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("NVCC_EXTRA", "").split()          # e.g. -DTOME_ATTN_TRACE for tools/trace_attn_f32.py
 
 
 def _nvcc():

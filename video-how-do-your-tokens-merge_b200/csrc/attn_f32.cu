@@ -7,23 +7,25 @@
 //     P           fp32 softmax numerators, split exactly into three bf16 planes in registers
 //     O = P V     six plane products, V consumed as TMA wrote it (rows = keys: MN-major B operand)
 // Flash-style: one CTA per (128 queries, head, clip) walks the keys in blocks of 64 with a running maximum; the block's
-// scores are read out of TMEM ONCE (64 values per thread), the block's P V lands in its own TMEM columns and is folded
+// scores are read out of TMEM ONCE (64 values per row), the block's P V lands in its own TMEM columns and is folded
 // into the row's fp32 accumulator in registers with the usual rescale, so no accumulator is ever rescaled in TMEM.
-//   warp 0      TMA producer: Q planes once, then K / V planes of each key block (2-stage ring, SWIZZLE_128B);
-//   warp 1      MMA issuer: S(j + 1) is issued before waiting for P(j), so it runs beside the softmax of block j;
-//   warps 2-9   TWO threads per query row, 32 key columns of the block and 32 channels of O each (with one thread per row
-//               the single softmax warp per scheduler was the critical path: 657 us at N = 1568): scores -> row maximum
-//               (halves exchanged through shared memory, one named barrier per block) -> exp2 / sum -> three P planes into
-//               swizzled shared memory -> accumulate O.
+//   warp 0      TMA producer: K / V planes of each key block (3-stage ring, SWIZZLE_128B, separate K and V barriers);
+//   warp 1      S issuer, warp 10 P V issuer: converged warps, one elected lane, one UTCHMMA per MMA;
+//   warps 2-9   TWO threads per query row, 32 key columns of the block and 32 channels of O each: Q planes into TMEM once,
+//               then per block scores -> row maximum (halves exchanged through shared memory) -> exp2 / sum -> three P
+//               planes into TMEM (tcgen05.st) -> accumulate O.
+// History of the kernel (profiles/r02_attn_f32_ncu.txt): 637 us at 8 x 12 x 1568 with one barrier pair per stage; 480 us with
+// separate K / V barriers; 326 us once the MMA warp ran converged (as `if (lane == 0)` every tcgen05.mma sat in an ELECT /
+// vote loop of ~70 cycles, twice the MMA's own 32-cycle slot) with the A operands in tensor memory; 279 us with the two
+// issue streams in separate warps, where the tensor pipe is busy back to back in steady state (1536 cycles per block).
 #include <cstdlib>
 
 #include "tc_ptx.cuh"
 
 namespace tome {
 
-constexpr int AF_BM = 128, AF_BKV = 64, AF_D = 64, AF_THREADS = 320;      // TMA, MMA, 2 x 4 softmax warps
+constexpr int AF_BM = 128, AF_BKV = 64, AF_D = 64;
 constexpr int AF_SM = 256;                                                  // softmax threads: two per query row
-constexpr uint32_t AF_QP = AF_BM * 128u;            // one Q / P plane: 128 rows x 128 bytes
 constexpr uint32_t AF_KP = AF_BKV * 128u;           // one K / V plane of a key block: 64 rows x 128 bytes
 constexpr uint32_t AF_STAGE = 6u * AF_KP;           // K h,m,l | V h,m,l
 
@@ -55,264 +57,22 @@ __device__ __forceinline__ uint32_t af_pack(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(AF_THREADS, 1)
-attn_f32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const AfParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int C = p.heads * AF_D, C3 = 3 * C;
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sm_q = base, sm_kv = sm_q + 3u * AF_QP, sm_p = sm_kv + 2u * AF_STAGE, bars = sm_p + 3u * AF_QP;
-  const uint32_t bar_q = bars, bar_kfull = bars + 8, bar_kempty = bars + 24, bar_s = bars + 40, bar_sfree = bars + 56,
-                 bar_p = bars + 72, bar_o = bars + 80, tmem_slot = bars + 88, bar_vfull = bars + 96, bar_vempty = bars + 112,
-                 sm_xch = bars + 128;
-  uint8_t* p_gen = gen + (sm_p - base);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
-
-  if (threadIdx.x == 0) {
-    prefetch_tensormap(&map_q);
-    prefetch_tensormap(&map_kv);
-    mbar_init(bar_q, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_kfull + 8u * s, 1); mbar_init(bar_kempty + 8u * s, 1);
-      mbar_init(bar_vfull + 8u * s, 1); mbar_init(bar_vempty + 8u * s, 1);
-      mbar_init(bar_s + 8u * s, 1); mbar_init(bar_sfree + 8u * s, AF_SM);
-    }
-    mbar_init(bar_p, AF_SM); mbar_init(bar_o, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-  const int row0 = b * p.N;
-  const int nb = p.nblk;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(bar_q, 3u * AF_QP);
-#pragma unroll
-      for (int pl = 0; pl < 3; ++pl) tma_load_2d(sm_q + pl * AF_QP, &map_q, pl * C3 + h * AF_D, row0 + qt * AF_BM, bar_q);
-      // K of a stage is free as soon as S (j) has been computed, V only after P V (j): separate barriers, so the K of block
-      // j + 2 is requested a whole iteration before it is needed (one barrier pair per stage exposed ~1.5 us of load
-      // latency per block: 637 us at N = 1568, tensor pipe 31 % busy -- profiles/r02_attn_f32_ncu.txt)
-      for (int j = 0; j < nb; ++j) {
-        const uint32_t s = (uint32_t)(j & 1), k = (uint32_t)(j >> 1);
-        const uint32_t st = sm_kv + s * AF_STAGE;
-        if (k >= 1) mbar_wait_sleep(bar_kempty + 8u * s, (k - 1) & 1u, 32);
-        mbar_expect_tx(bar_kfull + 8u * s, 3u * AF_KP);
-#pragma unroll
-        for (int pl = 0; pl < 3; ++pl) tma_load_2d(st + pl * AF_KP, &map_kv, pl * C3 + C + h * AF_D, row0 + j * AF_BKV, bar_kfull + 8u * s);
-        if (k >= 1) mbar_wait_sleep(bar_vempty + 8u * s, (k - 1) & 1u, 32);
-        mbar_expect_tx(bar_vfull + 8u * s, 3u * AF_KP);
-#pragma unroll
-        for (int pl = 0; pl < 3; ++pl) tma_load_2d(st + (3 + pl) * AF_KP, &map_kv, pl * C3 + 2 * C + h * AF_D, row0 + j * AF_BKV, bar_vfull + 8u * s);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AF_BKV >> 3) << 17) | ((uint32_t)(AF_BM >> 4) << 24);
-      const uint32_t idesc_o = idesc_s | (1u << 16);                        // B MN-major, N = 64 as well
-      // plane pairs (query / P plane, key / V plane): h.h, h.m, m.h, m.m, h.l, l.h
-      const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
-      // descriptors once: the issuing thread is a single lane and a freshly built descriptor pair cost ~16 instructions per
-      // MMA, as long as the MMA itself (24 per stage)
-      uint64_t dq[3], dp[3], dk[2][3], dv[2][3];
-#pragma unroll
-      for (int pl = 0; pl < 3; ++pl) {
-        dq[pl] = make_sw128_desc(sm_q + pl * AF_QP);
-        dp[pl] = make_sw128_desc(sm_p + pl * AF_QP);
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          dk[s][pl] = make_sw128_desc(sm_kv + s * AF_STAGE + pl * AF_KP);
-          dv[s][pl] = af_desc_mn(sm_kv + s * AF_STAGE + (3 + pl) * AF_KP);
-        }
-      }
-      auto issue_s = [&](int j) {
-        const uint32_t s = (uint32_t)(j & 1), k = (uint32_t)(j >> 1);
-        mbar_wait(bar_kfull + 8u * s, k & 1u);
-        if (k >= 1) mbar_wait(bar_sfree + 8u * s, (k - 1) & 1u);             // the softmax has pulled the previous S out of this buffer
-        tc_fence_after();
-        const uint32_t d = tmem_base + s * 64u;
-        uint32_t first = 1u;
-#pragma unroll
-        for (int t = 5; t >= 0; --t) {                                       // smallest products first
-#pragma unroll
-          for (int ks = 0; ks < AF_D / 16; ++ks) {                           // +32 bytes inside the swizzle row per k-step
-            umma_bf16(d, dq[pa[t]] + (uint64_t)(2 * ks), (s ? dk[1][pb[t]] : dk[0][pb[t]]) + (uint64_t)(2 * ks), idesc_s, first ? 0u : 1u);
-            first = 0u;
-          }
-        }
-        umma_commit(bar_s + 8u * s);
-        umma_commit(bar_kempty + 8u * s);
-      };
-      mbar_wait(bar_q, 0);
-      issue_s(0);
-      for (int j = 0; j < nb; ++j) {
-        if (j + 1 < nb) issue_s(j + 1);
-        const uint32_t s = (uint32_t)(j & 1);
-        mbar_wait(bar_vfull + 8u * s, (uint32_t)((j >> 1) & 1));
-        mbar_wait(bar_p, (uint32_t)(j & 1));
-        tc_fence_after();
-        const uint32_t d = tmem_base + 128u;
-        uint32_t first = 1u;
-#pragma unroll
-        for (int t = 5; t >= 0; --t) {
-#pragma unroll
-          for (int ks = 0; ks < AF_BKV / 16; ++ks) {                         // P: +32 bytes per k-step; V: 16 keys = 2048 bytes
-            umma_bf16(d, dp[pa[t]] + (uint64_t)(2 * ks), (s ? dv[1][pb[t]] : dv[0][pb[t]]) + (uint64_t)(128 * ks), idesc_o, first ? 0u : 1u);
-            first = 0u;
-          }
-        }
-        umma_commit(bar_o);
-        umma_commit(bar_vempty + 8u * s);
-      }
-    }
-  } else {
-    const int q4 = warp & 3;
-    const int half = (warp - 2) >> 2;                          // which 32 key columns of a block / 32 channels of O
-    const int row = q4 * 32 + lane;
-    const int s_idx = qt * AF_BM + row;                        // query token within the clip
-    const bool live = s_idx < p.N;
-    const bool biased = p.bias != nullptr && s_idx >= p.nobias_q;
-    const uint32_t tlane = (uint32_t)(q4 * 32) << 16;
-    const float* brow = p.bias ? p.bias + (long long)b * p.N : nullptr;
-    const bool bias_vec = (p.N & 3) == 0;
-    float* xch = reinterpret_cast<float*>(gen + (sm_xch - base));          // [2 blocks][2 halves][128 rows]
-    const float LOG2E = 1.4426950408889634f;
-    float m = -INFINITY, l = 0.f;
-    float oacc[32];
-#pragma unroll
-    for (int e = 0; e < 32; ++e) oacc[e] = 0.f;
-    auto fold_o = [&]() {                                      // O_acc += the finished P V block (TMEM columns 128..191)
-      float v[32];
-      tmem_ld32(tmem_base + tlane + 128u + 32u * half, v);
-#pragma unroll
-      for (int e = 0; e < 32; ++e) oacc[e] += v[e];
-    };
-    for (int j = 0; j < nb; ++j) {
-      const uint32_t sb = (uint32_t)(j & 1), k = (uint32_t)(j >> 1);
-      mbar_wait(bar_s + 8u * sb, k & 1u);
-      tc_fence_after();
-      float t[32];
-      tmem_ld32(tmem_base + tlane + sb * 64u + 32u * half, t);
-      tc_fence_before();
-      af_arrive(bar_sfree + 8u * sb);
-      // logits in log2 units, key bias, padding
-      const int key0 = j * AF_BKV + 32 * half;
-#pragma unroll
-      for (int e = 0; e < 32; e += 4) {
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (biased && bias_vec && key0 + e + 3 < p.N) b4 = __ldg(reinterpret_cast<const float4*>(brow + key0 + e));
-        else if (biased && key0 + e + 3 < p.N) {               // rows of the bias are not 16-byte aligned (n % 4 != 0)
-          b4.x = __ldg(brow + key0 + e); b4.y = __ldg(brow + key0 + e + 1); b4.z = __ldg(brow + key0 + e + 2); b4.w = __ldg(brow + key0 + e + 3);
-        } else if (biased) {
-          b4.x = key0 + e < p.N ? __ldg(brow + key0 + e) : 0.f;
-          b4.y = key0 + e + 1 < p.N ? __ldg(brow + key0 + e + 1) : 0.f;
-          b4.z = key0 + e + 2 < p.N ? __ldg(brow + key0 + e + 2) : 0.f;
-        }
-        t[e] = fmaf(t[e], p.scale_log2e, b4.x * LOG2E);
-        t[e + 1] = fmaf(t[e + 1], p.scale_log2e, b4.y * LOG2E);
-        t[e + 2] = fmaf(t[e + 2], p.scale_log2e, b4.z * LOG2E);
-        t[e + 3] = fmaf(t[e + 3], p.scale_log2e, b4.w * LOG2E);
-      }
-      if (key0 + 32 > p.N) {                                   // last block: keys beyond the clip
-#pragma unroll
-        for (int e = 0; e < 32; ++e) if (key0 + e >= p.N) t[e] = -INFINITY;
-      }
-      float bmax = -INFINITY;
-#pragma unroll
-      for (int e = 0; e < 32; e += 4) bmax = fmaxf(bmax, fmaxf(fmaxf(t[e], t[e + 1]), fmaxf(t[e + 2], t[e + 3])));
-      // the row's other half
-      xch[(sb * 2 + half) * AF_BM + row] = bmax;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      bmax = fmaxf(bmax, xch[(sb * 2 + (half ^ 1)) * AF_BM + row]);
-      const float m_new = fmaxf(m, bmax);                      // finite: the first half of every block holds a real key
-      const float alpha = af_ex2(m - m_new);                   // 0 on the first block (m = -inf)
-      // probabilities, split exactly into three bf16 planes -- computed BEFORE waiting for the previous block's P V (which
-      // still reads the P tile), so the exponentials run beside those MMAs and only the stores wait
-      float l0 = 0.f, l1 = 0.f;
-      uint32_t wh[16], wm[16], wl[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float p0 = af_ex2(t[2 * i] - m_new), p1 = af_ex2(t[2 * i + 1] - m_new);
-        l0 += p0; l1 += p1;
-        const float h0 = __bfloat162float(__float2bfloat16_rn(p0)), h1 = __bfloat162float(__float2bfloat16_rn(p1));
-        const float r0 = p0 - h0, r1 = p1 - h1;
-        const float m0 = __bfloat162float(__float2bfloat16_rn(r0)), m1 = __bfloat162float(__float2bfloat16_rn(r1));
-        wh[i] = af_pack(h0, h1);
-        wm[i] = af_pack(m0, m1);
-        wl[i] = af_pack(r0 - m0, r1 - m1);
-      }
-      if (j > 0) {                                             // P V of the previous block: also frees the P tile
-        mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
-        tc_fence_after();
-        fold_o();
-      }
-#pragma unroll
-      for (int e = 0; e < 32; ++e) oacc[e] *= alpha;
-      l *= alpha;
-      m = m_new;
-      // K-major SWIZZLE_128B P tiles: row = 128 bytes, 16-byte chunk index (4 * half + cc) XOR (row % 8)
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const uint32_t ci = (uint32_t)(4 * half + cc);
-        uint8_t* dst = p_gen + (size_t)row * 128 + ((ci ^ ((uint32_t)row & 7u)) << 4);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(wh[4 * cc], wh[4 * cc + 1], wh[4 * cc + 2], wh[4 * cc + 3]);
-        *reinterpret_cast<uint4*>(dst + AF_QP) = make_uint4(wm[4 * cc], wm[4 * cc + 1], wm[4 * cc + 2], wm[4 * cc + 3]);
-        *reinterpret_cast<uint4*>(dst + 2 * AF_QP) = make_uint4(wl[4 * cc], wl[4 * cc + 1], wl[4 * cc + 2], wl[4 * cc + 3]);
-      }
-      l += l0 + l1;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      tc_fence_before();                                       // the O columns were read above: P V (j) may overwrite them
-      af_arrive(bar_p);
-    }
-    mbar_wait(bar_o, (uint32_t)((nb - 1) & 1));
-    tc_fence_after();
-    fold_o();
-    // the row sum of both halves (same running maximum, so the partial sums simply add)
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    xch[half * AF_BM + row] = l;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    l += xch[(half ^ 1) * AF_BM + row];
-    if (live) {
-      const float inv = 1.0f / l;
-#pragma unroll
-      for (int e = 0; e < 32; ++e) oacc[e] *= inv;
-      if (p.out) {
-        float4* dst = reinterpret_cast<float4*>(p.out + ((long long)b * p.N + s_idx) * C + h * AF_D + 32 * half);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) dst[e] = make_float4(oacc[4 * e], oacc[4 * e + 1], oacc[4 * e + 2], oacc[4 * e + 3]);
-      }
-      if (p.out3) {
-        __nv_bfloat16* d3 = p.out3 + ((long long)b * p.N + s_idx) * 3 * C + h * AF_D + 32 * half;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) store_planes8(d3 + 8 * e, C, reinterpret_cast<const float(&)[8]>(oacc[8 * e]));
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
-  }
-}
-
-// ---- the same attention with the A operands in tensor memory ------------------------------------------------------------
-// The kernel above is bound by the shared-memory port, not by the tensor pipe: an SS-mode 128 x 64 x 16 MMA reads 6 KB of
-// operands per 32-cycle slot (192 B / cycle against a 128 B / cycle port; profiles/r02_attn_f32_ncu.txt).  Both A operands
-// can live in tensor memory instead -- Q for the whole CTA (three planes x 32 columns, written once by the softmax threads
+// ---- A operands in tensor memory ----------------------------------------------------------------------------------------
+// An SS-mode 128 x 64 x 16 MMA reads 6 KB of operands per 32-cycle slot (192 B / cycle against a 128 B / cycle shared-memory
+// port).  Both A operands live in tensor memory instead -- Q for the whole CTA (three planes x 32 columns, written once by the softmax threads
 // straight from global memory: no Q tile, no TMA for it) and P (three planes x 32 columns, written with tcgen05.st in the
 // layout the softmax threads already hold: lane = row, column c = keys 2c, 2c + 1) -- so every MMA reads only its 2 KB B
 // operand from shared memory and runs at the tensor pipe's floor.  The 96 KB of Q / P tiles that leaves pays for a third
 // K / V stage.  TMEM columns: S0 0..63 | S1 64..127 | O 128..191 | P h,m,l 192..287 | Q h,m,l 288..383 (512 allocated).
 constexpr int AT_NST = 3;
+// -DTOME_ATTN_TRACE: clock64 stamps of one CTA's issue / softmax events per key block (tools/trace_attn_f32.py; the timeline
+// that found the serialised issue streams is in profiles/r02_attn_f32_ncu.txt)
+#ifdef TOME_ATTN_TRACE
+__device__ long long g_af_trace[8 * 32];
+#define AF_TR(ev, j) do { if (tr && (j) < 32) g_af_trace[(ev) * 32 + (j)] = clock64(); } while (0)
+#else
+#define AF_TR(ev, j) do { } while (0)
+#endif
 constexpr uint32_t AT_S1 = 64u, AT_O = 128u, AT_P = 192u, AT_Q = 288u;
 
 // p -> exact bf16 planes of a pair of probabilities without the single-value F2F conversions (XU pipe, 16 / clk / SM: with 64 of
@@ -325,9 +85,11 @@ __device__ __forceinline__ void af_split_pair(float p0, float p1, uint32_t& wh, 
   wl = af_pack(r0 - __uint_as_float(wm << 16), r1 - __uint_as_float(wm & 0xffff0000u));
 }
 
+constexpr int AT_THREADS = 352;     // TMA, S issuer, 2 x 4 softmax warps, P V issuer
+
 template <bool HAS_BIAS>
-__global__ void __launch_bounds__(AF_THREADS, 1)
-attn_f32_ts_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16* __restrict__ qkv3, const AfParams p) {
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_f32_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16* __restrict__ qkv3, const AfParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler, see the MMA warp
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -359,6 +121,9 @@ attn_f32_ts_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int row0 = b * p.N;
   const int nb = p.nblk;
+#ifdef TOME_ATTN_TRACE
+  const bool tr = blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+#endif
 
   if (warp == 0) {
     if (lane == 0) {
@@ -383,14 +148,14 @@ attn_f32_ts_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat
     const bool leader = elect_one_sync();
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AF_BKV >> 3) << 17) | ((uint32_t)(AF_BM >> 4) << 24);
-    const uint32_t idesc_o = idesc_s | (1u << 16);                          // B MN-major, N = 64 as well
-    const uint64_t dk0 = make_sw128_desc(sm_kv), dv0 = af_desc_mn(sm_kv + 3u * AF_KP);   // stage 0, plane h; a plane / stage further is
+    const uint64_t dk0 = make_sw128_desc(sm_kv);                            // stage 0, plane h; a plane / stage further is
     constexpr uint64_t PL = AF_KP >> 4, ST = AF_STAGE >> 4;                               // a constant in the address field
     auto issue_s = [&](int j) {
       const uint32_t s = (uint32_t)(j % AT_NST), k = (uint32_t)(j / AT_NST), sb = (uint32_t)(j & 1), kb = (uint32_t)(j >> 1);
       mbar_wait(bar_kfull + 8u * s, k & 1u);
       if (kb >= 1) mbar_wait(bar_sfree + 8u * sb, (kb - 1) & 1u);           // the softmax has pulled the previous S out of this buffer
       tc_fence_after();
+      AF_TR(0, j);
       if (leader) {
         const uint32_t d = tb + sb * AT_S1;
         const uint64_t dk = dk0 + (uint64_t)s * ST;
@@ -405,19 +170,29 @@ attn_f32_ts_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat
         umma_commit(bar_kempty + 8u * s);
       }
       __syncwarp();
+      AF_TR(1, j);
     };
     mbar_wait(bar_q, 0);
-    issue_s(0);
+    for (int j = 0; j < nb; ++j) issue_s(j);                                // up to two blocks ahead of the softmax (S is double-buffered)
+  } else if (warp == 10) {
+    // P V from a warp of its own: in one warp the two issue streams serialise -- an MMA enters the pipe only as fast as
+    // the pipe drains (~800 cycles per batch of 24) and every mbarrier poll between the batches is a ~100-cycle round
+    // trip, 2250 cycles per block against 1536 of tensor time (the timeline in profiles/r02_attn_f32_ncu.txt)
+    const bool leader = elect_one_sync();
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(AF_D >> 3) << 17) | ((uint32_t)(AF_BM >> 4) << 24);
+    const uint64_t dv0 = af_desc_mn(sm_kv + 3u * AF_KP);
+    constexpr uint64_t PL = AF_KP >> 4, ST = AF_STAGE >> 4;
     for (int j = 0; j < nb; ++j) {
-      if (j + 1 < nb) issue_s(j + 1);
       const uint32_t s = (uint32_t)(j % AT_NST);
       mbar_wait(bar_vfull + 8u * s, (uint32_t)((j / AT_NST) & 1));
       mbar_wait(bar_p, (uint32_t)(j & 1));
       tc_fence_after();
+      AF_TR(2, j);
       if (leader) {
         const uint32_t d = tb + AT_O;
         const uint64_t dv = dv0 + (uint64_t)s * ST;
-        // (P plane, V plane), same order; P: 8 columns per 16 keys; V: 16 keys = 2048 bytes
+        // (P plane, V plane), smallest products first; P: 8 columns per 16 keys; V (MN-major): 16 keys = 2048 bytes
 #define TOME_AT_O(PP_, VP_, ACC_)                                                                                        \
         _Pragma("unroll") for (int ks = 0; ks < AF_BKV / 16; ++ks)                                                       \
           umma_bf16_ts(d, tb + AT_P + 32u * (PP_) + 8u * ks, dv + (VP_) * PL + (uint64_t)(128 * ks), idesc_o, (ACC_) || ks ? 1u : 0u);
@@ -427,8 +202,9 @@ attn_f32_ts_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat
         umma_commit(bar_vempty + 8u * s);
       }
       __syncwarp();
+      AF_TR(3, j);
     }
-  } else {
+  } else if (warp >= 2) {
     const int q4 = warp & 3;
     const int half = (warp - 2) >> 2;                          // which 32 key columns of a block / 32 channels of O
     const int row = q4 * 32 + lane;
@@ -471,6 +247,7 @@ attn_f32_ts_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat
       const uint32_t sb = (uint32_t)(j & 1), k = (uint32_t)(j >> 1);
       mbar_wait(bar_s + 8u * sb, k & 1u);
       tc_fence_after();
+      if (warp == 2) AF_TR(4, j);
       float t[32];
       tmem_ld32(tmem_base + tlane + sb * AT_S1 + 32u * half, t);
       tc_fence_before();
@@ -517,9 +294,11 @@ attn_f32_ts_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat
         l0 += p0; l1 += p1;
         af_split_pair(p0, p1, wh[i], wm[i], wl[i]);
       }
+      if (warp == 2) AF_TR(5, j);
       if (j > 0) {                                             // P V of the previous block: also frees the P columns
         mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
         tc_fence_after();
+        if (warp == 2) AF_TR(6, j);
         fold_o();
       }
 #pragma unroll
@@ -534,6 +313,7 @@ attn_f32_ts_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat
       tmem_st_wait();
       tc_fence_before();                                       // the O columns were read above: P V (j) may overwrite them
       af_arrive(bar_p);
+      if (warp == 2) AF_TR(7, j);
     }
     mbar_wait(bar_o, (uint32_t)((nb - 1) & 1));
     tc_fence_after();
@@ -576,32 +356,26 @@ int launch_attention_f32(const void* qkv3, int B, int N, int heads, float scale,
   p.scale_log2e = scale * 1.4426950408889634f;
   p.bias = bias; p.out = (float*)out; p.out3 = (__nv_bfloat16*)out3;
   const long long rows = (long long)B * N, cols = 9LL * heads * AF_D;
-  alignas(64) CUtensorMap map_q, map_kv;
-  int rc = make_bf16_map(&map_q, qkv3, rows, cols, cols, AF_BM, "tome_attention_f32");
-  if (rc) return rc;
-  rc = make_bf16_map(&map_kv, qkv3, rows, cols, cols, AF_BKV, "tome_attention_f32");
+  alignas(64) CUtensorMap map_kv;
+  int rc = make_bf16_map(&map_kv, qkv3, rows, cols, cols, AF_BKV, "tome_attention_f32");
   if (rc) return rc;
   dim3 grid((N + AF_BM - 1) / AF_BM, heads, B);
   if (grid.z > 65535) return set_error(TOME_ERR_UNSUPPORTED, "tome_attention_f32: batch %d > 65535", B);
-  static const bool ss_mode = [] { const char* e = getenv("TOME_ATTN_F32_SS"); return e && e[0] == '1'; }();
-  if (!ss_mode) {                                    // A operands (Q, P) in tensor memory
-    const size_t smem = 1024 + AT_NST * AF_STAGE + 192 + 4 * AF_BM * sizeof(float);
-    static PerDeviceOnce once;
-    if (once.first_time()) {
-      TOME_CUDA(cudaFuncSetAttribute(attn_f32_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      TOME_CUDA(cudaFuncSetAttribute(attn_f32_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    if (bias) attn_f32_ts_kernel<true><<<grid, AF_THREADS, smem, st>>>(map_kv, (const __nv_bfloat16*)qkv3, p);
-    else attn_f32_ts_kernel<false><<<grid, AF_THREADS, smem, st>>>(map_kv, (const __nv_bfloat16*)qkv3, p);
-    TOME_LAUNCH_CHECK("attn_f32_ts_kernel");
-    return TOME_OK;
-  }
-  const size_t smem = 1024 + 3 * AF_QP + 2 * AF_STAGE + 3 * AF_QP + 128 + 4 * AF_BM * sizeof(float);
+  const size_t smem = 1024 + AT_NST * AF_STAGE + 192 + 4 * AF_BM * sizeof(float);
   static PerDeviceOnce once;
-  if (once.first_time()) TOME_CUDA(cudaFuncSetAttribute(attn_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attn_f32_kernel<<<grid, AF_THREADS, smem, st>>>(map_q, map_kv, p);
+  if (once.first_time()) {
+    TOME_CUDA(cudaFuncSetAttribute(attn_f32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TOME_CUDA(cudaFuncSetAttribute(attn_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  if (bias) attn_f32_kernel<true><<<grid, AT_THREADS, smem, st>>>(map_kv, (const __nv_bfloat16*)qkv3, p);
+  else attn_f32_kernel<false><<<grid, AT_THREADS, smem, st>>>(map_kv, (const __nv_bfloat16*)qkv3, p);
   TOME_LAUNCH_CHECK("attn_f32_kernel");
   return TOME_OK;
 }
 
 }  // namespace tome
+#ifdef TOME_ATTN_TRACE
+extern "C" TOME_API int tome_debug_attn_trace(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, tome::g_af_trace, sizeof(long long) * 8 * 32);
+}
+#endif
