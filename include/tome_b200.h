@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 22
+#define TOME_ABI_VERSION 23
 
 #if defined(__GNUC__)
 #define TOME_API __attribute__((visibility("default")))
@@ -333,6 +333,14 @@ TOME_API int tome_linear_f32(const void* x3, const void* w3, const void* bias, i
  * (the output projection's operand). */
 TOME_API int tome_attention_f32(const void* qkv3, int32_t b, int32_t n, int32_t heads, int32_t d, float scale,
                        const float* key_bias, int32_t unbiased_queries, void* out, void* out_planes, void* stream);
+
+/* Caller-side bf16 attention with the proportional-attention key bias for sequences of any length (SURVEY.md 8f-f1;
+ * tome/patch/videomae.py:58-68, vivit.py:98-117: `attn + size.log()`): out (b, n, heads*64) bf16 = softmax(scale * q k^T +
+ * key_bias) v per head, flash-style (running maximum over 128-key blocks, fp32 softmax and accumulation), q / k / v read in
+ * place from the QKV GEMM's contiguous (b, n, 3*heads*64) bf16 output.  key_bias (b, n) fp32 or NULL; the first
+ * `unbiased_queries` queries take no bias. */
+TOME_API int tome_attention_bf16(const void* qkv, int32_t b, int32_t n, int32_t heads, int32_t d, float scale,
+                        const float* key_bias, int32_t unbiased_queries, void* out, void* stream);
 
 /* unmerge (merge.py:87-100): x (bm, n - r, c) -> out (bm, n, c); contiguous tensors. */
 TOME_API int tome_unmerge(const tome_plan* plan, const void* x, int32_t dtype, int32_t c, void* out,

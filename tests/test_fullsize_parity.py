@@ -90,6 +90,24 @@ def test_bf16_teacher_forced_1e2(case):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("case", [c for c in fullsize.FULL_CASES if c["model"] in ("videomae", "vivit") and c["kw"].get("prop_attn", True)],
+                         ids=lambda c: c["name"])
+def test_bf16_teacher_forced_with_own_attention(case, monkeypatch):
+    """The same bar with proportional attention on tome_attention_bf16 (opt-in, TOME_ATTENTION_BF16=1) instead of the
+    folded-bias library call."""
+    from tome import _native
+    monkeypatch.setenv("TOME_ATTENTION_BF16", "1")
+    before = _native.launch_count()
+    r = fullsize.run_case(case, torch.bfloat16, forced=True)
+    print(f"[fullsize, own bf16 attention] {r}")
+    assert _native.launch_count() > before
+    slack = {"vivit": 1.25}.get(case["model"])
+    tol = 1e-2 if slack is None else max(1e-2, slack * r["unpatched_err"])
+    assert r["err"] < tol, r
+    assert r["top1_same"] or r["top1_margin"] < tol, r
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("case", fullsize.FULL_CASES, ids=lambda c: c["name"])
 def test_bf16_free_running_first_divergence(case):
     """bf16 keys decide differently from fp32 keys from the first layer on (hard part 6: the

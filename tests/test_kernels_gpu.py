@@ -1184,6 +1184,44 @@ def test_linear_f32_matches_fp64(native, shape, terms):
 
 @pytest.mark.timeout(180)
 @pytest.mark.parametrize("with_bias", [False, True], ids=["plain", "prop_attn"])
+@pytest.mark.parametrize("N", [3137, 1568, 470, 129, 128, 65])
+def test_attention_bf16_matches_fp64(native, N, with_bias):
+    """tome_attention_bf16 (tcgen05 flash attention with the key bias, q / k / v in place from the QKV output) against fp64
+    softmax attention on the same bf16 operands: the bf16 bar of the north star (1e-2), and no worse than 2x the library's
+    bf16 attention with the reference's masked formulation (tome/patch/videomae.py:58-68)."""
+    g = torch.Generator().manual_seed(N)
+    B, h, d = 2, 3, 64
+    C = h * d
+    qkv = (torch.randn(B, N, 3 * C, generator=g) * 1.5).to(torch.bfloat16).cuda()
+    bias = (torch.randint(1, 8, (B, N), generator=g).float().log()).cuda() if with_bias else None
+    q, k, v = qkv.double().reshape(B, N, 3, h, d).permute(2, 0, 3, 1, 4)
+    sc = (q @ k.transpose(-1, -2)) * d ** -0.5
+    if bias is not None:
+        sc = sc + bias.double()[:, None, None, :]
+    want = (sc.softmax(-1) @ v).transpose(1, 2).reshape(B, N, C)
+    qf, kf, vf = qkv.reshape(B, N, 3, h, d).permute(2, 0, 3, 1, 4)
+    mask = None if bias is None else bias.to(torch.bfloat16)[:, None, None, :].expand(B, 1, N, N)
+    lib = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf, attn_mask=mask, scale=d ** -0.5).transpose(1, 2).reshape(B, N, C)
+    scale = want.abs().max().item()
+    lib_err = (lib.double() - want).abs().max().item() / scale
+    with torch.no_grad():
+        assert native.attention_bf16_usable(qkv, h, bias)
+        out = native.attention_bf16(qkv, h, d ** -0.5, bias)
+    assert out.dtype == torch.bfloat16 and out.shape == (B, N, C)
+    err = (out.double() - want).abs().max().item() / scale
+    print(f"[attention_bf16] N={N} bias={with_bias}: max err / max|y| = {err:.2e} (library bf16 attention: {lib_err:.2e})")
+    assert err <= 1e-2 and err <= max(2.0 * lib_err, 4e-3), (err, lib_err)
+    if with_bias:                                             # unbiased leading query (TimeSformer's class token)
+        with torch.no_grad():
+            out1 = native.attention_bf16(qkv, h, d ** -0.5, bias, unbiased_queries=1)
+        sc0 = (q @ k.transpose(-1, -2)) * d ** -0.5
+        want0 = (sc0.softmax(-1) @ v).transpose(1, 2).reshape(B, N, C)
+        torch.testing.assert_close(out1[:, 0].double(), want0[:, 0], rtol=2e-2, atol=2e-2)
+        assert torch.equal(out1[:, 1:], out[:, 1:])
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("with_bias", [False, True], ids=["plain", "prop_attn"])
 @pytest.mark.parametrize("N", [1568, 468, 196, 100])
 def test_attention_f32_matches_fp64(native, N, with_bias):
     """tome_attention_f32 (exact-split tcgen05 flash attention) against fp64 softmax attention; its error must be in the class of

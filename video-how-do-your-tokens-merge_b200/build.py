@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libtome_b200.so")
 STAMP = os.path.join(LIBDIR, "libtome_b200.stamp")
-SOURCES = ["tome_abi.cu", "match_exact.cu", "match_sm100.cu", "plan_cluster.cu", "select.cu", "sets.cu", "trace.cu", "merge.cu", "attn_bias.cu", "attn_short.cu", "attn_frames.cu", "attn_f32.cu", "patchify.cu", "linear_gelu.cu", "linear_f32.cu"]
+SOURCES = ["tome_abi.cu", "match_exact.cu", "match_sm100.cu", "plan_cluster.cu", "select.cu", "sets.cu", "trace.cu", "merge.cu", "attn_bias.cu", "attn_short.cu", "attn_frames.cu", "attn_f32.cu", "attn_bf16.cu", "patchify.cu", "linear_gelu.cu", "linear_f32.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

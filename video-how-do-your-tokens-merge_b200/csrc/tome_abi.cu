@@ -89,6 +89,7 @@ int launch_traj_temporal(const void*, const void*, const void*, long long, int, 
 int launch_split3(const void*, long long, int, long long, void*, cudaStream_t);
 int launch_linear_f32(const void*, const void*, const void*, int, int, int, int, int, void*, void*, cudaStream_t);
 int launch_attention_f32(const void*, int, int, int, float, const float*, int, void*, void*, cudaStream_t);
+int launch_attention_bf16(const void*, int, int, int, float, const float*, int, void*, cudaStream_t);
 struct ClsArgs {
   const void *a, *add, *mean_src;
   long long a_sb, add_sb, m_sb, m_st;
@@ -537,6 +538,15 @@ int tome_attention_f32(const void* qkv3, int32_t b, int32_t n, int32_t heads, in
   TOME_CHECK_ARG(qkv3 && (out || out_planes) && b > 0 && n > 0 && heads > 0 && unbiased_queries >= 0, "tome_attention_f32: NULL pointer or empty shape");
   if (d != 64) return set_error(TOME_ERR_UNSUPPORTED, "tome_attention_f32: head dimension %d (64 only)", d);
   return launch_attention_f32(qkv3, b, n, heads, scale, key_bias, unbiased_queries, out, out_planes, (cudaStream_t)stream);
+}
+
+int tome_attention_bf16(const void* qkv, int32_t b, int32_t n, int32_t heads, int32_t d, float scale, const float* key_bias,
+                        int32_t unbiased_queries, void* out, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(qkv && out && b > 0 && n > 0 && heads > 0 && unbiased_queries >= 0, "tome_attention_bf16: NULL pointer or empty shape");
+  if (d != 64) return set_error(TOME_ERR_UNSUPPORTED, "tome_attention_bf16: head dimension %d (64 only)", d);
+  return launch_attention_bf16(qkv, b, n, heads, scale, key_bias, unbiased_queries, out, (cudaStream_t)stream);
 }
 
 int tome_cls_rows(const void* a, int64_t a_stride_b, const void* add, int64_t add_stride_b, const void* mean_src, int64_t mean_stride_b,

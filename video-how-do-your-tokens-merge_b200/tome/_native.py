@@ -18,7 +18,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 22
+ABI_VERSION = 23
 
 TOME_F32, TOME_BF16, TOME_U8 = 0, 1, 2
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -33,7 +33,7 @@ EXPORTS = (
     "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_linear_gelu", "tome_unmerge",
     "tome_match_sets_workspace_bytes", "tome_match_sets", "tome_group_reduce", "tome_gather_rows",
     "tome_source_compose", "tome_source_dense", "tome_random_rowmax", "tome_merge_add_norm_rv", "tome_rows_add_layernorm", "tome_attn_short",
-    "tome_frames_attention", "tome_traj_temporal", "tome_split3", "tome_linear_f32", "tome_attention_f32", "tome_cls_rows",
+    "tome_frames_attention", "tome_traj_temporal", "tome_split3", "tome_linear_f32", "tome_attention_f32", "tome_cls_rows", "tome_attention_bf16",
 )
 
 
@@ -133,7 +133,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.tome_split3.argtypes = [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp]
     lib.tome_linear_f32.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]
     lib.tome_attention_f32.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_i32, c_vp, c_vp, c_vp]
-    for name in ("tome_split3", "tome_linear_f32", "tome_attention_f32"):
+    lib.tome_attention_bf16.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_i32, c_vp, c_vp]
+    for name in ("tome_split3", "tome_linear_f32", "tome_attention_f32", "tome_attention_bf16"):
         getattr(lib, name).restype = c_i32
     lib.tome_frames_attention.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp]
     lib.tome_traj_temporal.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]
@@ -863,6 +864,33 @@ def attention_f32(qkv, heads: int, scale: float, key_bias: Optional[torch.Tensor
                                       torch.cuda.current_stream(dev).cuda_stream), lib)
     p3 = None if res3 is None else Planes(res3, (B, N, c))
     return res if out == "fp32" else p3 if out == "planes" else (res, p3)
+
+
+def attention_bf16_usable(qkv: torch.Tensor, heads: int, key_bias: Optional[torch.Tensor] = None) -> bool:
+    return (qkv.is_cuda and qkv.dtype == torch.bfloat16 and qkv.dim() == 3 and qkv.is_contiguous() and qkv.shape[-1] == 3 * heads * 64
+            and qkv.data_ptr() % 16 == 0 and qkv.shape[0] <= 65535 and not torch.is_grad_enabled()
+            and (key_bias is None or (key_bias.is_cuda and tuple(key_bias.shape) == tuple(qkv.shape[:2]))))
+
+
+def attention_bf16(qkv: torch.Tensor, heads: int, scale: float, key_bias: Optional[torch.Tensor] = None,
+                   unbiased_queries: int = 0) -> torch.Tensor:
+    """softmax(scale * q k^T + key_bias) v per head on bf16 tensor cores (include/tome_b200.h: tome_attention_bf16) from the
+    QKV GEMM's contiguous (B, N, 3 * heads * 64) output; ``key_bias`` (B, N) fp32 = log size of the key token
+    (tome/patch/videomae.py:62-63); the first ``unbiased_queries`` queries take no bias.  Returns (B, N, heads * 64) bf16."""
+    lib = load_library()
+    _require_cuda(qkv, "qkv")
+    if qkv.dtype != torch.bfloat16 or qkv.dim() != 3 or not qkv.is_contiguous() or qkv.shape[-1] != 3 * heads * 64:
+        raise RuntimeError("tome_b200: attention_bf16 needs a contiguous (B, N, 3 * heads * 64) bf16 tensor")
+    B, N, _ = qkv.shape
+    bp = None
+    if key_bias is not None:
+        key_bias = key_bias.reshape(B, N).float().contiguous()
+        bp = key_bias.data_ptr()
+    with torch.cuda.device(qkv.device):
+        out = torch.empty(B, N, heads * 64, dtype=torch.bfloat16, device=qkv.device)
+        _check(lib.tome_attention_bf16(qkv.data_ptr(), B, N, heads, 64, float(scale), bp, int(unbiased_queries), out.data_ptr(),
+                                       _stream(qkv)), lib)
+    return out
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:

@@ -25,6 +25,10 @@ def usable(x: torch.Tensor, module) -> bool:
     return (x.is_cuda and x.dtype == torch.bfloat16 and not torch.is_grad_enabled() and not module.training)
 
 
+def own_bf16_enabled() -> bool:
+    return os.environ.get("TOME_ATTENTION_BF16", "0") == "1"
+
+
 def _key_of(tensors):
     return tuple((t.data_ptr(), t._version, t.dtype, t.device) if t is not None else None for t in tensors)
 
@@ -86,6 +90,26 @@ def attention(x, owner, heads, d, scale, log_size, wq, wk, wv, bq=None, bk=None,
             kb = F.pad(kb, (lead, 0))
         ctx, _ = _native.frames_attention(qkv, heads, 1, scale, kb, want_diag=False, lead=0, unbiased_queries=lead)
         return ctx.view(B, N, heads * d), k
+    if d == 64 and own_bf16_enabled():
+        # opt-in (TOME_ATTENTION_BF16=1): the library's own bf16 flash attention takes the (B, N) key bias directly, on the
+        # unpadded projection.  Correct at any length but slower than the folded-bias library call at these shapes (211 us
+        # against 101 us at 8 x 12 x 1568: exp2-pipe bound), so the fold below stays the default.
+        key = _key_of((wq, wk, wv, bq, bk, bv))
+        cached = getattr(owner, "_tome_plain_qkv", None)
+        if cached is None or cached[0] != key:
+            w = torch.cat((wq, wk, wv), 0).detach().contiguous()
+            zb = lambda t, ref: t.detach() if t is not None else torch.zeros(ref.shape[0], dtype=ref.dtype, device=ref.device)
+            bcat = None if (bq is None and bk is None and bv is None) else torch.cat((zb(bq, wq), zb(bk, wk), zb(bv, wv)), 0).contiguous()
+            cached = owner._tome_plain_qkv = (key, w, bcat)
+        qkv = F.linear(x, cached[1], cached[2])
+        if _native.attention_bf16_usable(qkv, heads):
+            k = qkv[..., heads * d:2 * heads * d].view(B, N, heads, d).transpose(1, 2)
+            if on_keys is not None:
+                on_keys(k)
+            kb = log_size.reshape(B, N - lead).float()
+            if lead:
+                kb = F.pad(kb, (lead, 0))
+            return _native.attention_bf16(qkv, heads, scale, kb, unbiased_queries=lead), k
     da = d + PAD
     weight, bias = padded_qkv(owner, heads, d, wq, wk, wv, bq, bk, bv)
     qkv = F.linear(x, weight, bias)
