@@ -68,7 +68,7 @@ __device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr) {
 __global__ void __launch_bounds__(FA_THREADS, 2)
 frames_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const FaParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int C = p.heads * FA_D;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -118,36 +118,48 @@ frames_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // S = Q K^T: D fp32, A/B bf16, both K-major, M = 128, N = PB.   O = P V: B MN-major (bit 16), N = 64.
-      const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.PB >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
-      const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(FA_D >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
-      mbar_wait_sleep(bar_q, 0, 64);
-      for (int f = 0; f < p.F; ++f) {
-        const uint32_t ph = (uint32_t)(f & 1);
-        if (f > 0) mbar_wait_sleep(bar_sfree, (f - 1) & 1, 64);          // O(f-1) has been read out of the columns S(f) lands in
-        mbar_wait_sleep(bar_k, ph, 64);
-        tc_fence_after();
+    // The MMA warp runs converged with warp-uniform operands and one elected lane issuing: under `if (lane == 0)` the
+    // compiler wraps every tcgen05.mma in an ELECT / vote loop (~70 cycles per MMA, attn_f32.cu), and the 17 MMAs of a
+    // frame sit on its serial path.
+    // S = Q K^T: D fp32, A/B bf16, both K-major, M = 128, N = PB.   O = P V: B MN-major (bit 16), N = 64.
+    const bool leader = elect_one_sync();
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.PB >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(FA_D >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+    const uint64_t dq = make_sw128_desc(sm_q), dk = make_sw128_desc(sm_k), dp = make_sw128_desc(sm_p), dv = make_sw128_mn_desc(sm_v);
+    constexpr uint64_t PBLK = (FA_BM * 128u) >> 4;               // one 64-key block of the P tile
+    mbar_wait_sleep(bar_q, 0, 64);
+    for (int f = 0; f < p.F; ++f) {
+      const uint32_t ph = (uint32_t)(f & 1);
+      if (f > 0) mbar_wait_sleep(bar_sfree, (f - 1) & 1, 64);          // O(f-1) has been read out of the columns S(f) lands in
+      mbar_wait_sleep(bar_k, ph, 64);
+      tc_fence_after();
+      if (leader) {
 #pragma unroll
-        for (int k = 0; k < FA_D / 16; ++k)
-          umma_bf16(tmem_base, make_sw128_desc(sm_q + 32u * k), make_sw128_desc(sm_k + 32u * k), idesc1, k ? 1u : 0u);
+        for (int k = 0; k < FA_D / 16; ++k) umma_bf16(tb, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc1, k ? 1u : 0u);
         umma_commit(bar_s);
-        mbar_wait_sleep(bar_v, ph, 64);
-        mbar_wait_sleep(bar_p0, ph, 64);
-        tc_fence_after();
-        for (int ks = 0; ks < h0; ++ks)
-          umma_bf16(tmem_base, make_sw128_desc(sm_p + (uint32_t)(ks >> 2) * (FA_BM * 128u) + 32u * (ks & 3)),
-                    make_sw128_mn_desc(sm_v + 2048u * ks), idesc2, ks ? 1u : 0u);
-        if (nks > h0) {
-          umma_commit(bar_pfree);
-          mbar_wait_sleep(bar_p1, ph, 64);
-          tc_fence_after();
-          for (int ks = h0; ks < nks; ++ks)
-            umma_bf16(tmem_base, make_sw128_desc(sm_p + (uint32_t)((ks - h0) >> 2) * (FA_BM * 128u) + 32u * ((ks - h0) & 3)),
-                      make_sw128_mn_desc(sm_v + 2048u * ks), idesc2, 1u);
-        }
-        umma_commit(bar_o);
       }
+      __syncwarp();
+      mbar_wait_sleep(bar_v, ph, 64);
+      mbar_wait_sleep(bar_p0, ph, 64);
+      tc_fence_after();
+      if (leader) {
+        for (int ks = 0; ks < h0; ++ks)                          // P: k-block ks / 4, +32 bytes per k-step; V: 16 keys = 2048 bytes
+          umma_bf16(tb, dp + (uint64_t)(ks >> 2) * PBLK + (uint64_t)(2 * (ks & 3)), dv + (uint64_t)(128 * ks), idesc2, ks ? 1u : 0u);
+        if (nks > h0) umma_commit(bar_pfree);
+      }
+      __syncwarp();
+      if (nks > h0) {
+        mbar_wait_sleep(bar_p1, ph, 64);
+        tc_fence_after();
+        if (leader) {
+          for (int ks = h0; ks < nks; ++ks)
+            umma_bf16(tb, dp + (uint64_t)((ks - h0) >> 2) * PBLK + (uint64_t)(2 * ((ks - h0) & 3)), dv + (uint64_t)(128 * ks), idesc2, 1u);
+        }
+        __syncwarp();
+      }
+      if (leader) umma_commit(bar_o);
+      __syncwarp();
     }
   } else {
     const int q4 = warp & 3;                                   // TMEM lane quarter this warp may touch
