@@ -348,7 +348,7 @@ __device__ __forceinline__ float warp_exact32(const float* __restrict__ a_blk, c
 __global__ void __launch_bounds__(TC_THREADS, 3)
 match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int jt = blockIdx.x, it = blockIdx.y, b = blockIdx.z;
 
   if (threadIdx.x == 0) TC_TRACE(0);
@@ -382,11 +382,15 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int row_a = b * p.n + it * TC_BM;               // rows of the split buffer (h plane)
   const int row_b = b * p.n + p.na + jt * p.BN;
 
+  // Producer and MMA warps run converged with one elected lane issuing: under `if (lane == 0)` the compiler cannot prove the
+  // operands warp-uniform and wraps every TMA / tcgen05.mma issue in an ELECT / vote loop of ~70 cycles (attn_f32.cu), more
+  // than the 56-cycle slot of a 128 x 112 x 16 MMA -- and this kernel is one serial chain of such latencies.
   if (warp == 0) {
-    if (lane == 0) {
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % p.stages;
-        mbar_wait(bar_empty + 8u * s, ((kb / p.stages) & 1) ^ 1);
+    const bool leader = elect_one_sync();
+    for (int kb = 0; kb < p.num_kb; ++kb) {
+      const int s = kb % p.stages;
+      mbar_wait(bar_empty + 8u * s, ((kb / p.stages) & 1) ^ 1);
+      if (leader) {
         const uint32_t st = base + (uint32_t)s * stage_bytes, full = bar_full + 8u * s;
         mbar_expect_tx(full, stage_bytes);
         tma_load_2d(st, &map_a, kb * TC_BK, row_a, full);                                   // A h
@@ -394,15 +398,18 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         tma_load_2d(st + 2u * a_bytes, &map_b, kb * TC_BK, row_b, full);                    // B h
         tma_load_2d(st + 2u * a_bytes + b_bytes, &map_b, kb * TC_BK, row_b + p.rows_total, full);  // B m
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % p.stages;
-        mbar_wait(bar_full + 8u * s, (kb / p.stages) & 1);
-        tc_fence_after();
+    const bool leader = elect_one_sync();
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    for (int kb = 0; kb < p.num_kb; ++kb) {
+      const int s = kb % p.stages;
+      mbar_wait(bar_full + 8u * s, (kb / p.stages) & 1);
+      tc_fence_after();
+      if (leader) {
         if (kb == 0) TC_TRACE(2);
         if (kb == p.num_kb - 1) TC_TRACE(3);
         const uint32_t st = base + (uint32_t)s * stage_bytes;
@@ -411,15 +418,19 @@ match_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
         for (int k = 0; k < TC_BK / TC_UK; ++k) {
           const uint64_t adv = (uint64_t)((k * TC_UK * 2) >> 4);     // +32 bytes inside the swizzle row
-          umma_bf16(tmem_base, a_h + adv, b_h + adv, idesc, (kb | k) ? 1u : 0u);
-          umma_bf16(tmem_base, a_h + adv, b_m + adv, idesc, 1u);
-          umma_bf16(tmem_base, a_m + adv, b_h + adv, idesc, 1u);
+          umma_bf16(tb, a_h + adv, b_h + adv, idesc, (kb | k) ? 1u : 0u);
+          umma_bf16(tb, a_h + adv, b_m + adv, idesc, 1u);
+          umma_bf16(tb, a_m + adv, b_h + adv, idesc, 1u);
         }
         umma_commit(bar_empty + 8u * s);      // frees the stage when these MMAs retire
       }
+      __syncwarp();
+    }
+    if (leader) {
       umma_commit(bar_tmem);                  // accumulator complete
       TC_TRACE(4);
     }
+    __syncwarp();
   } else {
     // ---- epilogue: thread <-> TMEM lane <-> A row ------------------------------------------
     const int q = warp & 3;                    // TMEM lane quarter this warp may touch

@@ -301,7 +301,7 @@ template <typename T>
 __global__ void __launch_bounds__(PC_THREADS, 1)
 plan_cluster_kernel(const __grid_constant__ CUtensorMap map_b, const T* __restrict__ metric, const PcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int c = (int)cluster_ctarank(), b = blockIdx.y;
   const int CS = p.CS, RA = p.RA, RB = p.RB, BN = p.BN, NST = p.stages;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -425,24 +425,32 @@ plan_cluster_kernel(const __grid_constant__ CUtensorMap map_b, const T* __restri
   // tile t of this CTA is the B rows of peer (c + t) % CS (its own first: L2-hot); peers that own no B rows are skipped by
   // every role alike
   int ntiles = 0;
+  // producer and MMA warps converged, one elected lane issuing (one UTMALDG / UTCHMMA per issue instead of an ELECT / vote
+  // loop of ~70 cycles around each: attn_f32.cu)
   if (warp == 0) {
-    if (lane == 0 && sweeping) {
+    if (sweeping) {
+      const bool leader = elect_one_sync();
       int it = 0;
       for (int t = 0; t < CS; ++t) {
         const int pt = (c + t) % CS;
         if (nb - pt * RB <= 0) continue;
         const int s = it % NST;
         mbar_wait(bar_empty + 8u * s, ((it / NST) & 1) ^ 1);
-        const uint32_t st = base + L.stage0 + (uint32_t)s * L.stage_bytes, full = bar_full + 8u * s;
-        mbar_expect_tx(full, L.stage_bytes);
-        const int grow = b * nb + pt * RB;
-        tma_load_2d(st, &map_b, 0, grow, full);                                       // h rows
-        tma_load_2d(st + (uint32_t)BN * 128u, &map_b, 0, p.rows_total + grow, full);  // m rows
+        if (leader) {
+          const uint32_t st = base + L.stage0 + (uint32_t)s * L.stage_bytes, full = bar_full + 8u * s;
+          mbar_expect_tx(full, L.stage_bytes);
+          const int grow = b * nb + pt * RB;
+          tma_load_2d(st, &map_b, 0, grow, full);                                       // h rows
+          tma_load_2d(st + (uint32_t)BN * 128u, &map_b, 0, p.rows_total + grow, full);  // m rows
+        }
+        __syncwarp();
         ++it;
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && sweeping) {
+    if (sweeping) {
+      const bool leader = elect_one_sync();
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint64_t a_h = make_sw128_desc(base + L.a_h), a_m = make_sw128_desc(base + L.a_m);
       int it = 0;
@@ -451,27 +459,30 @@ plan_cluster_kernel(const __grid_constant__ CUtensorMap map_b, const T* __restri
         if (nb - pt * RB <= 0) continue;
         const int s = it % NST, acc = it & 1;
         mbar_wait(bar_tempty + 8u * acc, ((it >> 1) & 1) ^ 1);       // the workers have read this accumulator out
-        PC_TILE(32, it, 0);
+        if (leader) PC_TILE(32, it, 0);
         mbar_wait(bar_full + 8u * s, (it / NST) & 1);
         tc_fence_after();
-        PC_TILE(32, it, 1);
-        const uint32_t st = base + L.stage0 + (uint32_t)s * L.stage_bytes;
-        const uint64_t b_h = make_sw128_desc(st), b_m = make_sw128_desc(st + (uint32_t)BN * 128u);
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
+        if (leader) {
+          PC_TILE(32, it, 1);
+          const uint32_t st = base + L.stage0 + (uint32_t)s * L.stage_bytes;
+          const uint64_t b_h = make_sw128_desc(st), b_m = make_sw128_desc(st + (uint32_t)BN * 128u);
+          const uint32_t d_tmem = tb + (uint32_t)acc * 128u;
 #pragma unroll
-        for (int k = 0; k < PC_K / 16; ++k) {
-          const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);        // +32 bytes inside the swizzle row
-          umma_bf16(d_tmem, a_h + adv, b_h + adv, idesc, k ? 1u : 0u);
-          umma_bf16(d_tmem, a_h + adv, b_m + adv, idesc, 1u);
-          umma_bf16(d_tmem, a_m + adv, b_h + adv, idesc, 1u);
+          for (int k = 0; k < PC_K / 16; ++k) {
+            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);        // +32 bytes inside the swizzle row
+            umma_bf16(d_tmem, a_h + adv, b_h + adv, idesc, k ? 1u : 0u);
+            umma_bf16(d_tmem, a_h + adv, b_m + adv, idesc, 1u);
+            umma_bf16(d_tmem, a_m + adv, b_h + adv, idesc, 1u);
+          }
+          umma_commit(bar_empty + 8u * s);                             // the stage is free once these MMAs retire
+          umma_commit(bar_tfull + 8u * acc);                           // and the accumulator is complete
+          PC_TILE(32, it, 2);
+          if (it == 0) PC_TRACE(32, 10);
         }
-        umma_commit(bar_empty + 8u * s);                             // the stage is free once these MMAs retire
-        umma_commit(bar_tfull + 8u * acc);                           // and the accumulator is complete
-        PC_TILE(32, it, 2);
-        if (it == 0) PC_TRACE(32, 10);
+        __syncwarp();
         ++it;
       }
-      PC_TRACE(32, 11);
+      if (leader) PC_TRACE(32, 11);
     }
   }
   // ---- workers: epilogue of every tile, refine, rank ---------------------------------------------------------------
