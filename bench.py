@@ -321,9 +321,12 @@ def workload_config(args, cpu=False):
         "parallelism": f"dp{args.gpus}",
         "cuda_graph": not args.no_graph,
         "fp32_arithmetic": "fp32 model, TF32 off everywhere (torch default, as slowfast/utils/model_benchmark.py runs it); the "
-                           "host model's linear layers run on tcgen05 through the exact three-way bf16 split (nine products, fp32 "
-                           "accumulation: tome_linear_f32, fp32-GEMM accuracy, tests/test_kernels_gpu.py::test_linear_f32_matches_fp64); "
-                           "TOME_LINEAR_F32=0 gives the library SGEMMs",
+                           "host model's linear layers and attention run on tcgen05 through the exact three-way bf16 split of every fp32 "
+                           "operand with fp32 accumulation (tome_linear_f32: " + os.environ.get("TOME_LINEAR_F32_TERMS", "8") + " of the nine plane "
+                           "products -- the default leaves out l.l, <= 2^-32 of |x||w|, below the accumulator's resolution; measured equal to "
+                           "the nine-product result at fp32 resolution and as close to fp64 as the library SGEMM: "
+                           "tests/test_kernels_gpu.py::test_linear_f32_matches_fp64, ::test_linear_f32_eight_products_equal_nine_at_fp32_resolution; "
+                           "TOME_LINEAR_F32_TERMS=9 runs all nine); TOME_LINEAR_F32=0 gives the library SGEMMs",
         "l2": "each step reads a different resident input batch (4 rotate) and the model's weights (344 MB fp32 / "
               "172 MB bf16): working set > 126 MB L2",
     }

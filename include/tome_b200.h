@@ -314,7 +314,8 @@ TOME_API int tome_linear_gelu(const void* x, const void* w, const void* bias, in
 /* Caller-side fp32 linear layers on tcgen05 at fp32 accuracy (the reference benchmark runs fp32 with
  * TF32 off, slowfast/utils/model_benchmark.py:21-45).  An fp32 value is exactly h + m + l with three bf16 terms and a
  * bf16 x bf16 product is exact in fp32, so accumulating the nine plane products in fp32 (terms = 9) is an fp32 GEMM
- * without TF32 truncation; terms = 6 drops m.l, l.m, l.l (<= 2^-23 relative per product).
+ * without TF32 truncation; terms = 8 leaves out l.l (<= 2^-32 of |a||b| per product, 2^-8 of the accumulator's own
+ * rounding unit: the host mirror's default), terms = 6 also m.l and l.m (<= 2^-23 relative per product).
  * tome_split3: x (rows, k) fp32, rows `row_stride` elements apart -> out (rows, 3k) bf16 planes [h | m | l]; k % 4 == 0.
  * tome_linear_f32: out (m, n) fp32 = act(x @ W^T + bias) from the split planes x3 (m, 3k), w3 (n, 3k); bias (n) fp32 or
  *   NULL; gelu 0 / 1 (erf GELU, exact erf).  n % 256 == 0, k % 32 == 0.  out_planes (m, 3n) bf16: the result ALSO (or, with

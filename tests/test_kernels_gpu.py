@@ -1151,7 +1151,7 @@ def test_traj_temporal_matches_einsum_formulation(native):
 
 @pytest.mark.timeout(180)
 @pytest.mark.parametrize("shape", [(300, 256, 64), (1000, 768, 768), (2100, 3072, 768), (777, 768, 3072)], ids=str)
-@pytest.mark.parametrize("terms", [9, 6])
+@pytest.mark.parametrize("terms", [9, 8, 6])
 def test_linear_f32_matches_fp64(native, shape, terms):
     """tome_linear_f32: fp32 GEMM on tcgen05 through the exact three-way bf16 split (nine products, fp32 accumulation).
     Against fp64 it must be in the accuracy class of torch's fp32 GEMM with TF32 off (the reference's arithmetic,
@@ -1180,6 +1180,29 @@ def test_linear_f32_matches_fp64(native, shape, terms):
         torch.testing.assert_close(act, torch.nn.functional.gelu(out), rtol=1e-6, atol=1e-6)
         nob = native.linear_f32(x, w, None, terms=terms)
         torch.testing.assert_close(nob + b, out, rtol=1e-6, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(1000, 768, 768), (2100, 3072, 768), (777, 768, 3072)], ids=str)
+def test_linear_f32_eight_products_equal_nine_at_fp32_resolution(native, shape):
+    """The default drops ONE of the nine plane products, l.l (<= 2^-32 of |a||b| per product: 2^-8 of the fp32 accumulator's own
+    rounding unit).  Against the nine-product result the outputs must agree to within one fp32 epsilon of the output scale,
+    and against fp64 the two must be equally far away."""
+    m, n, k = shape
+    g = torch.Generator().manual_seed(m + n + k)
+    x = torch.randn(m, k, generator=g).cuda()
+    w = (torch.randn(n, k, generator=g) * k ** -0.5).cuda()
+    b = torch.randn(n, generator=g).cuda()
+    want = x.double() @ w.double().t() + b.double()
+    scale = want.abs().max().item()
+    with torch.no_grad():
+        y9 = native.linear_f32(x, w, b, terms=9)
+        y8 = native.linear_f32(x, w, b, terms=8)
+    diff = (y8.double() - y9.double()).abs().max().item() / scale
+    e9 = (y9.double() - want).abs().max().item() / scale
+    e8 = (y8.double() - want).abs().max().item() / scale
+    print(f"[linear_f32] {shape}: |x8 - x9| / max|y| = {diff:.2e} (2^-24 = 5.96e-08); error vs fp64: x9 {e9:.3e}, x8 {e8:.3e}")
+    assert diff <= 2.0 ** -24, diff                      # below one fp32 epsilon of the output scale (measured 1.6e-8 .. 3.4e-8): single flipped roundings
+    assert e8 <= e9 * 1.02 + 1e-9
 
 
 @pytest.mark.timeout(180)

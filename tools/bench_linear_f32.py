@@ -18,7 +18,7 @@ for name, n, k, gelu in (("qkv", 2304, 768, False), ("proj", 768, 768, False), (
         lib = (lambda i: torch.nn.functional.gelu(torch.nn.functional.linear(xs[i % 3], w, b))) if gelu else (lambda i: torch.nn.functional.linear(xs[i % 3], w, b))
         t_lib, _ = bench.graph_time([lambda i=i: lib(i) for i in range(3)])
         row = [f"library {t_lib:7.1f} us ({flop / t_lib / 1e6:5.1f} TFLOP/s)"]
-        for terms in (9, 6):
+        for terms in (9, 8, 6):
             t, _ = bench.graph_time([lambda i=i: _native.linear_f32(xs[i % 3], w, b, gelu=gelu, terms=terms) for i in range(3)])
             x3 = [_native.split3(x) for x in xs]
             row.append(f"x{terms} {t:7.1f} us ({flop / t / 1e6:5.1f} TFLOP/s incl. split)")

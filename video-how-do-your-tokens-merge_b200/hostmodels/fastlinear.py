@@ -1,5 +1,5 @@
 """nn.Linear whose fp32 CUDA inference forward runs on the tensor cores at fp32 accuracy (``tome_linear_f32``: exact
-three-way bf16 split, nine products, fp32 accumulation) instead of the library's CUDA-core SGEMM -- the reference benchmark
+three-way bf16 split, the plane products down to 2^-32 of the term, fp32 accumulation) instead of the library's CUDA-core SGEMM -- the reference benchmark
 runs the models in fp32 with TF32 off (slowfast/utils/model_benchmark.py:21-45), and those SGEMMs are 83 % of the patched
 VideoMAE step.  Same parameters, same state-dict keys; every other case (training, bf16, odd shapes, CPU) is nn.Linear."""
 import torch

@@ -804,8 +804,9 @@ class Planes:
 
 def linear_f32(x, weight: torch.Tensor, bias: Optional[torch.Tensor], gelu: bool = False, terms: Optional[int] = None,
                out: str = "fp32"):
-    """act(x @ weight^T + bias) in fp32 on the tensor cores (exact bf16 three-way split, nine products; include/tome_b200.h:
-    tome_linear_f32).  ``x``: an fp32 tensor or a ``Planes``; the weight's planes are cached until the weight changes.
+    """act(x @ weight^T + bias) in fp32 on the tensor cores (exact bf16 three-way split; ``terms`` plane products: 8 by default =
+    all but l.l, which lies below the fp32 accumulator's resolution, 9 = all, TOME_LINEAR_F32_TERMS overrides;
+    include/tome_b200.h: tome_linear_f32).  ``x``: an fp32 tensor or a ``Planes``; the weight's planes are cached until the weight changes.
     ``out``: "fp32" (tensor), "planes" (``Planes`` only: the next exact-split kernel's operand) or "both"."""
     lib = load_library()
     n, k = weight.shape
@@ -817,7 +818,7 @@ def linear_f32(x, weight: torch.Tensor, bias: Optional[torch.Tensor], gelu: bool
         x3, lead = split3(x), tuple(x.shape[:-1])
     m = x3.shape[0]
     if terms is None:
-        terms = int(os.environ.get("TOME_LINEAR_F32_TERMS", "9"))
+        terms = int(os.environ.get("TOME_LINEAR_F32_TERMS", "8"))
     dev = x3.device
     with torch.cuda.device(dev):
         res = torch.empty(m, n, dtype=torch.float32, device=dev) if out in ("fp32", "both") else None
