@@ -806,6 +806,11 @@ def test_second_device_in_the_same_process(native):
             a = torch.randn(4096, 768, device=f"cuda:{dev}", dtype=torch.bfloat16)
             w = torch.randn(3072, 768, device=f"cuda:{dev}", dtype=torch.bfloat16)
             native.linear_gelu(a, w, None)
+            qkv = torch.randn(1, 300, 3 * 128, device=f"cuda:{dev}")                     # the attention and fp32 GEMM kernels as well
+            native.attention_f32(qkv, 2, 0.125)
+            native.attention_bf16(qkv.to(torch.bfloat16), 2, 0.125)
+            native.frames_attention(torch.randn(1, 1 + 2 * 50, 3 * 128, device=f"cuda:{dev}").to(torch.bfloat16), 2, 2, 0.125)
+            native.linear_f32(torch.randn(256, 64, device=f"cuda:{dev}"), torch.randn(256, 64, device=f"cuda:{dev}"), None)
             torch.cuda.synchronize(dev)
     assert torch.equal(plans[0].src_idx.cpu(), plans[1].src_idx.cpu())
     assert torch.equal(plans[0].dst_idx.cpu(), plans[1].dst_idx.cpu())

@@ -37,5 +37,17 @@ with torch.no_grad():
     wq = torch.randn(3 * C, C, device=dev, generator=g) * C ** -0.5
     for _ in range(2):
         _native.linear_f32(xm, wq, None)
+    # fp32 attention (VideoMAE layer 0), bf16 attention with the key bias (opt-in kernel), class-token rows (TimeSformer)
+    qf = torch.randn(8, 1568, 3 * C, device=dev, generator=g)
+    for _ in range(2):
+        _native.attention_f32(qf, 12, 0.125)
+    qb = qf.to(torch.bfloat16)
+    bias = torch.rand(8, 1568, device=dev, generator=g)
+    for _ in range(2):
+        _native.attention_bf16(qb, 12, 0.125, bias)
+    res_s = torch.randn(B * T, 1 + P, C, device=dev, generator=g).to(torch.bfloat16)
+    cls = torch.empty(B, C, device=dev, dtype=torch.bfloat16)
+    for _ in range(2):
+        _native.cls_rows(x[:, 0], mean_src=res_s.view(B, T, 1 + P, C)[:, :, 0], sum_out=cls)
 torch.cuda.synchronize()
 print("done")

@@ -111,6 +111,21 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16*
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  const int row0 = b * p.N;
+  const int nb = p.nblk;
+  // the softmax threads' query loads go out before the TMEM allocation and the barrier, so that their latency (the planes of
+  // a 173 MB tensor: mostly HBM) overlaps the CTA's set-up: 32 channels (64 bytes) per plane and thread; rows past the tensor
+  // are zero
+  uint4 qv[12];
+  if (warp >= 2 && warp < 10) {
+    const int s_q = qt * AF_BM + (warp & 3) * 32 + lane;
+    const bool in = (long long)row0 + s_q < (long long)p.B * p.N;
+    const uint4* src = reinterpret_cast<const uint4*>(qkv3 + ((long long)row0 + s_q) * (3LL * C3) + h * AF_D + 32 * ((warp - 2) >> 2));
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qv[4 * pl + i] = in ? __ldg(src + (size_t)pl * (C3 / 8) + i) : make_uint4(0u, 0u, 0u, 0u);
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -119,8 +134,6 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16*
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const int row0 = b * p.N;
-  const int nb = p.nblk;
 #ifdef TOME_ATTN_TRACE
   const bool tr = blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
 #endif
@@ -216,15 +229,13 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16*
     const bool bias_vec = (p.N & 3) == 0;
     float* xch = reinterpret_cast<float*>(gen + (sm_xch - base));          // [2 blocks][2 halves][128 rows]
     const float LOG2E = 1.4426950408889634f;
-    {   // this row's query planes into tensor memory: 32 channels (64 bytes) per plane and thread; rows past the tensor are zero
-      const bool in = (long long)row0 + s_idx < (long long)p.B * p.N;
-      const uint4* src = reinterpret_cast<const uint4*>(qkv3 + ((long long)row0 + s_idx) * (3LL * C3) + h * AF_D + 32 * half);
+    {   // this row's query planes (loaded above) into tensor memory
 #pragma unroll
       for (int pl = 0; pl < 3; ++pl) {
         uint32_t w[16];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const uint4 v = in ? __ldg(src + (size_t)pl * (C3 / 8) + i) : make_uint4(0u, 0u, 0u, 0u);
+          const uint4 v = qv[4 * pl + i];
           w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
         }
         tmem_st16(tmem_base + tlane + AT_Q + 32u * pl + 16u * half, w);
