@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 23
+#define TOME_ABI_VERSION 24
 
 #if defined(__GNUC__)
 #define TOME_API __attribute__((visibility("default")))
@@ -284,7 +284,7 @@ TOME_API int tome_attn_short(const void* q, const void* k, const void* v, int32_
  *   this is plain attention over up to 256 tokens with a key bias -- TimeSformer's spatial attention
  *   (tome/patch/timesformer.py:70-79), whose class QUERY takes no bias: unbiased_queries = 1.
  * tome_traj_temporal -- the temporal stage: out[r, h] = sum_f softmax_f(scale * q2[r,h] . k2[r,f,h]) * vals[r,f,h] for
- *   rows r = (b, s); q2 / out (rows, heads*64), k2 / vals (rows, frames, heads*64), frames <= 32. */
+ *   rows r = (b, s); q2 / out (rows, heads*64), k2 / vals (rows, frames, heads*64), frames <= 32; bf16 or fp32 tensors. */
 TOME_API int tome_frames_attention(const void* qkv, int32_t dtype, int32_t b, int32_t n, int32_t heads, int32_t d, int32_t frames,
                           int32_t keys_per_frame, int32_t lead, int32_t unbiased_queries, float scale, const float* key_bias,
                           void* xs, void* x_diag, void* stream);
@@ -334,6 +334,15 @@ TOME_API int tome_linear_f32(const void* x3, const void* w3, const void* bias, i
  * (the output projection's operand). */
 TOME_API int tome_attention_f32(const void* qkv3, int32_t b, int32_t n, int32_t heads, int32_t d, float scale,
                        const float* key_bias, int32_t unbiased_queries, void* out, void* out_planes, void* stream);
+
+/* tome_frames_attention in fp32 accuracy (the fp32 Motionformer: the reference benchmark's arithmetic): the same per-frame
+ * attention on the exact-split kernel of tome_attention_f32 (which is its frames == 1, lead == 0 case), from qkv3 =
+ * tome_split3 of the QKV GEMM's output viewed (b*n, 3*heads*64).  Any keys_per_frame; xs (b, S, frames, heads*64) fp32 and /
+ * or xs_planes (b*S*frames, 3*heads*64) bf16 planes (the operand of the K projection that follows); x_diag (b, S, heads*64)
+ * fp32 or NULL. */
+TOME_API int tome_frames_attention_f32(const void* qkv3, int32_t b, int32_t n, int32_t heads, int32_t d, int32_t frames,
+                              int32_t keys_per_frame, int32_t lead, float scale, const float* key_bias, void* xs,
+                              void* xs_planes, void* x_diag, void* stream);
 
 /* Caller-side bf16 attention with the proportional-attention key bias for sequences of any length (SURVEY.md 8f-f1;
  * tome/patch/videomae.py:58-68, vivit.py:98-117: `attn + size.log()`): out (b, n, heads*64) bf16 = softmax(scale * q k^T +

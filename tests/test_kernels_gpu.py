@@ -1137,6 +1137,53 @@ def test_frames_attention_matches_per_frame_softmax(native, P, with_bias):
     assert torch.equal(diag, xs[:, torch.arange(S, device="cuda"), frame])
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("with_bias", [False, True], ids=["plain", "prop_attn"])
+@pytest.mark.parametrize("P", [196, 178, 64, 37, 9])
+def test_frames_attention_f32_matches_per_frame_softmax(native, P, with_bias):
+    """tome_frames_attention_f32 (the exact-split attention kernel, one problem per frame) against the eager formulation of
+    Motionformer's space attention (tome/patch/motionformer.py:105-115) in fp64: fp32-class accuracy; the planes output is
+    the exact split of xs, x_diag its own-frame slice."""
+    g = torch.Generator().manual_seed(P)
+    B, h, Fr, d = 2, 3, 4, 64
+    S, C = Fr * P, h * d
+    qkv = torch.randn(B, 1 + S, 3 * C, generator=g).cuda()
+    bias = (torch.randint(1, 6, (B, S), generator=g).float().log()).cuda() if with_bias else None
+    with torch.no_grad():
+        assert native.frames_attention_f32_usable(qkv[..., :C], h)
+        xs, xs3, diag = native.frames_attention_f32(qkv, h, Fr, d ** -0.5, bias)
+    q, k, v = qkv.double().reshape(B, 1 + S, 3, h, d).permute(2, 0, 3, 1, 4)          # (B, h, N, d)
+    q, k, v = q[:, :, 1:], k[:, :, 1:].reshape(B, h, Fr, P, d), v[:, :, 1:].reshape(B, h, Fr, P, d)
+    sc = torch.einsum("bhsd,bhfpd->bhsfp", q, k) * d ** -0.5
+    if bias is not None:
+        sc = sc + bias.double().reshape(B, 1, 1, Fr, P)
+    want = torch.einsum("bhsfp,bhfpd->bsfhd", sc.softmax(-1), v).reshape(B, S, Fr, C)
+    err = (xs.double() - want).abs().max().item() / want.abs().max().item()
+    print(f"[frames_attention_f32] P={P} bias={with_bias}: max err / max|y| = {err:.2e}")
+    assert err <= 2e-6, err
+    frame = torch.arange(S, device="cuda") // P
+    assert torch.equal(diag, xs[:, torch.arange(S, device="cuda"), frame])
+    assert torch.equal(xs3.float(), xs)                                               # h + m + l == xs, bit for bit
+
+
+def test_traj_temporal_fp32_matches_einsum_formulation(native):
+    """fp32 tome_traj_temporal against vit_helper.py:232-243 in fp64."""
+    g = torch.Generator().manual_seed(4)
+    B, S, Fr, h, d = 2, 77, 8, 3, 64
+    C = h * d
+    q2 = torch.randn(B, S, C, generator=g).cuda()
+    k2 = torch.randn(B, S, Fr, C, generator=g).cuda()
+    xs = torch.randn(B, S, Fr, C, generator=g).cuda()
+    out = native.traj_temporal(q2, k2, xs, h, d ** -0.5)
+    assert out.dtype == torch.float32
+    qd = q2.double().reshape(B, S, h, d).transpose(1, 2) * d ** -0.5
+    kd = k2.double().reshape(B, S, Fr, h, d).permute(0, 3, 1, 2, 4)
+    vd = xs.double().reshape(B, S, Fr, h, d).permute(0, 3, 1, 2, 4)
+    attn = torch.einsum("bhsd,bhsfd->bhsf", qd, kd).softmax(-1)
+    want = torch.einsum("bhsf,bhsfd->bhsd", attn, vd).transpose(1, 2).reshape(B, S, C)
+    torch.testing.assert_close(out.double(), want, rtol=2e-5, atol=2e-5)
+
+
 def test_traj_temporal_matches_einsum_formulation(native):
     """tome_traj_temporal against vit_helper.py:232-243 (softmax over frames of q2 . k2, values = xs) in fp64."""
     g = torch.Generator().manual_seed(3)

@@ -29,12 +29,17 @@ constexpr int AF_SM = 256;                                                  // s
 constexpr uint32_t AF_KP = AF_BKV * 128u;           // one K / V plane of a key block: 64 rows x 128 bytes
 constexpr uint32_t AF_STAGE = 6u * AF_KP;           // K h,m,l | V h,m,l
 
+// One problem per (clip, frame): the S = F * P queries of a clip (tokens tok0 .. tok0 + S - 1 of its N) against the P keys of
+// frame f, softmax per frame -- the space stage of Motionformer's trajectory attention (tome/patch/motionformer.py:105-115).
+// Plain attention is the case F = 1, P = N, tok0 = 0: xs (B, S, 1, C) is then the (B, N, C) output.
 struct AfParams {
   int B, N, heads, nblk, nobias_q;
+  int F, P, S, tok0;
   float scale_log2e;
-  const float* bias;                                // (B, N) log size per key, or NULL
-  float* out;                                       // (B, N, heads * 64), or NULL
-  __nv_bfloat16* out3;                              // (B * N, 3 * heads * 64) bf16 planes of the same values (the projection's operand), or NULL
+  const float* bias;                                // (B, F * P) log size per key, or NULL
+  float* out;                                       // xs (B, S, F, heads * 64), or NULL
+  __nv_bfloat16* out3;                              // (B * S * F, 3 * heads * 64) bf16 planes of the same values (the next GEMM's operand), or NULL
+  float* diag;                                      // (B, S, heads * 64): xs[b, s, frame(s)] (the trajectory "diagonal"), or NULL
 };
 
 __device__ __forceinline__ float af_ex2(float x) {
@@ -92,7 +97,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_f32_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16* __restrict__ qkv3, const AfParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler, see the MMA warp
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z / p.F, f = blockIdx.z - b * p.F;
   const int C = p.heads * AF_D, C3 = 3 * C;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -111,7 +116,8 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16*
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const int row0 = b * p.N;
+  const int row0 = b * p.N + p.tok0;                 // first query token of the clip
+  const int krow0 = row0 + f * p.P;                  // first key of this frame
   const int nb = p.nblk;
   // the softmax threads' query loads go out before the TMEM allocation and the barrier, so that their latency (the planes of
   // a 173 MB tensor: mostly HBM) overlaps the CTA's set-up: 32 channels (64 bytes) per plane and thread; rows past the tensor
@@ -146,11 +152,11 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16*
         if (k >= 1) mbar_wait_sleep(bar_kempty + 8u * s, (k - 1) & 1u, 32);
         mbar_expect_tx(bar_kfull + 8u * s, 3u * AF_KP);
 #pragma unroll
-        for (int pl = 0; pl < 3; ++pl) tma_load_2d(st + pl * AF_KP, &map_kv, pl * C3 + C + h * AF_D, row0 + j * AF_BKV, bar_kfull + 8u * s);
+        for (int pl = 0; pl < 3; ++pl) tma_load_2d(st + pl * AF_KP, &map_kv, pl * C3 + C + h * AF_D, krow0 + j * AF_BKV, bar_kfull + 8u * s);
         if (k >= 1) mbar_wait_sleep(bar_vempty + 8u * s, (k - 1) & 1u, 32);
         mbar_expect_tx(bar_vfull + 8u * s, 3u * AF_KP);
 #pragma unroll
-        for (int pl = 0; pl < 3; ++pl) tma_load_2d(st + (3 + pl) * AF_KP, &map_kv, pl * C3 + 2 * C + h * AF_D, row0 + j * AF_BKV, bar_vfull + 8u * s);
+        for (int pl = 0; pl < 3; ++pl) tma_load_2d(st + (3 + pl) * AF_KP, &map_kv, pl * C3 + 2 * C + h * AF_D, krow0 + j * AF_BKV, bar_vfull + 8u * s);
       }
     }
   } else if (warp == 1) {
@@ -222,11 +228,11 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16*
     const int half = (warp - 2) >> 2;                          // which 32 key columns of a block / 32 channels of O
     const int row = q4 * 32 + lane;
     const int s_idx = qt * AF_BM + row;                        // query token within the clip
-    const bool live = s_idx < p.N;
+    const bool live = s_idx < p.S;
     const bool biased = p.bias != nullptr && s_idx >= p.nobias_q;
     const uint32_t tlane = (uint32_t)(q4 * 32) << 16;
-    const float* brow = p.bias ? p.bias + (long long)b * p.N : nullptr;
-    const bool bias_vec = (p.N & 3) == 0;
+    const float* brow = p.bias ? p.bias + (long long)b * p.S + (long long)f * p.P : nullptr;      // this frame's keys
+    const bool bias_vec = ((p.P | p.S) & 3) == 0;
     float* xch = reinterpret_cast<float*>(gen + (sm_xch - base));          // [2 blocks][2 halves][128 rows]
     const float LOG2E = 1.4426950408889634f;
     {   // this row's query planes (loaded above) into tensor memory
@@ -268,13 +274,13 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16*
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (biased && bias_vec && key0 + e + 3 < p.N) b4 = __ldg(reinterpret_cast<const float4*>(brow + key0 + e));
-          else if (biased && key0 + e + 3 < p.N) {             // rows of the bias are not 16-byte aligned (n % 4 != 0)
+          if (biased && bias_vec && key0 + e + 3 < p.P) b4 = __ldg(reinterpret_cast<const float4*>(brow + key0 + e));
+          else if (biased && key0 + e + 3 < p.P) {             // rows of the bias are not 16-byte aligned (n % 4 != 0)
             b4.x = __ldg(brow + key0 + e); b4.y = __ldg(brow + key0 + e + 1); b4.z = __ldg(brow + key0 + e + 2); b4.w = __ldg(brow + key0 + e + 3);
           } else if (biased) {
-            b4.x = key0 + e < p.N ? __ldg(brow + key0 + e) : 0.f;
-            b4.y = key0 + e + 1 < p.N ? __ldg(brow + key0 + e + 1) : 0.f;
-            b4.z = key0 + e + 2 < p.N ? __ldg(brow + key0 + e + 2) : 0.f;
+            b4.x = key0 + e < p.P ? __ldg(brow + key0 + e) : 0.f;
+            b4.y = key0 + e + 1 < p.P ? __ldg(brow + key0 + e + 1) : 0.f;
+            b4.z = key0 + e + 2 < p.P ? __ldg(brow + key0 + e + 2) : 0.f;
           }
           t[e] = fmaf(t[e], p.scale_log2e, b4.x * LOG2E);
           t[e + 1] = fmaf(t[e + 1], p.scale_log2e, b4.y * LOG2E);
@@ -285,9 +291,9 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16*
 #pragma unroll
         for (int e = 0; e < 32; ++e) t[e] *= p.scale_log2e;    // (the reference's q * scale, in log2 units)
       }
-      if (key0 + 32 > p.N) {                                   // last block: keys beyond the clip
+      if (key0 + 32 > p.P) {                                   // last block: keys beyond the frame / clip
 #pragma unroll
-        for (int e = 0; e < 32; ++e) if (key0 + e >= p.N) t[e] = -INFINITY;
+        for (int e = 0; e < 32; ++e) if (key0 + e >= p.P) t[e] = -INFINITY;
       }
       float bmax = -INFINITY;
 #pragma unroll
@@ -337,13 +343,19 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16*
       const float inv = 1.0f / l;
 #pragma unroll
       for (int e = 0; e < 32; ++e) oacc[e] *= inv;
+      const long long orow = ((long long)b * p.S + s_idx) * p.F + f;       // row of xs (B, S, F, C)
       if (p.out) {
-        float4* dst = reinterpret_cast<float4*>(p.out + ((long long)b * p.N + s_idx) * C + h * AF_D + 32 * half);
+        float4* dst = reinterpret_cast<float4*>(p.out + orow * C + h * AF_D + 32 * half);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dst[e] = make_float4(oacc[4 * e], oacc[4 * e + 1], oacc[4 * e + 2], oacc[4 * e + 3]);
+      }
+      if (p.diag && s_idx / p.P == f) {                                    // the query's own frame
+        float4* dst = reinterpret_cast<float4*>(p.diag + ((long long)b * p.S + s_idx) * C + h * AF_D + 32 * half);
 #pragma unroll
         for (int e = 0; e < 8; ++e) dst[e] = make_float4(oacc[4 * e], oacc[4 * e + 1], oacc[4 * e + 2], oacc[4 * e + 3]);
       }
       if (p.out3) {
-        __nv_bfloat16* d3 = p.out3 + ((long long)b * p.N + s_idx) * 3 * C + h * AF_D + 32 * half;
+        __nv_bfloat16* d3 = p.out3 + orow * 3 * C + h * AF_D + 32 * half;
 #pragma unroll
         for (int e = 0; e < 4; ++e) store_planes8(d3 + 8 * e, C, reinterpret_cast<const float(&)[8]>(oacc[8 * e]));
       }
@@ -357,21 +369,26 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16*
   }
 }
 
-int launch_attention_f32(const void* qkv3, int B, int N, int heads, float scale, const float* bias, int nobias_q, void* out,
-                         void* out3, cudaStream_t st) {
+// qkv3 (B * N, 9 * heads * 64) bf16 planes; per clip the queries are tokens tok0 .. tok0 + F * P - 1 and frame f's keys tokens
+// tok0 + f * P .. + P - 1 (plain attention: F = 1, P = N, tok0 = 0)
+int launch_frames_attention_f32(const void* qkv3, int B, int N, int heads, int F, int P, int tok0, float scale, const float* bias,
+                                int nobias_q, void* out, void* out3, void* diag, cudaStream_t st) {
   if (!out && !out3) return set_error(TOME_ERR_ARG, "tome_attention_f32: no output");
-  if (((uintptr_t)qkv3 & 15) || ((uintptr_t)out & 15) || ((uintptr_t)out3 & 15) || (bias && ((uintptr_t)bias & 15)))
+  if (F < 1 || P < 1 || tok0 < 0 || N != tok0 + F * P)
+    return set_error(TOME_ERR_ARG, "tome_frames_attention_f32: N=%d != lead + F*P (lead=%d F=%d P=%d)", N, tok0, F, P);
+  if (((uintptr_t)qkv3 & 15) || ((uintptr_t)out & 15) || ((uintptr_t)out3 & 15) || ((uintptr_t)diag & 15) || (bias && ((uintptr_t)bias & 15)))
     return set_error(TOME_ERR_ALIGN, "tome_attention_f32: buffers must be 16-byte aligned");
   AfParams p;
-  p.B = B; p.N = N; p.heads = heads; p.nblk = (N + AF_BKV - 1) / AF_BKV; p.nobias_q = nobias_q;
+  p.B = B; p.N = N; p.heads = heads; p.nblk = (P + AF_BKV - 1) / AF_BKV; p.nobias_q = nobias_q;
+  p.F = F; p.P = P; p.S = F * P; p.tok0 = tok0;
   p.scale_log2e = scale * 1.4426950408889634f;
-  p.bias = bias; p.out = (float*)out; p.out3 = (__nv_bfloat16*)out3;
+  p.bias = bias; p.out = (float*)out; p.out3 = (__nv_bfloat16*)out3; p.diag = (float*)diag;
   const long long rows = (long long)B * N, cols = 9LL * heads * AF_D;
   alignas(64) CUtensorMap map_kv;
   int rc = make_bf16_map(&map_kv, qkv3, rows, cols, cols, AF_BKV, "tome_attention_f32");
   if (rc) return rc;
-  dim3 grid((N + AF_BM - 1) / AF_BM, heads, B);
-  if (grid.z > 65535) return set_error(TOME_ERR_UNSUPPORTED, "tome_attention_f32: batch %d > 65535", B);
+  if ((long long)B * F > 65535) return set_error(TOME_ERR_UNSUPPORTED, "tome_attention_f32: batch x frames %lld > 65535", (long long)B * F);
+  dim3 grid((p.S + AF_BM - 1) / AF_BM, heads, B * F);
   const size_t smem = 1024 + AT_NST * AF_STAGE + 192 + 4 * AF_BM * sizeof(float);
   static PerDeviceOnce once;
   if (once.first_time()) {
@@ -384,7 +401,13 @@ int launch_attention_f32(const void* qkv3, int B, int N, int heads, float scale,
   return TOME_OK;
 }
 
+int launch_attention_f32(const void* qkv3, int B, int N, int heads, float scale, const float* bias, int nobias_q, void* out,
+                         void* out3, cudaStream_t st) {
+  return launch_frames_attention_f32(qkv3, B, N, heads, 1, N, 0, scale, bias, nobias_q, out, out3, nullptr, st);
+}
+
 }  // namespace tome
+
 #ifdef TOME_ATTN_TRACE
 extern "C" TOME_API int tome_debug_attn_trace(long long* out) {
   return (int)cudaMemcpyFromSymbol(out, tome::g_af_trace, sizeof(long long) * 8 * 32);

@@ -304,40 +304,56 @@ frames_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 }
 
 // ---- temporal stage of the trajectory attention (vit_helper.py:216-243): one query per (token, head) against the F
-// per-frame keys k2 = proj_k(xs), values = xs itself (use_original_code) or v2.  One thread per (token, head).
-__global__ void __launch_bounds__(128) traj_temporal_kernel(const __nv_bfloat16* __restrict__ q2, const __nv_bfloat16* __restrict__ k2,
-                                                           const __nv_bfloat16* __restrict__ vals, long long rows, int F, int heads,
-                                                           float scale, __nv_bfloat16* __restrict__ out) {
+// per-frame keys k2 = proj_k(xs), values = xs itself (use_original_code) or v2.  One thread per (token, head); bf16 or
+// fp32 tensors (the fp32 models: tome_frames_attention_f32 in front of it), fp32 arithmetic either way.
+__device__ __forceinline__ void tt_load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+}
+__device__ __forceinline__ void tt_load8(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void tt_store8(__nv_bfloat16* p, const float (&f)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+__device__ __forceinline__ void tt_store8(float* p, const float (&f)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) traj_temporal_kernel(const T* __restrict__ q2, const T* __restrict__ k2, const T* __restrict__ vals,
+                                                           long long rows, int F, int heads, float scale, T* __restrict__ out) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= rows * heads) return;
   const int h = (int)(gid % heads);
   const long long r = gid / heads;
   const int C = heads * FA_D;
   float q[FA_D];
-  {
-    const uint4* qp = reinterpret_cast<const uint4*>(q2 + r * C + h * FA_D);
 #pragma unroll
-    for (int c = 0; c < FA_D / 8; ++c) {
-      const uint4 v = __ldg(qp + c);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  for (int c = 0; c < FA_D / 8; ++c) {
+    float v[8];
+    tt_load8(q2 + r * C + h * FA_D + 8 * c, v);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { q[8 * c + 2 * i] = __uint_as_float(w[i] << 16) * scale; q[8 * c + 2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u) * scale; }
-    }
+    for (int i = 0; i < 8; ++i) q[8 * c + i] = v[i] * scale;
   }
   float sc[32];
   float m = -INFINITY;
 #pragma unroll 1
   for (int f = 0; f < F; ++f) {
-    const uint4* kp = reinterpret_cast<const uint4*>(k2 + (r * F + f) * C + h * FA_D);
+    const T* kp = k2 + (r * F + f) * C + h * FA_D;
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
     for (int c = 0; c < FA_D / 8; ++c) {
-      const uint4 v = __ldg(kp + c);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      float v[8];
+      tt_load8(kp + 8 * c, v);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        a0 = fmaf(q[8 * c + 2 * i], __uint_as_float(w[i] << 16), a0);
-        a1 = fmaf(q[8 * c + 2 * i + 1], __uint_as_float(w[i] & 0xFFFF0000u), a1);
+      for (int i = 0; i < 8; i += 2) {
+        a0 = fmaf(q[8 * c + i], v[i], a0);
+        a1 = fmaf(q[8 * c + i + 1], v[i + 1], a1);
       }
     }
     const float d = a0 + a1;
@@ -358,23 +374,17 @@ __global__ void __launch_bounds__(128) traj_temporal_kernel(const __nv_bfloat16*
 #pragma unroll
     for (int u = 0; u < 32; ++u) if (u == f) pw = sc[u];
     pw *= inv;
-    const uint4* vp = reinterpret_cast<const uint4*>(vals + (r * F + f) * C + h * FA_D);
+    const T* vp = vals + (r * F + f) * C + h * FA_D;
 #pragma unroll
     for (int c = 0; c < FA_D / 8; ++c) {
-      const uint4 v = __ldg(vp + c);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      float v[8];
+      tt_load8(vp + 8 * c, v);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        acc[8 * c + 2 * i] = fmaf(pw, __uint_as_float(w[i] << 16), acc[8 * c + 2 * i]);
-        acc[8 * c + 2 * i + 1] = fmaf(pw, __uint_as_float(w[i] & 0xFFFF0000u), acc[8 * c + 2 * i + 1]);
-      }
+      for (int i = 0; i < 8; ++i) acc[8 * c + i] = fmaf(pw, v[i], acc[8 * c + i]);
     }
   }
-  uint4* op = reinterpret_cast<uint4*>(out + r * C + h * FA_D);
 #pragma unroll
-  for (int c = 0; c < FA_D / 8; ++c)
-    op[c] = make_uint4(pack_bf16(acc[8 * c], acc[8 * c + 1]), pack_bf16(acc[8 * c + 2], acc[8 * c + 3]),
-                       pack_bf16(acc[8 * c + 4], acc[8 * c + 5]), pack_bf16(acc[8 * c + 6], acc[8 * c + 7]));
+  for (int c = 0; c < FA_D / 8; ++c) tt_store8(out + r * C + h * FA_D + 8 * c, reinterpret_cast<const float(&)[8]>(acc[8 * c]));
 }
 
 // ---- host -------------------------------------------------------------------------------------------------------
@@ -405,15 +415,19 @@ int launch_frames_attention(const void* qkv, int B, int N, int heads, int F, int
   return TOME_OK;
 }
 
-int launch_traj_temporal(const void* q2, const void* k2, const void* vals, long long rows, int F, int heads, float scale, void* out,
-                         cudaStream_t st) {
+int launch_traj_temporal(const void* q2, const void* k2, const void* vals, int dtype, long long rows, int F, int heads, float scale,
+                         void* out, cudaStream_t st) {
   if (F < 1 || F > 32) return set_error(TOME_ERR_UNSUPPORTED, "tome_traj_temporal: %d frames (1..32)", F);
   if (((uintptr_t)q2 & 15) || ((uintptr_t)k2 & 15) || ((uintptr_t)vals & 15) || ((uintptr_t)out & 15))
     return set_error(TOME_ERR_ALIGN, "tome_traj_temporal: buffers must be 16-byte aligned");
   const long long total = rows * heads;
-  traj_temporal_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>((const __nv_bfloat16*)q2, (const __nv_bfloat16*)k2,
-                                                                         (const __nv_bfloat16*)vals, rows, F, heads, scale,
-                                                                         (__nv_bfloat16*)out);
+  const unsigned grid = (unsigned)((total + 127) / 128);
+  if (dtype == TOME_BF16)
+    traj_temporal_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q2, (const __nv_bfloat16*)k2, (const __nv_bfloat16*)vals,
+                                                               rows, F, heads, scale, (__nv_bfloat16*)out);
+  else if (dtype == TOME_F32)
+    traj_temporal_kernel<float><<<grid, 128, 0, st>>>((const float*)q2, (const float*)k2, (const float*)vals, rows, F, heads, scale, (float*)out);
+  else return set_error(TOME_ERR_DTYPE, "tome_traj_temporal: unsupported dtype %d", dtype);
   TOME_LAUNCH_CHECK("traj_temporal_kernel");
   return TOME_OK;
 }

@@ -85,7 +85,8 @@ int launch_group_reduce(const void*, int, int, int, const View&, const int*, lon
 int launch_gather_rows(const void*, int, int, int, int, const int*, int, void*, cudaStream_t);
 int launch_attn_short(const void*, const void*, const void*, int, long long, int, int, int, long long, long long, float, void*, cudaStream_t);
 int launch_frames_attention(const void*, int, int, int, int, int, float, const float*, void*, void*, int, int, cudaStream_t);
-int launch_traj_temporal(const void*, const void*, const void*, long long, int, int, float, void*, cudaStream_t);
+int launch_traj_temporal(const void*, const void*, const void*, int, long long, int, int, float, void*, cudaStream_t);
+int launch_frames_attention_f32(const void*, int, int, int, int, int, int, float, const float*, int, void*, void*, void*, cudaStream_t);
 int launch_split3(const void*, long long, int, long long, void*, cudaStream_t);
 int launch_linear_f32(const void*, const void*, const void*, int, int, int, int, int, void*, void*, cudaStream_t);
 int launch_attention_f32(const void*, int, int, int, float, const float*, int, void*, void*, cudaStream_t);
@@ -511,8 +512,9 @@ int tome_traj_temporal(const void* q2, const void* k2, const void* vals, int32_t
   int rc = ensure_device_ok();
   if (rc) return rc;
   TOME_CHECK_ARG(q2 && k2 && vals && out && rows > 0 && frames > 0 && heads > 0, "tome_traj_temporal: NULL pointer or empty shape");
-  if (dtype != TOME_BF16 || d != 64) return set_error(TOME_ERR_UNSUPPORTED, "tome_traj_temporal: bf16 with head dimension 64 only (dtype %d, d %d)", dtype, d);
-  return launch_traj_temporal(q2, k2, vals, rows, frames, heads, scale, out, (cudaStream_t)stream);
+  if ((dtype != TOME_BF16 && dtype != TOME_F32) || d != 64)
+    return set_error(TOME_ERR_UNSUPPORTED, "tome_traj_temporal: bf16 / fp32 with head dimension 64 only (dtype %d, d %d)", dtype, d);
+  return launch_traj_temporal(q2, k2, vals, dtype, rows, frames, heads, scale, out, (cudaStream_t)stream);
 }
 
 int tome_split3(const void* x, int64_t rows, int32_t k, int64_t row_stride, void* out, void* stream) {
@@ -538,6 +540,17 @@ int tome_attention_f32(const void* qkv3, int32_t b, int32_t n, int32_t heads, in
   TOME_CHECK_ARG(qkv3 && (out || out_planes) && b > 0 && n > 0 && heads > 0 && unbiased_queries >= 0, "tome_attention_f32: NULL pointer or empty shape");
   if (d != 64) return set_error(TOME_ERR_UNSUPPORTED, "tome_attention_f32: head dimension %d (64 only)", d);
   return launch_attention_f32(qkv3, b, n, heads, scale, key_bias, unbiased_queries, out, out_planes, (cudaStream_t)stream);
+}
+
+int tome_frames_attention_f32(const void* qkv3, int32_t b, int32_t n, int32_t heads, int32_t d, int32_t frames, int32_t keys_per_frame,
+                              int32_t lead, float scale, const float* key_bias, void* xs, void* xs_planes, void* x_diag, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(qkv3 && (xs || xs_planes) && b > 0 && n > 0 && heads > 0 && frames > 0 && keys_per_frame > 0 && lead >= 0,
+                 "tome_frames_attention_f32: NULL pointer or empty shape");
+  if (d != 64) return set_error(TOME_ERR_UNSUPPORTED, "tome_frames_attention_f32: head dimension %d (64 only)", d);
+  return launch_frames_attention_f32(qkv3, b, n, heads, frames, keys_per_frame, lead, scale, key_bias, 0, xs, xs_planes, x_diag,
+                                     (cudaStream_t)stream);
 }
 
 int tome_attention_bf16(const void* qkv, int32_t b, int32_t n, int32_t heads, int32_t d, float scale, const float* key_bias,

@@ -18,7 +18,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 23
+ABI_VERSION = 24
 
 TOME_F32, TOME_BF16, TOME_U8 = 0, 1, 2
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -33,7 +33,7 @@ EXPORTS = (
     "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_linear_gelu", "tome_unmerge",
     "tome_match_sets_workspace_bytes", "tome_match_sets", "tome_group_reduce", "tome_gather_rows",
     "tome_source_compose", "tome_source_dense", "tome_random_rowmax", "tome_merge_add_norm_rv", "tome_rows_add_layernorm", "tome_attn_short",
-    "tome_frames_attention", "tome_traj_temporal", "tome_split3", "tome_linear_f32", "tome_attention_f32", "tome_cls_rows", "tome_attention_bf16",
+    "tome_frames_attention", "tome_traj_temporal", "tome_split3", "tome_linear_f32", "tome_attention_f32", "tome_cls_rows", "tome_attention_bf16", "tome_frames_attention_f32",
 )
 
 
@@ -134,7 +134,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.tome_linear_f32.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]
     lib.tome_attention_f32.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_i32, c_vp, c_vp, c_vp]
     lib.tome_attention_bf16.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_i32, c_vp, c_vp]
-    for name in ("tome_split3", "tome_linear_f32", "tome_attention_f32", "tome_attention_bf16"):
+    lib.tome_frames_attention_f32.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]
+    for name in ("tome_split3", "tome_linear_f32", "tome_attention_f32", "tome_attention_bf16", "tome_frames_attention_f32"):
         getattr(lib, name).restype = c_i32
     lib.tome_frames_attention.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp]
     lib.tome_traj_temporal.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]
@@ -865,6 +866,47 @@ def attention_f32(qkv, heads: int, scale: float, key_bias: Optional[torch.Tensor
                                       torch.cuda.current_stream(dev).cuda_stream), lib)
     p3 = None if res3 is None else Planes(res3, (B, N, c))
     return res if out == "fp32" else p3 if out == "planes" else (res, p3)
+
+
+def frames_attention_f32_usable(x: torch.Tensor, heads: int) -> bool:
+    """tome_frames_attention_f32 / fp32 tome_traj_temporal serve this trajectory-attention input: CUDA fp32 inference, head
+    dimension 64."""
+    return (x.is_cuda and not torch.is_grad_enabled() and x.dtype == torch.float32 and x.dim() == 3 and x.shape[2] == 64 * heads
+            and os.environ.get("TOME_ATTENTION_F32", "1") != "0")
+
+
+def frames_attention_f32(qkv, heads: int, frames: int, scale: float, key_bias: Optional[torch.Tensor] = None, lead: int = 1,
+                         want_diag: bool = True):
+    """Space stage of the trajectory attention in fp32 accuracy (include/tome_b200.h: tome_frames_attention_f32) from the QKV
+    GEMM's output (B, lead + F*P, 3 * heads * 64) as an fp32 tensor or ``Planes``: returns xs (B, F*P, F, heads*64) fp32, the
+    same values as ``Planes`` (the K projection's operand) and x_diag (B, F*P, heads*64) = xs[b, s, frame(s)] (or None).
+    ``key_bias`` (B, F*P) fp32 in the token order."""
+    lib = load_library()
+    if isinstance(qkv, Planes):
+        B, N, c3 = qkv.shape
+        x3 = qkv.data
+    else:
+        _require_cuda(qkv, "qkv")
+        B, N, c3 = qkv.shape
+        x3 = split3(qkv.reshape(B * N, c3))
+    c = c3 // 3
+    S = N - lead
+    P = S // frames
+    if S != frames * P:
+        raise RuntimeError(f"tome_b200: frames_attention_f32: {N} tokens != {lead} + {frames} frames x P")
+    bp = None
+    if key_bias is not None:
+        key_bias = key_bias.to(torch.float32).reshape(B, S).contiguous()
+        bp = key_bias.data_ptr()
+    dev = x3.device
+    with torch.cuda.device(dev):
+        xs = torch.empty(B, S, frames, c, dtype=torch.float32, device=dev)
+        xs3 = torch.empty(B * S * frames, 3 * c, dtype=torch.bfloat16, device=dev)
+        xd = torch.empty(B, S, c, dtype=torch.float32, device=dev) if want_diag else None
+        _check(lib.tome_frames_attention_f32(x3.data_ptr(), B, N, heads, c // heads, frames, P, lead, float(scale), bp, xs.data_ptr(),
+                                             xs3.data_ptr(), None if xd is None else xd.data_ptr(),
+                                             torch.cuda.current_stream(dev).cuda_stream), lib)
+    return xs, Planes(xs3, (B, S, frames, c)), xd
 
 
 def attention_bf16_usable(qkv: torch.Tensor, heads: int, key_bias: Optional[torch.Tensor] = None) -> bool:

@@ -17,6 +17,16 @@ from tome.patch.videomae import _normed_or, _swap, fusable_norm, lazy_head_mean
 from tome.utils import parse_r
 
 
+def _weight_rows(mod, tag, w, lo, hi):
+    """A row slice of ``w`` as one long-lived tensor object, so that tome_linear_f32's per-weight plane cache (keyed by the
+    tensor's identity) holds: a fresh ``w[lo:hi]`` view per call would re-split the weight every time."""
+    cache = mod.__dict__.setdefault("_tome_weight_rows", {})
+    hit = cache.get(tag)
+    if hit is None or hit[0] is not w or hit[1] != w._version:
+        hit = cache[tag] = (w, w._version, w[lo:hi])
+    return hit[2]
+
+
 def trajectory_attention(mod, x, num_frames, log_size=None, on_keys=None):
     """vit_helper.py:146-267 (approx == 'none').  x (B, 1 + F*P, C), tokens '(f n)'.
     ``log_size`` (B, F*P) adds the proportional-attention key bias in the flat key order
@@ -39,6 +49,27 @@ def trajectory_attention(mod, x, num_frames, log_size=None, on_keys=None):
         wkv, bkv = mod.proj_kv.weight, mod.proj_kv.bias
         k2 = F.linear(xs, wkv[:C], None if bkv is None else bkv[:C])
         vals = xs if mod.use_original_code else F.linear(xs, wkv[C:], None if bkv is None else bkv[C:])
+        out = _native.traj_temporal(q2, k2, vals, h, mod.scale)
+        out = mod.proj_drop(mod.proj(torch.cat((cls_out, out), dim=1)))
+        return out, k[:, :, 1:]
+    if (d == 64 and _native.frames_attention_f32_usable(x, h) and N == 1 + Fr * P and Fr <= 32
+            and _native.linear_f32_usable(x, mod.qkv.weight, mod.qkv.bias) and _native.linear_f32_weight_ok(mod.proj_kv.weight[:C], None)):
+        # fp32 inference (the reference benchmark's arithmetic): both stages on the exact-split tensor-core kernels
+        # (tome_frames_attention_f32: tome_attention_f32 with one problem per frame; fp32 tome_traj_temporal); the QKV GEMM
+        # hands its result over as split planes, the space stage hands xs over as planes to the K projection
+        qkv, qkv3 = _native.linear_f32(x, mod.qkv.weight, mod.qkv.bias, out="both")
+        q, k, v = qkv.view(B, N, 3, h, d).permute(2, 0, 3, 1, 4)
+        if on_keys is not None:
+            on_keys(k[:, :, 1:])
+        cls_out = F.scaled_dot_product_attention(q[:, :, 0:1], k, v, scale=mod.scale).transpose(1, 2).reshape(B, 1, C)
+        xs, xs3, x_diag = _native.frames_attention_f32(qkv3, h, Fr, mod.scale, log_size)
+        q2 = mod.proj_q(x_diag)
+        wkv, bkv = mod.proj_kv.weight, mod.proj_kv.bias
+        k2 = _native.linear_f32(xs3, _weight_rows(mod, "k", wkv, 0, C), None if bkv is None else bkv[:C])
+        if mod.use_original_code:
+            vals = xs
+        else:
+            vals = _native.linear_f32(xs3, _weight_rows(mod, "v", wkv, C, 2 * C), None if bkv is None else bkv[C:])
         out = _native.traj_temporal(q2, k2, vals, h, mod.scale)
         out = mod.proj_drop(mod.proj(torch.cat((cls_out, out), dim=1)))
         return out, k[:, :, 1:]
