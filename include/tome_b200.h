@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 24
+#define TOME_ABI_VERSION 25
 
 #if defined(__GNUC__)
 #define TOME_API __attribute__((visibility("default")))
@@ -334,6 +334,12 @@ TOME_API int tome_linear_f32(const void* x3, const void* w3, const void* bias, i
  * (the output projection's operand). */
 TOME_API int tome_attention_f32(const void* qkv3, int32_t b, int32_t n, int32_t heads, int32_t d, float scale,
                        const float* key_bias, int32_t unbiased_queries, void* out, void* out_planes, void* stream);
+
+/* One query token against the whole sequence (Motionformer's class token, slowfast vit_helper.py:181-189 `cls_out`): out (b,
+ * heads*64) = softmax(scale * q[b, query_token] . k[b, :]) v[b, :] per head from the QKV GEMM's contiguous (b, n, 3*heads*64)
+ * output, bf16 or fp32 (fp32 arithmetic either way). */
+TOME_API int tome_cls_attention(const void* qkv, int32_t dtype, int32_t b, int32_t n, int32_t heads, int32_t d, int32_t query_token,
+                       float scale, void* out, void* stream);
 
 /* tome_frames_attention in fp32 accuracy (the fp32 Motionformer: the reference benchmark's arithmetic): the same per-frame
  * attention on the exact-split kernel of tome_attention_f32 (which is its frames == 1, lead == 0 case), from qkv3 =

@@ -1184,6 +1184,22 @@ def test_traj_temporal_fp32_matches_einsum_formulation(native):
     torch.testing.assert_close(out.double(), want, rtol=2e-5, atol=2e-5)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("N", [1569, 197, 41])
+def test_cls_attention_matches_single_query_softmax(native, N, dtype):
+    """tome_cls_attention (Motionformer's class-token row, vit_helper.py:181-189) against fp64."""
+    g = torch.Generator().manual_seed(N)
+    B, h, d = 2, 3, 64
+    C = h * d
+    qkv = torch.randn(B, N, 3 * C, generator=g).to("cuda", dtype)
+    out = native.cls_attention(qkv, h, d ** -0.5)
+    q, k, v = qkv.double().reshape(B, N, 3, h, d).permute(2, 0, 3, 1, 4)
+    want = (((q[:, :, 0:1] @ k.transpose(-1, -2)) * d ** -0.5).softmax(-1) @ v).transpose(1, 2).reshape(B, 1, C)
+    tol = 1e-2 if dtype == torch.bfloat16 else 2e-6
+    assert out.shape == (B, 1, C) and out.dtype == dtype
+    torch.testing.assert_close(out.double(), want, rtol=tol, atol=tol)
+
+
 def test_traj_temporal_matches_einsum_formulation(native):
     """tome_traj_temporal against vit_helper.py:232-243 (softmax over frames of q2 . k2, values = xs) in fp64."""
     g = torch.Generator().manual_seed(3)

@@ -32,6 +32,8 @@ template <> struct Ld8<__nv_bfloat16> {
     }
     *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
   }
+  static __device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static __device__ __forceinline__ __nv_bfloat16 from_float(float v) { return __float2bfloat16_rn(v); }
 };
 template <> struct Ld8<float> {
   static __device__ __forceinline__ void load(const float* p, float (&f)[8]) {
@@ -42,6 +44,8 @@ template <> struct Ld8<float> {
     reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
     reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
   }
+  static __device__ __forceinline__ float to_float(float v) { return v; }
+  static __device__ __forceinline__ float from_float(float v) { return v; }
 };
 
 // q / k / v element (s, t, h, c) at base + s * ss + t * st + h * D + c; out (s, t, h, c) contiguous.
@@ -135,6 +139,89 @@ int launch_attn_short(const void* q, const void* k, const void* v, int dtype, lo
   else
     return set_error(TOME_ERR_DTYPE, "tome_attn_short: unsupported dtype %d", dtype);
   TOME_LAUNCH_CHECK("attn_short_kernel");
+  return TOME_OK;
+}
+
+// ---- one query against a whole sequence: Motionformer's class token (vit_helper.py:181-189: `cls_out`), which attends to all
+// 1 + F * P tokens while the patch queries go through the per-frame kernel.  The library's fused attention spends 86 us per
+// layer on that single row in fp32 (a 64 x 64-tile kernel with one live query); it is a 77 MB streaming pass: one CTA per
+// (clip, head), scores of all keys in shared memory, then channel c of the output by thread c of each of four key groups.
+constexpr int CA_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(CA_THREADS) cls_attn_kernel(const T* __restrict__ qkv, int n, int heads, int q_tok, float scale,
+                                                             T* __restrict__ out) {
+  extern __shared__ float ca_sm[];                     // [n scores][CA_THREADS reduction scratch]
+  float* sc = ca_sm;
+  float* red = ca_sm + n;
+  const int b = blockIdx.x / heads, h = blockIdx.x - b * heads, tid = threadIdx.x;
+  const int C = heads * 64;
+  const long long row = 3LL * C;
+  const T* base = qkv + (long long)b * n * row;
+  float q[64];
+#pragma unroll
+  for (int c = 0; c < 64; c += 8) {
+    float f[8];
+    Ld8<T>::load(base + (long long)q_tok * row + h * 64 + c, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q[c + e] = f[e] * scale;
+  }
+  float m = -INFINITY;
+  for (int t = tid; t < n; t += CA_THREADS) {
+    const T* kr = base + (long long)t * row + C + h * 64;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 64; c += 8) {
+      float f[8];
+      Ld8<T>::load(kr + c, f);
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) { a0 = fmaf(q[c + e], f[e], a0); a1 = fmaf(q[c + e + 1], f[e + 1], a1); }
+    }
+    const float d = a0 + a1;
+    sc[t] = d;
+    m = fmaxf(m, d);
+  }
+  red[tid] = m;
+  __syncthreads();
+  for (int of = CA_THREADS / 2; of > 0; of >>= 1) { if (tid < of) red[tid] = fmaxf(red[tid], red[tid + of]); __syncthreads(); }
+  m = red[0];
+  __syncthreads();
+  float l = 0.f;
+  for (int t = tid; t < n; t += CA_THREADS) { const float e = __expf(sc[t] - m); sc[t] = e; l += e; }
+  red[tid] = l;
+  __syncthreads();
+  for (int of = CA_THREADS / 2; of > 0; of >>= 1) { if (tid < of) red[tid] += red[tid + of]; __syncthreads(); }
+  const float inv = 1.0f / red[0];
+  __syncthreads();
+  // out[c] = sum_t p_t v[t][c]: thread (c, g) takes the keys t = g mod 4: 64 consecutive channels per key row
+  const int c = tid & 63, g = tid >> 6;
+  float acc = 0.f;
+  for (int t = g; t < n; t += CA_THREADS / 64) acc = fmaf(sc[t], Ld8<T>::to_float(base[(long long)t * row + 2 * C + h * 64 + c]), acc);
+  red[tid] = acc;
+  __syncthreads();
+  if (tid < 64) {
+    const float y = ((red[tid] + red[tid + 64]) + (red[tid + 128] + red[tid + 192])) * inv;
+    out[(long long)b * C + h * 64 + tid] = Ld8<T>::from_float(y);
+  }
+}
+
+int launch_cls_attention(const void* qkv, int dtype, int b, int n, int heads, int q_tok, float scale, void* out, cudaStream_t stm) {
+  if (((uintptr_t)qkv & 15) || ((uintptr_t)out & 3)) return set_error(TOME_ERR_ALIGN, "tome_cls_attention: qkv must be 16-byte aligned");
+  if (q_tok < 0 || q_tok >= n) return set_error(TOME_ERR_ARG, "tome_cls_attention: query token %d outside 0..%d", q_tok, n - 1);
+  const size_t smem = ((size_t)n + CA_THREADS) * sizeof(float);
+  if (smem > 200 * 1024) return set_error(TOME_ERR_UNSUPPORTED, "tome_cls_attention: %d tokens", n);
+  if (dtype == TOME_F32) {
+    static PerDeviceOnce once;
+    if (once.first_time()) TOME_CUDA(cudaFuncSetAttribute(cls_attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    cls_attn_kernel<float><<<b * heads, CA_THREADS, smem, stm>>>((const float*)qkv, n, heads, q_tok, scale, (float*)out);
+  } else if (dtype == TOME_BF16) {
+    static PerDeviceOnce once;
+    if (once.first_time()) TOME_CUDA(cudaFuncSetAttribute(cls_attn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    cls_attn_kernel<__nv_bfloat16><<<b * heads, CA_THREADS, smem, stm>>>((const __nv_bfloat16*)qkv, n, heads, q_tok, scale, (__nv_bfloat16*)out);
+  } else {
+    return set_error(TOME_ERR_DTYPE, "tome_cls_attention: unsupported dtype %d", dtype);
+  }
+  TOME_LAUNCH_CHECK("cls_attn_kernel");
   return TOME_OK;
 }
 

@@ -84,6 +84,7 @@ int launch_match_sets(const void*, int, int, int, const View&, const int*, long 
 int launch_group_reduce(const void*, int, int, int, const View&, const int*, long long, int, int, const int*, int, void*, cudaStream_t);
 int launch_gather_rows(const void*, int, int, int, int, const int*, int, void*, cudaStream_t);
 int launch_attn_short(const void*, const void*, const void*, int, long long, int, int, int, long long, long long, float, void*, cudaStream_t);
+int launch_cls_attention(const void*, int, int, int, int, int, float, void*, cudaStream_t);
 int launch_frames_attention(const void*, int, int, int, int, int, float, const float*, void*, void*, int, int, cudaStream_t);
 int launch_traj_temporal(const void*, const void*, const void*, int, long long, int, int, float, void*, cudaStream_t);
 int launch_frames_attention_f32(const void*, int, int, int, int, int, int, float, const float*, int, void*, void*, void*, cudaStream_t);
@@ -540,6 +541,16 @@ int tome_attention_f32(const void* qkv3, int32_t b, int32_t n, int32_t heads, in
   TOME_CHECK_ARG(qkv3 && (out || out_planes) && b > 0 && n > 0 && heads > 0 && unbiased_queries >= 0, "tome_attention_f32: NULL pointer or empty shape");
   if (d != 64) return set_error(TOME_ERR_UNSUPPORTED, "tome_attention_f32: head dimension %d (64 only)", d);
   return launch_attention_f32(qkv3, b, n, heads, scale, key_bias, unbiased_queries, out, out_planes, (cudaStream_t)stream);
+}
+
+int tome_cls_attention(const void* qkv, int32_t dtype, int32_t b, int32_t n, int32_t heads, int32_t d, int32_t query_token, float scale,
+                       void* out, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(qkv && out && b > 0 && n > 0 && heads > 0, "tome_cls_attention: NULL pointer or empty shape");
+  if (d != 64) return set_error(TOME_ERR_UNSUPPORTED, "tome_cls_attention: head dimension %d (64 only)", d);
+  if ((long long)b * heads > 0x7fffffffLL) return set_error(TOME_ERR_UNSUPPORTED, "tome_cls_attention: too many (clip, head) pairs");
+  return launch_cls_attention(qkv, dtype, b, n, heads, query_token, scale, out, (cudaStream_t)stream);
 }
 
 int tome_frames_attention_f32(const void* qkv3, int32_t b, int32_t n, int32_t heads, int32_t d, int32_t frames, int32_t keys_per_frame,

@@ -18,7 +18,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 24
+ABI_VERSION = 25
 
 TOME_F32, TOME_BF16, TOME_U8 = 0, 1, 2
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -33,7 +33,7 @@ EXPORTS = (
     "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_linear_gelu", "tome_unmerge",
     "tome_match_sets_workspace_bytes", "tome_match_sets", "tome_group_reduce", "tome_gather_rows",
     "tome_source_compose", "tome_source_dense", "tome_random_rowmax", "tome_merge_add_norm_rv", "tome_rows_add_layernorm", "tome_attn_short",
-    "tome_frames_attention", "tome_traj_temporal", "tome_split3", "tome_linear_f32", "tome_attention_f32", "tome_cls_rows", "tome_attention_bf16", "tome_frames_attention_f32",
+    "tome_frames_attention", "tome_traj_temporal", "tome_split3", "tome_linear_f32", "tome_attention_f32", "tome_cls_rows", "tome_attention_bf16", "tome_frames_attention_f32", "tome_cls_attention",
 )
 
 
@@ -135,7 +135,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.tome_attention_f32.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_i32, c_vp, c_vp, c_vp]
     lib.tome_attention_bf16.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_i32, c_vp, c_vp]
     lib.tome_frames_attention_f32.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]
-    for name in ("tome_split3", "tome_linear_f32", "tome_attention_f32", "tome_attention_bf16", "tome_frames_attention_f32"):
+    lib.tome_cls_attention.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]
+    for name in ("tome_split3", "tome_linear_f32", "tome_attention_f32", "tome_attention_bf16", "tome_frames_attention_f32", "tome_cls_attention"):
         getattr(lib, name).restype = c_i32
     lib.tome_frames_attention.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp]
     lib.tome_traj_temporal.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]
@@ -866,6 +867,21 @@ def attention_f32(qkv, heads: int, scale: float, key_bias: Optional[torch.Tensor
                                       torch.cuda.current_stream(dev).cuda_stream), lib)
     p3 = None if res3 is None else Planes(res3, (B, N, c))
     return res if out == "fp32" else p3 if out == "planes" else (res, p3)
+
+
+def cls_attention(qkv: torch.Tensor, heads: int, scale: float, query_token: int = 0) -> torch.Tensor:
+    """One query token against the whole sequence (include/tome_b200.h: tome_cls_attention): qkv (B, N, 3 * heads * 64)
+    contiguous, bf16 or fp32 -> (B, 1, heads * 64)."""
+    lib = load_library()
+    _require_cuda(qkv, "qkv")
+    if qkv.dim() != 3 or not qkv.is_contiguous() or qkv.shape[-1] != 3 * heads * 64:
+        raise RuntimeError("tome_b200: cls_attention needs a contiguous (B, N, 3 * heads * 64) tensor")
+    B, N, _ = qkv.shape
+    with torch.cuda.device(qkv.device):
+        out = torch.empty(B, 1, heads * 64, dtype=qkv.dtype, device=qkv.device)
+        _check(lib.tome_cls_attention(qkv.data_ptr(), _dtype_code(qkv), B, N, heads, 64, int(query_token), float(scale), out.data_ptr(),
+                                      _stream(qkv)), lib)
+    return out
 
 
 def frames_attention_f32_usable(x: torch.Tensor, heads: int) -> bool:

@@ -61,7 +61,7 @@ def trajectory_attention(mod, x, num_frames, log_size=None, on_keys=None):
         q, k, v = qkv.view(B, N, 3, h, d).permute(2, 0, 3, 1, 4)
         if on_keys is not None:
             on_keys(k[:, :, 1:])
-        cls_out = F.scaled_dot_product_attention(q[:, :, 0:1], k, v, scale=mod.scale).transpose(1, 2).reshape(B, 1, C)
+        cls_out = _native.cls_attention(qkv, h, mod.scale)                 # the class token attends to everything, unbiased
         xs, xs3, x_diag = _native.frames_attention_f32(qkv3, h, Fr, mod.scale, log_size)
         q2 = mod.proj_q(x_diag)
         wkv, bkv = mod.proj_kv.weight, mod.proj_kv.bias
