@@ -92,12 +92,12 @@ __device__ __forceinline__ void af_split_pair(float p0, float p1, uint32_t& wh, 
 
 constexpr int AT_THREADS = 352;     // TMA, S issuer, 2 x 4 softmax warps, P V issuer
 
-template <bool HAS_BIAS>
+template <bool HAS_BIAS, bool FRAMES>                   // FRAMES: more than one frame per clip (the loop carries frame boundaries)
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_f32_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16* __restrict__ qkv3, const AfParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler, see the MMA warp
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z / p.F, f = blockIdx.z - b * p.F;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int C = p.heads * AF_D, C3 = 3 * C;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -116,9 +116,9 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16*
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const int row0 = b * p.N + p.tok0;                 // first query token of the clip
-  const int krow0 = row0 + f * p.P;                  // first key of this frame
-  const int nb = p.nblk;
+  const int row0 = b * p.N + p.tok0;                 // first query token of the clip == first key of frame 0
+  const int nbf = p.nblk;                            // 64-key blocks per frame
+  const int nb = FRAMES ? p.F * nbf : nbf;           // the CTA walks the blocks of all frames: Q, TMEM and the pipeline are set up once
   // the softmax threads' query loads go out before the TMEM allocation and the barrier, so that their latency (the planes of
   // a 173 MB tensor: mostly HBM) overlaps the CTA's set-up: 32 channels (64 bytes) per plane and thread; rows past the tensor
   // are zero
@@ -149,14 +149,16 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16*
       for (int j = 0; j < nb; ++j) {
         const uint32_t s = (uint32_t)(j % AT_NST), k = (uint32_t)(j / AT_NST);
         const uint32_t st = sm_kv + s * AF_STAGE;
+        const int fj = FRAMES ? j / nbf : 0;
+        const int krow = row0 + fj * p.P + (j - fj * nbf) * AF_BKV;         // block j - fj * nbf of frame fj
         if (k >= 1) mbar_wait_sleep(bar_kempty + 8u * s, (k - 1) & 1u, 32);
         mbar_expect_tx(bar_kfull + 8u * s, 3u * AF_KP);
 #pragma unroll
-        for (int pl = 0; pl < 3; ++pl) tma_load_2d(st + pl * AF_KP, &map_kv, pl * C3 + C + h * AF_D, krow0 + j * AF_BKV, bar_kfull + 8u * s);
+        for (int pl = 0; pl < 3; ++pl) tma_load_2d(st + pl * AF_KP, &map_kv, pl * C3 + C + h * AF_D, krow, bar_kfull + 8u * s);
         if (k >= 1) mbar_wait_sleep(bar_vempty + 8u * s, (k - 1) & 1u, 32);
         mbar_expect_tx(bar_vfull + 8u * s, 3u * AF_KP);
 #pragma unroll
-        for (int pl = 0; pl < 3; ++pl) tma_load_2d(st + (3 + pl) * AF_KP, &map_kv, pl * C3 + 2 * C + h * AF_D, krow0 + j * AF_BKV, bar_vfull + 8u * s);
+        for (int pl = 0; pl < 3; ++pl) tma_load_2d(st + (3 + pl) * AF_KP, &map_kv, pl * C3 + 2 * C + h * AF_D, krow, bar_vfull + 8u * s);
       }
     }
   } else if (warp == 1) {
@@ -231,9 +233,10 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16*
     const bool live = s_idx < p.S;
     const bool biased = p.bias != nullptr && s_idx >= p.nobias_q;
     const uint32_t tlane = (uint32_t)(q4 * 32) << 16;
-    const float* brow = p.bias ? p.bias + (long long)b * p.S + (long long)f * p.P : nullptr;      // this frame's keys
+    const float* bias_b = p.bias ? p.bias + (long long)b * p.S : nullptr;
     const bool bias_vec = ((p.P | p.S) & 3) == 0;
     float* xch = reinterpret_cast<float*>(gen + (sm_xch - base));          // [2 blocks][2 halves][128 rows]
+    float* lx = xch + 4 * AF_BM;                                           // [2 frames][2 halves][128 rows]: a finished frame's row sums
     const float LOG2E = 1.4426950408889634f;
     {   // this row's query planes (loaded above) into tensor memory
 #pragma unroll
@@ -260,8 +263,39 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16*
 #pragma unroll
       for (int e = 0; e < 32; ++e) oacc[e] += v[e];
     };
+    // the finished frame fd: O / l -> xs (B, S, F, C), its planes, the trajectory diagonal
+    auto write_frame = [&](int fd, float lsum) {
+      if (!live) return;
+      const float inv = 1.0f / lsum;
+      float o[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) o[e] = oacc[e] * inv;
+      const long long orow = ((long long)b * p.S + s_idx) * p.F + fd;      // row of xs
+      if (p.out) {
+        float4* dst = reinterpret_cast<float4*>(p.out + orow * C + h * AF_D + 32 * half);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+      }
+      if (p.diag && s_idx / p.P == fd) {                                   // the query's own frame
+        float4* dst = reinterpret_cast<float4*>(p.diag + ((long long)b * p.S + s_idx) * C + h * AF_D + 32 * half);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+      }
+      if (p.out3) {
+        __nv_bfloat16* d3 = p.out3 + orow * 3 * C + h * AF_D + 32 * half;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) store_planes8(d3 + 8 * e, C, reinterpret_cast<const float(&)[8]>(o[8 * e]));
+      }
+    };
     for (int j = 0; j < nb; ++j) {
       const uint32_t sb = (uint32_t)(j & 1), k = (uint32_t)(j >> 1);
+      const int f = FRAMES ? j / nbf : 0, jf = j - f * nbf;    // frame, block within the frame
+      const bool frame_start = FRAMES && jf == 0 && j > 0;     // (warp-uniform) the previous block closed frame f - 1
+      if (frame_start) {                                       // park that frame's row sum for the other half, start afresh:
+        lx[(((f - 1) & 1) * 2 + half) * AF_BM + row] = l;      // alpha below is 0 (m = -inf), which also clears the accumulator
+        m = -INFINITY;
+      }
+      const float* brow = HAS_BIAS ? bias_b + (long long)f * p.P : nullptr;      // this frame's keys
       mbar_wait(bar_s + 8u * sb, k & 1u);
       tc_fence_after();
       if (warp == 2) AF_TR(4, j);
@@ -269,7 +303,7 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16*
       tmem_ld32(tmem_base + tlane + sb * AT_S1 + 32u * half, t);
       tc_fence_before();
       af_arrive(bar_sfree + 8u * sb);
-      const int key0 = j * AF_BKV + 32 * half;
+      const int key0 = jf * AF_BKV + 32 * half;
       if (HAS_BIAS) {
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {
@@ -318,6 +352,8 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16*
         if (warp == 2) AF_TR(6, j);
         fold_o();
       }
+      if (frame_start)                                         // the other half's sum became visible at this block's barrier
+        write_frame(f - 1, l + lx[(((f - 1) & 1) * 2 + (half ^ 1)) * AF_BM + row]);
 #pragma unroll
       for (int e = 0; e < 32; ++e) oacc[e] *= alpha;
       l *= alpha;
@@ -339,27 +375,7 @@ attn_f32_kernel(const __grid_constant__ CUtensorMap map_kv, const __nv_bfloat16*
     xch[half * AF_BM + row] = l;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     l += xch[(half ^ 1) * AF_BM + row];
-    if (live) {
-      const float inv = 1.0f / l;
-#pragma unroll
-      for (int e = 0; e < 32; ++e) oacc[e] *= inv;
-      const long long orow = ((long long)b * p.S + s_idx) * p.F + f;       // row of xs (B, S, F, C)
-      if (p.out) {
-        float4* dst = reinterpret_cast<float4*>(p.out + orow * C + h * AF_D + 32 * half);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) dst[e] = make_float4(oacc[4 * e], oacc[4 * e + 1], oacc[4 * e + 2], oacc[4 * e + 3]);
-      }
-      if (p.diag && s_idx / p.P == f) {                                    // the query's own frame
-        float4* dst = reinterpret_cast<float4*>(p.diag + ((long long)b * p.S + s_idx) * C + h * AF_D + 32 * half);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) dst[e] = make_float4(oacc[4 * e], oacc[4 * e + 1], oacc[4 * e + 2], oacc[4 * e + 3]);
-      }
-      if (p.out3) {
-        __nv_bfloat16* d3 = p.out3 + orow * 3 * C + h * AF_D + 32 * half;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) store_planes8(d3 + 8 * e, C, reinterpret_cast<const float(&)[8]>(oacc[8 * e]));
-      }
-    }
+    write_frame(FRAMES ? p.F - 1 : 0, l);
   }
   tc_fence_before();
   __syncthreads();
@@ -387,16 +403,24 @@ int launch_frames_attention_f32(const void* qkv3, int B, int N, int heads, int F
   alignas(64) CUtensorMap map_kv;
   int rc = make_bf16_map(&map_kv, qkv3, rows, cols, cols, AF_BKV, "tome_attention_f32");
   if (rc) return rc;
-  if ((long long)B * F > 65535) return set_error(TOME_ERR_UNSUPPORTED, "tome_attention_f32: batch x frames %lld > 65535", (long long)B * F);
-  dim3 grid((p.S + AF_BM - 1) / AF_BM, heads, B * F);
-  const size_t smem = 1024 + AT_NST * AF_STAGE + 192 + 4 * AF_BM * sizeof(float);
+  if (B > 65535) return set_error(TOME_ERR_UNSUPPORTED, "tome_attention_f32: batch %d > 65535", B);
+  dim3 grid((p.S + AF_BM - 1) / AF_BM, heads, B);
+  const size_t smem = 1024 + AT_NST * AF_STAGE + 192 + 8 * AF_BM * sizeof(float);
   static PerDeviceOnce once;
   if (once.first_time()) {
-    TOME_CUDA(cudaFuncSetAttribute(attn_f32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TOME_CUDA(cudaFuncSetAttribute(attn_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TOME_CUDA(cudaFuncSetAttribute(attn_f32_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TOME_CUDA(cudaFuncSetAttribute(attn_f32_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TOME_CUDA(cudaFuncSetAttribute(attn_f32_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TOME_CUDA(cudaFuncSetAttribute(attn_f32_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  if (bias) attn_f32_kernel<true><<<grid, AT_THREADS, smem, st>>>(map_kv, (const __nv_bfloat16*)qkv3, p);
-  else attn_f32_kernel<false><<<grid, AT_THREADS, smem, st>>>(map_kv, (const __nv_bfloat16*)qkv3, p);
+  const __nv_bfloat16* q3 = (const __nv_bfloat16*)qkv3;
+  if (F > 1) {
+    if (bias) attn_f32_kernel<true, true><<<grid, AT_THREADS, smem, st>>>(map_kv, q3, p);
+    else attn_f32_kernel<false, true><<<grid, AT_THREADS, smem, st>>>(map_kv, q3, p);
+  } else {
+    if (bias) attn_f32_kernel<true, false><<<grid, AT_THREADS, smem, st>>>(map_kv, q3, p);
+    else attn_f32_kernel<false, false><<<grid, AT_THREADS, smem, st>>>(map_kv, q3, p);
+  }
   TOME_LAUNCH_CHECK("attn_f32_kernel");
   return TOME_OK;
 }
