@@ -318,7 +318,7 @@ TOME_API int tome_linear_gelu(const void* x, const void* w, const void* bias, in
  * rounding unit: the host mirror's default), terms = 6 also m.l and l.m (<= 2^-23 relative per product).
  * tome_split3: x (rows, k) fp32, rows `row_stride` elements apart -> out (rows, 3k) bf16 planes [h | m | l]; k % 4 == 0.
  * tome_linear_f32: out (m, n) fp32 = act(x @ W^T + bias) from the split planes x3 (m, 3k), w3 (n, 3k); bias (n) fp32 or
- *   NULL; gelu 0 / 1 (erf GELU, exact erf).  n % 256 == 0, k % 32 == 0.  out_planes (m, 3n) bf16: the result ALSO (or, with
+ *   NULL; gelu 0 / 1 (erf GELU, exact erf) / 2 (HuggingFace "gelu_fast", tanhf).  n % 256 == 0, k % 32 == 0.  out_planes (m, 3n) bf16: the result ALSO (or, with
  *   out == NULL, ONLY) as split planes -- the operand of the next tome_linear_f32 / tome_attention_f32 without an fp32
  *   round trip (fc1 -> fc2, qkv -> attention). */
 TOME_API int tome_split3(const void* x, int64_t rows, int32_t k, int64_t row_stride, void* out, void* stream);

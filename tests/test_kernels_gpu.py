@@ -1248,6 +1248,8 @@ def test_linear_f32_matches_fp64(native, shape, terms):
         torch.testing.assert_close(act, torch.nn.functional.gelu(out), rtol=1e-6, atol=1e-6)
         nob = native.linear_f32(x, w, None, terms=terms)
         torch.testing.assert_close(nob + b, out, rtol=1e-6, atol=1e-5)
+        from hostmodels.vivit import gelu_fast                   # HF FastGELUActivation, ViViT's hidden_act, in the epilogue
+        torch.testing.assert_close(native.linear_f32(x, w, b, gelu="gelu_fast", terms=terms), gelu_fast(out), rtol=2e-6, atol=2e-6)
 
 
 @pytest.mark.parametrize("shape", [(1000, 768, 768), (2100, 3072, 768), (777, 768, 3072)], ids=str)

@@ -42,7 +42,7 @@ struct LinearF32Params {
   const float* bias;                                // (n) or NULL
   float* out;                                       // (m, n) row-major, or NULL
   __nv_bfloat16* out3;                              // (m, 3n) bf16 planes of the same values (the next GEMM's operand), or NULL
-  int gelu;                                         // 0: bias only; 1: erf GELU (nn.GELU)
+  int gelu;                                         // 0: bias only; 1: erf GELU (nn.GELU); 2: HF "gelu_fast" (tanh form)
 };
 
 // ---- split -----------------------------------------------------------------------------------------------------
@@ -220,6 +220,10 @@ linear_f32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (p.gelu == 1) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) o[e] = 0.5f * o[e] * (1.0f + erff(o[e] * 0.70710678118654752440f));     // nn.GELU, exact erf
+            } else if (p.gelu == 2) {                       // HuggingFace FastGELUActivation (ViViT's hidden_act), libdevice tanhf
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                o[e] = 0.5f * o[e] * (1.0f + tanhf(o[e] * 0.7978845608f * (1.0f + 0.044715f * o[e] * o[e])));
             }
             if (orow) { orow[c * 8 + g] = make_float4(o[0], o[1], o[2], o[3]); orow[c * 8 + g + 1] = make_float4(o[4], o[5], o[6], o[7]); }
             if (prow) store_planes8(prow + c * 32 + g * 4, p.n, o);       // the next GEMM's operand, no fp32 round trip

@@ -530,7 +530,7 @@ int tome_linear_f32(const void* x3, const void* w3, const void* bias, int32_t m,
   int rc = ensure_device_ok();
   if (rc) return rc;
   TOME_CHECK_ARG(x3 && w3 && (out || out_planes) && m > 0 && n > 0 && k > 0, "tome_linear_f32: NULL pointer or bad shape");
-  TOME_CHECK_ARG(gelu == 0 || gelu == 1, "tome_linear_f32: gelu must be 0 or 1");
+  TOME_CHECK_ARG(gelu >= 0 && gelu <= 2, "tome_linear_f32: gelu must be 0, 1 or 2");
   return launch_linear_f32(x3, w3, bias, m, n, k, gelu, terms, out, out_planes, (cudaStream_t)stream);
 }
 

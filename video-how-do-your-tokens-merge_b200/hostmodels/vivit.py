@@ -125,6 +125,15 @@ class VivitIntermediate(nn.Module):
             from tome import _native
             if _native.linear_gelu_supported(x, self.dense.weight, self.dense.bias):
                 return _native.linear_gelu(x, self.dense.weight, self.dense.bias, gelu="gelu_fast")
+        if (self.intermediate_act_fn is gelu_fast and not self.training and x.is_cuda and x.dtype == torch.float32
+                and not torch.is_grad_enabled()):
+            # fp32 inference: dense + bias + gelu_fast in the exact-split GEMM's epilogue (tome_linear_f32, gelu = 2) instead of
+            # a GEMM plus seven elementwise passes (16 % of the fp32 ViViT step); the result goes to the output projection as
+            # split planes when that is an exact-split GEMM too
+            from tome import _native
+            if _native.linear_f32_usable(x, self.dense.weight, self.dense.bias):
+                return _native.linear_f32(x, self.dense.weight, self.dense.bias, gelu="gelu_fast",
+                                          out="planes" if getattr(self, "_planes_to_output", False) else "fp32")
         return self.intermediate_act_fn(self.dense(hidden_states))
 
 
@@ -183,6 +192,8 @@ class ViViT(nn.Module):                                 # vivit_video_model_buil
         self.classifier = nn.Linear(self.config.hidden_size, num_classes) if num_classes > 0 else nn.Identity()
         self.apply(self._init_weights)
         fastlinear.install(self)                        # fp32 CUDA inference: linears on tome_linear_f32
+        for layer in self.vivit.encoder.layer:          # fc1 may hand its result to fc2 as split planes
+            layer.intermediate._planes_to_output = isinstance(layer.output.dense, fastlinear.TomeLinear)
 
     def _init_weights(self, m):                         # HF VivitPreTrainedModel._init_weights
         std = self.config.initializer_range

@@ -825,7 +825,8 @@ def linear_f32(x, weight: torch.Tensor, bias: Optional[torch.Tensor], gelu: bool
     with torch.cuda.device(dev):
         res = torch.empty(m, n, dtype=torch.float32, device=dev) if out in ("fp32", "both") else None
         res3 = torch.empty(m, 3 * n, dtype=torch.bfloat16, device=dev) if out in ("planes", "both") else None
-        _check(lib.tome_linear_f32(x3.data_ptr(), w3.data_ptr(), None if bias is None else bias.data_ptr(), m, n, k, int(bool(gelu)),
+        gelu_code = 2 if gelu == "gelu_fast" else int(bool(gelu))          # HF FastGELUActivation (ViViT) / nn.GELU / none
+        _check(lib.tome_linear_f32(x3.data_ptr(), w3.data_ptr(), None if bias is None else bias.data_ptr(), m, n, k, gelu_code,
                                    int(terms), None if res is None else res.data_ptr(), None if res3 is None else res3.data_ptr(),
                                    torch.cuda.current_stream(dev).cuda_stream), lib)
     t = None if res is None else res.reshape(*lead, n)
