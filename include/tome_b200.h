@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 25
+#define TOME_ABI_VERSION 26
 
 #if defined(__GNUC__)
 #define TOME_API __attribute__((visibility("default")))
@@ -322,6 +322,9 @@ TOME_API int tome_linear_gelu(const void* x, const void* w, const void* bias, in
  *   out == NULL, ONLY) as split planes -- the operand of the next tome_linear_f32 / tome_attention_f32 without an fp32
  *   round trip (fc1 -> fc2, qkv -> attention). */
 TOME_API int tome_split3(const void* x, int64_t rows, int32_t k, int64_t row_stride, void* out, void* stream);
+/* The inverse on a column slice: out (rows, ncols) fp32 = h + m + l (exact) of columns col0 .. col0 + ncols - 1 of a planes
+ * tensor x3 (rows, 3n); multiples of 8.  (The K third of a QKV result held as planes, for the matching metric.) */
+TOME_API int tome_planes_sum(const void* x3, int64_t rows, int32_t n, int32_t col0, int32_t ncols, void* out, void* stream);
 TOME_API int tome_linear_f32(const void* x3, const void* w3, const void* bias, int32_t m, int32_t n, int32_t k, int32_t gelu,
                     int32_t terms, void* out, void* out_planes, void* stream);
 

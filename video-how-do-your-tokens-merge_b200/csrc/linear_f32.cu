@@ -240,6 +240,42 @@ linear_f32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   }
 }
 
+// The fp32 value of a column slice of a planes tensor: out (rows, ncols) = h + m + l, exact (h + m and (h + m) + l are both
+// representable).  The QKV GEMM hands its result over as planes ONLY -- writing the fp32 tensor as well from the same epilogue
+// costs more than this pass over the K third that the matching metric needs (329 us against 251 + 15 at 12544 x 2304:
+// tools/bench_linear_f32_outputs.py).
+__global__ void __launch_bounds__(256) planes_sum_kernel(const __nv_bfloat16* __restrict__ x3, long long rows, int n, int col0, int ncols,
+                                                        float* __restrict__ out) {
+  const int per_row = ncols >> 3;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= rows * per_row) return;
+  const long long r = gid / per_row;
+  const int c = (int)(gid - r * per_row) * 8;
+  const __nv_bfloat16* src = x3 + r * 3 * n + col0 + c;
+  const uint4 vh = __ldg(reinterpret_cast<const uint4*>(src)), vm = __ldg(reinterpret_cast<const uint4*>(src + n)),
+              vl = __ldg(reinterpret_cast<const uint4*>(src + 2 * n));
+  const uint32_t wh[4] = {vh.x, vh.y, vh.z, vh.w}, wm[4] = {vm.x, vm.y, vm.z, vm.w}, wl[4] = {vl.x, vl.y, vl.z, vl.w};
+  float f[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = (__uint_as_float(wh[i] << 16) + __uint_as_float(wm[i] << 16)) + __uint_as_float(wl[i] << 16);
+    f[2 * i + 1] = (__uint_as_float(wh[i] & 0xFFFF0000u) + __uint_as_float(wm[i] & 0xFFFF0000u)) + __uint_as_float(wl[i] & 0xFFFF0000u);
+  }
+  float4* dst = reinterpret_cast<float4*>(out + r * ncols + c);
+  dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+  dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+int launch_planes_sum(const void* x3, long long rows, int n, int col0, int ncols, void* out, cudaStream_t st) {
+  if (n % 8 || col0 % 8 || ncols % 8 || col0 < 0 || ncols < 8 || col0 + ncols > n)
+    return set_error(TOME_ERR_ARG, "tome_planes_sum: columns %d..%d of %d (multiples of 8 inside the row)", col0, col0 + ncols, n);
+  if (((uintptr_t)x3 & 15) || ((uintptr_t)out & 15)) return set_error(TOME_ERR_ALIGN, "tome_planes_sum: buffers must be 16-byte aligned");
+  const long long total = rows * (ncols >> 3);
+  planes_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)x3, rows, n, col0, ncols, (float*)out);
+  TOME_LAUNCH_CHECK("planes_sum_kernel");
+  return TOME_OK;
+}
+
 // ---- host -----------------------------------------------------------------------------------------------------
 int launch_split3(const void* x, long long rows, int k, long long row_stride, void* out, cudaStream_t st) {
   if (k % 4 != 0 || ((uintptr_t)x & 15) || ((uintptr_t)out & 7) || row_stride % 4)

@@ -89,6 +89,7 @@ int launch_frames_attention(const void*, int, int, int, int, int, float, const f
 int launch_traj_temporal(const void*, const void*, const void*, int, long long, int, int, float, void*, cudaStream_t);
 int launch_frames_attention_f32(const void*, int, int, int, int, int, int, float, const float*, int, void*, void*, void*, cudaStream_t);
 int launch_split3(const void*, long long, int, long long, void*, cudaStream_t);
+int launch_planes_sum(const void*, long long, int, int, int, void*, cudaStream_t);
 int launch_linear_f32(const void*, const void*, const void*, int, int, int, int, int, void*, void*, cudaStream_t);
 int launch_attention_f32(const void*, int, int, int, float, const float*, int, void*, void*, cudaStream_t);
 int launch_attention_bf16(const void*, int, int, int, float, const float*, int, void*, cudaStream_t);
@@ -523,6 +524,13 @@ int tome_split3(const void* x, int64_t rows, int32_t k, int64_t row_stride, void
   if (rc) return rc;
   TOME_CHECK_ARG(x && out && rows > 0 && k > 0 && row_stride >= k, "tome_split3: NULL pointer or bad shape");
   return launch_split3(x, rows, k, row_stride, out, (cudaStream_t)stream);
+}
+
+int tome_planes_sum(const void* x3, int64_t rows, int32_t n, int32_t col0, int32_t ncols, void* out, void* stream) {
+  int rc = ensure_device_ok();
+  if (rc) return rc;
+  TOME_CHECK_ARG(x3 && out && rows > 0 && n > 0, "tome_planes_sum: NULL pointer or empty shape");
+  return launch_planes_sum(x3, rows, n, col0, ncols, out, (cudaStream_t)stream);
 }
 
 int tome_linear_f32(const void* x3, const void* w3, const void* bias, int32_t m, int32_t n, int32_t k, int32_t gelu, int32_t terms,

@@ -76,15 +76,16 @@ class Attention(nn.Module):                             # builder:59-103
         qkv_bias = None
         if self.q_bias is not None:
             qkv_bias = torch.cat((self.q_bias, torch.zeros_like(self.v_bias, requires_grad=False), self.v_bias))
-        qkv_flat, qkv3 = fastlinear.linear(x, self.qkv.weight, qkv_bias, out="both")
         if x.is_cuda and x.dtype == torch.float32 and not self.training:
             from tome import _native
-            if qkv_flat.shape[-1] == 3 * 64 * self.num_heads and _native.attention_f32_usable(qkv_flat, self.num_heads):
-                # fp32 inference: exact-split flash attention on tcgen05 (tome_attention_f32), planes in and out
-                keep = isinstance(self.proj, fastlinear.TomeLinear) and qkv3 is not None
-                ctx = _native.attention_f32(qkv3 if qkv3 is not None else qkv_flat, self.num_heads, self.scale,
-                                            out="planes" if keep else "fp32")
+            if _native.linear_f32_usable(x, self.qkv.weight, qkv_bias) and _native.attention_f32_planes_ok(x, self.qkv.weight, self.num_heads):
+                # fp32 inference: exact-split QKV GEMM and flash attention on tcgen05 (tome_linear_f32 / tome_attention_f32),
+                # planes from one to the other and on to the projection
+                qkv3 = _native.linear_f32(x, self.qkv.weight, qkv_bias, out="planes")
+                keep = isinstance(self.proj, fastlinear.TomeLinear)
+                ctx = _native.attention_f32(qkv3, self.num_heads, self.scale, out="planes" if keep else "fp32")
                 return self.proj_drop(self.proj(ctx))
+        qkv_flat = fastlinear.linear(x, self.qkv.weight, qkv_bias)
         qkv = qkv_flat.reshape(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4)
         x = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], scale=self.scale,
                                            dropout_p=self.attn_drop.p if self.training else 0.0)

@@ -81,7 +81,8 @@ class VivitSelfAttention(nn.Module):
             if prop_attention.usable_f32(hidden_states, self, self.num_attention_heads, self.attention_head_size):
                 ctx, _ = prop_attention.attention_f32(hidden_states, self, self.num_attention_heads, self.attention_head_size,
                                                       self.scaling, None, self.query.weight, self.key.weight, self.value.weight,
-                                                      self.query.bias, self.key.bias, self.value.bias)
+                                                      self.query.bias, self.key.bias, self.value.bias,
+                                                      planes_for=getattr(self, "_tome_ctx_consumer", None))
                 return ctx, None
         shp = (B, -1, self.num_attention_heads, self.attention_head_size)
         q = self.query(hidden_states).view(*shp).transpose(1, 2)
@@ -107,6 +108,7 @@ class VivitAttention(nn.Module):
         self.output = VivitSelfOutput(config)
 
     def forward(self, hidden_states, **kwargs):
+        object.__setattr__(self.attention, "_tome_ctx_consumer", self.output.dense)   # a hint (see tome/attention.py), not a submodule
         return self.output(self.attention(hidden_states)[0], hidden_states)
 
 

@@ -18,7 +18,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_PKG, "lib", "libtome_b200.so")
-ABI_VERSION = 25
+ABI_VERSION = 26
 
 TOME_F32, TOME_BF16, TOME_U8 = 0, 1, 2
 MATCH_AUTO, MATCH_EXACT_SIMT, MATCH_TCGEN05 = 0, 1, 2
@@ -33,7 +33,7 @@ EXPORTS = (
     "tome_merge_source", "tome_attn_key_bias", "tome_patchify", "tome_linear_gelu", "tome_unmerge",
     "tome_match_sets_workspace_bytes", "tome_match_sets", "tome_group_reduce", "tome_gather_rows",
     "tome_source_compose", "tome_source_dense", "tome_random_rowmax", "tome_merge_add_norm_rv", "tome_rows_add_layernorm", "tome_attn_short",
-    "tome_frames_attention", "tome_traj_temporal", "tome_split3", "tome_linear_f32", "tome_attention_f32", "tome_cls_rows", "tome_attention_bf16", "tome_frames_attention_f32", "tome_cls_attention",
+    "tome_frames_attention", "tome_traj_temporal", "tome_split3", "tome_linear_f32", "tome_attention_f32", "tome_cls_rows", "tome_attention_bf16", "tome_frames_attention_f32", "tome_cls_attention", "tome_planes_sum",
 )
 
 
@@ -135,6 +135,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.tome_attention_f32.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_i32, c_vp, c_vp, c_vp]
     lib.tome_attention_bf16.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_i32, c_vp, c_vp]
     lib.tome_frames_attention_f32.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]
+    lib.tome_planes_sum.argtypes = [c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp]
+    lib.tome_planes_sum.restype = c_i32
     lib.tome_cls_attention.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]
     for name in ("tome_split3", "tome_linear_f32", "tome_attention_f32", "tome_attention_bf16", "tome_frames_attention_f32", "tome_cls_attention"):
         getattr(lib, name).restype = c_i32
@@ -804,6 +806,21 @@ class Planes:
         return ((d[:, :k] + d[:, k:2 * k]) + d[:, 2 * k:]).reshape(self.shape)
 
 
+def planes_to_f32(planes: "Planes", col0: int = 0, ncols: Optional[int] = None) -> torch.Tensor:
+    """The fp32 tensor (exact: h + m + l) of columns ``col0 .. col0 + ncols`` of the last axis of a ``Planes``
+    (include/tome_b200.h: tome_planes_sum); shape planes.shape[:-1] + (ncols,)."""
+    lib = load_library()
+    n = planes.shape[-1]
+    ncols = n - col0 if ncols is None else ncols
+    rows = planes.data.shape[0]
+    dev = planes.data.device
+    with torch.cuda.device(dev):
+        out = torch.empty(*planes.shape[:-1], ncols, dtype=torch.float32, device=dev)
+        _check(lib.tome_planes_sum(planes.data.data_ptr(), rows, n, int(col0), int(ncols), out.data_ptr(),
+                                   torch.cuda.current_stream(dev).cuda_stream), lib)
+    return out
+
+
 def linear_f32(x, weight: torch.Tensor, bias: Optional[torch.Tensor], gelu: bool = False, terms: Optional[int] = None,
                out: str = "fp32"):
     """act(x @ weight^T + bias) in fp32 on the tensor cores (exact bf16 three-way split; ``terms`` plane products: 8 by default =
@@ -839,6 +856,12 @@ def attention_f32_usable(qkv: torch.Tensor, heads: int, key_bias: Optional[torch
     return (qkv.is_cuda and qkv.dtype == torch.float32 and not torch.is_grad_enabled() and qkv.dim() == 3
             and qkv.shape[2] == 3 * 64 * heads and qkv.shape[1] >= 64
             and os.environ.get("TOME_ATTENTION_F32", "1") != "0")
+
+
+def attention_f32_planes_ok(x: torch.Tensor, qkv_weight: torch.Tensor, heads: int) -> bool:
+    """The QKV GEMM of this input can hand its result to tome_attention_f32 as planes only (64-channel heads, >= 64 tokens)."""
+    return (x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled() and x.dim() == 3 and x.shape[1] >= 64
+            and qkv_weight.shape[0] == 3 * 64 * heads and os.environ.get("TOME_ATTENTION_F32", "1") != "0")
 
 
 def attention_f32(qkv, heads: int, scale: float, key_bias: Optional[torch.Tensor] = None, unbiased_queries: int = 0,

@@ -146,10 +146,12 @@ class _Probe:
 _PROBE = _Probe()
 
 
-def attention_f32(x, owner, heads, d, scale, log_size, wq, wk, wv, bq=None, bk=None, bv=None, lead=0, on_keys=None):
+def attention_f32(x, owner, heads, d, scale, log_size, wq, wk, wv, bq=None, bk=None, bv=None, lead=0, on_keys=None, planes_for=None):
     """fp32 attention over x (B, N, C), ``log_size`` (B, N - lead[, 1]) or None added to the logits of the non-leading
     keys (for the non-leading queries only when lead > 0): one exact-split QKV GEMM (``tome_linear_f32`` on the cached
-    concatenated weight) and ``tome_attention_f32``.  Returns (context (B, N, heads * d), keys (B, heads, N, d))."""
+    concatenated weight, handing its result over as split planes) and ``tome_attention_f32``.  Returns (context (B, N,
+    heads * d), keys (B, heads, N, d)); the context comes as ``Planes`` when ``planes_for`` -- the linear layer it feeds -- is
+    an exact-split GEMM itself (no fp32 round trip, no second split)."""
     from tome import _native
     B, N, _ = x.shape
     key = _key_of((wq, wk, wv, bq, bk, bv))
@@ -159,8 +161,14 @@ def attention_f32(x, owner, heads, d, scale, log_size, wq, wk, wv, bq=None, bk=N
         zb = lambda t, ref: t.detach() if t is not None else torch.zeros(ref.shape[0], dtype=ref.dtype, device=ref.device)
         bcat = None if (bq is None and bk is None and bv is None) else torch.cat((zb(bq, wq), zb(bk, wk), zb(bv, wv)), 0).contiguous()
         cached = owner._tome_plain_qkv = (key, w, bcat)
-    qkv = _native.linear(x, cached[1], cached[2])
-    k = qkv[..., heads * d:2 * heads * d].view(B, N, heads, d).transpose(1, 2)
+    qkv3 = None
+    if _native.linear_f32_usable(x, cached[1], cached[2]):
+        # planes only: writing the fp32 tensor from the same epilogue costs more than the exact sum of the K planes below
+        qkv3 = _native.linear_f32(x, cached[1], cached[2], out="planes")
+        k = _native.planes_to_f32(qkv3, heads * d, heads * d).view(B, N, heads, d).transpose(1, 2)
+    else:
+        qkv = F.linear(x, cached[1], cached[2])
+        k = qkv[..., heads * d:2 * heads * d].view(B, N, heads, d).transpose(1, 2)
     if on_keys is not None:
         on_keys(k)
     kb = None
@@ -168,7 +176,10 @@ def attention_f32(x, owner, heads, d, scale, log_size, wq, wk, wv, bq=None, bk=N
         kb = log_size.reshape(B, N - lead).float()
         if lead:
             kb = F.pad(kb, (lead, 0))
-    ctx = _native.attention_f32(qkv, heads, scale, kb, unbiased_queries=lead if kb is not None else 0)
+    as_planes = (planes_for is not None and type(planes_for).__name__ == "TomeLinear" and not planes_for.training
+                 and _native.linear_f32_weight_ok(planes_for.weight, planes_for.bias))
+    ctx = _native.attention_f32(qkv3 if qkv3 is not None else qkv, heads, scale, kb, unbiased_queries=lead if kb is not None else 0,
+                                out="planes" if as_planes else "fp32")
     return ctx, k
 
 

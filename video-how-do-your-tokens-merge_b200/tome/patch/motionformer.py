@@ -57,7 +57,8 @@ def trajectory_attention(mod, x, num_frames, log_size=None, on_keys=None):
         # fp32 inference (the reference benchmark's arithmetic): both stages on the exact-split tensor-core kernels
         # (tome_frames_attention_f32: tome_attention_f32 with one problem per frame; fp32 tome_traj_temporal); the QKV GEMM
         # hands its result over as split planes, the space stage hands xs over as planes to the K projection
-        qkv, qkv3 = _native.linear_f32(x, mod.qkv.weight, mod.qkv.bias, out="both")
+        qkv = _native.linear_f32(x, mod.qkv.weight, mod.qkv.bias)          # fp32 for the class row and the metric, and its split
+        qkv3 = _native.Planes(_native.split3(qkv.view(B * N, 3 * C)), (B, N, 3 * C))    # (one epilogue writing both is slower)
         q, k, v = qkv.view(B, N, 3, h, d).permute(2, 0, 3, 1, 4)
         if on_keys is not None:
             on_keys(k[:, :, 1:])

@@ -154,7 +154,8 @@ class ToMeAttentionMixin:
             early = {}
             x, k = prop_attention.attention_f32(
                 x, self, self.num_heads, C // self.num_heads, self.scale, None if size is None else log_size, wq, wk, wv, bq, bk, bv,
-                lead=1, on_keys=lambda keys: early.update(metric=prop_attention.early_metric(self, keys[:, :, 1:, :])))
+                lead=1, on_keys=lambda keys: early.update(metric=prop_attention.early_metric(self, keys[:, :, 1:, :])),
+                planes_for=self.proj)
             return self.proj_drop(self.proj(x)), early["metric"]
         if self.with_qkv:
             qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)

@@ -151,17 +151,29 @@ class ToMeAttentionMixin:
                                             self.q_bias, None, self.v_bias, on_keys=on_keys)
         else:
             from tome import _native
-            qkv3 = None
-            if _native.linear_f32_usable(x, self.qkv.weight, qkv_bias):   # fp32 inference: tome_linear_f32, result also as split planes
-                qkv_flat, qkv3 = _native.linear_f32(x, self.qkv.weight, qkv_bias, out="both")
-            else:
-                qkv_flat = F.linear(x, self.qkv.weight, qkv_bias)
-            qkv = qkv_flat.reshape(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4)
-            q, k, v = qkv[0], qkv[1], qkv[2]
-            on_keys(k)
             if size is not None and log_size is None:   # proportional attention (videomae.py:62-63)
                 log_size = size.log()
             kb = None if size is None else log_size[..., 0]
+            qkv3 = None
+            if _native.linear_f32_usable(x, self.qkv.weight, qkv_bias) and _native.attention_f32_planes_ok(x, self.qkv.weight, self.num_heads):
+                # fp32 inference: the QKV GEMM (tome_linear_f32) hands its result over as split planes ONLY; the fp32 keys the
+                # matching metric needs are the exact sum of their three planes (tome_planes_sum on the K third)
+                qkv3 = _native.linear_f32(x, self.qkv.weight, qkv_bias, out="planes")
+                C1 = self.qkv.weight.shape[0] // 3
+                k = _native.planes_to_f32(qkv3, C1, C1).view(B, N, self.num_heads, -1).transpose(1, 2)
+                on_keys(k)
+                keep = type(self.proj).__name__ == "TomeLinear"           # proj takes the planes directly
+                x = _native.attention_f32(qkv3, self.num_heads, self.scale, kb, out="planes" if keep else "fp32")
+                x = self.proj_drop(self.proj(x))
+                if head_aggregation == 'mean':
+                    return x, early["metric"]
+                if head_aggregation == 'concat':
+                    return x, k.transpose(1, 2).reshape(B, N, -1)
+                raise ValueError(f"head_aggregation must be 'mean' or 'concat', got {head_aggregation!r}")
+            qkv_flat = _native.linear(x, self.qkv.weight, qkv_bias) if x.is_cuda else F.linear(x, self.qkv.weight, qkv_bias)
+            qkv = qkv_flat.reshape(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4)
+            q, k, v = qkv[0], qkv[1], qkv[2]
+            on_keys(k)
             if q.shape[-1] == 64 and _native.attention_f32_usable(qkv_flat, self.num_heads, kb):
                 # fp32 inference: exact-split flash attention on tcgen05, key bias taken directly
                 keep = qkv3 is not None and type(self.proj).__name__ == "TomeLinear"      # proj takes the planes directly

@@ -65,6 +65,9 @@ class ToMeVivitAttentionMixin:
     """vivit.py:69-83."""
 
     def forward(self, hidden_states, size=None, head_aggregation='mean', log_size=None, **kwargs):
+        # the context may come back as split planes when the output projection consumes them directly (fp32 inference);
+        # kept out of the module registry: it is a hint, not a parameter
+        object.__setattr__(self.attention, "_tome_ctx_consumer", getattr(self.output, "dense", None))
         ctx, metric = self.attention(hidden_states, size, head_aggregation, log_size)
         return self.output(ctx, hidden_states), metric
 
@@ -94,7 +97,8 @@ class ToMeVivitSelfAttentionMixin:
                 log_size = size.log()
             ctx, k = prop_attention.attention_f32(hidden_states, self, h, d, d ** -0.5, None if size is None else log_size,
                                                   self.query.weight, self.key.weight, self.value.weight,
-                                                  self.query.bias, self.key.bias, self.value.bias, on_keys=on_keys)
+                                                  self.query.bias, self.key.bias, self.value.bias, on_keys=on_keys,
+                                                  planes_for=getattr(self, "_tome_ctx_consumer", None))
         else:
             q = self.query(hidden_states).view(B, N, h, d).transpose(1, 2)
             k = self.key(hidden_states).view(B, N, h, d).transpose(1, 2)
