@@ -1,5 +1,7 @@
+#!/usr/bin/env python3
+"""tome_linear_f32 output modes at the QKV shape: fp32, planes, both, and a separate tome_split3 of the result."""
 import os, sys
-ROOT = "/root/repo"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "video-how-do-your-tokens-merge_b200")]
 import torch, bench
 from tome import _native
