@@ -525,9 +525,17 @@ def merge_frames(plan: DevicePlan, x: torch.Tensor, frames: int, mode: str, size
     m = _MODES[mode]
     Pn = P - plan.r
     thr = float("nan") if hybrid_threshold is None else float(hybrid_threshold)
+    same_layout = residual is not None and tuple(residual.shape) == tuple(x.shape) and T > 1      # Motionformer: x + attn_out
+    cls_ok = C % (8 if x.dtype == torch.bfloat16 else 4) == 0 and C <= (2048 if x.dtype == torch.bfloat16 else 1024)
     with torch.cuda.device(x.device):
         out = torch.empty(B, 1 + Pn * T, C, dtype=x.dtype, device=x.device)
-        out[:, 0] = x[:, 0] if cls is None else cls
+        cls_src = x[:, 0] if cls is None else cls
+        cls_add = residual[:, 0] if same_layout else None
+        if not (cls_ok and norm is not None):                  # (with a fused LayerNorm the class row is written below, one launch)
+            if cls_ok and cls_src.stride(-1) == 1 and (cls_add is None or cls_add.stride(-1) == 1):
+                cls_rows(cls_src, add=cls_add, sum_out=out[:, 0])
+            else:
+                out[:, 0] = cls_src if cls_add is None else cls_src + cls_add
         size_out = torch.empty(B * T, Pn, dtype=torch.float32, device=x.device)
         logsize_out = torch.empty(B * T, Pn, dtype=torch.float32, device=x.device)
         sp = None
@@ -542,9 +550,17 @@ def merge_frames(plan: DevicePlan, x: torch.Tensor, frames: int, mode: str, size
                                   _stream(x)), lib)
             return out, size_out, logsize_out
         rp, rv = None, None
-        if residual is not None:
+        if same_layout:                                        # residual laid out like x: 'b (1 + p t)'
+            if residual.dtype != x.dtype or residual.device != x.device:
+                raise RuntimeError("tome_b200: merge_frames residual must have x's dtype and device")
+            if residual.stride(2) != 1:
+                residual = residual.contiguous()
+                cls_add = residual[:, 0]
+            rp = residual[:, 1:].data_ptr()
+            rv = ctypes.byref(TomeViewC(residual.stride(0), residual.stride(1), T * residual.stride(1), T))
+        elif residual is not None:
             if tuple(residual.shape) != (B * T, 1 + P, C) or residual.dtype != x.dtype or residual.device != x.device:
-                raise RuntimeError(f"tome_b200: merge_frames residual must be ({B * T}, {1 + P}, {C}) of x's dtype; got {tuple(residual.shape)}")
+                raise RuntimeError(f"tome_b200: merge_frames residual must be ({B * T}, {1 + P}, {C}) or x's shape, of x's dtype; got {tuple(residual.shape)}")
             if residual.stride(2) != 1:
                 residual = residual.contiguous()
             rp = residual[:, 1:].data_ptr()
@@ -554,7 +570,11 @@ def merge_frames(plan: DevicePlan, x: torch.Tensor, frames: int, mode: str, size
         if norm is not None:
             wp, bp, eps = _norm_args(norm, x)
             normed = torch.empty_like(out)
-            normed[:, 0] = torch.nn.functional.layer_norm(out[:, 0], (C,), norm[0], norm[1], eps)     # class token row
+            if cls_ok and cls_src.stride(-1) == 1 and (cls_add is None or cls_add.stride(-1) == 1):
+                cls_rows(cls_src, add=cls_add, sum_out=out[:, 0], norm=norm, normed_out=normed[:, 0:1])     # class token row, one launch
+            else:
+                out[:, 0] = cls_src if cls_add is None else cls_src + cls_add
+                normed[:, 0] = torch.nn.functional.layer_norm(out[:, 0], (C,), norm[0], norm[1], eps)
             nv = ctypes.byref(TomeViewC(normed.stride(0), normed.stride(1), T * normed.stride(1), T))
             npz = normed[:, 1:].data_ptr()
         _check(lib.tome_merge_add_norm_rv(plan.c_ptr(), x[:, 1:].data_ptr(), rp, rv, _dtype_code(x), C, ctypes.byref(xv), sp, m,

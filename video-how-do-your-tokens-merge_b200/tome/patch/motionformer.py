@@ -13,7 +13,7 @@ from tome.merge import (Drop, Merge, bipartite_soft_matching, bipartite_soft_mat
                         bipartite_soft_matching_hybrid, finish_source, trace_source)
 from tome.patch.timesformer import _frames_back, _frames_view, _merge_frames_generic
 from tome import attention as prop_attention
-from tome.patch.videomae import _normed_or, _swap, fusable_norm, lazy_head_mean
+from tome.patch.videomae import _close_block, _norm1_or, _normed_or, _swap, fusable_norm, lazy_head_mean, link_blocks
 from tome.utils import parse_r
 
 
@@ -110,11 +110,12 @@ class ToMeBlockMixin:
         info = self._tome_info
         attn_size = info["size"] if info["prop_attn"] else None
         attn_bias = info.get("log_size") if info["prop_attn"] else None
-        attn_out, _, metric = self.attn(self.norm1(x), seq_len=seq_len, num_frames=num_frames, approx=approx,
+        attn_out, _, metric = self.attn(_norm1_or(self, x, info), seq_len=seq_len, num_frames=num_frames, approx=approx,
                                         num_landmarks=num_landmarks, size=attn_size, log_size=attn_bias)
-        x = x + self.drop_path(attn_out)
-        x = self.reduction_function(metric, x, info, num_frames, norm=self.norm2)
-        return x + self.drop_path(self.mlp(_normed_or(self.norm2, x, info)))
+        # x = x + attn_out is taken inside the merge kernel, x + mlp(...) together with the next block's norm1
+        # (tome_add_layernorm), when they can be (CUDA inference): SURVEY.md 8f-f2
+        x = self.reduction_function(metric, x, info, num_frames, norm=self.norm2, residual=self.drop_path(attn_out))
+        return _close_block(self, x, self.mlp(_normed_or(self.norm2, x, info)), info)
 
 
 class ToMeTrajectoryAttentionMixin:
@@ -140,10 +141,18 @@ class ToMeTrajectoryAttentionMixin:
         return out, None, early["metric"]
 
 
-def motionformer_merge(metric, x, _tome_info, num_frames, norm=None):
-    """motionformer.py:147-170."""
+def _residual_in_kernel(x, residual):
+    return (residual is not None and x.is_cuda and not torch.is_grad_enabled() and residual.shape == x.shape
+            and residual.dtype == x.dtype and x.dtype in (torch.float32, torch.bfloat16))
+
+
+def motionformer_merge(metric, x, _tome_info, num_frames, norm=None, residual=None):
+    """motionformer.py:147-170.  ``residual``: the pending ``x + attn_out`` (motionformer.py:24), added inside the merge kernel
+    when it runs."""
     _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
+    if residual is not None and not (r > 0 and _residual_in_kernel(x, residual)):
+        x, residual = x + residual, None
     if r > 0:
         B, T = x.size(0), num_frames
         P = (x.size(1) - 1) // T
@@ -153,19 +162,23 @@ def motionformer_merge(metric, x, _tome_info, num_frames, norm=None):
             if _tome_info["trace_source"]:
                 _tome_info["source"] = trace_source(merge, None, _tome_info["source"])
             fn = fusable_norm(norm, x) if norm is not None else None
-            res = merge.wavg_frames(x, T, _tome_info["size"], norm=fn)
+            res = merge.wavg_frames(x, T, _tome_info["size"], norm=fn, residual=residual)
             x, _tome_info["size"], _tome_info["log_size"] = res[0], res[1], res[2]
             _tome_info["normed"] = res[3] if fn is not None else None
         else:
+            if residual is not None:
+                x = x + residual
             x = _merge_frames_generic(merge, x, _tome_info, B, T, P)
         if _tome_info['verbose']:
             print(f'Merged {P} to {(x.size(1) - 1) // T} tokens')
     return x
 
 
-def motionformer_drop(metric, x, _tome_info, num_frames, norm=None):
+def motionformer_drop(metric, x, _tome_info, num_frames, norm=None, residual=None):
     """motionformer.py:173-200."""
     _tome_info["normed"] = None
+    if residual is not None:
+        x = x + residual
     r = _tome_info["r"].pop(0)
     if r > 0:
         B, T = x.size(0), num_frames
@@ -188,10 +201,12 @@ def motionformer_drop(metric, x, _tome_info, num_frames, norm=None):
     return x
 
 
-def motionformer_hybrid(metric, x, _tome_info, num_frames, norm=None):
+def motionformer_hybrid(metric, x, _tome_info, num_frames, norm=None, residual=None):
     """motionformer.py:203-227."""
     _tome_info["normed"] = None
     r = _tome_info["r"].pop(0)
+    if residual is not None and not (r > 0 and _residual_in_kernel(x, residual)):
+        x, residual = x + residual, None
     if r > 0:
         B, T = x.size(0), num_frames
         P = (x.size(1) - 1) // T
@@ -201,10 +216,12 @@ def motionformer_hybrid(metric, x, _tome_info, num_frames, norm=None):
             if _tome_info["trace_source"]:
                 _tome_info["source"] = trace_source(merge, None, _tome_info["source"])
             fn = fusable_norm(norm, x) if norm is not None else None
-            res = merge.wavg_frames(x, T, _tome_info["size"], norm=fn)
+            res = merge.wavg_frames(x, T, _tome_info["size"], norm=fn, residual=residual)
             x, _tome_info["size"], _tome_info["log_size"] = res[0], res[1], res[2]
             _tome_info["normed"] = res[3] if fn is not None else None
         else:
+            if residual is not None:
+                x = x + residual
             x = _merge_frames_generic(merge, x, _tome_info, B, T, P)
         if _tome_info['verbose']:
             print(f'Merged {P} to {(x.size(1) - 1) // T} tokens')
@@ -233,6 +250,7 @@ def make_tome_class(transformer_class):
             self._tome_info["log_size"] = None
             self._tome_info["normed"] = None
             self._tome_info["source"] = None
+            link_blocks(self.blocks, self._tome_info)
             out = super().forward(*args, **kwdargs)
             finish_source(self._tome_info)          # compact source map -> the reference's dense matrix, once
             return out
