@@ -96,8 +96,14 @@ class PatchEmbed3D(nn.Module):                          # vit_helper.py:410-432
         if self.training or not x.is_cuda:
             return self.proj(x).flatten(2).transpose(1, 2)
         z, p = self.z, self.patch_size                  # kernel == stride: one GEMM over tubelets
-        x = x.reshape(B, C, T // z, z, H // p, p, W // p, p).permute(0, 2, 4, 6, 1, 3, 5, 7)
-        x = x.reshape(B, (T // z) * (H // p) * (W // p), C * z * p * p)
+        wdt = self.proj.weight.dtype
+        if (not torch.is_grad_enabled() and p % 8 == 0 and x.dtype in (torch.float32, torch.bfloat16, torch.uint8)
+                and wdt in (torch.float32, torch.bfloat16)):
+            from tome import _native                    # one coalesced pass instead of torch's generic 8-d strided copy
+            x = _native.patchify(x, z, p, p, wdt)
+        else:
+            x = x.reshape(B, C, T // z, z, H // p, p, W // p, p).permute(0, 2, 4, 6, 1, 3, 5, 7)
+            x = x.reshape(B, (T // z) * (H // p) * (W // p), C * z * p * p)
         return fastlinear.linear(x, self.proj.weight.reshape(self.proj.out_channels, -1), self.proj.bias)
 
 
