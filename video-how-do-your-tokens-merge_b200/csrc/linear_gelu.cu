@@ -170,13 +170,16 @@ linear_gelu_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float x0 = v[g4 * 8 + 2 * i] + bf[2 * i], x1 = v[g4 * 8 + 2 * i + 1] + bf[2 * i + 1];
-            if (p.gelu == 1) {
-              // round to bf16 first: the value F.linear would have stored and nn.GELU would have read
-              x0 = gelu_erf(__bfloat162float(__float2bfloat16_rn(x0)));
-              x1 = gelu_erf(__bfloat162float(__float2bfloat16_rn(x1)));
-            } else if (p.gelu == 2) {
-              x0 = gelu_tanh_fast(__bfloat162float(__float2bfloat16_rn(x0)));
-              x1 = gelu_tanh_fast(__bfloat162float(__float2bfloat16_rn(x1)));
+            if (p.gelu) {
+              // round to bf16 first: the value F.linear would have stored and the activation would have read.  The packed
+              // conversion is an ALU instruction and a bf16 is the upper half of its fp32; the single-value conversion goes
+              // through the XU pipe (16 / clk / SM), which the activation's MUFU.RCP / EX2 already keep half busy
+              const __nv_bfloat162 r2 = __floats2bfloat162_rn(x0, x1);
+              const uint32_t rw = *reinterpret_cast<const uint32_t*>(&r2);
+              x0 = __uint_as_float(rw << 16);
+              x1 = __uint_as_float(rw & 0xFFFF0000u);
+              if (p.gelu == 1) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); }
+              else { x0 = gelu_tanh_fast(x0); x1 = gelu_tanh_fast(x1); }
             }
             const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
             w[i] = *reinterpret_cast<const uint32_t*>(&h);
