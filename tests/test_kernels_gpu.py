@@ -1252,6 +1252,22 @@ def test_linear_f32_matches_fp64(native, shape, terms):
         torch.testing.assert_close(native.linear_f32(x, w, b, gelu="gelu_fast", terms=terms), gelu_fast(out), rtol=2e-6, atol=2e-6)
 
 
+def test_planes_round_trip_is_exact(native):
+    """tome_split3 -> tome_planes_sum returns the fp32 tensor bit for bit (h + m + l == x), on a column slice too; the planes
+    output of tome_linear_f32 sums to its fp32 output."""
+    g = torch.Generator().manual_seed(21)
+    x = (torch.randn(515, 2304, generator=g) * torch.logspace(-6, 6, 2304)).cuda()
+    p3 = native.Planes(native.split3(x), (515, 2304))
+    assert torch.equal(native.planes_to_f32(p3), x)
+    assert torch.equal(native.planes_to_f32(p3, 768, 768), x[:, 768:1536])
+    w = (torch.randn(768, 2304, generator=g) * 0.02).cuda()
+    with torch.no_grad():
+        y, y3 = native.linear_f32(p3, w, None, out="both")
+    assert torch.equal(native.planes_to_f32(y3), y)
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        native.planes_to_f32(p3, 4, 768)
+
+
 @pytest.mark.parametrize("shape", [(1000, 768, 768), (2100, 3072, 768), (777, 768, 3072)], ids=str)
 def test_linear_f32_eight_products_equal_nine_at_fp32_resolution(native, shape):
     """The default drops ONE of the nine plane products, l.l (<= 2^-32 of |a||b| per product: 2^-8 of the fp32 accumulator's own
