@@ -114,8 +114,14 @@ class PatchEmbed(nn.Module):                            # timesformer.py:155-175
         B, C, T, H, W = x.shape
         ph, pw = self.patch_size
         if x.is_cuda and not self.training:             # kernel == stride: one GEMM over patches
-            x = x.permute(0, 2, 1, 3, 4).reshape(B * T, C, H // ph, ph, W // pw, pw).permute(0, 2, 4, 1, 3, 5)
-            x = x.reshape(B * T, (H // ph) * (W // pw), C * ph * pw)
+            wdt = self.proj.weight.dtype
+            if (not torch.is_grad_enabled() and pw % 8 == 0 and x.dtype in (torch.float32, torch.bfloat16, torch.uint8)
+                    and wdt in (torch.float32, torch.bfloat16) and x.is_contiguous()):
+                from tome import _native                # one coalesced pass (a tubelet of one frame) instead of two strided copies
+                x = _native.patchify(x, 1, ph, pw, wdt).view(B * T, (H // ph) * (W // pw), C * ph * pw)
+            else:
+                x = x.permute(0, 2, 1, 3, 4).reshape(B * T, C, H // ph, ph, W // pw, pw).permute(0, 2, 4, 1, 3, 5)
+                x = x.reshape(B * T, (H // ph) * (W // pw), C * ph * pw)
             return fastlinear.linear(x, self.proj.weight.reshape(self.proj.out_channels, -1), self.proj.bias), T, W // pw
         x = self.proj(x.permute(0, 2, 1, 3, 4).reshape(B * T, C, H, W))
         Wp = x.size(-1)
@@ -168,6 +174,13 @@ class VisionTransformer(nn.Module):                     # timesformer.py:178-321
     def forward_features(self, x):
         B = x.shape[0]
         x, T, W = self.patch_embed(x)                    # (B*T, P, C)
+        if (self.attention_type == 'divided_space_time' and x.is_cuda and not self.training and not torch.is_grad_enabled()
+                and x.dtype in (torch.float32, torch.bfloat16) and x.size(2) % 8 == 0 and x.is_contiguous()
+                and self.pos_embed.size(1) == x.size(1) + 1 and self.time_embed.size(1) == T):
+            x = self._embed_fused(x, B, T)
+            for blk in self.blocks:
+                x = blk(x, B, T, W)
+            return self.norm(x)[:, 0]
         x = torch.cat((self.cls_token.expand(x.size(0), -1, -1), x), dim=1) + self.pos_embed
         x = self.pos_drop(x)
         if self.attention_type != 'space_only':
@@ -181,6 +194,26 @@ class VisionTransformer(nn.Module):                     # timesformer.py:178-321
         if self.attention_type == 'space_only':
             x = x.reshape(B, T, x.size(1), x.size(2)).mean(1)
         return self.norm(x)[:, 0]
+
+    def _embed_fused(self, x, B, T):
+        """cat(cls, x) + pos_embed, '(b t) n m -> b (n t) m', + time_embed, cat(cls, ...) (timesformer.py:287-318 of the reference
+        model) as ONE pass over the patch-embedding GEMM's output: out[b, 1 + p T + t] = x[(b t), p] + (pos[1 + p] + time[t])
+        through (b, p, t) row views (tome_rows_add_layernorm), out[b, 0] = cls + pos[0].  Inference only (both dropouts are
+        identities); the two embedding tables are summed once and cached."""
+        from tome import _native
+        P, C = x.size(1), x.size(2)
+        key = (self.pos_embed._version, self.time_embed._version, self.cls_token._version, x.dtype, x.device, T)
+        cached = self.__dict__.get("_tome_embed_sum")
+        if cached is None or cached[0] != key:
+            pos, tim = self.pos_embed.detach().to(x.dtype), self.time_embed.detach().to(x.dtype)
+            emb = (pos[0, 1:, None, :] + tim[0, None, :, :]).contiguous()                  # (P, T, C)
+            cls_row = (self.cls_token.detach().to(x.dtype)[0, 0] + pos[0, 0]).contiguous()    # (C,)
+            cached = self.__dict__["_tome_embed_sum"] = (key, emb, cls_row)
+        out = torch.empty(B, 1 + P * T, C, dtype=x.dtype, device=x.device)
+        _native.rows_add_layernorm(x.view(B, T, P, C).permute(0, 2, 1, 3), cached[1].unsqueeze(0).expand(B, P, T, C), None,
+                                   out[:, 1:].unflatten(1, (P, T)), None)
+        out[:, 0] = cached[2]
+        return out
 
     def forward(self, x):
         return self.head(self.forward_features(x[0]))
