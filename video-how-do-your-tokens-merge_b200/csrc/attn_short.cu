@@ -49,71 +49,99 @@ template <> struct Ld8<float> {
 };
 
 // q / k / v element (s, t, h, c) at base + s * ss + t * st + h * D + c; out (s, t, h, c) contiguous.
-template <typename T, int D>
+// FOUR threads per (sequence, head, query), 16 channels each (adjacent lanes: a quad reads one 128-byte head row per key,
+// partial dot products meet in two shuffles).  With one thread per query the 64-channel q and accumulator rows cost ~150
+// registers, twelve warps per SM were resident and the 77 MB streaming pass ran at a third of the HBM rate (35 us).
+template <typename T, int D, int MAXT>                    // MAXT: 8 (TimeSformer's frames: every loop unrolled, scores indexed statically) or AS_MAX_T
 __global__ void __launch_bounds__(128) attn_short_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
                                                          long long ss, long long st, long long seqs, int heads, int tn, float scale,
                                                          T* __restrict__ out) {
+  constexpr int DP = D / 4;                              // channels per thread
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = seqs * heads * tn;
-  if (gid >= total) return;
-  const int i = (int)(gid % tn);
-  const long long sh = gid / tn;
+  const int part = (int)(gid & 3);
+  const bool valid = (gid >> 2) < total;
+  const long long quad = valid ? (gid >> 2) : total - 1;   // idle quads of the last warp recompute the last row (shuffles stay full-mask)
+  const int i = (int)(quad % tn);
+  const long long sh = quad / tn;
   const int h = (int)(sh % heads);
   const long long s = sh / heads;
-  const long long base = s * ss + (long long)h * D;
-  float qr[D];
+  const long long base = s * ss + (long long)h * D + part * DP;
+  float qr[DP];
 #pragma unroll
-  for (int c = 0; c < D; c += 8) {
+  for (int c = 0; c < DP; c += 8) {
     float f[8];
     Ld8<T>::load(q + base + (long long)i * st + c, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) qr[c + e] = f[e] * scale;
   }
-  float sc[AS_MAX_T];
+  float sc[MAXT];
   float m = -INFINITY;
-#pragma unroll 1
-  for (int j = 0; j < tn; ++j) {
+  auto score = [&](int j) {                                // q . k_j over this thread's channels, summed over the quad
     const T* kr = k + base + (long long)j * st;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-    for (int c = 0; c < D; c += 8) {
+    for (int c = 0; c < DP; c += 8) {
       float f[8];
       Ld8<T>::load(kr + c, f);
       a0 = fmaf(qr[c], f[0], a0); a1 = fmaf(qr[c + 1], f[1], a1); a2 = fmaf(qr[c + 2], f[2], a2); a3 = fmaf(qr[c + 3], f[3], a3);
       a0 = fmaf(qr[c + 4], f[4], a0); a1 = fmaf(qr[c + 5], f[5], a1); a2 = fmaf(qr[c + 6], f[6], a2); a3 = fmaf(qr[c + 7], f[7], a3);
     }
-    const float d = (a0 + a1) + (a2 + a3);
+    float d = (a0 + a1) + (a2 + a3);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);               // the quad's four partial sums: every lane ends with the same total
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    return d;
+  };
+  if constexpr (MAXT <= 8) {
 #pragma unroll
-    for (int u = 0; u < AS_MAX_T; ++u) if (u == j) sc[u] = d;      // static indexing keeps sc[] in registers
-    m = fmaxf(m, d);
+    for (int j = 0; j < MAXT; ++j) {                       // tn is warp-uniform: the shuffles stay converged
+      sc[j] = j < tn ? score(j) : -INFINITY;
+      m = fmaxf(m, sc[j]);
+    }
+  } else {
+#pragma unroll 1
+    for (int j = 0; j < tn; ++j) {
+      const float d = score(j);
+#pragma unroll
+      for (int u = 0; u < MAXT; ++u) if (u == j) sc[u] = d;      // static indexing keeps sc[] in registers
+      m = fmaxf(m, d);
+    }
   }
   float l = 0.f;
 #pragma unroll
-  for (int u = 0; u < AS_MAX_T; ++u) {
+  for (int u = 0; u < MAXT; ++u) {
     if (u < tn) { sc[u] = sizeof(T) == 4 ? expf(sc[u] - m) : __expf(sc[u] - m); l += sc[u]; }
   }
   const float inv = 1.0f / l;
-  float acc[D];
+  float acc[DP];
 #pragma unroll
-  for (int c = 0; c < D; ++c) acc[c] = 0.f;
-#pragma unroll 1
-  for (int j = 0; j < tn; ++j) {
-    float p = 0.f;
-#pragma unroll
-    for (int u = 0; u < AS_MAX_T; ++u) if (u == j) p = sc[u];
-    p *= inv;
+  for (int c = 0; c < DP; ++c) acc[c] = 0.f;
+  auto accumulate = [&](int j, float p) {
     const T* vr = v + base + (long long)j * st;
 #pragma unroll
-    for (int c = 0; c < D; c += 8) {
+    for (int c = 0; c < DP; c += 8) {
       float f[8];
       Ld8<T>::load(vr + c, f);
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[c + e] = fmaf(p, f[e], acc[c + e]);
     }
-  }
-  T* orow = out + ((s * tn + i) * heads + h) * D;
+  };
+  if constexpr (MAXT <= 8) {
 #pragma unroll
-  for (int c = 0; c < D; c += 8) {
+    for (int j = 0; j < MAXT; ++j) if (j < tn) accumulate(j, sc[j] * inv);
+  } else {
+#pragma unroll 1
+    for (int j = 0; j < tn; ++j) {
+      float p = 0.f;
+#pragma unroll
+      for (int u = 0; u < MAXT; ++u) if (u == j) p = sc[u];
+      accumulate(j, p * inv);
+    }
+  }
+  if (!valid) return;
+  T* orow = out + ((s * tn + i) * heads + h) * D + part * DP;
+#pragma unroll
+  for (int c = 0; c < DP; c += 8) {
     float f[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) f[e] = acc[c + e];
@@ -128,16 +156,13 @@ int launch_attn_short(const void* q, const void* k, const void* v, int dtype, lo
   const int e = dtype == TOME_F32 ? 4 : 8;     // 16-byte loads
   if (((uintptr_t)q & 15) || ((uintptr_t)k & 15) || ((uintptr_t)v & 15) || ((uintptr_t)out & 15) || ss % e || st % e)
     return set_error(TOME_ERR_ALIGN, "tome_attn_short: q / k / v / out must be 16-byte aligned with 16-byte aligned strides");
-  const long long total = seqs * heads * tn;
+  const long long total = seqs * heads * tn * 4;         // four threads per (sequence, head, query)
   const unsigned grid = (unsigned)((total + 127) / 128);
-  if (dtype == TOME_BF16)
-    attn_short_kernel<__nv_bfloat16, 64><<<grid, 128, 0, stm>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
-                                                                 ss, st, seqs, heads, tn, scale, (__nv_bfloat16*)out);
-  else if (dtype == TOME_F32)
-    attn_short_kernel<float, 64><<<grid, 128, 0, stm>>>((const float*)q, (const float*)k, (const float*)v, ss, st, seqs, heads, tn, scale,
-                                                         (float*)out);
-  else
-    return set_error(TOME_ERR_DTYPE, "tome_attn_short: unsupported dtype %d", dtype);
+#define TOME_AS(T_, M_) attn_short_kernel<T_, 64, M_><<<grid, 128, 0, stm>>>((const T_*)q, (const T_*)k, (const T_*)v, ss, st, seqs, heads, tn, scale, (T_*)out)
+  if (dtype == TOME_BF16) { if (tn <= 8) TOME_AS(__nv_bfloat16, 8); else TOME_AS(__nv_bfloat16, AS_MAX_T); }
+  else if (dtype == TOME_F32) { if (tn <= 8) TOME_AS(float, 8); else TOME_AS(float, AS_MAX_T); }
+  else return set_error(TOME_ERR_DTYPE, "tome_attn_short: unsupported dtype %d", dtype);
+#undef TOME_AS
   TOME_LAUNCH_CHECK("attn_short_kernel");
   return TOME_OK;
 }
