@@ -324,30 +324,36 @@ __device__ __forceinline__ void tt_store8(float* p, const float (&f)[8]) {
   reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
 }
 
-template <typename T>
+// FOUR threads per (token, head), 16 channels each (adjacent lanes: a quad reads one 128-byte head row per frame, partial dot
+// products meet in two shuffles); MAXF = 8: loops unrolled, scores indexed statically.  (One thread per (token, head) with 64-
+// channel q / accumulator rows and a 32-way select per frame to keep the scores in registers was 12 % of the bf16 Motionformer
+// step; the same change took tome_attn_short from 35 us to a fraction.)
+template <typename T, int MAXF>
 __global__ void __launch_bounds__(128) traj_temporal_kernel(const T* __restrict__ q2, const T* __restrict__ k2, const T* __restrict__ vals,
                                                            long long rows, int F, int heads, float scale, T* __restrict__ out) {
+  constexpr int DP = FA_D / 4;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= rows * heads) return;
-  const int h = (int)(gid % heads);
-  const long long r = gid / heads;
+  const long long total = rows * heads;
+  const int part = (int)(gid & 3);
+  const bool valid = (gid >> 2) < total;
+  const long long quad = valid ? (gid >> 2) : total - 1;   // idle quads of the last warp recompute the last row (full-mask shuffles)
+  const int h = (int)(quad % heads);
+  const long long r = quad / heads;
   const int C = heads * FA_D;
-  float q[FA_D];
+  const int off = h * FA_D + part * DP;
+  float q[DP];
 #pragma unroll
-  for (int c = 0; c < FA_D / 8; ++c) {
+  for (int c = 0; c < DP / 8; ++c) {
     float v[8];
-    tt_load8(q2 + r * C + h * FA_D + 8 * c, v);
+    tt_load8(q2 + r * C + off + 8 * c, v);
 #pragma unroll
     for (int i = 0; i < 8; ++i) q[8 * c + i] = v[i] * scale;
   }
-  float sc[32];
-  float m = -INFINITY;
-#pragma unroll 1
-  for (int f = 0; f < F; ++f) {
-    const T* kp = k2 + (r * F + f) * C + h * FA_D;
+  auto score = [&](int f) {
+    const T* kp = k2 + (r * F + f) * C + off;
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-    for (int c = 0; c < FA_D / 8; ++c) {
+    for (int c = 0; c < DP / 8; ++c) {
       float v[8];
       tt_load8(kp + 8 * c, v);
 #pragma unroll
@@ -356,35 +362,60 @@ __global__ void __launch_bounds__(128) traj_temporal_kernel(const T* __restrict_
         a1 = fmaf(q[8 * c + i + 1], v[i + 1], a1);
       }
     }
-    const float d = a0 + a1;
+    float d = a0 + a1;
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    return d;
+  };
+  float sc[MAXF];
+  float m = -INFINITY;
+  if constexpr (MAXF <= 8) {
 #pragma unroll
-    for (int u = 0; u < 32; ++u) if (u == f) sc[u] = d;
-    m = fmaxf(m, d);
+    for (int f = 0; f < MAXF; ++f) {                        // F is uniform: the shuffles stay converged
+      sc[f] = f < F ? score(f) : -INFINITY;
+      m = fmaxf(m, sc[f]);
+    }
+  } else {
+#pragma unroll 1
+    for (int f = 0; f < F; ++f) {
+      const float d = score(f);
+#pragma unroll
+      for (int u = 0; u < MAXF; ++u) if (u == f) sc[u] = d;
+      m = fmaxf(m, d);
+    }
   }
   float l = 0.f;
 #pragma unroll
-  for (int u = 0; u < 32; ++u) if (u < F) { sc[u] = __expf(sc[u] - m); l += sc[u]; }
+  for (int u = 0; u < MAXF; ++u) if (u < F) { sc[u] = __expf(sc[u] - m); l += sc[u]; }
   const float inv = 1.0f / l;
-  float acc[FA_D];
+  float acc[DP];
 #pragma unroll
-  for (int c = 0; c < FA_D; ++c) acc[c] = 0.f;
-#pragma unroll 1
-  for (int f = 0; f < F; ++f) {
-    float pw = 0.f;
+  for (int c = 0; c < DP; ++c) acc[c] = 0.f;
+  auto accumulate = [&](int f, float pw) {
+    const T* vp = vals + (r * F + f) * C + off;
 #pragma unroll
-    for (int u = 0; u < 32; ++u) if (u == f) pw = sc[u];
-    pw *= inv;
-    const T* vp = vals + (r * F + f) * C + h * FA_D;
-#pragma unroll
-    for (int c = 0; c < FA_D / 8; ++c) {
+    for (int c = 0; c < DP / 8; ++c) {
       float v[8];
       tt_load8(vp + 8 * c, v);
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[8 * c + i] = fmaf(pw, v[i], acc[8 * c + i]);
     }
-  }
+  };
+  if constexpr (MAXF <= 8) {
 #pragma unroll
-  for (int c = 0; c < FA_D / 8; ++c) tt_store8(out + r * C + h * FA_D + 8 * c, reinterpret_cast<const float(&)[8]>(acc[8 * c]));
+    for (int f = 0; f < MAXF; ++f) if (f < F) accumulate(f, sc[f] * inv);
+  } else {
+#pragma unroll 1
+    for (int f = 0; f < F; ++f) {
+      float pw = 0.f;
+#pragma unroll
+      for (int u = 0; u < MAXF; ++u) if (u == f) pw = sc[u];
+      accumulate(f, pw * inv);
+    }
+  }
+  if (!valid) return;
+#pragma unroll
+  for (int c = 0; c < DP / 8; ++c) tt_store8(out + r * C + off + 8 * c, reinterpret_cast<const float(&)[8]>(acc[8 * c]));
 }
 
 // ---- host -------------------------------------------------------------------------------------------------------
@@ -420,14 +451,13 @@ int launch_traj_temporal(const void* q2, const void* k2, const void* vals, int d
   if (F < 1 || F > 32) return set_error(TOME_ERR_UNSUPPORTED, "tome_traj_temporal: %d frames (1..32)", F);
   if (((uintptr_t)q2 & 15) || ((uintptr_t)k2 & 15) || ((uintptr_t)vals & 15) || ((uintptr_t)out & 15))
     return set_error(TOME_ERR_ALIGN, "tome_traj_temporal: buffers must be 16-byte aligned");
-  const long long total = rows * heads;
+  const long long total = rows * heads * 4;              // four threads per (token, head)
   const unsigned grid = (unsigned)((total + 127) / 128);
-  if (dtype == TOME_BF16)
-    traj_temporal_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q2, (const __nv_bfloat16*)k2, (const __nv_bfloat16*)vals,
-                                                               rows, F, heads, scale, (__nv_bfloat16*)out);
-  else if (dtype == TOME_F32)
-    traj_temporal_kernel<float><<<grid, 128, 0, st>>>((const float*)q2, (const float*)k2, (const float*)vals, rows, F, heads, scale, (float*)out);
+#define TOME_TT(T_, M_) traj_temporal_kernel<T_, M_><<<grid, 128, 0, st>>>((const T_*)q2, (const T_*)k2, (const T_*)vals, rows, F, heads, scale, (T_*)out)
+  if (dtype == TOME_BF16) { if (F <= 8) TOME_TT(__nv_bfloat16, 8); else TOME_TT(__nv_bfloat16, 32); }
+  else if (dtype == TOME_F32) { if (F <= 8) TOME_TT(float, 8); else TOME_TT(float, 32); }
   else return set_error(TOME_ERR_DTYPE, "tome_traj_temporal: unsupported dtype %d", dtype);
+#undef TOME_TT
   TOME_LAUNCH_CHECK("traj_temporal_kernel");
   return TOME_OK;
 }
