@@ -18,7 +18,7 @@ from tome.merge import (Merge, bipartite_soft_matching, bipartite_soft_matching_
                         bipartite_soft_matching_hybrid, finish_source, merge_source, merge_wavg,
                         trace_source)
 from tome import attention as prop_attention
-from tome.patch.videomae import _fusable_residual, _normed_or, _swap, _wavg, lazy_head_mean
+from tome.patch.videomae import _fusable_residual, _normed_or, _swap, _wavg, fusable_norm, lazy_head_mean
 from tome.utils import parse_r
 
 
@@ -39,13 +39,32 @@ class ToMeVivitLayerMixin:
         info = self._tome_info
         attn_size = info["size"] if info["prop_attn"] else None
         attn_bias = info.get("log_size") if info["prop_attn"] else None
-        attention_output, metric = self.attention(self.layernorm_before(hidden_states), attn_size,
-                                                  info["head_aggregation"], attn_bias)
+        pre = info.pop("normed1", None)          # layernorm_before(hidden_states), made by the previous layer's closing add
+        normed = (pre[2] if pre is not None and pre[0] is hidden_states and pre[1] is self.layernorm_before
+                  else self.layernorm_before(hidden_states))
+        attention_output, metric = self.attention(normed, attn_size, info["head_aggregation"], attn_bias)
         # first residual (attention_output + hidden_states), taken inside the merge kernel when it can be
         hidden_states = self.reduction_function(metric, hidden_states, info, norm=self.layernorm_after,
                                                 residual=attention_output)
-        layer_output = self.output(self.intermediate(_normed_or(self.layernorm_after, hidden_states, info)), hidden_states)
+        h = self.intermediate(_normed_or(self.layernorm_after, hidden_states, info))
+        layer_output = self._close(h, hidden_states, info)
         return (layer_output,) if self._tome_tuple_api else layer_output
+
+    def _close(self, h, hidden_states, info):
+        """output.dense(h) + hidden_states (vivit.py:44-45); on the CUDA inference path the add and the NEXT layer's
+        layernorm_before are one pass (tome_add_layernorm), parked in info["normed1"]."""
+        nxt = (info.get("next_norm1") or {}).get(id(self))
+        fn = fusable_norm(nxt, hidden_states) if nxt is not None else None
+        dense = getattr(self.output, "dense", None)
+        if fn is None or dense is None or self.training or not hidden_states.is_contiguous():
+            return self.output(h, hidden_states)
+        y = dense(h)                                  # (the module's dropout is the identity in eval)
+        if y.shape != hidden_states.shape or y.dtype != hidden_states.dtype:
+            return y + hidden_states
+        from tome import _native
+        s, normed = _native.add_layernorm(hidden_states, y, fn)
+        info["normed1"] = (s, nxt, normed)
+        return s
 
 
 class ToMeDuplicateVivitLayerMixin:
@@ -232,6 +251,11 @@ def make_tome_class(transformer_class):
             self._tome_info["log_size"] = None
             self._tome_info["normed"] = None
             self._tome_info["source"] = None
+            layers, chain, seen = list(self.vivit.encoder.layer), {}, set()
+            for cur, nxt in zip(layers[:-1], layers[1:]):          # layer -> the LayerNorm the following layer opens with
+                chain[id(cur)] = None if id(cur) in seen else getattr(nxt, "layernorm_before", None)
+                seen.add(id(cur))
+            self._tome_info["next_norm1"], self._tome_info["normed1"] = chain, None
             out = super().forward(*args, **kwdargs)
             finish_source(self._tome_info)          # compact source map -> the reference's dense matrix, once
             return out
