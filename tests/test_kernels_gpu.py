@@ -1166,6 +1166,22 @@ def test_frames_attention_f32_matches_per_frame_softmax(native, P, with_bias):
     assert torch.equal(xs3.float(), xs)                                               # h + m + l == xs, bit for bit
 
 
+def test_frames_attention_f32_with_one_frame_is_plain_attention(native):
+    """Plain attention is the one-frame, no-lead case of the frames kernel (same template, FRAMES = false vs true paths): the
+    two entry points must agree bit for bit, with and without the key bias."""
+    g = torch.Generator().manual_seed(77)
+    B, h, d, N = 2, 3, 64, 333
+    qkv = torch.randn(B, N, 3 * h * d, generator=g).cuda()
+    bias = torch.rand(B, N, generator=g).cuda()
+    with torch.no_grad():
+        for kb in (None, bias):
+            want = native.attention_f32(qkv, h, d ** -0.5, kb)
+            xs, xs3, diag = native.frames_attention_f32(qkv, h, 1, d ** -0.5, kb, lead=0)
+            assert torch.equal(xs.view(B, N, h * d), want)
+            assert torch.equal(diag, want)                    # every query's own frame is frame 0
+            assert torch.equal(xs3.float().view(B, N, h * d), want)
+
+
 def test_traj_temporal_fp32_matches_einsum_formulation(native):
     """fp32 tome_traj_temporal against vit_helper.py:232-243 in fp64."""
     g = torch.Generator().manual_seed(4)
