@@ -92,7 +92,7 @@ __device__ __forceinline__ uint64_t make_sw64_desc(uint32_t smem_addr) {
 __global__ void __launch_bounds__(LF_THREADS, 1)
 linear_f32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const LinearF32Params p) {
   extern __shared__ uint8_t smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + LF_STAGES * LF_STAGE_BYTES;
   const uint32_t bar_full = bars, bar_empty = bars + 8u * LF_STAGES;
@@ -116,14 +116,19 @@ linear_f32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // Producer and MMA warps run converged with one elected lane issuing ("Issuing tcgen05.mma"): under
+  // `if (lane == 0)` every TMA / tcgen05.mma issue sits in an ELECT / vote loop of ~70 cycles plus a descriptor built in
+  // ordinary registers -- 16 MMAs a stage came to ~1600 of the stage's 2048 tensor cycles, close enough for every barrier poll to
+  // open a gap in the tensor pipe.
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
-        const int mt = t / p.tiles_n, nt = t - mt * p.tiles_n;
-        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-          const uint32_t s = it % LF_STAGES, ph = (it / LF_STAGES) & 1u;
-          mbar_wait_sleep(bar_empty + 8u * s, ph ^ 1u, 64);
+    const bool leader = elect_one_sync();
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      const int mt = t / p.tiles_n, nt = t - mt * p.tiles_n;
+      for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+        const uint32_t s = it % LF_STAGES, ph = (it / LF_STAGES) & 1u;
+        mbar_wait_sleep(bar_empty + 8u * s, ph ^ 1u, 64);
+        if (leader) {
           const uint32_t st = base + s * LF_STAGE_BYTES, full = bar_full + 8u * s;
           mbar_expect_tx(full, LF_STAGE_BYTES);
 #pragma unroll
@@ -132,24 +137,30 @@ linear_f32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             tma_load_2d(st + 3u * LF_A_BYTES + pl * LF_B_BYTES, &map_w, pl * p.k + kb * LF_BK, nt * LF_BN, full);
           }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LF_BN >> 3) << 17) | ((uint32_t)(LF_BM >> 4) << 24);
-      uint32_t it = 0, cl = 0;                                   // k-block and chunk counters across tiles
-      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
-        for (int kb0 = 0; kb0 < p.num_kb; kb0 += LF_CHUNK_KB, ++cl) {
-          const uint32_t acc = cl & 1u, aph = (cl >> 1) & 1u;
-          mbar_wait_sleep(bar_tempty + 8u * acc, aph ^ 1u, 64);   // the epilogue has pulled the previous chunk out of this buffer
+    const bool leader = elect_one_sync();
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LF_BN >> 3) << 17) | ((uint32_t)(LF_BM >> 4) << 24);
+    const uint64_t da0 = make_sw64_desc(base), db0 = make_sw64_desc(base + 3u * LF_A_BYTES);   // stage 0, plane h; planes / stages
+    constexpr uint64_t PA = LF_A_BYTES >> 4, PB = LF_B_BYTES >> 4, ST = LF_STAGE_BYTES >> 4;  // further are constants in the address field
+    const int terms = p.terms;
+    uint32_t it = 0, cl = 0;                                   // k-block and chunk counters across tiles
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      for (int kb0 = 0; kb0 < p.num_kb; kb0 += LF_CHUNK_KB, ++cl) {
+        const uint32_t acc = cl & 1u, aph = (cl >> 1) & 1u;
+        mbar_wait_sleep(bar_tempty + 8u * acc, aph ^ 1u, 64);   // the epilogue has pulled the previous chunk out of this buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tb + acc * (uint32_t)LF_BN;
+        const int kb1 = min(p.num_kb, kb0 + LF_CHUNK_KB);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const uint32_t s = it % LF_STAGES, ph = (it / LF_STAGES) & 1u;
+          mbar_wait_sleep(bar_full + 8u * s, ph, 20);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * (uint32_t)LF_BN;
-          const int kb1 = min(p.num_kb, kb0 + LF_CHUNK_KB);
-          for (int kb = kb0; kb < kb1; ++kb, ++it) {
-            const uint32_t s = it % LF_STAGES, ph = (it / LF_STAGES) & 1u;
-            mbar_wait_sleep(bar_full + 8u * s, ph, 20);
-            tc_fence_after();
-            const uint32_t st = base + s * LF_STAGE_BYTES;
+          if (leader) {
+            const uint64_t da = da0 + (uint64_t)s * ST, db = db0 + (uint64_t)s * ST;
             uint32_t first = kb == kb0 ? 1u : 0u;
 #pragma unroll
             for (int k = 0; k < LF_BK / 16; ++k) {
@@ -159,17 +170,18 @@ linear_f32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               for (int i = 2; i >= 0; --i) {
 #pragma unroll
                 for (int j = 2; j >= 0; --j) {
-                  if ((p.terms == 6 && i + j >= 3) || (p.terms == 8 && i + j == 4)) continue;   // 6: m.l, l.m, l.l; 8: l.l
-                  umma_bf16(d_tmem, make_sw64_desc(st + i * LF_A_BYTES) + adv,
-                            make_sw64_desc(st + 3u * LF_A_BYTES + j * LF_B_BYTES) + adv, idesc, first ? 0u : 1u);
+                  if ((terms == 6 && i + j >= 3) || (terms == 8 && i + j == 4)) continue;   // 6: m.l, l.m, l.l; 8: l.l
+                  umma_bf16(d_tmem, da + (uint64_t)i * PA + adv, db + (uint64_t)j * PB + adv, idesc, first ? 0u : 1u);
                   first = 0u;
                 }
               }
             }
             umma_commit(bar_empty + 8u * s);
           }
-          umma_commit(bar_tfull + 8u * acc);
+          __syncwarp();
         }
+        if (leader) umma_commit(bar_tfull + 8u * acc);
+        __syncwarp();
       }
     }
   } else {
